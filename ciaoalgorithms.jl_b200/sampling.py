@@ -1,0 +1,123 @@
+"""Host-side index selection — the RNG call sites of the reference stay on the host.
+
+The engine takes index sequences as INPUTS at the C ABI (1-based int64, as
+Julia produces them), so the sample path is whatever the host RNG draws:
+  * the Julia shim (julia/CIAOAlgorithmsCUDA.jl) calls the reference's own
+    ``rand`` / ``StatsBase.sample`` / ``randperm`` in the reference's order, so
+    its index stream is the reference's bit for bit;
+  * this Python mirror draws from ``numpy.random.Generator`` through the same
+    call structure (one call per reference call site).
+
+Reference call sites:
+  rand(state.ind, state.m)              SVRG_basic.jl:73
+  rand(1:iter.N)                        SAGA_basic.jl:55
+  sample(1:N, batch, replace=false)     Finito_basic.jl:97, ProShI_basic.jl:98
+  randperm(d)                           Finito_basic.jl:102, Finito_LFinito.jl:89, ProShI_basic.jl:103
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class HostRNG:
+    """The four draws the reference makes, 1-based like Julia."""
+
+    def __init__(self, seed=0):
+        self.g = np.random.default_rng(seed)
+
+    def rand_range(self, N: int) -> int:                       # rand(1:N)
+        return int(self.g.integers(1, N + 1))
+
+    def rand_vec(self, N: int, m: int) -> np.ndarray:          # rand(collect(1:N), m)
+        return self.g.integers(1, N + 1, size=m, dtype=np.int64)
+
+    def sample_norep(self, N: int, k: int) -> np.ndarray:      # sample(1:N, k, replace=false)
+        return (self.g.choice(N, size=k, replace=False) + 1).astype(np.int64)
+
+    def randperm(self, n: int) -> np.ndarray:                  # randperm(n)
+        return (self.g.permutation(n) + 1).astype(np.int64)
+
+
+def static_batches(N: int, r: int):
+    """Finito_basic.jl:52-57 / Finito_LFinito.jl:44-49 / ProShI_basic.jl:52-57:
+    batch j (1-based) = r(j−1)+1 .. jr, plus one remainder batch."""
+    nb_full = N // r
+    out = [np.arange(r * j + 1, r * (j + 1) + 1, dtype=np.int64) for j in range(nb_full)]
+    if r * nb_full < N:
+        out.append(np.arange(r * nb_full + 1, N + 1, dtype=np.int64))
+    return out
+
+
+def n_batches(N: int, r: int) -> int:
+    return -(-N // r)  # cld(N, r)   Finito_basic.jl:59
+
+
+class BatchSweeper:
+    """Index selection of Finito_basic.jl:96-108 and ProShI_basic.jl:97-109.
+
+    sweeping 1: a fresh ``sample(1:N, r, replace=false)`` every step;
+    sweeping 2: cyclic over the static batches, ``idxr = mod(idxr, d) + 1`` from
+                ``idxr = 1`` — the first batch visited is #2 (a reference quirk);
+    sweeping 3: natural order 1..d for the first pass (``inds = 1:d``, ``idx = 0``),
+                a fresh ``randperm(d)`` at the start of every later pass.
+    """
+
+    def __init__(self, N: int, batch: int, sweeping: int, rng: HostRNG):
+        assert sweeping in (1, 2, 3)
+        self.N, self.r, self.sweeping, self.rng = N, batch, sweeping, rng
+        self.d = n_batches(N, batch)
+        self.idxr, self.idx = 1, 0                      # Finito_basic.jl:38-39
+        self.inds = np.arange(1, self.d + 1, dtype=np.int64)  # :40
+
+    def batch_rows(self, j1: int) -> np.ndarray:
+        lo = self.r * (j1 - 1) + 1
+        hi = min(self.r * j1, self.N)
+        return np.arange(lo, hi + 1, dtype=np.int64)
+
+    def next(self) -> np.ndarray:
+        if self.sweeping == 1:
+            return self.rng.sample_norep(self.N, self.r)
+        if self.sweeping == 2:
+            self.idxr = self.idxr % self.d + 1
+        else:
+            if self.idx == self.d:
+                self.inds = self.rng.randperm(self.d)
+                self.idx = 1
+            else:
+                self.idx += 1
+            self.idxr = int(self.inds[self.idx - 1])
+        return self.batch_rows(self.idxr)
+
+    def take(self, k: int):
+        return [self.next() for _ in range(k)]
+
+
+class LFinitoSweeper:
+    """Finito_LFinito.jl:89-91: ``inds = randperm(d)`` before every sweep when
+    sweeping == 3, otherwise the natural order (sweeping 1 is silently cyclic)."""
+
+    def __init__(self, N: int, batch: int, sweeping: int, rng: HostRNG):
+        self.N, self.r, self.sweeping, self.rng = N, batch, sweeping, rng
+        self.d = n_batches(N, batch)
+        self.inds = np.arange(1, self.d + 1, dtype=np.int64)
+
+    def next(self) -> np.ndarray:
+        if self.sweeping == 3:
+            self.inds = self.rng.randperm(self.d)
+        return self.inds
+
+
+def csr(batches):
+    """list of 1-based index arrays → (idx, ptr) for the ``*_steps`` ABI calls."""
+    ptr = np.zeros(len(batches) + 1, dtype=np.int64)
+    if batches:
+        ptr[1:] = np.cumsum([len(b) for b in batches])
+        idx = np.ascontiguousarray(np.concatenate(batches), dtype=np.int64)
+    else:
+        idx = np.zeros(0, dtype=np.int64)
+    return idx, ptr
+
+
+def shard_rows(N: int, world: int, rank: int):
+    """Contiguous row partition: rank k owns rows [k·N/G, (k+1)·N/G)."""
+    return (rank * N) // world, ((rank + 1) * N) // world

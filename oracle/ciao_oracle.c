@@ -1,0 +1,495 @@
+/* ciao_oracle.c — CPU restatement of the CIAOAlgorithms.jl iteration loops.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle and the CPU
+ * baseline for the B200 engine (libciao_cuda).  Nothing in the product path
+ * (ciaoalgorithms.jl_b200/, include/) may include, link or call it; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs do.
+ *
+ * It restates, operation by operation and in the reference's order of
+ * separate vector passes, the Julia loops of
+ *   src/algorithms/SVRG/SVRG_basic.jl:30-96
+ *   src/algorithms/SAGA_SAG/SAGA_basic.jl:26-68
+ *   src/algorithms/Finito/Finito_basic.jl:44-121
+ *   src/algorithms/Finito/Finito_LFinito.jl:40-103
+ *   src/algorithms/ProShI/ProShI_basic.jl:44-132
+ * together with the slice of the un-vendored dependency ProximalOperators.jl
+ * 0.14 (Project.toml:10,16) those loops call: gradient!/prox! of
+ * LeastSquares (dense 1×d), Precompose(LogisticLoss), Sum(Quadratic(diag),
+ * SqrDistL2(IndBox)), NormL1, IndBox, Zero.
+ *
+ * Parity pinning: Julia is not installed in this image, so the reference
+ * cannot be executed; the oracle is pinned against every golden vector the
+ * reference's tests hold for this path (tests/test_oracle_golden.py):
+ * x_star of test/test_logistic_l1.jl:29, sum_star of test/test_sharing.jl:28
+ * and the planted optimum f* of test/test_lasso.jl:18-47, under the reference's
+ * own maxit / stepsize choices and pass criteria (1e-4).  The reference holds
+ * no per-step trajectories, so per-step parity rests on this restatement.
+ *
+ * Index sequences are INPUTS (1-based int64, exactly as Julia's rand / sample /
+ * randperm would hand them over), never drawn here.
+ *
+ * Build: see oracle/Makefile  (gcc -O3 -march=x86-64-v3 -ffp-contract=off).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/ciao_gen.h"
+
+#define ORC_LOSS_LS 0       /* LeastSquares(A_i (1×d), b_i, λ_i)            */
+#define ORC_LOSS_LOGISTIC 1 /* Precompose(LogisticLoss([y_i], μ_i), a_i', 1) */
+#define ORC_LOSS_DIAGQUAD 2 /* Sum(Quadratic(diag(q_i), c_i), SqrDistL2(IndBox(lo,hi), η)) */
+
+#define ORC_REG_ZERO 0
+#define ORC_REG_NORML1 1
+#define ORC_REG_INDBOX 2
+
+typedef struct {
+    int32_t loss_kind;
+    int32_t reg_kind;
+    int64_t N;          /* number of components f_i                         */
+    int64_t d;          /* dimension of x (rows) or of one block (sharing)  */
+    int64_t lda;        /* leading dimension of A / Qdiag / qlin            */
+    const double *A;    /* rows a_i (LS, logistic) or diag(Q_i) (diagquad)  */
+    const double *b;    /* b_i (LS), y_i (logistic), linear terms N×d (diagquad) */
+    const double *lam;  /* λ_i (LS) or μ_i (logistic), length N             */
+    double box_lo, box_hi, eta; /* SqrDistL2(IndBox(lo,hi), η)              */
+    double reg_lambda;  /* NormL1(λ)                                        */
+    const double *reg_lo; /* IndBox lower bound: length d, or NULL → scalar */
+    const double *reg_hi;
+    double reg_lo_s, reg_hi_s;
+} orc_problem;
+
+/* ------------------------------------------------------------------------ */
+/* ProximalOperators.jl 0.14 semantics                                       */
+/* ------------------------------------------------------------------------ */
+
+/* dot of a 1×d matrix row with x: BLAS gemv on a 1×d matrix; summation order
+ * is BLAS-internal, restated here left to right. */
+static double orc_dot(const double *a, const double *x, int64_t d) {
+    double s = 0.0;
+    for (int64_t k = 0; k < d; ++k) s += a[k] * x[k];
+    return s;
+}
+
+/* gradient!(y, F[i], x); returns f_i(x).
+ * LeastSquares (direct):  res = A x − b;  y = Aᴴ res;  y .*= λ;  f = (λ/2)·res²
+ * Precompose(LogisticLoss): u = L x;  c = −μ y /(1 + exp(y u));  y = Lᴴ c;
+ *                           f = μ·log(1 + 1/exp(y u))
+ * Sum(Quadratic, SqrDistL2): y = Q x + q  +  η (x − Π_box x)
+ */
+double orc_gradient(const orc_problem *p, int64_t i, const double *x, double *y) {
+    const int64_t d = p->d;
+    const double *a = p->A + i * p->lda;
+    if (p->loss_kind == ORC_LOSS_LS) {
+        double res = orc_dot(a, x, d) - p->b[i];
+        double lam = p->lam[i];
+        for (int64_t k = 0; k < d; ++k) y[k] = a[k] * res;
+        for (int64_t k = 0; k < d; ++k) y[k] *= lam;
+        return (lam / 2) * (res * res);
+    } else if (p->loss_kind == ORC_LOSS_LOGISTIC) {
+        double yi = p->b[i], mu = p->lam[i];
+        double u = orc_dot(a, x, d);
+        double expyx = exp(yi * u);
+        double c = -mu * yi / (1 + expyx);
+        for (int64_t k = 0; k < d; ++k) y[k] = a[k] * c;
+        return mu * log(1 + 1 / expyx);
+    } else {
+        const double *q = p->b + i * p->lda;
+        double val = 0.0;
+        for (int64_t k = 0; k < d; ++k) {
+            double xk = x[k];
+            double g1 = a[k] * xk + q[k];                 /* Quadratic: Qx + q  */
+            double pr = xk < p->box_lo ? p->box_lo : (xk > p->box_hi ? p->box_hi : xk);
+            double dist = xk - pr;
+            double g2 = p->eta * dist;                    /* SqrDistL2          */
+            y[k] = g1 + g2;
+            val += 0.5 * a[k] * xk * xk + q[k] * xk + (p->eta / 2) * dist * dist;
+        }
+        return val;
+    }
+}
+
+/* prox!(y, g, x, γ) */
+void orc_prox(const orc_problem *p, double *y, const double *x, double gamma) {
+    const int64_t d = p->d;
+    if (p->reg_kind == ORC_REG_NORML1) {
+        double gl = gamma * p->reg_lambda;
+        for (int64_t k = 0; k < d; ++k) {
+            double xk = x[k];
+            y[k] = xk + (xk <= -gl ? gl : (xk >= gl ? -gl : -xk));
+        }
+    } else if (p->reg_kind == ORC_REG_INDBOX) {
+        for (int64_t k = 0; k < d; ++k) {
+            double lo = p->reg_lo ? p->reg_lo[k] : p->reg_lo_s;
+            double hi = p->reg_hi ? p->reg_hi[k] : p->reg_hi_s;
+            double xk = x[k];
+            y[k] = xk < lo ? lo : (xk > hi ? hi : xk);
+        }
+    } else {
+        if (y != x) memcpy(y, x, (size_t)d * sizeof(double));
+    }
+}
+
+double orc_reg_value(const orc_problem *p, const double *x) {
+    if (p->reg_kind == ORC_REG_NORML1) {
+        double s = 0.0;
+        for (int64_t k = 0; k < p->d; ++k) s += fabs(x[k]);
+        return p->reg_lambda * s;
+    }
+    return 0.0;
+}
+
+/* (1/N) Σ f_i(x) and g(x) — the cost the reference's tests evaluate
+ * (test/test_lasso.jl:45). */
+void orc_objective(const orc_problem *p, const double *x, double *f_mean, double *g_val) {
+    double *tmp = (double *)malloc((size_t)p->d * sizeof(double));
+    double s = 0.0;
+    for (int64_t i = 0; i < p->N; ++i) s += orc_gradient(p, i, x, tmp);
+    free(tmp);
+    *f_mean = s / (double)p->N;
+    *g_val = orc_reg_value(p, x);
+}
+
+/* out = scale · Σ_i ∇f_i(x), accumulated in the reference's order
+ * (SVRG_basic.jl:58-63: each gradient scaled first, then added). */
+void orc_full_gradient(const orc_problem *p, const double *x, double scale, double *out) {
+    const int64_t d = p->d;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    memset(out, 0, (size_t)d * sizeof(double));
+    for (int64_t i = 0; i < p->N; ++i) {
+        orc_gradient(p, i, x, g);
+        for (int64_t k = 0; k < d; ++k) g[k] *= scale;
+        for (int64_t k = 0; k < d; ++k) out[k] += g[k];
+    }
+    free(g);
+}
+
+/* Julia's sum over a Vector of d-vectors with stride ld (Base.mapreduce_impl:
+ * pairwise, sequential below 1024 terms).  out = Σ_{i in [lo,hi)} v_i */
+static void orc_pairwise_sum(const double *v, int64_t ld, int64_t d, int64_t lo, int64_t hi,
+                             const double *div, double *out) {
+    if (hi - lo < 1024) {
+        for (int64_t k = 0; k < d; ++k) out[k] = div ? v[lo * ld + k] / div[lo] : v[lo * ld + k];
+        for (int64_t i = lo + 1; i < hi; ++i)
+            for (int64_t k = 0; k < d; ++k)
+                out[k] += div ? v[i * ld + k] / div[i] : v[i * ld + k];
+    } else {
+        int64_t mid = lo + ((hi - lo) >> 1);
+        double *r = (double *)malloc((size_t)d * sizeof(double));
+        orc_pairwise_sum(v, ld, d, lo, mid, div, out);
+        orc_pairwise_sum(v, ld, d, mid, hi, div, r);
+        for (int64_t k = 0; k < d; ++k) out[k] += r[k];
+        free(r);
+    }
+}
+
+static double orc_pairwise_scalar(const double *v, int64_t lo, int64_t hi, int recip) {
+    if (hi - lo < 1024) {
+        double s = recip ? 1 / v[lo] : v[lo];
+        for (int64_t i = lo + 1; i < hi; ++i) s += recip ? 1 / v[i] : v[i];
+        return s;
+    }
+    int64_t mid = lo + ((hi - lo) >> 1);
+    return orc_pairwise_scalar(v, lo, mid, recip) + orc_pairwise_scalar(v, mid, hi, recip);
+}
+
+/* γ̂ = 1/sum(1 ./ γ)  (Finito_basic.jl:82, Finito_LFinito.jl:66) */
+double orc_finito_hat_gamma(const double *gamma, int64_t N) {
+    return 1 / orc_pairwise_scalar(gamma, 0, N, 1);
+}
+/* γ̂ = sum(γ)  (ProShI_basic.jl:82) */
+double orc_proshi_hat_gamma(const double *gamma, int64_t N) {
+    return orc_pairwise_scalar(gamma, 0, N, 0);
+}
+
+/* ------------------------------------------------------------------------ */
+/* SVRG / SVRG++   (SVRG_basic.jl)                                           */
+/* ------------------------------------------------------------------------ */
+
+/* SVRG_basic.jl:58-66 — av = Σ ∇f_i(x0)/N ; z_full = x0 ; z = 0 ; w = x0 */
+void orc_svrg_init(const orc_problem *p, const double *x0, double *av, double *z,
+                   double *z_full, double *w) {
+    const int64_t d = p->d, N = p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    memset(av, 0, (size_t)d * sizeof(double));
+    for (int64_t i = 0; i < N; ++i) {
+        orc_gradient(p, i, x0, g);
+        for (int64_t k = 0; k < d; ++k) g[k] /= (double)N;
+        for (int64_t k = 0; k < d; ++k) av[k] += g[k];
+    }
+    free(g);
+    memcpy(z_full, x0, (size_t)d * sizeof(double));
+    memset(z, 0, (size_t)d * sizeof(double));
+    memcpy(w, x0, (size_t)d * sizeof(double));
+}
+
+/* SVRG_basic.jl:73-82 — the m sequential inner steps on the given indices */
+void orc_svrg_inner(const orc_problem *p, double gamma, const int64_t *idx1, int64_t m,
+                    const double *av, double *z, const double *z_full, double *w) {
+    const int64_t d = p->d;
+    double *temp = (double *)malloc((size_t)d * sizeof(double));
+    double *gtmp = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t s = 0; s < m; ++s) {
+        int64_t i = idx1[s] - 1;
+        orc_gradient(p, i, z_full, temp);                          /* :74 */
+        orc_gradient(p, i, w, gtmp);                               /* :75 */
+        for (int64_t k = 0; k < d; ++k) temp[k] -= gtmp[k];        /* :76 */
+        for (int64_t k = 0; k < d; ++k) temp[k] -= av[k];          /* :77 */
+        for (int64_t k = 0; k < d; ++k) temp[k] *= gamma;          /* :78 */
+        for (int64_t k = 0; k < d; ++k) temp[k] += w[k];           /* :79 */
+        orc_prox(p, w, temp, gamma);                               /* :80 */
+        for (int64_t k = 0; k < d; ++k) z[k] += w[k];              /* :81 */
+    }
+    free(temp);
+    free(gtmp);
+}
+
+/* SVRG_basic.jl:71-96 — one outer iteration (inner loop + snapshot + full gradient).
+ * The caller doubles m when plus (SVRG_basic.jl:93). */
+void orc_svrg_epoch(const orc_problem *p, double gamma, int plus, const int64_t *idx1, int64_t m,
+                    double *av, double *z, double *z_full, double *w) {
+    const int64_t d = p->d, N = p->N;
+    orc_svrg_inner(p, gamma, idx1, m, av, z, z_full, w);
+    for (int64_t k = 0; k < d; ++k) z_full[k] = z[k] / (double)m;  /* :84 */
+    if (!plus) memcpy(w, z_full, (size_t)d * sizeof(double));      /* :85 */
+    memset(z, 0, (size_t)d * sizeof(double));                      /* :86 */
+    memset(av, 0, (size_t)d * sizeof(double));                     /* :87 */
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t i = 0; i < N; ++i) {                              /* :88-92 */
+        orc_gradient(p, i, z_full, g);
+        for (int64_t k = 0; k < d; ++k) g[k] /= (double)N;
+        for (int64_t k = 0; k < d; ++k) av[k] += g[k];
+    }
+    free(g);
+}
+
+/* ------------------------------------------------------------------------ */
+/* SAGA / SAG   (SAGA_basic.jl)                                              */
+/* ------------------------------------------------------------------------ */
+
+/* SAGA_basic.jl:41-48 — table s_i = ∇f_i(x0); av = sum(s)/N; z = prox_g((1−γ)x0, γ) */
+void orc_saga_init(const orc_problem *p, const double *x0, double gamma, double *s, double *av,
+                   double *z) {
+    const int64_t d = p->d, N = p->N;
+    for (int64_t i = 0; i < N; ++i) orc_gradient(p, i, x0, s + i * d);
+    orc_pairwise_sum(s, d, d, 0, N, NULL, av);
+    for (int64_t k = 0; k < d; ++k) av[k] /= (double)N;
+    double *t = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t k = 0; k < d; ++k) t[k] = (1 - gamma) * x0[k];
+    orc_prox(p, z, t, gamma);
+    free(t);
+}
+
+/* SAGA_basic.jl:53-68 — K sequential single-sample steps */
+void orc_saga_steps(const orc_problem *p, double gamma, int sag, const int64_t *idx1, int64_t K,
+                    double *s, double *av, double *z) {
+    const int64_t d = p->d;
+    const double N = (double)p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    double *w = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t t = 0; t < K; ++t) {
+        int64_t i = idx1[t] - 1;
+        double *si = s + i * d;
+        orc_gradient(p, i, z, g);                                               /* :56 */
+        if (sag) {
+            for (int64_t k = 0; k < d; ++k) av[k] += (g[k] - si[k]) / N;        /* :58 */
+            for (int64_t k = 0; k < d; ++k) w[k] = z[k] - gamma * av[k];        /* :59 */
+        } else {
+            for (int64_t k = 0; k < d; ++k) w[k] = z[k] - gamma * (g[k] - si[k] + av[k]); /* :61 */
+            for (int64_t k = 0; k < d; ++k) av[k] += (g[k] - si[k]) / N;        /* :62 */
+        }
+        orc_prox(p, z, w, gamma);                                               /* :64 */
+        memcpy(si, g, (size_t)d * sizeof(double));                              /* :65 */
+    }
+    free(g);
+    free(w);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Finito / MISO / DIAG basic   (Finito_basic.jl)                            */
+/* ------------------------------------------------------------------------ */
+
+/* Finito_basic.jl:76-84 — s_i = x0 − (γ_i/N)∇f_i(x0); av = γ̂·sum(s ./ γ); z = prox_g(av, γ̂) */
+void orc_finito_init(const orc_problem *p, const double *x0, const double *gamma, double hat_gamma,
+                     double *s, double *av, double *z) {
+    const int64_t d = p->d, N = p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t i = 0; i < N; ++i) {
+        orc_gradient(p, i, x0, g);
+        double c = gamma[i] / (double)N;
+        for (int64_t k = 0; k < d; ++k) s[i * d + k] = x0[k] - c * g[k];
+    }
+    free(g);
+    orc_pairwise_sum(s, d, d, 0, N, gamma, av);
+    for (int64_t k = 0; k < d; ++k) av[k] = hat_gamma * av[k];
+    orc_prox(p, z, av, hat_gamma);
+}
+
+/* Finito_basic.jl:110-118 — batches in CSR form: batch j = idx1[ptr[j] .. ptr[j+1]) ;
+ * the prox closes every batch. Index selection (:96-108) is the caller's. */
+void orc_finito_steps(const orc_problem *p, const double *gamma, double hat_gamma,
+                      const int64_t *idx1, const int64_t *ptr, int64_t n_batches, double *s,
+                      double *av, double *z) {
+    const int64_t d = p->d;
+    const double N = (double)p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t j = 0; j < n_batches; ++j) {
+        for (int64_t t = ptr[j]; t < ptr[j + 1]; ++t) {
+            int64_t i = idx1[t] - 1;
+            double *si = s + i * d;
+            orc_gradient(p, i, z, g);                                           /* :112 */
+            double c = -(gamma[i] / N);
+            for (int64_t k = 0; k < d; ++k) g[k] *= c;                          /* :113 */
+            for (int64_t k = 0; k < d; ++k) g[k] += z[k];                       /* :114 */
+            double r = hat_gamma / gamma[i];
+            for (int64_t k = 0; k < d; ++k) av[k] += (g[k] - si[k]) * r;        /* :115 */
+            memcpy(si, g, (size_t)d * sizeof(double));                          /* :116 */
+        }
+        orc_prox(p, z, av, hat_gamma);                                          /* :118 */
+    }
+    free(g);
+}
+
+/* ------------------------------------------------------------------------ */
+/* LFinito   (Finito_LFinito.jl)                                             */
+/* ------------------------------------------------------------------------ */
+
+/* Finito_LFinito.jl:67-72 — av = x0 − Σ (γ̂/N)∇f_i(x0); z = z_full = copy(av) (ctor :33-35) */
+void orc_lfinito_init(const orc_problem *p, const double *x0, double hat_gamma, double *av,
+                      double *z, double *z_full) {
+    const int64_t d = p->d, N = p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    memcpy(av, x0, (size_t)d * sizeof(double));
+    double c = hat_gamma / (double)N;
+    for (int64_t i = 0; i < N; ++i) {
+        orc_gradient(p, i, x0, g);
+        for (int64_t k = 0; k < d; ++k) g[k] *= c;
+        for (int64_t k = 0; k < d; ++k) av[k] -= g[k];
+    }
+    free(g);
+    memcpy(z, av, (size_t)d * sizeof(double));
+    memcpy(z_full, av, (size_t)d * sizeof(double));
+}
+
+/* Finito_LFinito.jl:78-103 — one outer iteration.  batch_order1 = state.inds
+ * (1-based batch numbers, after the optional randperm :89); batch j covers rows
+ * r(j−1)+1 .. min(jr, N) (:44-49). */
+void orc_lfinito_outer(const orc_problem *p, const double *gamma, double hat_gamma,
+                       const int64_t *batch_order1, int64_t n_batches, int64_t r, double *av,
+                       double *z, double *z_full) {
+    const int64_t d = p->d, N = p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    double c = hat_gamma / (double)N;
+    orc_prox(p, z_full, av, hat_gamma);                                         /* :83 */
+    memcpy(av, z_full, (size_t)d * sizeof(double));                             /* :84 */
+    for (int64_t i = 0; i < N; ++i) {                                           /* :85-88 */
+        orc_gradient(p, i, z_full, g);
+        for (int64_t k = 0; k < d; ++k) av[k] -= c * g[k];
+    }
+    for (int64_t jj = 0; jj < n_batches; ++jj) {                                /* :91 */
+        int64_t j = batch_order1[jj] - 1;
+        orc_prox(p, z, av, hat_gamma);                                          /* :92 */
+        int64_t lo = r * j, hi = lo + r < N ? lo + r : N;
+        for (int64_t i = lo; i < hi; ++i) {
+            orc_gradient(p, i, z_full, g);                                      /* :94 */
+            for (int64_t k = 0; k < d; ++k) av[k] += c * g[k];                  /* :95 */
+            orc_gradient(p, i, z, g);                                           /* :96 */
+            for (int64_t k = 0; k < d; ++k) av[k] -= c * g[k];                  /* :97 */
+            double rr = hat_gamma / gamma[i];
+            for (int64_t k = 0; k < d; ++k) av[k] += rr * (z[k] - z_full[k]);   /* :98 */
+        }
+    }
+    free(g);
+}
+
+/* ------------------------------------------------------------------------ */
+/* ProShI   (ProShI_basic.jl)                                                */
+/* ------------------------------------------------------------------------ */
+
+static void orc_proshi_dual(const orc_problem *p, double hat_gamma, const double *av, double *z) {
+    const int64_t d = p->d;
+    orc_prox(p, z, av, hat_gamma);                         /* :84 / :121 */
+    for (int64_t k = 0; k < d; ++k) z[k] -= av[k];         /* :85 / :122 */
+    for (int64_t k = 0; k < d; ++k) z[k] /= hat_gamma;     /* :86 / :123 */
+}
+
+/* ProShI_basic.jl:76-86 — s_i = x0 − (γ_i/N)∇f_i(x0); av = sum(s); z = (prox_g(av,γ̂) − av)/γ̂ */
+void orc_proshi_init(const orc_problem *p, const double *x0, const double *gamma, double hat_gamma,
+                     double *s, double *av, double *z) {
+    const int64_t d = p->d, N = p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t i = 0; i < N; ++i) {
+        orc_gradient(p, i, x0, g);
+        double c = gamma[i] / (double)N;
+        for (int64_t k = 0; k < d; ++k) s[i * d + k] = x0[k] - c * g[k];
+    }
+    free(g);
+    orc_pairwise_sum(s, d, d, 0, N, NULL, av);
+    orc_proshi_dual(p, hat_gamma, av, z);
+}
+
+/* ProShI_basic.jl:111-123 — CSR batches as in orc_finito_steps */
+void orc_proshi_steps(const orc_problem *p, const double *gamma, double hat_gamma,
+                      const int64_t *idx1, const int64_t *ptr, int64_t n_batches, double *s,
+                      double *av, double *z) {
+    const int64_t d = p->d;
+    const double N = (double)p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t j = 0; j < n_batches; ++j) {
+        for (int64_t t = ptr[j]; t < ptr[j + 1]; ++t) {
+            int64_t i = idx1[t] - 1;
+            double *si = s + i * d;
+            for (int64_t k = 0; k < d; ++k) av[k] -= si[k];                     /* :113 */
+            for (int64_t k = 0; k < d; ++k) si[k] += gamma[i] * z[k];           /* :114 */
+            orc_gradient(p, i, si, g);                                          /* :115 */
+            double c = -(gamma[i] / N);
+            for (int64_t k = 0; k < d; ++k) g[k] *= c;                          /* :116 */
+            for (int64_t k = 0; k < d; ++k) g[k] += si[k];                      /* :117 */
+            for (int64_t k = 0; k < d; ++k) av[k] += g[k];                      /* :118 */
+            memcpy(si, g, (size_t)d * sizeof(double));                          /* :119 */
+        }
+        orc_proshi_dual(p, hat_gamma, av, z);                                   /* :121-123 */
+    }
+    free(g);
+}
+
+/* ProShI_basic.jl:127-132 — IN-PLACE s_i += γ_i z for all i, every call */
+void orc_proshi_solution(const orc_problem *p, const double *gamma, const double *z, double *s) {
+    const int64_t d = p->d;
+    for (int64_t i = 0; i < p->N; ++i)
+        for (int64_t k = 0; k < d; ++k) s[i * d + k] += gamma[i] * z[k];
+}
+
+/* ------------------------------------------------------------------------ */
+/* synthetic inputs (bit-identical to the device generator, include/ciao_gen.h) */
+/* ------------------------------------------------------------------------ */
+
+void orc_gen_rows(int kind, int64_t d, uint64_t seed, int64_t i0, int64_t n, double *A, double *rhs) {
+    for (int64_t r = 0; r < n; ++r) {
+        int64_t i = i0 + r;
+        for (int64_t j = 0; j < d; ++j) A[r * d + j] = ciao_syn_entry(kind, d, seed, i, j);
+        if (rhs && kind != CIAO_SYN_SHARING) rhs[r] = ciao_syn_rhs(kind, d, seed, i);
+    }
+}
+
+void orc_gen_xtrue(int kind, int64_t d, uint64_t seed, double *x) {
+    memset(x, 0, (size_t)d * sizeof(double));
+    int64_t p = ciao_syn_support_size(kind, d);
+    for (int64_t t = 0; t < p; ++t)
+        x[ciao_syn_support_pos(kind, d, seed, t)] = ciao_syn_support_val(seed, t);
+}
+
+/* max_i ‖a_i‖² over rows [0,N) — L_i = λ_i‖a_i‖² (LS, test_lasso.jl:55) or
+ * 0.25‖a_i‖² (logistic, test_logistic_l1.jl:39) */
+double orc_max_row_sqnorm(const orc_problem *p) {
+    double mx = 0.0;
+    for (int64_t i = 0; i < p->N; ++i) {
+        const double *a = p->A + i * p->lda;
+        double s = orc_dot(a, a, p->d);
+        if (s > mx) mx = s;
+    }
+    return mx;
+}
