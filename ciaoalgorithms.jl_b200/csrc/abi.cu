@@ -1,0 +1,720 @@
+// abi.cu — the C ABI of libciao_cuda (include/ciao_cuda.h): context lifetime,
+// problem upload, the solver entry points that replace Base.iterate of the
+// reference's iterables, state read-back and measurement.  Unity build: the
+// kernel files are included here so that every kernel lives in one module.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+void ciao_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#include "pass.cu"
+#include "gen.cu"
+#include "indices.cu"
+#include "seq.cu"
+#include "proshi.cu"
+#include "comm.cu"
+
+void ciao_comm_destroy(ciao_ctx *c);
+
+// ---------------------------------------------------------------------------
+// small elementwise kernels
+// ---------------------------------------------------------------------------
+// out = prox_g(in, γ)      prox!(z, g, av, γ̂)  Finito_basic.jl:84, Finito_LFinito.jl:83
+__global__ void prox_vec_kernel(const double *in, double *out, int64_t d_pad, double gamma, RegParams reg) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= d_pad) return;
+    const double lo = reg.lo_v ? reg.lo_v[j] : reg.lo_s, hi = reg.hi_v ? reg.hi_v[j] : reg.hi_s;
+    out[j] = prox_rt(reg.kind, in[j], gamma * reg.lambda, lo, hi);
+}
+// z = prox_g((1−γ)·x0, γ)   SAGA_basic.jl:48
+__global__ void saga_z0_kernel(const double *x0, double *z, int64_t d_pad, double gamma, RegParams reg) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= d_pad) return;
+    const double lo = reg.lo_v ? reg.lo_v[j] : reg.lo_s, hi = reg.hi_v ? reg.hi_v[j] : reg.hi_s;
+    z[j] = prox_rt(reg.kind, __dmul_rn(1 - gamma, x0[j]), gamma * reg.lambda, lo, hi);
+}
+// record tails: [b_i | scale_i | γ_i | 0]
+__global__ void pack_tails_kernel(double *rec, int64_t n_rows, int64_t d_pad, int64_t ld, const double *b,
+                                  const double *scale, double scale_scalar) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    double *t = rec + i * ld + d_pad;
+    t[0] = b[i];
+    t[1] = scale ? scale[i] : scale_scalar;
+    t[2] = 0.0;
+    t[3] = 0.0;
+}
+__global__ void set_gamma_tail_kernel(double *rec, int64_t n_rows, int64_t d_pad, int64_t ld, const double *gam) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_rows) rec[i * ld + d_pad + 2] = gam[i];
+}
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+static inline int blocks_for(int64_t n) { return (int)((n + 255) / 256); }
+
+static void free_problem(ciao_ctx *c) {
+    cudaFree(c->rec); cudaFree(c->qd); cudaFree(c->ql); cudaFree(c->vecs); cudaFree(c->table);
+    cudaFree(c->gamma_dev); cudaFree(c->partial); cudaFree(c->reg_bounds);
+    c->rec = c->qd = c->ql = c->vecs = c->table = c->gamma_dev = c->partial = c->reg_bounds = nullptr;
+    c->reg = RegParams{CIAO_REG_ZERO, 0, 0, 0, nullptr, nullptr};
+    c->loss_kind = -1;
+    c->algo = 0;
+}
+
+static int alloc_common(ciao_ctx *c, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d) {
+    free_problem(c);
+    c->N_total = N_total; c->row0 = row0; c->n_rows = n_rows; c->d = d;
+    c->d_pad = (d + 3) / 4 * 4;
+    c->ld = c->d_pad + CIAO_TAIL;
+    CUDA_TRY(cudaMalloc(&c->vecs, (size_t)CIAO_NUM_VECS * c->d_pad * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(c->vecs, 0, (size_t)CIAO_NUM_VECS * c->d_pad * sizeof(double), c->stream));
+    CUDA_TRY(cudaMalloc(&c->partial, (size_t)(c->d_pad + 8) * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(c->partial, 0, (size_t)(c->d_pad + 8) * sizeof(double), c->stream));
+    return CIAO_OK;
+}
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// host vector (length d) → state vector `which` (padding stays zero); blocks until the copy is done
+static int upload_vec(ciao_ctx *c, int which, const double *x) {
+    double *dst = ctx_vec(c, which);
+    if (is_device_ptr(x)) {
+        CUDA_TRY(cudaMemcpyAsync(dst, x, (size_t)c->d * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(dst, x, (size_t)c->d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return CIAO_OK;
+}
+
+static int copy_vec(ciao_ctx *c, int dst, int src) {
+    CUDA_TRY(cudaMemcpyAsync(ctx_vec(c, dst), ctx_vec(c, src), (size_t)c->d_pad * sizeof(double), cudaMemcpyDeviceToDevice,
+                             c->stream));
+    return CIAO_OK;
+}
+
+static int check_err_flag(ciao_ctx *c) {
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, c->err_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (h) {
+        CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
+        CIAO_FAIL(CIAO_ERR_INVALID, "index out of range 1..N (or malformed batch_ptr / batch_order) in a previous call");
+    }
+    return CIAO_OK;
+}
+
+static int reserve_idx(ciao_ctx *c, size_t n) {
+    if (n > c->idx_cap) {
+        // keep staged raw indices across a growth of the buffers
+        int64_t *nr = nullptr, *np = nullptr;
+        const size_t cap = std::max(n, c->idx_cap * 2);
+        CUDA_TRY(cudaMalloc(&nr, cap * sizeof(int64_t)));
+        CUDA_TRY(cudaMalloc(&np, cap * sizeof(int64_t)));
+        if (c->idx_raw && c->staged > 0)
+            CUDA_TRY(cudaMemcpyAsync(nr, c->idx_raw, (size_t)c->staged * sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        cudaFree(c->idx_raw); cudaFree(c->idx_prep);
+        c->idx_raw = nr; c->idx_prep = np; c->idx_cap = cap;
+    }
+    return CIAO_OK;
+}
+
+// Brings n raw (1-based) indices to the device: *raw_dev points at them.
+static int fetch_raw_indices(ciao_ctx *c, const int64_t *idx, int64_t n, const int64_t **raw_dev) {
+    if (n < 0) CIAO_FAIL(CIAO_ERR_INVALID, "negative index count");
+    if (idx == nullptr) {
+        if (c->staged < n) CIAO_FAIL(CIAO_ERR_STATE, "idx == NULL but only %lld indices are staged (need %lld)",
+                                     (long long)c->staged, (long long)n);
+        *raw_dev = c->idx_raw;
+        return CIAO_OK;
+    }
+    CIAO_TRY(reserve_idx(c, (size_t)std::max<int64_t>(n, 1)));
+    if (is_device_ptr(idx)) {
+        *raw_dev = idx;
+        return CIAO_OK;
+    }
+    c->staged = 0;
+    CUDA_TRY(cudaMemcpyAsync(c->idx_raw, idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // host buffer is borrowed for the call only
+    *raw_dev = c->idx_raw;
+    return CIAO_OK;
+}
+
+static int upload_ptr(ciao_ctx *c, const int64_t *ptr, int64_t n, const int64_t **out) {
+    if (is_device_ptr(ptr)) {
+        *out = ptr;
+        return CIAO_OK;
+    }
+    if ((size_t)n > c->ptr_cap) {
+        cudaFree(c->ptr_dev);
+        c->ptr_dev = nullptr;
+        c->ptr_cap = 0;
+        CUDA_TRY(cudaMalloc(&c->ptr_dev, (size_t)n * 2 * sizeof(int64_t)));
+        c->ptr_cap = (size_t)n * 2;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->ptr_dev, ptr, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out = c->ptr_dev;
+    return CIAO_OK;
+}
+
+static int need_rows(ciao_ctx *c, const char *who, bool whole) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "%s: null context", who);
+    if (c->loss_kind != CIAO_LOSS_LS && c->loss_kind != CIAO_LOSS_LOGISTIC)
+        CIAO_FAIL(CIAO_ERR_STATE, "%s: no row problem set (ciao_set_rows / ciao_gen_synthetic first)", who);
+    if (whole && c->n_rows != c->N_total)
+        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "%s: the sequential loops run on one GPU holding all N rows (this context holds a shard)", who);
+    CUDA_TRY(cudaSetDevice(c->device));
+    return CIAO_OK;
+}
+
+static int alloc_table(ciao_ctx *c) {
+    if (!c->table) CUDA_TRY(cudaMalloc(&c->table, (size_t)c->n_rows * c->d_pad * sizeof(double)));
+    return CIAO_OK;
+}
+
+static int set_gammas(ciao_ctx *c, const double *gamma_N, bool tails) {
+    if (!c->gamma_dev) CUDA_TRY(cudaMalloc(&c->gamma_dev, (size_t)c->N_total * sizeof(double)));
+    if (is_device_ptr(gamma_N)) {
+        CUDA_TRY(cudaMemcpyAsync(c->gamma_dev, gamma_N, (size_t)c->N_total * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(c->gamma_dev, gamma_N, (size_t)c->N_total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if (tails) {
+        set_gamma_tail_kernel<<<blocks_for(c->n_rows), 256, 0, c->stream>>>(c->rec, c->n_rows, c->d_pad, c->ld, c->gamma_dev);
+        CUDA_TRY(cudaGetLastError());
+        c->timing.launches += 1;
+    }
+    return CIAO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------
+extern "C" int ciao_version(void) { return CIAO_VERSION; }
+extern "C" const char *ciao_last_error(void) { return g_err; }
+
+extern "C" int ciao_device_count(int *n) {
+    if (!n) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_device_count: null output");
+    *n = 0;
+    CUDA_TRY(cudaGetDeviceCount(n));
+    return CIAO_OK;
+}
+
+extern "C" int ciao_create(ciao_ctx **out, int device) {
+    if (!out) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_create: null output");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        CIAO_FAIL(CIAO_ERR_CUDA, "no CUDA device available (%s); libciao_cuda has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_create: device %d not in [0,%d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    ciao_ctx *c = new (std::nothrow) ciao_ctx();
+    if (!c) CIAO_FAIL(CIAO_ERR_OOM, "host allocation failed");
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    cudaEvent_t *evs[] = {&c->ev_pa, &c->ev_pb, &c->ev_sa, &c->ev_sb, &c->tm_a, &c->tm_b};
+    for (auto ev : evs) CUDA_TRY(cudaEventCreate(ev));
+    CUDA_TRY(cudaMalloc(&c->err_dev, sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
+    *out = c;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_destroy(ciao_ctx *c) {
+    if (!c) return CIAO_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    ciao_comm_destroy(c);
+    free_problem(c);
+    cudaFree(c->ws); cudaFree(c->idx_raw); cudaFree(c->idx_prep); cudaFree(c->ptr_dev); cudaFree(c->err_dev);
+    cudaEvent_t evs[] = {c->ev_pa, c->ev_pb, c->ev_sa, c->ev_sb, c->tm_a, c->tm_b};
+    for (auto ev : evs) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_sync(ciao_ctx *c) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_sync: null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_err_flag(c);
+}
+
+extern "C" int ciao_set_tuning(ciao_ctx *c, int pass_threads, int pass_stages, int pass_ctas_per_sm, int seq_cluster, int seq_threads) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_tuning: null context");
+    if (seq_cluster != 0 && seq_cluster != 1 && seq_cluster != 2 && seq_cluster != 4 && seq_cluster != 8)
+        CIAO_FAIL(CIAO_ERR_INVALID, "seq_cluster must be 0, 1, 2, 4 or 8");
+    if (pass_threads < 0 || pass_threads > 512 || seq_threads < 0 || seq_threads > 512 || pass_stages < 0 || pass_ctas_per_sm < 0 || pass_ctas_per_sm > 4)
+        CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_tuning: value out of range");
+    c->pass_threads = pass_threads; c->pass_stages = pass_stages; c->pass_ctas = pass_ctas_per_sm;
+    c->seq_cluster = seq_cluster; c->seq_threads = seq_threads;
+    return CIAO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// problem
+// ---------------------------------------------------------------------------
+extern "C" int ciao_set_rows(ciao_ctx *c, int loss_kind, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d,
+                             const double *A, int64_t lda, const double *b_or_y, const double *scale, double scale_scalar) {
+    if (!c || !A || !b_or_y) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_rows: null argument");
+    if (loss_kind != CIAO_LOSS_LS && loss_kind != CIAO_LOSS_LOGISTIC) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "ciao_set_rows: unknown loss kind %d", loss_kind);
+    if (N_total <= 0 || n_rows <= 0 || d <= 0 || lda < d || row0 < 0 || row0 + n_rows > N_total)
+        CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_rows: bad shape N=%lld row0=%lld n_rows=%lld d=%lld lda=%lld", (long long)N_total,
+                  (long long)row0, (long long)n_rows, (long long)d, (long long)lda);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CIAO_TRY(alloc_common(c, N_total, row0, n_rows, d));
+    CUDA_TRY(cudaMalloc(&c->rec, (size_t)n_rows * c->ld * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(c->rec, 0, (size_t)n_rows * c->ld * sizeof(double), c->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(c->rec, (size_t)c->ld * sizeof(double), A, (size_t)lda * sizeof(double), (size_t)d * sizeof(double),
+                               (size_t)n_rows, cudaMemcpyDefault, c->stream));
+    double *tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&tmp, (size_t)n_rows * 2 * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(tmp, b_or_y, (size_t)n_rows * sizeof(double), cudaMemcpyDefault, c->stream));
+    if (scale) CUDA_TRY(cudaMemcpyAsync(tmp + n_rows, scale, (size_t)n_rows * sizeof(double), cudaMemcpyDefault, c->stream));
+    pack_tails_kernel<<<blocks_for(n_rows), 256, 0, c->stream>>>(c->rec, n_rows, c->d_pad, c->ld, tmp, scale ? tmp + n_rows : nullptr, scale_scalar);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(tmp);
+    c->loss_kind = loss_kind;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_set_blocks(ciao_ctx *c, int64_t N, int64_t n, const double *Qdiag, int64_t ldq, const double *qlin,
+                               int64_t ldl, double box_lo, double box_hi, double eta) {
+    if (!c || !Qdiag || !qlin) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_blocks: null argument");
+    if (N <= 0 || n <= 0 || ldq < n || ldl < n || !(box_lo <= box_hi)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_blocks: bad shape");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CIAO_TRY(alloc_common(c, N, 0, N, n));
+    const size_t bytes = (size_t)N * c->d_pad * sizeof(double);
+    CUDA_TRY(cudaMalloc(&c->qd, bytes));
+    CUDA_TRY(cudaMalloc(&c->ql, bytes));
+    CUDA_TRY(cudaMemsetAsync(c->qd, 0, bytes, c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->ql, 0, bytes, c->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(c->qd, (size_t)c->d_pad * 8, Qdiag, (size_t)ldq * 8, (size_t)n * 8, (size_t)N, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(c->ql, (size_t)c->d_pad * 8, qlin, (size_t)ldl * 8, (size_t)n * 8, (size_t)N, cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->box_lo = box_lo; c->box_hi = box_hi; c->eta = eta;
+    c->loss_kind = CIAO_LOSS_DIAGQUAD;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_set_reg(ciao_ctx *c, int reg_kind, const double *params, int64_t nparams) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_reg: null context");
+    if (c->loss_kind < 0) CIAO_FAIL(CIAO_ERR_STATE, "ciao_set_reg: set the problem (F) first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    RegParams r{reg_kind, 0, 0, 0, nullptr, nullptr};
+    if (reg_kind == CIAO_REG_ZERO) {
+    } else if (reg_kind == CIAO_REG_NORML1) {
+        if (!params || nparams != 1 || !(params[0] >= 0)) CIAO_FAIL(CIAO_ERR_INVALID, "NormL1 takes one parameter λ ≥ 0");
+        r.lambda = params[0];
+    } else if (reg_kind == CIAO_REG_INDBOX) {
+        if (params && nparams == 2) {
+            r.lo_s = params[0]; r.hi_s = params[1];
+            if (!(r.lo_s <= r.hi_s)) CIAO_FAIL(CIAO_ERR_INVALID, "IndBox: lo > hi");
+        } else if (params && nparams == 2 * c->d) {
+            cudaFree(c->reg_bounds);
+            c->reg_bounds = nullptr;
+            CUDA_TRY(cudaMalloc(&c->reg_bounds, (size_t)2 * c->d_pad * sizeof(double)));
+            std::vector<double> h((size_t)2 * c->d_pad, 0.0);
+            for (int64_t j = 0; j < c->d; ++j) {
+                if (!(params[j] <= params[c->d + j])) CIAO_FAIL(CIAO_ERR_INVALID, "IndBox: lo[%lld] > hi[%lld]", (long long)j, (long long)j);
+                h[j] = params[j];
+                h[c->d_pad + j] = params[c->d + j];
+            }
+            CUDA_TRY(cudaMemcpy(c->reg_bounds, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+            r.lo_v = c->reg_bounds;
+            r.hi_v = c->reg_bounds + c->d_pad;
+        } else {
+            CIAO_FAIL(CIAO_ERR_INVALID, "IndBox takes {lo,hi} or lo[d] followed by hi[d]");
+        }
+    } else {
+        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "unknown g kind %d (supported: Zero, NormL1, IndBox)", reg_kind);
+    }
+    c->reg = r;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_gen_synthetic(ciao_ctx *c, int kind, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d,
+                                  uint64_t seed, double scale) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_gen_synthetic: null context");
+    if (kind < 0 || kind > 2 || N_total <= 0 || n_rows <= 0 || d <= 0 || row0 < 0 || row0 + n_rows > N_total)
+        CIAO_FAIL(CIAO_ERR_INVALID, "ciao_gen_synthetic: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CIAO_TRY(alloc_common(c, N_total, row0, n_rows, d));
+    if (kind == CIAO_SYNTH_SHARING) {
+        if (row0 != 0 || n_rows != N_total) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "sharing blocks are not sharded");
+        const size_t bytes = (size_t)N_total * c->d_pad * sizeof(double);
+        CUDA_TRY(cudaMalloc(&c->qd, bytes));
+        CUDA_TRY(cudaMalloc(&c->ql, bytes));
+        CIAO_TRY(launch_gen_blocks(c, seed));
+        c->box_lo = -2.0; c->box_hi = 2.0; c->eta = 10.0 * (double)N_total;  // test_sharing.jl:15-16
+        c->loss_kind = CIAO_LOSS_DIAGQUAD;
+    } else {
+        CUDA_TRY(cudaMalloc(&c->rec, (size_t)n_rows * c->ld * sizeof(double)));
+        CIAO_TRY(launch_gen_records(c, kind, seed, scale));
+        c->loss_kind = kind == CIAO_SYNTH_LASSO ? CIAO_LOSS_LS : CIAO_LOSS_LOGISTIC;
+    }
+    return CIAO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// passes
+// ---------------------------------------------------------------------------
+__global__ void finish_kernel(const double *partial, const double *base, double scale, double den, int64_t d_pad, double *out) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= d_pad) return;
+    double v = partial[j];
+    if (den != 1.0) v = __ddiv_rn(v, den);
+    if (scale != 1.0) v = __dmul_rn(scale, v);
+    out[j] = base ? __dadd_rn(base[j], v) : v;
+}
+// out = base + scale·(Σ/den)
+static int run_finish(ciao_ctx *c, const double *base, double scale, double den, double *out) {
+    finish_kernel<<<blocks_for(c->d_pad), 256, 0, c->stream>>>(c->partial, base, scale, den, c->d_pad, out);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_full_gradient(ciao_ctx *c, const double *x, double scale, double *out) {
+    CIAO_TRY(need_rows(c, "ciao_full_gradient", false));
+    if (x) CIAO_TRY(upload_vec(c, CIAO_VEC_X, x));
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X)));
+    CIAO_TRY(run_finish(c, nullptr, scale, 1.0, ctx_vec(c, CIAO_VEC_TMP)));
+    if (out) {
+        CUDA_TRY(cudaMemcpyAsync(out, ctx_vec(c, CIAO_VEC_TMP), (size_t)c->d * sizeof(double), cudaMemcpyDefault, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return CIAO_OK;
+}
+
+extern "C" int ciao_objective(ciao_ctx *c, const double *x, double *f_mean, double *g_val) {
+    CIAO_TRY(need_rows(c, "ciao_objective", false));
+    if (!x || !f_mean) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_objective: null argument");
+    std::vector<double> hx((size_t)c->d);
+    CUDA_TRY(cudaMemcpy(hx.data(), x, (size_t)c->d * sizeof(double), cudaMemcpyDefault));
+    CIAO_TRY(upload_vec(c, CIAO_VEC_X, hx.data()));
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X)));
+    double fs = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(&fs, c->partial + c->d_pad, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *f_mean = fs / (double)c->N_total;
+    if (g_val) {
+        double g = 0.0;
+        if (c->reg.kind == CIAO_REG_NORML1) {
+            for (int64_t j = 0; j < c->d; ++j) g += fabs(hx[j]);
+            g *= c->reg.lambda;
+        }
+        *g_val = g;
+    }
+    return CIAO_OK;
+}
+
+extern "C" int ciao_max_row_sqnorm(ciao_ctx *c, double *out) {
+    CIAO_TRY(need_rows(c, "ciao_max_row_sqnorm", false));
+    if (!out) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_max_row_sqnorm: null output");
+    CIAO_TRY(run_row_pass(c, PASS_NORMS, ctx_vec(c, CIAO_VEC_X)));
+    CUDA_TRY(cudaMemcpyAsync(out, c->partial + c->d_pad, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CIAO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// SVRG / SVRG++
+// ---------------------------------------------------------------------------
+extern "C" int ciao_svrg_init(ciao_ctx *c, const double *x0, double gamma, int plus) {
+    CIAO_TRY(need_rows(c, "ciao_svrg_init", false));
+    if (!x0 || !(gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_svrg_init: x0 is null or γ ≤ 0 (SVRG.jl:39)");
+    c->algo = ALG_SVRG; c->gamma = gamma; c->plus = plus ? 1 : 0;
+    CIAO_TRY(upload_vec(c, CIAO_VEC_Z_FULL, x0));                                  // z_full = copy(x0)  :64
+    CIAO_TRY(copy_vec(c, CIAO_VEC_W, CIAO_VEC_Z_FULL));                            // w = copy(x0)       :66
+    CUDA_TRY(cudaMemsetAsync(ctx_vec(c, CIAO_VEC_Z), 0, (size_t)c->d_pad * 8, c->stream));  // z = 0        :65
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL)));             // :58-63
+    return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
+}
+
+extern "C" int ciao_svrg_epoch(ciao_ctx *c, const int64_t *idx, int64_t m) {
+    CIAO_TRY(need_rows(c, "ciao_svrg_epoch", true));
+    if (c->algo != ALG_SVRG) CIAO_FAIL(CIAO_ERR_STATE, "ciao_svrg_epoch before ciao_svrg_init");
+    if (m <= 0) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_svrg_epoch: m must be positive");
+    const int64_t *raw;
+    CIAO_TRY(fetch_raw_indices(c, idx, m, &raw));
+    CIAO_TRY(launch_prep_indices(c, raw, m, c->N_total, c->idx_prep));
+    CIAO_TRY(run_seq(c, ALG_SVRG, c->idx_prep, m, (double)m));                     // :73-86
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL)));             // :87-92
+    return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
+}
+
+// ---------------------------------------------------------------------------
+// SAGA / SAG
+// ---------------------------------------------------------------------------
+extern "C" int ciao_saga_init(ciao_ctx *c, const double *x0, double gamma, int sag) {
+    CIAO_TRY(need_rows(c, "ciao_saga_init", true));
+    if (!x0 || !(gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_saga_init: x0 is null or γ ≤ 0 (SAGA.jl:37)");
+    c->algo = ALG_SAGA; c->gamma = gamma; c->sag = sag ? 1 : 0;
+    CIAO_TRY(alloc_table(c));
+    CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
+    CIAO_TRY(run_row_pass(c, PASS_SAGA_INIT, ctx_vec(c, CIAO_VEC_X0)));            // :41-45
+    CIAO_TRY(run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV)));  // :47
+    saga_z0_kernel<<<blocks_for(c->d_pad), 256, 0, c->stream>>>(ctx_vec(c, CIAO_VEC_X0), ctx_vec(c, CIAO_VEC_Z), c->d_pad, gamma, c->reg);  // :48
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_saga_steps(ciao_ctx *c, const int64_t *idx, int64_t K) {
+    CIAO_TRY(need_rows(c, "ciao_saga_steps", true));
+    if (c->algo != ALG_SAGA) CIAO_FAIL(CIAO_ERR_STATE, "ciao_saga_steps before ciao_saga_init");
+    if (K == 0) return CIAO_OK;
+    const int64_t *raw;
+    CIAO_TRY(fetch_raw_indices(c, idx, K, &raw));
+    CIAO_TRY(launch_prep_indices(c, raw, K, c->N_total, c->idx_prep));
+    return run_seq(c, ALG_SAGA, c->idx_prep, K, 1.0);
+}
+
+// ---------------------------------------------------------------------------
+// Finito / LFinito
+// ---------------------------------------------------------------------------
+static int prox_vec(ciao_ctx *c, int src, int dst, double gamma) {
+    prox_vec_kernel<<<blocks_for(c->d_pad), 256, 0, c->stream>>>(ctx_vec(c, src), ctx_vec(c, dst), c->d_pad, gamma, c->reg);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_finito_init(ciao_ctx *c, const double *x0, const double *gamma_N, double hat_gamma) {
+    CIAO_TRY(need_rows(c, "ciao_finito_init", true));
+    if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_finito_init: null argument or γ̂ ≤ 0");
+    c->algo = ALG_FINITO; c->hat_gamma = hat_gamma;
+    CIAO_TRY(alloc_table(c));
+    CIAO_TRY(set_gammas(c, gamma_N, true));
+    CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
+    CIAO_TRY(run_row_pass(c, PASS_FINITO_INIT, ctx_vec(c, CIAO_VEC_X0)));          // :76-80
+    CIAO_TRY(run_finish(c, nullptr, hat_gamma, 1.0, ctx_vec(c, CIAO_VEC_AV)));     // :83
+    return prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, hat_gamma);                        // :84
+}
+
+static int batched_indices(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches, int64_t *n_idx_out) {
+    if (!batch_ptr || n_batches < 0) CIAO_FAIL(CIAO_ERR_INVALID, "batch_ptr is null or n_batches < 0");
+    int64_t ends[2] = {0, 0};
+    CUDA_TRY(cudaMemcpy(&ends[0], batch_ptr, sizeof(int64_t), cudaMemcpyDefault));
+    CUDA_TRY(cudaMemcpy(&ends[1], batch_ptr + n_batches, sizeof(int64_t), cudaMemcpyDefault));
+    if (ends[0] != 0 || ends[1] < 0) CIAO_FAIL(CIAO_ERR_INVALID, "batch_ptr must start at 0 and be non-decreasing");
+    const int64_t n_idx = ends[1];
+    *n_idx_out = n_idx;
+    if (n_idx == 0) return CIAO_OK;
+    const int64_t *raw, *ptr_dev;
+    CIAO_TRY(fetch_raw_indices(c, idx, n_idx, &raw));
+    CIAO_TRY(upload_ptr(c, batch_ptr, n_batches + 1, &ptr_dev));
+    CIAO_TRY(launch_prep_indices(c, raw, n_idx, c->N_total, c->idx_prep));
+    return launch_mark_batch_ends(c, ptr_dev, n_batches, n_idx, c->idx_prep);
+}
+
+extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches) {
+    CIAO_TRY(need_rows(c, "ciao_finito_steps", true));
+    if (c->algo != ALG_FINITO) CIAO_FAIL(CIAO_ERR_STATE, "ciao_finito_steps before ciao_finito_init");
+    int64_t n_idx = 0;
+    CIAO_TRY(batched_indices(c, idx, batch_ptr, n_batches, &n_idx));
+    return run_seq(c, ALG_FINITO, c->idx_prep, n_idx, 1.0);
+}
+
+extern "C" int ciao_lfinito_init(ciao_ctx *c, const double *x0, const double *gamma_N, double hat_gamma) {
+    CIAO_TRY(need_rows(c, "ciao_lfinito_init", true));
+    if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_lfinito_init: null argument or γ̂ ≤ 0");
+    c->algo = ALG_LFINITO; c->hat_gamma = hat_gamma;
+    CIAO_TRY(set_gammas(c, gamma_N, true));
+    CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X0)));                 // :68-72
+    CIAO_TRY(run_finish(c, ctx_vec(c, CIAO_VEC_X0), -(hat_gamma / (double)c->N_total), 1.0, ctx_vec(c, CIAO_VEC_AV)));
+    CIAO_TRY(copy_vec(c, CIAO_VEC_Z, CIAO_VEC_AV));                                // placeholders, ctor :33-35
+    return copy_vec(c, CIAO_VEC_Z_FULL, CIAO_VEC_AV);
+}
+
+extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64_t n_batches, int64_t r) {
+    CIAO_TRY(need_rows(c, "ciao_lfinito_outer", true));
+    if (c->algo != ALG_LFINITO) CIAO_FAIL(CIAO_ERR_STATE, "ciao_lfinito_outer before ciao_lfinito_init");
+    if (!batch_order || r <= 0 || n_batches < 0) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_lfinito_outer: bad arguments");
+    const int64_t N = c->N_total, nb = (N + r - 1) / r;
+    // where does the (possibly short) last static batch sit in the order?
+    std::vector<int64_t> order((size_t)n_batches);
+    CUDA_TRY(cudaMemcpy(order.data(), batch_order, (size_t)n_batches * sizeof(int64_t), cudaMemcpyDefault));
+    const int64_t last_len = N - r * (nb - 1);
+    int64_t short_pos = -1, total = 0;
+    for (int64_t jj = 0; jj < n_batches; ++jj) {
+        const int64_t j = order[jj];
+        if (j < 1 || j > nb) CIAO_FAIL(CIAO_ERR_INVALID, "batch_order[%lld] = %lld not in 1..%lld", (long long)jj, (long long)j, (long long)nb);
+        if (j == nb && last_len != r) {
+            if (short_pos >= 0) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "the short last batch may appear once per sweep");
+            short_pos = jj;
+        }
+        total += (j == nb) ? last_len : r;
+    }
+    CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z_FULL, c->hat_gamma));             // :83
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL)));             // :85-88
+    CIAO_TRY(run_finish(c, ctx_vec(c, CIAO_VEC_Z_FULL), -(c->hat_gamma / (double)N), 1.0, ctx_vec(c, CIAO_VEC_AV)));
+    if (total == 0) return CIAO_OK;
+    CIAO_TRY(reserve_idx(c, (size_t)total));
+    const int64_t *order_dev;
+    CIAO_TRY(upload_ptr(c, order.data(), n_batches, &order_dev));
+    CIAO_TRY(launch_expand_batches(c, order_dev, n_batches, r, N, nb, short_pos, c->idx_prep));
+    return run_seq(c, ALG_LFINITO, c->idx_prep, total, 1.0);                       // :91-100
+}
+
+// ---------------------------------------------------------------------------
+// ProShI
+// ---------------------------------------------------------------------------
+static int need_blocks(ciao_ctx *c, const char *who) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "%s: null context", who);
+    if (c->loss_kind != CIAO_LOSS_DIAGQUAD) CIAO_FAIL(CIAO_ERR_STATE, "%s: no sharing problem set (ciao_set_blocks first)", who);
+    CUDA_TRY(cudaSetDevice(c->device));
+    return CIAO_OK;
+}
+
+extern "C" int ciao_proshi_init(ciao_ctx *c, const double *x0, const double *gamma_N, double hat_gamma) {
+    CIAO_TRY(need_blocks(c, "ciao_proshi_init"));
+    if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_proshi_init: null argument or γ̂ ≤ 0");
+    c->algo = 5; c->hat_gamma = hat_gamma;
+    CIAO_TRY(alloc_table(c));
+    CIAO_TRY(set_gammas(c, gamma_N, false));
+    CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
+    CIAO_TRY(run_proshi_init(c, ctx_vec(c, CIAO_VEC_X0)));                         // :76-80
+    CIAO_TRY(run_finish(c, nullptr, 1.0, 1.0, ctx_vec(c, CIAO_VEC_AV)));           // :83
+    return run_proshi_dual(c);                                                     // :84-86
+}
+
+extern "C" int ciao_proshi_steps(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches) {
+    CIAO_TRY(need_blocks(c, "ciao_proshi_steps"));
+    if (c->algo != 5) CIAO_FAIL(CIAO_ERR_STATE, "ciao_proshi_steps before ciao_proshi_init");
+    int64_t n_idx = 0;
+    CIAO_TRY(batched_indices(c, idx, batch_ptr, n_batches, &n_idx));
+    return run_proshi_steps(c, c->idx_prep, n_idx);
+}
+
+extern "C" int ciao_proshi_solution(ciao_ctx *c, double *S_out) {
+    CIAO_TRY(need_blocks(c, "ciao_proshi_solution"));
+    if (c->algo != 5) CIAO_FAIL(CIAO_ERR_STATE, "ciao_proshi_solution before ciao_proshi_init");
+    CIAO_TRY(run_proshi_solution(c));
+    if (S_out) {
+        CUDA_TRY(cudaMemcpy2DAsync(S_out, (size_t)c->d * 8, c->table, (size_t)c->d_pad * 8, (size_t)c->d * 8, (size_t)c->N_total,
+                                   cudaMemcpyDefault, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return CIAO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// state access
+// ---------------------------------------------------------------------------
+extern "C" int ciao_get_vec(ciao_ctx *c, int which, double *out, int64_t len) {
+    if (!c || !out) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_get_vec: null argument");
+    if (!c->vecs) CIAO_FAIL(CIAO_ERR_STATE, "ciao_get_vec: no problem set");
+    if (which < 0 || which > CIAO_VEC_X || len != c->d) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_get_vec: bad vector id or length (d = %lld)", (long long)c->d);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(out, ctx_vec(c, which), (size_t)len * sizeof(double), cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_err_flag(c);
+}
+
+extern "C" int ciao_set_vec(ciao_ctx *c, int which, const double *in, int64_t len) {
+    if (!c || !in) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_vec: null argument");
+    if (!c->vecs) CIAO_FAIL(CIAO_ERR_STATE, "ciao_set_vec: no problem set");
+    if (which < 0 || which > CIAO_VEC_X || len != c->d) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_vec: bad vector id or length");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return upload_vec(c, which, in);
+}
+
+extern "C" int ciao_get_table_rows(ciao_ctx *c, int64_t i0, int64_t n, double *out) {
+    if (!c || !out) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_get_table_rows: null argument");
+    if (!c->table) CIAO_FAIL(CIAO_ERR_STATE, "ciao_get_table_rows: no table (SAGA/Finito/ProShI init first)");
+    if (i0 < 0 || n < 0 || i0 + n > c->n_rows) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_get_table_rows: rows out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return CIAO_OK;
+    CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)c->d * 8, c->table + i0 * c->d_pad, (size_t)c->d_pad * 8, (size_t)c->d * 8, (size_t)n,
+                               cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CIAO_OK;
+}
+
+extern "C" int ciao_table_colsum(ciao_ctx *c, double *out) {
+    if (!c || !out) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_table_colsum: null argument");
+    if (!c->table) CIAO_FAIL(CIAO_ERR_STATE, "ciao_table_colsum: no table");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CIAO_TRY(run_table_colsum(c, c->n_rows));
+    CUDA_TRY(cudaMemcpyAsync(out, c->partial, (size_t)c->d * sizeof(double), cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CIAO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// measurement
+// ---------------------------------------------------------------------------
+extern "C" int ciao_stage_indices(ciao_ctx *c, const int64_t *idx_host, int64_t n) {
+    if (!c || !idx_host || n <= 0) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_stage_indices: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->staged = 0;
+    CIAO_TRY(reserve_idx(c, (size_t)n));
+    CUDA_TRY(cudaMemcpyAsync(c->idx_raw, idx_host, (size_t)n * sizeof(int64_t), cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->staged = n;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_timer_begin(ciao_ctx *c) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->tm_a, c->stream));
+    return CIAO_OK;
+}
+
+extern "C" int ciao_timer_end(ciao_ctx *c, float *ms) {
+    if (!c || !ms) CIAO_FAIL(CIAO_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->tm_b, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->tm_b));
+    CUDA_TRY(cudaEventElapsedTime(ms, c->tm_a, c->tm_b));
+    return CIAO_OK;
+}
+
+extern "C" int ciao_last_timing(ciao_ctx *c, ciao_timing *out) {
+    if (!c || !out) CIAO_FAIL(CIAO_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->pass_timed) CUDA_TRY(cudaEventElapsedTime(&c->timing.last_pass_ms, c->ev_pa, c->ev_pb));
+    if (c->seq_timed) CUDA_TRY(cudaEventElapsedTime(&c->timing.last_seq_ms, c->ev_sa, c->ev_sb));
+    *out = c->timing;
+    return CIAO_OK;
+}

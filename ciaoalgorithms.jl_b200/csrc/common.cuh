@@ -1,0 +1,225 @@
+// common.cuh — context, error plumbing, sm_100a PTX wrappers (mbarrier, TMA bulk
+// copy, cluster/DSMEM) and the operator device functions shared by all kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ciao_cuda.h"
+
+// ---------------------------------------------------------------------------
+// HBM data layout
+//   records : [n_rows][ld]  fp64, ld = d_pad + 4, d_pad = round_up(d, 4)
+//             row record i = [ a_i (d, zero padded to d_pad) | b_i or y_i | λ_i or μ_i | γ_i | 0 ]
+//             → one TMA bulk copy brings a row and its scalars; records are 32-byte aligned.
+//   table   : [N][d_pad]    fp64  (SAGA gradients / Finito, ProShI s_i)
+//   vecs    : [CIAO_NUM_VECS][d_pad]  state vectors
+// ---------------------------------------------------------------------------
+#define CIAO_TAIL 4
+#define CIAO_NUM_VECS 8
+#define CIAO_VEC_SPARE 5
+#define CIAO_VEC_X0 6
+#define CIAO_VEC_TMP 7
+
+#define CIAO_IDX_MASK 0x0000FFFFFFFFFFFFll
+#define CIAO_FLAG_HAZARD (1ll << 62)  // same row was written < prefetch-depth steps ago: reload the table row
+#define CIAO_FLAG_PROX (1ll << 61)    // batch boundary: apply prox_g at this step (after: Finito/ProShI, before: LFinito)
+
+struct RegParams {
+    int kind;
+    double lambda;       // NormL1
+    double lo_s, hi_s;   // IndBox scalar bounds
+    const double *lo_v;  // IndBox vector bounds (device, length d_pad) or nullptr
+    const double *hi_v;
+};
+
+struct ciao_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_pa = nullptr, ev_pb = nullptr, ev_sa = nullptr, ev_sb = nullptr, tm_a = nullptr, tm_b = nullptr;
+    bool pass_timed = false, seq_timed = false;
+    // problem
+    int loss_kind = -1;
+    int64_t N_total = 0, row0 = 0, n_rows = 0, d = 0, d_pad = 0, ld = 0;
+    double *rec = nullptr;             // row records
+    double *qd = nullptr, *ql = nullptr;  // sharing blocks: diag(Q_i), linear term  [N][d_pad]
+    double box_lo = 0, box_hi = 0, eta = 0;
+    RegParams reg{CIAO_REG_ZERO, 0, 0, 0, nullptr, nullptr};
+    double *reg_bounds = nullptr;
+    // state
+    double *vecs = nullptr;
+    double *table = nullptr;
+    double *gamma_dev = nullptr;       // [N]
+    int algo = 0;                      // 1 svrg, 2 saga, 3 finito, 4 lfinito, 5 proshi
+    double gamma = 0, hat_gamma = 0;
+    int plus = 0, sag = 0;
+    // workspace
+    double *ws = nullptr;  size_t ws_bytes = 0;
+    double *partial = nullptr;         // [d_pad + 8] partial d-vector + scalars (allreduce buffer)
+    int64_t *idx_raw = nullptr, *idx_prep = nullptr, *ptr_dev = nullptr;
+    size_t idx_cap = 0, ptr_cap = 0;
+    int64_t staged = 0;
+    int *err_dev = nullptr;
+    double *host_pin = nullptr; size_t host_pin_bytes = 0;
+    // comm
+    void *nccl_comm = nullptr; int rank = 0, world = 1;
+    // tuning
+    int pass_threads = 0, pass_stages = 0, pass_ctas = 0, seq_cluster = 0, seq_threads = 0;
+    ciao_timing timing{0, 0, 0, 0, 0};
+};
+
+void ciao_set_error(const char *fmt, ...);
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            ciao_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? CIAO_ERR_OOM : CIAO_ERR_CUDA;          \
+        }                                                                                     \
+    } while (0)
+#define CIAO_TRY(expr)            \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != CIAO_OK) return _r; \
+    } while (0)
+#define CIAO_FAIL(code, ...)        \
+    do {                            \
+        ciao_set_error(__VA_ARGS__); \
+        return (code);              \
+    } while (0)
+
+static inline double *ctx_vec(ciao_ctx *c, int which) { return c->vecs + (size_t)which * c->d_pad; }
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra W_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// cluster-scope acquire wait (pairs with remote arrive.release.cluster)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra W_%=;\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared::cta, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// same, with an L2 evict-first policy for data that is streamed exactly once
+__device__ __forceinline__ void tma_load_1d_stream(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar,
+                                                   uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v2f64(uint32_t addr, double a, double b) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// operator device functions (ProximalOperators.jl 0.14 semantics)
+// ---------------------------------------------------------------------------
+// prox!(y, g, x, γ) for one coordinate.  NormL1: gl = γλ; y = x + (x ≤ −gl ? gl : (x ≥ gl ? −gl : −x))
+template <int REG>
+__device__ __forceinline__ double prox_elem(double x, double gl, double lo, double hi) {
+    if (REG == CIAO_REG_NORML1) {
+        double adj = (x <= -gl) ? gl : ((x >= gl) ? -gl : -x);
+        return __dadd_rn(x, adj);
+    } else if (REG == CIAO_REG_INDBOX) {
+        return x < lo ? lo : (x > hi ? hi : x);
+    }
+    return x;
+}
+
+// scalar c(u) with ∇f_i(x) = c · a_i  and the value f_i(x), from u = a_i·x
+//   LS:       res = u − b;  ∇ = (a·res)·λ  (two roundings per element, as gradient! does);  f = (λ/2)·res²
+//   logistic: c = −μ y /(1 + exp(y u));  ∇ = a·c;  f = μ·log(1 + 1/exp(y u))
+template <int LOSS>
+__device__ __forceinline__ double loss_coef(double u, double b, double lam) {
+    if (LOSS == CIAO_LOSS_LS) return __dsub_rn(u, b);  // residual; λ applied per element
+    double e = exp(__dmul_rn(b, u));
+    return __ddiv_rn(__dmul_rn(-lam, b), __dadd_rn(1.0, e));
+}
+template <int LOSS>
+__device__ __forceinline__ double loss_value(double u, double b, double lam) {
+    if (LOSS == CIAO_LOSS_LS) {
+        double r = u - b;
+        return (lam / 2) * (r * r);
+    }
+    double e = exp(b * u);
+    return lam * log(1 + 1 / e);
+}
+// one gradient coordinate in the reference's rounding order
+template <int LOSS>
+__device__ __forceinline__ double grad_elem(double a, double c, double lam) {
+    if (LOSS == CIAO_LOSS_LS) return __dmul_rn(__dmul_rn(a, c), lam);
+    return __dmul_rn(a, c);
+}
+#endif  // __CUDACC__

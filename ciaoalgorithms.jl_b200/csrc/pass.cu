@@ -1,0 +1,284 @@
+// pass.cu — K1/K2/K9: the HBM-bound streaming passes over all row records.
+//
+//   PASS_GRAD        out = Σ_i ∇f_i(x)            SVRG_basic.jl:58-63, 88-92; Finito_LFinito.jl:68-72, 85-88
+//   PASS_SAGA_INIT   s_i = ∇f_i(x0); Σ s_i        SAGA_basic.jl:41-47
+//   PASS_FINITO_INIT s_i = x0 − (γ_i/N)∇f_i(x0); Σ s_i/γ_i     Finito_basic.jl:76-83
+//   PASS_NORMS       max_i ‖a_i‖²                 (L_i of test_lasso.jl:55, test_logistic_l1.jl:39)
+// every mode also yields Σ_i f_i(x) (the objective of test_lasso.jl:45) for free.
+//
+// Design: one persistent CTA per SM streams contiguous groups
+// of RPG row records (≈32 KB) through an S-stage shared-memory ring filled by
+// 1-D TMA bulk copies (cp.async.bulk → UBLKCP) with an L2 evict-first policy.
+// A is read from HBM exactly once: a thread owns CPT fixed columns, pulls them
+// from the ring into registers, the row dot a_i·x is reduced warp-shuffle →
+// shared → all threads (fixed order), and the axpy  acc += c_i·a_i  reuses the
+// registers.  CTA partial d-vectors go to a workspace and are summed by
+// reduce_ws_kernel in a fixed order: no floating-point atomics anywhere, so the
+// result is bitwise reproducible run to run (test_lasso.jl:192 `==` tests).
+#include <algorithm>
+
+#include "common.cuh"
+
+enum { PASS_GRAD = 0, PASS_SAGA_INIT = 1, PASS_FINITO_INIT = 2, PASS_NORMS = 3 };
+
+struct PassArgs {
+    const double *rec;   // [n_rows][ld]
+    int64_t n_rows, ld, d_pad;
+    const double *x;     // [d_pad]
+    double *ws;          // [grid][d_pad]
+    double *fws;         // [grid]
+    double *table;       // [n_rows][d_pad] or nullptr
+    double Nd;           // (double) N_total
+    int stages;
+};
+
+template <int CPT, int MODE, int LOSS>
+__global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
+    constexpr int RPG = 16 / CPT;  // rows per group: RPG·CPT = 16 doubles of row data per thread
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const int S = p.stages;
+    const size_t stage_doubles = (size_t)RPG * p.ld;
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    double *red = ring + (size_t)S * stage_doubles;  // [2][RPG][32]
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * RPG * 32);
+
+    const int64_t n_groups = (p.n_rows + RPG - 1) / RPG;
+    const int64_t my_count = (blockIdx.x < n_groups) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    uint64_t policy = 0;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+        policy = l2_policy_evict_first();
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t it) {
+        const int64_t g = blockIdx.x + it * (int64_t)gridDim.x;
+        const int64_t r0 = g * RPG;
+        const int rows = (int)min((int64_t)RPG, p.n_rows - r0);
+        const uint32_t bytes = (uint32_t)(rows * p.ld * sizeof(double));
+        const int slot = (int)(it % S);
+        mbar_arrive_expect_tx(&full[slot], bytes);
+        tma_load_1d_stream(ring + (size_t)slot * stage_doubles, p.rec + r0 * p.ld, bytes, &full[slot], policy);
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < my_count && it < S; ++it) issue(it);
+
+    // this thread's columns: double2 units u = tid + T·k
+    double xr[CPT], acc[CPT];
+    int col[CPT / 2];
+#pragma unroll
+    for (int k = 0; k < CPT / 2; ++k) {
+        col[k] = 2 * (tid + T * k);
+        const bool v = col[k] < p.d_pad;
+        if (!v) col[k] = -1;
+        xr[2 * k] = (v && MODE != PASS_NORMS) ? p.x[col[k]] : 0.0;
+        xr[2 * k + 1] = (v && MODE != PASS_NORMS) ? p.x[col[k] + 1] : 0.0;
+        acc[2 * k] = acc[2 * k + 1] = 0.0;
+    }
+    double fsum = 0.0;  // thread 0: Σ f_i (or max ‖a_i‖²)
+
+    for (int64_t it = 0; it < my_count; ++it) {
+        const int slot = (int)(it % S);
+        const uint32_t parity = (uint32_t)((it / S) & 1);
+        const int par = (int)(it & 1);
+        const int64_t g = blockIdx.x + it * (int64_t)gridDim.x;
+        const int64_t r0 = g * RPG;
+        const int rows = (int)min((int64_t)RPG, p.n_rows - r0);
+        mbar_wait(&full[slot], parity);
+        const double *sp = ring + (size_t)slot * stage_doubles;
+
+        double a[RPG][CPT], pd[RPG], tb[RPG], tl[RPG], tg[RPG];
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+            pd[r] = 0.0;
+            const bool rv = r < rows;
+            const double *rp = sp + (size_t)r * p.ld;
+#pragma unroll
+            for (int k = 0; k < CPT / 2; ++k) {
+                double2 v = make_double2(0.0, 0.0);
+                if (rv && col[k] >= 0) v = *reinterpret_cast<const double2 *>(rp + col[k]);
+                a[r][2 * k] = v.x;
+                a[r][2 * k + 1] = v.y;
+                if (MODE == PASS_NORMS) {
+                    pd[r] = fma(v.x, v.x, pd[r]);
+                    pd[r] = fma(v.y, v.y, pd[r]);
+                } else {
+                    pd[r] = fma(v.x, xr[2 * k], pd[r]);
+                    pd[r] = fma(v.y, xr[2 * k + 1], pd[r]);
+                }
+            }
+            tb[r] = rv ? rp[p.d_pad] : 0.0;
+            tl[r] = rv ? rp[p.d_pad + 1] : 0.0;
+            tg[r] = (rv && MODE == PASS_FINITO_INIT) ? rp[p.d_pad + 2] : 1.0;
+        }
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+            pd[r] = warp_sum(pd[r]);
+            if (lane == 0) red[(par * RPG + r) * 32 + warp] = pd[r];
+        }
+        __syncthreads();
+        // every thread has its slice of the stage in registers: the slot can be refilled
+        if (tid == 0 && it + S < my_count) issue(it + S);
+
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+            double u = 0.0;
+            const double *rr = red + (par * RPG + r) * 32;
+            for (int w = 0; w < W; ++w) u += rr[w];
+            if (r >= rows) continue;
+            if (MODE == PASS_NORMS) {
+                if (tid == 0) fsum = fmax(fsum, u);
+                continue;
+            }
+            const double c = loss_coef<LOSS>(u, tb[r], tl[r]);
+            if (tid == 0) fsum += loss_value<LOSS>(u, tb[r], tl[r]);
+            if (MODE == PASS_GRAD) {
+                const double cc = (LOSS == CIAO_LOSS_LS) ? c * tl[r] : c;
+#pragma unroll
+                for (int e = 0; e < CPT; ++e) acc[e] = fma(cc, a[r][e], acc[e]);
+            } else {
+                const double cg = __ddiv_rn(tg[r], p.Nd);  // γ_i / N
+                double *trow = p.table + (r0 + r) * p.d_pad;
+#pragma unroll
+                for (int k = 0; k < CPT / 2; ++k) {
+                    double s0 = grad_elem<LOSS>(a[r][2 * k], c, tl[r]);
+                    double s1 = grad_elem<LOSS>(a[r][2 * k + 1], c, tl[r]);
+                    if (MODE == PASS_FINITO_INIT) {
+                        s0 = __dsub_rn(xr[2 * k], __dmul_rn(cg, s0));
+                        s1 = __dsub_rn(xr[2 * k + 1], __dmul_rn(cg, s1));
+                        acc[2 * k] += __ddiv_rn(s0, tg[r]);
+                        acc[2 * k + 1] += __ddiv_rn(s1, tg[r]);
+                    } else {
+                        acc[2 * k] += s0;
+                        acc[2 * k + 1] += s1;
+                    }
+                    if (col[k] >= 0) __stcs(reinterpret_cast<double2 *>(trow + col[k]), make_double2(s0, s1));
+                }
+            }
+        }
+    }
+
+    if (MODE != PASS_NORMS) {
+        double *wrow = p.ws + (size_t)blockIdx.x * p.d_pad;
+#pragma unroll
+        for (int k = 0; k < CPT / 2; ++k)
+            if (col[k] >= 0) *reinterpret_cast<double2 *>(wrow + col[k]) = make_double2(acc[2 * k], acc[2 * k + 1]);
+    }
+    if (tid == 0) p.fws[blockIdx.x] = fsum;
+}
+
+// second stage: fixed-order sum of the CTA partials.  out[j] = Σ_b ws[b][j];  fout = Σ_b fws[b] (or max)
+__global__ void reduce_ws_kernel(const double *ws, const double *fws, int G, int64_t d_pad, double *out, double *fout,
+                                 int fmax_mode, int with_vec) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (with_vec && j < d_pad) {
+        double s = 0.0;
+        for (int b = 0; b < G; ++b) s += ws[(size_t)b * d_pad + j];
+        out[j] = s;
+    }
+    if (j == 0) {
+        double f = 0.0;
+        for (int b = 0; b < G; ++b) f = fmax_mode ? fmax(f, fws[b]) : f + fws[b];
+        *fout = f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+template <int CPT, int MODE, int LOSS>
+static int launch_one(ciao_ctx *c, const PassArgs &a, int grid, int T, size_t smem) {
+    auto kern = row_pass_kernel<CPT, MODE, LOSS>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, T, smem, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return CIAO_OK;
+}
+
+template <int CPT>
+static int launch_cpt(ciao_ctx *c, int mode, const PassArgs &a, int grid, int T, size_t smem) {
+    const bool ls = c->loss_kind == CIAO_LOSS_LS;
+    switch (mode) {
+        case PASS_GRAD:
+            return ls ? launch_one<CPT, PASS_GRAD, CIAO_LOSS_LS>(c, a, grid, T, smem)
+                      : launch_one<CPT, PASS_GRAD, CIAO_LOSS_LOGISTIC>(c, a, grid, T, smem);
+        case PASS_SAGA_INIT:
+            return ls ? launch_one<CPT, PASS_SAGA_INIT, CIAO_LOSS_LS>(c, a, grid, T, smem)
+                      : launch_one<CPT, PASS_SAGA_INIT, CIAO_LOSS_LOGISTIC>(c, a, grid, T, smem);
+        case PASS_FINITO_INIT:
+            return ls ? launch_one<CPT, PASS_FINITO_INIT, CIAO_LOSS_LS>(c, a, grid, T, smem)
+                      : launch_one<CPT, PASS_FINITO_INIT, CIAO_LOSS_LOGISTIC>(c, a, grid, T, smem);
+        default:
+            return launch_one<CPT, PASS_NORMS, CIAO_LOSS_LS>(c, a, grid, T, smem);
+    }
+}
+
+int ciao_comm_allreduce(ciao_ctx *c, double *buf, int64_t count, int op_max);  // comm.cu
+
+// Runs one streaming pass.  Result: c->partial[0..d_pad) = Σ (unscaled, all ranks), c->partial[d_pad] = Σ f_i (or max).
+int run_row_pass(ciao_ctx *c, int mode, const double *x_dev) {
+    if (c->loss_kind != CIAO_LOSS_LS && c->loss_kind != CIAO_LOSS_LOGISTIC)
+        CIAO_FAIL(CIAO_ERR_STATE, "row pass: no row problem set (ciao_set_rows / ciao_gen_synthetic first)");
+    const int64_t d_pad = c->d_pad;
+    int T_target = c->pass_threads > 0 ? c->pass_threads : 256;
+    int cpt = 2;
+    while (cpt < 16 && (d_pad + cpt - 1) / cpt > T_target) cpt *= 2;
+    int64_t Tn = ((d_pad + cpt - 1) / cpt + 31) / 32 * 32;
+    if (Tn > 512) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "row pass: d = %lld exceeds the engine limit 8192", (long long)c->d);
+    const int T = (int)Tn;
+    const int rpg = 16 / cpt;
+    const size_t stage_bytes = (size_t)rpg * c->ld * sizeof(double);
+    const int ctas_per_sm = c->pass_ctas > 0 ? c->pass_ctas : 1;
+    const size_t fixed = 2 * rpg * 32 * sizeof(double) + 16 * sizeof(uint64_t) + 256;
+    const size_t budget = (size_t)(227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
+    int S = c->pass_stages > 0 ? c->pass_stages : 8;
+    while (S > 1 && (size_t)S * stage_bytes + fixed > budget) --S;
+    if ((size_t)S * stage_bytes + fixed > budget) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "row pass: stage does not fit shared memory");
+    if (S > 16) S = 16;
+    const size_t smem = (size_t)S * stage_bytes + fixed;
+    const int64_t n_groups = (c->n_rows + rpg - 1) / rpg;
+    int grid = (int)std::min<int64_t>(n_groups, (int64_t)c->num_sms * ctas_per_sm);
+    if (grid < 1) grid = 1;
+
+    const size_t need = ((size_t)grid * d_pad + grid + 16) * sizeof(double);
+    if (need > c->ws_bytes) {
+        if (c->ws) cudaFree(c->ws);
+        c->ws = nullptr;
+        CUDA_TRY(cudaMalloc(&c->ws, need));
+        c->ws_bytes = need;
+    }
+    PassArgs a;
+    a.rec = c->rec; a.n_rows = c->n_rows; a.ld = c->ld; a.d_pad = d_pad; a.x = x_dev;
+    a.ws = c->ws; a.fws = c->ws + (size_t)grid * d_pad; a.table = c->table;
+    a.Nd = (double)c->N_total; a.stages = S;
+    if ((mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT) && !c->table)
+        CIAO_FAIL(CIAO_ERR_STATE, "table init pass without a table");
+
+    CUDA_TRY(cudaEventRecord(c->ev_pa, c->stream));
+    int rc;
+    switch (cpt) {
+        case 2: rc = launch_cpt<2>(c, mode, a, grid, T, smem); break;
+        case 4: rc = launch_cpt<4>(c, mode, a, grid, T, smem); break;
+        case 8: rc = launch_cpt<8>(c, mode, a, grid, T, smem); break;
+        default: rc = launch_cpt<16>(c, mode, a, grid, T, smem); break;
+    }
+    CIAO_TRY(rc);
+    CUDA_TRY(cudaEventRecord(c->ev_pb, c->stream));
+    const int nb = (int)((d_pad + 255) / 256);
+    reduce_ws_kernel<<<nb, 256, 0, c->stream>>>(a.ws, a.fws, grid, d_pad, c->partial, c->partial + d_pad,
+                                                mode == PASS_NORMS, mode != PASS_NORMS);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 2;
+    c->pass_timed = true;
+    c->timing.last_pass_bytes = (int64_t)c->n_rows * c->ld * 8 +
+                                ((mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT) ? (int64_t)c->n_rows * d_pad * 8 : 0);
+    if (c->world > 1) {
+        if (mode == PASS_NORMS) {
+            CIAO_TRY(ciao_comm_allreduce(c, c->partial + d_pad, 1, 1));
+        } else {
+            CIAO_TRY(ciao_comm_allreduce(c, c->partial, d_pad + 1, 0));
+        }
+    }
+    return CIAO_OK;
+}

@@ -1,0 +1,257 @@
+// proshi.cu — K7: ProShI block updates for the sharing problem
+//   (1/N) Σ f_i(x_i) + g(Σ x_i),   f_i = ½x'diag(q_i)x + c_i'x + (η/2)dist²(x,[lo,hi])   (test_sharing.jl:15-22)
+//
+//   proshi_init_kernel      s_i = x0 − (γ_i/N)∇f_i(x0);  Σ s_i           ProShI_basic.jl:76-83
+//   proshi_steps_kernel     block steps + dual update                     ProShI_basic.jl:111-123
+//   proshi_solution_kernel  s_i += γ_i z  IN PLACE                        ProShI_basic.jl:127-132
+//
+// Design.  With a diagonal Q_i the block update has no coupling
+// between coordinates: every column j of (s, av, z) evolves independently given the
+// index sequence.  proshi_steps_kernel therefore gives each thread two columns, keeps
+// z_j and av_j in registers for the whole call and walks the host-generated index
+// sequence with a P-deep register prefetch of (γ_i, q_i, c_i, s_i) — no barrier, no
+// reduction, no kernel launch per step; the n columns are spread over many SMs so
+// the gathers of different columns overlap.
+#include <algorithm>
+
+#include "common.cuh"
+
+struct ProshiArgs {
+    const double *qd, *ql;  // [N][n_pad]
+    double *table;          // [N][n_pad]
+    const double *gam;      // [N]
+    const int64_t *idx;     // prepared
+    int64_t K, N, n_pad;
+    double *v_z, *v_av;
+    double box_lo, box_hi, eta, Nd, hat_gamma;
+    RegParams reg;
+};
+
+__device__ __forceinline__ double proshi_grad(double q, double c, double s, double lo, double hi, double eta) {
+    // Sum(Quadratic, SqrDistL2): (q·s + c) + η·(s − Π_box s)
+    const double g1 = __dadd_rn(__dmul_rn(q, s), c);
+    const double pr = s < lo ? lo : (s > hi ? hi : s);
+    const double g2 = __dmul_rn(eta, __dsub_rn(s, pr));
+    return __dadd_rn(g1, g2);
+}
+
+__device__ __forceinline__ double proshi_prox_rt(const RegParams &r, double x, double gl, double lo, double hi) {
+    if (r.kind == CIAO_REG_NORML1) return prox_elem<CIAO_REG_NORML1>(x, gl, lo, hi);
+    if (r.kind == CIAO_REG_INDBOX) return prox_elem<CIAO_REG_INDBOX>(x, gl, lo, hi);
+    return x;
+}
+
+constexpr int PROSHI_P = 8;
+
+__global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
+    const int64_t col = 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+    if (col >= p.n_pad) return;
+    double z0 = p.v_z[col], z1 = p.v_z[col + 1], av0 = p.v_av[col], av1 = p.v_av[col + 1];
+    const double lo0 = p.reg.lo_v ? p.reg.lo_v[col] : p.reg.lo_s, lo1 = p.reg.lo_v ? p.reg.lo_v[col + 1] : p.reg.lo_s;
+    const double hi0 = p.reg.hi_v ? p.reg.hi_v[col] : p.reg.hi_s, hi1 = p.reg.hi_v ? p.reg.hi_v[col + 1] : p.reg.hi_s;
+    const double gl = p.hat_gamma * p.reg.lambda;
+
+    int64_t iq[PROSHI_P];
+    double gq[PROSHI_P];
+    double2 qq[PROSHI_P], cq[PROSHI_P], sq[PROSHI_P];
+    auto fetch = [&](int j, int64_t pidx) {
+        const int64_t i = pidx & CIAO_IDX_MASK;
+        iq[j] = pidx;
+        gq[j] = __ldg(p.gam + i);
+        qq[j] = __ldg(reinterpret_cast<const double2 *>(p.qd + i * p.n_pad + col));
+        cq[j] = __ldg(reinterpret_cast<const double2 *>(p.ql + i * p.n_pad + col));
+        sq[j] = __ldcg(reinterpret_cast<const double2 *>(p.table + i * p.n_pad + col));
+    };
+#pragma unroll
+    for (int j = 0; j < PROSHI_P; ++j)
+        if (j < p.K) fetch(j, __ldg(p.idx + j));
+    int64_t in1 = (PROSHI_P < p.K) ? __ldg(p.idx + PROSHI_P) : 0;
+
+    for (int64_t k0 = 0; k0 < p.K; k0 += PROSHI_P) {
+#pragma unroll
+        for (int j = 0; j < PROSHI_P; ++j) {
+            const int64_t k = k0 + j;
+            if (k >= p.K) break;
+            const int64_t ik = iq[j];
+            double2 *srow = reinterpret_cast<double2 *>(p.table + (ik & CIAO_IDX_MASK) * p.n_pad + col);
+            double2 s = sq[j];
+            if (ik & CIAO_FLAG_HAZARD) s = __ldcg(srow);
+            const double gi = gq[j];
+            const double cneg = -__ddiv_rn(gi, p.Nd);
+            // ProShI_basic.jl:113-119
+            av0 = __dsub_rn(av0, s.x);
+            av1 = __dsub_rn(av1, s.y);
+            const double x0 = __dadd_rn(s.x, __dmul_rn(gi, z0)), x1 = __dadd_rn(s.y, __dmul_rn(gi, z1));
+            double t0 = __dmul_rn(proshi_grad(qq[j].x, cq[j].x, x0, p.box_lo, p.box_hi, p.eta), cneg);
+            double t1 = __dmul_rn(proshi_grad(qq[j].y, cq[j].y, x1, p.box_lo, p.box_hi, p.eta), cneg);
+            t0 = __dadd_rn(t0, x0);
+            t1 = __dadd_rn(t1, x1);
+            av0 = __dadd_rn(av0, t0);
+            av1 = __dadd_rn(av1, t1);
+            __stcg(srow, make_double2(t0, t1));
+            if (ik & CIAO_FLAG_PROX) {  // :121-123
+                z0 = __ddiv_rn(__dsub_rn(proshi_prox_rt(p.reg, av0, gl, lo0, hi0), av0), p.hat_gamma);
+                z1 = __ddiv_rn(__dsub_rn(proshi_prox_rt(p.reg, av1, gl, lo1, hi1), av1), p.hat_gamma);
+            }
+            if (k + PROSHI_P < p.K) fetch(j, in1);
+            in1 = (k + PROSHI_P + 1 < p.K) ? __ldg(p.idx + k + PROSHI_P + 1) : 0;
+        }
+    }
+    p.v_z[col] = z0; p.v_z[col + 1] = z1;
+    p.v_av[col] = av0; p.v_av[col + 1] = av1;
+}
+
+// grid (row groups, column chunks of 512); ws[blockIdx.x][n_pad] = partial Σ s_i
+__global__ void __launch_bounds__(256) proshi_init_kernel(const double *qd, const double *ql, const double *gam,
+                                                          const double *x0, double *table, double *ws, int64_t N,
+                                                          int64_t n_pad, double box_lo, double box_hi, double eta,
+                                                          double Nd) {
+    const int64_t col = 2 * (blockIdx.y * (int64_t)blockDim.x + threadIdx.x);
+    if (col >= n_pad) return;
+    const double xa = x0[col], xb = x0[col + 1];
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
+        const double2 q = __ldcs(reinterpret_cast<const double2 *>(qd + i * n_pad + col));
+        const double2 c = __ldcs(reinterpret_cast<const double2 *>(ql + i * n_pad + col));
+        const double cg = __ddiv_rn(__ldg(gam + i), Nd);
+        const double s0 = __dsub_rn(xa, __dmul_rn(cg, proshi_grad(q.x, c.x, xa, box_lo, box_hi, eta)));
+        const double s1 = __dsub_rn(xb, __dmul_rn(cg, proshi_grad(q.y, c.y, xb, box_lo, box_hi, eta)));
+        __stcs(reinterpret_cast<double2 *>(table + i * n_pad + col), make_double2(s0, s1));
+        a0 += s0;
+        a1 += s1;
+    }
+    ws[(size_t)blockIdx.x * n_pad + col] = a0;
+    ws[(size_t)blockIdx.x * n_pad + col + 1] = a1;
+}
+
+// ws[blockIdx.x][n_pad] = partial Σ_i table_i   (sum(x_proshi), test_sharing.jl:42)
+__global__ void __launch_bounds__(256) table_colsum_kernel(const double *table, double *ws, int64_t N, int64_t n_pad) {
+    const int64_t col = 2 * (blockIdx.y * (int64_t)blockDim.x + threadIdx.x);
+    if (col >= n_pad) return;
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
+        const double2 s = __ldcs(reinterpret_cast<const double2 *>(table + i * n_pad + col));
+        a0 += s.x;
+        a1 += s.y;
+    }
+    ws[(size_t)blockIdx.x * n_pad + col] = a0;
+    ws[(size_t)blockIdx.x * n_pad + col + 1] = a1;
+}
+
+__global__ void __launch_bounds__(256) proshi_solution_kernel(double *table, const double *gam, const double *z, int64_t N,
+                                                              int64_t n_pad) {
+    const int64_t col = 2 * (blockIdx.y * (int64_t)blockDim.x + threadIdx.x);
+    if (col >= n_pad) return;
+    const double z0 = z[col], z1 = z[col + 1];
+    for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
+        double2 *sp = reinterpret_cast<double2 *>(table + i * n_pad + col);
+        double2 s = *sp;
+        const double gi = __ldg(gam + i);
+        s.x = __dadd_rn(s.x, __dmul_rn(gi, z0));
+        s.y = __dadd_rn(s.y, __dmul_rn(gi, z1));
+        *sp = s;
+    }
+}
+
+// z = (prox_g(av, γ̂) − av)/γ̂     ProShI_basic.jl:84-86
+__global__ void proshi_dual_kernel(const double *av, double *z, int64_t n_pad, double hat_gamma, RegParams reg) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n_pad) return;
+    const double lo = reg.lo_v ? reg.lo_v[j] : reg.lo_s, hi = reg.hi_v ? reg.hi_v[j] : reg.hi_s;
+    const double a = av[j];
+    z[j] = __ddiv_rn(__dsub_rn(proshi_prox_rt(reg, a, hat_gamma * reg.lambda, lo, hi), a), hat_gamma);
+}
+
+static int ws_reserve(ciao_ctx *c, size_t need) {
+    if (need > c->ws_bytes) {
+        if (c->ws) cudaFree(c->ws);
+        c->ws = nullptr;
+        c->ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&c->ws, need));
+        c->ws_bytes = need;
+    }
+    return CIAO_OK;
+}
+
+static void grid2d(ciao_ctx *c, int64_t N, int64_t n_pad, dim3 *grid, int *G) {
+    const int chunks = (int)((n_pad / 2 + 255) / 256);
+    int rows = std::max(1, c->num_sms * 8 / chunks);
+    if (rows > N) rows = (int)N;
+    *grid = dim3(rows, chunks);
+    *G = rows;
+}
+
+// leaves Σ (column sums) in c->partial[0..n_pad)
+static int reduce_partials(ciao_ctx *c, int G) {
+    const int nb = (int)((c->d_pad + 255) / 256);
+    reduce_ws_kernel<<<nb, 256, 0, c->stream>>>(c->ws, c->ws, G, c->d_pad, c->partial, c->partial + c->d_pad, 0, 1);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+int run_proshi_init(ciao_ctx *c, const double *x0_dev) {
+    dim3 grid; int G;
+    grid2d(c, c->N_total, c->d_pad, &grid, &G);
+    CIAO_TRY(ws_reserve(c, ((size_t)G * c->d_pad + 16) * sizeof(double)));
+    CUDA_TRY(cudaEventRecord(c->ev_pa, c->stream));
+    proshi_init_kernel<<<grid, 256, 0, c->stream>>>(c->qd, c->ql, c->gamma_dev, x0_dev, c->table, c->ws, c->N_total,
+                                                    c->d_pad, c->box_lo, c->box_hi, c->eta, (double)c->N_total);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev_pb, c->stream));
+    c->timing.launches += 1;
+    c->timing.last_pass_bytes = c->N_total * c->d_pad * 24;
+    c->pass_timed = true;
+    return reduce_partials(c, G);
+}
+
+int run_proshi_dual(ciao_ctx *c) {
+    const int nb = (int)((c->d_pad + 255) / 256);
+    proshi_dual_kernel<<<nb, 256, 0, c->stream>>>(ctx_vec(c, CIAO_VEC_AV), ctx_vec(c, CIAO_VEC_Z), c->d_pad, c->hat_gamma, c->reg);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K) {
+    if (K <= 0) return CIAO_OK;
+    ProshiArgs a;
+    a.qd = c->qd; a.ql = c->ql; a.table = c->table; a.gam = c->gamma_dev; a.idx = idx_prepared;
+    a.K = K; a.N = c->N_total; a.n_pad = c->d_pad;
+    a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_av = ctx_vec(c, CIAO_VEC_AV);
+    a.box_lo = c->box_lo; a.box_hi = c->box_hi; a.eta = c->eta; a.Nd = (double)c->N_total; a.hat_gamma = c->hat_gamma;
+    a.reg = c->reg;
+    const int T = c->seq_threads > 0 ? std::min(c->seq_threads, 64) : 32;
+    const int grid = (int)((c->d_pad / 2 + T - 1) / T);
+    CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
+    proshi_steps_kernel<<<grid, T, 0, c->stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));
+    c->timing.launches += 1;
+    c->timing.last_seq_steps = K;
+    c->seq_timed = true;
+    return CIAO_OK;
+}
+
+int run_proshi_solution(ciao_ctx *c) {
+    dim3 grid; int G;
+    grid2d(c, c->N_total, c->d_pad, &grid, &G);
+    CUDA_TRY(cudaEventRecord(c->ev_pa, c->stream));
+    proshi_solution_kernel<<<grid, 256, 0, c->stream>>>(c->table, c->gamma_dev, ctx_vec(c, CIAO_VEC_Z), c->N_total, c->d_pad);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev_pb, c->stream));
+    c->timing.launches += 1;
+    c->timing.last_pass_bytes = c->N_total * c->d_pad * 16;
+    c->pass_timed = true;
+    return CIAO_OK;
+}
+
+int run_table_colsum(ciao_ctx *c, int64_t n_rows) {
+    dim3 grid; int G;
+    grid2d(c, n_rows, c->d_pad, &grid, &G);
+    CIAO_TRY(ws_reserve(c, ((size_t)G * c->d_pad + 16) * sizeof(double)));
+    table_colsum_kernel<<<grid, 256, 0, c->stream>>>(c->table, c->ws, n_rows, c->d_pad);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return reduce_partials(c, G);
+}

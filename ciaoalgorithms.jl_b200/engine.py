@@ -1,0 +1,194 @@
+"""Thin object wrapper over one ``ciao_ctx`` (one GPU).  Every method is one C-ABI call."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import CiaoError, check, f64arr, i64arr, ptr  # noqa: F401
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = L.load()
+        self.h = C.c_void_p()
+        check(self.lib.ciao_create(C.byref(self.h), device))
+        self.device = device
+        self.N = self.d = self.n_rows = 0
+
+    # -- lifetime -------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.ciao_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        check(self.lib.ciao_sync(self.h))
+
+    # -- problem --------------------------------------------------------------
+    def set_rows(self, loss_kind, A, b, scale=1.0, N_total=None, row0=0):
+        A = f64arr(A)
+        n_rows, d = A.shape
+        b = f64arr(b)
+        assert b.shape == (n_rows,)
+        sv = None if np.isscalar(scale) else f64arr(scale)
+        N_total = n_rows if N_total is None else N_total
+        check(self.lib.ciao_set_rows(self.h, loss_kind, N_total, row0, n_rows, d, ptr(A), A.strides[0] // 8, ptr(b),
+                                     ptr(sv), float(scale) if sv is None else 0.0))
+        self.N, self.d, self.n_rows = N_total, d, n_rows
+
+    def set_blocks(self, Qdiag, qlin, box, eta):
+        Q, q = f64arr(Qdiag), f64arr(qlin)
+        N, n = Q.shape
+        assert q.shape == (N, n)
+        check(self.lib.ciao_set_blocks(self.h, N, n, ptr(Q), n, ptr(q), n, float(box[0]), float(box[1]), float(eta)))
+        self.N, self.d, self.n_rows = N, n, N
+
+    def set_reg(self, kind, *params):
+        if kind == L.REG_INDBOX and len(params) == 2 and (np.ndim(params[0]) > 0 or np.ndim(params[1]) > 0):
+            lo = np.broadcast_to(np.asarray(params[0], dtype=np.float64), (self.d,))
+            hi = np.broadcast_to(np.asarray(params[1], dtype=np.float64), (self.d,))
+            p = f64arr(np.concatenate([lo, hi]))
+        else:
+            p = f64arr(np.asarray(params, dtype=np.float64).reshape(-1))
+        check(self.lib.ciao_set_reg(self.h, kind, ptr(p) if p.size else None, p.size))
+
+    def gen_synthetic(self, kind, N_total, d, seed, scale=1.0, row0=0, n_rows=None):
+        n_rows = N_total if n_rows is None else n_rows
+        check(self.lib.ciao_gen_synthetic(self.h, kind, N_total, row0, n_rows, d, seed, float(scale)))
+        self.N, self.d, self.n_rows = N_total, d, n_rows
+
+    @staticmethod
+    def gen_host(kind, d, seed, row0, n_rows):
+        A = np.empty((n_rows, d))
+        rhs = np.empty(n_rows)
+        check(L.load().ciao_gen_host(kind, d, seed, row0, n_rows, ptr(A), ptr(rhs)))
+        return A, (None if kind == L.SYNTH_SHARING else rhs)
+
+    # -- multi-GPU -------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(L.load().ciao_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(uid, 128)
+        check(self.lib.ciao_comm_init(self.h, buf, rank, world))
+
+    # -- passes ----------------------------------------------------------------
+    def full_gradient(self, x=None, scale=1.0, out=True):
+        xv = None if x is None else f64arr(x)
+        o = np.empty(self.d) if out else None
+        check(self.lib.ciao_full_gradient(self.h, ptr(xv), float(scale), ptr(o)))
+        return o
+
+    def objective(self, x):
+        xv = f64arr(x)
+        f, g = C.c_double(), C.c_double()
+        check(self.lib.ciao_objective(self.h, ptr(xv), C.byref(f), C.byref(g)))
+        return f.value, g.value
+
+    def max_row_sqnorm(self):
+        o = C.c_double()
+        check(self.lib.ciao_max_row_sqnorm(self.h, C.byref(o)))
+        return o.value
+
+    # -- solvers ---------------------------------------------------------------
+    def svrg_init(self, x0, gamma, plus=False):
+        check(self.lib.ciao_svrg_init(self.h, ptr(f64arr(x0)), float(gamma), int(plus)))
+
+    def svrg_epoch(self, idx, m=None):
+        """idx: int64 numpy array (host), an int device address, or None (staged indices)."""
+        if isinstance(idx, np.ndarray):
+            idx = i64arr(idx)
+            m = len(idx) if m is None else m
+        check(self.lib.ciao_svrg_epoch(self.h, ptr(idx), int(m)))
+
+    def saga_init(self, x0, gamma, sag=False):
+        check(self.lib.ciao_saga_init(self.h, ptr(f64arr(x0)), float(gamma), int(sag)))
+
+    def saga_steps(self, idx, K=None):
+        if isinstance(idx, np.ndarray):
+            idx = i64arr(idx)
+            K = len(idx) if K is None else K
+        check(self.lib.ciao_saga_steps(self.h, ptr(idx), int(K)))
+
+    def finito_init(self, x0, gamma_N, hat_gamma):
+        check(self.lib.ciao_finito_init(self.h, ptr(f64arr(x0)), ptr(f64arr(gamma_N)), float(hat_gamma)))
+
+    def finito_steps(self, idx, batch_ptr):
+        idx, bp = (i64arr(idx) if isinstance(idx, np.ndarray) else idx), i64arr(batch_ptr)
+        check(self.lib.ciao_finito_steps(self.h, ptr(idx), ptr(bp), len(bp) - 1))
+
+    def lfinito_init(self, x0, gamma_N, hat_gamma):
+        check(self.lib.ciao_lfinito_init(self.h, ptr(f64arr(x0)), ptr(f64arr(gamma_N)), float(hat_gamma)))
+
+    def lfinito_outer(self, batch_order, r):
+        o = i64arr(batch_order)
+        check(self.lib.ciao_lfinito_outer(self.h, ptr(o), len(o), int(r)))
+
+    def proshi_init(self, x0, gamma_N, hat_gamma):
+        check(self.lib.ciao_proshi_init(self.h, ptr(f64arr(x0)), ptr(f64arr(gamma_N)), float(hat_gamma)))
+
+    def proshi_steps(self, idx, batch_ptr):
+        idx, bp = (i64arr(idx) if isinstance(idx, np.ndarray) else idx), i64arr(batch_ptr)
+        check(self.lib.ciao_proshi_steps(self.h, ptr(idx), ptr(bp), len(bp) - 1))
+
+    def proshi_solution(self, out=None):
+        check(self.lib.ciao_proshi_solution(self.h, ptr(out)))
+        return out
+
+    # -- state -------------------------------------------------------------------
+    def get_vec(self, which, out=None):
+        out = np.empty(self.d) if out is None else out
+        check(self.lib.ciao_get_vec(self.h, which, ptr(out), self.d))
+        return out
+
+    def set_vec(self, which, x):
+        check(self.lib.ciao_set_vec(self.h, which, ptr(f64arr(x)), self.d))
+
+    def get_table_rows(self, i0=0, n=None, out=None):
+        n = self.n_rows - i0 if n is None else n
+        out = np.empty((n, self.d)) if out is None else out
+        check(self.lib.ciao_get_table_rows(self.h, i0, n, ptr(out)))
+        return out
+
+    def table_colsum(self):
+        o = np.empty(self.d)
+        check(self.lib.ciao_table_colsum(self.h, ptr(o)))
+        return o
+
+    # -- measurement ---------------------------------------------------------------
+    def stage_indices(self, idx):
+        idx = i64arr(idx)
+        check(self.lib.ciao_stage_indices(self.h, ptr(idx), len(idx)))
+
+    def timer_begin(self):
+        check(self.lib.ciao_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        check(self.lib.ciao_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def last_timing(self) -> L.Timing:
+        t = L.Timing()
+        check(self.lib.ciao_last_timing(self.h, C.byref(t)))
+        return t
+
+    def set_tuning(self, pass_threads=0, pass_stages=0, pass_ctas_per_sm=0, seq_cluster=0, seq_threads=0):
+        check(self.lib.ciao_set_tuning(self.h, pass_threads, pass_stages, pass_ctas_per_sm, seq_cluster, seq_threads))

@@ -1,0 +1,392 @@
+"""T2/T3 — the CUDA engine (through the C ABI) against the CPU oracle on the same
+inputs and the same host-generated index sequences; golden vectors of the
+reference's tests; bitwise run-to-run determinism; error behaviour.
+
+Tolerances (BASELINE.json north_star): rel. objective ≤ 1e-8, ‖x − x_ref‖/‖x_ref‖ ≤ 1e-6
+after K epochs.  The per-pass / few-step checks below use much tighter bounds
+(the only differences are summation order and FMA contraction in the dots).
+"""
+import numpy as np
+import pytest
+
+import fixtures
+from oracle import oracle as orc
+from ciaoalgorithms_jl_b200 import _lib as L
+from ciaoalgorithms_jl_b200.engine import CiaoError, Engine
+from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, LFinitoSweeper, csr
+
+pytestmark = pytest.mark.gpu
+
+REL_ITERATE = 1e-6     # north_star tolerance after K epochs
+REL_OBJECTIVE = 1e-8
+TIGHT = 1e-11          # single pass / short runs: reduction-order noise only
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+# ----------------------------------------------------------------------------
+def make_rows(kind, N, d, seed, lam_reg, scale=None):
+    """Synthetic row problem on both sides: oracle (host arrays) and engine (device generator)."""
+    syn = orc.SYN_LASSO if kind == orc.LOSS_LS else orc.SYN_LOGISTIC
+    A, rhs = orc.gen_rows(syn, d, seed, 0, N)
+    sc = float(N) if (scale is None and kind == orc.LOSS_LS) else (1.0 if scale is None else scale)
+    p = orc.Problem(kind, A, rhs, np.full(N, sc)).set_reg(orc.REG_NORML1, lam=lam_reg)
+    e = Engine(0)
+    e.gen_synthetic(L.SYNTH_LASSO if kind == orc.LOSS_LS else L.SYNTH_LOGISTIC, N, d, seed, scale=sc)
+    e.set_reg(L.REG_NORML1, lam_reg)
+    return p, e
+
+
+def fixture_rows(which):
+    if which == "lasso":
+        fx = fixtures.planted_lasso(0)
+        p = orc.Problem(orc.LOSS_LS, fx["A"], fx["b"], fx["scale"]).set_reg(orc.REG_NORML1, lam=fx["lam"])
+        e = Engine(0)
+        e.set_rows(L.LOSS_LS, fx["A"], fx["b"], fx["scale"])
+    else:
+        fx = fixtures.logistic_l1()
+        p = orc.Problem(orc.LOSS_LOGISTIC, fx["A"], fx["y"], fx["mu"]).set_reg(orc.REG_NORML1, lam=fx["lam"])
+        e = Engine(0)
+        e.set_rows(L.LOSS_LOGISTIC, fx["A"], fx["y"], fx["mu"])
+    e.set_reg(L.REG_NORML1, fx["lam"])
+    return fx, p, e
+
+
+# ----------------------------------------------------------------------------
+# K1 / K9 / K10: streaming passes and the device generator
+@pytest.mark.parametrize("kind", [orc.LOSS_LS, orc.LOSS_LOGISTIC])
+@pytest.mark.parametrize("N,d", [(7, 3), (1000, 64), (999, 130), (4096, 1024), (1536, 4096), (300, 8192)])
+def test_full_gradient_and_objective(kind, N, d):
+    p, e = make_rows(kind, N, d, 0x5EED0000 + d, lam_reg=0.1, scale=1.0)
+    x = np.random.default_rng(d).standard_normal(d) / np.sqrt(d)
+    g_ref = p.full_gradient(x, 1.0 / N)
+    g = e.full_gradient(x, 1.0 / N)
+    assert rel(g, g_ref) < TIGHT
+    f_ref, r_ref = p.objective(x)
+    f, r = e.objective(x)
+    assert abs(f - f_ref) <= 1e-12 * abs(f_ref) and abs(r - r_ref) <= 1e-13 * abs(r_ref)
+    assert abs(e.max_row_sqnorm() - p.max_row_sqnorm()) <= 1e-12 * p.max_row_sqnorm()
+    # bitwise reproducible (no floating-point atomics)
+    assert np.array_equal(g, e.full_gradient(x, 1.0 / N))
+    e.close()
+
+
+def test_full_gradient_host_rows_match_generated_rows():
+    """ciao_set_rows (host upload, lda > d) and the device generator produce the same problem."""
+    N, d = 513, 96
+    A, b = Engine.gen_host(L.SYNTH_LASSO, d, 77, 0, N)
+    A2, b2 = orc.gen_rows(orc.SYN_LASSO, d, 77, 0, N)
+    assert np.array_equal(A, A2) and np.array_equal(b, b2)
+    wide = np.zeros((N, d + 5))
+    wide[:, :d] = A
+    x = np.linspace(-1, 1, d)
+    with Engine(0) as e1, Engine(0) as e2:
+        e1.set_rows(L.LOSS_LS, wide[:, :d], b, 2.5)           # strided view: lda = d + 5
+        e2.gen_synthetic(L.SYNTH_LASSO, N, d, 77, scale=2.5)
+        assert np.array_equal(e1.full_gradient(x), e2.full_gradient(x))
+
+
+@pytest.mark.parametrize("threads,stages,ctas", [(128, 3, 2), (512, 2, 1), (256, 8, 1)])
+def test_full_gradient_tuning_shapes(threads, stages, ctas):
+    p, e = make_rows(orc.LOSS_LS, 2000, 1024, 5, lam_reg=0.1, scale=1.0)
+    x = np.random.default_rng(1).standard_normal(1024)
+    e.set_tuning(pass_threads=threads, pass_stages=stages, pass_ctas_per_sm=ctas)
+    assert rel(e.full_gradient(x), p.full_gradient(x)) < TIGHT
+    e.close()
+
+
+# ----------------------------------------------------------------------------
+# K3: SVRG / SVRG++
+@pytest.mark.parametrize("kind,N,d,cluster", [(orc.LOSS_LS, 600, 64, 0), (orc.LOSS_LOGISTIC, 700, 256, 0),
+                                               (orc.LOSS_LS, 512, 1024, 0), (orc.LOSS_LS, 384, 4096, 0),
+                                               (orc.LOSS_LS, 384, 4096, 1), (orc.LOSS_LOGISTIC, 512, 1024, 2)])
+@pytest.mark.parametrize("plus", [False, True])
+def test_svrg_epochs(kind, N, d, cluster, plus):
+    p, e = make_rows(kind, N, d, 0xABC + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N, scale=None)
+    if cluster:
+        e.set_tuning(seq_cluster=cluster, seq_threads=512 if cluster == 1 else 0)
+    Lmax = p.max_row_sqnorm() * (N if kind == orc.LOSS_LS else 0.25)
+    gamma = 1 / (7 * Lmax)
+    x0 = np.zeros(d) if kind == orc.LOSS_LS else np.ones(d)
+    m0 = N // 4 if plus else N
+    ref = orc.SVRGState(p, x0, gamma, m=m0, plus=plus)
+    e.svrg_init(x0, gamma, plus)
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < TIGHT
+    rng = HostRNG(3)
+    m = m0
+    for _ in range(3):
+        idx = rng.rand_vec(N, m)
+        ref.epoch(idx)
+        e.svrg_epoch(idx)
+        if plus:
+            m *= 2
+    assert rel(e.get_vec(L.VEC_Z_FULL), ref.z_full) < 1e-9
+    assert rel(e.get_vec(L.VEC_W), ref.w) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    assert np.all(e.get_vec(L.VEC_Z) == 0.0)
+    f_ref, f = sum(p.objective(ref.z_full)), sum(e.objective(e.get_vec(L.VEC_Z_FULL)))
+    assert abs(f - f_ref) <= REL_OBJECTIVE * abs(f_ref)
+    e.close()
+
+
+def test_svrg_staged_indices_and_determinism():
+    N, d = 800, 512
+    p, e = make_rows(orc.LOSS_LS, N, d, 11, lam_reg=0.05)
+    gamma = 1 / (7 * N * p.max_row_sqnorm())
+    idx = HostRNG(5).rand_vec(N, N)
+    outs = []
+    for staged in (False, True, False):
+        e.svrg_init(np.zeros(d), gamma, False)
+        if staged:
+            e.stage_indices(idx)
+            e.svrg_epoch(None, N)
+        else:
+            e.svrg_epoch(idx)
+        outs.append(e.get_vec(L.VEC_Z_FULL))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    e.close()
+
+
+# ----------------------------------------------------------------------------
+# K2 + K4: SAGA / SAG
+@pytest.mark.parametrize("kind,N,d", [(orc.LOSS_LS, 300, 64), (orc.LOSS_LOGISTIC, 500, 1024), (orc.LOSS_LS, 256, 4096)])
+@pytest.mark.parametrize("sag", [False, True])
+def test_saga_steps(kind, N, d, sag):
+    p, e = make_rows(kind, N, d, 0x5A6A + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
+    Lmax = p.max_row_sqnorm() * (N if kind == orc.LOSS_LS else 0.25)
+    gamma = 1 / ((16 if sag else 3) * Lmax)
+    x0 = np.full(d, 0.25)
+    ref = orc.SAGAState(p, x0, gamma, sag=sag)
+    e.saga_init(x0, gamma, sag)
+    assert rel(e.get_table_rows(), ref.s) < TIGHT
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < TIGHT
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < TIGHT
+    rng = HostRNG(9)
+    idx = np.array([rng.rand_range(N) for _ in range(3 * N)], dtype=np.int64)
+    idx[10:14] = idx[9]          # force back-to-back repeats: exercises the table hazard path
+    idx[40] = idx[38]
+    ref.steps(idx)
+    e.saga_steps(idx[:N])
+    e.saga_steps(idx[N:])
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    assert rel(e.get_table_rows(), ref.s) < 1e-9
+    e.close()
+
+
+# ----------------------------------------------------------------------------
+# K2 + K5: Finito / MISO / DIAG
+@pytest.mark.parametrize("kind,N,d", [(orc.LOSS_LS, 250, 64), (orc.LOSS_LOGISTIC, 401, 1024)])
+@pytest.mark.parametrize("sweeping,batch", [(1, 1), (2, 1), (3, 1), (1, 7), (2, 16), (3, 5)])
+def test_finito_steps(kind, N, d, sweeping, batch):
+    p, e = make_rows(kind, N, d, 0xF1 + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
+    A = p.A
+    Li = np.sum(A * A, axis=1) * (N if kind == orc.LOSS_LS else 0.25)
+    gam = 0.999 * N / Li
+    x0 = np.full(d, 0.1)
+    ref = orc.FinitoState(p, x0, gam)
+    e.finito_init(x0, gam, ref.hat_gamma)
+    assert rel(e.get_table_rows(), ref.s) < TIGHT
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-10
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-10
+    batches = BatchSweeper(N, batch, sweeping, HostRNG(4)).take(2 * (-(-N // batch)) + 3)
+    ref.steps(batches)
+    idx, bp = csr(batches)
+    e.finito_steps(idx, bp)
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    assert rel(e.get_table_rows(), ref.s) < 1e-9
+    e.close()
+
+
+# K6: LFinito
+@pytest.mark.parametrize("kind,N,d", [(orc.LOSS_LS, 250, 64), (orc.LOSS_LOGISTIC, 401, 1024)])
+@pytest.mark.parametrize("sweeping,batch", [(2, 1), (3, 1), (2, 16), (3, 7)])
+def test_lfinito_outer(kind, N, d, sweeping, batch):
+    p, e = make_rows(kind, N, d, 0x1F + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
+    Li = np.sum(p.A * p.A, axis=1) * (N if kind == orc.LOSS_LS else 0.25)
+    gam = 0.999 * N / Li
+    x0 = np.full(d, 0.1)
+    ref = orc.LFinitoState(p, x0, gam, batch)
+    e.lfinito_init(x0, gam, ref.hat_gamma)
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < TIGHT
+    sw = LFinitoSweeper(N, batch, sweeping, HostRNG(2))
+    for _ in range(3):
+        order = sw.next()
+        ref.outer(order)
+        e.lfinito_outer(order, batch)
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+    assert rel(e.get_vec(L.VEC_Z_FULL), ref.z_full) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    e.close()
+
+
+# ----------------------------------------------------------------------------
+# K7: ProShI
+@pytest.mark.parametrize("N,n", [(3, 2), (200, 64), (333, 1024)])
+@pytest.mark.parametrize("sweeping,batch", [(1, 1), (2, 1), (3, 1), (1, 5), (2, 8), (3, 3)])
+def test_proshi_steps(N, n, sweeping, batch):
+    if N == 3:
+        fx = fixtures.sharing()
+        Q, ql, box, eta, Li = fx["Qdiag"], fx["qlin"], fx["box"], fx["eta"], fx["L"]
+        batch = min(batch, 3)
+    else:
+        Q, _ = orc.gen_rows(orc.SYN_SHARING, n, 0x5EED0005, 0, N)
+        ql, box, eta = np.ones((N, n)), (-2.0, 2.0), 10.0 * N
+        Li = np.abs(Q).max(axis=1) + eta
+    p = orc.Problem(orc.LOSS_DIAGQUAD, Q, ql, box=box, eta=eta).set_reg(orc.REG_INDBOX, lo=-np.inf, hi=np.ones(n))
+    gam = 0.999 * N / Li
+    x0 = np.zeros(n)
+    ref = orc.ProshiState(p, x0, gam)
+    with Engine(0) as e:
+        if N == 3:
+            e.set_blocks(Q, ql, box, eta)
+        else:
+            e.gen_synthetic(L.SYNTH_SHARING, N, n, 0x5EED0005)
+        e.set_reg(L.REG_INDBOX, -np.inf, np.ones(n))
+        e.proshi_init(x0, gam, ref.hat_gamma)
+        assert rel(e.get_table_rows(), ref.s) < TIGHT
+        assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-10
+        assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+        batches = BatchSweeper(N, batch, sweeping, HostRNG(4)).take(3 * (-(-N // batch)) + 2)
+        ref.steps(batches)
+        idx, bp = csr(batches)
+        e.proshi_steps(idx, bp)
+        assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-9
+        assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-8
+        assert rel(e.get_table_rows(), ref.s) < 1e-9
+        # solution() mutates the table on every call (ProShI_basic.jl:127-132)
+        s1 = ref.solution().copy()
+        out = np.empty((N, n))
+        e.proshi_solution(out)
+        assert rel(out, s1) < 1e-9
+        assert rel(e.table_colsum(), s1.sum(axis=0)) < 1e-9
+        e.proshi_solution(out)
+        assert rel(out, ref.solution()) < 1e-9
+
+
+# ----------------------------------------------------------------------------
+# golden vectors of the reference's tests, reached by the CUDA engine
+def test_golden_logistic_finito_svrg_saga():
+    fx, p, e = fixture_rows("logistic")
+    N, x0 = fx["N"], fx["x0"]
+    gam = 0.999 * N / fx["L"]
+    hat = 1 / np.sum(1 / gam)
+    for sweeping in (1, 2, 3):                                       # test_logistic_l1.jl:54-59
+        e.finito_init(x0, gam, hat)
+        idx, bp = csr(BatchSweeper(N, 1, sweeping, HostRNG(1)).take(8999))
+        e.finito_steps(idx, bp)
+        assert np.abs(e.get_vec(L.VEC_Z) - fx["x_star"]).max() < 1e-4
+    e.lfinito_init(x0, gam, hat)                                     # :62-68
+    for _ in range(2000):
+        e.lfinito_outer(np.arange(1, N + 1), 1)
+    assert np.abs(e.get_vec(L.VEC_Z) - fx["x_star"]).max() < 1e-4
+    gamma = 1 / (10 * fx["L"].max())                                 # :126-131
+    e.svrg_init(x0, gamma, False)
+    rng = HostRNG(1)
+    for _ in range(3000):
+        e.svrg_epoch(rng.rand_vec(N, N))
+    assert np.linalg.norm(e.get_vec(L.VEC_Z_FULL) - fx["x_star"]) < 1e-4
+    e.saga_init(x0, 1 / (3 * fx["L"].max()), False)                  # :160-164
+    e.saga_steps(HostRNG(1).rand_vec(N, 8999))
+    assert np.linalg.norm(e.get_vec(L.VEC_Z) - fx["x_star"]) < 5e-3
+    e.close()
+
+
+def test_golden_lasso_all_solvers():
+    fx, p, e = fixture_rows("lasso")
+    N, x0, cost, fs = fx["N"], fx["x0"], fx["cost"], fx["f_star"]
+    gam = 0.999 * N / fx["L"]
+    hat = 1 / np.sum(1 / gam)
+    for sweeping, batch in [(1, 1), (2, 1), (3, 1), (1, 2), (2, 2), (3, 3)]:   # test_lasso.jl:70-75, 101-111
+        e.finito_init(x0, gam, hat)
+        idx, bp = csr(BatchSweeper(N, batch, sweeping, HostRNG(1)).take(999))
+        e.finito_steps(idx, bp)
+        assert cost(e.get_vec(L.VEC_Z)) - fs < 1e-4
+    for sweeping, batch in [(2, 1), (3, 1), (2, 2), (3, 3)]:                    # :78-85, 114-125
+        e.lfinito_init(x0, gam, hat)
+        sw = LFinitoSweeper(N, batch, sweeping, HostRNG(1))
+        for _ in range(999):
+            e.lfinito_outer(sw.next(), batch)
+        assert cost(e.get_vec(L.VEC_Z)) - fs < 1e-4
+    gamma = 1 / (7 * fx["L"].max())                                             # :164-176
+    e.svrg_init(x0, gamma, False)
+    rng = HostRNG(1)
+    for _ in range(999):
+        e.svrg_epoch(rng.rand_vec(N, N))
+    assert cost(e.get_vec(L.VEC_Z_FULL)) - fs < 1e-4
+    e.svrg_init(x0, gamma, True)
+    m = 1
+    for _ in range(15):
+        e.svrg_epoch(rng.rand_vec(N, m))
+        m *= 2
+    assert cost(e.get_vec(L.VEC_Z_FULL)) - fs < 1e-4
+    e.saga_init(x0, 1 / (3 * fx["L"].max()), False)                             # :199-203
+    e.saga_steps(rng.rand_vec(N, 999))
+    assert cost(e.get_vec(L.VEC_Z)) - fs < 1e-4
+    e.saga_init(x0, 1 / (16 * fx["L"].max()), True)                             # :236-240
+    e.saga_steps(rng.rand_vec(N, 9999))
+    assert cost(e.get_vec(L.VEC_Z)) - fs < 1e-4
+    e.close()
+
+
+def test_golden_sharing_proshi():
+    fx = fixtures.sharing()
+    N = fx["N"]
+    gam = 0.999 * N / fx["L"]
+    with Engine(0) as e:
+        e.set_blocks(fx["Qdiag"], fx["qlin"], fx["box"], fx["eta"])
+        e.set_reg(L.REG_INDBOX, -np.inf, fx["g_hi"])
+        for sweeping, batch in [(1, 1), (2, 1), (3, 1), (1, 2), (2, 2), (3, 3)]:  # test_sharing.jl:38-57
+            e.proshi_init(fx["x0"], gam, float(np.sum(gam)))
+            idx, bp = csr(BatchSweeper(N, batch, sweeping, HostRNG(1)).take(999))
+            e.proshi_steps(idx, bp)
+            e.proshi_solution(None)
+            assert np.abs(e.table_colsum() - fx["sum_star"]).max() < 1e-4
+
+
+# ----------------------------------------------------------------------------
+# end-to-end tolerance of the north star after K epochs at a reduced scale
+def test_svrg_pp_k_epochs_tolerance():
+    N, d = 4096, 4096
+    p, e = make_rows(orc.LOSS_LS, N, d, 0x5EED0003, lam_reg=N / 100.0)
+    gamma = 1 / (7 * N * p.max_row_sqnorm())
+    ref = orc.SVRGState(p, np.zeros(d), gamma, m=N // 16, plus=True)
+    e.svrg_init(np.zeros(d), gamma, True)
+    rng, m = HostRNG(0x1D0003), N // 16
+    for _ in range(5):
+        idx = rng.rand_vec(N, m)
+        ref.epoch(idx)
+        e.svrg_epoch(idx)
+        m *= 2
+    x, x_ref = e.get_vec(L.VEC_Z_FULL), ref.z_full
+    assert rel(x, x_ref) < REL_ITERATE
+    f, f_ref = sum(e.objective(x)), sum(p.objective(x_ref))
+    assert abs(f - f_ref) <= REL_OBJECTIVE * abs(f_ref)
+    assert f_ref < sum(p.objective(np.zeros(d)))      # it actually descended
+    e.close()
+
+
+# ----------------------------------------------------------------------------
+# error behaviour at the boundary (reference: @warn + `return nothing`)
+def test_errors():
+    with Engine(0) as e:
+        with pytest.raises(CiaoError) as ei:
+            e.svrg_init(np.zeros(4), 0.1)
+        assert ei.value.code == -3                                   # no problem set
+        e.gen_synthetic(L.SYNTH_LASSO, 64, 16, 1)
+        with pytest.raises(CiaoError):
+            e.svrg_epoch(np.array([1, 2, 3], dtype=np.int64))        # epoch before init
+        with pytest.raises(CiaoError):
+            e.svrg_init(np.zeros(16), -1.0)                          # γ ≤ 0 (SVRG.jl:39)
+        e.svrg_init(np.zeros(16), 1e-3)
+        e.svrg_epoch(np.array([1, 65, 3], dtype=np.int64))           # 65 > N: flagged, memory-safe
+        with pytest.raises(CiaoError) as ei:
+            e.sync()
+        assert ei.value.code == -1
+        with pytest.raises(CiaoError):
+            e.proshi_steps(np.array([1], dtype=np.int64), np.array([0, 1], dtype=np.int64))  # wrong problem kind
+        with pytest.raises(CiaoError):
+            e.set_reg(7)
