@@ -78,6 +78,7 @@ static void free_problem(ciao_ctx *c) {
 static int alloc_common(ciao_ctx *c, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d) {
     free_problem(c);
     c->N_total = N_total; c->row0 = row0; c->n_rows = n_rows; c->d = d;
+    c->win0 = c->win_n = 0;
     c->d_pad = (d + 3) / 4 * 4;
     c->ld = c->d_pad + CIAO_TAIL;
     CUDA_TRY(cudaMalloc(&c->vecs, (size_t)CIAO_NUM_VECS * c->d_pad * sizeof(double)));
@@ -281,6 +282,18 @@ extern "C" int ciao_set_tuning(ciao_ctx *c, int pass_threads, int pass_stages, i
         CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_tuning: value out of range");
     c->pass_threads = pass_threads; c->pass_stages = pass_stages; c->pass_ctas = pass_ctas_per_sm;
     c->seq_cluster = seq_cluster; c->seq_threads = seq_threads;
+    return CIAO_OK;
+}
+
+extern "C" int ciao_set_pass_window(ciao_ctx *c, int64_t row_lo, int64_t n) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_pass_window: null context");
+    if (n == 0) {
+        c->win0 = c->win_n = 0;
+        return CIAO_OK;
+    }
+    if (row_lo < 0 || n < 0 || row_lo + n > c->n_rows) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_pass_window: window outside the local rows");
+    c->win0 = row_lo;
+    c->win_n = n;
     return CIAO_OK;
 }
 

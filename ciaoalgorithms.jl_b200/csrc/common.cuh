@@ -43,6 +43,7 @@ struct ciao_ctx {
     // problem
     int loss_kind = -1;
     int64_t N_total = 0, row0 = 0, n_rows = 0, d = 0, d_pad = 0, ld = 0;
+    int64_t win0 = 0, win_n = 0;       // pass window over the local rows (0 = all)
     double *rec = nullptr;             // row records
     double *qd = nullptr, *ql = nullptr;  // sharing blocks: diag(Q_i), linear term  [N][d_pad]
     double box_lo = 0, box_hi = 0, eta = 0;

@@ -237,7 +237,9 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev) {
     if ((size_t)S * stage_bytes + fixed > budget) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "row pass: stage does not fit shared memory");
     if (S > 16) S = 16;
     const size_t smem = (size_t)S * stage_bytes + fixed;
-    const int64_t n_groups = (c->n_rows + rpg - 1) / rpg;
+    const bool windowed = c->win_n > 0 && (mode == PASS_GRAD || mode == PASS_NORMS);
+    const int64_t w0 = windowed ? c->win0 : 0, wn = windowed ? c->win_n : c->n_rows;
+    const int64_t n_groups = (wn + rpg - 1) / rpg;
     int grid = (int)std::min<int64_t>(n_groups, (int64_t)c->num_sms * ctas_per_sm);
     if (grid < 1) grid = 1;
 
@@ -249,7 +251,7 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev) {
         c->ws_bytes = need;
     }
     PassArgs a;
-    a.rec = c->rec; a.n_rows = c->n_rows; a.ld = c->ld; a.d_pad = d_pad; a.x = x_dev;
+    a.rec = c->rec + w0 * c->ld; a.n_rows = wn; a.ld = c->ld; a.d_pad = d_pad; a.x = x_dev;
     a.ws = c->ws; a.fws = c->ws + (size_t)grid * d_pad; a.table = c->table;
     a.Nd = (double)c->N_total; a.stages = S;
     if ((mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT) && !c->table)
@@ -271,7 +273,7 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev) {
     CUDA_TRY(cudaGetLastError());
     c->timing.launches += 2;
     c->pass_timed = true;
-    c->timing.last_pass_bytes = (int64_t)c->n_rows * c->ld * 8 +
+    c->timing.last_pass_bytes = (int64_t)wn * c->ld * 8 +
                                 ((mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT) ? (int64_t)c->n_rows * d_pad * 8 : 0);
     if (c->world > 1) {
         if (mode == PASS_NORMS) {

@@ -89,6 +89,9 @@ class Engine:
         buf = C.create_string_buffer(uid, 128)
         check(self.lib.ciao_comm_init(self.h, buf, rank, world))
 
+    def set_pass_window(self, row_lo, n):
+        check(self.lib.ciao_set_pass_window(self.h, int(row_lo), int(n)))
+
     # -- passes ----------------------------------------------------------------
     def full_gradient(self, x=None, scale=1.0, out=True):
         xv = None if x is None else f64arr(x)

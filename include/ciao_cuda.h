@@ -104,6 +104,10 @@ int ciao_gen_host(int synth_kind, int64_t d, uint64_t seed, int64_t row0, int64_
 /* out must hold 128 bytes (ncclUniqueId); rank 0 creates it, the host broadcasts it */
 int ciao_comm_unique_id(void *out128);
 int ciao_comm_init(ciao_ctx *ctx, const void *id128, int rank, int world);
+/* Replicated data, sharded pass: restrict the full-gradient / objective passes of this context to
+ * the local rows [row_lo, row_lo + n) (0-based); with a communicator the partial d-vectors are
+ * all-reduced, so G ranks holding the same rows each stream 1/G of them.  n = 0 resets. */
+int ciao_set_pass_window(ciao_ctx *ctx, int64_t row_lo, int64_t n);
 
 /* ---- streaming passes (HBM-bound) ------------------------------------------ */
 /* out = scale · Σ_i ∇f_i(x)      (SVRG_basic.jl:58-63, 88-92; Finito_LFinito.jl:68-72, 85-88) */

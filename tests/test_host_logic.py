@@ -1,0 +1,132 @@
+"""Host-side logic: index selection quirks of the reference, operator recognition, row sharding,
+and the N>1 exchange step emulated with gloo on CPU (world_size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)       # spawned gloo workers re-import this module without conftest
+import ciao_pkg  # noqa: E402
+
+ciao_pkg.load()
+
+from ciaoalgorithms_jl_b200 import operators as ops  # noqa: E402
+from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, LFinitoSweeper, csr, shard_rows, static_batches  # noqa: E402
+
+
+def test_cyclic_sweep_starts_at_batch_two():                      # Finito_basic.jl:38,99
+    sw = BatchSweeper(6, 1, 2, HostRNG(0))
+    assert [int(b[0]) for b in sw.take(7)] == [2, 3, 4, 5, 6, 1, 2]
+
+
+def test_shuffled_sweep_first_pass_is_natural_order():            # Finito_basic.jl:39-40,101-107
+    sw = BatchSweeper(5, 1, 3, HostRNG(0))
+    first = [int(b[0]) for b in sw.take(5)]
+    second = sorted(int(b[0]) for b in sw.take(5))
+    assert first == [1, 2, 3, 4, 5] and second == [1, 2, 3, 4, 5]
+
+
+def test_static_batches_with_remainder():                         # Finito_basic.jl:52-57
+    b = static_batches(7, 3)
+    assert [list(x) for x in b] == [[1, 2, 3], [4, 5, 6], [7]]
+    sw = BatchSweeper(7, 3, 2, HostRNG(0))
+    assert sw.d == 3 and list(sw.next()) == [4, 5, 6] and list(sw.next()) == [7] and list(sw.next()) == [1, 2, 3]
+
+
+def test_random_minibatch_without_replacement():                  # Finito_basic.jl:97
+    sw = BatchSweeper(10, 4, 1, HostRNG(3))
+    for b in sw.take(20):
+        assert len(set(b.tolist())) == 4 and b.min() >= 1 and b.max() <= 10
+
+
+def test_lfinito_sweeper():                                       # Finito_LFinito.jl:89-91
+    assert list(LFinitoSweeper(5, 2, 2, HostRNG(0)).next()) == [1, 2, 3]
+    assert list(LFinitoSweeper(5, 2, 1, HostRNG(0)).next()) == [1, 2, 3]          # sweeping 1 is silently cyclic
+    assert sorted(LFinitoSweeper(5, 2, 3, HostRNG(0)).next()) == [1, 2, 3]
+
+
+def test_csr():
+    idx, ptr = csr([np.array([3, 1]), np.array([2]), np.array([], dtype=np.int64)])
+    assert idx.tolist() == [3, 1, 2] and ptr.tolist() == [0, 2, 3, 3]
+
+
+def test_shard_rows_partition():
+    for N, G in [(10, 3), (1 << 22, 8), (7, 8)]:
+        bounds = [shard_rows(N, G, r) for r in range(G)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == N
+        assert all(bounds[r][1] == bounds[r + 1][0] for r in range(G - 1))
+
+
+def test_operator_recognition():
+    F = [ops.LeastSquares(np.array([[1.0, 2.0, 3.0]]), np.array([0.5]), 6.0) for _ in range(4)]
+    kind, loss, A, b, s = ops.pack_F(F, 4)
+    assert kind == "rows" and loss == 0 and A.shape == (4, 3) and np.all(b == 0.5) and np.all(s == 6.0)
+    F = [ops.Precompose(ops.LogisticLoss(np.array([-1.0]), 1.0), np.ones((1, 5)), 1.0) for _ in range(3)]
+    kind, loss, A, y, mu = ops.pack_F(F, 3)
+    assert loss == 1 and np.all(y == -1.0) and A.shape == (3, 5)
+    box = ops.IndBox(-2.0, 2.0)
+    F = [ops.Sum(ops.Quadratic(np.diag([1.0, 2.0]), np.ones(2)), ops.SqrDistL2(box, 30.0)) for _ in range(3)]
+    kind, Qd, ql, bx, eta = ops.pack_F(F, 3)
+    assert kind == "blocks" and Qd.shape == (3, 2) and bx == (-2.0, 2.0) and eta == 30.0
+    with pytest.raises(ops.UnsupportedOperator):
+        ops.pack_F([ops.Sum(ops.Quadratic(np.array([[1.0, 0.5], [0.5, 1.0]]), np.ones(2)), ops.SqrDistL2(box, 1.0))], 1)
+    with pytest.raises(ops.UnsupportedOperator):
+        ops.pack_F([object()], 1)
+    assert ops.reg_params(ops.NormL1(0.3)) == (1, 0.3) and ops.reg_params(ops.Zero()) == (0,)
+
+
+# ---------------------------------------------------------------------------------------------
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    """The sharded pass of SURVEY.md §8e on CPU: each rank evaluates its contiguous row shard with the
+    oracle, one all_reduce(sum) of the d-vector, result must equal the unsharded pass."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    import ciao_pkg
+    ciao_pkg.load()
+    from ciaoalgorithms_jl_b200.sampling import shard_rows as sr
+    from oracle import oracle as orc
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, d, seed = 301, 48, 99
+    lo, hi = sr(N, world, rank)
+    A, b = orc.gen_rows(orc.SYN_LASSO, d, seed, lo, hi - lo)      # each shard generates its own rows
+    x = np.linspace(-1, 1, d)
+    part = orc.Problem(orc.LOSS_LS, A, b, np.full(hi - lo, float(N))).full_gradient(x, 1.0)
+    t = torch.from_numpy(part.copy())
+    dist.all_reduce(t)
+    fs = torch.tensor([orc.Problem(orc.LOSS_LS, A, b, np.full(hi - lo, float(N))).objective(x)[0] * (hi - lo)], dtype=torch.float64)
+    dist.all_reduce(fs)
+    if rank == 0:
+        Af, bf = orc.gen_rows(orc.SYN_LASSO, d, seed, 0, N)
+        full = orc.Problem(orc.LOSS_LS, Af, bf, np.full(N, float(N)))
+        q.put((np.abs(t.numpy() / N - full.full_gradient(x, 1.0 / N)).max() / np.abs(full.full_gradient(x, 1.0 / N)).max(),
+               abs(fs.item() / N - full.objective(x)[0]) / full.objective(x)[0]))
+    dist.destroy_process_group()
+
+
+def test_sharded_pass_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err_g, err_f = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err_g < 1e-13 and err_f < 1e-13
