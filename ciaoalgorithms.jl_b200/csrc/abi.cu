@@ -731,3 +731,12 @@ extern "C" int ciao_last_timing(ciao_ctx *c, ciao_timing *out) {
     *out = c->timing;
     return CIAO_OK;
 }
+
+#ifdef CIAO_SEQ_PROFILE
+// debug builds only (scripts/prof_seq.py): per-phase cycles of the last sequential kernel
+extern "C" int ciao_debug_seq_prof(ciao_ctx *c, long long *out4) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(out4, g_seq_prof, 4 * sizeof(long long)));
+    return CIAO_OK;
+}
+#endif

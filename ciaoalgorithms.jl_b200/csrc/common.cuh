@@ -174,6 +174,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 __device__ __forceinline__ void st_cluster_v2f64(uint32_t addr, double a, double b) {
     asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
 }
+// remote shared-memory store whose completion is signalled on a (remote) mbarrier by tx-count:
+// no release/acquire fence at cluster scope is needed on either side (SASS: STAS)
+__device__ __forceinline__ void st_async_v2f64(uint32_t remote_addr, double a, double b, uint32_t remote_bar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(remote_addr),
+                 "d"(a), "d"(b), "r"(remote_bar_addr)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
 }

@@ -229,7 +229,7 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev) {
     const int T = (int)Tn;
     const int rpg = 16 / cpt;
     const size_t stage_bytes = (size_t)rpg * c->ld * sizeof(double);
-    const int ctas_per_sm = c->pass_ctas > 0 ? c->pass_ctas : 1;
+    const int ctas_per_sm = c->pass_ctas > 0 ? c->pass_ctas : 2;  // 2 × 3 stages beat 1 × 6 (profiles/tune_r1.md)
     const size_t fixed = 2 * rpg * 32 * sizeof(double) + 16 * sizeof(uint64_t) + 256;
     const size_t budget = (size_t)(227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
     int S = c->pass_stages > 0 ? c->pass_stages : 8;

@@ -13,10 +13,11 @@
 //      TMA-prefetched (cp.async.bulk, D-deep mbarrier ring) from the host-generated
 //      index sequence, D−1 steps ahead;
 //   2. partial dots → warp shuffles → each warp pushes its partial into EVERY CTA of
-//      the cluster through DSMEM (st.shared::cluster) and arrives on that CTA's
-//      mbarrier (release.cluster); every thread then sums the C·W partials in one
-//      fixed order, so all CTAs hold bit-identical scalars — no CTA or cluster
-//      barrier instruction on the step's critical path;
+//      the cluster through DSMEM with st.async (remote store that completes on the
+//      destination CTA's mbarrier by tx-count, so neither side needs a cluster-scope
+//      fence); every thread then sums the C·W partials in one fixed order, so all
+//      CTAs hold bit-identical scalars — no CTA or cluster barrier instruction on
+//      the step's critical path;
 //   3. the variance-reduced / aggregated update, the table row write and prox_g are
 //      fused, element by element, in the reference's rounding order.
 // Table rows are prefetched P steps ahead into registers by their owner threads
@@ -40,6 +41,15 @@ struct SeqArgs {
     int plus, sag;
     RegParams reg;
 };
+
+#ifdef CIAO_SEQ_PROFILE
+__device__ long long g_seq_prof[4];  // accumulated cycles of thread 0 of CTA 0 per phase (debug builds only)
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(i, a, b) prof_acc[i] += (b) - (a)
+#else
+#define PROF_T(var)
+#define PROF_ADD(i, a, b)
+#endif
 
 #define SEQ_MAX_PART 128  // C·W ≤ 128
 
@@ -69,8 +79,8 @@ __global__ void __launch_bounds__(512, 1) seq_kernel(const SeqArgs p) {
 
     if (tid == 0) {
         for (int s = 0; s < D; ++s) mbar_init(&row_bar[s], 1);
-        mbar_init(&part_bar[0], C * W);
-        mbar_init(&part_bar[1], C * W);
+        mbar_init(&part_bar[0], 1);  // one local arrive (expect_tx) per phase; the data arrives as tx bytes
+        mbar_init(&part_bar[1], 1);
         fence_mbar_init();
     }
     cluster_sync_all();  // peers' barriers exist before anyone arrives on them
@@ -137,17 +147,27 @@ __global__ void __launch_bounds__(512, 1) seq_kernel(const SeqArgs p) {
         if (P < K) issue_row(P, in1);
     }
 
+    const uint32_t part_bytes = C * W * 16;
+#ifdef CIAO_SEQ_PROFILE
+    long long prof_acc[4] = {0, 0, 0, 0};
+#endif
+    int slot = 0;
+    uint32_t row_phase = 0;
     for (int64_t k0 = 0; k0 < K; k0 += P) {
 #pragma unroll
         for (int j = 0; j < P; ++j) {
             const int64_t k = k0 + j;
             if (k >= K) break;
-            // slot (k−1)%D was fully read by every warp before it arrived for step k−1
-            if (tid == 0 && k >= 1 && k + P < K) issue_row(k + P, in1);
-            const int64_t ik = iq[j];
-            const int slot = (int)(k % D);
             const int par = (int)(k & 1);
-            mbar_wait(&row_bar[slot], (uint32_t)((k / D) & 1));
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&part_bar[par], part_bytes);  // arm this step's exchange phase
+                // slot (k−1)%D was fully read by every warp before it sent its partial for step k−1
+                if (k >= 1 && k + P < K) issue_row(k + P, in1);
+            }
+            const int64_t ik = iq[j];
+            PROF_T(t_a);
+            mbar_wait(&row_bar[slot], row_phase);
+            PROF_T(t_b);
             const double *rp = ring + slot * slot_doubles;
             double a[CPT];
 #pragma unroll
@@ -173,12 +193,13 @@ __global__ void __launch_bounds__(512, 1) seq_kernel(const SeqArgs p) {
             }
             v0 = warp_sum(v0);
             if (TWO_DOTS) v1 = warp_sum(v1);
+            PROF_T(t_c);
             if (lane < C) {
                 const uint32_t slot_addr = smem_u32(part + ((size_t)par * SEQ_MAX_PART + rank * W + warp) * 2);
-                st_cluster_v2f64(mapa_u32(slot_addr, lane), v0, v1);
-                mbar_arrive_remote(mapa_u32(smem_u32(&part_bar[par]), lane));
+                st_async_v2f64(mapa_u32(slot_addr, lane), v0, v1, mapa_u32(smem_u32(&part_bar[par]), lane));
             }
-            mbar_wait_cluster(&part_bar[par], (uint32_t)((k >> 1) & 1));
+            mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
+            PROF_T(t_d);
             double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
             {
                 const double2 *pp = reinterpret_cast<const double2 *>(part + (size_t)par * SEQ_MAX_PART * 2);
@@ -277,6 +298,15 @@ __global__ void __launch_bounds__(512, 1) seq_kernel(const SeqArgs p) {
             }
             in1 = in2;
             in2 = (k + P + 2 < K) ? __ldg(p.idx + k + P + 2) : 0;
+            PROF_T(t_e);
+            PROF_ADD(0, t_a, t_b);  // wait for the prefetched row
+            PROF_ADD(1, t_b, t_c);  // LDS + dots + warp shuffles
+            PROF_ADD(2, t_c, t_d);  // cluster exchange
+            PROF_ADD(3, t_d, t_e);  // sum of partials + fused update + pipeline rotation
+            if (++slot == D) {
+                slot = 0;
+                row_phase ^= 1;
+            }
         }
     }
 
@@ -299,6 +329,10 @@ __global__ void __launch_bounds__(512, 1) seq_kernel(const SeqArgs p) {
             }
         }
     }
+#ifdef CIAO_SEQ_PROFILE
+    if (tid == 0 && rank == 0)
+        for (int i = 0; i < 4; ++i) g_seq_prof[i] = prof_acc[i];
+#endif
     cluster_sync_all();  // nobody exits while a peer may still touch its shared memory
 }
 
