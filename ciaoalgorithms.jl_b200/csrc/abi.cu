@@ -22,7 +22,25 @@ void ciao_set_error(const char *fmt, ...) {
 #include "pass.cu"
 #include "gen.cu"
 #include "indices.cu"
-#include "seq.cu"
+
+// the sequential kernels live in their own translation units (seq_svrg.cu, seq_saga.cu, …)
+int run_seq_svrg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
+int run_seq_saga(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
+int run_seq_finito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
+int run_seq_lfinito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
+static int run_seq(ciao_ctx *c, int alg, const int64_t *idx_prepared, int64_t K, double m_d) {
+    switch (alg) {
+        case ALG_SVRG: return run_seq_svrg(c, idx_prepared, K, m_d);
+        case ALG_SAGA: return run_seq_saga(c, idx_prepared, K, m_d);
+        case ALG_FINITO: return run_seq_finito(c, idx_prepared, K, m_d);
+        default: return run_seq_lfinito(c, idx_prepared, K, m_d);
+    }
+}
+__device__ __forceinline__ double prox_rt(int kind, double x, double gl, double lo, double hi) {
+    if (kind == CIAO_REG_NORML1) return prox_elem<CIAO_REG_NORML1>(x, gl, lo, hi);
+    if (kind == CIAO_REG_INDBOX) return prox_elem<CIAO_REG_INDBOX>(x, gl, lo, hi);
+    return x;
+}
 #include "proshi.cu"
 #include "comm.cu"
 
@@ -190,6 +208,10 @@ static int need_rows(ciao_ctx *c, const char *who, bool whole) {
     CUDA_TRY(cudaSetDevice(c->device));
     return CIAO_OK;
 }
+
+// index staging buffers sized once per solver (cudaMalloc/cudaFree next to a 137 GB allocation cost ~100 ms each)
+static int reserve_idx(ciao_ctx *c, size_t n);
+static int reserve_for_solver(ciao_ctx *c) { return reserve_idx(c, (size_t)std::max<int64_t>(c->N_total, 1 << 16)); }
 
 static int alloc_table(ciao_ctx *c) {
     if (!c->table) CUDA_TRY(cudaMalloc(&c->table, (size_t)c->n_rows * c->d_pad * sizeof(double)));
@@ -473,6 +495,7 @@ extern "C" int ciao_svrg_init(ciao_ctx *c, const double *x0, double gamma, int p
     CIAO_TRY(need_rows(c, "ciao_svrg_init", false));
     if (!x0 || !(gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_svrg_init: x0 is null or γ ≤ 0 (SVRG.jl:39)");
     c->algo = ALG_SVRG; c->gamma = gamma; c->plus = plus ? 1 : 0;
+    CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(upload_vec(c, CIAO_VEC_Z_FULL, x0));                                  // z_full = copy(x0)  :64
     CIAO_TRY(copy_vec(c, CIAO_VEC_W, CIAO_VEC_Z_FULL));                            // w = copy(x0)       :66
     CUDA_TRY(cudaMemsetAsync(ctx_vec(c, CIAO_VEC_Z), 0, (size_t)c->d_pad * 8, c->stream));  // z = 0        :65
@@ -499,6 +522,7 @@ extern "C" int ciao_saga_init(ciao_ctx *c, const double *x0, double gamma, int s
     CIAO_TRY(need_rows(c, "ciao_saga_init", true));
     if (!x0 || !(gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_saga_init: x0 is null or γ ≤ 0 (SAGA.jl:37)");
     c->algo = ALG_SAGA; c->gamma = gamma; c->sag = sag ? 1 : 0;
+    CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(alloc_table(c));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
     CIAO_TRY(run_row_pass(c, PASS_SAGA_INIT, ctx_vec(c, CIAO_VEC_X0)));            // :41-45
@@ -533,6 +557,7 @@ extern "C" int ciao_finito_init(ciao_ctx *c, const double *x0, const double *gam
     CIAO_TRY(need_rows(c, "ciao_finito_init", true));
     if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_finito_init: null argument or γ̂ ≤ 0");
     c->algo = ALG_FINITO; c->hat_gamma = hat_gamma;
+    CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(alloc_table(c));
     CIAO_TRY(set_gammas(c, gamma_N, true));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
@@ -569,6 +594,7 @@ extern "C" int ciao_lfinito_init(ciao_ctx *c, const double *x0, const double *ga
     CIAO_TRY(need_rows(c, "ciao_lfinito_init", true));
     if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_lfinito_init: null argument or γ̂ ≤ 0");
     c->algo = ALG_LFINITO; c->hat_gamma = hat_gamma;
+    CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(set_gammas(c, gamma_N, true));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
     CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X0)));                 // :68-72
@@ -620,7 +646,8 @@ static int need_blocks(ciao_ctx *c, const char *who) {
 extern "C" int ciao_proshi_init(ciao_ctx *c, const double *x0, const double *gamma_N, double hat_gamma) {
     CIAO_TRY(need_blocks(c, "ciao_proshi_init"));
     if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_proshi_init: null argument or γ̂ ≤ 0");
-    c->algo = 5; c->hat_gamma = hat_gamma;
+    c->algo = ALG_PROSHI; c->hat_gamma = hat_gamma;
+    CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(alloc_table(c));
     CIAO_TRY(set_gammas(c, gamma_N, false));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
@@ -631,7 +658,7 @@ extern "C" int ciao_proshi_init(ciao_ctx *c, const double *x0, const double *gam
 
 extern "C" int ciao_proshi_steps(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches) {
     CIAO_TRY(need_blocks(c, "ciao_proshi_steps"));
-    if (c->algo != 5) CIAO_FAIL(CIAO_ERR_STATE, "ciao_proshi_steps before ciao_proshi_init");
+    if (c->algo != ALG_PROSHI) CIAO_FAIL(CIAO_ERR_STATE, "ciao_proshi_steps before ciao_proshi_init");
     int64_t n_idx = 0;
     CIAO_TRY(batched_indices(c, idx, batch_ptr, n_batches, &n_idx));
     return run_proshi_steps(c, c->idx_prep, n_idx);
@@ -639,7 +666,7 @@ extern "C" int ciao_proshi_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
 
 extern "C" int ciao_proshi_solution(ciao_ctx *c, double *S_out) {
     CIAO_TRY(need_blocks(c, "ciao_proshi_solution"));
-    if (c->algo != 5) CIAO_FAIL(CIAO_ERR_STATE, "ciao_proshi_solution before ciao_proshi_init");
+    if (c->algo != ALG_PROSHI) CIAO_FAIL(CIAO_ERR_STATE, "ciao_proshi_solution before ciao_proshi_init");
     CIAO_TRY(run_proshi_solution(c));
     if (S_out) {
         CUDA_TRY(cudaMemcpy2DAsync(S_out, (size_t)c->d * 8, c->table, (size_t)c->d_pad * 8, (size_t)c->d * 8, (size_t)c->N_total,
@@ -731,12 +758,3 @@ extern "C" int ciao_last_timing(ciao_ctx *c, ciao_timing *out) {
     *out = c->timing;
     return CIAO_OK;
 }
-
-#ifdef CIAO_SEQ_PROFILE
-// debug builds only (scripts/prof_seq.py): per-phase cycles of the last sequential kernel
-extern "C" int ciao_debug_seq_prof(ciao_ctx *c, long long *out4) {
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpyFromSymbol(out4, g_seq_prof, 4 * sizeof(long long)));
-    return CIAO_OK;
-}
-#endif

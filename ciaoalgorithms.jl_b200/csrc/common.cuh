@@ -26,6 +26,8 @@
 #define CIAO_FLAG_HAZARD (1ll << 62)  // same row was written < prefetch-depth steps ago: reload the table row
 #define CIAO_FLAG_PROX (1ll << 61)    // batch boundary: apply prox_g at this step (after: Finito/ProShI, before: LFinito)
 
+enum { ALG_SVRG = 1, ALG_SAGA = 2, ALG_FINITO = 3, ALG_LFINITO = 4, ALG_PROSHI = 5 };
+
 struct RegParams {
     int kind;
     double lambda;       // NormL1

@@ -1,0 +1,455 @@
+// seq_impl.cuh — K3..K6: the sequential inner loops as ONE persistent thread-block-cluster
+// kernel per call (no kernel launch per sample).
+//
+//   ALG_SVRG    SVRG_basic.jl:73-87      m inner steps + snapshot average
+//   ALG_SAGA    SAGA_basic.jl:55-65      K single-sample steps with the N×d gradient table (SAGA and SAG)
+//   ALG_FINITO  Finito_basic.jl:110-118  steps/batches with the N×d table s_i and per-component γ_i
+//   ALG_LFINITO Finito_LFinito.jl:91-100 one sweep of corrections over all batches (no table)
+//
+// Design.  A cluster of C CTAs splits the d columns; a compute thread
+// owns CPT fixed columns of every state vector (w/z, av, z_full, Σw) in REGISTERS for
+// the whole call.  Each CTA has W compute warps and one PRODUCER warp.  Per step:
+//   1. producer: the sampled row slice a_i[cols of this CTA] + its scalars (b_i, λ_i, γ_i)
+//      is TMA-prefetched (cp.async.bulk, D-deep mbarrier ring) from the host-generated
+//      index sequence D steps ahead; a slot is known to be free when the exchange phase
+//      of the step that used it has completed;
+//   2. compute: partial dots → warp shuffles → each warp pushes its partial into EVERY CTA
+//      of the cluster through DSMEM with st.async (a remote store that completes on the
+//      destination CTA's mbarrier by tx-count, so neither side needs a cluster-scope
+//      fence); every warp then reduces the C·W partials with the same xor-butterfly, so
+//      all threads of all CTAs hold bit-identical scalars — no CTA or cluster barrier
+//      instruction on the step's critical path;
+//   3. the variance-reduced / aggregated update, the table row write and prox_g are
+//      fused, element by element, in the reference's rounding order.
+// Table rows are prefetched P steps ahead into registers by their owner threads
+// (generic proxy; the same thread reads and writes a given address → coherent); when a
+// row index repeats inside the prefetch window the step is flagged by
+// prep_indices_kernel and reloads the row after the previous write.
+// The step is latency/issue bound (one warp per SM sub-partition), so the loop body is
+// kept free of predicates: ring slots are zero padded to the thread grid.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+struct SeqArgs {
+    const double *rec;
+    int64_t ld, d_pad, dc;  // dc = columns per CTA
+    const int64_t *idx;     // prepared: 0-based row | flags
+    int64_t K;
+    double *table;
+    double *v_z, *v_zfull, *v_w, *v_av, *v_zsum;
+    double gamma, hat_gamma, Nd, m_d;
+    int plus, sag;
+    int npart_pad;          // C·W rounded up to a multiple of 32
+    RegParams reg;
+};
+
+#ifdef CIAO_SEQ_PROFILE
+__device__ long long g_seq_prof[4];  // accumulated cycles of thread 0 of CTA 0 per phase (debug builds only)
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(i, a, b) prof_acc[i] += (b) - (a)
+#else
+#define PROF_T(var)
+#define PROF_ADD(i, a, b)
+#endif
+
+constexpr int SEQ_D = 8;          // row ring depth (steps of prefetch)
+constexpr int SEQ_MAX_PART = 128; // C·W ≤ 128
+
+template <int CPT, int ALG, int LOSS, int REG>
+__global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
+    constexpr bool TABLE = (ALG == ALG_SAGA || ALG == ALG_FINITO);
+    constexpr bool TWO_DOTS = (ALG == ALG_SVRG || ALG == ALG_LFINITO);
+    constexpr bool NEED_IDX = (ALG != ALG_SVRG);
+    constexpr int P = CPT >= 8 ? 4 : 6;  // table-row / index prefetch distance in steps
+    constexpr int D = SEQ_D;
+    constexpr int H = CPT / 2;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Tc = blockDim.x - 32;  // compute threads; the last warp is the producer
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = Tc >> 5;
+    const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
+    const int64_t dc = p.dc;
+    const int cover = Tc * CPT;                       // columns covered by the thread grid (≥ dc)
+    const size_t slot_doubles = (size_t)cover + CIAO_TAIL;
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    double *part = ring + D * slot_doubles;           // [2][npart_pad][2]
+    uint64_t *row_bar = reinterpret_cast<uint64_t *>(part + 2 * (size_t)p.npart_pad * 2);
+    uint64_t *part_bar = row_bar + D;
+    const int64_t K = p.K;
+    const int64_t cbase = (int64_t)rank * dc;
+    const uint32_t part_bytes = C * W * 16;
+
+    // zero the ring padding and the unused partial slots once
+    for (size_t i = tid; i < D * slot_doubles + 2 * (size_t)p.npart_pad * 2; i += blockDim.x) ring[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < D; ++s) mbar_init(&row_bar[s], 1);
+        mbar_init(&part_bar[0], 1);  // one local arrive (expect_tx) per phase; the data arrives as tx bytes
+        mbar_init(&part_bar[1], 1);
+        fence_mbar_init();
+    }
+    fence_proxy_async();  // the zero fill (generic proxy) is ordered before the TMA writes into the ring
+    __syncthreads();
+    cluster_sync_all();   // peers' barriers exist before anyone sends to them
+
+    if (warp == W) {
+        // ===================== producer warp =====================
+        if (lane == 0) {
+            auto issue_row = [&](int64_t step, int64_t pidx) {
+                const int64_t i = pidx & CIAO_IDX_MASK;
+                const int slot = (int)(step & (D - 1));
+                double *dst = ring + slot * slot_doubles;
+                const double *src = p.rec + i * p.ld;
+                mbar_arrive_expect_tx(&row_bar[slot], (uint32_t)(dc * 8 + CIAO_TAIL * 8));
+                tma_load_1d(dst, src + cbase, (uint32_t)(dc * 8), &row_bar[slot]);
+                tma_load_1d(dst + cover, src + p.d_pad, CIAO_TAIL * 8, &row_bar[slot]);
+            };
+            if (K > 0) mbar_arrive_expect_tx(&part_bar[0], part_bytes);
+            if (K > 1) mbar_arrive_expect_tx(&part_bar[1], part_bytes);
+            for (int64_t s = 0; s < D && s < K; ++s) issue_row(s, __ldg(p.idx + s));
+            int64_t n1 = (D < K) ? __ldg(p.idx + D) : 0, n2 = (D + 1 < K) ? __ldg(p.idx + D + 1) : 0;
+            for (int64_t k = 0; k < K; ++k) {
+                const int par = (int)(k & 1);
+                // phase k complete ⇒ every warp of the cluster has consumed row k and sent its partial
+                mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
+                if (k + 2 < K) mbar_arrive_expect_tx(&part_bar[par], part_bytes);  // arm the exchange of step k+2
+                if (k + D < K) issue_row(k + D, n1);
+                n1 = n2;
+                n2 = (k + D + 2 < K) ? __ldg(p.idx + k + D + 2) : 0;
+            }
+        }
+    } else {
+        // ===================== compute warps =====================
+        int lcol[H];
+        int64_t gcol[H];
+        bool valid[H];
+        double z[CPT], av[CPT], zf[CPT], zs[CPT], blo[CPT], bhi[CPT];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            lcol[h] = 2 * (tid + Tc * h);
+            valid[h] = lcol[h] < dc;
+            gcol[h] = cbase + (valid[h] ? lcol[h] : 0);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int q = 2 * h + e;
+                const bool v = valid[h];
+                const int64_t g = gcol[h] + e;
+                z[q] = v ? (ALG == ALG_SVRG ? p.v_w[g] : p.v_z[g]) : 0.0;  // the running iterate: SVRG → w, others → z
+                av[q] = v ? p.v_av[g] : 0.0;
+                zf[q] = (v && TWO_DOTS) ? p.v_zfull[g] : 0.0;
+                zs[q] = (v && ALG == ALG_SVRG) ? p.v_zsum[g] : 0.0;
+                blo[q] = (v && REG == CIAO_REG_INDBOX && p.reg.lo_v) ? p.reg.lo_v[g] : p.reg.lo_s;
+                bhi[q] = (v && REG == CIAO_REG_INDBOX && p.reg.hi_v) ? p.reg.hi_v[g] : p.reg.hi_s;
+            }
+        }
+        const double gstep = (ALG == ALG_SVRG || ALG == ALG_SAGA) ? p.gamma : p.hat_gamma;
+        const double gl = gstep * p.reg.lambda;
+        const double cN = __ddiv_rn(p.hat_gamma, p.Nd);  // LFinito: γ̂/N
+        const int E = p.npart_pad >> 5;                  // partials per lane in the final butterfly
+
+        // ---- index / table-row prefetch pipelines (not needed by SVRG) -------------------
+        int64_t iq[P];
+        double2 tbuf[P][H];
+        int64_t in1 = 0, in2 = 0;
+        if (NEED_IDX) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                iq[j] = (j < K) ? __ldg(p.idx + j) : 0;
+                if (TABLE && j < K) {
+                    const double *trow = p.table + (iq[j] & CIAO_IDX_MASK) * p.d_pad;
+#pragma unroll
+                    for (int h = 0; h < H; ++h)
+                        tbuf[j][h] = valid[h] ? __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h])) : make_double2(0, 0);
+                }
+            }
+            in1 = (P < K) ? __ldg(p.idx + P) : 0;          // index of step k+P   (k = 0)
+            in2 = (P + 1 < K) ? __ldg(p.idx + P + 1) : 0;  // index of step k+P+1
+        }
+
+#ifdef CIAO_SEQ_PROFILE
+        long long prof_acc[4] = {0, 0, 0, 0};
+#endif
+        int slot = 0;
+        uint32_t row_phase = 0;
+        // software pipeline: the row of step k+1 is pulled into registers while step k's exchange is in flight
+        double a[CPT], tb = 0.0, tl = 0.0, tgam = 0.0;
+        auto load_row = [&](double (&ar)[CPT], double &rb, double &rl, double &rg) {
+            mbar_wait(&row_bar[slot], row_phase);
+            const double *rp = ring + slot * slot_doubles;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const double2 v = *reinterpret_cast<const double2 *>(rp + lcol[h]);
+                ar[2 * h] = v.x;
+                ar[2 * h + 1] = v.y;
+            }
+            rb = rp[cover];
+            rl = rp[cover + 1];
+            rg = rp[cover + 2];
+            if (++slot == D) {
+                slot = 0;
+                row_phase ^= 1;
+            }
+        };
+        if (K > 0) load_row(a, tb, tl, tgam);
+        for (int64_t k0 = 0; k0 < K; k0 += P) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const int64_t k = k0 + j;
+                if (k >= K) break;
+                const int par = (int)(k & 1);
+                const int64_t ik = NEED_IDX ? iq[j] : 0;
+                PROF_T(t_a);
+                PROF_T(t_b);
+
+                if (ALG == ALG_LFINITO && (ik & CIAO_FLAG_PROX)) {  // Finito_LFinito.jl:92
+#pragma unroll
+                    for (int q = 0; q < CPT; ++q) z[q] = prox_elem<REG>(av[q], gl, blo[q], bhi[q]);
+                }
+
+                // ---- dots: v0 = a·(w|z), v1 = a·z_full ------------------------------------
+                double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) {
+                    v0 = fma(a[q], z[q], v0);
+                    if (TWO_DOTS) v1 = fma(a[q], zf[q], v1);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                    if (TWO_DOTS) v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                }
+                PROF_T(t_c);
+                if (lane < C) {
+                    const uint32_t dst = smem_u32(part + ((size_t)par * p.npart_pad + rank * W + warp) * 2);
+                    st_async_v2f64(mapa_u32(dst, lane), v0, v1, mapa_u32(smem_u32(&part_bar[par]), lane));
+                }
+                double an[CPT], nb = 0.0, nl = 0.0, ng = 0.0;
+                if (k + 1 < K) load_row(an, nb, nl, ng);
+                mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
+                PROF_T(t_d);
+                // every warp reduces the same C·W partials with the same butterfly → identical bits everywhere
+                double u0 = 0.0, u1 = 0.0;
+                {
+                    const double2 *pp = reinterpret_cast<const double2 *>(part + (size_t)par * p.npart_pad * 2) + lane;
+                    for (int e = 0; e < E; ++e) {
+                        const double2 v = pp[e * 32];
+                        u0 += v.x;
+                        if (TWO_DOTS) u1 += v.y;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        u0 += __shfl_xor_sync(0xffffffffu, u0, o);
+                        if (TWO_DOTS) u1 += __shfl_xor_sync(0xffffffffu, u1, o);
+                    }
+                }
+
+                // ---- fused update ---------------------------------------------------------
+                if (ALG == ALG_SVRG) {  // SVRG_basic.jl:74-81
+                    const double cz = loss_coef<LOSS>(u1, tb, tl), cw = loss_coef<LOSS>(u0, tb, tl);
+#pragma unroll
+                    for (int q = 0; q < CPT; ++q) {
+                        double t = __dsub_rn(grad_elem<LOSS>(a[q], cz, tl), grad_elem<LOSS>(a[q], cw, tl));
+                        t = __dsub_rn(t, av[q]);
+                        t = __dmul_rn(t, p.gamma);
+                        t = __dadd_rn(t, z[q]);
+                        z[q] = prox_elem<REG>(t, gl, blo[q], bhi[q]);
+                        zs[q] = __dadd_rn(zs[q], z[q]);
+                    }
+                } else if (ALG == ALG_LFINITO) {  // Finito_LFinito.jl:94-98
+                    const double czf = loss_coef<LOSS>(u1, tb, tl), czz = loss_coef<LOSS>(u0, tb, tl);
+                    const double rr = __ddiv_rn(p.hat_gamma, tgam);
+#pragma unroll
+                    for (int q = 0; q < CPT; ++q) {
+                        av[q] = __dadd_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(a[q], czf, tl)));
+                        av[q] = __dsub_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(a[q], czz, tl)));
+                        av[q] = __dadd_rn(av[q], __dmul_rn(rr, __dsub_rn(z[q], zf[q])));
+                    }
+                } else {
+                    const double c = loss_coef<LOSS>(u0, tb, tl);
+                    double2 sold[H];
+                    double *trow = p.table + (ik & CIAO_IDX_MASK) * p.d_pad;
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        sold[h] = tbuf[j][h];
+                        if ((ik & CIAO_FLAG_HAZARD) && valid[h])
+                            sold[h] = __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h]));
+                    }
+                    double snew[CPT];
+                    if (ALG == ALG_SAGA) {  // SAGA_basic.jl:56-65
+#pragma unroll
+                        for (int q = 0; q < CPT; ++q) {
+                            const double so = (q & 1) ? sold[q / 2].y : sold[q / 2].x;
+                            const double g = grad_elem<LOSS>(a[q], c, tl);
+                            const double diff = __dsub_rn(g, so);
+                            double w;
+                            if (p.sag) {
+                                av[q] = __dadd_rn(av[q], __ddiv_rn(diff, p.Nd));
+                                w = __dsub_rn(z[q], __dmul_rn(p.gamma, av[q]));
+                            } else {
+                                w = __dsub_rn(z[q], __dmul_rn(p.gamma, __dadd_rn(diff, av[q])));
+                                av[q] = __dadd_rn(av[q], __ddiv_rn(diff, p.Nd));
+                            }
+                            z[q] = prox_elem<REG>(w, gl, blo[q], bhi[q]);
+                            snew[q] = g;
+                        }
+                    } else {  // Finito_basic.jl:112-118
+                        const double cneg = -__ddiv_rn(tgam, p.Nd);
+                        const double rr = __ddiv_rn(p.hat_gamma, tgam);
+#pragma unroll
+                        for (int q = 0; q < CPT; ++q) {
+                            const double so = (q & 1) ? sold[q / 2].y : sold[q / 2].x;
+                            double t = __dmul_rn(grad_elem<LOSS>(a[q], c, tl), cneg);
+                            t = __dadd_rn(t, z[q]);
+                            av[q] = __dadd_rn(av[q], __dmul_rn(__dsub_rn(t, so), rr));
+                            snew[q] = t;
+                        }
+                        if (ik & CIAO_FLAG_PROX) {
+#pragma unroll
+                            for (int q = 0; q < CPT; ++q) z[q] = prox_elem<REG>(av[q], gl, blo[q], bhi[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < H; ++h)
+                        if (valid[h])
+                            __stcg(reinterpret_cast<double2 *>(trow + gcol[h]), make_double2(snew[2 * h], snew[2 * h + 1]));
+                }
+
+                // ---- rotate the pipelines: this register slot now serves step k+P ---------
+                if (NEED_IDX) {
+                    iq[j] = in1;
+                    if (TABLE && k + P < K) {
+                        const double *nrow = p.table + (in1 & CIAO_IDX_MASK) * p.d_pad;
+#pragma unroll
+                        for (int h = 0; h < H; ++h)
+                            if (valid[h]) tbuf[j][h] = __ldcg(reinterpret_cast<const double2 *>(nrow + gcol[h]));
+                    }
+                    in1 = in2;
+                    in2 = (k + P + 2 < K) ? __ldg(p.idx + k + P + 2) : 0;
+                }
+                PROF_T(t_e);
+                PROF_ADD(0, t_a, t_b);  // wait for the prefetched row
+                PROF_ADD(1, t_b, t_c);  // LDS + dots + warp shuffles
+                PROF_ADD(2, t_c, t_d);  // cluster exchange
+                PROF_ADD(3, t_d, t_e);  // butterfly of partials + fused update + pipeline rotation
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) a[q] = an[q];
+                tb = nb;
+                tl = nl;
+                tgam = ng;
+            }
+        }
+
+        // ---- epilogue: state back to HBM ------------------------------------------------
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            if (!valid[h]) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int q = 2 * h + e;
+                const int64_t g = gcol[h] + e;
+                if (ALG == ALG_SVRG) {  // SVRG_basic.jl:84-86
+                    const double zfull = __ddiv_rn(zs[q], p.m_d);
+                    p.v_zfull[g] = zfull;
+                    p.v_w[g] = p.plus ? z[q] : zfull;
+                    p.v_zsum[g] = 0.0;
+                } else {
+                    p.v_z[g] = z[q];
+                    p.v_av[g] = av[q];
+                }
+            }
+        }
+#ifdef CIAO_SEQ_PROFILE
+        if (tid == 0 && rank == 0)
+            for (int i = 0; i < 4; ++i) g_seq_prof[i] = prof_acc[i];
+#endif
+    }
+    cluster_sync_all();  // nobody exits while a peer may still touch its shared memory
+}
+
+// ---------------------------------------------------------------------------
+struct SeqShape {
+    int C, Tc, cpt, npart_pad;
+    int64_t dc;
+};
+
+template <int CPT, int ALG, int LOSS, int REG>
+static int launch_seq(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
+    auto kern = seq_kernel<CPT, ALG, LOSS, REG>;
+    const size_t smem = (size_t)SEQ_D * ((size_t)sh.Tc * CPT + CIAO_TAIL) * 8 + 2 * (size_t)sh.npart_pad * 2 * 8 + (SEQ_D + 2) * 8 + 128;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sh.C);
+    cfg.blockDim = dim3(sh.Tc + 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = sh.C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+    return CIAO_OK;
+}
+
+template <int CPT, int ALG, int LOSS>
+static int launch_seq_reg(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
+    switch (c->reg.kind) {
+        case CIAO_REG_NORML1: return launch_seq<CPT, ALG, LOSS, CIAO_REG_NORML1>(c, a, sh);
+        case CIAO_REG_INDBOX: return launch_seq<CPT, ALG, LOSS, CIAO_REG_INDBOX>(c, a, sh);
+        default: return launch_seq<CPT, ALG, LOSS, CIAO_REG_ZERO>(c, a, sh);
+    }
+}
+
+template <int CPT, int ALG>
+static int launch_seq_loss(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
+    return c->loss_kind == CIAO_LOSS_LS ? launch_seq_reg<CPT, ALG, CIAO_LOSS_LS>(c, a, sh)
+                                        : launch_seq_reg<CPT, ALG, CIAO_LOSS_LOGISTIC>(c, a, sh);
+}
+
+// Chooses the cluster shape: C CTAs × Tc compute threads × CPT columns per thread cover d_pad.
+static int seq_shape(ciao_ctx *c, SeqShape *sh) {
+    const int64_t d_pad = c->d_pad;
+    int C = c->seq_cluster > 0 ? c->seq_cluster : (d_pad >= 2048 ? 8 : (d_pad >= 512 ? 4 : 1));
+    while (C > 1 && (d_pad % (4 * C) != 0)) C >>= 1;
+    const int64_t dc = d_pad / C;
+    const int T_target = c->seq_threads > 0 ? std::min(c->seq_threads, 256) : 128;
+    int cpt = 2;
+    while (cpt < 8 && (dc + cpt - 1) / cpt > T_target) cpt *= 2;
+    const int64_t T = ((dc + cpt - 1) / cpt + 31) / 32 * 32;
+    if (T > 256 || C * (T / 32) > SEQ_MAX_PART)
+        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "sequential kernel: d = %lld too large for cluster %d", (long long)c->d, C);
+    sh->C = C; sh->Tc = (int)T; sh->cpt = cpt; sh->dc = dc;
+    sh->npart_pad = (C * (int)(T / 32) + 31) / 32 * 32;
+    return CIAO_OK;
+}
+
+// one translation unit per algorithm (seq_svrg.cu, …) instantiates this
+template <int ALG>
+static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d) {
+    if (K <= 0) return CIAO_OK;
+    SeqShape sh;
+    CIAO_TRY(seq_shape(c, &sh));
+    SeqArgs a;
+    a.rec = c->rec; a.ld = c->ld; a.d_pad = c->d_pad; a.dc = sh.dc;
+    a.idx = idx_prepared; a.K = K; a.table = c->table;
+    a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_zfull = ctx_vec(c, CIAO_VEC_Z_FULL); a.v_w = ctx_vec(c, CIAO_VEC_W);
+    a.v_av = ctx_vec(c, CIAO_VEC_AV); a.v_zsum = ctx_vec(c, CIAO_VEC_Z);  // SVRG: state.z is the running sum of inner iterates
+    a.gamma = c->gamma; a.hat_gamma = c->hat_gamma; a.Nd = (double)c->N_total; a.m_d = m_d;
+    a.plus = c->plus; a.sag = c->sag; a.reg = c->reg; a.npart_pad = sh.npart_pad;
+    CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
+    int rc;
+    switch (sh.cpt) {
+        case 2: rc = launch_seq_loss<2, ALG>(c, a, sh); break;
+        case 4: rc = launch_seq_loss<4, ALG>(c, a, sh); break;
+        default: rc = launch_seq_loss<8, ALG>(c, a, sh); break;
+    }
+    CIAO_TRY(rc);
+    CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));
+    c->timing.launches += 1;
+    c->timing.last_seq_steps = K;
+    c->seq_timed = true;
+    return CIAO_OK;
+}

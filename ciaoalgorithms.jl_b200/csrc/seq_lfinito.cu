@@ -1,0 +1,7 @@
+// seq_lfinito.cu — instantiates the persistent cluster kernel (seq_impl.cuh) for ALG_LFINITO; one translation
+// unit per algorithm so that the template instances compile in parallel.
+#include "seq_impl.cuh"
+
+int run_seq_lfinito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d) {
+    return run_seq_alg<ALG_LFINITO>(c, idx_prepared, K, m_d);
+}

@@ -1,0 +1,16 @@
+// seq_svrg.cu — instantiates the persistent cluster kernel (seq_impl.cuh) for ALG_SVRG; one translation
+// unit per algorithm so that the template instances compile in parallel.
+#include "seq_impl.cuh"
+
+int run_seq_svrg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d) {
+    return run_seq_alg<ALG_SVRG>(c, idx_prepared, K, m_d);
+}
+
+#ifdef CIAO_SEQ_PROFILE
+// debug builds only (scripts/prof_seq.py): per-phase cycles of the last SVRG inner kernel
+extern "C" int ciao_debug_seq_prof(ciao_ctx *c, long long *out4) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(out4, g_seq_prof, 4 * sizeof(long long)));
+    return CIAO_OK;
+}
+#endif

@@ -17,7 +17,7 @@ m = min(N, 1 << 17)
 idx = np.random.default_rng(1).integers(1, N + 1, size=m, dtype=np.int64)
 names = ["wait_row", "lds_dot_shfl", "exchange", "sum_update"]
 prof = (C.c_longlong * 4)()
-for C_, T in [(8, 128), (4, 256), (8, 64), (2, 512), (8, 256)]:
+for C_, T in [(8, 128), (4, 256), (8, 64), (8, 256), (4, 128)]:
     e.set_tuning(seq_cluster=C_, seq_threads=T)
     e.svrg_init(np.zeros(d), gamma, True)
     e.svrg_epoch(idx)
