@@ -214,7 +214,7 @@ def main():
     x0 = np.zeros(d)
     peak, peak_src = measured_peak()
     K, W = args.steps, max(args.warmup, 3)
-    ld = (d + 3) // 4 * 4 + 4
+    ld = (d + 3) // 4 * 4 + 8
 
     sampler = ClockSampler(local)
     if rank == 0:

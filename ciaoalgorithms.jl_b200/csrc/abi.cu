@@ -71,12 +71,17 @@ __global__ void pack_tails_kernel(double *rec, int64_t n_rows, int64_t d_pad, in
     double *t = rec + i * ld + d_pad;
     t[0] = b[i];
     t[1] = scale ? scale[i] : scale_scalar;
-    t[2] = 0.0;
-    t[3] = 0.0;
+    for (int k = 2; k < CIAO_TAIL; ++k) t[k] = 0.0;
 }
-__global__ void set_gamma_tail_kernel(double *rec, int64_t n_rows, int64_t d_pad, int64_t ld, const double *gam) {
+__global__ void set_gamma_tail_kernel(double *rec, int64_t n_rows, int64_t d_pad, int64_t ld, const double *gam, double Nd,
+                                      double hat_gamma) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n_rows) rec[i * ld + d_pad + 2] = gam[i];
+    if (i >= n_rows) return;
+    double *t = rec + i * ld + d_pad;
+    const double g = gam[i];
+    t[TAIL_GAM] = g;
+    t[TAIL_GAM_N] = __ddiv_rn(g, Nd);
+    t[TAIL_HAT_GAM] = __ddiv_rn(hat_gamma, g);
 }
 
 // ---------------------------------------------------------------------------
@@ -219,7 +224,7 @@ static int alloc_table(ciao_ctx *c) {
 }
 
 static int set_gammas(ciao_ctx *c, const double *gamma_N, bool tails) {
-    if (!c->gamma_dev) CUDA_TRY(cudaMalloc(&c->gamma_dev, (size_t)c->N_total * sizeof(double)));
+    if (!c->gamma_dev) CUDA_TRY(cudaMalloc(&c->gamma_dev, (size_t)c->N_total * 2 * sizeof(double)));  // γ_i, then γ_i/N
     if (is_device_ptr(gamma_N)) {
         CUDA_TRY(cudaMemcpyAsync(c->gamma_dev, gamma_N, (size_t)c->N_total * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     } else {
@@ -227,7 +232,8 @@ static int set_gammas(ciao_ctx *c, const double *gamma_N, bool tails) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
     if (tails) {
-        set_gamma_tail_kernel<<<blocks_for(c->n_rows), 256, 0, c->stream>>>(c->rec, c->n_rows, c->d_pad, c->ld, c->gamma_dev);
+        set_gamma_tail_kernel<<<blocks_for(c->n_rows), 256, 0, c->stream>>>(c->rec, c->n_rows, c->d_pad, c->ld, c->gamma_dev,
+                                                                             (double)c->N_total, c->hat_gamma);
         CUDA_TRY(cudaGetLastError());
         c->timing.launches += 1;
     }

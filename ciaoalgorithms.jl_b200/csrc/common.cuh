@@ -10,13 +10,20 @@
 
 // ---------------------------------------------------------------------------
 // HBM data layout
-//   records : [n_rows][ld]  fp64, ld = d_pad + 4, d_pad = round_up(d, 4)
-//             row record i = [ a_i (d, zero padded to d_pad) | b_i or y_i | λ_i or μ_i | γ_i | 0 ]
-//             → one TMA bulk copy brings a row and its scalars; records are 32-byte aligned.
+//   records : [n_rows][ld]  fp64, ld = d_pad + 8, d_pad = round_up(d, 4)
+//             row record i = [ a_i (d, zero padded to d_pad) | tail of 8 scalars ]
+//             tail = b_i or y_i | λ_i or μ_i | γ_i | γ_i/N | γ̂/γ_i | 0 | 0 | 0
+//             → one TMA bulk copy brings a row and its scalars (no per-step division, no
+//             dependent scalar loads); records are 32-byte aligned.
 //   table   : [N][d_pad]    fp64  (SAGA gradients / Finito, ProShI s_i)
 //   vecs    : [CIAO_NUM_VECS][d_pad]  state vectors
 // ---------------------------------------------------------------------------
-#define CIAO_TAIL 4
+#define CIAO_TAIL 8
+#define TAIL_B 0       // b_i (LS) or y_i (logistic)
+#define TAIL_LAM 1     // λ_i or μ_i
+#define TAIL_GAM 2     // γ_i                      (Finito/LFinito, Finito_basic.jl:61-74)
+#define TAIL_GAM_N 3   // γ_i / N                  (Finito_basic.jl:79,113)
+#define TAIL_HAT_GAM 4 // γ̂ / γ_i                  (Finito_basic.jl:115, Finito_LFinito.jl:98)
 #define CIAO_NUM_VECS 8
 #define CIAO_VEC_SPARE 5
 #define CIAO_VEC_X0 6
@@ -185,6 +192,15 @@ __device__ __forceinline__ void st_async_v2f64(uint32_t remote_addr, double a, d
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+
+// x / den for a loop-invariant den with rden = 1/den precomputed (correctly rounded): one Newton
+// correction of q0 = x·rden with the exact remainder.  Gives the correctly rounded quotient (Markstein)
+// without the ~40-instruction division subroutine on the step's critical path.
+__device__ __forceinline__ double div_by(double x, double den, double rden) {
+    const double q0 = __dmul_rn(x, rden);
+    const double rem = fma(-q0, den, x);
+    return fma(rem, rden, q0);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -3,7 +3,7 @@
 #include "common.cuh"
 #include "../../include/ciao_gen.h"
 
-// row records [n_rows][ld]: a_i | b_i or y_i | scale | γ_i = 0 | 0
+// row records [n_rows][ld]: a_i | tail = b_i or y_i | scale | 0 …
 __global__ void gen_records_kernel(double *rec, int64_t n_rows, int64_t row0, int64_t d, int64_t d_pad, int64_t ld,
                                    int kind, uint64_t seed, double scale) {
     const int64_t total = n_rows * ld;

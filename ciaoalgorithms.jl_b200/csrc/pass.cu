@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
         mbar_wait(&full[slot], parity);
         const double *sp = ring + (size_t)slot * stage_doubles;
 
-        double a[RPG][CPT], pd[RPG], tb[RPG], tl[RPG], tg[RPG];
+        double a[RPG][CPT], pd[RPG], tb[RPG], tl[RPG], tg[RPG], tgn[RPG];
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
             pd[r] = 0.0;
@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
                 }
             }
             tb[r] = rv ? rp[p.d_pad] : 0.0;
-            tl[r] = rv ? rp[p.d_pad + 1] : 0.0;
-            tg[r] = (rv && MODE == PASS_FINITO_INIT) ? rp[p.d_pad + 2] : 1.0;
+            tl[r] = rv ? rp[p.d_pad + TAIL_LAM] : 0.0;
+            tg[r] = (rv && MODE == PASS_FINITO_INIT) ? rp[p.d_pad + TAIL_GAM] : 1.0;
+            tgn[r] = (rv && MODE == PASS_FINITO_INIT) ? rp[p.d_pad + TAIL_GAM_N] : 0.0;
         }
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
 #pragma unroll
                 for (int e = 0; e < CPT; ++e) acc[e] = fma(cc, a[r][e], acc[e]);
             } else {
-                const double cg = __ddiv_rn(tg[r], p.Nd);  // γ_i / N
+                const double cg = tgn[r];  // γ_i / N, precomputed in the record tail
                 double *trow = p.table + (r0 + r) * p.d_pad;
 #pragma unroll
                 for (int k = 0; k < CPT / 2; ++k) {

@@ -20,6 +20,7 @@ struct ProshiArgs {
     const double *qd, *ql;  // [N][n_pad]
     double *table;          // [N][n_pad]
     const double *gam;      // [N]
+    const double *gam_n;    // [N]  γ_i/N, precomputed (ProShI_basic.jl:116)
     const int64_t *idx;     // prepared
     int64_t K, N, n_pad;
     double *v_z, *v_av;
@@ -50,14 +51,16 @@ __global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
     const double lo0 = p.reg.lo_v ? p.reg.lo_v[col] : p.reg.lo_s, lo1 = p.reg.lo_v ? p.reg.lo_v[col + 1] : p.reg.lo_s;
     const double hi0 = p.reg.hi_v ? p.reg.hi_v[col] : p.reg.hi_s, hi1 = p.reg.hi_v ? p.reg.hi_v[col + 1] : p.reg.hi_s;
     const double gl = p.hat_gamma * p.reg.lambda;
+    const double rhat = __ddiv_rn(1.0, p.hat_gamma);
 
     int64_t iq[PROSHI_P];
-    double gq[PROSHI_P];
+    double gq[PROSHI_P], nq[PROSHI_P];
     double2 qq[PROSHI_P], cq[PROSHI_P], sq[PROSHI_P];
     auto fetch = [&](int j, int64_t pidx) {
         const int64_t i = pidx & CIAO_IDX_MASK;
         iq[j] = pidx;
         gq[j] = __ldg(p.gam + i);
+        nq[j] = __ldg(p.gam_n + i);
         qq[j] = __ldg(reinterpret_cast<const double2 *>(p.qd + i * p.n_pad + col));
         cq[j] = __ldg(reinterpret_cast<const double2 *>(p.ql + i * p.n_pad + col));
         sq[j] = __ldcg(reinterpret_cast<const double2 *>(p.table + i * p.n_pad + col));
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
             double2 s = sq[j];
             if (ik & CIAO_FLAG_HAZARD) s = __ldcg(srow);
             const double gi = gq[j];
-            const double cneg = -__ddiv_rn(gi, p.Nd);
+            const double cneg = -nq[j];
             // ProShI_basic.jl:113-119
             av0 = __dsub_rn(av0, s.x);
             av1 = __dsub_rn(av1, s.y);
@@ -90,8 +93,8 @@ __global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
             av1 = __dadd_rn(av1, t1);
             __stcg(srow, make_double2(t0, t1));
             if (ik & CIAO_FLAG_PROX) {  // :121-123
-                z0 = __ddiv_rn(__dsub_rn(proshi_prox_rt(p.reg, av0, gl, lo0, hi0), av0), p.hat_gamma);
-                z1 = __ddiv_rn(__dsub_rn(proshi_prox_rt(p.reg, av1, gl, lo1, hi1), av1), p.hat_gamma);
+                z0 = div_by(__dsub_rn(proshi_prox_rt(p.reg, av0, gl, lo0, hi0), av0), p.hat_gamma, rhat);
+                z1 = div_by(__dsub_rn(proshi_prox_rt(p.reg, av1, gl, lo1, hi1), av1), p.hat_gamma, rhat);
             }
             if (k + PROSHI_P < p.K) fetch(j, in1);
             in1 = (k + PROSHI_P + 1 < p.K) ? __ldg(p.idx + k + PROSHI_P + 1) : 0;
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
 
 // grid (row groups, column chunks of 512); ws[blockIdx.x][n_pad] = partial Σ s_i
 __global__ void __launch_bounds__(256) proshi_init_kernel(const double *qd, const double *ql, const double *gam,
-                                                          const double *x0, double *table, double *ws, int64_t N,
+                                                          double *gam_n, const double *x0, double *table, double *ws, int64_t N,
                                                           int64_t n_pad, double box_lo, double box_hi, double eta,
                                                           double Nd) {
     const int64_t col = 2 * (blockIdx.y * (int64_t)blockDim.x + threadIdx.x);
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(256) proshi_init_kernel(const double *qd, cons
         const double2 q = __ldcs(reinterpret_cast<const double2 *>(qd + i * n_pad + col));
         const double2 c = __ldcs(reinterpret_cast<const double2 *>(ql + i * n_pad + col));
         const double cg = __ddiv_rn(__ldg(gam + i), Nd);
+        if (col == 0) gam_n[i] = cg;
         const double s0 = __dsub_rn(xa, __dmul_rn(cg, proshi_grad(q.x, c.x, xa, box_lo, box_hi, eta)));
         const double s1 = __dsub_rn(xb, __dmul_rn(cg, proshi_grad(q.y, c.y, xb, box_lo, box_hi, eta)));
         __stcs(reinterpret_cast<double2 *>(table + i * n_pad + col), make_double2(s0, s1));
@@ -195,7 +199,7 @@ int run_proshi_init(ciao_ctx *c, const double *x0_dev) {
     grid2d(c, c->N_total, c->d_pad, &grid, &G);
     CIAO_TRY(ws_reserve(c, ((size_t)G * c->d_pad + 16) * sizeof(double)));
     CUDA_TRY(cudaEventRecord(c->ev_pa, c->stream));
-    proshi_init_kernel<<<grid, 256, 0, c->stream>>>(c->qd, c->ql, c->gamma_dev, x0_dev, c->table, c->ws, c->N_total,
+    proshi_init_kernel<<<grid, 256, 0, c->stream>>>(c->qd, c->ql, c->gamma_dev, c->gamma_dev + c->N_total, x0_dev, c->table, c->ws, c->N_total,
                                                     c->d_pad, c->box_lo, c->box_hi, c->eta, (double)c->N_total);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev_pb, c->stream));
@@ -216,7 +220,7 @@ int run_proshi_dual(ciao_ctx *c) {
 int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K) {
     if (K <= 0) return CIAO_OK;
     ProshiArgs a;
-    a.qd = c->qd; a.ql = c->ql; a.table = c->table; a.gam = c->gamma_dev; a.idx = idx_prepared;
+    a.qd = c->qd; a.ql = c->ql; a.table = c->table; a.gam = c->gamma_dev; a.gam_n = c->gamma_dev + c->N_total; a.idx = idx_prepared;
     a.K = K; a.N = c->N_total; a.n_pad = c->d_pad;
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_av = ctx_vec(c, CIAO_VEC_AV);
     a.box_lo = c->box_lo; a.box_hi = c->box_hi; a.eta = c->eta; a.Nd = (double)c->N_total; a.hat_gamma = c->hat_gamma;

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
         const double gstep = (ALG == ALG_SVRG || ALG == ALG_SAGA) ? p.gamma : p.hat_gamma;
         const double gl = gstep * p.reg.lambda;
         const double cN = __ddiv_rn(p.hat_gamma, p.Nd);  // LFinito: γ̂/N
+        const double rN = __ddiv_rn(1.0, p.Nd);
         const int E = p.npart_pad >> 5;                  // partials per lane in the final butterfly
 
         // ---- index / table-row prefetch pipelines (not needed by SVRG) -------------------
@@ -173,8 +174,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
         int slot = 0;
         uint32_t row_phase = 0;
         // software pipeline: the row of step k+1 is pulled into registers while step k's exchange is in flight
-        double a[CPT], tb = 0.0, tl = 0.0, tgam = 0.0;
-        auto load_row = [&](double (&ar)[CPT], double &rb, double &rl, double &rg) {
+        double a[CPT], tb = 0.0, tl = 0.0, tgn = 0.0, thg = 0.0;
+        auto load_row = [&](double (&ar)[CPT], double &rb, double &rl, double &rg, double &rh) {
             mbar_wait(&row_bar[slot], row_phase);
             const double *rp = ring + slot * slot_doubles;
 #pragma unroll
@@ -184,14 +185,15 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 ar[2 * h + 1] = v.y;
             }
             rb = rp[cover];
-            rl = rp[cover + 1];
-            rg = rp[cover + 2];
+            rl = rp[cover + TAIL_LAM];
+            rg = (ALG == ALG_FINITO) ? rp[cover + TAIL_GAM_N] : 0.0;                          // γ_i/N
+            rh = (ALG == ALG_FINITO || ALG == ALG_LFINITO) ? rp[cover + TAIL_HAT_GAM] : 0.0;  // γ̂/γ_i
             if (++slot == D) {
                 slot = 0;
                 row_phase ^= 1;
             }
         };
-        if (K > 0) load_row(a, tb, tl, tgam);
+        if (K > 0) load_row(a, tb, tl, tgn, thg);
         for (int64_t k0 = 0; k0 < K; k0 += P) {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
@@ -224,8 +226,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                     const uint32_t dst = smem_u32(part + ((size_t)par * p.npart_pad + rank * W + warp) * 2);
                     st_async_v2f64(mapa_u32(dst, lane), v0, v1, mapa_u32(smem_u32(&part_bar[par]), lane));
                 }
-                double an[CPT], nb = 0.0, nl = 0.0, ng = 0.0;
-                if (k + 1 < K) load_row(an, nb, nl, ng);
+                double an[CPT], nb = 0.0, nl = 0.0, ng = 0.0, nh = 0.0;
+                if (k + 1 < K) load_row(an, nb, nl, ng, nh);
                 mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
                 PROF_T(t_d);
                 // every warp reduces the same C·W partials with the same butterfly → identical bits everywhere
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                     }
                 } else if (ALG == ALG_LFINITO) {  // Finito_LFinito.jl:94-98
                     const double czf = loss_coef<LOSS>(u1, tb, tl), czz = loss_coef<LOSS>(u0, tb, tl);
-                    const double rr = __ddiv_rn(p.hat_gamma, tgam);
+                    const double rr = thg;  // γ̂/γ_i
 #pragma unroll
                     for (int q = 0; q < CPT; ++q) {
                         av[q] = __dadd_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(a[q], czf, tl)));
@@ -284,18 +286,18 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                             const double diff = __dsub_rn(g, so);
                             double w;
                             if (p.sag) {
-                                av[q] = __dadd_rn(av[q], __ddiv_rn(diff, p.Nd));
+                                av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));
                                 w = __dsub_rn(z[q], __dmul_rn(p.gamma, av[q]));
                             } else {
                                 w = __dsub_rn(z[q], __dmul_rn(p.gamma, __dadd_rn(diff, av[q])));
-                                av[q] = __dadd_rn(av[q], __ddiv_rn(diff, p.Nd));
+                                av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));
                             }
                             z[q] = prox_elem<REG>(w, gl, blo[q], bhi[q]);
                             snew[q] = g;
                         }
                     } else {  // Finito_basic.jl:112-118
-                        const double cneg = -__ddiv_rn(tgam, p.Nd);
-                        const double rr = __ddiv_rn(p.hat_gamma, tgam);
+                        const double cneg = -tgn;  // −(γ_i/N)
+                        const double rr = thg;     // γ̂/γ_i
 #pragma unroll
                         for (int q = 0; q < CPT; ++q) {
                             const double so = (q & 1) ? sold[q / 2].y : sold[q / 2].x;
@@ -336,7 +338,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 for (int q = 0; q < CPT; ++q) a[q] = an[q];
                 tb = nb;
                 tl = nl;
-                tgam = ng;
+                tgn = ng;
+                thg = nh;
             }
         }
 

@@ -1,0 +1,376 @@
+# CIAOAlgorithmsCUDA.jl — drop-in Julia front-end over libciao_cuda (B200, sm_100a).
+#
+# Same solver structs, keyword arguments, `iterate`/`solution`/`iterator` protocol and
+# count semantics as kul-optec/CIAOAlgorithms.jl v0.1.1; the bodies of `Base.iterate`
+# are `ccall`s into the C ABI of include/ciao_cuda.h instead of Julia loops over
+# ProximalOperators calls.  Index draws stay here, through the reference's own RNG
+# call sites (rand / StatsBase.sample / randperm on the global RNG), so the sampled
+# sequence is the reference's bit for bit.
+#
+# NOTE: Julia is not installed in the build image, so this file has not been executed
+# there; the Python twin (ciaoalgorithms.jl_b200/solvers.py) exercises the same ABI
+# calls in the same order and is the tested path.  Field names of ProximalOperators
+# objects (A, b, lambda; f, L; y, mu; Q, q; ind, lambda; fs; lb, ub) follow v0.14.
+module CIAOAlgorithmsCUDA
+
+using LinearAlgebra, Random, Printf
+using ProximalOperators
+using StatsBase: sample
+using Base.Iterators: take
+
+export solution, SVRG, SAGA, SAG, Finito, Proshi, iterator
+
+const libciao = get(ENV, "LIBCIAO_CUDA", "libciao_cuda")
+const Maybe{T} = Union{T,Nothing}
+const CIAO_VEC_Z, CIAO_VEC_Z_FULL, CIAO_VEC_W, CIAO_VEC_AV = Cint(0), Cint(1), Cint(2), Cint(3)
+
+struct CiaoError <: Exception
+    code::Cint
+    msg::String
+end
+function check(code::Cint)
+    code == 0 && return nothing
+    throw(CiaoError(code, unsafe_string(ccall((:ciao_last_error, libciao), Cstring, ()))))
+end
+
+mutable struct Ctx
+    h::Ptr{Cvoid}
+    N::Int
+    d::Int
+    function Ctx(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ciao_create, libciao), Cint, (Ref{Ptr{Cvoid}}, Cint), r, device))
+        c = new(r[], 0, 0)
+        finalizer(x -> ccall((:ciao_destroy, libciao), Cint, (Ptr{Cvoid},), x.h), c)
+        return c
+    end
+end
+
+# ---- F / g recognition (replaces dynamic dispatch on F::Array{Tf}, SVRG_basic.jl:2) --------------
+function set_problem!(c::Ctx, F::AbstractVector, g, N::Int)
+    f1 = F[1]
+    if f1 isa ProximalOperators.LeastSquares            # test_lasso.jl:53-54: LeastSquares(A[i:i,:], b[i:i], N)
+        d = size(f1.A, 2)
+        A = Matrix{Float64}(undef, d, N)                 # column-major d×N == row-major N×d
+        b = Vector{Float64}(undef, N); s = Vector{Float64}(undef, N)
+        for i = 1:N
+            size(F[i].A, 1) == 1 || error("engine covers 1×d LeastSquares terms")
+            copyto!(view(A, :, i), vec(F[i].A)); b[i] = F[i].b[1]; s[i] = F[i].lambda
+        end
+        GC.@preserve A b s check(ccall((:ciao_set_rows, libciao), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Float64),
+            c.h, 0, N, 0, N, d, A, d, b, s, 0.0))
+        c.N, c.d = N, d
+    elseif f1 isa ProximalOperators.Precompose && f1.f isa ProximalOperators.LogisticLoss   # test_logistic_l1.jl:36
+        d = size(f1.L, 2)
+        A = Matrix{Float64}(undef, d, N); y = Vector{Float64}(undef, N); mu = Vector{Float64}(undef, N)
+        for i = 1:N
+            copyto!(view(A, :, i), vec(F[i].L)); y[i] = F[i].f.y[1]; mu[i] = F[i].f.mu
+        end
+        GC.@preserve A y mu check(ccall((:ciao_set_rows, libciao), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Float64),
+            c.h, 1, N, 0, N, d, A, d, y, mu, 0.0))
+        c.N, c.d = N, d
+    elseif f1 isa ProximalOperators.Sum                  # test_sharing.jl:18-22: Sum(Quadratic(diagm(d_i), q), SqrDistL2(IndBox, η))
+        quad(f) = first(x for x in f.fs if x isa ProximalOperators.Quadratic)
+        dist(f) = first(x for x in f.fs if x isa ProximalOperators.SqrDistL2)
+        n = length(quad(f1).q)
+        Qd = Matrix{Float64}(undef, n, N); ql = Matrix{Float64}(undef, n, N)
+        for i = 1:N
+            Q = quad(F[i]).Q
+            isdiag(Q) || error("engine covers diagonal Quadratic terms")
+            Qd[:, i] .= diag(Q); ql[:, i] .= quad(F[i]).q
+        end
+        bx = dist(f1).ind
+        GC.@preserve Qd ql check(ccall((:ciao_set_blocks, libciao), Cint,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Float64, Float64),
+            c.h, N, n, Qd, n, ql, n, Float64(bx.lb), Float64(bx.ub), Float64(dist(f1).lambda)))
+        c.N, c.d = N, n
+    else
+        error("f_i of type $(typeof(f1)) is outside the engine's scope (no CPU fallback)")
+    end
+    if g isa ProximalOperators.NormL1
+        p = Float64[g.lambda]; GC.@preserve p check(ccall((:ciao_set_reg, libciao), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), c.h, 1, p, 1))
+    elseif g isa ProximalOperators.IndBox
+        lo = g.lb isa Number ? fill(Float64(g.lb), c.d) : Vector{Float64}(g.lb)
+        hi = g.ub isa Number ? fill(Float64(g.ub), c.d) : Vector{Float64}(g.ub)
+        p = vcat(lo, hi); GC.@preserve p check(ccall((:ciao_set_reg, libciao), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), c.h, 2, p, length(p)))
+    elseif g isa ProximalOperators.Zero
+        check(ccall((:ciao_set_reg, libciao), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), c.h, 0, C_NULL, 0))
+    else
+        error("g of type $(typeof(g)) is outside the engine's scope (Zero, NormL1, IndBox)")
+    end
+    return c
+end
+
+getvec!(c::Ctx, which::Cint, out::Vector{Float64}) =
+    (GC.@preserve out check(ccall((:ciao_get_vec, libciao), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), c.h, which, out, length(out))); out)
+
+# ================================ SVRG / SVRG++ (SVRG.jl, SVRG_basic.jl) ================================
+struct SVRG{R<:Real}
+    γ::Maybe{R}; maxit::Int; verbose::Bool; freq::Int; m::Maybe{Int}; plus::Bool
+    function SVRG{R}(; γ::Maybe{R} = nothing, maxit::Int = 10000, verbose::Bool = false, freq::Int = 1000,
+                     m::Maybe{Int} = nothing, plus::Bool = false) where {R}
+        @assert γ === nothing || γ > 0
+        @assert maxit > 0
+        @assert freq > 0
+        new(γ, maxit, verbose, freq, m, plus)
+    end
+end
+SVRG(::Type{R}; kwargs...) where {R} = SVRG{R}(; kwargs...)
+SVRG(; kwargs...) = SVRG(Float64; kwargs...)
+
+struct SVRG_basic_iterable{R,Tx,Tf,Tg}
+    F::Tf; g::Tg; x0::Tx; N::Int; L; μ; γ::Maybe{R}; m::Maybe{Int}; plus::Bool
+end
+mutable struct SVRG_basic_state{R}
+    ctx::Ctx; γ::R; m::Int; z_full::Vector{Float64}; ind::Vector{Int}
+end
+
+function Base.iterate(iter::SVRG_basic_iterable{R}) where {R}
+    N = iter.N
+    m = iter.m === nothing ? N : iter.m
+    if iter.γ === nothing
+        if iter.plus
+            @warn "provide a stepsize γ"; return nothing
+        elseif iter.L === nothing || iter.μ === nothing
+            @warn "smoothness or convexity parameter absent"; return nothing
+        end
+        L_M = maximum(iter.L); μ_M = maximum(iter.μ); γ = 1 / (10 * L_M)
+        rho = (1 + 4 * L_M * γ^2 * μ_M * (N + 1)) / (μ_M * γ * N * (1 - 4L_M * γ))
+        rho >= 1 && @warn "convergence condition violated...provide a stepsize!"
+    else
+        γ = iter.γ
+    end
+    c = set_problem!(Ctx(), iter.F, iter.g, N)
+    x0 = Vector{Float64}(iter.x0)
+    GC.@preserve x0 check(ccall((:ciao_svrg_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint), c.h, x0, γ, iter.plus))
+    state = SVRG_basic_state{R}(c, γ, m, zeros(length(x0)), collect(1:N))
+    return state, state
+end
+
+function Base.iterate(iter::SVRG_basic_iterable{R}, state::SVRG_basic_state{R}) where {R}
+    idx = rand(state.ind, state.m)                     # SVRG_basic.jl:73 — the reference's own RNG call
+    GC.@preserve idx check(ccall((:ciao_svrg_epoch, libciao), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64), state.ctx.h, idx, length(idx)))
+    iter.plus && (state.m *= 2)                        # :93
+    return state, state
+end
+solution(state::SVRG_basic_state) = getvec!(state.ctx, CIAO_VEC_Z_FULL, state.z_full)   # same array every call (===)
+
+function (solver::SVRG{R})(x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, μ = nothing, N = N) where {R}
+    m = solver.m === nothing ? N : solver.m
+    maxit = solver.maxit
+    if solver.plus && solver.maxit > 25
+        maxit = 25
+        @warn "exponential number of inner updates...reverted to 25 maximum iterations"
+    end
+    iter = SVRG_basic_iterable{R,typeof(x0),typeof(F),typeof(g)}(F, g, x0, N, L, μ, solver.γ, m, solver.plus)
+    return drive(solver, iter, maxit, s -> s.γ)
+end
+iterator(solver::SVRG{R}, x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, μ = nothing, N = N) where {R} =
+    SVRG_basic_iterable{R,typeof(x0),typeof(F),typeof(g)}(F, g, x0, N, L, μ, solver.γ, solver.m === nothing ? N : solver.m, solver.plus)
+
+# ================================ SAGA / SAG (SAGA.jl, SAGA_basic.jl) ================================
+struct SAGA{R<:Real}
+    γ::Maybe{R}; maxit::Int; verbose::Bool; freq::Int; SAG_flag::Bool
+    function SAGA{R}(; γ::Maybe{R} = nothing, maxit::Int = 10000, verbose::Bool = false, freq::Int = 1000, SAG_flag::Bool = false) where {R}
+        @assert γ === nothing || γ > 0
+        @assert maxit > 0
+        @assert freq > 0
+        new(γ, maxit, verbose, freq, SAG_flag)
+    end
+end
+SAGA(::Type{R}; kwargs...) where {R} = SAGA{R}(; kwargs...)
+SAGA(; kwargs...) = SAGA(Float64; kwargs...)
+SAG(::Type{R}; kwargs...) where {R} = SAGA{R}(; kwargs..., SAG_flag = true)
+SAG(; kwargs...) = SAG(Float64; kwargs...)
+
+struct SAGA_basic_iterable{R,Tx,Tf,Tg}
+    F::Tf; g::Tg; x0::Tx; N::Int; L; γ::Maybe{R}; SAG::Bool
+end
+mutable struct SAGA_basic_state{R}
+    ctx::Ctx; γ::R; z::Vector{Float64}; ind::Int
+end
+function Base.iterate(iter::SAGA_basic_iterable{R}) where {R}
+    if iter.γ === nothing
+        iter.L === nothing && (@warn "smoothness parameter absent"; return nothing)
+        L_M = maximum(iter.L)
+        γ = iter.SAG ? 1 / (16 * L_M) : 1 / (3 * L_M)
+    else
+        γ = iter.γ
+    end
+    c = set_problem!(Ctx(), iter.F, iter.g, iter.N)
+    x0 = Vector{Float64}(iter.x0)
+    GC.@preserve x0 check(ccall((:ciao_saga_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint), c.h, x0, γ, iter.SAG))
+    state = SAGA_basic_state{R}(c, γ, zeros(length(x0)), 1)
+    return state, state
+end
+# k reference iterations fused into one persistent kernel; the k draws are k calls of rand(1:N) (SAGA_basic.jl:55)
+function steps!(iter::SAGA_basic_iterable, state::SAGA_basic_state, k::Int)
+    idx = Int64[rand(1:iter.N) for _ = 1:k]
+    state.ind = idx[end]
+    GC.@preserve idx check(ccall((:ciao_saga_steps, libciao), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64), state.ctx.h, idx, k))
+    return state
+end
+Base.iterate(iter::SAGA_basic_iterable{R}, state::SAGA_basic_state{R}) where {R} = (steps!(iter, state, 1); (state, state))
+solution(state::SAGA_basic_state) = getvec!(state.ctx, CIAO_VEC_Z, state.z)
+
+(solver::SAGA{R})(x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
+    drive(solver, SAGA_basic_iterable{R,typeof(x0),typeof(F),typeof(g)}(F, g, x0, N, L, solver.γ, solver.SAG_flag), solver.maxit, s -> s.γ)
+iterator(solver::SAGA{R}, x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
+    SAGA_basic_iterable{R,typeof(x0),typeof(F),typeof(g)}(F, g, x0, N, L, solver.γ, solver.SAG_flag)
+
+# ============================ Finito / MISO / DIAG, LFinito, ProShI ============================
+struct Finito{R<:Real}
+    γ::Maybe{Union{Array{R},R}}; sweeping::Int8; LFinito::Bool; adaptive::Bool; minibatch::Tuple{Bool,Int}
+    maxit::Int; verbose::Bool; freq::Int; α::R; tol::R; tol_b::R
+    function Finito{R}(; γ::Maybe{Union{Array{R},R}} = nothing, sweeping = 1, LFinito::Bool = false, adaptive::Bool = false,
+                       minibatch::Tuple{Bool,Int} = (false, 1), maxit::Int = 10000, verbose::Bool = false, freq::Int = 10000,
+                       α::R = R(0.999), tol::R = R(1e-8), tol_b::R = R(1e-9)) where {R}
+        @assert γ === nothing || minimum(γ) > 0
+        @assert maxit > 0 && tol > 0 && tol_b > 0 && freq > 0
+        new(γ, sweeping, LFinito, adaptive, minibatch, maxit, verbose, freq, α, tol, tol_b)
+    end
+end
+Finito(::Type{R}; kwargs...) where {R} = Finito{R}(; kwargs...)
+Finito(; kwargs...) = Finito(Float64; kwargs...)
+
+struct Proshi{R<:Real}
+    γ::Maybe{Union{Array{R},R}}; sweeping::Int8; minibatch::Tuple{Bool,Int}; maxit::Int; verbose::Bool; freq::Int; α::R
+    function Proshi{R}(; γ::Maybe{Union{Array{R},R}} = nothing, sweeping = 1, minibatch::Tuple{Bool,Int} = (false, 1),
+                       maxit::Int = 10000, verbose::Bool = false, freq::Int = 10000, α::R = R(0.999)) where {R}
+        @assert γ === nothing || minimum(γ) > 0
+        @assert maxit > 0 && freq > 0
+        new(γ, sweeping, minibatch, maxit, verbose, freq, α)
+    end
+end
+Proshi(::Type{R}; kwargs...) where {R} = Proshi{R}(; kwargs...)
+Proshi(; kwargs...) = Proshi(Float64; kwargs...)
+
+# kind: :finito | :lfinito | :proshi
+struct Table_iterable{R,Tx,Tf,Tg}
+    kind::Symbol; F::Tf; g::Tg; x0::Tx; N::Int; L; γ; sweeping::Int8; batch::Int; α::R
+end
+mutable struct Table_state{R}
+    kind::Symbol; ctx::Ctx; γ::Vector{R}; hat_γ::R; z::Vector{Float64}; s::Matrix{Float64}
+    d::Int; idxr::Int; idx::Int; inds::Vector{Int}
+end
+
+function stepsizes(iter::Table_iterable{R}) where {R}      # Finito_basic.jl:61-74
+    N = iter.N
+    if iter.γ === nothing
+        iter.L === nothing && (@warn "--> smoothness parameter absent"; return nothing)
+        return iter.L isa Real ? fill(iter.α * R(N) / iter.L, N) : R[iter.α * R(N) / iter.L[i] for i = 1:N]
+    end
+    return iter.γ isa Real ? fill(R(iter.γ), N) : Vector{R}(iter.γ)
+end
+
+function Base.iterate(iter::Table_iterable{R}) where {R}
+    γ = stepsizes(iter)
+    γ === nothing && return nothing
+    N = iter.N
+    hat_γ = iter.kind == :proshi ? sum(γ) : 1 / sum(1 ./ γ)           # ProShI_basic.jl:82 / Finito_basic.jl:82
+    c = set_problem!(Ctx(), iter.F, iter.g, N)
+    x0 = Vector{Float64}(iter.x0)
+    sym = iter.kind == :finito ? :ciao_finito_init : iter.kind == :lfinito ? :ciao_lfinito_init : :ciao_proshi_init
+    GC.@preserve x0 γ begin
+        if iter.kind == :finito
+            check(ccall((:ciao_finito_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ, hat_γ))
+        elseif iter.kind == :lfinito
+            check(ccall((:ciao_lfinito_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ, hat_γ))
+        else
+            check(ccall((:ciao_proshi_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ, hat_γ))
+        end
+    end
+    d = cld(N, iter.batch)
+    s = iter.kind == :proshi ? Matrix{Float64}(undef, length(x0), N) : Matrix{Float64}(undef, 0, 0)
+    state = Table_state{R}(iter.kind, c, γ, hat_γ, zeros(length(x0)), s, d, 1, 0, collect(1:d))
+    return state, state
+end
+
+batch_rows(iter::Table_iterable, j::Int) = collect(iter.batch*(j-1)+1:min(iter.batch * j, iter.N))   # Finito_basic.jl:52-57
+
+function next_batch!(iter::Table_iterable, state::Table_state)          # Finito_basic.jl:96-108, ProShI_basic.jl:97-109
+    if iter.sweeping == 1
+        return sample(1:iter.N, iter.batch, replace = false)
+    elseif iter.sweeping == 2
+        state.idxr = mod(state.idxr, state.d) + 1
+    else
+        if state.idx == state.d
+            state.inds = randperm(state.d); state.idx = 1
+        else
+            state.idx += 1
+        end
+        state.idxr = state.inds[state.idx]
+    end
+    return batch_rows(iter, state.idxr)
+end
+
+function steps!(iter::Table_iterable, state::Table_state, k::Int)
+    if iter.kind == :lfinito
+        for _ = 1:k
+            iter.sweeping == 3 && (state.inds = randperm(state.d))       # Finito_LFinito.jl:89
+            ord = Vector{Int64}(state.inds)
+            GC.@preserve ord check(ccall((:ciao_lfinito_outer, libciao), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Int64), state.ctx.h, ord, length(ord), iter.batch))
+        end
+        return state
+    end
+    idx = Int64[]; ptr = Int64[0]
+    for _ = 1:k
+        append!(idx, next_batch!(iter, state)); push!(ptr, length(idx))
+    end
+    GC.@preserve idx ptr begin
+        if iter.kind == :finito
+            check(ccall((:ciao_finito_steps, libciao), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64), state.ctx.h, idx, ptr, k))
+        else
+            check(ccall((:ciao_proshi_steps, libciao), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64), state.ctx.h, idx, ptr, k))
+        end
+    end
+    return state
+end
+Base.iterate(iter::Table_iterable{R}, state::Table_state{R}) where {R} = (steps!(iter, state, 1); (state, state))
+
+function solution(state::Table_state)
+    if state.kind == :proshi                                             # ProShI_basic.jl:127-132 — mutates the table on every call
+        s = state.s
+        GC.@preserve s check(ccall((:ciao_proshi_solution, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}), state.ctx.h, s))
+        return s                                                         # n×N column-major: column i is x_i
+    end
+    return getvec!(state.ctx, CIAO_VEC_Z, state.z)                        # Finito_basic.jl:123, Finito_LFinito.jl:105
+end
+
+function table_iterable(solver::Finito{R}, x0, F, g, L, N) where {R}
+    solver.adaptive && !solver.LFinito && error("adaptive Finito is outside the engine's scope; use CIAOAlgorithms.jl")
+    kind = solver.LFinito ? :lfinito : :finito
+    Table_iterable{R,typeof(x0),typeof(F),typeof(g)}(kind, F, g, x0, N, L, solver.γ, solver.sweeping, solver.minibatch[2], solver.α)
+end
+table_iterable(solver::Proshi{R}, x0, F, g, L, N) where {R} =
+    Table_iterable{R,typeof(x0),typeof(F),typeof(g)}(:proshi, F, g, x0, N, L, solver.γ, solver.sweeping, solver.minibatch[2], solver.α)
+
+(solver::Union{Finito{R},Proshi{R}})(x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
+    drive(solver, table_iterable(solver, x0, F, g, L, N), solver.maxit, s -> s.hat_γ)
+iterator(solver::Union{Finito{R},Proshi{R}}, x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
+    table_iterable(solver, x0, F, g, L, N)
+
+# ---- the driver loop of SVRG.jl:70-83 with the steps between two prints fused into one call ----------
+function drive(solver, iter, maxit::Int, field)
+    disp(it, state) = @printf "%5d | %.3e  \n" it field(state)
+    next = iterate(iter)
+    next === nothing && return solution(nothing)          # MethodError, as upstream
+    state = next[1]
+    it = 1
+    fused = !(iter isa SVRG_basic_iterable)
+    while it < maxit
+        nxt = solver.verbose ? min(maxit, (div(it, solver.freq) + 1) * solver.freq) : maxit
+        if fused
+            steps!(iter, state, nxt - it); it = nxt
+        else
+            iterate(iter, state); it += 1
+        end
+        solver.verbose && mod(it, solver.freq) == 0 && disp(it, state)
+    end
+    solver.verbose && mod(it, solver.freq) !== 0 && disp(it, state)
+    return solution(state), it
+end
+
+end # module

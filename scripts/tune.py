@@ -14,7 +14,7 @@ N = 1 << rows_log2
 e = Engine(0)
 e.gen_synthetic(L.SYNTH_LASSO, N, d, 0x5EED0003, scale=float(N))
 e.set_reg(L.REG_NORML1, N / 100.0)
-ld = (d + 3) // 4 * 4 + 4
+ld = (d + 3) // 4 * 4 + 8
 res = []
 if "pass" in what:
     e.set_vec(L.VEC_X, np.full(d, 1e-3))

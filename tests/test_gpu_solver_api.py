@@ -1,0 +1,177 @@
+"""The reference's own test files, replayed through the host-side mirror of its API
+(operators.py objects → solvers.py → C ABI → CUDA).  Each test cites the @testset it mirrors.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+import fixtures
+from ciaoalgorithms_jl_b200 import operators as ops
+from ciaoalgorithms_jl_b200 import solvers as S
+from ciaoalgorithms_jl_b200.sampling import HostRNG
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def lasso_problem():
+    fx = fixtures.planted_lasso(0)
+    N = fx["N"]
+    F = [ops.LeastSquares(fx["A"][i:i + 1, :], fx["b"][i:i + 1], float(N)) for i in range(N)]   # test_lasso.jl:52-58
+    return fx, F, ops.NormL1(fx["lam"])
+
+
+def logistic_problem():
+    fx = fixtures.logistic_l1()
+    F = [ops.Precompose(ops.LogisticLoss(np.array([fx["y"][i]]), 1.0), fx["A"][i].reshape(1, -1), 1.0)
+         for i in range(fx["N"])]                                                               # test_logistic_l1.jl:36
+    return fx, F, ops.NormL1(fx["lam"])
+
+
+def sharing_problem():
+    fx = fixtures.sharing()
+    box = ops.IndBox(-2.0, 2.0)
+    F = [ops.Sum(ops.Quadratic(np.diag(fx["Qdiag"][i]), np.ones(fx["n"])), ops.SqrDistL2(box, fx["eta"]))
+         for i in range(fx["N"])]                                                               # test_sharing.jl:18-23
+    return fx, F, ops.IndBox(-np.inf, np.ones(fx["n"]))
+
+
+# ---- test_lasso.jl -------------------------------------------------------------------------
+@pytest.mark.parametrize("sweeping", [1, 2, 3])
+def test_lasso_basic_finito(sweeping):                                          # :70-75
+    fx, F, g = lasso_problem()
+    x, it = S.Finito(maxit=1000, sweeping=sweeping)(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"], rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL and it == 1000 and x.dtype == np.float64
+
+
+@pytest.mark.parametrize("sweeping,batch,lfinito", [(2, 1, True), (3, 1, True), (1, 2, False), (2, 2, False), (3, 3, False),
+                                                     (2, 2, True), (3, 3, True)])
+def test_lasso_lfinito_and_minibatch(sweeping, batch, lfinito):                 # :78-125
+    fx, F, g = lasso_problem()
+    solver = S.Finito(maxit=1000, sweeping=sweeping, LFinito=lfinito, minibatch=(True, batch))
+    x, _ = solver(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"], rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL
+
+
+def test_lasso_scalar_gamma_and_scalar_L():                                     # :128-140
+    fx, F, g = lasso_problem()
+    N = fx["N"]
+    x, _ = S.Finito(maxit=1000, gamma=N / fx["L"].max())(fx["x0"], F=F, g=g, L=fx["L"], N=N, rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL
+    x, _ = S.Finito(maxit=1000)(fx["x0"], F=F, g=g, L=float(fx["L"].max()), N=N, rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL
+
+
+@pytest.mark.parametrize("sweeping,lfinito", [(1, False), (2, False), (3, True)])
+def test_lasso_finito_iterator(sweeping, lfinito):                              # :143-157
+    fx, F, g = lasso_problem()
+    solver = S.Finito(sweeping=sweeping, LFinito=lfinito)
+    it = S.iterator(solver, fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"], rng=HostRNG(1))
+    assert it.x0 is fx["x0"]
+    for state in itertools.islice(it, 2):
+        assert S.solution(state) is state.z and S.solution(state).dtype == np.float64
+
+
+def test_lasso_svrg_and_svrg_plus_plus():                                       # :164-176
+    fx, F, g = lasso_problem()
+    gamma = 1 / (7 * fx["L"].max())
+    x, it = S.SVRG(maxit=1000, gamma=gamma)(fx["x0"], F=F, g=g, N=fx["N"], rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL and it == 1000
+    x, it = S.SVRG(maxit=16, gamma=gamma, m=1, plus=True)(fx["x0"], F=F, g=g, N=fx["N"], rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL and it == 16
+
+
+def test_lasso_svrg_iterator_and_maxit_one():                                   # :179-193
+    fx, F, g = lasso_problem()
+    gamma = 1 / (7 * fx["L"].max())
+    it = S.iterator(S.SVRG(gamma=gamma), fx["x0"], F=F, g=g, N=fx["N"], rng=HostRNG(1))
+    assert it.x0 is fx["x0"]
+    for state in itertools.islice(it, 2):
+        assert S.solution(state) is state.z_full
+    first = next(iter(it))
+    x1, n = S.SVRG(gamma=gamma, maxit=1)(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"])
+    assert n == 1 and np.array_equal(S.solution(first), x1)                    # `==` upstream: bitwise
+
+
+@pytest.mark.parametrize("sag", [False, True])
+def test_lasso_saga_sag(sag):                                                   # :196-267
+    fx, F, g = lasso_problem()
+    make = S.SAG if sag else S.SAGA
+    x, _ = make(maxit=10000 if sag else 1000)(fx["x0"], F=F, g=g, N=fx["N"], L=fx["L"], rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL
+    gamma = 1 / ((16 if sag else 3) * fx["L"].max())
+    x, _ = make(maxit=10000 if sag else 1000, gamma=gamma)(fx["x0"], F=F, g=g, N=fx["N"], rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL
+    it = S.iterator(make(gamma=gamma), fx["x0"], F=F, g=g, N=fx["N"], rng=HostRNG(1))
+    for state in itertools.islice(it, 2):
+        assert S.solution(state) is state.z
+    first = next(iter(it))
+    x1, n = make(gamma=gamma, maxit=1)(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"])
+    assert n == 1 and np.array_equal(S.solution(first), x1)
+
+
+def test_missing_stepsize_warns_and_ends():                                     # SVRG_basic.jl:36-42, SAGA_basic.jl:30-32
+    fx, F, g = lasso_problem()
+    with pytest.warns(UserWarning):
+        assert list(S.iterator(S.SVRG(plus=True), fx["x0"], F=F, g=g, N=fx["N"])) == []
+    with pytest.warns(UserWarning):
+        assert list(S.iterator(S.SAGA(), fx["x0"], F=F, g=g, N=fx["N"])) == []
+    with pytest.warns(UserWarning), pytest.raises(TypeError):
+        S.Finito()(fx["x0"], F=F, g=g, N=fx["N"])                              # solution(nothing) upstream
+
+
+# ---- test_logistic_l1.jl ---------------------------------------------------------------------
+@pytest.mark.parametrize("sweeping", [1, 2, 3])
+def test_logistic_finito_golden(sweeping):                                      # :54-59
+    fx, F, g = logistic_problem()
+    x, _ = S.Finito(maxit=9000, sweeping=sweeping)(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"], rng=HostRNG(1))
+    assert np.abs(x - fx["x_star"]).max() < TOL
+
+
+def test_logistic_cyclic_solver_equals_iterator():                              # :111-122
+    fx, F, g = logistic_problem()
+    for lf in (False, True):
+        solver = S.Finito(maxit=10, sweeping=2, LFinito=lf)
+        x, _ = solver(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"])
+        last = None
+        for last in itertools.islice(S.iterator(solver, fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"]), 10):
+            pass
+        assert np.array_equal(S.solution(last), x)
+
+
+def test_logistic_svrg_golden():                                                # :126-138
+    fx, F, g = logistic_problem()
+    gamma = 1 / (10 * fx["L"].max())
+    x, _ = S.SVRG(maxit=3000, gamma=gamma)(fx["x0"], F=F, g=g, N=fx["N"], rng=HostRNG(1))
+    assert np.linalg.norm(x - fx["x_star"]) < TOL
+    x, _ = S.SVRG(maxit=16, gamma=gamma, m=fx["N"], plus=True)(fx["x0"], F=F, g=g, N=fx["N"], rng=HostRNG(1))
+    assert np.linalg.norm(x - fx["x_star"]) < TOL
+    # γ = nothing with L and μ given: γ = 1/(10 L_max) and the Theorem 3.1 check (SVRG_basic.jl:44-52)
+    with pytest.warns(UserWarning):
+        x, _ = S.SVRG(maxit=50)(fx["x0"], F=F, g=g, L=fx["L"], mu=np.full(fx["N"], 1e-6), N=fx["N"], rng=HostRNG(1))
+    assert x.shape == fx["x0"].shape
+
+
+# ---- test_sharing.jl -------------------------------------------------------------------------
+@pytest.mark.parametrize("sweeping,batch", [(1, 1), (2, 1), (3, 1), (1, 2), (2, 2), (3, 3)])
+def test_sharing_proshi_golden(sweeping, batch):                                # :38-57
+    fx, F, g = sharing_problem()
+    solver = S.Proshi(maxit=1000, sweeping=sweeping, minibatch=(True, batch))
+    x, _ = solver(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"], rng=HostRNG(1))
+    assert np.abs(x.sum(axis=0) - fx["sum_star"]).max() < TOL and x.shape == (fx["N"], fx["n"])
+
+
+def test_sharing_iterator_solution_is_table():                                  # :76-84
+    fx, F, g = sharing_problem()
+    it = S.iterator(S.Proshi(sweeping=2), fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"])
+    for state in itertools.islice(it, 2):
+        assert S.solution(state) is state.s
+
+
+def test_unsupported_operator_is_rejected_before_any_device_call():
+    fx, F, g = lasso_problem()
+    with pytest.raises(ops.UnsupportedOperator):
+        S.SAGA(gamma=0.1)(fx["x0"], F=[object()] * fx["N"], g=g, N=fx["N"])
+    with pytest.raises(ops.UnsupportedOperator):
+        S.Finito(adaptive=True)(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"])
