@@ -15,7 +15,7 @@ evaluations in one-data-pass accounting: a step with inner length m is (m + N)/N
               timed region.  The data matrix is uploaded/generated once per solve (like F in
               `solver(x0; F=...)`), reported under "setup".
   roofline  : the full-gradient pass kernel (row_pass_kernel), HBM-bound; algorithmic bytes
-              = N·(d_pad+4)·8 per launch (the row records incl. b_i, λ_i).
+              = N·(d_pad+8)·8 per launch (the row records incl. the 8-scalar tail b_i, λ_i, …).
   N > 1     : one process per GPU.  Every rank holds the full problem; the full-gradient pass is
               row-sharded (each rank streams N/G rows) and all-reduced over NCCL, the sequential
               inner epoch is replicated (it is sequential in i) → "strong" scaling.
@@ -63,33 +63,59 @@ def m_of(step, N):
 
 # ------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md), read through NVML in-process:
+    forking `nvidia-smi` every 200 ms from a process that maps 137 GB stalls the launching thread
+    (measured: ≈ 190 ms over a 5 s region), so nvidia-smi is only the fallback."""
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu]) if vis and vis.split(",")[gpu].isdigit() else gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        if self.nv is not None:
+            nv = self.nv
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            names = [n for n, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                                      ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                                      ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                                      ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)) if r & bit]
+            return float(sm), float(mx), names
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        out = [c.strip() for c in out]
+        names = [n for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:6])
+                 if v.lower().startswith("active")]
+        return float(out[0]), float(out[1]), names
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.rows.append(self._sample())
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if self.nv is not None else 1.0)
 
     def summary(self):
         self.stop_flag = True
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n in r[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 def measured_peak():
@@ -227,14 +253,16 @@ def main():
             e.full_gradient(None, 1.0 / N, out=False)
         barrier()
         l0 = e.last_timing().launches
+        pass_ms_list = []
         e.timer_begin()
         for _ in range(K):
             e.full_gradient(None, 1.0 / N, out=False)
+            pass_ms_list.append(e.last_timing().last_pass_ms)
         ms = max_over_ranks(e.timer_end())
         barrier()
         tm = e.last_timing()
         launches = tm.launches - l0
-        pass_ms = max_over_ranks(tm.last_pass_ms)
+        pass_ms = max_over_ranks(float(np.mean(pass_ms_list)))
         value = K * world / (ms / 1e3)          # epochs of 2^22 rows per second, whole job
         out = e.full_gradient(None, 1.0 / N, out=True)
         e2e_t0 = time.perf_counter()

@@ -102,6 +102,7 @@ static int alloc_common(ciao_ctx *c, int64_t N_total, int64_t row0, int64_t n_ro
     free_problem(c);
     c->N_total = N_total; c->row0 = row0; c->n_rows = n_rows; c->d = d;
     c->win0 = c->win_n = 0;
+    c->cz_valid = false;
     c->d_pad = (d + 3) / 4 * 4;
     c->ld = c->d_pad + CIAO_TAIL;
     CUDA_TRY(cudaMalloc(&c->vecs, (size_t)CIAO_NUM_VECS * c->d_pad * sizeof(double)));
@@ -505,7 +506,7 @@ extern "C" int ciao_svrg_init(ciao_ctx *c, const double *x0, double gamma, int p
     CIAO_TRY(upload_vec(c, CIAO_VEC_Z_FULL, x0));                                  // z_full = copy(x0)  :64
     CIAO_TRY(copy_vec(c, CIAO_VEC_W, CIAO_VEC_Z_FULL));                            // w = copy(x0)       :66
     CUDA_TRY(cudaMemsetAsync(ctx_vec(c, CIAO_VEC_Z), 0, (size_t)c->d_pad * 8, c->stream));  // z = 0        :65
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL)));             // :58-63
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), true));       // :58-63 (+ caches c_i(z_full))
     return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
 }
 
@@ -517,7 +518,7 @@ extern "C" int ciao_svrg_epoch(ciao_ctx *c, const int64_t *idx, int64_t m) {
     CIAO_TRY(fetch_raw_indices(c, idx, m, &raw));
     CIAO_TRY(launch_prep_indices(c, raw, m, c->N_total, c->idx_prep));
     CIAO_TRY(run_seq(c, ALG_SVRG, c->idx_prep, m, (double)m));                     // :73-86
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL)));             // :87-92
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), true));       // :87-92 (+ caches c_i(z_full))
     return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
 }
 
@@ -572,7 +573,8 @@ extern "C" int ciao_finito_init(ciao_ctx *c, const double *x0, const double *gam
     return prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, hat_gamma);                        // :84
 }
 
-static int batched_indices(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches, int64_t *n_idx_out) {
+static int batched_indices(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches, int64_t *n_idx_out,
+                           const int64_t **ptr_dev_out = nullptr) {
     if (!batch_ptr || n_batches < 0) CIAO_FAIL(CIAO_ERR_INVALID, "batch_ptr is null or n_batches < 0");
     int64_t ends[2] = {0, 0};
     CUDA_TRY(cudaMemcpy(&ends[0], batch_ptr, sizeof(int64_t), cudaMemcpyDefault));
@@ -584,6 +586,7 @@ static int batched_indices(ciao_ctx *c, const int64_t *idx, const int64_t *batch
     const int64_t *raw, *ptr_dev;
     CIAO_TRY(fetch_raw_indices(c, idx, n_idx, &raw));
     CIAO_TRY(upload_ptr(c, batch_ptr, n_batches + 1, &ptr_dev));
+    if (ptr_dev_out) *ptr_dev_out = ptr_dev;
     CIAO_TRY(launch_prep_indices(c, raw, n_idx, c->N_total, c->idx_prep));
     return launch_mark_batch_ends(c, ptr_dev, n_batches, n_idx, c->idx_prep);
 }
@@ -600,6 +603,7 @@ extern "C" int ciao_lfinito_init(ciao_ctx *c, const double *x0, const double *ga
     CIAO_TRY(need_rows(c, "ciao_lfinito_init", true));
     if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_lfinito_init: null argument or γ̂ ≤ 0");
     c->algo = ALG_LFINITO; c->hat_gamma = hat_gamma;
+    c->cz_valid = false;
     CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(set_gammas(c, gamma_N, true));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
@@ -629,7 +633,7 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
         total += (j == nb) ? last_len : r;
     }
     CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z_FULL, c->hat_gamma));             // :83
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL)));             // :85-88
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), true));       // :85-88 (+ caches c_i(z_full))
     CIAO_TRY(run_finish(c, ctx_vec(c, CIAO_VEC_Z_FULL), -(c->hat_gamma / (double)N), 1.0, ctx_vec(c, CIAO_VEC_AV)));
     if (total == 0) return CIAO_OK;
     CIAO_TRY(reserve_idx(c, (size_t)total));
@@ -666,8 +670,9 @@ extern "C" int ciao_proshi_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
     CIAO_TRY(need_blocks(c, "ciao_proshi_steps"));
     if (c->algo != ALG_PROSHI) CIAO_FAIL(CIAO_ERR_STATE, "ciao_proshi_steps before ciao_proshi_init");
     int64_t n_idx = 0;
-    CIAO_TRY(batched_indices(c, idx, batch_ptr, n_batches, &n_idx));
-    return run_proshi_steps(c, c->idx_prep, n_idx);
+    const int64_t *ptr_dev = nullptr;
+    CIAO_TRY(batched_indices(c, idx, batch_ptr, n_batches, &n_idx, &ptr_dev));
+    return run_proshi_steps(c, c->idx_prep, n_idx, ptr_dev, n_batches);
 }
 
 extern "C" int ciao_proshi_solution(ciao_ctx *c, double *S_out) {
@@ -700,6 +705,7 @@ extern "C" int ciao_set_vec(ciao_ctx *c, int which, const double *in, int64_t le
     if (!c->vecs) CIAO_FAIL(CIAO_ERR_STATE, "ciao_set_vec: no problem set");
     if (which < 0 || which > CIAO_VEC_X || len != c->d) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_vec: bad vector id or length");
     CUDA_TRY(cudaSetDevice(c->device));
+    c->cz_valid = false;  // z_full may have changed: the cached c_i(z_full) no longer apply
     return upload_vec(c, which, in);
 }
 

@@ -12,7 +12,7 @@
 // HBM data layout
 //   records : [n_rows][ld]  fp64, ld = d_pad + 8, d_pad = round_up(d, 4)
 //             row record i = [ a_i (d, zero padded to d_pad) | tail of 8 scalars ]
-//             tail = b_i or y_i | λ_i or μ_i | γ_i | γ_i/N | γ̂/γ_i | 0 | 0 | 0
+//             tail = b_i or y_i | λ_i or μ_i | γ_i | γ_i/N | γ̂/γ_i | c_i(z_full) | 0 | 0
 //             → one TMA bulk copy brings a row and its scalars (no per-step division, no
 //             dependent scalar loads); records are 32-byte aligned.
 //   table   : [N][d_pad]    fp64  (SAGA gradients / Finito, ProShI s_i)
@@ -24,6 +24,7 @@
 #define TAIL_GAM 2     // γ_i                      (Finito/LFinito, Finito_basic.jl:61-74)
 #define TAIL_GAM_N 3   // γ_i / N                  (Finito_basic.jl:79,113)
 #define TAIL_HAT_GAM 4 // γ̂ / γ_i                  (Finito_basic.jl:115, Finito_LFinito.jl:98)
+#define TAIL_CZ 5      // c_i(z_full) cached by the last full-gradient pass at z_full (SVRG_basic.jl:74)
 #define CIAO_NUM_VECS 8
 #define CIAO_VEC_SPARE 5
 #define CIAO_VEC_X0 6
@@ -65,6 +66,7 @@ struct ciao_ctx {
     int algo = 0;                      // 1 svrg, 2 saga, 3 finito, 4 lfinito, 5 proshi
     double gamma = 0, hat_gamma = 0;
     int plus = 0, sag = 0;
+    bool cz_valid = false;             // record tails hold c_i(z_full) for the current z_full
     // workspace
     double *ws = nullptr;  size_t ws_bytes = 0;
     double *partial = nullptr;         // [d_pad + 8] partial d-vector + scalars (allreduce buffer)

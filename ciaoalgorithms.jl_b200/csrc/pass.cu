@@ -23,6 +23,7 @@ enum { PASS_GRAD = 0, PASS_SAGA_INIT = 1, PASS_FINITO_INIT = 2, PASS_NORMS = 3 }
 
 struct PassArgs {
     const double *rec;   // [n_rows][ld]
+    double *cz_out;      // same records, written: tail slot TAIL_CZ ← c_i(x) (nullptr: do not cache)
     int64_t n_rows, ld, d_pad;
     const double *x;     // [d_pad]
     double *ws;          // [grid][d_pad]
@@ -135,7 +136,10 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
                 continue;
             }
             const double c = loss_coef<LOSS>(u, tb[r], tl[r]);
-            if (tid == 0) fsum += loss_value<LOSS>(u, tb[r], tl[r]);
+            if (tid == 0) {
+                fsum += loss_value<LOSS>(u, tb[r], tl[r]);
+                if (MODE == PASS_GRAD && p.cz_out) p.cz_out[(r0 + r) * p.ld + p.d_pad + TAIL_CZ] = c;
+            }
             if (MODE == PASS_GRAD) {
                 const double cc = (LOSS == CIAO_LOSS_LS) ? c * tl[r] : c;
 #pragma unroll
@@ -218,7 +222,7 @@ static int launch_cpt(ciao_ctx *c, int mode, const PassArgs &a, int grid, int T,
 int ciao_comm_allreduce(ciao_ctx *c, double *buf, int64_t count, int op_max);  // comm.cu
 
 // Runs one streaming pass.  Result: c->partial[0..d_pad) = Σ (unscaled, all ranks), c->partial[d_pad] = Σ f_i (or max).
-int run_row_pass(ciao_ctx *c, int mode, const double *x_dev) {
+int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = false) {
     if (c->loss_kind != CIAO_LOSS_LS && c->loss_kind != CIAO_LOSS_LOGISTIC)
         CIAO_FAIL(CIAO_ERR_STATE, "row pass: no row problem set (ciao_set_rows / ciao_gen_synthetic first)");
     const int64_t d_pad = c->d_pad;
@@ -252,7 +256,9 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev) {
         c->ws_bytes = need;
     }
     PassArgs a;
-    a.rec = c->rec + w0 * c->ld; a.n_rows = wn; a.ld = c->ld; a.d_pad = d_pad; a.x = x_dev;
+    a.rec = c->rec + w0 * c->ld; a.n_rows = wn; a.ld = c->ld;
+    a.cz_out = (cache_cz && mode == PASS_GRAD && !windowed && c->world == 1) ? c->rec : nullptr;
+    if (mode == PASS_GRAD && cache_cz) c->cz_valid = a.cz_out != nullptr; a.d_pad = d_pad; a.x = x_dev;
     a.ws = c->ws; a.fws = c->ws + (size_t)grid * d_pad; a.table = c->table;
     a.Nd = (double)c->N_total; a.stages = S;
     if ((mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT) && !c->table)

@@ -104,6 +104,96 @@ __global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
     p.v_av[col] = av0; p.v_av[col + 1] = av1;
 }
 
+// ---------------------------------------------------------------------------
+// Minibatch path (batch ≥ PROSHI_BATCH_MIN blocks): inside a batch every block uses the same z
+// (ProShI_basic.jl:111-120), so the blocks are independent and av only needs Σ_i (t_i − s_i).  A CTA owns
+// 8 columns (one 64-byte chunk of every row) for the WHOLE call, its threads work through the blocks of
+// a batch in parallel, a fixed-order CTA reduction closes the batch and the dual update of the CTA's own
+// columns follows — columns never interact, so there is no grid-wide synchronisation and the kernel
+// streams the three block arrays at HBM rate.  Bitwise reproducible (fixed thread ↔ block mapping).
+constexpr int PROSHI_BATCH_MIN = 64;
+constexpr int PROSHI_BT = 256;  // threads per CTA
+
+__global__ void __launch_bounds__(PROSHI_BT) proshi_batch_kernel(const ProshiArgs p, const int64_t *ptr, int64_t n_batches) {
+    __shared__ double red[2][PROSHI_BT / 32][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t col = 8 * (int64_t)blockIdx.x;
+    bool cv[4];
+    double z[8], av[8], lo[8], hi[8];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        cv[h] = col + 2 * h < p.n_pad;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int q = 2 * h + e;
+            const int64_t g = col + q;
+            z[q] = cv[h] ? p.v_z[g] : 0.0;
+            av[q] = cv[h] ? p.v_av[g] : 0.0;
+            lo[q] = (cv[h] && p.reg.lo_v) ? p.reg.lo_v[g] : p.reg.lo_s;
+            hi[q] = (cv[h] && p.reg.hi_v) ? p.reg.hi_v[g] : p.reg.hi_s;
+        }
+    }
+    const double gl = p.hat_gamma * p.reg.lambda;
+    const double rhat = __ddiv_rn(1.0, p.hat_gamma);
+
+    for (int64_t b = 0; b < n_batches; ++b) {
+        const int64_t lo_t = ptr[b], hi_t = ptr[b + 1];
+        double ds[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ds[q] = 0.0;
+        for (int64_t t = lo_t + tid; t < hi_t; t += PROSHI_BT) {
+            const int64_t i = __ldg(p.idx + t) & CIAO_IDX_MASK;
+            const double gi = __ldg(p.gam + i), cneg = -__ldg(p.gam_n + i);
+            const int64_t off = i * p.n_pad + col;
+            double2 q2[4], c2[4], s2[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (!cv[h]) continue;
+                q2[h] = __ldcs(reinterpret_cast<const double2 *>(p.qd + off) + h);
+                c2[h] = __ldcs(reinterpret_cast<const double2 *>(p.ql + off) + h);
+                s2[h] = __ldcg(reinterpret_cast<const double2 *>(p.table + off) + h);
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (!cv[h]) continue;
+                // ProShI_basic.jl:114-119 for two columns
+                const double x0 = __dadd_rn(s2[h].x, __dmul_rn(gi, z[2 * h])), x1 = __dadd_rn(s2[h].y, __dmul_rn(gi, z[2 * h + 1]));
+                const double t0 = __dadd_rn(__dmul_rn(proshi_grad(q2[h].x, c2[h].x, x0, p.box_lo, p.box_hi, p.eta), cneg), x0);
+                const double t1 = __dadd_rn(__dmul_rn(proshi_grad(q2[h].y, c2[h].y, x1, p.box_lo, p.box_hi, p.eta), cneg), x1);
+                ds[2 * h] += __dsub_rn(t0, s2[h].x);
+                ds[2 * h + 1] += __dsub_rn(t1, s2[h].y);
+                __stcg(reinterpret_cast<double2 *>(p.table + off) + h, make_double2(t0, t1));
+            }
+        }
+        // close the batch: fixed-order CTA reduction of Σ(t − s), then av and the dual variable z (:121-123)
+        const int par = (int)(b & 1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            ds[q] = warp_sum(ds[q]);
+            if (lane == 0) red[par][warp][q] = ds[q];
+        }
+        __syncthreads();  // also orders this batch's table writes before the next batch's reads (same CTA, same columns)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < PROSHI_BT / 32; ++w) s += red[par][w][q];
+            av[q] = __dadd_rn(av[q], s);
+            z[q] = div_by(__dsub_rn(proshi_prox_rt(p.reg, av[q], gl, lo[q], hi[q]), av[q]), p.hat_gamma, rhat);
+        }
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (!cv[h]) continue;
+            p.v_z[col + 2 * h] = z[2 * h];
+            p.v_z[col + 2 * h + 1] = z[2 * h + 1];
+            p.v_av[col + 2 * h] = av[2 * h];
+            p.v_av[col + 2 * h + 1] = av[2 * h + 1];
+        }
+    }
+}
+
 // grid (row groups, column chunks of 512); ws[blockIdx.x][n_pad] = partial Σ s_i
 __global__ void __launch_bounds__(256) proshi_init_kernel(const double *qd, const double *ql, const double *gam,
                                                           double *gam_n, const double *x0, double *table, double *ws, int64_t N,
@@ -217,7 +307,7 @@ int run_proshi_dual(ciao_ctx *c) {
     return CIAO_OK;
 }
 
-int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K) {
+int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, const int64_t *ptr_dev, int64_t n_batches) {
     if (K <= 0) return CIAO_OK;
     ProshiArgs a;
     a.qd = c->qd; a.ql = c->ql; a.table = c->table; a.gam = c->gamma_dev; a.gam_n = c->gamma_dev + c->N_total; a.idx = idx_prepared;
@@ -225,10 +315,15 @@ int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K) {
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_av = ctx_vec(c, CIAO_VEC_AV);
     a.box_lo = c->box_lo; a.box_hi = c->box_hi; a.eta = c->eta; a.Nd = (double)c->N_total; a.hat_gamma = c->hat_gamma;
     a.reg = c->reg;
-    const int T = c->seq_threads > 0 ? std::min(c->seq_threads, 64) : 32;
-    const int grid = (int)((c->d_pad / 2 + T - 1) / T);
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
-    proshi_steps_kernel<<<grid, T, 0, c->stream>>>(a);
+    if (n_batches > 0 && K / n_batches >= PROSHI_BATCH_MIN) {
+        // minibatches: blocks of a batch in parallel, one CTA per 8 columns
+        proshi_batch_kernel<<<(int)((c->d_pad + 7) / 8), PROSHI_BT, 0, c->stream>>>(a, ptr_dev, n_batches);
+    } else {
+        const int T = c->seq_threads > 0 ? std::min(c->seq_threads, 64) : 32;
+        const int grid = (int)((c->d_pad / 2 + T - 1) / T);
+        proshi_steps_kernel<<<grid, T, 0, c->stream>>>(a);
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));
     c->timing.launches += 1;

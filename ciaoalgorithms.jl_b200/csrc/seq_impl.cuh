@@ -9,24 +9,27 @@
 // Design.  A cluster of C CTAs splits the d columns; a compute thread
 // owns CPT fixed columns of every state vector (w/z, av, z_full, Σw) in REGISTERS for
 // the whole call.  Each CTA has W compute warps and one PRODUCER warp.  Per step:
-//   1. producer: the sampled row slice a_i[cols of this CTA] + its scalars (b_i, λ_i, γ_i)
-//      is TMA-prefetched (cp.async.bulk, D-deep mbarrier ring) from the host-generated
-//      index sequence D steps ahead; a slot is known to be free when the exchange phase
-//      of the step that used it has completed;
+//   1. producer: the sampled row slice a_i[cols of this CTA] + its record tail (b_i, λ_i,
+//      γ_i/N, γ̂/γ_i, cached c_i(z_full)) + the prepared index word are staged D steps ahead
+//      into an mbarrier ring by TMA (cp.async.bulk), driven by the host-generated index
+//      sequence; table rows (SAGA/Finito) are pulled into L2 by a bulk L2 prefetch at the
+//      same time.  A slot is free once the exchange phase of the step that used it is over.
 //   2. compute: partial dots → warp shuffles → each warp pushes its partial into EVERY CTA
 //      of the cluster through DSMEM with st.async (a remote store that completes on the
 //      destination CTA's mbarrier by tx-count, so neither side needs a cluster-scope
 //      fence); every warp then reduces the C·W partials with the same xor-butterfly, so
 //      all threads of all CTAs hold bit-identical scalars — no CTA or cluster barrier
-//      instruction on the step's critical path;
+//      instruction on the step's critical path.  While the exchange is in flight the row
+//      of step k+1 and the table row of step k+2 are pulled into registers.
 //   3. the variance-reduced / aggregated update, the table row write and prox_g are
 //      fused, element by element, in the reference's rounding order.
-// Table rows are prefetched P steps ahead into registers by their owner threads
-// (generic proxy; the same thread reads and writes a given address → coherent); when a
-// row index repeats inside the prefetch window the step is flagged by
-// prep_indices_kernel and reloads the row after the previous write.
+// Table rows are read and written by their owner threads only (generic proxy; the same
+// thread reads and writes a given address → coherent); when a row index repeats inside
+// the two-step register prefetch window the step is flagged by prep_indices_kernel and
+// reloads the row after the previous write.
 // The step is latency/issue bound (one warp per SM sub-partition), so the loop body is
-// kept free of predicates: ring slots are zero padded to the thread grid.
+// kept free of predicates and global index loads: ring slots are zero padded to the thread
+// grid and carry everything a step needs.
 #pragma once
 #include <algorithm>
 
@@ -54,15 +57,21 @@ __device__ long long g_seq_prof[4];  // accumulated cycles of thread 0 of CTA 0 
 #define PROF_ADD(i, a, b)
 #endif
 
-constexpr int SEQ_D = 8;          // row ring depth (steps of prefetch)
-constexpr int SEQ_MAX_PART = 128; // C·W ≤ 128
+constexpr int SEQ_D = 8;           // row ring depth (steps of prefetch), power of two
+constexpr int SEQ_MAX_PART = 128;  // C·W ≤ 128
+constexpr int SEQ_SLOT_EXTRA = CIAO_TAIL + 2;  // record tail + index word (+ pad to keep slots 16-byte aligned)
 
-template <int CPT, int ALG, int LOSS, int REG>
+__device__ __forceinline__ void tma_prefetch_l2(const void *gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+
+// CZ: c_i(z_full) is read from the record tail (written by the last full-gradient pass at z_full)
+// instead of being recomputed from a second dot product a_i·z_full.
+template <int CPT, int ALG, int LOSS, int REG, bool CZ>
 __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
     constexpr bool TABLE = (ALG == ALG_SAGA || ALG == ALG_FINITO);
-    constexpr bool TWO_DOTS = (ALG == ALG_SVRG || ALG == ALG_LFINITO);
-    constexpr bool NEED_IDX = (ALG != ALG_SVRG);
-    constexpr int P = CPT >= 8 ? 4 : 6;  // table-row / index prefetch distance in steps
+    constexpr bool USES_ZFULL = (ALG == ALG_SVRG || ALG == ALG_LFINITO);
+    constexpr bool TWO_DOTS = USES_ZFULL && !CZ;
     constexpr int D = SEQ_D;
     constexpr int H = CPT / 2;
 
@@ -72,7 +81,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
     const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
     const int64_t dc = p.dc;
     const int cover = Tc * CPT;                       // columns covered by the thread grid (≥ dc)
-    const size_t slot_doubles = (size_t)cover + CIAO_TAIL;
+    const size_t slot_doubles = (size_t)cover + SEQ_SLOT_EXTRA;
     double *ring = reinterpret_cast<double *>(smem_raw);
     double *part = ring + D * slot_doubles;           // [2][npart_pad][2]
     uint64_t *row_bar = reinterpret_cast<uint64_t *>(part + 2 * (size_t)p.npart_pad * 2);
@@ -101,9 +110,11 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const int slot = (int)(step & (D - 1));
                 double *dst = ring + slot * slot_doubles;
                 const double *src = p.rec + i * p.ld;
+                *reinterpret_cast<int64_t *>(dst + cover + CIAO_TAIL) = pidx;  // released by the arrive below
                 mbar_arrive_expect_tx(&row_bar[slot], (uint32_t)(dc * 8 + CIAO_TAIL * 8));
                 tma_load_1d(dst, src + cbase, (uint32_t)(dc * 8), &row_bar[slot]);
                 tma_load_1d(dst + cover, src + p.d_pad, CIAO_TAIL * 8, &row_bar[slot]);
+                if (TABLE) tma_prefetch_l2(p.table + i * p.d_pad + cbase, (uint32_t)(dc * 8));
             };
             if (K > 0) mbar_arrive_expect_tx(&part_bar[0], part_bytes);
             if (K > 1) mbar_arrive_expect_tx(&part_bar[1], part_bytes);
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const int64_t g = gcol[h] + e;
                 z[q] = v ? (ALG == ALG_SVRG ? p.v_w[g] : p.v_z[g]) : 0.0;  // the running iterate: SVRG → w, others → z
                 av[q] = v ? p.v_av[g] : 0.0;
-                zf[q] = (v && TWO_DOTS) ? p.v_zfull[g] : 0.0;
+                zf[q] = (v && USES_ZFULL) ? p.v_zfull[g] : 0.0;
                 zs[q] = (v && ALG == ALG_SVRG) ? p.v_zsum[g] : 0.0;
                 blo[q] = (v && REG == CIAO_REG_INDBOX && p.reg.lo_v) ? p.reg.lo_v[g] : p.reg.lo_s;
                 bhi[q] = (v && REG == CIAO_REG_INDBOX && p.reg.hi_v) ? p.reg.hi_v[g] : p.reg.hi_s;
@@ -149,197 +160,183 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
         const double rN = __ddiv_rn(1.0, p.Nd);
         const int E = p.npart_pad >> 5;                  // partials per lane in the final butterfly
 
-        // ---- index / table-row prefetch pipelines (not needed by SVRG) -------------------
-        int64_t iq[P];
-        double2 tbuf[P][H];
-        int64_t in1 = 0, in2 = 0;
-        if (NEED_IDX) {
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                iq[j] = (j < K) ? __ldg(p.idx + j) : 0;
-                if (TABLE && j < K) {
-                    const double *trow = p.table + (iq[j] & CIAO_IDX_MASK) * p.d_pad;
-#pragma unroll
-                    for (int h = 0; h < H; ++h)
-                        tbuf[j][h] = valid[h] ? __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h])) : make_double2(0, 0);
-                }
-            }
-            in1 = (P < K) ? __ldg(p.idx + P) : 0;          // index of step k+P   (k = 0)
-            in2 = (P + 1 < K) ? __ldg(p.idx + P + 1) : 0;  // index of step k+P+1
-        }
-
-#ifdef CIAO_SEQ_PROFILE
-        long long prof_acc[4] = {0, 0, 0, 0};
-#endif
-        int slot = 0;
-        uint32_t row_phase = 0;
-        // software pipeline: the row of step k+1 is pulled into registers while step k's exchange is in flight
-        double a[CPT], tb = 0.0, tl = 0.0, tgn = 0.0, thg = 0.0;
-        auto load_row = [&](double (&ar)[CPT], double &rb, double &rl, double &rg, double &rh) {
-            mbar_wait(&row_bar[slot], row_phase);
+        struct RowRegs {
+            double a[CPT];
+            double b, lam, gn, hg, cz;  // tail: b_i | λ_i | γ_i/N | γ̂/γ_i | c_i(z_full)
+            int64_t ik;                 // prepared index word (row | flags)
+        };
+        // waits for the staged row of `step` and pulls this thread's slice + the scalars into registers
+        auto load_row = [&](int64_t step, RowRegs &r) {
+            const int slot = (int)(step & (D - 1));
+            mbar_wait(&row_bar[slot], (uint32_t)((step >> 3) & 1));
             const double *rp = ring + slot * slot_doubles;
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 const double2 v = *reinterpret_cast<const double2 *>(rp + lcol[h]);
-                ar[2 * h] = v.x;
-                ar[2 * h + 1] = v.y;
+                r.a[2 * h] = v.x;
+                r.a[2 * h + 1] = v.y;
             }
-            rb = rp[cover];
-            rl = rp[cover + TAIL_LAM];
-            rg = (ALG == ALG_FINITO) ? rp[cover + TAIL_GAM_N] : 0.0;                          // γ_i/N
-            rh = (ALG == ALG_FINITO || ALG == ALG_LFINITO) ? rp[cover + TAIL_HAT_GAM] : 0.0;  // γ̂/γ_i
-            if (++slot == D) {
-                slot = 0;
-                row_phase ^= 1;
-            }
+            r.b = rp[cover + TAIL_B];
+            r.lam = rp[cover + TAIL_LAM];
+            r.gn = (ALG == ALG_FINITO) ? rp[cover + TAIL_GAM_N] : 0.0;
+            r.hg = (ALG == ALG_FINITO || ALG == ALG_LFINITO) ? rp[cover + TAIL_HAT_GAM] : 0.0;
+            r.cz = (USES_ZFULL && CZ) ? rp[cover + TAIL_CZ] : 0.0;
+            r.ik = (ALG != ALG_SVRG) ? *reinterpret_cast<const int64_t *>(rp + cover + CIAO_TAIL) : 0;
         };
-        if (K > 0) load_row(a, tb, tl, tgn, thg);
-        for (int64_t k0 = 0; k0 < K; k0 += P) {
+        // index word of a step further ahead (its row has landed long ago: D-deep ring)
+        auto peek_index = [&](int64_t step) -> int64_t {
+            const int slot = (int)(step & (D - 1));
+            mbar_wait(&row_bar[slot], (uint32_t)((step >> 3) & 1));
+            return *reinterpret_cast<const int64_t *>(ring + slot * slot_doubles + cover + CIAO_TAIL);
+        };
+        auto load_table = [&](int64_t pidx, double2 (&t)[H]) {
+            const double *trow = p.table + (pidx & CIAO_IDX_MASK) * p.d_pad;
 #pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const int64_t k = k0 + j;
-                if (k >= K) break;
-                const int par = (int)(k & 1);
-                const int64_t ik = NEED_IDX ? iq[j] : 0;
-                PROF_T(t_a);
-                PROF_T(t_b);
+            for (int h = 0; h < H; ++h)
+                t[h] = valid[h] ? __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h])) : make_double2(0.0, 0.0);
+        };
 
-                if (ALG == ALG_LFINITO && (ik & CIAO_FLAG_PROX)) {  // Finito_LFinito.jl:92
+        RowRegs cur, nxt;
+        double2 t_cur[H], t_n1[H], t_n2[H];
+        if (K > 0) {
+            load_row(0, cur);
+            if (TABLE) {
+                load_table(cur.ik, t_cur);
+                if (K > 1) load_table(peek_index(1), t_n1);
+            }
+        }
+#ifdef CIAO_SEQ_PROFILE
+        long long prof_acc[4] = {0, 0, 0, 0};
+#endif
+        for (int64_t k = 0; k < K; ++k) {
+            const int par = (int)(k & 1);
+            PROF_T(t_a);
+            if (ALG == ALG_LFINITO && (cur.ik & CIAO_FLAG_PROX)) {  // Finito_LFinito.jl:92
 #pragma unroll
-                    for (int q = 0; q < CPT; ++q) z[q] = prox_elem<REG>(av[q], gl, blo[q], bhi[q]);
-                }
-
-                // ---- dots: v0 = a·(w|z), v1 = a·z_full ------------------------------------
-                double v0 = 0.0, v1 = 0.0;
+                for (int q = 0; q < CPT; ++q) z[q] = prox_elem<REG>(av[q], gl, blo[q], bhi[q]);
+            }
+            // ---- dots: v0 = a·(w|z), v1 = a·z_full ------------------------------------
+            double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-                for (int q = 0; q < CPT; ++q) {
-                    v0 = fma(a[q], z[q], v0);
-                    if (TWO_DOTS) v1 = fma(a[q], zf[q], v1);
+            for (int q = 0; q < CPT; ++q) {
+                v0 = fma(cur.a[q], z[q], v0);
+                if (TWO_DOTS) v1 = fma(cur.a[q], zf[q], v1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                if (TWO_DOTS) v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            }
+            PROF_T(t_b);
+            if (lane < C) {
+                const uint32_t dst = smem_u32(part + ((size_t)par * p.npart_pad + rank * W + warp) * 2);
+                st_async_v2f64(mapa_u32(dst, lane), v0, v1, mapa_u32(smem_u32(&part_bar[par]), lane));
+            }
+            // ---- while the exchange is in flight: next row, and the table row two steps ahead
+            if (k + 1 < K) load_row(k + 1, nxt);
+            if (TABLE && k + 2 < K) load_table(peek_index(k + 2), t_n2);
+            PROF_T(t_c);
+            mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
+            PROF_T(t_d);
+            // every warp reduces the same C·W partials with the same butterfly → identical bits everywhere
+            double u0 = 0.0, u1 = 0.0;
+            {
+                const double2 *pp = reinterpret_cast<const double2 *>(part + (size_t)par * p.npart_pad * 2) + lane;
+                for (int e = 0; e < E; ++e) {
+                    const double2 v = pp[e * 32];
+                    u0 += v.x;
+                    if (TWO_DOTS) u1 += v.y;
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-                    if (TWO_DOTS) v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                    u0 += __shfl_xor_sync(0xffffffffu, u0, o);
+                    if (TWO_DOTS) u1 += __shfl_xor_sync(0xffffffffu, u1, o);
                 }
-                PROF_T(t_c);
-                if (lane < C) {
-                    const uint32_t dst = smem_u32(part + ((size_t)par * p.npart_pad + rank * W + warp) * 2);
-                    st_async_v2f64(mapa_u32(dst, lane), v0, v1, mapa_u32(smem_u32(&part_bar[par]), lane));
-                }
-                double an[CPT], nb = 0.0, nl = 0.0, ng = 0.0, nh = 0.0;
-                if (k + 1 < K) load_row(an, nb, nl, ng, nh);
-                mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
-                PROF_T(t_d);
-                // every warp reduces the same C·W partials with the same butterfly → identical bits everywhere
-                double u0 = 0.0, u1 = 0.0;
-                {
-                    const double2 *pp = reinterpret_cast<const double2 *>(part + (size_t)par * p.npart_pad * 2) + lane;
-                    for (int e = 0; e < E; ++e) {
-                        const double2 v = pp[e * 32];
-                        u0 += v.x;
-                        if (TWO_DOTS) u1 += v.y;
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        u0 += __shfl_xor_sync(0xffffffffu, u0, o);
-                        if (TWO_DOTS) u1 += __shfl_xor_sync(0xffffffffu, u1, o);
-                    }
-                }
+            }
+            const double tb = cur.b, tl = cur.lam;
 
-                // ---- fused update ---------------------------------------------------------
-                if (ALG == ALG_SVRG) {  // SVRG_basic.jl:74-81
-                    const double cz = loss_coef<LOSS>(u1, tb, tl), cw = loss_coef<LOSS>(u0, tb, tl);
+            // ---- fused update ---------------------------------------------------------
+            if (ALG == ALG_SVRG) {  // SVRG_basic.jl:74-81
+                const double cz = CZ ? cur.cz : loss_coef<LOSS>(u1, tb, tl);
+                const double cw = loss_coef<LOSS>(u0, tb, tl);
 #pragma unroll
-                    for (int q = 0; q < CPT; ++q) {
-                        double t = __dsub_rn(grad_elem<LOSS>(a[q], cz, tl), grad_elem<LOSS>(a[q], cw, tl));
-                        t = __dsub_rn(t, av[q]);
-                        t = __dmul_rn(t, p.gamma);
-                        t = __dadd_rn(t, z[q]);
-                        z[q] = prox_elem<REG>(t, gl, blo[q], bhi[q]);
-                        zs[q] = __dadd_rn(zs[q], z[q]);
-                    }
-                } else if (ALG == ALG_LFINITO) {  // Finito_LFinito.jl:94-98
-                    const double czf = loss_coef<LOSS>(u1, tb, tl), czz = loss_coef<LOSS>(u0, tb, tl);
-                    const double rr = thg;  // γ̂/γ_i
+                for (int q = 0; q < CPT; ++q) {
+                    double t = __dsub_rn(grad_elem<LOSS>(cur.a[q], cz, tl), grad_elem<LOSS>(cur.a[q], cw, tl));
+                    t = __dsub_rn(t, av[q]);
+                    t = __dmul_rn(t, p.gamma);
+                    t = __dadd_rn(t, z[q]);
+                    z[q] = prox_elem<REG>(t, gl, blo[q], bhi[q]);
+                    zs[q] = __dadd_rn(zs[q], z[q]);
+                }
+            } else if (ALG == ALG_LFINITO) {  // Finito_LFinito.jl:94-98
+                const double czf = CZ ? cur.cz : loss_coef<LOSS>(u1, tb, tl);
+                const double czz = loss_coef<LOSS>(u0, tb, tl);
+                const double rr = cur.hg;  // γ̂/γ_i
 #pragma unroll
-                    for (int q = 0; q < CPT; ++q) {
-                        av[q] = __dadd_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(a[q], czf, tl)));
-                        av[q] = __dsub_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(a[q], czz, tl)));
-                        av[q] = __dadd_rn(av[q], __dmul_rn(rr, __dsub_rn(z[q], zf[q])));
-                    }
-                } else {
-                    const double c = loss_coef<LOSS>(u0, tb, tl);
-                    double2 sold[H];
-                    double *trow = p.table + (ik & CIAO_IDX_MASK) * p.d_pad;
-#pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        sold[h] = tbuf[j][h];
-                        if ((ik & CIAO_FLAG_HAZARD) && valid[h])
-                            sold[h] = __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h]));
-                    }
-                    double snew[CPT];
-                    if (ALG == ALG_SAGA) {  // SAGA_basic.jl:56-65
-#pragma unroll
-                        for (int q = 0; q < CPT; ++q) {
-                            const double so = (q & 1) ? sold[q / 2].y : sold[q / 2].x;
-                            const double g = grad_elem<LOSS>(a[q], c, tl);
-                            const double diff = __dsub_rn(g, so);
-                            double w;
-                            if (p.sag) {
-                                av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));
-                                w = __dsub_rn(z[q], __dmul_rn(p.gamma, av[q]));
-                            } else {
-                                w = __dsub_rn(z[q], __dmul_rn(p.gamma, __dadd_rn(diff, av[q])));
-                                av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));
-                            }
-                            z[q] = prox_elem<REG>(w, gl, blo[q], bhi[q]);
-                            snew[q] = g;
-                        }
-                    } else {  // Finito_basic.jl:112-118
-                        const double cneg = -tgn;  // −(γ_i/N)
-                        const double rr = thg;     // γ̂/γ_i
-#pragma unroll
-                        for (int q = 0; q < CPT; ++q) {
-                            const double so = (q & 1) ? sold[q / 2].y : sold[q / 2].x;
-                            double t = __dmul_rn(grad_elem<LOSS>(a[q], c, tl), cneg);
-                            t = __dadd_rn(t, z[q]);
-                            av[q] = __dadd_rn(av[q], __dmul_rn(__dsub_rn(t, so), rr));
-                            snew[q] = t;
-                        }
-                        if (ik & CIAO_FLAG_PROX) {
-#pragma unroll
-                            for (int q = 0; q < CPT; ++q) z[q] = prox_elem<REG>(av[q], gl, blo[q], bhi[q]);
-                        }
-                    }
+                for (int q = 0; q < CPT; ++q) {
+                    av[q] = __dadd_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(cur.a[q], czf, tl)));
+                    av[q] = __dsub_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(cur.a[q], czz, tl)));
+                    av[q] = __dadd_rn(av[q], __dmul_rn(rr, __dsub_rn(z[q], zf[q])));
+                }
+            } else {
+                const double c = loss_coef<LOSS>(u0, tb, tl);
+                double *trow = p.table + (cur.ik & CIAO_IDX_MASK) * p.d_pad;
+                if (cur.ik & CIAO_FLAG_HAZARD) {  // the row was rewritten after its prefetch was issued
 #pragma unroll
                     for (int h = 0; h < H; ++h)
-                        if (valid[h])
-                            __stcg(reinterpret_cast<double2 *>(trow + gcol[h]), make_double2(snew[2 * h], snew[2 * h + 1]));
+                        if (valid[h]) t_cur[h] = __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h]));
                 }
-
-                // ---- rotate the pipelines: this register slot now serves step k+P ---------
-                if (NEED_IDX) {
-                    iq[j] = in1;
-                    if (TABLE && k + P < K) {
-                        const double *nrow = p.table + (in1 & CIAO_IDX_MASK) * p.d_pad;
+                double snew[CPT];
+                if (ALG == ALG_SAGA) {  // SAGA_basic.jl:56-65
 #pragma unroll
-                        for (int h = 0; h < H; ++h)
-                            if (valid[h]) tbuf[j][h] = __ldcg(reinterpret_cast<const double2 *>(nrow + gcol[h]));
+                    for (int q = 0; q < CPT; ++q) {
+                        const double so = (q & 1) ? t_cur[q / 2].y : t_cur[q / 2].x;
+                        const double g = grad_elem<LOSS>(cur.a[q], c, tl);
+                        const double diff = __dsub_rn(g, so);
+                        double w;
+                        if (p.sag) {
+                            av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));
+                            w = __dsub_rn(z[q], __dmul_rn(p.gamma, av[q]));
+                        } else {
+                            w = __dsub_rn(z[q], __dmul_rn(p.gamma, __dadd_rn(diff, av[q])));
+                            av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));
+                        }
+                        z[q] = prox_elem<REG>(w, gl, blo[q], bhi[q]);
+                        snew[q] = g;
                     }
-                    in1 = in2;
-                    in2 = (k + P + 2 < K) ? __ldg(p.idx + k + P + 2) : 0;
-                }
-                PROF_T(t_e);
-                PROF_ADD(0, t_a, t_b);  // wait for the prefetched row
-                PROF_ADD(1, t_b, t_c);  // LDS + dots + warp shuffles
-                PROF_ADD(2, t_c, t_d);  // cluster exchange
-                PROF_ADD(3, t_d, t_e);  // butterfly of partials + fused update + pipeline rotation
+                } else {  // Finito_basic.jl:112-118
+                    const double cneg = -cur.gn;  // −(γ_i/N)
+                    const double rr = cur.hg;     // γ̂/γ_i
 #pragma unroll
-                for (int q = 0; q < CPT; ++q) a[q] = an[q];
-                tb = nb;
-                tl = nl;
-                tgn = ng;
-                thg = nh;
+                    for (int q = 0; q < CPT; ++q) {
+                        const double so = (q & 1) ? t_cur[q / 2].y : t_cur[q / 2].x;
+                        double t = __dmul_rn(grad_elem<LOSS>(cur.a[q], c, tl), cneg);
+                        t = __dadd_rn(t, z[q]);
+                        av[q] = __dadd_rn(av[q], __dmul_rn(__dsub_rn(t, so), rr));
+                        snew[q] = t;
+                    }
+                    if (cur.ik & CIAO_FLAG_PROX) {
+#pragma unroll
+                        for (int q = 0; q < CPT; ++q) z[q] = prox_elem<REG>(av[q], gl, blo[q], bhi[q]);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < H; ++h)
+                    if (valid[h])
+                        __stcg(reinterpret_cast<double2 *>(trow + gcol[h]), make_double2(snew[2 * h], snew[2 * h + 1]));
+            }
+            PROF_T(t_e);
+            PROF_ADD(0, t_a, t_b);  // dots + warp shuffles
+            PROF_ADD(1, t_b, t_c);  // send + next-row / table-row register prefetch
+            PROF_ADD(2, t_c, t_d);  // remaining wait for the cluster exchange
+            PROF_ADD(3, t_d, t_e);  // butterfly of partials + fused update
+            cur = nxt;
+            if (TABLE) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    t_cur[h] = t_n1[h];
+                    t_n1[h] = t_n2[h];
+                }
             }
         }
 
@@ -376,10 +373,10 @@ struct SeqShape {
     int64_t dc;
 };
 
-template <int CPT, int ALG, int LOSS, int REG>
+template <int CPT, int ALG, int LOSS, int REG, bool CZ>
 static int launch_seq(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
-    auto kern = seq_kernel<CPT, ALG, LOSS, REG>;
-    const size_t smem = (size_t)SEQ_D * ((size_t)sh.Tc * CPT + CIAO_TAIL) * 8 + 2 * (size_t)sh.npart_pad * 2 * 8 + (SEQ_D + 2) * 8 + 128;
+    auto kern = seq_kernel<CPT, ALG, LOSS, REG, CZ>;
+    const size_t smem = (size_t)SEQ_D * ((size_t)sh.Tc * CPT + SEQ_SLOT_EXTRA) * 8 + 2 * (size_t)sh.npart_pad * 2 * 8 + (SEQ_D + 2) * 8 + 128;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(sh.C);
@@ -397,12 +394,20 @@ static int launch_seq(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
     return CIAO_OK;
 }
 
+template <int CPT, int ALG, int LOSS, int REG>
+static int launch_seq_cz(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
+    if constexpr (ALG == ALG_SVRG || ALG == ALG_LFINITO) {
+        if (c->cz_valid) return launch_seq<CPT, ALG, LOSS, REG, true>(c, a, sh);
+    }
+    return launch_seq<CPT, ALG, LOSS, REG, false>(c, a, sh);
+}
+
 template <int CPT, int ALG, int LOSS>
 static int launch_seq_reg(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
     switch (c->reg.kind) {
-        case CIAO_REG_NORML1: return launch_seq<CPT, ALG, LOSS, CIAO_REG_NORML1>(c, a, sh);
-        case CIAO_REG_INDBOX: return launch_seq<CPT, ALG, LOSS, CIAO_REG_INDBOX>(c, a, sh);
-        default: return launch_seq<CPT, ALG, LOSS, CIAO_REG_ZERO>(c, a, sh);
+        case CIAO_REG_NORML1: return launch_seq_cz<CPT, ALG, LOSS, CIAO_REG_NORML1>(c, a, sh);
+        case CIAO_REG_INDBOX: return launch_seq_cz<CPT, ALG, LOSS, CIAO_REG_INDBOX>(c, a, sh);
+        default: return launch_seq_cz<CPT, ALG, LOSS, CIAO_REG_ZERO>(c, a, sh);
     }
 }
 

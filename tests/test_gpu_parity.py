@@ -267,6 +267,33 @@ def test_proshi_steps(N, n, sweeping, batch):
         assert rel(out, ref.solution()) < 1e-9
 
 
+@pytest.mark.parametrize("N,n,batch", [(700, 100, 64), (2000, 1024, 256), (1500, 36, 700)])
+@pytest.mark.parametrize("sweeping", [1, 2, 3])
+def test_proshi_parallel_minibatch_kernel(N, n, batch, sweeping):
+    """Batches of ≥ 64 blocks take the column-sliced parallel kernel (proshi_batch_kernel)."""
+    Q, _ = orc.gen_rows(orc.SYN_SHARING, n, 0x5EED0005, 0, N)
+    ql, box, eta = np.ones((N, n)), (-2.0, 2.0), 10.0 * N
+    hi = np.linspace(0.5, 1.5, n)                                        # vector bounds for g = IndBox(-Inf, hi)
+    p = orc.Problem(orc.LOSS_DIAGQUAD, Q, ql, box=box, eta=eta).set_reg(orc.REG_INDBOX, lo=-np.inf, hi=hi)
+    gam = 0.999 * N / (np.abs(Q).max(axis=1) + eta)
+    ref = orc.ProshiState(p, np.zeros(n), gam)
+    with Engine(0) as e:
+        e.gen_synthetic(L.SYNTH_SHARING, N, n, 0x5EED0005)
+        e.set_reg(L.REG_INDBOX, -np.inf, hi)
+        e.proshi_init(np.zeros(n), gam, ref.hat_gamma)
+        batches = BatchSweeper(N, batch, sweeping, HostRNG(8)).take(3 * (-(-N // batch)) + 1)
+        ref.steps(batches)
+        idx, bp = csr(batches)
+        e.proshi_steps(idx, bp)
+        assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-9
+        assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-8
+        assert rel(e.get_table_rows(), ref.s) < 1e-9
+        z1 = e.get_vec(L.VEC_Z)
+        e.proshi_init(np.zeros(n), gam, ref.hat_gamma)                   # bitwise reproducible
+        e.proshi_steps(idx, bp)
+        assert np.array_equal(z1, e.get_vec(L.VEC_Z))
+
+
 # ----------------------------------------------------------------------------
 # golden vectors of the reference's tests, reached by the CUDA engine
 def test_golden_logistic_finito_svrg_saga():
