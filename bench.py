@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--workload", default="svrgpp", choices=["svrgpp", "fullgrad"])
     ap.add_argument("--rows-log2", type=int, default=22)
     ap.add_argument("--d", type=int, default=4096)
-    ap.add_argument("--cpu-rows-log2", type=int, default=14)
+    ap.add_argument("--cpu-rows-log2", type=int, default=17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tune", default="", help="pass_threads,pass_stages,pass_ctas,seq_cluster,seq_threads")
     return ap.parse_args()
@@ -153,8 +153,10 @@ def cpu_reference(args, N_full, d, steps, warmup):
             t_total += t2 - t0
     per_eval = t_total / evals
     return {"value": 1.0 / (per_eval * N_full), "unit": "epochs/s", "cores": 1, "kind": "port",
-            "sample": f"oracle SVRG++ outer iterations on {Ns} rows x {d} (same generator), {steps} steps, "
-                      f"{evals} component gradients in {t_total:.2f} s; extrapolated to N = {N_full} per-evaluation",
+            "sample": f"oracle (C restatement of the single-threaded reference; Julia is not installed) SVRG++ outer "
+                      f"iterations on {Ns} rows x {d} (same generator), {steps} steps, {evals} component gradients in "
+                      f"{t_total:.2f} s on 1 core (the reference has no threading; its BLAS calls are 1 x d gemv); "
+                      f"extrapolated per component gradient to N = {N_full}",
             "us_per_inner_step": 1e6 * t_inner / max(1, evals - steps * Ns),
             "us_per_pass_row": 1e6 * t_pass / (steps * Ns), "seconds": t_total}, t_total / steps
 
@@ -265,9 +267,10 @@ def main():
         pass_ms = max_over_ranks(float(np.mean(pass_ms_list)))
         value = K * world / (ms / 1e3)          # epochs of 2^22 rows per second, whole job
         out = e.full_gradient(None, 1.0 / N, out=True)
+        xh = torch.full((d,), 1e-3, dtype=torch.float64).pin_memory().numpy()
+        barrier()
         e2e_t0 = time.perf_counter()
         e.timer_begin()
-        xh = torch.full((d,), 1e-3, dtype=torch.float64).pin_memory().numpy()
         for _ in range(K):
             out = e.full_gradient(xh, 1.0 / N, out=True)
         e2e_ms = max_over_ranks(e.timer_end())
@@ -346,6 +349,9 @@ def main():
 
     clocks = sampler.summary() if rank == 0 else None
     achieved = algo_bytes / pass_ms / 1e6     # GB/s
+    # dram__bytes_read.sum + dram__bytes_write.sum of row_pass_kernel from the committed `ncu --set full` capture
+    # (profiles/ncu_row_pass_r1.csv: 137.796 GB + 12 MB per launch at N=2^22, d=4096, one GPU); null for other shapes
+    traffic = 137.808e9 if (rows_per_gpu == 1 << 22 and d == 4096 and (world == 1 or weak_pass)) else None
     line = {
         "metric": "epochs/s (Lasso 4M x 4096 fp64, SVRG++)" if not weak_pass else "epochs/s (full-gradient passes, 2^22-row epochs)",
         "value": value, "unit": "epochs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -354,7 +360,7 @@ def main():
                    "epoch": "N component-gradient evaluations; step = (m + N)/N epochs", "seeds": [SEED_DATA, SEED_IDX]},
         "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "row_pass_kernel (full gradient)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes},
         "clocks": clocks, "setup": {"what": "ciao_gen_synthetic (rows generated in HBM)", "seconds": setup_s},
     }

@@ -141,28 +141,42 @@ __global__ void __launch_bounds__(PROSHI_BT) proshi_batch_kernel(const ProshiArg
         double ds[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) ds[q] = 0.0;
-        for (int64_t t = lo_t + tid; t < hi_t; t += PROSHI_BT) {
-            const int64_t i = __ldg(p.idx + t) & CIAO_IDX_MASK;
-            const double gi = __ldg(p.gam + i), cneg = -__ldg(p.gam_n + i);
-            const int64_t off = i * p.n_pad + col;
-            double2 q2[4], c2[4], s2[4];
+        // two blocks per iteration: all twelve 16-byte loads of both blocks are in flight before the first use
+        for (int64_t t = lo_t + tid; t < hi_t; t += 2 * PROSHI_BT) {
+            const bool second = t + PROSHI_BT < hi_t;
+            int64_t off[2];
+            double gi[2], cneg[2];
+            double2 q2[2][4], c2[2][4], s2[2][4];
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                if (!cv[h]) continue;
-                q2[h] = __ldcs(reinterpret_cast<const double2 *>(p.qd + off) + h);
-                c2[h] = __ldcs(reinterpret_cast<const double2 *>(p.ql + off) + h);
-                s2[h] = __ldcg(reinterpret_cast<const double2 *>(p.table + off) + h);
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !second) continue;
+                const int64_t i = __ldg(p.idx + t + u * PROSHI_BT) & CIAO_IDX_MASK;
+                gi[u] = __ldg(p.gam + i);
+                cneg[u] = -__ldg(p.gam_n + i);
+                off[u] = i * p.n_pad + col;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    if (!cv[h]) continue;
+                    q2[u][h] = __ldcs(reinterpret_cast<const double2 *>(p.qd + off[u]) + h);
+                    c2[u][h] = __ldcs(reinterpret_cast<const double2 *>(p.ql + off[u]) + h);
+                    s2[u][h] = __ldcg(reinterpret_cast<const double2 *>(p.table + off[u]) + h);
+                }
             }
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                if (!cv[h]) continue;
-                // ProShI_basic.jl:114-119 for two columns
-                const double x0 = __dadd_rn(s2[h].x, __dmul_rn(gi, z[2 * h])), x1 = __dadd_rn(s2[h].y, __dmul_rn(gi, z[2 * h + 1]));
-                const double t0 = __dadd_rn(__dmul_rn(proshi_grad(q2[h].x, c2[h].x, x0, p.box_lo, p.box_hi, p.eta), cneg), x0);
-                const double t1 = __dadd_rn(__dmul_rn(proshi_grad(q2[h].y, c2[h].y, x1, p.box_lo, p.box_hi, p.eta), cneg), x1);
-                ds[2 * h] += __dsub_rn(t0, s2[h].x);
-                ds[2 * h + 1] += __dsub_rn(t1, s2[h].y);
-                __stcg(reinterpret_cast<double2 *>(p.table + off) + h, make_double2(t0, t1));
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !second) continue;
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    if (!cv[h]) continue;
+                    // ProShI_basic.jl:114-119 for two columns
+                    const double x0 = __dadd_rn(s2[u][h].x, __dmul_rn(gi[u], z[2 * h]));
+                    const double x1 = __dadd_rn(s2[u][h].y, __dmul_rn(gi[u], z[2 * h + 1]));
+                    const double t0 = __dadd_rn(__dmul_rn(proshi_grad(q2[u][h].x, c2[u][h].x, x0, p.box_lo, p.box_hi, p.eta), cneg[u]), x0);
+                    const double t1 = __dadd_rn(__dmul_rn(proshi_grad(q2[u][h].y, c2[u][h].y, x1, p.box_lo, p.box_hi, p.eta), cneg[u]), x1);
+                    ds[2 * h] += __dsub_rn(t0, s2[u][h].x);
+                    ds[2 * h + 1] += __dsub_rn(t1, s2[u][h].y);
+                    __stcg(reinterpret_cast<double2 *>(p.table + off[u]) + h, make_double2(t0, t1));
+                }
             }
         }
         // close the batch: fixed-order CTA reduction of Σ(t − s), then av and the dual variable z (:121-123)

@@ -417,3 +417,116 @@ def test_errors():
             e.proshi_steps(np.array([1], dtype=np.int64), np.array([0, 1], dtype=np.int64))  # wrong problem kind
         with pytest.raises(CiaoError):
             e.set_reg(7)
+
+
+# ----------------------------------------------------------------------------
+# edge cases: empty / ragged inputs, tiny shapes, heavy index repetition
+def test_edge_cases_empty_and_tiny():
+    # N = 1, d = 1
+    p = orc.Problem(orc.LOSS_LS, np.array([[2.0]]), np.array([1.0]), np.array([1.0])).set_reg(orc.REG_NORML1, lam=0.01)
+    with Engine(0) as e:
+        e.set_rows(L.LOSS_LS, np.array([[2.0]]), np.array([1.0]), 1.0)
+        e.set_reg(L.REG_NORML1, 0.01)
+        ref = orc.SAGAState(p, np.zeros(1), 0.05)
+        e.saga_init(np.zeros(1), 0.05, False)
+        e.saga_steps(np.zeros(0, dtype=np.int64))                    # K = 0: nothing happens
+        assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-15
+        idx = np.ones(50, dtype=np.int64)                            # the same row 50 times: every step is a table hazard
+        ref.steps(idx)
+        e.saga_steps(idx)
+        assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-13 and rel(e.get_table_rows(), ref.s) < 1e-13
+        gam = np.array([0.3])
+        reff = orc.FinitoState(p, np.zeros(1), gam)
+        e.finito_init(np.zeros(1), gam, reff.hat_gamma)
+        e.finito_steps(np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64))          # zero batches
+        batches = [np.array([1]), np.zeros(0, dtype=np.int64), np.array([1])]              # an empty batch in the middle
+        reff.steps(batches)
+        e.finito_steps(*csr(batches))
+        assert rel(e.get_vec(L.VEC_Z), reff.z) < 1e-13
+        e.svrg_init(np.zeros(1), 0.05, False)
+        with pytest.raises(CiaoError):
+            e.svrg_epoch(np.zeros(0, dtype=np.int64), 0)             # m must be positive
+
+
+@pytest.mark.parametrize("N,d", [(37, 5), (64, 2), (129, 1027)])
+def test_ragged_shapes_all_algorithms(N, d):
+    """d not a multiple of 4 (zero-padded columns), remainder batches, N not a multiple of anything."""
+    p, e = make_rows(orc.LOSS_LOGISTIC, N, d, 0xE0 + d, lam_reg=1.0 / N)
+    Li = 0.25 * np.sum(p.A * p.A, axis=1)
+    gam = 0.999 * N / Li
+    x0 = np.linspace(-0.5, 0.5, d)
+    rng = HostRNG(6)
+    ref = orc.SVRGState(p, x0, 1 / (10 * Li.max()))
+    e.svrg_init(x0, 1 / (10 * Li.max()), False)
+    for _ in range(2):
+        idx = rng.rand_vec(N, N)
+        ref.epoch(idx)
+        e.svrg_epoch(idx)
+    assert rel(e.get_vec(L.VEC_Z_FULL), ref.z_full) < 1e-10
+    reff = orc.FinitoState(p, x0, gam)
+    e.finito_init(x0, gam, reff.hat_gamma)
+    batches = BatchSweeper(N, 5, 3, rng).take(3 * (-(-N // 5)))
+    reff.steps(batches)
+    e.finito_steps(*csr(batches))
+    assert rel(e.get_vec(L.VEC_Z), reff.z) < 1e-10 and rel(e.get_table_rows(), reff.s) < 1e-10
+    refl = orc.LFinitoState(p, x0, gam, 7)
+    e.lfinito_init(x0, gam, refl.hat_gamma)
+    sw = LFinitoSweeper(N, 7, 3, rng)
+    for _ in range(2):
+        o = sw.next()
+        refl.outer(o)
+        e.lfinito_outer(o, 7)
+    assert rel(e.get_vec(L.VEC_Z), refl.z) < 1e-10
+    e.close()
+
+
+# ----------------------------------------------------------------------------
+# BASELINE.json's full size (C3: N = 2^22, d = 4096, 137.6 GB of row records) through size-independent properties
+def test_full_scale_properties():
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 150e9:
+        pytest.skip("needs a 180 GB B200")
+    N, d = 1 << 22, 4096
+    with Engine(0) as e:
+        e.gen_synthetic(L.SYNTH_LASSO, N, d, 0x5EED0003, scale=float(N))
+        e.set_reg(L.REG_NORML1, N / 100.0)
+        rs = np.random.default_rng(0)
+        x, y = rs.standard_normal(d) * 1e-3, rs.standard_normal(d) * 1e-3
+        gx, gy = e.full_gradient(x, 1.0 / N), e.full_gradient(y, 1.0 / N)
+        # (1) bitwise run-to-run determinism of the 296-CTA streaming pass
+        assert np.array_equal(gx, e.full_gradient(x, 1.0 / N))
+        # (2) the least-squares gradient is affine in x
+        gm = e.full_gradient(0.25 * x + 0.75 * y, 1.0 / N)
+        assert rel(gm, 0.25 * gx + 0.75 * gy) < 1e-10
+        # (3) a sum of row-window passes is the full pass (what the sharded multi-GPU pass relies on)
+        acc = np.zeros(d)
+        for k in range(4):
+            e.set_pass_window(k * N // 4, N // 4)
+            acc += e.full_gradient(x, 1.0 / N)
+        e.set_pass_window(0, 0)
+        assert rel(acc, gx) < 1e-12
+        # (4) the planted model: the gradient at x_true is the noise term only, orders of magnitude below the one at 0
+        xt = orc.gen_xtrue(orc.SYN_LASSO, d, 0x5EED0003)
+        assert np.linalg.norm(e.full_gradient(xt, 1.0 / N)) < 1e-3 * np.linalg.norm(e.full_gradient(np.zeros(d), 1.0 / N))
+        # (5) rows regenerated on the host agree with what the device holds: spot-check the objective on a row window
+        A, b = Engine.gen_host(L.SYNTH_LASSO, d, 0x5EED0003, N - 1000, 1000)
+        e.set_pass_window(N - 1000, 1000)
+        f_dev = e.objective(x)[0] * N
+        e.set_pass_window(0, 0)
+        f_host = float(np.sum(0.5 * N * (A @ x - b) ** 2))
+        assert abs(f_dev - f_host) <= 1e-11 * f_host
+        # (6) SVRG++ outer iterations descend monotonically from x0 = 0 and are reproducible bit for bit
+        gamma = 1.0 / (7.0 * N * e.max_row_sqnorm())
+        idx = HostRNG(1).rand_vec(N, N // 16)
+        outs = []
+        for _ in range(2):
+            e.svrg_init(np.zeros(d), gamma, True)
+            f0 = sum(e.objective(np.zeros(d)))
+            e.svrg_epoch(idx)
+            z1 = e.get_vec(L.VEC_Z_FULL)
+            f1 = sum(e.objective(z1))
+            e.svrg_init(z1 * 0 + z1, gamma, True)
+            outs.append(z1)
+            assert f1 < f0
+        assert np.array_equal(outs[0], outs[1])
