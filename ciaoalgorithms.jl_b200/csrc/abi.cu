@@ -20,6 +20,7 @@ void ciao_set_error(const char *fmt, ...) {
 }
 
 #include "pass.cu"
+#include "batch.cu"
 #include "gen.cu"
 #include "indices.cu"
 
@@ -272,6 +273,7 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
     ciao_ctx *c = new (std::nothrow) ciao_ctx();
     if (!c) CIAO_FAIL(CIAO_ERR_OOM, "host allocation failed");
     c->device = device;
+    c->cache_cz = getenv("CIAO_CACHE_CZ") != nullptr && getenv("CIAO_CACHE_CZ")[0] == '1';
     c->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     cudaEvent_t *evs[] = {&c->ev_pa, &c->ev_pb, &c->ev_sa, &c->ev_sb, &c->tm_a, &c->tm_b};
@@ -506,7 +508,7 @@ extern "C" int ciao_svrg_init(ciao_ctx *c, const double *x0, double gamma, int p
     CIAO_TRY(upload_vec(c, CIAO_VEC_Z_FULL, x0));                                  // z_full = copy(x0)  :64
     CIAO_TRY(copy_vec(c, CIAO_VEC_W, CIAO_VEC_Z_FULL));                            // w = copy(x0)       :66
     CUDA_TRY(cudaMemsetAsync(ctx_vec(c, CIAO_VEC_Z), 0, (size_t)c->d_pad * 8, c->stream));  // z = 0        :65
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), true));       // :58-63 (+ caches c_i(z_full))
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz));  // :58-63
     return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
 }
 
@@ -518,7 +520,7 @@ extern "C" int ciao_svrg_epoch(ciao_ctx *c, const int64_t *idx, int64_t m) {
     CIAO_TRY(fetch_raw_indices(c, idx, m, &raw));
     CIAO_TRY(launch_prep_indices(c, raw, m, c->N_total, c->idx_prep));
     CIAO_TRY(run_seq(c, ALG_SVRG, c->idx_prep, m, (double)m));                     // :73-86
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), true));       // :87-92 (+ caches c_i(z_full))
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz));  // :87-92
     return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
 }
 
@@ -594,6 +596,29 @@ static int batched_indices(ciao_ctx *c, const int64_t *idx, const int64_t *batch
 extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches) {
     CIAO_TRY(need_rows(c, "ciao_finito_steps", true));
     if (c->algo != ALG_FINITO) CIAO_FAIL(CIAO_ERR_STATE, "ciao_finito_steps before ciao_finito_init");
+    // static minibatches (contiguous rows, Finito_basic.jl:52-57) of ≥ BATCH_MIN_ROWS rows: one streaming pass per batch
+    if (idx && batch_ptr && n_batches > 0 && !is_device_ptr(idx) && !is_device_ptr(batch_ptr)) {
+        bool contiguous = true;
+        int64_t longest = 0;
+        for (int64_t j = 0; j < n_batches && contiguous; ++j) {
+            const int64_t lo = batch_ptr[j], hi = batch_ptr[j + 1];
+            if (lo < 0 || hi < lo) CIAO_FAIL(CIAO_ERR_INVALID, "batch_ptr must be non-decreasing");
+            longest = std::max(longest, hi - lo);
+            if (hi > lo && (idx[lo] < 1 || idx[lo] + (hi - lo) - 1 > c->N_total)) contiguous = false;
+            for (int64_t t = lo + 1; t < hi && contiguous; ++t) contiguous = idx[t] == idx[t - 1] + 1;
+        }
+        if (contiguous && batch_ptr[0] == 0 && longest >= BATCH_MIN_ROWS) {
+            CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
+            for (int64_t j = 0; j < n_batches; ++j) {
+                const int64_t lo = batch_ptr[j], hi = batch_ptr[j + 1];
+                if (hi > lo) CIAO_TRY(run_batch_step(c, BATCH_FINITO, idx[lo] - 1, hi - lo));
+            }
+            CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));
+            c->timing.last_seq_steps = batch_ptr[n_batches];
+            c->seq_timed = true;
+            return CIAO_OK;
+        }
+    }
     int64_t n_idx = 0;
     CIAO_TRY(batched_indices(c, idx, batch_ptr, n_batches, &n_idx));
     return run_seq(c, ALG_FINITO, c->idx_prep, n_idx, 1.0);
@@ -633,9 +658,21 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
         total += (j == nb) ? last_len : r;
     }
     CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z_FULL, c->hat_gamma));             // :83
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), true));       // :85-88 (+ caches c_i(z_full))
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz));  // :85-88
     CIAO_TRY(run_finish(c, ctx_vec(c, CIAO_VEC_Z_FULL), -(c->hat_gamma / (double)N), 1.0, ctx_vec(c, CIAO_VEC_AV)));
     if (total == 0) return CIAO_OK;
+    if (r >= BATCH_MIN_ROWS) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
+        CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
+        for (int64_t jj = 0; jj < n_batches; ++jj) {
+            const int64_t j = order[jj];
+            CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));          // :92
+            CIAO_TRY(run_batch_step(c, BATCH_LFINITO, r * (j - 1), (j == nb) ? last_len : r));
+        }
+        CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));
+        c->timing.last_seq_steps = total;
+        c->seq_timed = true;
+        return CIAO_OK;
+    }
     CIAO_TRY(reserve_idx(c, (size_t)total));
     const int64_t *order_dev;
     CIAO_TRY(upload_ptr(c, order.data(), n_batches, &order_dev));

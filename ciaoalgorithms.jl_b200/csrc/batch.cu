@@ -1,0 +1,257 @@
+// batch.cu — minibatch steps of Finito and LFinito as streaming passes.
+//
+// Inside a minibatch every component gradient is evaluated at the same z (Finito_basic.jl:110-117,
+// Finito_LFinito.jl:93-99), so the rows of a batch are independent and only Σ over the batch enters av.
+// For the reference's static batches (contiguous rows r(j−1)+1..rj, Finito_basic.jl:52-57) a batch of
+// ≥ BATCH_MIN_ROWS rows is therefore one HBM-bound pass over a row window — the same TMA-ring / column-
+// owner structure as row_pass_kernel (pass.cu), plus the table read-modify-write for Finito:
+//
+//   BATCH_FINITO   t_i = z − (γ_i/N)∇f_i(z);  Σ_i (t_i − s_i)·(γ̂/γ_i);  s_i ← t_i        24·d bytes per row
+//   BATCH_LFINITO  Σ_i (γ̂/N)(∇f_i(z_full) − ∇f_i(z)),  Σ_i γ̂/γ_i                           8·d bytes per row
+//
+// followed by a fixed-order reduction of the CTA partials and a d-sized finish kernel (av update, prox).
+// Summation order inside a batch differs from the reference's sequential loop (rounding-level, covered by
+// the parity tolerance); results are bitwise reproducible run to run.
+#include "common.cuh"
+
+enum { BATCH_FINITO = 0, BATCH_LFINITO = 1 };
+constexpr int BATCH_MIN_ROWS = 256;
+
+struct BatchArgs {
+    const double *rec;   // first record of the batch window
+    int64_t n_rows, ld, d_pad;
+    const double *z, *zf;
+    double *table;       // first table row of the window (Finito)
+    double *ws, *fws;
+    double cN;           // γ̂/N
+    int stages;
+};
+
+template <int CPT, int MODE, int LOSS>
+__global__ void __launch_bounds__(256, 1) batch_pass_kernel(const BatchArgs p) {
+    constexpr int RPG = 16 / CPT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const int S = p.stages;
+    const size_t stage_doubles = (size_t)RPG * p.ld;
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    double *red = ring + (size_t)S * stage_doubles;  // [2][RPG][32][2]
+    uint64_t *full = reinterpret_cast<uint64_t *>(red + 2 * RPG * 32 * 2);
+
+    const int64_t n_groups = (p.n_rows + RPG - 1) / RPG;
+    const int64_t my_count = (blockIdx.x < n_groups) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    uint64_t policy = 0;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+        policy = l2_policy_evict_first();
+    }
+    __syncthreads();
+    auto issue = [&](int64_t it) {
+        const int64_t r0 = (blockIdx.x + it * (int64_t)gridDim.x) * RPG;
+        const int rows = (int)min((int64_t)RPG, p.n_rows - r0);
+        const uint32_t bytes = (uint32_t)(rows * p.ld * sizeof(double));
+        const int slot = (int)(it % S);
+        mbar_arrive_expect_tx(&full[slot], bytes);
+        tma_load_1d_stream(ring + (size_t)slot * stage_doubles, p.rec + r0 * p.ld, bytes, &full[slot], policy);
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < my_count && it < S; ++it) issue(it);
+
+    double zr[CPT], zfr[CPT], acc[CPT];
+    int col[CPT / 2];
+#pragma unroll
+    for (int k = 0; k < CPT / 2; ++k) {
+        col[k] = 2 * (tid + T * k);
+        const bool v = col[k] < p.d_pad;
+        if (!v) col[k] = -1;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            zr[2 * k + e] = v ? p.z[col[k] + e] : 0.0;
+            zfr[2 * k + e] = (v && MODE == BATCH_LFINITO) ? p.zf[col[k] + e] : 0.0;
+            acc[2 * k + e] = 0.0;
+        }
+    }
+    double fsum = 0.0;  // thread 0: Σ γ̂/γ_i (LFinito)
+
+    for (int64_t it = 0; it < my_count; ++it) {
+        const int slot = (int)(it % S);
+        const uint32_t parity = (uint32_t)((it / S) & 1);
+        const int par = (int)(it & 1);
+        const int64_t r0 = (blockIdx.x + it * (int64_t)gridDim.x) * RPG;
+        const int rows = (int)min((int64_t)RPG, p.n_rows - r0);
+        // old table rows: plain coalesced loads, issued before the wait so that they overlap it
+        double2 so[RPG][CPT / 2];
+        if (MODE == BATCH_FINITO) {
+#pragma unroll
+            for (int r = 0; r < RPG; ++r)
+#pragma unroll
+                for (int k = 0; k < CPT / 2; ++k)
+                    so[r][k] = (r < rows && col[k] >= 0)
+                                   ? __ldcs(reinterpret_cast<const double2 *>(p.table + (r0 + r) * p.d_pad + col[k]))
+                                   : make_double2(0.0, 0.0);
+        }
+        mbar_wait(&full[slot], parity);
+        const double *sp = ring + (size_t)slot * stage_doubles;
+        double a[RPG][CPT], p0[RPG], p1[RPG], tb[RPG], tl[RPG], tgn[RPG], thg[RPG];
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+            p0[r] = p1[r] = 0.0;
+            const bool rv = r < rows;
+            const double *rp = sp + (size_t)r * p.ld;
+#pragma unroll
+            for (int k = 0; k < CPT / 2; ++k) {
+                double2 v = make_double2(0.0, 0.0);
+                if (rv && col[k] >= 0) v = *reinterpret_cast<const double2 *>(rp + col[k]);
+                a[r][2 * k] = v.x;
+                a[r][2 * k + 1] = v.y;
+                p0[r] = fma(v.x, zr[2 * k], p0[r]);
+                p0[r] = fma(v.y, zr[2 * k + 1], p0[r]);
+                if (MODE == BATCH_LFINITO) {
+                    p1[r] = fma(v.x, zfr[2 * k], p1[r]);
+                    p1[r] = fma(v.y, zfr[2 * k + 1], p1[r]);
+                }
+            }
+            tb[r] = rv ? rp[p.d_pad + TAIL_B] : 0.0;
+            tl[r] = rv ? rp[p.d_pad + TAIL_LAM] : 0.0;
+            tgn[r] = rv ? rp[p.d_pad + TAIL_GAM_N] : 0.0;
+            thg[r] = rv ? rp[p.d_pad + TAIL_HAT_GAM] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+            p0[r] = warp_sum(p0[r]);
+            if (MODE == BATCH_LFINITO) p1[r] = warp_sum(p1[r]);
+            if (lane == 0) {
+                red[((par * RPG + r) * 32 + warp) * 2] = p0[r];
+                red[((par * RPG + r) * 32 + warp) * 2 + 1] = p1[r];
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && it + S < my_count) issue(it + S);
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
+            double u0 = 0.0, u1 = 0.0;
+            const double *rr = red + (par * RPG + r) * 32 * 2;
+            for (int w = 0; w < W; ++w) {
+                u0 += rr[2 * w];
+                u1 += rr[2 * w + 1];
+            }
+            if (r >= rows) continue;
+            const double cz = loss_coef<LOSS>(u0, tb[r], tl[r]);
+            if (MODE == BATCH_FINITO) {  // Finito_basic.jl:112-116
+                const double cneg = -tgn[r], rr2 = thg[r];
+                double *trow = p.table + (r0 + r) * p.d_pad;
+#pragma unroll
+                for (int k = 0; k < CPT / 2; ++k) {
+                    double t0 = __dadd_rn(__dmul_rn(grad_elem<LOSS>(a[r][2 * k], cz, tl[r]), cneg), zr[2 * k]);
+                    double t1 = __dadd_rn(__dmul_rn(grad_elem<LOSS>(a[r][2 * k + 1], cz, tl[r]), cneg), zr[2 * k + 1]);
+                    acc[2 * k] += __dmul_rn(__dsub_rn(t0, so[r][k].x), rr2);
+                    acc[2 * k + 1] += __dmul_rn(__dsub_rn(t1, so[r][k].y), rr2);
+                    if (col[k] >= 0) __stcs(reinterpret_cast<double2 *>(trow + col[k]), make_double2(t0, t1));
+                }
+            } else {  // Finito_LFinito.jl:94-98
+                const double czf = loss_coef<LOSS>(u1, tb[r], tl[r]);
+#pragma unroll
+                for (int e = 0; e < CPT; ++e) {
+                    acc[e] += __dmul_rn(p.cN, grad_elem<LOSS>(a[r][e], czf, tl[r]));
+                    acc[e] -= __dmul_rn(p.cN, grad_elem<LOSS>(a[r][e], cz, tl[r]));
+                }
+                if (tid == 0) fsum += thg[r];
+            }
+        }
+    }
+    double *wrow = p.ws + (size_t)blockIdx.x * p.d_pad;
+#pragma unroll
+    for (int k = 0; k < CPT / 2; ++k)
+        if (col[k] >= 0) *reinterpret_cast<double2 *>(wrow + col[k]) = make_double2(acc[2 * k], acc[2 * k + 1]);
+    if (tid == 0) p.fws[blockIdx.x] = fsum;
+}
+
+// Finito: av += Σ; z = prox_g(av, γ̂) (Finito_basic.jl:118).   LFinito: av += Σ + (z − z_full)·Σ γ̂/γ_i (:98)
+__global__ void batch_finish_kernel(const double *partial, double *av, double *z, const double *zf, int64_t d_pad, int mode,
+                                    double hat_gamma, RegParams reg) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= d_pad) return;
+    double a = __dadd_rn(av[j], partial[j]);
+    if (mode == BATCH_LFINITO) {
+        a = __dadd_rn(a, __dmul_rn(partial[d_pad], __dsub_rn(z[j], zf[j])));
+        av[j] = a;
+    } else {
+        av[j] = a;
+        const double lo = reg.lo_v ? reg.lo_v[j] : reg.lo_s, hi = reg.hi_v ? reg.hi_v[j] : reg.hi_s;
+        const double gl = hat_gamma * reg.lambda;
+        z[j] = reg.kind == CIAO_REG_NORML1 ? prox_elem<CIAO_REG_NORML1>(a, gl, lo, hi)
+               : reg.kind == CIAO_REG_INDBOX ? prox_elem<CIAO_REG_INDBOX>(a, gl, lo, hi) : a;
+    }
+}
+
+template <int CPT, int MODE>
+static int launch_batch_loss(ciao_ctx *c, const BatchArgs &a, int grid, int T, size_t smem) {
+    if (c->loss_kind == CIAO_LOSS_LS) {
+        auto kern = batch_pass_kernel<CPT, MODE, CIAO_LOSS_LS>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, T, smem, c->stream>>>(a);
+    } else {
+        auto kern = batch_pass_kernel<CPT, MODE, CIAO_LOSS_LOGISTIC>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, T, smem, c->stream>>>(a);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return CIAO_OK;
+}
+
+// One minibatch over the contiguous rows [row_lo, row_lo + n): pass + reduction + finish, on the context stream.
+int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
+    const int64_t d_pad = c->d_pad;
+    int cpt = 2;
+    while (cpt < 16 && (d_pad + cpt - 1) / cpt > 256) cpt *= 2;
+    const int64_t Tn = ((d_pad + cpt - 1) / cpt + 31) / 32 * 32;
+    if (Tn > 256) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "minibatch pass: d = %lld exceeds 4096", (long long)c->d);
+    const int T = (int)Tn, rpg = 16 / cpt;
+    const size_t stage_bytes = (size_t)rpg * c->ld * sizeof(double);
+    const size_t fixed = 2 * rpg * 32 * 2 * sizeof(double) + 16 * sizeof(uint64_t) + 256;
+    int S = 6;
+    while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)227 * 1024) --S;
+    const size_t smem = (size_t)S * stage_bytes + fixed;
+    const int64_t n_groups = (n + rpg - 1) / rpg;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_groups, c->num_sms));
+    const size_t need = ((size_t)grid * d_pad + grid + 16) * sizeof(double);
+    if (need > c->ws_bytes) {
+        if (c->ws) cudaFree(c->ws);
+        c->ws = nullptr;
+        c->ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&c->ws, need));
+        c->ws_bytes = need;
+    }
+    BatchArgs a;
+    a.rec = c->rec + row_lo * c->ld; a.n_rows = n; a.ld = c->ld; a.d_pad = d_pad;
+    a.z = ctx_vec(c, CIAO_VEC_Z); a.zf = ctx_vec(c, CIAO_VEC_Z_FULL);
+    a.table = c->table ? c->table + row_lo * d_pad : nullptr;
+    a.ws = c->ws; a.fws = c->ws + (size_t)grid * d_pad;
+    a.cN = c->hat_gamma / (double)c->N_total; a.stages = S;
+    int rc;
+    if (mode == BATCH_FINITO) {
+        switch (cpt) {
+            case 2: rc = launch_batch_loss<2, BATCH_FINITO>(c, a, grid, T, smem); break;
+            case 4: rc = launch_batch_loss<4, BATCH_FINITO>(c, a, grid, T, smem); break;
+            case 8: rc = launch_batch_loss<8, BATCH_FINITO>(c, a, grid, T, smem); break;
+            default: rc = launch_batch_loss<16, BATCH_FINITO>(c, a, grid, T, smem); break;
+        }
+    } else {
+        switch (cpt) {
+            case 2: rc = launch_batch_loss<2, BATCH_LFINITO>(c, a, grid, T, smem); break;
+            case 4: rc = launch_batch_loss<4, BATCH_LFINITO>(c, a, grid, T, smem); break;
+            case 8: rc = launch_batch_loss<8, BATCH_LFINITO>(c, a, grid, T, smem); break;
+            default: rc = launch_batch_loss<16, BATCH_LFINITO>(c, a, grid, T, smem); break;
+        }
+    }
+    CIAO_TRY(rc);
+    const int nb = (int)((d_pad + 255) / 256);
+    reduce_ws_kernel<<<nb, 256, 0, c->stream>>>(a.ws, a.fws, grid, d_pad, c->partial, c->partial + d_pad, 0, 1);
+    CUDA_TRY(cudaGetLastError());
+    batch_finish_kernel<<<nb, 256, 0, c->stream>>>(c->partial, ctx_vec(c, CIAO_VEC_AV), ctx_vec(c, CIAO_VEC_Z),
+                                                   ctx_vec(c, CIAO_VEC_Z_FULL), d_pad, mode, c->hat_gamma, c->reg);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 3;
+    return CIAO_OK;
+}

@@ -62,6 +62,25 @@ for sweeping in (1, 2):
         tot_ms += e.last_timing().last_seq_ms
     c2[f"finito_sweeping{sweeping}"] = {"epochs": K, "us_per_step": 1e3 * tot_ms / (K * N), "epochs_per_s": K / (tot_ms / 1e3),
                                         "objective": sum(e.objective(e.get_vec(L.VEC_Z)))}
+# Finito / LFinito with static minibatches of 4096 rows: streaming passes (batch.cu)
+gam = np.full(N, 0.999 * N / Lmax)
+hat = 1 / np.sum(1 / gam)
+e.finito_init(x0, gam, hat)
+sw = BatchSweeper(N, 4096, 2, rng)
+tot_ms = 0.0
+for ep in range(K):
+    idx, bp = csr(sw.take(sw.d))
+    e.finito_steps(idx, bp)
+    tot_ms += e.last_timing().last_seq_ms
+c2["finito_cyclic_batch4096"] = {"epochs": K, "us_per_row": 1e3 * tot_ms / (K * N), "epochs_per_s": K / (tot_ms / 1e3),
+                                 "GBs": K * N * (ld + 2 * d) * 8 / tot_ms / 1e6, "objective": sum(e.objective(e.get_vec(L.VEC_Z)))}
+e.lfinito_init(x0, gam, hat)
+tot_ms = 0.0
+for ep in range(K):
+    e.lfinito_outer(np.arange(1, sw.d + 1), 4096)
+    tot_ms += e.last_timing().last_seq_ms
+c2["lfinito_sweep_batch4096"] = {"sweeps": K, "us_per_row": 1e3 * tot_ms / (K * N), "sweeps_per_s": K / (tot_ms / 1e3),
+                                 "GBs": K * N * ld * 8 / tot_ms / 1e6, "objective": sum(e.objective(e.get_vec(L.VEC_Z)))}
 e.close()
 # CPU sample (oracle, 1 thread): SAGA steps on 2^14 rows
 Ns = 1 << 14
