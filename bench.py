@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="svrgpp", choices=["svrgpp", "fullgrad"])
+    ap.add_argument("--workload", default="svrgpp", choices=["svrgpp", "fullgrad", "svrgpp-sharded"])
     ap.add_argument("--rows-log2", type=int, default=22)
     ap.add_argument("--d", type=int, default=4096)
     ap.add_argument("--cpu-rows-log2", type=int, default=17)
@@ -217,12 +217,13 @@ def main():
     rows_per_gpu = 1 << args.rows_log2
     d = args.d
     weak_pass = args.workload == "fullgrad"
-    N = rows_per_gpu * world if weak_pass else rows_per_gpu
+    sharded = args.workload == "svrgpp-sharded"      # rows sharded over the GPUs, inner epoch reads remote rows over NVLink
+    N = rows_per_gpu * world if (weak_pass or sharded) else rows_per_gpu
     e = Engine(local)
     if args.tune:
         e.set_tuning(*[int(v) for v in args.tune.split(",")])
     t0 = time.perf_counter()
-    if weak_pass:
+    if weak_pass or sharded:
         e.gen_synthetic(L.SYNTH_LASSO, N, d, SEED_DATA, scale=float(N), row0=rank * rows_per_gpu, n_rows=rows_per_gpu)
     else:
         e.gen_synthetic(L.SYNTH_LASSO, N, d, SEED_DATA, scale=float(N))
@@ -235,7 +236,11 @@ def main():
             uid = torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         e.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
-        if not weak_pass:
+        if sharded:
+            handles = [None] * world
+            dist.all_gather_object(handles, e.rows_ipc_handle())
+            e.attach_peer_rows(handles, [r * rows_per_gpu for r in range(world)], [rows_per_gpu] * world, rank)
+        elif not weak_pass:
             lo, hi = (rank * N) // world, ((rank + 1) * N) // world
             e.set_pass_window(lo, hi - lo)
     gamma = 1.0 / (7.0 * N * e.max_row_sqnorm())
@@ -305,7 +310,8 @@ def main():
         ms = max_over_ranks(e.timer_end())
         barrier()
         launches = e.last_timing().launches - l0
-        epochs_total = sum((m_of(k, N) + N) / N for k in range(K))
+        epoch_rows = rows_per_gpu if sharded else N      # sharded: an "epoch" stays 2^22 component gradients
+        epochs_total = sum((m_of(k, N) + N) / epoch_rows for k in range(K))
         value = epochs_total / (ms / 1e3)
         pass_ms = max_over_ranks(float(np.mean(pass_ms_list)))
         inner_steps = sum(m_of(k, N) for k in range(K))
@@ -337,15 +343,20 @@ def main():
         e2e = {"value": epochs_total / (e2e_ms / 1e3), "unit": "epochs/s",
                "h2d_bytes_per_step": int(8 * inner_steps / K), "d2h_bytes_per_step": 8 * d, "wall_ms": wall_ms,
                "api": "solvers.iterator(SVRG(plus=True)) -> next(state) -> solution(state)"}
-        algo_bytes = (N // world) * ld * 8
+        algo_bytes = (rows_per_gpu if sharded else N // world) * ld * 8
         extra = {"svrg": {"inner_steps": inner_steps, "us_per_inner_step": 1e3 * float(np.sum(seq_ms_list)) / inner_steps,
                           "inner_ms": [round(v, 3) for v in seq_ms_list], "pass_ms": [round(v, 3) for v in pass_ms_list],
                           "objective_start": f_start, "objective_end": f_end, "checksum_x": float(np.sum(np.abs(xs)))},
-                 "full_gradient": {"rows_per_gpu": N // world, "kernel_ms": pass_ms, "gbs_per_gpu": algo_bytes / pass_ms / 1e6,
+                 "full_gradient": {"rows_per_gpu": rows_per_gpu if sharded else N // world, "kernel_ms": pass_ms,
+                                   "aggregate_gbs": N * ld * 8 / pass_ms / 1e6, "gbs_per_gpu": algo_bytes / pass_ms / 1e6,
                                    "frac_of_8TBs": algo_bytes / pass_ms / 1e6 / 8000.0}}
-        scaling = "strong"
-        workload = (f"C3 Lasso N=2^{args.rows_log2} d={d} fp64 SVRG++ gamma=1/(7 L_max) m=N/16*2^(k mod 5): persistent inner epoch + "
-                    f"full-gradient pass" + (f"; pass row-sharded over {world} GPUs + NCCL allreduce, inner epoch replicated" if world > 1 else ""))
+        scaling = "weak" if sharded else "strong"
+        if sharded:
+            workload = (f"C4-style Lasso N={world}x2^{args.rows_log2} rows sharded over {world} GPUs, d={d} fp64 SVRG++ m=N/16*2^(k mod 5): "
+                        f"sharded full-gradient pass + NCCL allreduce; inner epoch replicated, remote rows TMA-prefetched over NVLink (CUDA IPC)")
+        else:
+            workload = (f"C3 Lasso N=2^{args.rows_log2} d={d} fp64 SVRG++ gamma=1/(7 L_max) m=N/16*2^(k mod 5): persistent inner epoch + "
+                        f"full-gradient pass" + (f"; pass row-sharded over {world} GPUs + NCCL allreduce, inner epoch replicated" if world > 1 else ""))
 
     clocks = sampler.summary() if rank == 0 else None
     achieved = algo_bytes / pass_ms / 1e6     # GB/s
@@ -353,7 +364,8 @@ def main():
     # (profiles/ncu_row_pass_r1.csv: 137.796 GB + 12 MB per launch at N=2^22, d=4096, one GPU); null for other shapes
     traffic = 137.808e9 if (rows_per_gpu == 1 << 22 and d == 4096 and (world == 1 or weak_pass)) else None
     line = {
-        "metric": "epochs/s (Lasso 4M x 4096 fp64, SVRG++)" if not weak_pass else "epochs/s (full-gradient passes, 2^22-row epochs)",
+        "metric": ("epochs/s (full-gradient passes, 2^22-row epochs)" if weak_pass else
+                   "epochs/s (SVRG++ on row-sharded data, 2^22-row epochs)" if sharded else "epochs/s (Lasso 4M x 4096 fp64, SVRG++)"),
         "value": value, "unit": "epochs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "l2": "inputs larger than L2 (137 GB of row records per pass; rows sampled at random)",

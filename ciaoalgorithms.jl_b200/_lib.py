@@ -50,6 +50,8 @@ SIGNATURES = {
     "ciao_comm_unique_id": (i32, [C.c_void_p]),
     "ciao_comm_init": (i32, [_ctx, C.c_void_p, i32, i32]),
     "ciao_set_pass_window": (i32, [_ctx, i64, i64]),
+    "ciao_rows_ipc_handle": (i32, [_ctx, C.c_void_p]),
+    "ciao_attach_peer_rows": (i32, [_ctx, i32, C.c_void_p, C.c_void_p, C.c_void_p, i32]),
     "ciao_full_gradient": (i32, [_ctx, C.c_void_p, f64, C.c_void_p]),
     "ciao_objective": (i32, [_ctx, C.c_void_p, _dp, _dp]),
     "ciao_max_row_sqnorm": (i32, [_ctx, _dp]),

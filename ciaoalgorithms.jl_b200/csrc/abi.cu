@@ -37,11 +37,6 @@ static int run_seq(ciao_ctx *c, int alg, const int64_t *idx_prepared, int64_t K,
         default: return run_seq_lfinito(c, idx_prepared, K, m_d);
     }
 }
-__device__ __forceinline__ double prox_rt(int kind, double x, double gl, double lo, double hi) {
-    if (kind == CIAO_REG_NORML1) return prox_elem<CIAO_REG_NORML1>(x, gl, lo, hi);
-    if (kind == CIAO_REG_INDBOX) return prox_elem<CIAO_REG_INDBOX>(x, gl, lo, hi);
-    return x;
-}
 #include "proshi.cu"
 #include "comm.cu"
 
@@ -90,7 +85,9 @@ __global__ void set_gamma_tail_kernel(double *rec, int64_t n_rows, int64_t d_pad
 // ---------------------------------------------------------------------------
 static inline int blocks_for(int64_t n) { return (int)((n + 255) / 256); }
 
+static void detach_peers(ciao_ctx *c);
 static void free_problem(ciao_ctx *c) {
+    detach_peers(c);
     cudaFree(c->rec); cudaFree(c->qd); cudaFree(c->ql); cudaFree(c->vecs); cudaFree(c->table);
     cudaFree(c->gamma_dev); cudaFree(c->partial); cudaFree(c->reg_bounds);
     c->rec = c->qd = c->ql = c->vecs = c->table = c->gamma_dev = c->partial = c->reg_bounds = nullptr;
@@ -210,8 +207,9 @@ static int need_rows(ciao_ctx *c, const char *who, bool whole) {
     if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "%s: null context", who);
     if (c->loss_kind != CIAO_LOSS_LS && c->loss_kind != CIAO_LOSS_LOGISTIC)
         CIAO_FAIL(CIAO_ERR_STATE, "%s: no row problem set (ciao_set_rows / ciao_gen_synthetic first)", who);
-    if (whole && c->n_rows != c->N_total)
-        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "%s: the sequential loops run on one GPU holding all N rows (this context holds a shard)", who);
+    if (whole && c->n_rows != c->N_total && c->peers.n <= 1)
+        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "%s: the sequential loops need all N rows: this context holds a shard and no peer rows are attached "
+                  "(ciao_attach_peer_rows)", who);
     CUDA_TRY(cudaSetDevice(c->device));
     return CIAO_OK;
 }
@@ -221,6 +219,8 @@ static int reserve_idx(ciao_ctx *c, size_t n);
 static int reserve_for_solver(ciao_ctx *c) { return reserve_idx(c, (size_t)std::max<int64_t>(c->N_total, 1 << 16)); }
 
 static int alloc_table(ciao_ctx *c) {
+    if (c->n_rows != c->N_total)
+        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "the N×d tables of SAGA/Finito are not sharded: the context must hold all N rows");
     if (!c->table) CUDA_TRY(cudaMalloc(&c->table, (size_t)c->n_rows * c->d_pad * sizeof(double)));
     return CIAO_OK;
 }
@@ -313,6 +313,62 @@ extern "C" int ciao_set_tuning(ciao_ctx *c, int pass_threads, int pass_stages, i
         CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_tuning: value out of range");
     c->pass_threads = pass_threads; c->pass_stages = pass_stages; c->pass_ctas = pass_ctas_per_sm;
     c->seq_cluster = seq_cluster; c->seq_threads = seq_threads;
+    return CIAO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// remote rows over NVLink: every rank maps the other ranks' row shards with CUDA IPC, so
+// the sequential inner epochs (SVRG, LFinito) can sample from a problem that is sharded over several GPUs.
+// ---------------------------------------------------------------------------
+static void detach_peers(ciao_ctx *c) {
+    for (int s = 0; s < CIAO_MAX_PEERS; ++s) {
+        if (c->peer_mapped[s]) cudaIpcCloseMemHandle(c->peer_mapped[s]);
+        c->peer_mapped[s] = nullptr;
+    }
+    c->peers.n = 0;
+}
+
+extern "C" int ciao_rows_ipc_handle(ciao_ctx *c, void *out64) {
+    if (!c || !out64) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_rows_ipc_handle: null argument");
+    if (!c->rec) CIAO_FAIL(CIAO_ERR_STATE, "ciao_rows_ipc_handle: no row problem set");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, c->rec));
+    memcpy(out64, &h, sizeof(h));
+    return CIAO_OK;
+}
+
+extern "C" int ciao_attach_peer_rows(ciao_ctx *c, int n_shards, const void *handles64, const int64_t *row0, const int64_t *n_rows,
+                                     int my_shard) {
+    if (!c || !handles64 || !row0 || !n_rows) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_attach_peer_rows: null argument");
+    if (n_shards < 1 || n_shards > CIAO_MAX_PEERS || my_shard < 0 || my_shard >= n_shards)
+        CIAO_FAIL(CIAO_ERR_INVALID, "ciao_attach_peer_rows: 1..%d shards, my_shard inside", CIAO_MAX_PEERS);
+    if (!c->rec) CIAO_FAIL(CIAO_ERR_STATE, "ciao_attach_peer_rows: no row problem set");
+    if (row0[my_shard] != c->row0 || n_rows[my_shard] != c->n_rows) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_attach_peer_rows: my shard does not match this context's rows");
+    int64_t next = 0;
+    for (int s = 0; s < n_shards; ++s) {
+        if (row0[s] != next || n_rows[s] <= 0) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_attach_peer_rows: shards must tile [0, N) contiguously in order");
+        next += n_rows[s];
+    }
+    if (next != c->N_total) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_attach_peer_rows: shards cover %lld rows, N = %lld", (long long)next, (long long)c->N_total);
+    CUDA_TRY(cudaSetDevice(c->device));
+    detach_peers(c);
+    for (int s = 0; s < n_shards; ++s) {
+        c->peers.start[s] = row0[s];
+        if (s == my_shard) {
+            c->peers.base[s] = c->rec;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles64 + 64 * (size_t)s, sizeof(h));
+        void *ptr = nullptr;
+        CUDA_TRY(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_mapped[s] = ptr;
+        c->peers.base[s] = (const double *)ptr;
+    }
+    c->peers.start[n_shards] = c->N_total;
+    c->peers.n = n_shards;
     return CIAO_OK;
 }
 
@@ -661,7 +717,7 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
     CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz));  // :85-88
     CIAO_TRY(run_finish(c, ctx_vec(c, CIAO_VEC_Z_FULL), -(c->hat_gamma / (double)N), 1.0, ctx_vec(c, CIAO_VEC_AV)));
     if (total == 0) return CIAO_OK;
-    if (r >= BATCH_MIN_ROWS) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
+    if (r >= BATCH_MIN_ROWS && c->n_rows == c->N_total) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
         CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
         for (int64_t jj = 0; jj < n_batches; ++jj) {
             const int64_t j = order[jj];

@@ -180,8 +180,7 @@ __global__ void batch_finish_kernel(const double *partial, double *av, double *z
         av[j] = a;
         const double lo = reg.lo_v ? reg.lo_v[j] : reg.lo_s, hi = reg.hi_v ? reg.hi_v[j] : reg.hi_s;
         const double gl = hat_gamma * reg.lambda;
-        z[j] = reg.kind == CIAO_REG_NORML1 ? prox_elem<CIAO_REG_NORML1>(a, gl, lo, hi)
-               : reg.kind == CIAO_REG_INDBOX ? prox_elem<CIAO_REG_INDBOX>(a, gl, lo, hi) : a;
+        z[j] = prox_rt(reg.kind, a, gl, lo, hi);
     }
 }
 

@@ -26,7 +26,6 @@
 #define TAIL_HAT_GAM 4 // γ̂ / γ_i                  (Finito_basic.jl:115, Finito_LFinito.jl:98)
 #define TAIL_CZ 5      // c_i(z_full) cached by the last full-gradient pass at z_full (SVRG_basic.jl:74)
 #define CIAO_NUM_VECS 8
-#define CIAO_VEC_SPARE 5
 #define CIAO_VEC_X0 6
 #define CIAO_VEC_TMP 7
 
@@ -35,6 +34,15 @@
 #define CIAO_FLAG_PROX (1ll << 61)    // batch boundary: apply prox_g at this step (after: Finito/ProShI, before: LFinito)
 
 enum { ALG_SVRG = 1, ALG_SAGA = 2, ALG_FINITO = 3, ALG_LFINITO = 4, ALG_PROSHI = 5 };
+
+// Row shards reachable from this GPU: shard s holds rows [start[s], start[s+1]) at base[s] (its own HBM, or a peer's
+// HBM mapped through CUDA IPC and read over NVLink).  n = 1: everything is local.
+#define CIAO_MAX_PEERS 8
+struct PeerTable {
+    const double *base[CIAO_MAX_PEERS];
+    int64_t start[CIAO_MAX_PEERS + 1];
+    int n;
+};
 
 struct RegParams {
     int kind;
@@ -81,6 +89,8 @@ struct ciao_ctx {
     double *host_pin = nullptr; size_t host_pin_bytes = 0;
     // comm
     void *nccl_comm = nullptr; int rank = 0, world = 1;
+    PeerTable peers{};                 // filled by ciao_attach_peer_rows (n = 0: not attached)
+    void *peer_mapped[CIAO_MAX_PEERS] = {};  // cudaIpcOpenMemHandle results to close
     // tuning
     int pass_threads = 0, pass_stages = 0, pass_ctas = 0, seq_cluster = 0, seq_threads = 0;
     ciao_timing timing{0, 0, 0, 0, 0};
@@ -134,18 +144,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-// cluster-scope acquire wait (pairs with remote arrive.release.cluster)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "W_%=:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-        "@!p bra W_%=;\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
 // 1-D TMA bulk copy global -> shared::cta, completion on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
     asm volatile(
@@ -186,9 +184,6 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
     return r;
 }
-__device__ __forceinline__ void st_cluster_v2f64(uint32_t addr, double a, double b) {
-    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
-}
 // remote shared-memory store whose completion is signalled on a (remote) mbarrier by tx-count:
 // no release/acquire fence at cluster scope is needed on either side (SASS: STAS)
 __device__ __forceinline__ void st_async_v2f64(uint32_t remote_addr, double a, double b, uint32_t remote_bar_addr) {
@@ -196,10 +191,6 @@ __device__ __forceinline__ void st_async_v2f64(uint32_t remote_addr, double a, d
                  "d"(a), "d"(b), "r"(remote_bar_addr)
                  : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
-}
-
 // x / den for a loop-invariant den with rden = 1/den precomputed (correctly rounded): one Newton
 // correction of q0 = x·rden with the exact remainder.  Gives the correctly rounded quotient (Markstein)
 // without the ~40-instruction division subroutine on the step's critical path.
@@ -227,6 +218,13 @@ __device__ __forceinline__ double prox_elem(double x, double gl, double lo, doub
     } else if (REG == CIAO_REG_INDBOX) {
         return x < lo ? lo : (x > hi ? hi : x);
     }
+    return x;
+}
+
+// prox_g with the kind chosen at run time (d-sized helper kernels; the step kernels template on REG)
+__device__ __forceinline__ double prox_rt(int kind, double x, double gl, double lo, double hi) {
+    if (kind == CIAO_REG_NORML1) return prox_elem<CIAO_REG_NORML1>(x, gl, lo, hi);
+    if (kind == CIAO_REG_INDBOX) return prox_elem<CIAO_REG_INDBOX>(x, gl, lo, hi);
     return x;
 }
 

@@ -36,11 +36,6 @@ __device__ __forceinline__ double proshi_grad(double q, double c, double s, doub
     return __dadd_rn(g1, g2);
 }
 
-__device__ __forceinline__ double proshi_prox_rt(const RegParams &r, double x, double gl, double lo, double hi) {
-    if (r.kind == CIAO_REG_NORML1) return prox_elem<CIAO_REG_NORML1>(x, gl, lo, hi);
-    if (r.kind == CIAO_REG_INDBOX) return prox_elem<CIAO_REG_INDBOX>(x, gl, lo, hi);
-    return x;
-}
 
 constexpr int PROSHI_P = 8;
 
@@ -93,8 +88,8 @@ __global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
             av1 = __dadd_rn(av1, t1);
             __stcg(srow, make_double2(t0, t1));
             if (ik & CIAO_FLAG_PROX) {  // :121-123
-                z0 = div_by(__dsub_rn(proshi_prox_rt(p.reg, av0, gl, lo0, hi0), av0), p.hat_gamma, rhat);
-                z1 = div_by(__dsub_rn(proshi_prox_rt(p.reg, av1, gl, lo1, hi1), av1), p.hat_gamma, rhat);
+                z0 = div_by(__dsub_rn(prox_rt(p.reg.kind, av0, gl, lo0, hi0), av0), p.hat_gamma, rhat);
+                z1 = div_by(__dsub_rn(prox_rt(p.reg.kind, av1, gl, lo1, hi1), av1), p.hat_gamma, rhat);
             }
             if (k + PROSHI_P < p.K) fetch(j, in1);
             in1 = (k + PROSHI_P + 1 < p.K) ? __ldg(p.idx + k + PROSHI_P + 1) : 0;
@@ -193,7 +188,7 @@ __global__ void __launch_bounds__(PROSHI_BT) proshi_batch_kernel(const ProshiArg
 #pragma unroll
             for (int w = 0; w < PROSHI_BT / 32; ++w) s += red[par][w][q];
             av[q] = __dadd_rn(av[q], s);
-            z[q] = div_by(__dsub_rn(proshi_prox_rt(p.reg, av[q], gl, lo[q], hi[q]), av[q]), p.hat_gamma, rhat);
+            z[q] = div_by(__dsub_rn(prox_rt(p.reg.kind, av[q], gl, lo[q], hi[q]), av[q]), p.hat_gamma, rhat);
         }
     }
     if (tid == 0) {
@@ -267,7 +262,7 @@ __global__ void proshi_dual_kernel(const double *av, double *z, int64_t n_pad, d
     if (j >= n_pad) return;
     const double lo = reg.lo_v ? reg.lo_v[j] : reg.lo_s, hi = reg.hi_v ? reg.hi_v[j] : reg.hi_s;
     const double a = av[j];
-    z[j] = __ddiv_rn(__dsub_rn(proshi_prox_rt(reg, a, hat_gamma * reg.lambda, lo, hi), a), hat_gamma);
+    z[j] = __ddiv_rn(__dsub_rn(prox_rt(reg.kind, a, hat_gamma * reg.lambda, lo, hi), a), hat_gamma);
 }
 
 static int ws_reserve(ciao_ctx *c, size_t need) {

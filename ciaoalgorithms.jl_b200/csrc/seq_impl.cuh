@@ -36,7 +36,7 @@
 #include "common.cuh"
 
 struct SeqArgs {
-    const double *rec;
+    PeerTable rows;         // where row i lives (local HBM, or a peer's over NVLink)
     int64_t ld, d_pad, dc;  // dc = columns per CTA
     const int64_t *idx;     // prepared: 0-based row | flags
     int64_t K;
@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const int64_t i = pidx & CIAO_IDX_MASK;
                 const int slot = (int)(step & (D - 1));
                 double *dst = ring + slot * slot_doubles;
-                const double *src = p.rec + i * p.ld;
+                int s = 0;  // shard holding row i (≤ 8 shards: linear search, off the compute warps' critical path)
+                while (s + 1 < p.rows.n && i >= p.rows.start[s + 1]) ++s;
+                const double *src = p.rows.base[s] + (i - p.rows.start[s]) * p.ld;
                 *reinterpret_cast<int64_t *>(dst + cover + CIAO_TAIL) = pidx;  // released by the arrive below
                 mbar_arrive_expect_tx(&row_bar[slot], (uint32_t)(dc * 8 + CIAO_TAIL * 8));
                 tma_load_1d(dst, src + cbase, (uint32_t)(dc * 8), &row_bar[slot]);
@@ -441,7 +443,15 @@ static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, doub
     SeqShape sh;
     CIAO_TRY(seq_shape(c, &sh));
     SeqArgs a;
-    a.rec = c->rec; a.ld = c->ld; a.d_pad = c->d_pad; a.dc = sh.dc;
+    if (c->peers.n > 1) {
+        a.rows = c->peers;
+    } else {
+        a.rows.n = 1;
+        a.rows.base[0] = c->rec;
+        a.rows.start[0] = 0;
+        a.rows.start[1] = c->n_rows;
+    }
+    a.ld = c->ld; a.d_pad = c->d_pad; a.dc = sh.dc;
     a.idx = idx_prepared; a.K = K; a.table = c->table;
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_zfull = ctx_vec(c, CIAO_VEC_Z_FULL); a.v_w = ctx_vec(c, CIAO_VEC_W);
     a.v_av = ctx_vec(c, CIAO_VEC_AV); a.v_zsum = ctx_vec(c, CIAO_VEC_Z);  // SVRG: state.z is the running sum of inner iterates

@@ -89,6 +89,17 @@ class Engine:
         buf = C.create_string_buffer(uid, 128)
         check(self.lib.ciao_comm_init(self.h, buf, rank, world))
 
+    def rows_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self.lib.ciao_rows_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def attach_peer_rows(self, handles, row0, n_rows, my_shard):
+        """handles: list of 64-byte IPC handles in shard order (the entry of my_shard is ignored)."""
+        blob = C.create_string_buffer(b"".join(handles), 64 * len(handles))
+        r0, nr = i64arr(row0), i64arr(n_rows)
+        check(self.lib.ciao_attach_peer_rows(self.h, len(handles), blob, ptr(r0), ptr(nr), int(my_shard)))
+
     def set_pass_window(self, row_lo, n):
         check(self.lib.ciao_set_pass_window(self.h, int(row_lo), int(n)))
 

@@ -109,6 +109,14 @@ int ciao_comm_init(ciao_ctx *ctx, const void *id128, int rank, int world);
  * all-reduced, so G ranks holding the same rows each stream 1/G of them.  n = 0 resets. */
 int ciao_set_pass_window(ciao_ctx *ctx, int64_t row_lo, int64_t n);
 
+/* Row-sharded problems beyond one GPU's HBM: every rank exports its shard (ciao_rows_ipc_handle, 64 bytes, CUDA IPC),
+ * the host all-gathers the handles and shard bounds, and each rank attaches the peers' shards.  The sequential inner
+ * epochs without a table (SVRG/SVRG++, LFinito) then run replicated on every rank, TMA-prefetching remote rows over
+ * NVLink; the passes stay sharded + all-reduced.  Shards must tile [0, N) in rank order. */
+int ciao_rows_ipc_handle(ciao_ctx *ctx, void *out64);
+int ciao_attach_peer_rows(ciao_ctx *ctx, int n_shards, const void *handles64, const int64_t *row0, const int64_t *n_rows,
+                          int my_shard);
+
 /* ---- streaming passes (HBM-bound) ------------------------------------------ */
 /* out = scale · Σ_i ∇f_i(x)      (SVRG_basic.jl:58-63, 88-92; Finito_LFinito.jl:68-72, 85-88) */
 int ciao_full_gradient(ciao_ctx *ctx, const double *x, double scale, double *out_or_null);

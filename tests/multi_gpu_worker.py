@@ -1,0 +1,105 @@
+"""Worker of tests/test_gpu_multi.py — launched with torch.distributed.run on G GPUs of one box.
+
+Row-sharded problem (each rank generates and holds only its shard), NCCL allreduce in the passes, peers' shards
+attached over CUDA IPC so that the replicated SVRG++ / LFinito inner loops TMA-prefetch remote rows over NVLink.
+Every rank checks its results against a single-context run of the whole problem on its own GPU (bitwise for the
+sequential kernels, ≤ 1e-13 for the all-reduced passes) and rank 0 prints MULTI_GPU_OK."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ciao_pkg  # noqa: E402
+
+ciao_pkg.load()
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from ciaoalgorithms_jl_b200 import _lib as L  # noqa: E402
+from ciaoalgorithms_jl_b200.engine import Engine  # noqa: E402
+from ciaoalgorithms_jl_b200.sampling import HostRNG, LFinitoSweeper, shard_rows  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, d, seed = 6000 + 37, 1024, 0x5EED0003
+    lo, hi = shard_rows(N, world, rank)
+    lam = N / 100.0
+
+    sh = Engine(local)                                  # my shard only
+    sh.gen_synthetic(L.SYNTH_LASSO, N, d, seed, scale=float(N), row0=lo, n_rows=hi - lo)
+    sh.set_reg(L.REG_NORML1, lam)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    sh.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    handles = [None] * world
+    dist.all_gather_object(handles, (sh.rows_ipc_handle(), lo, hi - lo))
+    sh.attach_peer_rows([h[0] for h in handles], [h[1] for h in handles], [h[2] for h in handles], rank)
+
+    full = Engine(local)                                # the whole problem on this GPU, for comparison
+    full.gen_synthetic(L.SYNTH_LASSO, N, d, seed, scale=float(N))
+    full.set_reg(L.REG_NORML1, lam)
+
+    def rel(a, b):
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+    x = np.random.default_rng(0).standard_normal(d) * 1e-3
+    assert rel(sh.full_gradient(x, 1.0 / N), full.full_gradient(x, 1.0 / N)) < 1e-13
+    assert abs(sh.objective(x)[0] - full.objective(x)[0]) < 1e-13 * full.objective(x)[0]
+    assert abs(sh.max_row_sqnorm() - full.max_row_sqnorm()) == 0.0
+    gamma = 1.0 / (7.0 * N * full.max_row_sqnorm())
+
+    # SVRG++ on the sharded problem: passes all-reduced, inner epoch replicated with remote rows
+    rng_a, rng_b = HostRNG(5), HostRNG(5)
+    sh.svrg_init(np.zeros(d), gamma, True)
+    full.svrg_init(np.zeros(d), gamma, True)
+    m = N // 8
+    for _ in range(3):
+        sh.svrg_epoch(rng_a.rand_vec(N, m))
+        full.svrg_epoch(rng_b.rand_vec(N, m))
+        m *= 2
+    zs, zf = sh.get_vec(L.VEC_Z_FULL), full.get_vec(L.VEC_Z_FULL)
+    assert rel(zs, zf) < 1e-11, rel(zs, zf)
+    # all ranks hold the same iterate bit for bit (the inner epoch is replicated, the allreduce is identical everywhere)
+    t = torch.from_numpy(zs.copy()).cuda()
+    ref = t.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(t, ref)
+
+    # LFinito sweeps (sequential kernel with remote rows)
+    Li = np.full(N, N * full.max_row_sqnorm())
+    gam = 0.999 * N / Li
+    hat = 1 / np.sum(1 / gam)
+    sh.lfinito_init(np.zeros(d), gam, hat)
+    full.lfinito_init(np.zeros(d), gam, hat)
+    dist.barrier()                                      # peers' record tails (γ_i) are written before anyone reads them
+    sw = LFinitoSweeper(N, 1, 3, HostRNG(2))
+    for _ in range(2):
+        o = sw.next()
+        sh.lfinito_outer(o, 1)
+        full.lfinito_outer(o, 1)
+        dist.barrier()
+    assert rel(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) < 1e-11
+
+    # tables are not sharded: SAGA on a shard context is refused, not silently wrong
+    try:
+        sh.saga_init(np.zeros(d), gamma, False)
+        raise AssertionError("saga_init on a shard should fail")
+    except Exception as ex:
+        assert "not sharded" in str(ex)
+    dist.barrier()
+    if rank == 0:
+        print("MULTI_GPU_OK world", world)
+    sh.close()
+    full.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
