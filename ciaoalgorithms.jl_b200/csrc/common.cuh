@@ -200,6 +200,26 @@ __device__ __forceinline__ double div_by(double x, double den, double rden) {
     return fma(rem, rden, q0);
 }
 
+// Warp-wide sum on the fp64 tensor core: two m8n8k4 DMMAs and ONE shuffle instead of five shuffle+add rounds
+// (measured on B200, scripts/micro/dmma_micro.cu: DMMA ≈ 28 cycles, a double shuffle+DADD round ≈ 45 cycles, so
+// ≈ 105 instead of ≈ 225 cycles of latency).  Used where the reduction sits on a sequential critical path.
+//   1st DMMA:  A[r][k] = v of lane 4r+k, B = 1  →  every lane of group r = lane>>2 holds S_r = Σ_k v
+//   shuffle :  lane L fetches S_{(L&3) + 4((L>>2)&1)}, i.e. B[k][c] = S_{k + 4(c&1)}
+//   2nd DMMA:  A = 1  →  D[·][c] = S_0..3 (c even) or S_4..7 (c odd); a lane holds one of each → their sum is the total.
+// The result is identical in all 32 lanes and, for identical inputs, in all warps (fixed hardware summation order).
+__device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(d0), "=d"(d1)
+                 : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+__device__ __forceinline__ double warp_sum_mma(double v, int lane) {
+    double s0, s1, t0, t1;
+    dmma_884(s0, s1, v, 1.0);
+    const double b = __shfl_sync(0xffffffffu, s0, 4 * ((lane & 3) + 4 * ((lane >> 2) & 1)));
+    dmma_884(t0, t1, 1.0, b);
+    return t0 + t1;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -17,7 +17,8 @@
 //   2. compute: partial dots → warp shuffles → each warp pushes its partial into EVERY CTA
 //      of the cluster through DSMEM with st.async (a remote store that completes on the
 //      destination CTA's mbarrier by tx-count, so neither side needs a cluster-scope
-//      fence); every warp then reduces the C·W partials with the same xor-butterfly, so
+//      fence); every warp then reduces the C·W partials with the same tensor-core sum (two fp64
+//      DMMAs + one shuffle, common.cuh warp_sum_mma — half the latency of five shuffle rounds), so
 //      all threads of all CTAs hold bit-identical scalars — no CTA or cluster barrier
 //      instruction on the step's critical path.  While the exchange is in flight the row
 //      of step k+1 and the table row of step k+2 are pulled into registers.
@@ -224,11 +225,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 v0 = fma(cur.a[q], z[q], v0);
                 if (TWO_DOTS) v1 = fma(cur.a[q], zf[q], v1);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-                if (TWO_DOTS) v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-            }
+            v0 = warp_sum_mma(v0, lane);
+            if (TWO_DOTS) v1 = warp_sum_mma(v1, lane);
             PROF_T(t_b);
             if (lane < C) {
                 const uint32_t dst = smem_u32(part + ((size_t)par * p.npart_pad + rank * W + warp) * 2);
@@ -249,11 +247,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                     u0 += v.x;
                     if (TWO_DOTS) u1 += v.y;
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    u0 += __shfl_xor_sync(0xffffffffu, u0, o);
-                    if (TWO_DOTS) u1 += __shfl_xor_sync(0xffffffffu, u1, o);
-                }
+                u0 = warp_sum_mma(u0, lane);
+                if (TWO_DOTS) u1 = warp_sum_mma(u1, lane);
             }
             const double tb = cur.b, tl = cur.lam;
 
