@@ -28,7 +28,7 @@ struct BatchArgs {
 };
 
 template <int CPT, int MODE, int LOSS>
-__global__ void __launch_bounds__(256, 1) batch_pass_kernel(const BatchArgs p) {
+__global__ void __launch_bounds__(256, 2) batch_pass_kernel(const BatchArgs p) {
     constexpr int RPG = 16 / CPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
@@ -167,14 +167,33 @@ __global__ void __launch_bounds__(256, 1) batch_pass_kernel(const BatchArgs p) {
     if (tid == 0) p.fws[blockIdx.x] = fsum;
 }
 
+// Fixed-order reduction of the CTA partials fused with the batch's closing update (one launch instead of two):
 // Finito: av += Σ; z = prox_g(av, γ̂) (Finito_basic.jl:118).   LFinito: av += Σ + (z − z_full)·Σ γ̂/γ_i (:98)
-__global__ void batch_finish_kernel(const double *partial, double *av, double *z, const double *zf, int64_t d_pad, int mode,
-                                    double hat_gamma, RegParams reg) {
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= d_pad) return;
-    double a = __dadd_rn(av[j], partial[j]);
+__global__ void __launch_bounds__(32 * REDUCE_SLICES) batch_reduce_finish_kernel(const double *ws, const double *fws, int G,
+                                                                                  double *av, double *z, const double *zf,
+                                                                                  int64_t d_pad, int mode, double hat_gamma,
+                                                                                  RegParams reg) {
+    __shared__ double sm[REDUCE_SLICES][33];
+    __shared__ double fsh;
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int64_t j = blockIdx.x * 32ll + x;
+    double s = 0.0;
+    if (j < d_pad)
+        for (int b = y; b < G; b += REDUCE_SLICES) s += ws[(size_t)b * d_pad + j];
+    sm[y][x] = s;
+    if (mode == BATCH_LFINITO && x == 0 && y == 0) {
+        double f = 0.0;
+        for (int b = 0; b < G; ++b) f += fws[b];
+        fsh = f;
+    }
+    __syncthreads();
+    if (y != 0 || j >= d_pad) return;
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < REDUCE_SLICES; ++q) t += sm[q][x];
+    double a = __dadd_rn(av[j], t);
     if (mode == BATCH_LFINITO) {
-        a = __dadd_rn(a, __dmul_rn(partial[d_pad], __dsub_rn(z[j], zf[j])));
+        a = __dadd_rn(a, __dmul_rn(fsh, __dsub_rn(z[j], zf[j])));
         av[j] = a;
     } else {
         av[j] = a;
@@ -188,11 +207,19 @@ template <int CPT, int MODE>
 static int launch_batch_loss(ciao_ctx *c, const BatchArgs &a, int grid, int T, size_t smem) {
     if (c->loss_kind == CIAO_LOSS_LS) {
         auto kern = batch_pass_kernel<CPT, MODE, CIAO_LOSS_LS>;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t configured[CIAO_MAX_DEVICES] = {};
+        if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[c->device % CIAO_MAX_DEVICES] = smem;
+        }
         kern<<<grid, T, smem, c->stream>>>(a);
     } else {
         auto kern = batch_pass_kernel<CPT, MODE, CIAO_LOSS_LOGISTIC>;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t configured[CIAO_MAX_DEVICES] = {};
+        if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[c->device % CIAO_MAX_DEVICES] = smem;
+        }
         kern<<<grid, T, smem, c->stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
@@ -209,11 +236,11 @@ int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
     const int T = (int)Tn, rpg = 16 / cpt;
     const size_t stage_bytes = (size_t)rpg * c->ld * sizeof(double);
     const size_t fixed = 2 * rpg * 32 * 2 * sizeof(double) + 16 * sizeof(uint64_t) + 256;
-    int S = 6;
-    while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)227 * 1024) --S;
+    int S = 3;  // 2 CTAs per SM: a batch is short, so parallelism across CTAs matters more than ring depth
+    while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)112 * 1024) --S;
     const size_t smem = (size_t)S * stage_bytes + fixed;
     const int64_t n_groups = (n + rpg - 1) / rpg;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_groups, c->num_sms));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_groups, 2 * c->num_sms));
     const size_t need = ((size_t)grid * d_pad + grid + 16) * sizeof(double);
     if (need > c->ws_bytes) {
         if (c->ws) cudaFree(c->ws);
@@ -245,12 +272,9 @@ int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
         }
     }
     CIAO_TRY(rc);
-    const int nb = (int)((d_pad + 255) / 256);
-    reduce_ws_kernel<<<nb, 256, 0, c->stream>>>(a.ws, a.fws, grid, d_pad, c->partial, c->partial + d_pad, 0, 1);
+    batch_reduce_finish_kernel<<<(int)((d_pad + 31) / 32), dim3(32, REDUCE_SLICES), 0, c->stream>>>(
+        a.ws, a.fws, grid, ctx_vec(c, CIAO_VEC_AV), ctx_vec(c, CIAO_VEC_Z), ctx_vec(c, CIAO_VEC_Z_FULL), d_pad, mode, c->hat_gamma, c->reg);
     CUDA_TRY(cudaGetLastError());
-    batch_finish_kernel<<<nb, 256, 0, c->stream>>>(c->partial, ctx_vec(c, CIAO_VEC_AV), ctx_vec(c, CIAO_VEC_Z),
-                                                   ctx_vec(c, CIAO_VEC_Z_FULL), d_pad, mode, c->hat_gamma, c->reg);
-    CUDA_TRY(cudaGetLastError());
-    c->timing.launches += 3;
+    c->timing.launches += 2;
     return CIAO_OK;
 }

@@ -38,6 +38,7 @@ enum { ALG_SVRG = 1, ALG_SAGA = 2, ALG_FINITO = 3, ALG_LFINITO = 4, ALG_PROSHI =
 // Row shards reachable from this GPU: shard s holds rows [start[s], start[s+1]) at base[s] (its own HBM, or a peer's
 // HBM mapped through CUDA IPC and read over NVLink).  n = 1: everything is local.
 #define CIAO_MAX_PEERS 8
+#define CIAO_MAX_DEVICES 16
 struct PeerTable {
     const double *base[CIAO_MAX_PEERS];
     int64_t start[CIAO_MAX_PEERS + 1];

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
                 for (int e = 0; e < CPT; ++e) acc[e] = fma(cc, a[r][e], acc[e]);
             } else {
                 const double cg = tgn[r];  // γ_i / N, precomputed in the record tail
+                const double rg = (MODE == PASS_FINITO_INIT) ? __ddiv_rn(1.0, tg[r]) : 0.0;  // one division per row, not per element
                 double *trow = p.table + (r0 + r) * p.d_pad;
 #pragma unroll
                 for (int k = 0; k < CPT / 2; ++k) {
@@ -154,8 +155,8 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
                     if (MODE == PASS_FINITO_INIT) {
                         s0 = __dsub_rn(xr[2 * k], __dmul_rn(cg, s0));
                         s1 = __dsub_rn(xr[2 * k + 1], __dmul_rn(cg, s1));
-                        acc[2 * k] += __ddiv_rn(s0, tg[r]);
-                        acc[2 * k + 1] += __ddiv_rn(s1, tg[r]);
+                        acc[2 * k] += div_by(s0, tg[r], rg);
+                        acc[2 * k + 1] += div_by(s1, tg[r], rg);
                     } else {
                         acc[2 * k] += s0;
                         acc[2 * k + 1] += s1;
@@ -175,27 +176,50 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
     if (tid == 0) p.fws[blockIdx.x] = fsum;
 }
 
-// second stage: fixed-order sum of the CTA partials.  out[j] = Σ_b ws[b][j];  fout = Σ_b fws[b] (or max)
-__global__ void reduce_ws_kernel(const double *ws, const double *fws, int G, int64_t d_pad, double *out, double *fout,
-                                 int fmax_mode, int with_vec) {
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (with_vec && j < d_pad) {
+// second stage: fixed-order sum of the CTA partials.  out[j] = Σ_b ws[b][j];  fout = Σ_b fws[b] (or max).
+// Block = 32 columns × REDUCE_SLICES slices of b: thread (x, y) sums b = y, y+S, … (coalesced 256-byte rows),
+// the slices are then combined in a fixed order through shared memory — deterministic, and a few µs instead of
+// a G-long serial chain of global loads per column (which dominated the minibatch passes).
+constexpr int REDUCE_SLICES = 16;
+__global__ void __launch_bounds__(32 * REDUCE_SLICES) reduce_ws_kernel(const double *ws, const double *fws, int G, int64_t d_pad,
+                                                                       double *out, double *fout, int fmax_mode, int with_vec) {
+    __shared__ double sm[REDUCE_SLICES][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int64_t j = blockIdx.x * 32ll + x;
+    if (with_vec) {
         double s = 0.0;
-        for (int b = 0; b < G; ++b) s += ws[(size_t)b * d_pad + j];
-        out[j] = s;
+        if (j < d_pad)
+            for (int b = y; b < G; b += REDUCE_SLICES) s += ws[(size_t)b * d_pad + j];
+        sm[y][x] = s;
+        __syncthreads();
+        if (y == 0 && j < d_pad) {
+            double t = 0.0;
+#pragma unroll
+            for (int q = 0; q < REDUCE_SLICES; ++q) t += sm[q][x];
+            out[j] = t;
+        }
     }
-    if (j == 0) {
+    if (blockIdx.x == 0 && x == 0 && y == 0) {
         double f = 0.0;
         for (int b = 0; b < G; ++b) f = fmax_mode ? fmax(f, fws[b]) : f + fws[b];
         *fout = f;
     }
+}
+static inline void launch_reduce_ws(ciao_ctx *c, const double *ws, const double *fws, int G, double *out, double *fout, int fmax_mode,
+                                    int with_vec) {
+    reduce_ws_kernel<<<(int)((c->d_pad + 31) / 32), dim3(32, REDUCE_SLICES), 0, c->stream>>>(ws, fws, G, c->d_pad, out, fout, fmax_mode,
+                                                                                          with_vec);
 }
 
 // ---------------------------------------------------------------------------
 template <int CPT, int MODE, int LOSS>
 static int launch_one(ciao_ctx *c, const PassArgs &a, int grid, int T, size_t smem) {
     auto kern = row_pass_kernel<CPT, MODE, LOSS>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t configured[CIAO_MAX_DEVICES] = {};  // per device: the attribute is per device, and setting it costs several µs
+    if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device % CIAO_MAX_DEVICES] = smem;
+    }
     kern<<<grid, T, smem, c->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
     return CIAO_OK;
@@ -274,9 +298,7 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     }
     CIAO_TRY(rc);
     CUDA_TRY(cudaEventRecord(c->ev_pb, c->stream));
-    const int nb = (int)((d_pad + 255) / 256);
-    reduce_ws_kernel<<<nb, 256, 0, c->stream>>>(a.ws, a.fws, grid, d_pad, c->partial, c->partial + d_pad,
-                                                mode == PASS_NORMS, mode != PASS_NORMS);
+    launch_reduce_ws(c, a.ws, a.fws, grid, c->partial, c->partial + d_pad, mode == PASS_NORMS, mode != PASS_NORMS);
     CUDA_TRY(cudaGetLastError());
     c->timing.launches += 2;
     c->pass_timed = true;

@@ -374,7 +374,11 @@ template <int CPT, int ALG, int LOSS, int REG, bool CZ>
 static int launch_seq(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
     auto kern = seq_kernel<CPT, ALG, LOSS, REG, CZ>;
     const size_t smem = (size_t)SEQ_D * ((size_t)sh.Tc * CPT + SEQ_SLOT_EXTRA) * 8 + 2 * (size_t)sh.npart_pad * 2 * 8 + (SEQ_D + 2) * 8 + 128;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t configured[CIAO_MAX_DEVICES] = {};
+    if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device % CIAO_MAX_DEVICES] = smem;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(sh.C);
     cfg.blockDim = dim3(sh.Tc + 32);
