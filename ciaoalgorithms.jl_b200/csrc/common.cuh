@@ -234,6 +234,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <int REG>
 __device__ __forceinline__ double prox_elem(double x, double gl, double lo, double hi) {
     if (REG == CIAO_REG_NORML1) {
+        // (x − clamp(x, −gl, gl) gives the same bits in fewer instructions, but DMNMX is slow on B200: 0.40 vs 0.377 µs/step)
         double adj = (x <= -gl) ? gl : ((x >= gl) ? -gl : -x);
         return __dadd_rn(x, adj);
     } else if (REG == CIAO_REG_INDBOX) {

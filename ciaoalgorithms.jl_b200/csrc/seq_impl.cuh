@@ -199,19 +199,28 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 t[h] = valid[h] ? __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h])) : make_double2(0.0, 0.0);
         };
 
-        RowRegs cur, nxt;
+        // this lane's remote destinations in the exchange (lane l < C talks to CTA l): computed once, not per step
+        uint32_t send_dst[2], send_bar[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t peer = lane < C ? lane : 0;
+            send_dst[q] = mapa_u32(smem_u32(part + ((size_t)q * p.npart_pad + rank * W + warp) * 2), peer);
+            send_bar[q] = mapa_u32(smem_u32(&part_bar[q]), peer);
+        }
+        RowRegs rowA, rowB;
         double2 t_cur[H], t_n1[H], t_n2[H];
         if (K > 0) {
-            load_row(0, cur);
+            load_row(0, rowA);
             if (TABLE) {
-                load_table(cur.ik, t_cur);
+                load_table(rowA.ik, t_cur);
                 if (K > 1) load_table(peek_index(1), t_n1);
             }
         }
 #ifdef CIAO_SEQ_PROFILE
         long long prof_acc[4] = {0, 0, 0, 0};
 #endif
-        for (int64_t k = 0; k < K; ++k) {
+        // one step; cur = registers of step k, nxt = registers to fill for step k+1
+        auto step = [&](const int64_t k, RowRegs &cur, RowRegs &nxt) {
             const int par = (int)(k & 1);
             PROF_T(t_a);
             if (ALG == ALG_LFINITO && (cur.ik & CIAO_FLAG_PROX)) {  // Finito_LFinito.jl:92
@@ -228,10 +237,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             v0 = warp_sum_mma(v0, lane);
             if (TWO_DOTS) v1 = warp_sum_mma(v1, lane);
             PROF_T(t_b);
-            if (lane < C) {
-                const uint32_t dst = smem_u32(part + ((size_t)par * p.npart_pad + rank * W + warp) * 2);
-                st_async_v2f64(mapa_u32(dst, lane), v0, v1, mapa_u32(smem_u32(&part_bar[par]), lane));
-            }
+            if (lane < C) st_async_v2f64(send_dst[par], v0, v1, send_bar[par]);
             // ---- while the exchange is in flight: next row, and the table row two steps ahead
             if (k + 1 < K) load_row(k + 1, nxt);
             if (TABLE && k + 2 < K) load_table(peek_index(k + 2), t_n2);
@@ -242,10 +248,13 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             double u0 = 0.0, u1 = 0.0;
             {
                 const double2 *pp = reinterpret_cast<const double2 *>(part + (size_t)par * p.npart_pad * 2) + lane;
-                for (int e = 0; e < E; ++e) {
-                    const double2 v = pp[e * 32];
-                    u0 += v.x;
-                    if (TWO_DOTS) u1 += v.y;
+                const double2 v = pp[0];  // E == 1 (C·W ≤ 32) is the common shape: no loop, no branches
+                u0 = v.x;
+                if (TWO_DOTS) u1 = v.y;
+                for (int e = 1; e < E; ++e) {
+                    const double2 w = pp[e * 32];
+                    u0 += w.x;
+                    if (TWO_DOTS) u1 += w.y;
                 }
                 u0 = warp_sum_mma(u0, lane);
                 if (TWO_DOTS) u1 = warp_sum_mma(u1, lane);
@@ -327,7 +336,6 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             PROF_ADD(1, t_b, t_c);  // send + next-row / table-row register prefetch
             PROF_ADD(2, t_c, t_d);  // remaining wait for the cluster exchange
             PROF_ADD(3, t_d, t_e);  // butterfly of partials + fused update
-            cur = nxt;
             if (TABLE) {
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
@@ -335,7 +343,13 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                     t_n1[h] = t_n2[h];
                 }
             }
+        };
+        int64_t k = 0;
+        for (; k + 1 < K; k += 2) {  // ping-pong the row registers: no copies between steps
+            step(k, rowA, rowB);
+            step(k + 1, rowB, rowA);
         }
+        if (k < K) step(k, rowA, rowB);
 
         // ---- epilogue: state back to HBM ------------------------------------------------
 #pragma unroll

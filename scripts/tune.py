@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ciao_pkg; ciao_pkg.load()
 from ciaoalgorithms_jl_b200 import _lib as L
+if os.environ.get("CIAO_SO"): L.SO_PATH = os.environ["CIAO_SO"]
 from ciaoalgorithms_jl_b200.engine import Engine
 
 rows_log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 22
