@@ -435,7 +435,7 @@ static int launch_seq_loss(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
 // Chooses the cluster shape: C CTAs × Tc compute threads × CPT columns per thread cover d_pad.
 static int seq_shape(ciao_ctx *c, SeqShape *sh) {
     const int64_t d_pad = c->d_pad;
-    int C = c->seq_cluster > 0 ? c->seq_cluster : (d_pad >= 1024 ? 8 : (d_pad >= 256 ? 4 : 1))  // measured: profiles/tune_seq_r1.json;
+    int C = c->seq_cluster > 0 ? c->seq_cluster : (d_pad >= 1024 ? 8 : (d_pad >= 256 ? 4 : 1));  // measured: profiles/tune_seq_r1.json
     while (C > 1 && (d_pad % (4 * C) != 0)) C >>= 1;
     const int64_t dc = d_pad / C;
     const int T_target = c->seq_threads > 0 ? std::min(c->seq_threads, 256) : 128;
