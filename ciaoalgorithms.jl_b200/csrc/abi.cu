@@ -274,6 +274,7 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
     if (!c) CIAO_FAIL(CIAO_ERR_OOM, "host allocation failed");
     c->device = device;
     c->cache_cz = getenv("CIAO_CACHE_CZ") != nullptr && getenv("CIAO_CACHE_CZ")[0] == '1';
+    c->seq_table_ldg = getenv("CIAO_SEQ_TABLE_LDG") != nullptr && getenv("CIAO_SEQ_TABLE_LDG")[0] == '1';
     c->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     cudaEvent_t *evs[] = {&c->ev_pa, &c->ev_pb, &c->ev_sa, &c->ev_sb, &c->tm_a, &c->tm_b};

@@ -7,6 +7,9 @@
 #include <stdio.h>
 
 #include "../../include/ciao_cuda.h"
+#ifdef __CUDACC__
+#include "fastmath.cuh"
+#endif
 
 // ---------------------------------------------------------------------------
 // HBM data layout
@@ -80,6 +83,9 @@ struct ciao_ctx {
     // step needs one dot instead of two.  Measured at C3: −0.004 µs/step, but +1.4 ms per pass (4M scattered 8-byte
     // writes → partial-sector RMW), i.e. 6.7 → 6.3 TB/s on the roofline kernel — off by default.
     bool cache_cz = false;
+    // Debug/test knob (env CIAO_SEQ_TABLE_LDG=1): SAGA/Finito table rows by register prefetch instead of the TMA-staged
+    // ring (the path taken anyway when the ring does not fit in shared memory).
+    bool seq_table_ldg = false;
     // workspace
     double *ws = nullptr;  size_t ws_bytes = 0;
     double *partial = nullptr;         // [d_pad + 8] partial d-vector + scalars (allreduce buffer)
@@ -259,8 +265,12 @@ __device__ __forceinline__ double prox_rt(int kind, double x, double gl, double 
 template <int LOSS>
 __device__ __forceinline__ double loss_coef(double u, double b, double lam) {
     if (LOSS == CIAO_LOSS_LS) return __dsub_rn(u, b);  // residual; λ applied per element
-    double e = exp(__dmul_rn(b, u));
+#ifdef CIAO_LIBM_LOGISTIC
+    double e = exp(__dmul_rn(b, u));  // CUDA math library: ≈ 430 cycles of dependent latency per step
     return __ddiv_rn(__dmul_rn(-lam, b), __dadd_rn(1.0, e));
+#else
+    return logistic_coef_fast(u, b, lam);  // fastmath.cuh: same formula, latency-optimised exp and division
+#endif
 }
 template <int LOSS>
 __device__ __forceinline__ double loss_value(double u, double b, double lam) {

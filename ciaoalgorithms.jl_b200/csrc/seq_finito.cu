@@ -5,3 +5,12 @@
 int run_seq_finito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d) {
     return run_seq_alg<ALG_FINITO>(c, idx_prepared, K, m_d);
 }
+
+#ifdef CIAO_SEQ_PROFILE
+// debug builds only (scripts/prof_seq.py): per-phase cycles of the last inner kernel of this translation unit
+extern "C" int ciao_debug_seq_prof_finito(ciao_ctx *c, long long *out4) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(out4, g_seq_prof, 4 * sizeof(long long)));
+    return CIAO_OK;
+}
+#endif

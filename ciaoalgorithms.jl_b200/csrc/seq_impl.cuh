@@ -10,10 +10,10 @@
 // owns CPT fixed columns of every state vector (w/z, av, z_full, Σw) in REGISTERS for
 // the whole call.  Each CTA has W compute warps and one PRODUCER warp.  Per step:
 //   1. producer: the sampled row slice a_i[cols of this CTA] + its record tail (b_i, λ_i,
-//      γ_i/N, γ̂/γ_i, cached c_i(z_full)) + the prepared index word are staged D steps ahead
-//      into an mbarrier ring by TMA (cp.async.bulk), driven by the host-generated index
-//      sequence; table rows (SAGA/Finito) are pulled into L2 by a bulk L2 prefetch at the
-//      same time.  A slot is free once the exchange phase of the step that used it is over.
+//      γ_i/N, γ̂/γ_i, cached c_i(z_full)) + the prepared index word + (SAGA/Finito) the same
+//      slice of the table row s_i are staged D steps ahead into an mbarrier ring by TMA
+//      (cp.async.bulk), driven by the host-generated index sequence.  A slot is free once the
+//      exchange phase of the step that used it is over.
 //   2. compute: partial dots → warp shuffles → each warp pushes its partial into EVERY CTA
 //      of the cluster through DSMEM with st.async (a remote store that completes on the
 //      destination CTA's mbarrier by tx-count, so neither side needs a cluster-scope
@@ -21,13 +21,13 @@
 //      DMMAs + one shuffle, common.cuh warp_sum_mma — half the latency of five shuffle rounds), so
 //      all threads of all CTAs hold bit-identical scalars — no CTA or cluster barrier
 //      instruction on the step's critical path.  While the exchange is in flight the row
-//      of step k+1 and the table row of step k+2 are pulled into registers.
+//      and the table row of step k+1 are pulled into the other (ping-pong) register set.
 //   3. the variance-reduced / aggregated update, the table row write and prox_g are
 //      fused, element by element, in the reference's rounding order.
-// Table rows are read and written by their owner threads only (generic proxy; the same
-// thread reads and writes a given address → coherent); when a row index repeats inside
-// the two-step register prefetch window the step is flagged by prep_indices_kernel and
-// reloads the row after the previous write.
+// Table rows are written by their owner threads only (st.global.cg → L2).  A staged copy is
+// stale when the same row index occurs again within the D-step prefetch window; such steps are
+// flagged by prep_indices_kernel (HAZARD) and re-read the row with ld.global.cg after the previous
+// write (same thread wrote those addresses → coherent).
 // The step is latency/issue bound (one warp per SM sub-partition), so the loop body is
 // kept free of predicates and global index loads: ring slots are zero padded to the thread
 // grid and carry everything a step needs.
@@ -46,11 +46,12 @@ struct SeqArgs {
     double gamma, hat_gamma, Nd, m_d;
     int plus, sag;
     int npart_pad;          // C·W rounded up to a multiple of 32
+    int table_tma;          // table rows are staged in the ring by TMA (else: register prefetch with ld.global)
     RegParams reg;
 };
 
 #ifdef CIAO_SEQ_PROFILE
-__device__ long long g_seq_prof[4];  // accumulated cycles of thread 0 of CTA 0 per phase (debug builds only)
+static __device__ long long g_seq_prof[4];  // accumulated cycles of thread 0 of CTA 0 per phase (debug builds only)
 #define PROF_T(var) const long long var = clock64()
 #define PROF_ADD(i, a, b) prof_acc[i] += (b) - (a)
 #else
@@ -82,7 +83,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
     const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
     const int64_t dc = p.dc;
     const int cover = Tc * CPT;                       // columns covered by the thread grid (≥ dc)
-    const size_t slot_doubles = (size_t)cover + SEQ_SLOT_EXTRA;
+    const bool TT = TABLE && p.table_tma;             // table row slices ride in the ring slots, behind the record tail
+    const size_t slot_doubles = (size_t)cover + SEQ_SLOT_EXTRA + (TT ? cover : 0);
     double *ring = reinterpret_cast<double *>(smem_raw);
     double *part = ring + D * slot_doubles;           // [2][npart_pad][2]
     uint64_t *row_bar = reinterpret_cast<uint64_t *>(part + 2 * (size_t)p.npart_pad * 2);
@@ -114,10 +116,11 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 while (s + 1 < p.rows.n && i >= p.rows.start[s + 1]) ++s;
                 const double *src = p.rows.base[s] + (i - p.rows.start[s]) * p.ld;
                 *reinterpret_cast<int64_t *>(dst + cover + CIAO_TAIL) = pidx;  // released by the arrive below
-                mbar_arrive_expect_tx(&row_bar[slot], (uint32_t)(dc * 8 + CIAO_TAIL * 8));
+                mbar_arrive_expect_tx(&row_bar[slot], (uint32_t)(dc * 8 * (TT ? 2 : 1) + CIAO_TAIL * 8));
                 tma_load_1d(dst, src + cbase, (uint32_t)(dc * 8), &row_bar[slot]);
                 tma_load_1d(dst + cover, src + p.d_pad, CIAO_TAIL * 8, &row_bar[slot]);
-                if (TABLE) tma_prefetch_l2(p.table + i * p.d_pad + cbase, (uint32_t)(dc * 8));
+                if (TT) tma_load_1d(dst + cover + SEQ_SLOT_EXTRA, p.table + i * p.d_pad + cbase, (uint32_t)(dc * 8), &row_bar[slot]);
+                else if (TABLE) tma_prefetch_l2(p.table + i * p.d_pad + cbase, (uint32_t)(dc * 8));
             };
             if (K > 0) mbar_arrive_expect_tx(&part_bar[0], part_bytes);
             if (K > 1) mbar_arrive_expect_tx(&part_bar[1], part_bytes);
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             double a[CPT];
             double b, lam, gn, hg, cz;  // tail: b_i | λ_i | γ_i/N | γ̂/γ_i | c_i(z_full)
             int64_t ik;                 // prepared index word (row | flags)
+            double2 t[H];               // this thread's slice of the table row s_i (SAGA/Finito)
         };
         // waits for the staged row of `step` and pulls this thread's slice + the scalars into registers
         auto load_row = [&](int64_t step, RowRegs &r) {
@@ -185,18 +189,20 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             r.hg = (ALG == ALG_FINITO || ALG == ALG_LFINITO) ? rp[cover + TAIL_HAT_GAM] : 0.0;
             r.cz = (USES_ZFULL && CZ) ? rp[cover + TAIL_CZ] : 0.0;
             r.ik = (ALG != ALG_SVRG) ? *reinterpret_cast<const int64_t *>(rp + cover + CIAO_TAIL) : 0;
+            if (TT) {  // the table row slice was staged D steps ago (stale if the row was rewritten since: HAZARD flag)
+#pragma unroll
+                for (int h = 0; h < H; ++h) r.t[h] = *reinterpret_cast<const double2 *>(rp + cover + SEQ_SLOT_EXTRA + lcol[h]);
+            }
         };
-        // index word of a step further ahead (its row has landed long ago: D-deep ring)
-        auto peek_index = [&](int64_t step) -> int64_t {
-            const int slot = (int)(step & (D - 1));
-            mbar_wait(&row_bar[slot], (uint32_t)((step >> 3) & 1));
-            return *reinterpret_cast<const int64_t *>(ring + slot * slot_doubles + cover + CIAO_TAIL);
-        };
-        auto load_table = [&](int64_t pidx, double2 (&t)[H]) {
-            const double *trow = p.table + (pidx & CIAO_IDX_MASK) * p.d_pad;
+        // Fallback when the ring with table slices does not fit in shared memory (!TT): the table row of the next step is
+        // pulled into the ping-pong register set with ld.global one step ahead (L2 prefetch issued D steps ago by the
+        // producer).  Slower: ptxas tracks both register sets' loads with one scoreboard, so the update of step k also waits
+        // for the load issued for step k+1 — the reason the TMA-staged ring is the default.
+        auto load_table = [&](RowRegs &r) {
+            const double *trow = p.table + (r.ik & CIAO_IDX_MASK) * p.d_pad;
 #pragma unroll
             for (int h = 0; h < H; ++h)
-                t[h] = valid[h] ? __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h])) : make_double2(0.0, 0.0);
+                r.t[h] = valid[h] ? __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h])) : make_double2(0.0, 0.0);
         };
 
         // this lane's remote destinations in the exchange (lane l < C talks to CTA l): computed once, not per step
@@ -208,13 +214,9 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             send_bar[q] = mapa_u32(smem_u32(&part_bar[q]), peer);
         }
         RowRegs rowA, rowB;
-        double2 t_cur[H], t_n1[H], t_n2[H];
         if (K > 0) {
             load_row(0, rowA);
-            if (TABLE) {
-                load_table(rowA.ik, t_cur);
-                if (K > 1) load_table(peek_index(1), t_n1);
-            }
+            if (TABLE && !TT) load_table(rowA);
         }
 #ifdef CIAO_SEQ_PROFILE
         long long prof_acc[4] = {0, 0, 0, 0};
@@ -238,9 +240,11 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             if (TWO_DOTS) v1 = warp_sum_mma(v1, lane);
             PROF_T(t_b);
             if (lane < C) st_async_v2f64(send_dst[par], v0, v1, send_bar[par]);
-            // ---- while the exchange is in flight: next row, and the table row two steps ahead
-            if (k + 1 < K) load_row(k + 1, nxt);
-            if (TABLE && k + 2 < K) load_table(peek_index(k + 2), t_n2);
+            // ---- while the exchange is in flight: the next row and its table row go to registers
+            if (k + 1 < K) {
+                load_row(k + 1, nxt);
+                if (TABLE && !TT) load_table(nxt);
+            }
             PROF_T(t_c);
             mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
             PROF_T(t_d);
@@ -290,13 +294,13 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 if (cur.ik & CIAO_FLAG_HAZARD) {  // the row was rewritten after its prefetch was issued
 #pragma unroll
                     for (int h = 0; h < H; ++h)
-                        if (valid[h]) t_cur[h] = __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h]));
+                        if (valid[h]) cur.t[h] = __ldcg(reinterpret_cast<const double2 *>(trow + gcol[h]));
                 }
                 double snew[CPT];
                 if (ALG == ALG_SAGA) {  // SAGA_basic.jl:56-65
 #pragma unroll
                     for (int q = 0; q < CPT; ++q) {
-                        const double so = (q & 1) ? t_cur[q / 2].y : t_cur[q / 2].x;
+                        const double so = (q & 1) ? cur.t[q / 2].y : cur.t[q / 2].x;
                         const double g = grad_elem<LOSS>(cur.a[q], c, tl);
                         const double diff = __dsub_rn(g, so);
                         double w;
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                     const double rr = cur.hg;     // γ̂/γ_i
 #pragma unroll
                     for (int q = 0; q < CPT; ++q) {
-                        const double so = (q & 1) ? t_cur[q / 2].y : t_cur[q / 2].x;
+                        const double so = (q & 1) ? cur.t[q / 2].y : cur.t[q / 2].x;
                         double t = __dmul_rn(grad_elem<LOSS>(cur.a[q], c, tl), cneg);
                         t = __dadd_rn(t, z[q]);
                         av[q] = __dadd_rn(av[q], __dmul_rn(__dsub_rn(t, so), rr));
@@ -336,13 +340,6 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             PROF_ADD(1, t_b, t_c);  // send + next-row / table-row register prefetch
             PROF_ADD(2, t_c, t_d);  // remaining wait for the cluster exchange
             PROF_ADD(3, t_d, t_e);  // butterfly of partials + fused update
-            if (TABLE) {
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    t_cur[h] = t_n1[h];
-                    t_n1[h] = t_n2[h];
-                }
-            }
         };
         int64_t k = 0;
         for (; k + 1 < K; k += 2) {  // ping-pong the row registers: no copies between steps
@@ -384,10 +381,15 @@ struct SeqShape {
     int64_t dc;
 };
 
+static size_t seq_smem_bytes(const SeqShape &sh, bool table_in_ring) {
+    const size_t cover = (size_t)sh.Tc * sh.cpt;
+    return (size_t)SEQ_D * (cover + SEQ_SLOT_EXTRA + (table_in_ring ? cover : 0)) * 8 + 2 * (size_t)sh.npart_pad * 2 * 8 + (SEQ_D + 2) * 8 + 128;
+}
+
 template <int CPT, int ALG, int LOSS, int REG, bool CZ>
 static int launch_seq(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
     auto kern = seq_kernel<CPT, ALG, LOSS, REG, CZ>;
-    const size_t smem = (size_t)SEQ_D * ((size_t)sh.Tc * CPT + SEQ_SLOT_EXTRA) * 8 + 2 * (size_t)sh.npart_pad * 2 * 8 + (SEQ_D + 2) * 8 + 128;
+    const size_t smem = seq_smem_bytes(sh, a.table_tma != 0);
     static size_t configured[CIAO_MAX_DEVICES] = {};
     if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -470,6 +472,7 @@ static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, doub
     a.v_av = ctx_vec(c, CIAO_VEC_AV); a.v_zsum = ctx_vec(c, CIAO_VEC_Z);  // SVRG: state.z is the running sum of inner iterates
     a.gamma = c->gamma; a.hat_gamma = c->hat_gamma; a.Nd = (double)c->N_total; a.m_d = m_d;
     a.plus = c->plus; a.sag = c->sag; a.reg = c->reg; a.npart_pad = sh.npart_pad;
+    a.table_tma = (ALG == ALG_SAGA || ALG == ALG_FINITO) && seq_smem_bytes(sh, true) <= 200 * 1024 && !c->seq_table_ldg;
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
     int rc;
     switch (sh.cpt) {

@@ -1,28 +1,54 @@
-"""Per-phase cycle profile of the sequential kernel (needs the CIAO_SEQ_PROFILE build: libciao_cuda_prof.so)."""
+"""Per-phase cycle profile of the sequential kernels (needs the CIAO_SEQ_PROFILE build: libciao_cuda_prof.so,
+`python ciaoalgorithms.jl_b200/build.py --profile`).
+
+    python scripts/prof_seq.py <log2 rows> <d> [svrg,saga,finito] [ls,logistic]
+"""
 import os, sys, ctypes as C
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ciao_pkg; ciao_pkg.load()
 from ciaoalgorithms_jl_b200 import _lib as L
-L.SO_PATH = os.path.join(ROOT, "ciaoalgorithms.jl_b200", "libciao_cuda_prof.so")
+L.SO_PATH = os.environ.get("CIAO_SO", os.path.join(ROOT, "ciaoalgorithms.jl_b200", "libciao_cuda_prof.so"))
 from ciaoalgorithms_jl_b200.engine import Engine
-import torch
 rows_log2, d = int(sys.argv[1]), int(sys.argv[2])
+algs = (sys.argv[3] if len(sys.argv) > 3 else "svrg").split(",")
+losses = (sys.argv[4] if len(sys.argv) > 4 else "ls").split(",")
+shapes = [(8, 128)] if len(sys.argv) > 5 else [(8, 128), (4, 256), (8, 64), (8, 256), (4, 128)]
 N = 1 << rows_log2
-e = Engine(0)
-e.gen_synthetic(L.SYNTH_LASSO, N, d, 0x5EED0003, scale=float(N)); e.set_reg(L.REG_NORML1, N / 100.0)
-gamma = 1.0 / (7.0 * N * e.max_row_sqnorm())
-m = min(N, 1 << 17)
-idx = np.random.default_rng(1).integers(1, N + 1, size=m, dtype=np.int64)
-names = ["wait_row", "lds_dot_shfl", "exchange", "sum_update"]
+names = ["dot_shfl", "send_prefetch", "exchange_wait", "sum_update"]
 prof = (C.c_longlong * 4)()
-for C_, T in [(8, 128), (4, 256), (8, 64), (8, 256), (4, 128)]:
-    e.set_tuning(seq_cluster=C_, seq_threads=T)
-    e.svrg_init(np.zeros(d), gamma, True)
-    e.svrg_epoch(idx)
-    t = e.last_timing()
-    e.lib.ciao_debug_seq_prof(e.h, prof)
-    tot = sum(prof)
-    print(f"C={C_} T={T}: {1e3 * t.last_seq_ms / m:.3f} us/step; cycles/step: " +
-          ", ".join(f"{n} {v / m:.0f}" for n, v in zip(names, prof)) + f", total {tot / m:.0f}")
+for loss in losses:
+    e = Engine(0)
+    if loss == "ls":
+        e.gen_synthetic(L.SYNTH_LASSO, N, d, 0x5EED0003, scale=float(N)); e.set_reg(L.REG_NORML1, N / 100.0)
+        Lmax = N * e.max_row_sqnorm()
+    else:
+        e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0); e.set_reg(L.REG_NORML1, 1.0 / N)
+        Lmax = 0.25 * e.max_row_sqnorm()
+    m = min(N, 1 << 17)
+    idx = np.random.default_rng(1).integers(1, N + 1, size=m, dtype=np.int64)
+    x0 = np.zeros(d) if loss == "ls" else np.ones(d)
+    for alg in algs:
+        for C_, T in shapes:
+            e.set_tuning(seq_cluster=C_, seq_threads=T)
+            if alg == "svrg":
+                e.svrg_init(x0, 1.0 / (7.0 * Lmax), True)
+                e.svrg_epoch(idx); e.svrg_epoch(idx)
+            elif alg == "saga":
+                e.saga_init(x0, 1.0 / (3.0 * Lmax), False)
+                e.saga_steps(idx); e.saga_steps(idx)
+            else:
+                gam = np.full(N, 0.999 * N / Lmax)
+                e.finito_init(x0, gam, 1 / np.sum(1 / gam))
+                bp = np.arange(m + 1, dtype=np.int64)
+                e.finito_steps(idx, bp); e.finito_steps(idx, bp)
+            t = e.last_timing()
+            fn = getattr(e.lib, f"ciao_debug_seq_prof_{alg}", None)
+            line = f"{alg:7s} {loss:8s} d={d} C={C_} T={T}: {1e3 * t.last_seq_ms / m:.4f} us/step"
+            if fn is not None:
+                fn.argtypes = [C.c_void_p, C.c_void_p]
+                fn(e.h, prof)
+                line += "; cycles/step: " + ", ".join(f"{n} {v / m:.0f}" for n, v in zip(names, prof)) + f", total {sum(prof) / m:.0f}"
+            print(line, flush=True)
+    e.close()

@@ -153,7 +153,11 @@ def test_svrg_staged_indices_and_determinism():
 # K2 + K4: SAGA / SAG
 @pytest.mark.parametrize("kind,N,d", [(orc.LOSS_LS, 300, 64), (orc.LOSS_LOGISTIC, 500, 1024), (orc.LOSS_LS, 256, 4096)])
 @pytest.mark.parametrize("sag", [False, True])
-def test_saga_steps(kind, N, d, sag):
+@pytest.mark.parametrize("table_path", ["tma_ring", "ldg_fallback"])
+def test_saga_steps(kind, N, d, sag, table_path, monkeypatch):
+    # table rows staged in the shared-memory ring by TMA (default) or prefetched into registers (fallback when the
+    # ring does not fit); the knob is read by ciao_create
+    monkeypatch.setenv("CIAO_SEQ_TABLE_LDG", "1" if table_path == "ldg_fallback" else "0")
     p, e = make_rows(kind, N, d, 0x5A6A + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
     Lmax = p.max_row_sqnorm() * (N if kind == orc.LOSS_LS else 0.25)
     gamma = 1 / ((16 if sag else 3) * Lmax)
@@ -167,6 +171,9 @@ def test_saga_steps(kind, N, d, sag):
     idx = np.array([rng.rand_range(N) for _ in range(3 * N)], dtype=np.int64)
     idx[10:14] = idx[9]          # force back-to-back repeats: exercises the table hazard path
     idx[40] = idx[38]
+    idx[68] = idx[60]            # repeats at the edge of the 8-step prefetch window of the TMA ring
+    idx[89] = idx[80]
+    idx[111] = idx[100]
     ref.steps(idx)
     e.saga_steps(idx[:N])
     e.saga_steps(idx[N:])
@@ -180,7 +187,9 @@ def test_saga_steps(kind, N, d, sag):
 # K2 + K5: Finito / MISO / DIAG
 @pytest.mark.parametrize("kind,N,d", [(orc.LOSS_LS, 250, 64), (orc.LOSS_LOGISTIC, 401, 1024)])
 @pytest.mark.parametrize("sweeping,batch", [(1, 1), (2, 1), (3, 1), (1, 7), (2, 16), (3, 5)])
-def test_finito_steps(kind, N, d, sweeping, batch):
+@pytest.mark.parametrize("table_path", ["tma_ring", "ldg_fallback"])
+def test_finito_steps(kind, N, d, sweeping, batch, table_path, monkeypatch):
+    monkeypatch.setenv("CIAO_SEQ_TABLE_LDG", "1" if table_path == "ldg_fallback" else "0")
     p, e = make_rows(kind, N, d, 0xF1 + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
     A = p.A
     Li = np.sum(A * A, axis=1) * (N if kind == orc.LOSS_LS else 0.25)
