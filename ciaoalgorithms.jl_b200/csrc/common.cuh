@@ -33,6 +33,9 @@
 #define CIAO_VEC_TMP 7
 
 #define CIAO_IDX_MASK 0x0000FFFFFFFFFFFFll
+// prep_indices_kernel flags a step whose row/block index also occurs 1 … CIAO_HAZARD_WINDOW − 1 steps earlier; the sequential
+// kernels stage table rows at most that many steps ahead (seq_impl.cuh SEQ_D = 8, proshi.cu PROSHI_D = 16)
+#define CIAO_HAZARD_WINDOW 20
 #define CIAO_FLAG_HAZARD (1ll << 62)  // same row was written < prefetch-depth steps ago: reload the table row
 #define CIAO_FLAG_PROX (1ll << 61)    // batch boundary: apply prox_g at this step (after: Finito/ProShI, before: LFinito)
 

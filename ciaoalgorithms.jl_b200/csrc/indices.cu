@@ -6,8 +6,8 @@
 #include "common.cuh"
 
 // A table row staged for step k was read from HBM after the exchange of step k − SEQ_D (seq_impl.cuh, SEQ_D = 8), i.e.
-// possibly before the writes of steps k − 8 … k − 1: flag a repeat within the last 8 steps (+ margin).
-constexpr int HAZARD_WINDOW = 12;  // flags j = 1 … 11 steps back
+// possibly before the writes of steps k − 8 … k − 1; ProShI stages PROSHI_D = 16 steps ahead (proshi.cu).
+constexpr int HAZARD_WINDOW = CIAO_HAZARD_WINDOW;  // flags j = 1 … 19 steps back
 
 // out[k] = (raw[k] − 1) | HAZARD if the same row occurs in steps (k − HAZARD_WINDOW, k)
 __global__ void prep_indices_kernel(const int64_t *raw, int64_t n, int64_t N, int64_t *out, int *err) {

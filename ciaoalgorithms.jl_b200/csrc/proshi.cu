@@ -37,66 +37,130 @@ __device__ __forceinline__ double proshi_grad(double q, double c, double s, doub
 }
 
 
-constexpr int PROSHI_P = 8;
+// Batch-1 steps: a true dependency chain per column (z_j → s_ij → av_j → z_j), so the kernel is latency bound and
+// everything that is not on that chain has to stay off it.  Each thread stages the 16-byte slices of (q_i, c_i, s_i)
+// and the scalars (γ_i, γ_i/N) of the block it will need PROSHI_D steps later into ITS OWN shared-memory cells with
+// cp.async, one commit group per step; `cp.async.wait_group D−1` then guarantees exactly the oldest group — a counted
+// in-order pipeline.  (The first version prefetched into registers with ld.global: ptxas tracks all those loads with one
+// scoreboard, so the first use of step k's registers also waited for the load just issued for step k+D — every step paid
+// a full DRAM latency: 0.74 µs/block.)  No barrier, no mbarrier, no reduction, no kernel launch per step; a warp reads the
+// index sequence 32 entries at a time (one coalesced load per 32 steps, prefetched a block ahead) and broadcasts by shuffle.
+constexpr int PROSHI_D = 16;  // steps of prefetch; a staged table slice is stale if the block recurs within D steps → HAZARD flag
+static_assert(PROSHI_D < 32 && (PROSHI_D & (PROSHI_D - 1)) == 0, "ring depth: power of two below the index block of 32");
+static_assert(PROSHI_D <= CIAO_HAZARD_WINDOW - 1, "prep_indices_kernel must flag repeats within the prefetch window");
+constexpr int PROSHI_SLOT_BYTES = 4 * 32 * 16;  // per warp and slot: q | c | s | (γ, γ/N), 16 bytes per lane each
+
+__device__ __forceinline__ void cp_async_cg16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_ca8(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 __global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
-    const int64_t col = 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
-    if (col >= p.n_pad) return;
+    constexpr int D = PROSHI_D;
+    extern __shared__ __align__(16) unsigned char proshi_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t col_raw = 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
+    const bool active = col_raw < p.n_pad;       // inactive lanes of the last warp shadow column 0 and never store
+    const int64_t col = active ? col_raw : 0;
     double z0 = p.v_z[col], z1 = p.v_z[col + 1], av0 = p.v_av[col], av1 = p.v_av[col + 1];
     const double lo0 = p.reg.lo_v ? p.reg.lo_v[col] : p.reg.lo_s, lo1 = p.reg.lo_v ? p.reg.lo_v[col + 1] : p.reg.lo_s;
     const double hi0 = p.reg.hi_v ? p.reg.hi_v[col] : p.reg.hi_s, hi1 = p.reg.hi_v ? p.reg.hi_v[col + 1] : p.reg.hi_s;
     const double gl = p.hat_gamma * p.reg.lambda;
     const double rhat = __ddiv_rn(1.0, p.hat_gamma);
+    const int64_t K = p.K;
+    const uint32_t cell0 = smem_u32(proshi_smem) + (uint32_t)warp * (D * PROSHI_SLOT_BYTES) + (uint32_t)lane * 16;
+    const unsigned char *cellp = proshi_smem + (size_t)warp * (D * PROSHI_SLOT_BYTES) + (size_t)lane * 16;
 
-    int64_t iq[PROSHI_P];
-    double gq[PROSHI_P], nq[PROSHI_P];
-    double2 qq[PROSHI_P], cq[PROSHI_P], sq[PROSHI_P];
-    auto fetch = [&](int j, int64_t pidx) {
+    auto issue = [&](int slot, int64_t pidx) {
         const int64_t i = pidx & CIAO_IDX_MASK;
-        iq[j] = pidx;
-        gq[j] = __ldg(p.gam + i);
-        nq[j] = __ldg(p.gam_n + i);
-        qq[j] = __ldg(reinterpret_cast<const double2 *>(p.qd + i * p.n_pad + col));
-        cq[j] = __ldg(reinterpret_cast<const double2 *>(p.ql + i * p.n_pad + col));
-        sq[j] = __ldcg(reinterpret_cast<const double2 *>(p.table + i * p.n_pad + col));
+        const uint32_t cb = cell0 + (uint32_t)slot * PROSHI_SLOT_BYTES;
+        cp_async_cg16(cb, p.qd + i * p.n_pad + col);
+        cp_async_cg16(cb + 512, p.ql + i * p.n_pad + col);
+        cp_async_cg16(cb + 1024, p.table + i * p.n_pad + col);
+        cp_async_ca8(cb + 1536, p.gam + i);
+        cp_async_ca8(cb + 1544, p.gam_n + i);
     };
-#pragma unroll
-    for (int j = 0; j < PROSHI_P; ++j)
-        if (j < p.K) fetch(j, __ldg(p.idx + j));
-    int64_t in1 = (PROSHI_P < p.K) ? __ldg(p.idx + PROSHI_P) : 0;
+    struct Blk {
+        double2 q, c, s;
+        double gi, gn;
+        int64_t ik;
+    };
+    auto take = [&](int slot, int64_t pidx, Blk &b) {
+        const unsigned char *cb = cellp + (size_t)slot * PROSHI_SLOT_BYTES;
+        b.q = *reinterpret_cast<const double2 *>(cb);
+        b.c = *reinterpret_cast<const double2 *>(cb + 512);
+        b.s = *reinterpret_cast<const double2 *>(cb + 1024);
+        const double2 g = *reinterpret_cast<const double2 *>(cb + 1536);
+        b.gi = g.x;
+        b.gn = g.y;
+        b.ik = pidx;
+    };
 
-    for (int64_t k0 = 0; k0 < p.K; k0 += PROSHI_P) {
+    // index blocks of 32 steps: iv_i covers the step being staged (k + D), iv_prev the block before it, iv_n the next one
+    int64_t iv_i = (lane < K) ? __ldg(p.idx + lane) : 0;
+    int64_t iv_n = (32 + lane < K) ? __ldg(p.idx + 32 + lane) : 0;
+    int64_t iv_prev = iv_i;
 #pragma unroll
-        for (int j = 0; j < PROSHI_P; ++j) {
-            const int64_t k = k0 + j;
-            if (k >= p.K) break;
-            const int64_t ik = iq[j];
-            double2 *srow = reinterpret_cast<double2 *>(p.table + (ik & CIAO_IDX_MASK) * p.n_pad + col);
-            double2 s = sq[j];
-            if (ik & CIAO_FLAG_HAZARD) s = __ldcg(srow);
-            const double gi = gq[j];
-            const double cneg = -nq[j];
-            // ProShI_basic.jl:113-119
-            av0 = __dsub_rn(av0, s.x);
-            av1 = __dsub_rn(av1, s.y);
-            const double x0 = __dadd_rn(s.x, __dmul_rn(gi, z0)), x1 = __dadd_rn(s.y, __dmul_rn(gi, z1));
-            double t0 = __dmul_rn(proshi_grad(qq[j].x, cq[j].x, x0, p.box_lo, p.box_hi, p.eta), cneg);
-            double t1 = __dmul_rn(proshi_grad(qq[j].y, cq[j].y, x1, p.box_lo, p.box_hi, p.eta), cneg);
-            t0 = __dadd_rn(t0, x0);
-            t1 = __dadd_rn(t1, x1);
-            av0 = __dadd_rn(av0, t0);
-            av1 = __dadd_rn(av1, t1);
-            __stcg(srow, make_double2(t0, t1));
-            if (ik & CIAO_FLAG_PROX) {  // :121-123
-                z0 = div_by(__dsub_rn(prox_rt(p.reg.kind, av0, gl, lo0, hi0), av0), p.hat_gamma, rhat);
-                z1 = div_by(__dsub_rn(prox_rt(p.reg.kind, av1, gl, lo1, hi1), av1), p.hat_gamma, rhat);
-            }
-            if (k + PROSHI_P < p.K) fetch(j, in1);
-            in1 = (k + PROSHI_P + 1 < p.K) ? __ldg(p.idx + k + PROSHI_P + 1) : 0;
-        }
+    for (int s = 0; s < D; ++s) {
+        const int64_t pidx = __shfl_sync(0xffffffffu, iv_i, s);
+        if (s < K) issue(s, pidx);
+        cp_async_commit();
     }
-    p.v_z[col] = z0; p.v_z[col + 1] = z1;
-    p.v_av[col] = av0; p.v_av[col + 1] = av1;
+    Blk cur;
+    cp_async_wait<D - 1>();
+    take(0, __shfl_sync(0xffffffffu, iv_i, 0), cur);
+
+    for (int64_t k = 0; k < K; ++k) {
+        double2 *srow = reinterpret_cast<double2 *>(p.table + (cur.ik & CIAO_IDX_MASK) * p.n_pad + col);
+        double2 s = cur.s;
+        if (cur.ik & CIAO_FLAG_HAZARD) s = __ldcg(srow);  // rewritten after its copy was issued: re-read behind our own store
+        const double gi = cur.gi;
+        const double cneg = -cur.gn;
+        // ProShI_basic.jl:113-119
+        av0 = __dsub_rn(av0, s.x);
+        av1 = __dsub_rn(av1, s.y);
+        const double x0 = __dadd_rn(s.x, __dmul_rn(gi, z0)), x1 = __dadd_rn(s.y, __dmul_rn(gi, z1));
+        double t0 = __dmul_rn(proshi_grad(cur.q.x, cur.c.x, x0, p.box_lo, p.box_hi, p.eta), cneg);
+        double t1 = __dmul_rn(proshi_grad(cur.q.y, cur.c.y, x1, p.box_lo, p.box_hi, p.eta), cneg);
+        t0 = __dadd_rn(t0, x0);
+        t1 = __dadd_rn(t1, x1);
+        av0 = __dadd_rn(av0, t0);
+        av1 = __dadd_rn(av1, t1);
+        if (active) __stcg(srow, make_double2(t0, t1));
+        if (cur.ik & CIAO_FLAG_PROX) {  // :121-123
+            z0 = div_by(__dsub_rn(prox_rt(p.reg.kind, av0, gl, lo0, hi0), av0), p.hat_gamma, rhat);
+            z1 = div_by(__dsub_rn(prox_rt(p.reg.kind, av1, gl, lo1, hi1), av1), p.hat_gamma, rhat);
+        }
+        // stage step k + D into the slot just consumed (issued after this step's store: only repeats inside the window are stale)
+        const int64_t sk = k + D;
+        if ((sk & 31) == 0) {
+            iv_prev = iv_i;
+            iv_i = iv_n;
+            iv_n = (sk + 32 + lane < K) ? __ldg(p.idx + sk + 32 + lane) : 0;
+        }
+        const int64_t pidx_s = __shfl_sync(0xffffffffu, iv_i, (int)(sk & 31));
+        if (sk < K) issue((int)(k & (D - 1)), pidx_s);
+        cp_async_commit();
+        // registers of step k + 1
+        const int64_t k1 = k + 1;
+        const int l1 = (int)(k1 & 31);
+        // iv_i is the index block of step k + D = k1 + D − 1; step k1 lies in the same block iff l1 + D − 1 < 32
+        const int64_t pidx_1 = __shfl_sync(0xffffffffu, (l1 + D - 1 < 32) ? iv_i : iv_prev, l1);
+        cp_async_wait<D - 1>();
+        if (k1 < K) take((int)(k1 & (D - 1)), pidx_1, cur);
+    }
+    cp_async_wait<0>();
+    if (active) {
+        p.v_z[col] = z0; p.v_z[col + 1] = z1;
+        p.v_av[col] = av0; p.v_av[col + 1] = av1;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -329,9 +393,15 @@ int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, const 
         // minibatches: blocks of a batch in parallel, one CTA per 8 columns
         proshi_batch_kernel<<<(int)((c->d_pad + 7) / 8), PROSHI_BT, 0, c->stream>>>(a, ptr_dev, n_batches);
     } else {
-        const int T = c->seq_threads > 0 ? std::min(c->seq_threads, 64) : 32;
+        const int T = (c->seq_threads > 32) ? 64 : 32;   // one warp per CTA spreads the columns over the most SMs
         const int grid = (int)((c->d_pad / 2 + T - 1) / T);
-        proshi_steps_kernel<<<grid, T, 0, c->stream>>>(a);
+        const size_t smem = (size_t)(T / 32) * PROSHI_D * PROSHI_SLOT_BYTES;
+        static bool configured = false;
+        if (!configured) {
+            CUDA_TRY(cudaFuncSetAttribute(proshi_steps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PROSHI_D * PROSHI_SLOT_BYTES));
+            configured = true;
+        }
+        proshi_steps_kernel<<<grid, T, smem, c->stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));

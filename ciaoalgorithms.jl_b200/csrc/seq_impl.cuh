@@ -60,6 +60,7 @@ static __device__ long long g_seq_prof[4];  // accumulated cycles of thread 0 of
 #endif
 
 constexpr int SEQ_D = 8;           // row ring depth (steps of prefetch), power of two
+static_assert(SEQ_D + 1 <= CIAO_HAZARD_WINDOW - 1, "prep_indices_kernel must flag repeats within the prefetch window");
 constexpr int SEQ_MAX_PART = 128;  // C·W ≤ 128
 constexpr int SEQ_SLOT_EXTRA = CIAO_TAIL + 2;  // record tail + index word (+ pad to keep slots 16-byte aligned)
 
