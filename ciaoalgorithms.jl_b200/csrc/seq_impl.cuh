@@ -396,6 +396,11 @@ static int launch_seq(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[c->device % CIAO_MAX_DEVICES] = smem;
     }
+    static bool big_cluster[CIAO_MAX_DEVICES] = {};
+    if (sh.C > 8 && !big_cluster[c->device % CIAO_MAX_DEVICES]) {  // 16 CTAs: non-portable cluster size (opt-in on sm_100)
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        big_cluster[c->device % CIAO_MAX_DEVICES] = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(sh.C);
     cfg.blockDim = dim3(sh.Tc + 32);

@@ -39,7 +39,7 @@ if "seq" in what:
     gamma = 1.0 / (7.0 * N * e.max_row_sqnorm())
     m = min(N, 1 << 18)
     idx = np.random.default_rng(1).integers(1, N + 1, size=m, dtype=np.int64)
-    for C, T in [(0, 0), (8, 64), (8, 128), (8, 256), (4, 128), (4, 256), (2, 256)]:
+    for C, T in [(0, 0), (16, 64), (16, 128), (16, 256), (8, 64), (8, 128), (8, 256), (4, 128), (4, 256), (2, 256)]:
         try:
             e.set_tuning(seq_cluster=C, seq_threads=T)
             e.svrg_init(np.zeros(d), gamma, True)

@@ -101,7 +101,8 @@ def test_full_gradient_tuning_shapes(threads, stages, ctas):
 # K3: SVRG / SVRG++
 @pytest.mark.parametrize("kind,N,d,cluster", [(orc.LOSS_LS, 600, 64, 0), (orc.LOSS_LOGISTIC, 700, 256, 0),
                                                (orc.LOSS_LS, 512, 1024, 0), (orc.LOSS_LS, 384, 4096, 0),
-                                               (orc.LOSS_LS, 384, 4096, 2), (orc.LOSS_LS, 300, 1024, 1), (orc.LOSS_LOGISTIC, 512, 1024, 2)])
+                                               (orc.LOSS_LS, 384, 4096, 2), (orc.LOSS_LS, 300, 1024, 1), (orc.LOSS_LOGISTIC, 512, 1024, 2),
+                                               (orc.LOSS_LS, 300, 4096, 16)])
 @pytest.mark.parametrize("plus", [False, True])
 def test_svrg_epochs(kind, N, d, cluster, plus):
     p, e = make_rows(kind, N, d, 0xABC + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N, scale=None)
