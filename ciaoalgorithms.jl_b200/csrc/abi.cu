@@ -89,8 +89,8 @@ static void detach_peers(ciao_ctx *c);
 static void free_problem(ciao_ctx *c) {
     detach_peers(c);
     cudaFree(c->rec); cudaFree(c->qd); cudaFree(c->ql); cudaFree(c->vecs); cudaFree(c->table);
-    cudaFree(c->gamma_dev); cudaFree(c->partial); cudaFree(c->reg_bounds);
-    c->rec = c->qd = c->ql = c->vecs = c->table = c->gamma_dev = c->partial = c->reg_bounds = nullptr;
+    cudaFree(c->gamma_dev); cudaFree(c->partial); cudaFree(c->reg_bounds); cudaFree(c->ss);
+    c->rec = c->qd = c->ql = c->vecs = c->table = c->gamma_dev = c->partial = c->reg_bounds = c->ss = nullptr;
     c->reg = RegParams{CIAO_REG_ZERO, 0, 0, 0, nullptr, nullptr};
     c->loss_kind = -1;
     c->algo = 0;
@@ -273,7 +273,7 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
     ciao_ctx *c = new (std::nothrow) ciao_ctx();
     if (!c) CIAO_FAIL(CIAO_ERR_OOM, "host allocation failed");
     c->device = device;
-    c->cache_cz = getenv("CIAO_CACHE_CZ") != nullptr && getenv("CIAO_CACHE_CZ")[0] == '1';
+    c->cache_cz = !(getenv("CIAO_CACHE_CZ") != nullptr && getenv("CIAO_CACHE_CZ")[0] == '0');
     c->seq_table_ldg = getenv("CIAO_SEQ_TABLE_LDG") != nullptr && getenv("CIAO_SEQ_TABLE_LDG")[0] == '1';
     c->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

@@ -15,7 +15,7 @@
 // HBM data layout
 //   records : [n_rows][ld]  fp64, ld = d_pad + 8, d_pad = round_up(d, 4)
 //             row record i = [ a_i (d, zero padded to d_pad) | tail of 8 scalars ]
-//             tail = b_i or y_i | λ_i or μ_i | γ_i | γ_i/N | γ̂/γ_i | c_i(z_full) | 0 | 0
+//             tail = b_i or y_i | λ_i or μ_i | γ_i | γ_i/N | γ̂/γ_i | 0 | 0 | 0
 //             → one TMA bulk copy brings a row and its scalars (no per-step division, no
 //             dependent scalar loads); records are 32-byte aligned.
 //   table   : [N][d_pad]    fp64  (SAGA gradients / Finito, ProShI s_i)
@@ -27,7 +27,7 @@
 #define TAIL_GAM 2     // γ_i                      (Finito/LFinito, Finito_basic.jl:61-74)
 #define TAIL_GAM_N 3   // γ_i / N                  (Finito_basic.jl:79,113)
 #define TAIL_HAT_GAM 4 // γ̂ / γ_i                  (Finito_basic.jl:115, Finito_LFinito.jl:98)
-#define TAIL_CZ 5      // c_i(z_full) cached by the last full-gradient pass at z_full (SVRG_basic.jl:74)
+#define CIAO_TAIL_USED 6  // doubles of the tail the sequential kernels stage (16-byte multiple)
 #define CIAO_NUM_VECS 8
 #define CIAO_VEC_X0 6
 #define CIAO_VEC_TMP 7
@@ -81,11 +81,14 @@ struct ciao_ctx {
     int algo = 0;                      // 1 svrg, 2 saga, 3 finito, 4 lfinito, 5 proshi
     double gamma = 0, hat_gamma = 0;
     int plus = 0, sag = 0;
-    bool cz_valid = false;             // record tails hold c_i(z_full) for the current z_full
-    // Opt-in (env CIAO_CACHE_CZ=1): the full-gradient pass caches c_i(z_full) in the record tails so that the SVRG/LFinito
-    // step needs one dot instead of two.  Measured at C3: −0.004 µs/step, but +1.4 ms per pass (4M scattered 8-byte
-    // writes → partial-sector RMW), i.e. 6.7 → 6.3 TB/s on the roofline kernel — off by default.
-    bool cache_cz = false;
+    bool cz_valid = false;             // ss holds c_i(z_full) for the current z_full
+    // The full-gradient pass at z_full leaves the scalars a sequential step needs, {b_i, λ_i, 0, c_i(z_full)}, in the dense
+    // array ss[n_rows][4] (one full 32-byte sector per row, 0.1 % of the pass traffic), so that the SVRG/LFinito step needs
+    // one dot product instead of two, forms ∇f_i(z_full) = c_i·a_i while the cluster exchange is in flight, and its producer
+    // stages the scalars with one bulk copy.  (A first version wrote c_i into the record tails: 4M scattered 8-byte writes
+    // → partial-sector RMW, +1.4 ms per pass.)  Single-process, un-windowed passes only; env CIAO_CACHE_CZ=0 disables it.
+    bool cache_cz = true;
+    double *ss = nullptr;
     // Debug/test knob (env CIAO_SEQ_TABLE_LDG=1): SAGA/Finito table rows by register prefetch instead of the TMA-staged
     // ring (the path taken anyway when the ring does not fit in shared memory).
     bool seq_table_ldg = false;
@@ -142,6 +145,29 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// variants taking shared-window addresses computed once (the producer loop of seq_impl.cuh)
+__device__ __forceinline__ void mbar_arrive_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "W_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra W_%=;\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d_s(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_b64(uint32_t addr, int64_t v) {
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(

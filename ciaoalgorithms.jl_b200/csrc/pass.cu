@@ -23,7 +23,7 @@ enum { PASS_GRAD = 0, PASS_SAGA_INIT = 1, PASS_FINITO_INIT = 2, PASS_NORMS = 3 }
 
 struct PassArgs {
     const double *rec;   // [n_rows][ld]
-    double *cz_out;      // same records, written: tail slot TAIL_CZ ← c_i(x) (nullptr: do not cache)
+    double *ss_out;      // dense [n_rows][4] ← {b_i, λ_i, 0, c_i(x)}, one 32-byte sector per row (nullptr: do not cache)
     int64_t n_rows, ld, d_pad;
     const double *x;     // [d_pad]
     double *ws;          // [grid][d_pad]
@@ -138,7 +138,11 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
             const double c = loss_coef<LOSS>(u, tb[r], tl[r]);
             if (tid == 0) {
                 fsum += loss_value<LOSS>(u, tb[r], tl[r]);
-                if (MODE == PASS_GRAD && p.cz_out) p.cz_out[(r0 + r) * p.ld + p.d_pad + TAIL_CZ] = c;
+                if (MODE == PASS_GRAD && p.ss_out) {
+                    double2 *o = reinterpret_cast<double2 *>(p.ss_out + 4 * (r0 + r));
+                    o[0] = make_double2(tb[r], tl[r]);
+                    o[1] = make_double2(0.0, c);
+                }
             }
             if (MODE == PASS_GRAD) {
                 const double cc = (LOSS == CIAO_LOSS_LS) ? c * tl[r] : c;
@@ -281,8 +285,13 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     }
     PassArgs a;
     a.rec = c->rec + w0 * c->ld; a.n_rows = wn; a.ld = c->ld;
-    a.cz_out = (cache_cz && mode == PASS_GRAD && !windowed && c->world == 1) ? c->rec : nullptr;
-    if (mode == PASS_GRAD && cache_cz) c->cz_valid = a.cz_out != nullptr; a.d_pad = d_pad; a.x = x_dev;
+    a.ss_out = nullptr;
+    if (cache_cz && mode == PASS_GRAD && !windowed && c->world == 1) {
+        if (!c->ss) CUDA_TRY(cudaMalloc(&c->ss, (size_t)(c->n_rows + 1) * 4 * sizeof(double)));
+        a.ss_out = c->ss;
+    }
+    if (mode == PASS_GRAD && cache_cz) c->cz_valid = a.ss_out != nullptr;
+    a.d_pad = d_pad; a.x = x_dev;
     a.ws = c->ws; a.fws = c->ws + (size_t)grid * d_pad; a.table = c->table;
     a.Nd = (double)c->N_total; a.stages = S;
     if ((mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT) && !c->table)

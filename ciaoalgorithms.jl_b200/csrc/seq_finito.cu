@@ -8,9 +8,9 @@ int run_seq_finito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m
 
 #ifdef CIAO_SEQ_PROFILE
 // debug builds only (scripts/prof_seq.py): per-phase cycles of the last inner kernel of this translation unit
-extern "C" int ciao_debug_seq_prof_finito(ciao_ctx *c, long long *out4) {
+extern "C" int ciao_debug_seq_prof_finito(ciao_ctx *c, long long *out128) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpyFromSymbol(out4, g_seq_prof, 4 * sizeof(long long)));
+    CUDA_TRY(cudaMemcpyFromSymbol(out128, g_seq_prof, 16 * 8 * sizeof(long long)));
     return CIAO_OK;
 }
 #endif

@@ -42,6 +42,7 @@ struct SeqArgs {
     const int64_t *idx;     // prepared: 0-based row | flags
     int64_t K;
     double *table;
+    const double *ss;       // [n_rows][4]: {b_i, λ_i, 0, c_i(z_full)} (CZ kernels), written by the last full-gradient pass
     double *v_z, *v_zfull, *v_w, *v_av, *v_zsum;
     double gamma, hat_gamma, Nd, m_d;
     int plus, sag;
@@ -51,7 +52,7 @@ struct SeqArgs {
 };
 
 #ifdef CIAO_SEQ_PROFILE
-static __device__ long long g_seq_prof[4];  // accumulated cycles of thread 0 of CTA 0 per phase (debug builds only)
+static __device__ long long g_seq_prof[16 * 8];  // [CTA rank][phase]: accumulated cycles of thread 0 of every CTA (debug builds only)
 #define PROF_T(var) const long long var = clock64()
 #define PROF_ADD(i, a, b) prof_acc[i] += (b) - (a)
 #else
@@ -62,7 +63,11 @@ static __device__ long long g_seq_prof[4];  // accumulated cycles of thread 0 of
 constexpr int SEQ_D = 8;           // row ring depth (steps of prefetch), power of two
 static_assert(SEQ_D + 1 <= CIAO_HAZARD_WINDOW - 1, "prep_indices_kernel must flag repeats within the prefetch window");
 constexpr int SEQ_MAX_PART = 128;  // C·W ≤ 128
-constexpr int SEQ_SLOT_EXTRA = CIAO_TAIL + 2;  // record tail + index word (+ pad to keep slots 16-byte aligned)
+constexpr int SEQ_SLOT_EXTRA = 12;  // staged scalars [0,10) + index word [10] + pad (slots stay 16-byte aligned)
+constexpr int SEQ_IDX_POS = 10;
+// scalar area of a slot:  record tail at [0,6)  (b | λ | γ | γ/N | γ̂/γ | 0),  and/or the pass-written {b, λ, 0, c_i(z_full)}:
+//   SVRG with cached c_i:    ss at [0,4)             → b, λ at 0, 1 as in the tail, c at 3        (2 bulk copies per step)
+//   LFinito with cached c_i: tail at [0,6), ss at [6,10) → γ̂/γ at 4, c at 9                        (3 bulk copies per step)
 
 __device__ __forceinline__ void tma_prefetch_l2(const void *gsrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
@@ -108,34 +113,74 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
 
     if (warp == W) {
         // ===================== producer warp =====================
+        // One lane drives the ring.  Its loop has to turn around faster than the compute warps' step (it re-arms the
+        // exchange barrier and refills one slot per step), so it is kept lean: 32-bit counters, shared-memory addresses
+        // and byte counts computed once, no shard search when all rows are local, two bulk copies per step for the
+        // table-free algorithms.  (Profile: a 64-bit/three-copy version took ≈ 650 cycles per iteration and was the
+        // bottleneck of every variant whose compute path is shorter than that.)
         if (lane == 0) {
-            auto issue_row = [&](int64_t step, int64_t pidx) {
+            const int Ki = (int)K;  // run_seq_alg guarantees K < 2^31
+            const uint32_t ring_s = smem_u32(ring), row_bar_s = smem_u32(row_bar), part_bar_s = smem_u32(part_bar);
+            const uint32_t slot_bytes = (uint32_t)(slot_doubles * 8);
+            const uint32_t row_bytes = (uint32_t)(dc * 8);
+            constexpr bool SS_ONLY = CZ && ALG == ALG_SVRG;     // the pass-written scalars replace the record tail
+            constexpr bool SS_EXTRA = CZ && ALG == ALG_LFINITO;  // … or come next to it
+            const uint32_t tail_off = (uint32_t)cover * 8, idx_off = (uint32_t)(cover + SEQ_IDX_POS) * 8;
+            const uint32_t table_off = (uint32_t)(cover + SEQ_SLOT_EXTRA) * 8;
+            const uint32_t tail_bytes = (uint32_t)(CIAO_TAIL_USED * 8);
+            const uint32_t tx_bytes = row_bytes * (TT ? 2u : 1u) + (SS_ONLY ? 32u : tail_bytes + (SS_EXTRA ? 32u : 0u));
+            const bool one_shard = p.rows.n <= 1;
+            const double *base0 = p.rows.base[0] + cbase;
+            const double *table0 = TABLE ? p.table + cbase : nullptr;
+            const int64_t ld = p.ld, d_pad = p.d_pad;
+            auto issue_row = [&](int step, int64_t pidx) {
                 const int64_t i = pidx & CIAO_IDX_MASK;
-                const int slot = (int)(step & (D - 1));
-                double *dst = ring + slot * slot_doubles;
-                int s = 0;  // shard holding row i (≤ 8 shards: linear search, off the compute warps' critical path)
-                while (s + 1 < p.rows.n && i >= p.rows.start[s + 1]) ++s;
-                const double *src = p.rows.base[s] + (i - p.rows.start[s]) * p.ld;
-                *reinterpret_cast<int64_t *>(dst + cover + CIAO_TAIL) = pidx;  // released by the arrive below
-                mbar_arrive_expect_tx(&row_bar[slot], (uint32_t)(dc * 8 * (TT ? 2 : 1) + CIAO_TAIL * 8));
-                tma_load_1d(dst, src + cbase, (uint32_t)(dc * 8), &row_bar[slot]);
-                tma_load_1d(dst + cover, src + p.d_pad, CIAO_TAIL * 8, &row_bar[slot]);
-                if (TT) tma_load_1d(dst + cover + SEQ_SLOT_EXTRA, p.table + i * p.d_pad + cbase, (uint32_t)(dc * 8), &row_bar[slot]);
-                else if (TABLE) tma_prefetch_l2(p.table + i * p.d_pad + cbase, (uint32_t)(dc * 8));
+                const uint32_t slot = (uint32_t)step & (D - 1);
+                const uint32_t dst = ring_s + slot * slot_bytes, bar = row_bar_s + slot * 8;
+                const double *src;
+                if (one_shard) {
+                    src = base0 + i * ld;
+                } else {  // shard holding row i (≤ 8 shards: linear search)
+                    int sh = 0;
+                    while (sh + 1 < p.rows.n && i >= p.rows.start[sh + 1]) ++sh;
+                    src = p.rows.base[sh] + (i - p.rows.start[sh]) * ld + cbase;
+                }
+                sts_b64(dst + idx_off, pidx);  // released by the arrive below
+                mbar_arrive_expect_tx_s(bar, tx_bytes);
+                tma_load_1d_s(dst, src, row_bytes, bar);
+                // the step's scalars: the record tail and/or {b_i, λ_i, 0, c_i(z_full)} from the dense array of the last pass
+                if (!SS_ONLY) tma_load_1d_s(dst + tail_off, src + (d_pad - cbase), tail_bytes, bar);
+                if (SS_ONLY) tma_load_1d_s(dst + tail_off, p.ss + 4 * i, 32, bar);
+                if (SS_EXTRA) tma_load_1d_s(dst + tail_off + CIAO_TAIL_USED * 8, p.ss + 4 * i, 32, bar);
+                if (TT) tma_load_1d_s(dst + table_off, table0 + i * d_pad, row_bytes, bar);
+                else if (TABLE) tma_prefetch_l2(table0 + i * d_pad, row_bytes);
             };
-            if (K > 0) mbar_arrive_expect_tx(&part_bar[0], part_bytes);
-            if (K > 1) mbar_arrive_expect_tx(&part_bar[1], part_bytes);
-            for (int64_t s = 0; s < D && s < K; ++s) issue_row(s, __ldg(p.idx + s));
-            int64_t n1 = (D < K) ? __ldg(p.idx + D) : 0, n2 = (D + 1 < K) ? __ldg(p.idx + D + 1) : 0;
-            for (int64_t k = 0; k < K; ++k) {
-                const int par = (int)(k & 1);
+            if (Ki > 0) mbar_arrive_expect_tx_s(part_bar_s, part_bytes);
+            if (Ki > 1) mbar_arrive_expect_tx_s(part_bar_s + 8, part_bytes);
+            for (int st = 0; st < D && st < Ki; ++st) issue_row(st, __ldg(p.idx + st));
+            int64_t n1 = (D < Ki) ? __ldg(p.idx + D) : 0, n2 = (D + 1 < Ki) ? __ldg(p.idx + D + 1) : 0;
+            const int64_t *idx_ahead = p.idx + D + 2;
+#ifdef CIAO_SEQ_PROFILE
+            long long prod_busy = 0;
+#endif
+            for (int k = 0; k < Ki; ++k) {
+                const uint32_t pb = part_bar_s + ((uint32_t)k & 1u) * 8;
                 // phase k complete ⇒ every warp of the cluster has consumed row k and sent its partial
-                mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
-                if (k + 2 < K) mbar_arrive_expect_tx(&part_bar[par], part_bytes);  // arm the exchange of step k+2
-                if (k + D < K) issue_row(k + D, n1);
+                mbar_wait_s(pb, ((uint32_t)k >> 1) & 1u);
+#ifdef CIAO_SEQ_PROFILE
+                const long long pw = clock64();
+#endif
+                if (k + 2 < Ki) mbar_arrive_expect_tx_s(pb, part_bytes);  // arm the exchange of step k+2
+                if (k + D < Ki) issue_row(k + D, n1);
                 n1 = n2;
-                n2 = (k + D + 2 < K) ? __ldg(p.idx + k + D + 2) : 0;
+                n2 = (k + D + 2 < Ki) ? __ldg(idx_ahead + k) : 0;
+#ifdef CIAO_SEQ_PROFILE
+                prod_busy += clock64() - pw;
+#endif
             }
+#ifdef CIAO_SEQ_PROFILE
+            g_seq_prof[rank * 8 + 5] = prod_busy;  // producer: cycles from wake-up to the end of its iteration
+#endif
         }
     } else {
         // ===================== compute warps =====================
@@ -188,8 +233,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             r.lam = rp[cover + TAIL_LAM];
             r.gn = (ALG == ALG_FINITO) ? rp[cover + TAIL_GAM_N] : 0.0;
             r.hg = (ALG == ALG_FINITO || ALG == ALG_LFINITO) ? rp[cover + TAIL_HAT_GAM] : 0.0;
-            r.cz = (USES_ZFULL && CZ) ? rp[cover + TAIL_CZ] : 0.0;
-            r.ik = (ALG != ALG_SVRG) ? *reinterpret_cast<const int64_t *>(rp + cover + CIAO_TAIL) : 0;
+            r.cz = (USES_ZFULL && CZ) ? rp[cover + (ALG == ALG_SVRG ? 3 : CIAO_TAIL_USED + 3)] : 0.0;
+            r.ik = (ALG != ALG_SVRG) ? *reinterpret_cast<const int64_t *>(rp + cover + SEQ_IDX_POS) : 0;
             if (TT) {  // the table row slice was staged D steps ago (stale if the row was rewritten since: HAZARD flag)
 #pragma unroll
                 for (int h = 0; h < H; ++h) r.t[h] = *reinterpret_cast<const double2 *>(rp + cover + SEQ_SLOT_EXTRA + lcol[h]);
@@ -220,7 +265,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             if (TABLE && !TT) load_table(rowA);
         }
 #ifdef CIAO_SEQ_PROFILE
-        long long prof_acc[4] = {0, 0, 0, 0};
+        long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
         // one step; cur = registers of step k, nxt = registers to fill for step k+1
         auto step = [&](const int64_t k, RowRegs &cur, RowRegs &nxt) {
@@ -241,8 +286,25 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             if (TWO_DOTS) v1 = warp_sum_mma(v1, lane);
             PROF_T(t_b);
             if (lane < C) st_async_v2f64(send_dst[par], v0, v1, send_bar[par]);
+            // ---- in the shadow of the exchange: ∇f_i(z_full) = c_i(z_full)·a_i from the cached scalar (the step is fp64-issue
+            //      bound after the exchange, so every product formed here comes off the critical path)
+            double gz[CPT];
+            if (CZ) {
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) {
+                    gz[q] = grad_elem<LOSS>(cur.a[q], cur.cz, cur.lam);
+                    if (ALG == ALG_LFINITO) gz[q] = __dmul_rn(cN, gz[q]);
+                }
+            }
             // ---- while the exchange is in flight: the next row and its table row go to registers
             if (k + 1 < K) {
+#ifdef CIAO_SEQ_PROFILE
+                {
+                    const long long w0 = clock64();
+                    mbar_wait(&row_bar[(k + 1) & (D - 1)], (uint32_t)(((k + 1) >> 3) & 1));
+                    prof_acc[4] += clock64() - w0;  // wait for the staged row of the next step (included in phase 1)
+                }
+#endif
                 load_row(k + 1, nxt);
                 if (TABLE && !TT) load_table(nxt);
             }
@@ -272,7 +334,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const double cw = loss_coef<LOSS>(u0, tb, tl);
 #pragma unroll
                 for (int q = 0; q < CPT; ++q) {
-                    double t = __dsub_rn(grad_elem<LOSS>(cur.a[q], cz, tl), grad_elem<LOSS>(cur.a[q], cw, tl));
+                    double t = __dsub_rn(CZ ? gz[q] : grad_elem<LOSS>(cur.a[q], cz, tl), grad_elem<LOSS>(cur.a[q], cw, tl));
                     t = __dsub_rn(t, av[q]);
                     t = __dmul_rn(t, p.gamma);
                     t = __dadd_rn(t, z[q]);
@@ -285,7 +347,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const double rr = cur.hg;  // γ̂/γ_i
 #pragma unroll
                 for (int q = 0; q < CPT; ++q) {
-                    av[q] = __dadd_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(cur.a[q], czf, tl)));
+                    av[q] = __dadd_rn(av[q], CZ ? gz[q] : __dmul_rn(cN, grad_elem<LOSS>(cur.a[q], czf, tl)));
                     av[q] = __dsub_rn(av[q], __dmul_rn(cN, grad_elem<LOSS>(cur.a[q], czz, tl)));
                     av[q] = __dadd_rn(av[q], __dmul_rn(rr, __dsub_rn(z[q], zf[q])));
                 }
@@ -299,21 +361,29 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 }
                 double snew[CPT];
                 if (ALG == ALG_SAGA) {  // SAGA_basic.jl:56-65
+                    // the SAG/SAGA choice is made once per step, outside the element loop: a branch per element keeps the
+                    // compiler from interleaving the four independent element chains (measured: 520 → 350 cycles at d = 4096)
+                    if (p.sag) {
 #pragma unroll
-                    for (int q = 0; q < CPT; ++q) {
-                        const double so = (q & 1) ? cur.t[q / 2].y : cur.t[q / 2].x;
-                        const double g = grad_elem<LOSS>(cur.a[q], c, tl);
-                        const double diff = __dsub_rn(g, so);
-                        double w;
-                        if (p.sag) {
-                            av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));
-                            w = __dsub_rn(z[q], __dmul_rn(p.gamma, av[q]));
-                        } else {
-                            w = __dsub_rn(z[q], __dmul_rn(p.gamma, __dadd_rn(diff, av[q])));
-                            av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));
+                        for (int q = 0; q < CPT; ++q) {
+                            const double so = (q & 1) ? cur.t[q / 2].y : cur.t[q / 2].x;
+                            const double g = grad_elem<LOSS>(cur.a[q], c, tl);
+                            av[q] = __dadd_rn(av[q], div_by(__dsub_rn(g, so), p.Nd, rN));      // :58
+                            const double w = __dsub_rn(z[q], __dmul_rn(p.gamma, av[q]));       // :59
+                            z[q] = prox_elem<REG>(w, gl, blo[q], bhi[q]);
+                            snew[q] = g;
                         }
-                        z[q] = prox_elem<REG>(w, gl, blo[q], bhi[q]);
-                        snew[q] = g;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < CPT; ++q) {
+                            const double so = (q & 1) ? cur.t[q / 2].y : cur.t[q / 2].x;
+                            const double g = grad_elem<LOSS>(cur.a[q], c, tl);
+                            const double diff = __dsub_rn(g, so);
+                            const double w = __dsub_rn(z[q], __dmul_rn(p.gamma, __dadd_rn(diff, av[q])));  // :61
+                            av[q] = __dadd_rn(av[q], div_by(diff, p.Nd, rN));                  // :62
+                            z[q] = prox_elem<REG>(w, gl, blo[q], bhi[q]);
+                            snew[q] = g;
+                        }
                     }
                 } else {  // Finito_basic.jl:112-118
                     const double cneg = -cur.gn;  // −(γ_i/N)
@@ -369,8 +439,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             }
         }
 #ifdef CIAO_SEQ_PROFILE
-        if (tid == 0 && rank == 0)
-            for (int i = 0; i < 4; ++i) g_seq_prof[i] = prof_acc[i];
+        if (tid == 0)
+            for (int i = 0; i < 5; ++i) g_seq_prof[rank * 8 + i] = prof_acc[i];  // [5] belongs to the producer lane
 #endif
     }
     cluster_sync_all();  // nobody exits while a peer may still touch its shared memory
@@ -461,6 +531,7 @@ static int seq_shape(ciao_ctx *c, SeqShape *sh) {
 template <int ALG>
 static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d) {
     if (K <= 0) return CIAO_OK;
+    if (K >= (int64_t)1 << 31) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "sequential kernel: more than 2^31 - 1 steps in one call");
     SeqShape sh;
     CIAO_TRY(seq_shape(c, &sh));
     SeqArgs a;
@@ -473,7 +544,7 @@ static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, doub
         a.rows.start[1] = c->n_rows;
     }
     a.ld = c->ld; a.d_pad = c->d_pad; a.dc = sh.dc;
-    a.idx = idx_prepared; a.K = K; a.table = c->table;
+    a.idx = idx_prepared; a.K = K; a.table = c->table; a.ss = c->ss;
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_zfull = ctx_vec(c, CIAO_VEC_Z_FULL); a.v_w = ctx_vec(c, CIAO_VEC_W);
     a.v_av = ctx_vec(c, CIAO_VEC_AV); a.v_zsum = ctx_vec(c, CIAO_VEC_Z);  // SVRG: state.z is the running sum of inner iterates
     a.gamma = c->gamma; a.hat_gamma = c->hat_gamma; a.Nd = (double)c->N_total; a.m_d = m_d;

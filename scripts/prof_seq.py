@@ -16,8 +16,9 @@ algs = (sys.argv[3] if len(sys.argv) > 3 else "svrg").split(",")
 losses = (sys.argv[4] if len(sys.argv) > 4 else "ls").split(",")
 shapes = [(8, 128)] if len(sys.argv) > 5 else [(8, 128), (4, 256), (8, 64), (8, 256), (4, 128)]
 N = 1 << rows_log2
-names = ["dot_shfl", "send_prefetch", "exchange_wait", "sum_update"]
-prof = (C.c_longlong * 4)()
+names = ["dot_shfl", "send_prefetch", "exchange_wait", "sum_update", "(row_wait)", "(producer_busy)"]
+prof = (C.c_longlong * 128)()
+per_cta = "--per-cta" in sys.argv
 for loss in losses:
     e = Engine(0)
     if loss == "ls":
@@ -49,6 +50,9 @@ for loss in losses:
             if fn is not None:
                 fn.argtypes = [C.c_void_p, C.c_void_p]
                 fn(e.h, prof)
-                line += "; cycles/step: " + ", ".join(f"{n} {v / m:.0f}" for n, v in zip(names, prof)) + f", total {sum(prof) / m:.0f}"
+                line += "; cycles/step: " + ", ".join(f"{n} {v / m:.0f}" for n, v in zip(names, prof)) + f", total {sum(prof[:4]) / m:.0f}"
+                if per_cta:
+                    for r in range(C_ if C_ else 8):
+                        line += f"\n      CTA {r}: " + ", ".join(f"{n} {prof[8 * r + j] / m:.0f}" for j, n in enumerate(names))
             print(line, flush=True)
     e.close()

@@ -132,6 +132,37 @@ def test_svrg_epochs(kind, N, d, cluster, plus):
     e.close()
 
 
+@pytest.mark.parametrize("kind,N,d", [(orc.LOSS_LS, 384, 4096), (orc.LOSS_LOGISTIC, 500, 256)])
+def test_svrg_lfinito_without_cached_coefficients(kind, N, d, monkeypatch):
+    """CIAO_CACHE_CZ=0: the step recomputes a_i·z_full (two dot products per step) instead of reading c_i(z_full) from
+    the dense cache the full-gradient pass leaves behind — the path multi-process and windowed passes take."""
+    monkeypatch.setenv("CIAO_CACHE_CZ", "0")
+    p, e = make_rows(kind, N, d, 0xC2 + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
+    Lmax = p.max_row_sqnorm() * (N if kind == orc.LOSS_LS else 0.25)
+    x0 = np.zeros(d) if kind == orc.LOSS_LS else np.ones(d)
+    ref = orc.SVRGState(p, x0, 1 / (7 * Lmax), m=N, plus=False)
+    e.svrg_init(x0, 1 / (7 * Lmax), False)
+    rng = HostRNG(8)
+    for _ in range(2):
+        idx = rng.rand_vec(N, N)
+        ref.epoch(idx)
+        e.svrg_epoch(idx)
+    assert rel(e.get_vec(L.VEC_Z_FULL), ref.z_full) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    Li = np.sum(p.A * p.A, axis=1) * (N if kind == orc.LOSS_LS else 0.25)
+    gam = 0.999 * N / Li
+    refl = orc.LFinitoState(p, x0 + 0.1, gam, 4)
+    e.lfinito_init(x0 + 0.1, gam, refl.hat_gamma)
+    sw = LFinitoSweeper(N, 4, 3, HostRNG(2))
+    for _ in range(2):
+        order = sw.next()
+        refl.outer(order)
+        e.lfinito_outer(order, 4)
+    assert rel(e.get_vec(L.VEC_Z), refl.z) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), refl.av) < 1e-8
+    e.close()
+
+
 def test_svrg_staged_indices_and_determinism():
     N, d = 800, 512
     p, e = make_rows(orc.LOSS_LS, N, d, 11, lam_reg=0.05)
