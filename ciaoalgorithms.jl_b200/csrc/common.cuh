@@ -236,12 +236,13 @@ __device__ __forceinline__ double div_by(double x, double den, double rden) {
     return fma(rem, rden, q0);
 }
 
-// Warp-wide sum on the fp64 tensor core: two m8n8k4 DMMAs and ONE shuffle instead of five shuffle+add rounds
-// (measured on B200, scripts/micro/dmma_micro.cu: DMMA ≈ 28 cycles, a double shuffle+DADD round ≈ 45 cycles, so
-// ≈ 105 instead of ≈ 225 cycles of latency).  Used where the reduction sits on a sequential critical path.
-//   1st DMMA:  A[r][k] = v of lane 4r+k, B = 1  →  every lane of group r = lane>>2 holds S_r = Σ_k v
-//   shuffle :  lane L fetches S_{(L&3) + 4((L>>2)&1)}, i.e. B[k][c] = S_{k + 4(c&1)}
-//   2nd DMMA:  A = 1  →  D[·][c] = S_0..3 (c even) or S_4..7 (c odd); a lane holds one of each → their sum is the total.
+// Warp-wide sum on the fp64 tensor core: two m8n8k4 DMMAs and one add, no shuffle (measured on B200,
+// scripts/micro/dmma_micro.cu: DMMA ≈ 28 cycles, a double shuffle+DADD round ≈ 45 cycles; five shuffle rounds ≈ 225
+// cycles, DMMA + SHFL + DMMA + DADD ≈ 90, this version ≈ 65).  Used where the reduction sits on a sequential critical path.
+// Fragment layout of mma.m8n8k4.f64: lane L holds A[L>>2][L&3], B[L&3][L>>2] and D[L>>2][2(L&3) + {0,1}].
+//   1st DMMA:  A = 1, B[k][j] = v of lane 4j+k  →  D[·][j] = S_j = Σ_k v_{4j+k}: lane L holds S_{2c}, S_{2c+1}, c = L&3
+//   add:       x = S_{2c} + S_{2c+1}, so the four lanes of every group hold the four pair sums
+//   2nd DMMA:  A[i][k] = x of lane 4i+k = S_{2k} + S_{2k+1}, B = 1  →  D[·][·] = Σ_k (S_{2k} + S_{2k+1}) = total
 // The result is identical in all 32 lanes and, for identical inputs, in all warps (fixed hardware summation order).
 __device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
@@ -249,11 +250,11 @@ __device__ __forceinline__ void dmma_884(double &d0, double &d1, double a, doubl
                  : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
 }
 __device__ __forceinline__ double warp_sum_mma(double v, int lane) {
+    (void)lane;
     double s0, s1, t0, t1;
-    dmma_884(s0, s1, v, 1.0);
-    const double b = __shfl_sync(0xffffffffu, s0, 4 * ((lane & 3) + 4 * ((lane >> 2) & 1)));
-    dmma_884(t0, t1, 1.0, b);
-    return t0 + t1;
+    dmma_884(s0, s1, 1.0, v);
+    dmma_884(t0, t1, s0 + s1, 1.0);
+    return t0;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -18,7 +18,7 @@
 //      of the cluster through DSMEM with st.async (a remote store that completes on the
 //      destination CTA's mbarrier by tx-count, so neither side needs a cluster-scope
 //      fence); every warp then reduces the C·W partials with the same tensor-core sum (two fp64
-//      DMMAs + one shuffle, common.cuh warp_sum_mma — half the latency of five shuffle rounds), so
+//      DMMAs + one add, no shuffle: common.cuh warp_sum_mma — a quarter of the latency of five shuffle rounds), so
 //      all threads of all CTAs hold bit-identical scalars — no CTA or cluster barrier
 //      instruction on the step's critical path.  While the exchange is in flight the row
 //      and the table row of step k+1 are pulled into the other (ping-pong) register set.
