@@ -63,6 +63,9 @@ SIGNATURES = {
     "ciao_finito_steps": (i32, [_ctx, C.c_void_p, C.c_void_p, i64]),
     "ciao_lfinito_init": (i32, [_ctx, C.c_void_p, C.c_void_p, f64]),
     "ciao_lfinito_outer": (i32, [_ctx, C.c_void_p, i64, i64]),
+    "ciao_finito_adaptive_init": (i32, [_ctx, C.c_void_p, f64, f64]),
+    "ciao_finito_adaptive_steps": (i32, [_ctx, C.c_void_p, i64, _ip]),
+    "ciao_finito_adaptive_get": (i32, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _ip]),
     "ciao_proshi_init": (i32, [_ctx, C.c_void_p, C.c_void_p, f64]),
     "ciao_proshi_steps": (i32, [_ctx, C.c_void_p, C.c_void_p, i64]),
     "ciao_proshi_solution": (i32, [_ctx, C.c_void_p]),

@@ -29,6 +29,9 @@ int run_seq_svrg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d
 int run_seq_saga(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
 int run_seq_finito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
 int run_seq_lfinito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
+int run_seq_adaptive(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double alpha, double tol_b);  // seq_adaptive.cu
+int run_adaptive_init(ciao_ctx *c, const double *x0_dev, double alpha, int *n_chunks_out);
+int run_adaptive_av(ciao_ctx *c, const double *S_dev, const double *G_dev, double hat_gamma);
 static int run_seq(ciao_ctx *c, int alg, const int64_t *idx_prepared, int64_t K, double m_d) {
     switch (alg) {
         case ALG_SVRG: return run_seq_svrg(c, idx_prepared, K, m_d);
@@ -89,8 +92,9 @@ static void detach_peers(ciao_ctx *c);
 static void free_problem(ciao_ctx *c) {
     detach_peers(c);
     cudaFree(c->rec); cudaFree(c->qd); cudaFree(c->ql); cudaFree(c->vecs); cudaFree(c->table);
-    cudaFree(c->gamma_dev); cudaFree(c->partial); cudaFree(c->reg_bounds); cudaFree(c->ss);
-    c->rec = c->qd = c->ql = c->vecs = c->table = c->gamma_dev = c->partial = c->reg_bounds = c->ss = nullptr;
+    cudaFree(c->gamma_dev); cudaFree(c->partial); cudaFree(c->reg_bounds); cudaFree(c->ss); cudaFree(c->adapt); cudaFree(c->adapt_scal); cudaFree(c->adapt_counters);
+    c->rec = c->qd = c->ql = c->vecs = c->table = c->gamma_dev = c->partial = c->reg_bounds = c->ss = c->adapt = c->adapt_scal = nullptr;
+    c->adapt_counters = nullptr;
     c->reg = RegParams{CIAO_REG_ZERO, 0, 0, 0, nullptr, nullptr};
     c->loss_kind = -1;
     c->algo = 0;
@@ -579,6 +583,98 @@ extern "C" int ciao_svrg_epoch(ciao_ctx *c, const int64_t *idx, int64_t m) {
     CIAO_TRY(run_seq(c, ALG_SVRG, c->idx_prep, m, (double)m));                     // :73-86
     CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz));  // :87-92
     return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
+}
+
+// ---------------------------------------------------------------------------
+// Finito adaptive  (Finito_adaptive.jl)
+// ---------------------------------------------------------------------------
+// Julia's sum(1 ./ γ): pairwise above 1024 terms (Base.mapreduce_impl), restated on the host like the shim does for the
+// other variants, so γ̂ carries the reference's rounding
+static int prox_vec(ciao_ctx *c, int src, int dst, double gamma);
+static double pairwise_recip_sum(const double *v, int64_t lo, int64_t hi) {
+    if (hi - lo < 1024) {
+        double s = 1 / v[lo];
+        for (int64_t i = lo + 1; i < hi; ++i) s += 1 / v[i];
+        return s;
+    }
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    return pairwise_recip_sum(v, lo, mid) + pairwise_recip_sum(v, mid, hi);
+}
+
+extern "C" int ciao_finito_adaptive_init(ciao_ctx *c, const double *x0, double alpha, double tol_b) {
+    CIAO_TRY(need_rows(c, "ciao_finito_adaptive_init", true));
+    if (!x0 || !(alpha > 0) || !(tol_b > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_finito_adaptive_init: x0 is null, α ≤ 0 or tol_b ≤ 0 (Finito.jl:57-60)");
+    if (c->peers.n > 1) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito keeps N×d tables: not available on row-sharded problems");
+    c->algo = ALG_FINITO_ADAPTIVE; c->adapt_alpha = alpha; c->adapt_tol_b = tol_b; c->adapt_backtracks = 0;
+    c->cz_valid = false;
+    CIAO_TRY(reserve_for_solver(c));
+    CIAO_TRY(alloc_table(c));
+    const int64_t N = c->N_total;
+    if (!c->adapt) CUDA_TRY(cudaMalloc(&c->adapt, (size_t)N * 4 * sizeof(double)));
+    if (!c->adapt_scal) CUDA_TRY(cudaMalloc(&c->adapt_scal, 8 * sizeof(double)));
+    if (!c->adapt_counters) CUDA_TRY(cudaMalloc(&c->adapt_counters, 4 * sizeof(int64_t)));
+    CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
+    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X0)));                  // sum(∇f)  :90
+    CIAO_TRY(run_finish(c, nullptr, 1.0, 1.0, ctx_vec(c, CIAO_VEC_TMP)));
+    int chunks = 0;
+    CIAO_TRY(run_adaptive_init(c, ctx_vec(c, CIAO_VEC_X0), alpha, &chunks));        // :65-87, partial sums of x0 ./ γ_i
+    launch_reduce_ws(c, c->ws, c->ws + (size_t)chunks * c->d_pad, chunks, c->partial, c->partial + c->d_pad, 0, 1);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    std::vector<double> gam((size_t)N);
+    CUDA_TRY(cudaMemcpy2DAsync(gam.data(), sizeof(double), c->adapt, 4 * sizeof(double), sizeof(double), (size_t)N, cudaMemcpyDeviceToHost,
+                               c->stream));
+    int h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, c->err_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (h) {
+        CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
+        c->algo = 0;
+        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito: ∇f_i(x0 + 1) == ∇f_i(x0) for some i; the reference then perturbs x0 at random "
+                  "(Finito_adaptive.jl:75-81), which the engine does not do — choose another x0");
+    }
+    c->hat_gamma = 1 / pairwise_recip_sum(gam.data(), 0, N);                        // :89
+    CUDA_TRY(cudaMemcpyAsync(c->adapt_scal, &c->hat_gamma, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CIAO_TRY(run_adaptive_av(c, c->partial, ctx_vec(c, CIAO_VEC_TMP), c->hat_gamma));  // :90
+    CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));                   // :91
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CIAO_OK;
+}
+
+extern "C" int ciao_finito_adaptive_steps(ciao_ctx *c, const int64_t *idx, int64_t K, int64_t *steps_done) {
+    CIAO_TRY(need_rows(c, "ciao_finito_adaptive_steps", true));
+    if (c->algo != ALG_FINITO_ADAPTIVE) CIAO_FAIL(CIAO_ERR_STATE, "ciao_finito_adaptive_steps before ciao_finito_adaptive_init");
+    if (K < 0) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_finito_adaptive_steps: negative step count");
+    if (steps_done) *steps_done = 0;
+    if (K == 0) return CIAO_OK;
+    const int64_t *raw;
+    CIAO_TRY(fetch_raw_indices(c, idx, K, &raw));
+    CIAO_TRY(launch_prep_indices(c, raw, K, c->N_total, c->idx_prep));
+    CIAO_TRY(check_err_flag(c));   // an out-of-range index must not reach the table updates
+    CIAO_TRY(run_seq_adaptive(c, c->idx_prep, K, c->adapt_alpha, c->adapt_tol_b));  // :101-160
+    int64_t cnt[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(cnt, c->adapt_counters, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&c->hat_gamma, c->adapt_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->adapt_backtracks += cnt[1];
+    if (steps_done) *steps_done = cnt[0];
+    return CIAO_OK;
+}
+
+// state.γ, state.fi_x, c_i with ∇f_i(x_i) = c_i·a_i (each N entries, any may be NULL), state.hat_γ, total reductions of γ
+extern "C" int ciao_finito_adaptive_get(ciao_ctx *c, double *gamma_N, double *fi_x_N, double *coef_N, double *hat_gamma, int64_t *backtracks) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_finito_adaptive_get: null context");
+    if (c->algo != ALG_FINITO_ADAPTIVE || !c->adapt) CIAO_FAIL(CIAO_ERR_STATE, "ciao_finito_adaptive_get before ciao_finito_adaptive_init");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double *outs[3] = {gamma_N, fi_x_N, coef_N};
+    for (int j = 0; j < 3; ++j)
+        if (outs[j])
+            CUDA_TRY(cudaMemcpy2DAsync(outs[j], sizeof(double), c->adapt + j, 4 * sizeof(double), sizeof(double), (size_t)c->N_total,
+                                       cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (hat_gamma) *hat_gamma = c->hat_gamma;
+    if (backtracks) *backtracks = c->adapt_backtracks;
+    return CIAO_OK;
 }
 
 // ---------------------------------------------------------------------------

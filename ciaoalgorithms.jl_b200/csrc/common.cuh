@@ -36,10 +36,11 @@
 // prep_indices_kernel flags a step whose row/block index also occurs 1 … CIAO_HAZARD_WINDOW − 1 steps earlier; the sequential
 // kernels stage table rows at most that many steps ahead (seq_impl.cuh SEQ_D = 8, proshi.cu PROSHI_D = 16)
 #define CIAO_HAZARD_WINDOW 20
+#define CIAO_HAZ_DIST_SHIFT 48         // bits 48..52 of a flagged step: distance (1 … CIAO_HAZARD_WINDOW − 1) to the previous occurrence
 #define CIAO_FLAG_HAZARD (1ll << 62)  // same row was written < prefetch-depth steps ago: reload the table row
 #define CIAO_FLAG_PROX (1ll << 61)    // batch boundary: apply prox_g at this step (after: Finito/ProShI, before: LFinito)
 
-enum { ALG_SVRG = 1, ALG_SAGA = 2, ALG_FINITO = 3, ALG_LFINITO = 4, ALG_PROSHI = 5 };
+enum { ALG_SVRG = 1, ALG_SAGA = 2, ALG_FINITO = 3, ALG_LFINITO = 4, ALG_PROSHI = 5, ALG_FINITO_ADAPTIVE = 6 };
 
 // Row shards reachable from this GPU: shard s holds rows [start[s], start[s+1]) at base[s] (its own HBM, or a peer's
 // HBM mapped through CUDA IPC and read over NVLink).  n = 1: everything is local.
@@ -78,6 +79,11 @@ struct ciao_ctx {
     double *vecs = nullptr;
     double *table = nullptr;
     double *gamma_dev = nullptr;       // [N]
+    // adaptive Finito (Finito_adaptive.jl): per-component {γ_i, f_i(x_i), c_i(x_i), 0}, γ̂ on the device, counters of the last call
+    double *adapt = nullptr, *adapt_scal = nullptr;
+    int64_t *adapt_counters = nullptr;
+    double adapt_alpha = 0, adapt_tol_b = 0;
+    int64_t adapt_backtracks = 0;
     int algo = 0;                      // 1 svrg, 2 saga, 3 finito, 4 lfinito, 5 proshi
     double gamma = 0, hat_gamma = 0;
     int plus = 0, sag = 0;

@@ -21,7 +21,7 @@ __global__ void prep_indices_kernel(const int64_t *raw, int64_t n, int64_t N, in
         int64_t o = v - 1;
         for (int j = 1; j < HAZARD_WINDOW && j <= k; ++j)
             if (raw[k - j] == v) {
-                o |= CIAO_FLAG_HAZARD;
+                o |= CIAO_FLAG_HAZARD | ((int64_t)j << CIAO_HAZ_DIST_SHIFT);  // nearest previous occurrence
                 break;
             }
         out[k] = o;

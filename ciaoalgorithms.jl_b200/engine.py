@@ -155,6 +155,25 @@ class Engine:
         o = i64arr(batch_order)
         check(self.lib.ciao_lfinito_outer(self.h, ptr(o), len(o), int(r)))
 
+    def finito_adaptive_init(self, x0, alpha=0.999, tol_b=1e-9):
+        check(self.lib.ciao_finito_adaptive_init(self.h, ptr(f64arr(x0)), float(alpha), float(tol_b)))
+
+    def finito_adaptive_steps(self, idx, K=None) -> int:
+        """Returns the number of steps completed (< K ⇔ `return nothing`, Finito_adaptive.jl:124-127)."""
+        if isinstance(idx, np.ndarray):
+            idx = i64arr(idx)
+            K = len(idx) if K is None else K
+        done = C.c_int64()
+        check(self.lib.ciao_finito_adaptive_steps(self.h, ptr(idx), int(K), C.byref(done)))
+        return done.value
+
+    def finito_adaptive_get(self, gamma=True, fi_x=False, coef=False):
+        """(γ, f_i(x_i), c_i, γ̂, number of γ reductions); arrays not asked for are None."""
+        outs = [np.empty(self.N) if w else None for w in (gamma, fi_x, coef)]
+        hg, nbt = C.c_double(), C.c_int64()
+        check(self.lib.ciao_finito_adaptive_get(self.h, ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), C.byref(hg), C.byref(nbt)))
+        return outs[0], outs[1], outs[2], hg.value, nbt.value
+
     def proshi_init(self, x0, gamma_N, hat_gamma):
         check(self.lib.ciao_proshi_init(self.h, ptr(f64arr(x0)), ptr(f64arr(gamma_N)), float(hat_gamma)))
 

@@ -13,6 +13,7 @@ Reference call sites:
   rand(1:iter.N)                        SAGA_basic.jl:55
   sample(1:N, batch, replace=false)     Finito_basic.jl:97, ProShI_basic.jl:98
   randperm(d)                           Finito_basic.jl:102, Finito_LFinito.jl:89, ProShI_basic.jl:103
+  rand(1:N), randperm(N)                Finito_adaptive.jl:108, 113
 """
 from __future__ import annotations
 
@@ -90,6 +91,37 @@ class BatchSweeper:
 
     def take(self, k: int):
         return [self.next() for _ in range(k)]
+
+
+class AdaptiveSweeper:
+    """Index selection of Finito_adaptive.jl:107-119 (single indices, no batches).
+
+    sweeping 1: ``rand(1:N)``;  sweeping 2: ``idxr = mod(idxr, N) + 1`` from ``idxr = 0`` — starts at 1 (unlike the
+    basic variant);  sweeping 3: natural order for the first pass (``ind = 1:N``, ``idx = 0``), then ``randperm(N)``.
+    """
+
+    def __init__(self, N: int, sweeping: int, rng: HostRNG):
+        assert sweeping in (1, 2, 3)
+        self.N, self.sweeping, self.rng = N, sweeping, rng
+        self.idxr, self.idx = 0, 0                       # Finito_adaptive.jl:54-55
+        self.ind = np.arange(1, N + 1, dtype=np.int64)   # :53
+
+    def next(self) -> int:
+        if self.sweeping == 1:
+            self.idxr = self.rng.rand_range(self.N)
+        elif self.sweeping == 2:
+            self.idxr = self.idxr % self.N + 1
+        else:
+            if self.idx == self.N:
+                self.ind = self.rng.randperm(self.N)
+                self.idx = 1
+            else:
+                self.idx += 1
+            self.idxr = int(self.ind[self.idx - 1])
+        return self.idxr
+
+    def take(self, k: int) -> np.ndarray:
+        return np.array([self.next() for _ in range(k)], dtype=np.int64)
 
 
 class LFinitoSweeper:

@@ -26,7 +26,7 @@ import numpy as np
 from . import _lib as L
 from . import operators as ops
 from .engine import Engine
-from .sampling import BatchSweeper, HostRNG, LFinitoSweeper, csr, n_batches
+from .sampling import AdaptiveSweeper, BatchSweeper, HostRNG, LFinitoSweeper, csr, n_batches
 
 GLOBAL_RNG = HostRNG(0)   # the reference draws from Julia's global RNG
 
@@ -299,6 +299,68 @@ class FINITO_LFinito_iterable(FINITO_basic_iterable):
             state.engine.lfinito_outer(state.sweeper.next(), self.batch)       # :78-103
 
 
+class FINITO_adaptive_state(_State):
+    """Finito_adaptive.jl:13-31.  γ and hat_γ change on the device during the linesearch: they are read back on access.
+    ∇f is held as the scalars c_i (∇f_i(x_i) = c_i·a_i for the row models the engine supports)."""
+    _vecs = {"z": L.VEC_Z, "av": L.VEC_AV}
+
+    def __init__(self, engine, sweeper):
+        super().__init__(engine)
+        self.sweeper = sweeper
+
+    @property
+    def γ(self):
+        return self.engine.finito_adaptive_get()[0]
+
+    gamma = γ
+
+    @property
+    def hat_γ(self):
+        return self.engine.finito_adaptive_get(gamma=False)[3]
+
+    hat_gamma = hat_γ
+
+    @property
+    def fi_x(self):
+        return self.engine.finito_adaptive_get(gamma=False, fi_x=True)[1]
+
+    @property
+    def backtracks(self):
+        return self.engine.finito_adaptive_get(gamma=False)[4]
+
+    @property
+    def s(self):
+        return self.engine.get_table_rows()
+
+
+class FINITO_adaptive_iterable:
+    """Finito_adaptive.jl:1-11; `tol` is carried but unused by the reference's iterate as well."""
+
+    def __init__(self, F, g, x0, N, L_, tol, tol_b, sweeping, alpha, rng=None, device=0):
+        self.F, self.g, self.x0, self.N, self.L, self.tol, self.tol_b = F, g, x0, N, L_, tol, tol_b
+        self.sweeping, self.α, self.rng, self.device = sweeping, alpha, rng, device
+
+    def _init(self):
+        e = _setup_engine(self.F, self.g, self.N, self.device)
+        e.finito_adaptive_init(self.x0, self.α, self.tol_b)                    # :59-99
+        return FINITO_adaptive_state(e, AdaptiveSweeper(self.N, self.sweeping, self.rng or GLOBAL_RNG))
+
+    def steps(self, state, k):
+        """k steps in one persistent-kernel call; returns the number completed (the linesearch may end the iteration)."""
+        done = state.engine.finito_adaptive_steps(state.sweeper.take(k))       # :101-160
+        if done < k:
+            warnings.warn("parameter `γ` became too small")                    # :125
+        return done
+
+    def __iter__(self):
+        state = self._init()
+        yield state
+        while True:
+            if self.steps(state, 1) < 1:
+                return                                                         # `return nothing`
+            yield state
+
+
 class Finito:
     def __init__(self, gamma=None, sweeping=1, LFinito=False, adaptive=False, minibatch=(False, 1), maxit=10000,
                  verbose=False, freq=10000, alpha=0.999, tol=1e-8, tol_b=1e-9):
@@ -311,7 +373,7 @@ class Finito:
         if self.LFinito:                                                       # Finito.jl:80-116
             cls = FINITO_LFinito_iterable
         elif self.adaptive:
-            raise ops.UnsupportedOperator("adaptive Finito (Finito_adaptive.jl) is outside the engine's scope (SURVEY.md §8f)")
+            return FINITO_adaptive_iterable(F, g, x0, N, L, self.tol, self.tol_b, self.sweeping, self.α, rng, device)
         else:
             cls = FINITO_basic_iterable
         return cls(F, g, x0, N, L, self.γ, self.sweeping, self.minibatch[1], self.α, rng, device)
@@ -393,7 +455,10 @@ def _drive(solver, iterable, maxit, disp_field):
         it = 1
         while it < maxit:
             nxt = min(maxit, (it // solver.freq + 1) * solver.freq) if solver.verbose else maxit
-            iterable.steps(state, nxt - it)
+            done = iterable.steps(state, nxt - it)
+            if done is not None and done < nxt - it:                            # the iterator returned `nothing` (adaptive Finito)
+                it += done
+                break
             it = nxt
             if solver.verbose and it % solver.freq == 0:
                 print("%5d | %.3e  " % (it, disp_field(state)))

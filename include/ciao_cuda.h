@@ -142,6 +142,18 @@ int ciao_lfinito_init(ciao_ctx *ctx, const double *x0, const double *gamma_N, do
 /* one outer iteration (:78-103): batch_order = state.inds (1-based), static batches of r rows */
 int ciao_lfinito_outer(ciao_ctx *ctx, const int64_t *batch_order, int64_t n_batches, int64_t r);
 
+/* ---- Finito adaptive  (Finito_adaptive.jl) ----------------------------------- */
+/* :59-99 — tables x_i = x0, ∇f_i(x0) (kept as the scalar c_i: ∇f_i = c_i·a_i for row models), f_i(x0);
+ * γ_i = α / (‖∇f_i(x0+1) − ∇f_i(x0)‖ / (√d·N)); γ̂, av, z.  CIAO_ERR_UNSUPPORTED if some ∇f_i(x0+1) == ∇f_i(x0)
+ * (the reference then draws random perturbations from the global RNG, :75-81). */
+int ciao_finito_adaptive_init(ciao_ctx *ctx, const double *x0, double alpha, double tol_b);
+/* :101-160, K single-index steps with the backtracking linesearch on γ_i; *steps_done < K ⇔ the reference's
+ * `return nothing` (γ_i < tol_b/N, :124-127) at step *steps_done + 1 */
+int ciao_finito_adaptive_steps(ciao_ctx *ctx, const int64_t *idx, int64_t K, int64_t *steps_done);
+/* state.γ, state.fi_x, c_i (N entries each, any may be NULL), state.hat_γ, number of 0.8-reductions so far */
+int ciao_finito_adaptive_get(ciao_ctx *ctx, double *gamma_N, double *fi_x_N, double *coef_N, double *hat_gamma,
+                             int64_t *backtracks);
+
 /* ---- ProShI  (ProShI_basic.jl) --------------------------------------------- */
 int ciao_proshi_init(ciao_ctx *ctx, const double *x0, const double *gamma_N, double hat_gamma);  /* :76-86 */
 int ciao_proshi_steps(ciao_ctx *ctx, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches); /* :111-123 */

@@ -12,6 +12,7 @@
  *   src/algorithms/SAGA_SAG/SAGA_basic.jl:26-68
  *   src/algorithms/Finito/Finito_basic.jl:44-121
  *   src/algorithms/Finito/Finito_LFinito.jl:40-103
+ *   src/algorithms/Finito/Finito_adaptive.jl:59-160
  *   src/algorithms/ProShI/ProShI_basic.jl:44-132
  * together with the slice of the un-vendored dependency ProximalOperators.jl
  * 0.14 (Project.toml:10,16) those loops call: gradient!/prox! of
@@ -351,6 +352,101 @@ void orc_finito_steps(const orc_problem *p, const double *gamma, double hat_gamm
         orc_prox(p, z, av, hat_gamma);                                          /* :118 */
     }
     free(g);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Finito adaptive   (Finito_adaptive.jl)                                     */
+/* ------------------------------------------------------------------------ */
+
+/* LinearAlgebra.norm of a d-vector (2-norm; BLAS nrm2 in the reference, restated as sqrt of the left-to-right
+ * sum of squares — the inputs here are far from over/underflow) */
+static double orc_norm2(const double *v, int64_t d) {
+    double s = 0.0;
+    for (int64_t k = 0; k < d; ++k) s += v[k] * v[k];
+    return sqrt(s);
+}
+
+/* Finito_adaptive.jl:59-99.  Tables: s (N×d, x_i), gf (N×d, ∇f_i(x_i)), fi_x (N), gamma (N, out).
+ * Returns 0, or −1 when ∇f_i(x0 + 1) == ∇f_i(x0) for some i: the reference then draws random perturbations
+ * (:75-81, global RNG) — unsupported here as in the engine. */
+int orc_finito_adaptive_init(const orc_problem *p, const double *x0, double alpha, double *s, double *gf,
+                             double *fi_x, double *gamma, double *hat_gamma, double *av, double *z) {
+    const int64_t d = p->d, N = p->N;
+    double *xeps = (double *)malloc((size_t)d * sizeof(double));
+    double *ge = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t i = 0; i < N; ++i) {                                            /* :65-68 */
+        fi_x[i] = orc_gradient(p, i, x0, gf + i * d);
+        memcpy(s + i * d, x0, (size_t)d * sizeof(double));
+    }
+    for (int64_t k = 0; k < d; ++k) xeps[k] = x0[k] + 1.0;                       /* :73 */
+    for (int64_t i = 0; i < N; ++i) {                                            /* :71-87 */
+        orc_gradient(p, i, xeps, ge);
+        for (int64_t k = 0; k < d; ++k) ge[k] -= gf[i * d + k];
+        double nmg = orc_norm2(ge, d);                                           /* :75 */
+        if (nmg < 2.220446049250313e-16) { free(xeps); free(ge); return -1; }    /* :77 eps(R) */
+        double L_int = nmg / (1 * sqrt((double)d));                              /* :84, t = 1 */
+        L_int /= (double)N;                                                      /* :85 */
+        gamma[i] = alpha / L_int;                                                /* :86 */
+    }
+    *hat_gamma = 1 / orc_pairwise_scalar(gamma, 0, N, 1);                        /* :89 */
+    double *sg = (double *)malloc((size_t)d * sizeof(double));
+    orc_pairwise_sum(s, d, d, 0, N, gamma, av);                                  /* sum(s ./ γ) */
+    orc_pairwise_sum(gf, d, d, 0, N, NULL, sg);                                  /* sum(∇f) */
+    for (int64_t k = 0; k < d; ++k) av[k] = *hat_gamma * (av[k] - sg[k] / (double)N);  /* :90 */
+    orc_prox(p, z, av, *hat_gamma);                                              /* :91 */
+    free(xeps); free(ge); free(sg);
+    return 0;
+}
+
+/* Finito_adaptive.jl:101-160, K steps on the given (1-based) indices (selection :107-119 is the caller's).
+ * Returns the number of steps completed: < K when γ_i fell below tol_b/N (:125-128, `return nothing`). */
+int64_t orc_finito_adaptive_steps(const orc_problem *p, double alpha, double tol_b, const int64_t *idx1, int64_t K,
+                                  double *s, double *gf, double *fi_x, double *gamma, double *hat_gamma,
+                                  double *av, double *z, int64_t *n_backtracks) {
+    const int64_t d = p->d;
+    const double N = (double)p->N;
+    double *res = (double *)malloc((size_t)d * sizeof(double));
+    double *tmp = (double *)malloc((size_t)d * sizeof(double));
+    double hg = *hat_gamma;
+    int64_t done = 0, nbt = 0;
+    for (int64_t t = 0; t < K; ++t) {
+        const int64_t i = idx1[t] - 1;
+        double *si = s + i * d, *gi = gf + i * d;
+        for (int64_t k = 0; k < d; ++k) res[k] = z[k] - si[k];                   /* :121 */
+        int stop = 0;
+        for (;;) {                                                               /* :123-147 */
+            if (gamma[i] < tol_b / N) { stop = 1; break; }                       /* :124-127 */
+            double fi_z = orc_gradient(p, i, z, tmp);                            /* :128 (value only) */
+            double nr = orc_norm2(res, d);
+            double fi_model = fi_x[i] + orc_dot(gi, res, d) + (0.5 * N * alpha / gamma[i]) * (nr * nr);  /* :129-132 */
+            double tol = 10 * 2.220446049250313e-16 * (1 + fabs(fi_z));          /* :133 */
+            if (fi_z <= fi_model + tol) break;                                   /* :134 */
+            double gamma_b = gamma[i];                                           /* :136 */
+            gamma[i] *= 0.8;                                                     /* :137 */
+            for (int64_t k = 0; k < d; ++k) av[k] /= hg;                         /* :139 */
+            for (int64_t k = 0; k < d; ++k) av[k] += si[k] / gamma[i];           /* :140 */
+            for (int64_t k = 0; k < d; ++k) av[k] -= si[k] / gamma_b;            /* :141 */
+            hg = 1 / (1 / hg + 1 / gamma[i] - 1 / gamma_b);                      /* :142 */
+            for (int64_t k = 0; k < d; ++k) av[k] *= hg;                         /* :143 */
+            orc_prox(p, z, av, hg);                                              /* :144 */
+            for (int64_t k = 0; k < d; ++k) res[k] = z[k] - si[k];               /* :145 */
+            ++nbt;
+        }
+        if (stop) break;
+        double r = hg / gamma[i];
+        for (int64_t k = 0; k < d; ++k) av[k] += r * (z[k] - si[k]);             /* :149 */
+        memcpy(si, z, (size_t)d * sizeof(double));                               /* :150 */
+        double c = hg / N;
+        for (int64_t k = 0; k < d; ++k) av[k] += c * gi[k];                      /* :151 */
+        fi_x[i] = orc_gradient(p, i, z, gi);                                     /* :152 */
+        for (int64_t k = 0; k < d; ++k) av[k] -= c * gi[k];                      /* :153 */
+        orc_prox(p, z, av, hg);                                                  /* :154 */
+        ++done;
+    }
+    *hat_gamma = hg;
+    if (n_backtracks) *n_backtracks = nbt;
+    free(res); free(tmp);
+    return done;
 }
 
 /* ------------------------------------------------------------------------ */

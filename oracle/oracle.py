@@ -215,6 +215,40 @@ class FinitoState:
         return self.z
 
 
+class FinitoAdaptiveState:
+    """Finito_adaptive.jl:13-57 + :59-160 (index selection is the caller's).  Tables s (x_i) and gf (∇f_i(x_i))."""
+
+    def __init__(self, prob: Problem, x0, alpha=0.999, tol_b=1e-9):
+        self.prob, self.alpha, self.tol_b = prob, float(alpha), float(tol_b)
+        N, d = prob.N, prob.d
+        self.s, self.gf = np.empty((N, d)), np.empty((N, d))
+        self.fi_x, self.gamma = np.empty(N), np.empty(N)
+        self.av, self.z = np.empty(d), np.empty(d)
+        hg = C.c_double()
+        lib().orc_finito_adaptive_init.restype = C.c_int
+        rc = lib().orc_finito_adaptive_init(prob.ref, _d(_f64(x0)), C.c_double(self.alpha), _d(self.s), _d(self.gf),
+                                            _d(self.fi_x), _d(self.gamma), C.byref(hg), _d(self.av), _d(self.z))
+        if rc != 0:
+            raise ValueError("∇f_i(x0 + 1) == ∇f_i(x0): the reference's random fallback (Finito_adaptive.jl:75-81) is not restated")
+        self.hat_gamma = hg.value
+        self.backtracks = 0
+
+    def steps(self, idx1):
+        """Returns the number of steps completed (< len(idx1) ⇔ the reference's `return nothing`, :125-128)."""
+        idx = _i64(idx1)
+        hg, nbt = C.c_double(self.hat_gamma), C.c_int64()
+        lib().orc_finito_adaptive_steps.restype = C.c_int64
+        done = lib().orc_finito_adaptive_steps(self.prob.ref, C.c_double(self.alpha), C.c_double(self.tol_b), _i(idx),
+                                               C.c_int64(len(idx)), _d(self.s), _d(self.gf), _d(self.fi_x), _d(self.gamma),
+                                               C.byref(hg), _d(self.av), _d(self.z), C.byref(nbt))
+        self.hat_gamma = hg.value
+        self.backtracks += nbt.value
+        return int(done)
+
+    def solution(self):
+        return self.z
+
+
 class LFinitoState:
     """Finito_LFinito.jl:13-24 + :40-103."""
 

@@ -13,7 +13,7 @@ import fixtures
 from oracle import oracle as orc
 from ciaoalgorithms_jl_b200 import _lib as L
 from ciaoalgorithms_jl_b200.engine import CiaoError, Engine
-from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, LFinitoSweeper, csr
+from ciaoalgorithms_jl_b200.sampling import AdaptiveSweeper, BatchSweeper, HostRNG, LFinitoSweeper, csr
 
 pytestmark = pytest.mark.gpu
 
@@ -239,6 +239,58 @@ def test_finito_steps(kind, N, d, sweeping, batch, table_path, monkeypatch):
     assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
     assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
     assert rel(e.get_table_rows(), ref.s) < 1e-9
+    e.close()
+
+
+# Finito adaptive (Finito_adaptive.jl): same linesearch decisions as the oracle, step for step
+@pytest.mark.parametrize("kind,N,d", [(orc.LOSS_LS, 250, 64), (orc.LOSS_LS, 300, 1024), (orc.LOSS_LS, 200, 4096), (orc.LOSS_LOGISTIC, 401, 1024),
+                                      (orc.LOSS_LS, 9, 5)])
+@pytest.mark.parametrize("sweeping", [1, 2, 3])
+def test_finito_adaptive_steps(kind, N, d, sweeping):
+    p, e = make_rows(kind, N, d, 0xAD + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
+    x0 = np.full(d, 0.1)
+    ref = orc.FinitoAdaptiveState(p, x0, alpha=0.999, tol_b=1e-9)
+    e.finito_adaptive_init(x0, 0.999, 1e-9)
+    gam, fi_x, coef, hat, _ = e.finito_adaptive_get(True, True, True)
+    assert rel(gam, ref.gamma) < 1e-12 and rel(fi_x, ref.fi_x) < 1e-12
+    assert abs(hat - ref.hat_gamma) <= 1e-12 * ref.hat_gamma
+    assert rel(e.get_table_rows(), ref.s) == 0.0
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-10 and rel(e.get_vec(L.VEC_Z), ref.z) < 1e-10
+    idx = AdaptiveSweeper(N, sweeping, HostRNG(4)).take(max(2 * N + 7, 80))
+    idx[20:23] = idx[19]            # immediate repeats and repeats inside the prefetch window: scalar history + table re-read
+    idx[40] = idx[33]
+    idx[60] = idx[49]
+    K1 = N // 2 + 3
+    assert ref.steps(idx) == len(idx)
+    assert e.finito_adaptive_steps(idx[:K1]) == K1               # two calls: state (γ, γ̂, tables) carries over
+    assert e.finito_adaptive_steps(idx[K1:]) == len(idx) - K1
+    gam, fi_x, coef, hat, nbt = e.finito_adaptive_get(True, True, True)
+    assert nbt == ref.backtracks                                 # identical linesearch decisions
+    assert rel(gam, ref.gamma) < 1e-12                           # γ_i only ever changes by factors 0.8: same count per component
+    assert abs(hat - ref.hat_gamma) <= 1e-12 * ref.hat_gamma
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    assert rel(e.get_table_rows(), ref.s) < 1e-9
+    assert rel(fi_x, ref.fi_x) < 1e-9
+    e.close()
+
+
+def test_finito_adaptive_stops_when_gamma_too_small():
+    N, d = 64, 128
+    p, e = make_rows(orc.LOSS_LS, N, d, 0xAD0, lam_reg=0.05)
+    x0 = np.full(d, 0.1)
+    ref = orc.FinitoAdaptiveState(p, x0, alpha=0.999, tol_b=1e-9)
+    thr_gamma = np.sort(ref.gamma)[N // 2]                       # about half of the components start below tol_b/N
+    tol_b = float(thr_gamma) * N
+    ref = orc.FinitoAdaptiveState(p, x0, alpha=0.999, tol_b=tol_b)
+    e.finito_adaptive_init(x0, 0.999, tol_b)
+    idx = AdaptiveSweeper(N, 1, HostRNG(7)).take(200)
+    done_ref = ref.steps(idx)
+    done = e.finito_adaptive_steps(idx)
+    assert done == done_ref < 200                                # `return nothing` at the same step (Finito_adaptive.jl:124-127)
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+    with pytest.raises(CiaoError):
+        e.finito_adaptive_steps(np.array([0, 1], dtype=np.int64))  # out-of-range index is rejected before any update
     e.close()
 
 

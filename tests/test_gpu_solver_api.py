@@ -54,6 +54,26 @@ def test_lasso_lfinito_and_minibatch(sweeping, batch, lfinito):                 
     assert fx["cost"](x) - fx["f_star"] < TOL
 
 
+@pytest.mark.parametrize("sweeping", [1, 2, 3])
+def test_lasso_adaptive_finito(sweeping):                                       # :88-98
+    fx, F, g = lasso_problem()
+    solver = S.Finito(maxit=1000, tol=1e-5, sweeping=sweeping, adaptive=True)
+    x, it = solver(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"], rng=HostRNG(1))
+    assert fx["cost"](x) - fx["f_star"] < TOL and it == 1000 and x.dtype == np.float64
+
+
+def test_lasso_adaptive_iterator_and_early_end():                               # :143-157 with adaptive = true; Finito_adaptive.jl:124-127
+    fx, F, g = lasso_problem()
+    it = S.iterator(S.Finito(sweeping=2, adaptive=True), fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"], rng=HostRNG(1))
+    assert it.x0 is fx["x0"]
+    for state in itertools.islice(it, 3):
+        assert S.solution(state) is state.z and len(state.γ) == fx["N"] and state.hat_γ > 0
+    # γ_i < tol_b/N at the first step: the iterator yields its initial state and ends, the solver stops at iteration 1
+    with pytest.warns(UserWarning, match="became too small"):
+        x, n = S.Finito(maxit=50, adaptive=True, tol_b=1e300)(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"], rng=HostRNG(1))
+    assert n == 1
+
+
 def test_lasso_scalar_gamma_and_scalar_L():                                     # :128-140
     fx, F, g = lasso_problem()
     N = fx["N"]
@@ -174,4 +194,4 @@ def test_unsupported_operator_is_rejected_before_any_device_call():
     with pytest.raises(ops.UnsupportedOperator):
         S.SAGA(gamma=0.1)(fx["x0"], F=[object()] * fx["N"], g=g, N=fx["N"])
     with pytest.raises(ops.UnsupportedOperator):
-        S.Finito(adaptive=True)(fx["x0"], F=F, g=g, L=fx["L"], N=fx["N"])
+        S.Finito(adaptive=True)(fx["x0"], F=F, g=object(), L=fx["L"], N=fx["N"])

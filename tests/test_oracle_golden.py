@@ -10,7 +10,7 @@ import pytest
 
 import fixtures
 from oracle import oracle as orc
-from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, LFinitoSweeper
+from ciaoalgorithms_jl_b200.sampling import AdaptiveSweeper, BatchSweeper, HostRNG, LFinitoSweeper
 
 TOL = 1e-4
 
@@ -49,6 +49,12 @@ def run_lfinito(p, x0, L, N, maxit, sweeping, batch=1, alpha=0.999, seed=1):
     for _ in range(maxit - 1):
         st.outer(sw.next())
     return st.solution()
+
+
+def run_finito_adaptive(p, x0, N, maxit, sweeping, alpha=0.999, tol_b=1e-9, seed=1):
+    st = orc.FinitoAdaptiveState(p, x0, alpha, tol_b)                         # Finito_adaptive.jl:59-99
+    st.steps(AdaptiveSweeper(N, sweeping, HostRNG(seed)).take(maxit - 1))     # :101-160
+    return st.solution(), st
 
 
 def run_svrg(p, x0, gamma, N, maxit, m=None, plus=False, seed=1):
@@ -205,6 +211,9 @@ def test_lasso_all_solvers(seed):
         assert cost(run_finito(p, x0, L, N, 1000, sweeping)) - fs < TOL
     for sweeping in (2, 3):                                                   # :78-85
         assert cost(run_lfinito(p, x0, L, N, 1000, sweeping)) - fs < TOL
+    for sweeping in (1, 2, 3):                                                # :88-98 adaptive finito
+        x, st = run_finito_adaptive(p, x0, N, 1000, sweeping)
+        assert cost(x) - fs < TOL
     for sweeping, batch in [(1, 2), (2, 2), (3, 3)]:                          # :101-111
         assert cost(run_finito(p, x0, L, N, 1000, sweeping, batch)) - fs < TOL
     for sweeping, batch in [(2, 1), (2, 2), (3, 3)]:                          # :114-125
@@ -239,3 +248,17 @@ def test_generator_is_deterministic_and_sane():
     assert set(np.unique(y)) <= {-1.0, 1.0} and np.all(A[:, -1] == 1.0)
     Q, none = orc.gen_rows(orc.SYN_SHARING, 64, 9, 0, 100)
     assert none is None and Q.min() > -1 and Q.max() < 10
+
+
+def test_adaptive_finito_backtracks_and_stops():
+    """Finito_adaptive.jl: the linesearch shrinks γ_i by 0.8 until the quadratic model holds (:134-145) and the iteration
+    ends (`return nothing`) when γ_i < tol_b/N (:124-127).  (The reference tests the adaptive variant on the Lasso only,
+    test_lasso.jl:88-98; that criterion is part of test_lasso_all_solvers above.)"""
+    fxl, pl = _lasso_problem(0)
+    st = orc.FinitoAdaptiveState(pl, fxl["x0"], alpha=0.999, tol_b=1e-9)
+    g0 = st.gamma.copy()
+    done = st.steps(AdaptiveSweeper(fxl["N"], 2, HostRNG(1)).take(200))
+    assert done == 200 and st.backtracks > 0 and np.all(st.gamma <= g0) and np.any(st.gamma < g0)
+    assert abs(st.hat_gamma - 1 / np.sum(1 / st.gamma)) <= 1e-12 * st.hat_gamma   # :142 keeps γ̂ = 1/Σ(1/γ_i)
+    st2 = orc.FinitoAdaptiveState(pl, fxl["x0"], alpha=0.999, tol_b=1e300)        # γ_i < tol_b/N at once
+    assert st2.steps(np.array([1, 2, 3], dtype=np.int64)) == 0
