@@ -339,8 +339,68 @@ function solution(state::Table_state)
     return getvec!(state.ctx, CIAO_VEC_Z, state.z)                        # Finito_basic.jl:123, Finito_LFinito.jl:105
 end
 
+# ---- adaptive Finito (Finito_adaptive.jl): linesearch on γ_i inside the persistent kernel ------------------------------
+struct FINITO_adaptive_iterable{R,Tx,Tf,Tg}
+    F::Tf; g::Tg; x0::Tx; N::Int; L; tol::R; tol_b::R; sweeping::Int8; α::R
+end
+mutable struct FINITO_adaptive_state{R}
+    ctx::Ctx; z::Vector{Float64}; γ::Vector{Float64}; hat_γ::R
+    ind::Vector{Int}; idx::Int; idxr::Int            # Finito_adaptive.jl:53-55
+end
+
+function refresh!(state::FINITO_adaptive_state)       # γ and hat_γ change on the device during the linesearch
+    hg = Ref{Float64}(0); nb = Ref{Int64}(0); γ = state.γ
+    GC.@preserve γ check(ccall((:ciao_finito_adaptive_get, libciao), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Int64}), state.ctx.h, γ, C_NULL, C_NULL, hg, nb))
+    state.hat_γ = hg[]
+    return state
+end
+
+function Base.iterate(iter::FINITO_adaptive_iterable{R}) where {R}
+    c = set_problem!(Ctx(), iter.F, iter.g, iter.N)
+    x0 = Vector{Float64}(iter.x0)
+    GC.@preserve x0 check(ccall((:ciao_finito_adaptive_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64),
+                                c.h, x0, Float64(iter.α), Float64(iter.tol_b)))                  # :59-99
+    state = FINITO_adaptive_state{R}(c, zeros(length(x0)), zeros(iter.N), R(0), collect(1:iter.N), 0, 0)
+    return refresh!(state), state
+end
+
+function next_index!(iter::FINITO_adaptive_iterable, state::FINITO_adaptive_state)               # :107-119
+    if iter.sweeping == 1
+        state.idxr = rand(1:iter.N)
+    elseif iter.sweeping == 2
+        state.idxr = mod(state.idxr, iter.N) + 1
+    else
+        if state.idx == iter.N
+            state.ind = randperm(iter.N); state.idx = 1
+        else
+            state.idx += 1
+        end
+        state.idxr = state.ind[state.idx]
+    end
+    return state.idxr
+end
+
+# k steps in one call; returns the number completed (< k ⇔ the reference's `return nothing`, :124-127)
+function steps!(iter::FINITO_adaptive_iterable, state::FINITO_adaptive_state, k::Int)
+    idx = Int64[next_index!(iter, state) for _ = 1:k]
+    done = Ref{Int64}(0)
+    GC.@preserve idx check(ccall((:ciao_finito_adaptive_steps, libciao), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Ref{Int64}),
+                                 state.ctx.h, idx, k, done))
+    refresh!(state)
+    done[] < k && @warn "parameter `γ` became too small ($(state.γ))"
+    return Int(done[])
+end
+function Base.iterate(iter::FINITO_adaptive_iterable{R}, state::FINITO_adaptive_state{R}) where {R}
+    steps!(iter, state, 1) < 1 && return nothing
+    return state, state
+end
+solution(state::FINITO_adaptive_state) = getvec!(state.ctx, CIAO_VEC_Z, state.z)                  # :162
+
 function table_iterable(solver::Finito{R}, x0, F, g, L, N) where {R}
-    solver.adaptive && !solver.LFinito && error("adaptive Finito is outside the engine's scope; use CIAOAlgorithms.jl")
+    if solver.adaptive && !solver.LFinito                                                        # Finito.jl:92-103
+        return FINITO_adaptive_iterable{R,typeof(x0),typeof(F),typeof(g)}(F, g, x0, N, L, solver.tol, solver.tol_b, solver.sweeping, solver.α)
+    end
     kind = solver.LFinito ? :lfinito : :finito
     Table_iterable{R,typeof(x0),typeof(F),typeof(g)}(kind, F, g, x0, N, L, solver.γ, solver.sweeping, solver.minibatch[2], solver.α)
 end
@@ -362,7 +422,12 @@ function drive(solver, iter, maxit::Int, field)
     fused = !(iter isa SVRG_basic_iterable)
     while it < maxit
         nxt = solver.verbose ? min(maxit, (div(it, solver.freq) + 1) * solver.freq) : maxit
-        if fused
+        if iter isa FINITO_adaptive_iterable
+            req = nxt - it
+            done = steps!(iter, state, req)
+            it += done
+            done < req && break                             # the iterator ended (`return nothing`)
+        elseif fused
             steps!(iter, state, nxt - it); it = nxt
         else
             iterate(iter, state); it += 1
