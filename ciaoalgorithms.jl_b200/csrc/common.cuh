@@ -79,6 +79,7 @@ struct ciao_ctx {
     double *vecs = nullptr;
     double *table = nullptr;
     double *gamma_dev = nullptr;       // [N]
+    double *gpair = nullptr;           // ProShI: [N][2] (γ_i, γ_i/N), what one block step needs in 16 bytes
     // adaptive Finito (Finito_adaptive.jl): per-component {γ_i, f_i(x_i), c_i(x_i), 0}, γ̂ on the device, counters of the last call
     double *adapt = nullptr, *adapt_scal = nullptr;
     int64_t *adapt_counters = nullptr;
@@ -174,6 +175,23 @@ __device__ __forceinline__ void tma_load_1d_s(uint32_t smem_dst, const void *gsr
 }
 __device__ __forceinline__ void sts_b64(uint32_t addr, int64_t v) {
     asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+// non-blocking phase test: issued early, its result consumed after independent work (latency ≈ 150 cycles)
+__device__ __forceinline__ uint32_t mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(

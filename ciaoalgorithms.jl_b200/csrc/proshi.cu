@@ -20,7 +20,7 @@ struct ProshiArgs {
     const double *qd, *ql;  // [N][n_pad]
     double *table;          // [N][n_pad]
     const double *gam;      // [N]
-    const double *gam_n;    // [N]  γ_i/N, precomputed (ProShI_basic.jl:116)
+    const double *gpair;    // [N][2]  (γ_i, γ_i/N): the pair a step needs, 16 bytes (γ_i/N precomputed, ProShI_basic.jl:116)
     const int64_t *idx;     // prepared
     int64_t K, N, n_pad;
     double *v_z, *v_av;
@@ -37,239 +37,253 @@ __device__ __forceinline__ double proshi_grad(double q, double c, double s, doub
 }
 
 
-// Batch-1 steps: a true dependency chain per column (z_j → s_ij → av_j → z_j), so the kernel is latency bound and
-// everything that is not on that chain has to stay off it.  Each thread stages the 16-byte slices of (q_i, c_i, s_i)
-// and the scalars (γ_i, γ_i/N) of the block it will need PROSHI_D steps later into ITS OWN shared-memory cells with
-// cp.async, one commit group per step; `cp.async.wait_group D−1` then guarantees exactly the oldest group — a counted
-// in-order pipeline.  (The first version prefetched into registers with ld.global: ptxas tracks all those loads with one
-// scoreboard, so the first use of step k's registers also waited for the load just issued for step k+D — every step paid
-// a full DRAM latency: 0.74 µs/block.)  No barrier, no mbarrier, no reduction, no kernel launch per step; a warp reads the
-// index sequence 32 entries at a time (one coalesced load per 32 steps, prefetched a block ahead) and broadcasts by shuffle.
-constexpr int PROSHI_D = 16;  // steps of prefetch; a staged table slice is stale if the block recurs within D steps → HAZARD flag
-static_assert(PROSHI_D < 32 && (PROSHI_D & (PROSHI_D - 1)) == 0, "ring depth: power of two below the index block of 32");
-static_assert(PROSHI_D <= CIAO_HAZARD_WINDOW - 1, "prep_indices_kernel must flag repeats within the prefetch window");
-constexpr int PROSHI_SLOT_BYTES = 4 * 32 * 16;  // per warp and slot: q | c | s | (γ, γ/N), 16 bytes per lane each
+// Batch-1 steps: a true dependency chain per column (z_j → s_ij → av_j → z_j), so the kernel is latency/issue bound and
+// everything that is not on that chain has to stay off the compute warp.  A CTA owns 32·CPT columns: ONE compute warp keeps
+// z_j, av_j of its columns in registers for the whole call; TWO producer lanes (warps 1 and 2, even and odd steps) TMA-stage
+// the column slices of (q_i, c_i, s_i), the pair (γ_i, γ_i/N) and the index word of the block needed PROSHI_D steps later
+// into a full/empty mbarrier ring.  No reduction, no CTA barrier, no kernel launch per step.
+// History: register prefetch with ld.global ran at 0.74 µs/block (ptxas tracks all those loads with one scoreboard, so the
+// first use of step k's registers also waited for the load just issued for step k+D: one DRAM latency per step); per-thread
+// cp.async groups at 0.30 µs/block (≈ 190 instructions per step on the one warp that also walks the chain); with the staging
+// moved to producer lanes the compute warp issues ≈ 70.
+constexpr int PROSHI_D = 16;  // ring depth; a staged table slice is stale if the block recurs within D + 1 steps → HAZARD flag
+static_assert((PROSHI_D & (PROSHI_D - 1)) == 0 && PROSHI_D + 1 <= CIAO_HAZARD_WINDOW - 1,
+              "prep_indices_kernel must flag repeats within the prefetch window");
 
-__device__ __forceinline__ void cp_async_cg16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_ca8(uint32_t dst, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
+#ifndef PROSHI_NP
+#define PROSHI_NP 2
+#endif
+constexpr int PROSHI_PRODUCERS = PROSHI_NP;  // producer lanes (one warp each), step st is staged by producer st mod NP
 
-__global__ void __launch_bounds__(64) proshi_steps_kernel(const ProshiArgs p) {
+template <int CPT, int REG>
+__global__ void __launch_bounds__(32 * (1 + PROSHI_PRODUCERS)) proshi_steps_kernel(const ProshiArgs p) {
     constexpr int D = PROSHI_D;
-    extern __shared__ __align__(16) unsigned char proshi_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t col_raw = 2 * (blockIdx.x * (int64_t)blockDim.x + threadIdx.x);
-    const bool active = col_raw < p.n_pad;       // inactive lanes of the last warp shadow column 0 and never store
-    const int64_t col = active ? col_raw : 0;
-    double z0 = p.v_z[col], z1 = p.v_z[col + 1], av0 = p.v_av[col], av1 = p.v_av[col + 1];
-    const double lo0 = p.reg.lo_v ? p.reg.lo_v[col] : p.reg.lo_s, lo1 = p.reg.lo_v ? p.reg.lo_v[col + 1] : p.reg.lo_s;
-    const double hi0 = p.reg.hi_v ? p.reg.hi_v[col] : p.reg.hi_s, hi1 = p.reg.hi_v ? p.reg.hi_v[col + 1] : p.reg.hi_s;
+    constexpr int COLS = 32 * CPT;                 // columns per CTA
+    constexpr int SLOT = 3 * COLS + 4;             // doubles: q | c | s | γ, γ/N | index word | pad
+    __shared__ __align__(128) double ring[D * SLOT];
+    __shared__ uint64_t full_bar[D], empty_bar[D];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t col0 = (int64_t)blockIdx.x * COLS;
+    const int64_t ncol = min((int64_t)COLS, p.n_pad - col0);   // columns of this CTA that exist (multiple of 4)
+    const int64_t K = p.K;
+    for (int i = tid; i < D * SLOT; i += blockDim.x) ring[i] = 0.0;
+    if (tid == 0) {
+        for (int s = 0; s < D; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        fence_mbar_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    if (warp >= 1) {
+        // ===================== producer lanes: warp 1 stages the even steps, warp 2 the odd ones =====================
+        if (lane == 0) {
+            const int Ki = (int)K;
+            const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
+            const uint32_t bytes = (uint32_t)ncol * 8;
+            const uint32_t tx = 3 * bytes + 16;
+            for (int st = warp - 1; st < Ki; st += PROSHI_PRODUCERS) {
+                const uint32_t slot = (uint32_t)st & (D - 1);
+                if (st >= D) mbar_wait_s(empty_s + slot * 8, (((uint32_t)st / D) - 1u) & 1u);  // step st − D has left the slot
+                const int64_t pidx = __ldg(p.idx + st);
+                const int64_t i = pidx & CIAO_IDX_MASK;
+                const int64_t off = i * p.n_pad + col0;
+                const uint32_t dst = ring_s + slot * (SLOT * 8), bar = full_s + slot * 8;
+                sts_b64(dst + (3 * COLS + 2) * 8, pidx);  // released by the arrive below
+                mbar_arrive_expect_tx_s(bar, tx);
+                tma_load_1d_s(dst, p.qd + off, bytes, bar);
+                tma_load_1d_s(dst + COLS * 8, p.ql + off, bytes, bar);
+                tma_load_1d_s(dst + 2 * COLS * 8, p.table + off, bytes, bar);
+                tma_load_1d_s(dst + 3 * COLS * 8, p.gpair + 2 * i, 16, bar);
+            }
+        }
+        return;
+    }
+    // ===================== compute warp =====================
+    const int lc = CPT * lane;                      // first local column of this lane
+    const bool active = lc < ncol;
+    const int64_t col = col0 + (active ? lc : 0);
+    double z[CPT], av[CPT], lo[CPT], hi[CPT];
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) {
+        z[e] = active ? p.v_z[col + e] : 0.0;
+        av[e] = active ? p.v_av[col + e] : 0.0;
+        lo[e] = (active && p.reg.lo_v) ? p.reg.lo_v[col + e] : p.reg.lo_s;
+        hi[e] = (active && p.reg.hi_v) ? p.reg.hi_v[col + e] : p.reg.hi_s;
+    }
     const double gl = p.hat_gamma * p.reg.lambda;
     const double rhat = __ddiv_rn(1.0, p.hat_gamma);
-    const int64_t K = p.K;
-    const uint32_t cell0 = smem_u32(proshi_smem) + (uint32_t)warp * (D * PROSHI_SLOT_BYTES) + (uint32_t)lane * 16;
-    const unsigned char *cellp = proshi_smem + (size_t)warp * (D * PROSHI_SLOT_BYTES) + (size_t)lane * 16;
-
-    auto issue = [&](int slot, int64_t pidx) {
-        const int64_t i = pidx & CIAO_IDX_MASK;
-        const uint32_t cb = cell0 + (uint32_t)slot * PROSHI_SLOT_BYTES;
-        cp_async_cg16(cb, p.qd + i * p.n_pad + col);
-        cp_async_cg16(cb + 512, p.ql + i * p.n_pad + col);
-        cp_async_cg16(cb + 1024, p.table + i * p.n_pad + col);
-        cp_async_ca8(cb + 1536, p.gam + i);
-        cp_async_ca8(cb + 1544, p.gam_n + i);
-    };
     struct Blk {
-        double2 q, c, s;
+        double q[CPT], c[CPT], s[CPT];
         double gi, gn;
         int64_t ik;
     };
-    auto take = [&](int slot, int64_t pidx, Blk &b) {
-        const unsigned char *cb = cellp + (size_t)slot * PROSHI_SLOT_BYTES;
-        b.q = *reinterpret_cast<const double2 *>(cb);
-        b.c = *reinterpret_cast<const double2 *>(cb + 512);
-        b.s = *reinterpret_cast<const double2 *>(cb + 1024);
-        const double2 g = *reinterpret_cast<const double2 *>(cb + 1536);
-        b.gi = g.x;
-        b.gn = g.y;
-        b.ik = pidx;
+    // pulls the staged block of `step` into registers and hands the slot back to the producers
+    auto take = [&](int64_t step, Blk &b) {
+        const int slot = (int)(step & (D - 1));
+        const double *sp = ring + slot * SLOT;
+        if (CPT == 2) {
+            const double2 vq = *reinterpret_cast<const double2 *>(sp + lc), vc = *reinterpret_cast<const double2 *>(sp + COLS + lc),
+                          vs = *reinterpret_cast<const double2 *>(sp + 2 * COLS + lc);
+            b.q[0] = vq.x; b.q[CPT - 1] = vq.y; b.c[0] = vc.x; b.c[CPT - 1] = vc.y; b.s[0] = vs.x; b.s[CPT - 1] = vs.y;
+        } else {
+            b.q[0] = sp[lc]; b.c[0] = sp[COLS + lc]; b.s[0] = sp[2 * COLS + lc];
+        }
+        const double2 g2 = *reinterpret_cast<const double2 *>(sp + 3 * COLS);
+        b.gi = g2.x; b.gn = g2.y;
+        b.ik = *reinterpret_cast<const int64_t *>(sp + 3 * COLS + 2);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[slot]);
     };
-
-    // index blocks of 32 steps: iv_i covers the step being staged (k + D), iv_prev the block before it, iv_n the next one
-    int64_t iv_i = (lane < K) ? __ldg(p.idx + lane) : 0;
-    int64_t iv_n = (32 + lane < K) ? __ldg(p.idx + 32 + lane) : 0;
-    int64_t iv_prev = iv_i;
-#pragma unroll
-    for (int s = 0; s < D; ++s) {
-        const int64_t pidx = __shfl_sync(0xffffffffu, iv_i, s);
-        if (s < K) issue(s, pidx);
-        cp_async_commit();
-    }
     Blk cur;
-    cp_async_wait<D - 1>();
-    take(0, __shfl_sync(0xffffffffu, iv_i, 0), cur);
-
-    for (int64_t k = 0; k < K; ++k) {
-        double2 *srow = reinterpret_cast<double2 *>(p.table + (cur.ik & CIAO_IDX_MASK) * p.n_pad + col);
-        double2 s = cur.s;
-        if (cur.ik & CIAO_FLAG_HAZARD) s = __ldcg(srow);  // rewritten after its copy was issued: re-read behind our own store
-        const double gi = cur.gi;
-        const double cneg = -cur.gn;
-        // ProShI_basic.jl:113-119
-        av0 = __dsub_rn(av0, s.x);
-        av1 = __dsub_rn(av1, s.y);
-        const double x0 = __dadd_rn(s.x, __dmul_rn(gi, z0)), x1 = __dadd_rn(s.y, __dmul_rn(gi, z1));
-        double t0 = __dmul_rn(proshi_grad(cur.q.x, cur.c.x, x0, p.box_lo, p.box_hi, p.eta), cneg);
-        double t1 = __dmul_rn(proshi_grad(cur.q.y, cur.c.y, x1, p.box_lo, p.box_hi, p.eta), cneg);
-        t0 = __dadd_rn(t0, x0);
-        t1 = __dadd_rn(t1, x1);
-        av0 = __dadd_rn(av0, t0);
-        av1 = __dadd_rn(av1, t1);
-        if (active) __stcg(srow, make_double2(t0, t1));
-        if (cur.ik & CIAO_FLAG_PROX) {  // :121-123
-            z0 = div_by(__dsub_rn(prox_rt(p.reg.kind, av0, gl, lo0, hi0), av0), p.hat_gamma, rhat);
-            z1 = div_by(__dsub_rn(prox_rt(p.reg.kind, av1, gl, lo1, hi1), av1), p.hat_gamma, rhat);
-        }
-        // stage step k + D into the slot just consumed (issued after this step's store: only repeats inside the window are stale)
-        const int64_t sk = k + D;
-        if ((sk & 31) == 0) {
-            iv_prev = iv_i;
-            iv_i = iv_n;
-            iv_n = (sk + 32 + lane < K) ? __ldg(p.idx + sk + 32 + lane) : 0;
-        }
-        const int64_t pidx_s = __shfl_sync(0xffffffffu, iv_i, (int)(sk & 31));
-        if (sk < K) issue((int)(k & (D - 1)), pidx_s);
-        cp_async_commit();
-        // registers of step k + 1
-        const int64_t k1 = k + 1;
-        const int l1 = (int)(k1 & 31);
-        // iv_i is the index block of step k + D = k1 + D − 1; step k1 lies in the same block iff l1 + D − 1 < 32
-        const int64_t pidx_1 = __shfl_sync(0xffffffffu, (l1 + D - 1 < 32) ? iv_i : iv_prev, l1);
-        cp_async_wait<D - 1>();
-        if (k1 < K) take((int)(k1 & (D - 1)), pidx_1, cur);
+    if (K > 0) {
+        mbar_wait(&full_bar[0], 0);
+        take(0, cur);
     }
-    cp_async_wait<0>();
+    for (int64_t k = 0; k < K; ++k) {
+        // is the next block staged?  asked now, looked at after this step's arithmetic (the test takes ≈ 150 cycles to answer)
+        const int64_t k1 = k + 1;
+        uint64_t *nbar = &full_bar[k1 & (D - 1)];
+        const uint32_t npar = (uint32_t)((k1 / D) & 1);
+        const uint32_t ready = (k1 < K) ? mbar_test(nbar, npar) : 1u;
+        const int64_t ik = cur.ik;
+        double *srow = p.table + (ik & CIAO_IDX_MASK) * p.n_pad + col;
+        double s[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) s[e] = cur.s[e];
+        if (ik & CIAO_FLAG_HAZARD) {  // rewritten after its copy was staged: re-read behind our own store
+#pragma unroll
+            for (int e = 0; e < CPT; ++e) s[e] = __ldcg(srow + e);
+        }
+        const double gi = cur.gi, cneg = -cur.gn;
+        double t[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) {  // ProShI_basic.jl:113-119
+            av[e] = __dsub_rn(av[e], s[e]);
+            const double x = __dadd_rn(s[e], __dmul_rn(gi, z[e]));
+            t[e] = __dadd_rn(__dmul_rn(proshi_grad(cur.q[e], cur.c[e], x, p.box_lo, p.box_hi, p.eta), cneg), x);
+            av[e] = __dadd_rn(av[e], t[e]);
+        }
+        if (active) {
+            if (CPT == 2) __stcg(reinterpret_cast<double2 *>(srow), make_double2(t[0], t[CPT - 1]));
+            else __stcg(srow, t[0]);
+        }
+        if (ik & CIAO_FLAG_PROX) {  // :121-123
+#pragma unroll
+            for (int e = 0; e < CPT; ++e)
+                z[e] = div_by(__dsub_rn(prox_elem<REG>(av[e], gl, lo[e], hi[e]), av[e]), p.hat_gamma, rhat);
+        }
+        if (k1 < K) {
+            if (!ready) mbar_wait(nbar, npar);
+            take(k1, cur);
+        }
+    }
     if (active) {
-        p.v_z[col] = z0; p.v_z[col + 1] = z1;
-        p.v_av[col] = av0; p.v_av[col + 1] = av1;
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) {
+            p.v_z[col + e] = z[e];
+            p.v_av[col + e] = av[e];
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
 // Minibatch path (batch ≥ PROSHI_BATCH_MIN blocks): inside a batch every block uses the same z
 // (ProShI_basic.jl:111-120), so the blocks are independent and av only needs Σ_i (t_i − s_i).  A CTA owns
-// 8 columns (one 64-byte chunk of every row) for the WHOLE call, its threads work through the blocks of
-// a batch in parallel, a fixed-order CTA reduction closes the batch and the dual update of the CTA's own
-// columns follows — columns never interact, so there is no grid-wide synchronisation and the kernel
-// streams the three block arrays at HBM rate.  Bitwise reproducible (fixed thread ↔ block mapping).
+// 8 columns (one 64-byte chunk of every row) for the WHOLE call; FOUR LANES share a block — each loads one 16-byte piece
+// of the chunk from each of the three arrays, so a warp-wide load instruction touches 8 blocks × 2 full sectors (the first
+// version gave every lane its own block: 32 half-used sectors per instruction, 2.3 TB/s).  A fixed-order CTA
+// reduction closes the batch and the dual update of the CTA's own columns follows — columns never interact, so there is
+// no grid-wide synchronisation and the kernel streams the three block arrays.  Bitwise reproducible (fixed thread ↔ block
+// mapping, fixed reduction order).
 constexpr int PROSHI_BATCH_MIN = 64;
-constexpr int PROSHI_BT = 256;  // threads per CTA
-
+// PROSHI_BT threads per CTA = BT/4 block slots × 4 lanes, PROSHI_BU blocks per thread in flight.  Measured at N = 2^18, n = 1024
+// (scripts/proshi_batch_probe.py): batch 4096 → 3.2 TB/s with (256, 4), 4.2 TB/s with (512, 4), 2.7 with (256, 8), 4.0 with
+// (1024, 2); batch 256 → 2.3 TB/s with (256, 4), 2.1 with (512, 4).
+template <int PROSHI_BT, int PROSHI_BU>
 __global__ void __launch_bounds__(PROSHI_BT) proshi_batch_kernel(const ProshiArgs p, const int64_t *ptr, int64_t n_batches) {
-    __shared__ double red[2][PROSHI_BT / 32][8];
+    __shared__ double red[2][PROSHI_BT / 32][4][2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t col = 8 * (int64_t)blockIdx.x;
-    bool cv[4];
-    double z[8], av[8], lo[8], hi[8];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-        cv[h] = col + 2 * h < p.n_pad;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int q = 2 * h + e;
-            const int64_t g = col + q;
-            z[q] = cv[h] ? p.v_z[g] : 0.0;
-            av[q] = cv[h] ? p.v_av[g] : 0.0;
-            lo[q] = (cv[h] && p.reg.lo_v) ? p.reg.lo_v[g] : p.reg.lo_s;
-            hi[q] = (cv[h] && p.reg.hi_v) ? p.reg.hi_v[g] : p.reg.hi_s;
-        }
-    }
+    const int h = tid & 3, rs = tid >> 2;            // piece of the 64-byte chunk, block slot
+    const int64_t col = 8 * (int64_t)blockIdx.x + 2 * h;
+    const bool cv = col < p.n_pad;
+    const int64_t colc = cv ? col : 0;
+    double z0 = cv ? p.v_z[colc] : 0.0, z1 = cv ? p.v_z[colc + 1] : 0.0;
+    double av0 = cv ? p.v_av[colc] : 0.0, av1 = cv ? p.v_av[colc + 1] : 0.0;
+    const double lo0 = (cv && p.reg.lo_v) ? p.reg.lo_v[colc] : p.reg.lo_s, lo1 = (cv && p.reg.lo_v) ? p.reg.lo_v[colc + 1] : p.reg.lo_s;
+    const double hi0 = (cv && p.reg.hi_v) ? p.reg.hi_v[colc] : p.reg.hi_s, hi1 = (cv && p.reg.hi_v) ? p.reg.hi_v[colc + 1] : p.reg.hi_s;
     const double gl = p.hat_gamma * p.reg.lambda;
     const double rhat = __ddiv_rn(1.0, p.hat_gamma);
+    constexpr int SLOTS = PROSHI_BT / 4;
 
     for (int64_t b = 0; b < n_batches; ++b) {
         const int64_t lo_t = ptr[b], hi_t = ptr[b + 1];
-        double ds[8];
+        double ds0 = 0.0, ds1 = 0.0;
+        for (int64_t t = lo_t + rs; t < hi_t; t += (int64_t)PROSHI_BU * SLOTS) {
+            bool act[PROSHI_BU];
+            int64_t off[PROSHI_BU];
+            double gi[PROSHI_BU], cneg[PROSHI_BU];
+            double2 q2[PROSHI_BU], c2[PROSHI_BU], s2[PROSHI_BU];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) ds[q] = 0.0;
-        // two blocks per iteration: all twelve 16-byte loads of both blocks are in flight before the first use
-        for (int64_t t = lo_t + tid; t < hi_t; t += 2 * PROSHI_BT) {
-            const bool second = t + PROSHI_BT < hi_t;
-            int64_t off[2];
-            double gi[2], cneg[2];
-            double2 q2[2][4], c2[2][4], s2[2][4];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (u == 1 && !second) continue;
-                const int64_t i = __ldg(p.idx + t + u * PROSHI_BT) & CIAO_IDX_MASK;
-                gi[u] = __ldg(p.gam + i);
-                cneg[u] = -__ldg(p.gam_n + i);
-                off[u] = i * p.n_pad + col;
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    if (!cv[h]) continue;
-                    q2[u][h] = __ldcs(reinterpret_cast<const double2 *>(p.qd + off[u]) + h);
-                    c2[u][h] = __ldcs(reinterpret_cast<const double2 *>(p.ql + off[u]) + h);
-                    s2[u][h] = __ldcg(reinterpret_cast<const double2 *>(p.table + off[u]) + h);
-                }
+            for (int u = 0; u < PROSHI_BU; ++u) {     // all loads of the four blocks are in flight before the first use
+                act[u] = cv && (t + (int64_t)u * SLOTS < hi_t);
+                const int64_t i = act[u] ? (__ldg(p.idx + t + (int64_t)u * SLOTS) & CIAO_IDX_MASK) : 0;
+                off[u] = i * p.n_pad + colc;
+                const double2 g2 = __ldg(reinterpret_cast<const double2 *>(p.gpair) + i);
+                gi[u] = g2.x;
+                cneg[u] = -g2.y;
+                q2[u] = __ldcs(reinterpret_cast<const double2 *>(p.qd + off[u]));
+                c2[u] = __ldcs(reinterpret_cast<const double2 *>(p.ql + off[u]));
+                s2[u] = __ldcg(reinterpret_cast<const double2 *>(p.table + off[u]));
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (u == 1 && !second) continue;
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    if (!cv[h]) continue;
-                    // ProShI_basic.jl:114-119 for two columns
-                    const double x0 = __dadd_rn(s2[u][h].x, __dmul_rn(gi[u], z[2 * h]));
-                    const double x1 = __dadd_rn(s2[u][h].y, __dmul_rn(gi[u], z[2 * h + 1]));
-                    const double t0 = __dadd_rn(__dmul_rn(proshi_grad(q2[u][h].x, c2[u][h].x, x0, p.box_lo, p.box_hi, p.eta), cneg[u]), x0);
-                    const double t1 = __dadd_rn(__dmul_rn(proshi_grad(q2[u][h].y, c2[u][h].y, x1, p.box_lo, p.box_hi, p.eta), cneg[u]), x1);
-                    ds[2 * h] += __dsub_rn(t0, s2[u][h].x);
-                    ds[2 * h + 1] += __dsub_rn(t1, s2[u][h].y);
-                    __stcg(reinterpret_cast<double2 *>(p.table + off[u]) + h, make_double2(t0, t1));
-                }
+            for (int u = 0; u < PROSHI_BU; ++u) {
+                if (!act[u]) continue;
+                // ProShI_basic.jl:114-119 for two columns
+                const double x0 = __dadd_rn(s2[u].x, __dmul_rn(gi[u], z0));
+                const double x1 = __dadd_rn(s2[u].y, __dmul_rn(gi[u], z1));
+                const double t0 = __dadd_rn(__dmul_rn(proshi_grad(q2[u].x, c2[u].x, x0, p.box_lo, p.box_hi, p.eta), cneg[u]), x0);
+                const double t1 = __dadd_rn(__dmul_rn(proshi_grad(q2[u].y, c2[u].y, x1, p.box_lo, p.box_hi, p.eta), cneg[u]), x1);
+                ds0 += __dsub_rn(t0, s2[u].x);
+                ds1 += __dsub_rn(t1, s2[u].y);
+                __stcg(reinterpret_cast<double2 *>(p.table + off[u]), make_double2(t0, t1));
             }
         }
-        // close the batch: fixed-order CTA reduction of Σ(t − s), then av and the dual variable z (:121-123)
+        // close the batch: fixed-order reduction of Σ(t − s) over the block slots (lanes with the same piece h, then warps),
+        // then av and the dual variable z (:121-123)
         const int par = (int)(b & 1);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            ds[q] = warp_sum(ds[q]);
-            if (lane == 0) red[par][warp][q] = ds[q];
+        for (int o = 4; o < 32; o <<= 1) {
+            ds0 += __shfl_xor_sync(0xffffffffu, ds0, o);
+            ds1 += __shfl_xor_sync(0xffffffffu, ds1, o);
+        }
+        if (lane < 4) {
+            red[par][warp][lane][0] = ds0;
+            red[par][warp][lane][1] = ds1;
         }
         __syncthreads();  // also orders this batch's table writes before the next batch's reads (same CTA, same columns)
+        double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < PROSHI_BT / 32; ++w) s += red[par][w][q];
-            av[q] = __dadd_rn(av[q], s);
-            z[q] = div_by(__dsub_rn(prox_rt(p.reg.kind, av[q], gl, lo[q], hi[q]), av[q]), p.hat_gamma, rhat);
+        for (int w = 0; w < PROSHI_BT / 32; ++w) {
+            s0 += red[par][w][h][0];
+            s1 += red[par][w][h][1];
         }
+        av0 = __dadd_rn(av0, s0);
+        av1 = __dadd_rn(av1, s1);
+        z0 = div_by(__dsub_rn(prox_rt(p.reg.kind, av0, gl, lo0, hi0), av0), p.hat_gamma, rhat);
+        z1 = div_by(__dsub_rn(prox_rt(p.reg.kind, av1, gl, lo1, hi1), av1), p.hat_gamma, rhat);
     }
-    if (tid == 0) {
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            if (!cv[h]) continue;
-            p.v_z[col + 2 * h] = z[2 * h];
-            p.v_z[col + 2 * h + 1] = z[2 * h + 1];
-            p.v_av[col + 2 * h] = av[2 * h];
-            p.v_av[col + 2 * h + 1] = av[2 * h + 1];
-        }
+    if (tid < 4 && cv) {
+        p.v_z[col] = z0; p.v_z[col + 1] = z1;
+        p.v_av[col] = av0; p.v_av[col + 1] = av1;
     }
 }
 
 // grid (row groups, column chunks of 512); ws[blockIdx.x][n_pad] = partial Σ s_i
 __global__ void __launch_bounds__(256) proshi_init_kernel(const double *qd, const double *ql, const double *gam,
-                                                          double *gam_n, const double *x0, double *table, double *ws, int64_t N,
+                                                          double *gpair, const double *x0, double *table, double *ws, int64_t N,
                                                           int64_t n_pad, double box_lo, double box_hi, double eta,
                                                           double Nd) {
     const int64_t col = 2 * (blockIdx.y * (int64_t)blockDim.x + threadIdx.x);
@@ -280,7 +294,7 @@ __global__ void __launch_bounds__(256) proshi_init_kernel(const double *qd, cons
         const double2 q = __ldcs(reinterpret_cast<const double2 *>(qd + i * n_pad + col));
         const double2 c = __ldcs(reinterpret_cast<const double2 *>(ql + i * n_pad + col));
         const double cg = __ddiv_rn(__ldg(gam + i), Nd);
-        if (col == 0) gam_n[i] = cg;
+        if (col == 0) reinterpret_cast<double2 *>(gpair)[i] = make_double2(__ldg(gam + i), cg);
         const double s0 = __dsub_rn(xa, __dmul_rn(cg, proshi_grad(q.x, c.x, xa, box_lo, box_hi, eta)));
         const double s1 = __dsub_rn(xb, __dmul_rn(cg, proshi_grad(q.y, c.y, xb, box_lo, box_hi, eta)));
         __stcs(reinterpret_cast<double2 *>(table + i * n_pad + col), make_double2(s0, s1));
@@ -361,8 +375,9 @@ int run_proshi_init(ciao_ctx *c, const double *x0_dev) {
     dim3 grid; int G;
     grid2d(c, c->N_total, c->d_pad, &grid, &G);
     CIAO_TRY(ws_reserve(c, ((size_t)G * c->d_pad + 16) * sizeof(double)));
+    if (!c->gpair) CUDA_TRY(cudaMalloc(&c->gpair, (size_t)c->N_total * 2 * sizeof(double)));
     CUDA_TRY(cudaEventRecord(c->ev_pa, c->stream));
-    proshi_init_kernel<<<grid, 256, 0, c->stream>>>(c->qd, c->ql, c->gamma_dev, c->gamma_dev + c->N_total, x0_dev, c->table, c->ws, c->N_total,
+    proshi_init_kernel<<<grid, 256, 0, c->stream>>>(c->qd, c->ql, c->gamma_dev, c->gpair, x0_dev, c->table, c->ws, c->N_total,
                                                     c->d_pad, c->box_lo, c->box_hi, c->eta, (double)c->N_total);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev_pb, c->stream));
@@ -382,8 +397,9 @@ int run_proshi_dual(ciao_ctx *c) {
 
 int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, const int64_t *ptr_dev, int64_t n_batches) {
     if (K <= 0) return CIAO_OK;
+    if (K >= (int64_t)1 << 31) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "ProShI: more than 2^31 - 1 block steps in one call");
     ProshiArgs a;
-    a.qd = c->qd; a.ql = c->ql; a.table = c->table; a.gam = c->gamma_dev; a.gam_n = c->gamma_dev + c->N_total; a.idx = idx_prepared;
+    a.qd = c->qd; a.ql = c->ql; a.table = c->table; a.gam = c->gamma_dev; a.gpair = c->gpair; a.idx = idx_prepared;
     a.K = K; a.N = c->N_total; a.n_pad = c->d_pad;
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_av = ctx_vec(c, CIAO_VEC_AV);
     a.box_lo = c->box_lo; a.box_hi = c->box_hi; a.eta = c->eta; a.Nd = (double)c->N_total; a.hat_gamma = c->hat_gamma;
@@ -391,17 +407,26 @@ int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, const 
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
     if (n_batches > 0 && K / n_batches >= PROSHI_BATCH_MIN) {
         // minibatches: blocks of a batch in parallel, one CTA per 8 columns
-        proshi_batch_kernel<<<(int)((c->d_pad + 7) / 8), PROSHI_BT, 0, c->stream>>>(a, ptr_dev, n_batches);
+        if (K / n_batches >= 1024) proshi_batch_kernel<512, 4><<<(int)((c->d_pad + 7) / 8), 512, 0, c->stream>>>(a, ptr_dev, n_batches);
+        else proshi_batch_kernel<256, 4><<<(int)((c->d_pad + 7) / 8), 256, 0, c->stream>>>(a, ptr_dev, n_batches);
     } else {
-        const int T = (c->seq_threads > 32) ? 64 : 32;   // one warp per CTA spreads the columns over the most SMs
-        const int grid = (int)((c->d_pad / 2 + T - 1) / T);
-        const size_t smem = (size_t)(T / 32) * PROSHI_D * PROSHI_SLOT_BYTES;
-        static bool configured = false;
-        if (!configured) {
-            CUDA_TRY(cudaFuncSetAttribute(proshi_steps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * PROSHI_D * PROSHI_SLOT_BYTES));
-            configured = true;
+        // one compute warp + two producer lanes per CTA; one column per thread while that still gives ≤ 2 CTAs per SM
+        const int64_t nc1 = (c->d_pad + 31) / 32;
+        const bool one = nc1 <= 2 * (int64_t)c->num_sms;
+        const int grid = (int)(one ? nc1 : (c->d_pad + 63) / 64);
+        switch (c->reg.kind) {
+            case CIAO_REG_NORML1:
+                if (one) proshi_steps_kernel<1, CIAO_REG_NORML1><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                else proshi_steps_kernel<2, CIAO_REG_NORML1><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                break;
+            case CIAO_REG_INDBOX:
+                if (one) proshi_steps_kernel<1, CIAO_REG_INDBOX><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                else proshi_steps_kernel<2, CIAO_REG_INDBOX><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                break;
+            default:
+                if (one) proshi_steps_kernel<1, CIAO_REG_ZERO><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                else proshi_steps_kernel<2, CIAO_REG_ZERO><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
         }
-        proshi_steps_kernel<<<grid, T, smem, c->stream>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));

@@ -37,10 +37,6 @@ constexpr int AD_HIST = 32;   // steps of per-component scalar history (≥ CIAO
 constexpr int AD_EXTRA = 12;  // scalar area of a slot: record tail [0,6) | {γ_i, f_i, c_i, 0} [6,10) | index word [10] | pad
 static_assert(AD_D + 1 <= CIAO_HAZARD_WINDOW - 1 && CIAO_HAZARD_WINDOW <= AD_HIST, "hazard window vs ring depth / history");
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 template <int CPT, int LOSS, int REG>
 __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
     constexpr int D = AD_D, H = CPT / 2;
