@@ -379,13 +379,30 @@ extern "C" int ciao_attach_peer_rows(ciao_ctx *c, int n_shards, const void *hand
 
 extern "C" int ciao_set_pass_window(ciao_ctx *c, int64_t row_lo, int64_t n) {
     if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_pass_window: null context");
+    c->win_uniform = false;
+    c->cz_valid = false;
     if (n == 0) {
         c->win0 = c->win_n = 0;
-        return CIAO_OK;
+        if (c->world <= 1) return CIAO_OK;
+    } else {
+        if (row_lo < 0 || n < 0 || row_lo + n > c->n_rows) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_pass_window: window outside the local rows");
+        c->win0 = row_lo;
+        c->win_n = n;
     }
-    if (row_lo < 0 || n < 0 || row_lo + n > c->n_rows) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_pass_window: window outside the local rows");
-    c->win0 = row_lo;
-    c->win_n = n;
+    if (c->world > 1 && c->nccl_comm && c->partial) {
+        // collective when a communicator exists: do all ranks window the same replicated problem uniformly?  Then a pass can
+        // all-gather the per-row step scalars of the windows for the replicated inner epochs.
+        CUDA_TRY(cudaSetDevice(c->device));
+        const bool ok = c->win_n > 0 && c->n_rows == c->N_total && c->N_total % c->world == 0 && c->win_n == c->N_total / c->world &&
+                        c->win0 == (int64_t)c->rank * c->win_n;
+        double flag = ok ? 0.0 : 1.0;
+        double *slot = c->partial + c->d_pad + 4;
+        CUDA_TRY(cudaMemcpyAsync(slot, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CIAO_TRY(ciao_comm_allreduce(c, slot, 1, 1));
+        CUDA_TRY(cudaMemcpyAsync(&flag, slot, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->win_uniform = flag == 0.0;
+    }
     return CIAO_OK;
 }
 

@@ -1,5 +1,5 @@
-// comm.cu — the only exchange step of the path: one allreduce of a d-vector (+ a
-// scalar) per row-sharded streaming pass.  One process per GPU;
+// comm.cu — the exchange steps of the path: one allreduce of a d-vector (+ a scalar) per row-sharded streaming pass
+//  and, when the pass feeds a replicated inner epoch, one all-gather of the per-row step scalars.  One process per GPU;
 // NCCL is bound at run time with dlopen so that libciao_cuda has no link-time
 // dependency on it and shares the copy already loaded by the host process.
 #include <dlfcn.h>
@@ -12,6 +12,7 @@ struct NcclUid { char internal[128]; };
 typedef int (*fn_GetUniqueId)(NcclUid *);
 typedef int (*fn_CommInitRank)(void **, int, NcclUid, int);
 typedef int (*fn_AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*fn_AllGather)(const void *, void *, size_t, int, void *, cudaStream_t);
 typedef int (*fn_CommDestroy)(void *);
 typedef const char *(*fn_GetErrorString)(int);
 struct NcclApi {
@@ -19,6 +20,7 @@ struct NcclApi {
     fn_GetUniqueId GetUniqueId = nullptr;
     fn_CommInitRank CommInitRank = nullptr;
     fn_AllReduce AllReduce = nullptr;
+    fn_AllGather AllGather = nullptr;
     fn_CommDestroy CommDestroy = nullptr;
     fn_GetErrorString GetErrorString = nullptr;
 } g_nccl;
@@ -36,6 +38,7 @@ int nccl_load() {
     g_nccl.GetUniqueId = (fn_GetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (fn_CommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
     g_nccl.AllReduce = (fn_AllReduce)dlsym(g_nccl.h, "ncclAllReduce");
+    g_nccl.AllGather = (fn_AllGather)dlsym(g_nccl.h, "ncclAllGather");
     g_nccl.CommDestroy = (fn_CommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
     g_nccl.GetErrorString = (fn_GetErrorString)dlsym(g_nccl.h, "ncclGetErrorString");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
@@ -83,6 +86,16 @@ int ciao_comm_allreduce(ciao_ctx *c, double *buf, int64_t count, int op_max) {
     if (c->world <= 1) return CIAO_OK;
     if (!c->nccl_comm) CIAO_FAIL(CIAO_ERR_STATE, "allreduce: communicator not initialised");
     NCCL_TRY(g_nccl.AllReduce(buf, buf, (size_t)count, kNcclFloat64, op_max ? kNcclMax : kNcclSum, c->nccl_comm, c->stream));
+    return CIAO_OK;
+}
+
+// in-place all-gather: rank r contributes buf[r·count .. (r+1)·count), every rank ends with all world·count doubles.
+// The second exchange of a row-sharded full-gradient pass: the per-row step scalars {b_i, λ_i, 0, c_i(z_full)} each rank
+// computed for its window, needed by the (replicated) sequential inner epoch.
+int ciao_comm_allgather_inplace(ciao_ctx *c, double *buf, int64_t count_per_rank) {
+    if (c->world <= 1) return CIAO_OK;
+    if (!c->nccl_comm || !g_nccl.AllGather) CIAO_FAIL(CIAO_ERR_STATE, "allgather: communicator not initialised");
+    NCCL_TRY(g_nccl.AllGather(buf + (size_t)c->rank * count_per_rank, buf, (size_t)count_per_rank, kNcclFloat64, c->nccl_comm, c->stream));
     return CIAO_OK;
 }
 

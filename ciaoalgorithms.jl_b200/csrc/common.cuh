@@ -70,6 +70,7 @@ struct ciao_ctx {
     int loss_kind = -1;
     int64_t N_total = 0, row0 = 0, n_rows = 0, d = 0, d_pad = 0, ld = 0;
     int64_t win0 = 0, win_n = 0;       // pass window over the local rows (0 = all)
+    bool win_uniform = false;          // every rank's window is rows [rank·N/world, (rank+1)·N/world): the step scalars can be all-gathered
     double *rec = nullptr;             // row records
     double *qd = nullptr, *ql = nullptr;  // sharing blocks: diag(Q_i), linear term  [N][d_pad]
     double box_lo = 0, box_hi = 0, eta = 0;

@@ -248,6 +248,7 @@ static int launch_cpt(ciao_ctx *c, int mode, const PassArgs &a, int grid, int T,
 }
 
 int ciao_comm_allreduce(ciao_ctx *c, double *buf, int64_t count, int op_max);  // comm.cu
+int ciao_comm_allgather_inplace(ciao_ctx *c, double *buf, int64_t count_per_rank);
 
 // Runs one streaming pass.  Result: c->partial[0..d_pad) = Σ (unscaled, all ranks), c->partial[d_pad] = Σ f_i (or max).
 int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = false) {
@@ -286,9 +287,12 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     PassArgs a;
     a.rec = c->rec + w0 * c->ld; a.n_rows = wn; a.ld = c->ld;
     a.ss_out = nullptr;
-    if (cache_cz && mode == PASS_GRAD && !windowed && c->world == 1) {
+    // the per-row step scalars for the inner kernels: all rows in one process, or — replicated rows, uniformly windowed
+    // passes — each rank its window, all-gathered after the kernel
+    const bool gather_ss = cache_cz && mode == PASS_GRAD && windowed && c->world > 1 && c->win_uniform;
+    if (cache_cz && mode == PASS_GRAD && ((!windowed && c->world == 1) || gather_ss)) {
         if (!c->ss) CUDA_TRY(cudaMalloc(&c->ss, (size_t)(c->n_rows + 1) * 4 * sizeof(double)));
-        a.ss_out = c->ss;
+        a.ss_out = c->ss + 4 * w0;
     }
     if (mode == PASS_GRAD && cache_cz) c->cz_valid = a.ss_out != nullptr;
     a.d_pad = d_pad; a.x = x_dev;
@@ -319,6 +323,7 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
         } else {
             CIAO_TRY(ciao_comm_allreduce(c, c->partial, d_pad + 1, 0));
         }
+        if (gather_ss) CIAO_TRY(ciao_comm_allgather_inplace(c, c->ss, 4 * wn));
     }
     return CIAO_OK;
 }

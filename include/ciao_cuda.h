@@ -106,7 +106,9 @@ int ciao_comm_unique_id(void *out128);
 int ciao_comm_init(ciao_ctx *ctx, const void *id128, int rank, int world);
 /* Replicated data, sharded pass: restrict the full-gradient / objective passes of this context to
  * the local rows [row_lo, row_lo + n) (0-based); with a communicator the partial d-vectors are
- * all-reduced, so G ranks holding the same rows each stream 1/G of them.  n = 0 resets. */
+ * all-reduced, so G ranks holding the same rows each stream 1/G of them.  n = 0 resets.  With a communicator the call is
+ * COLLECTIVE (all ranks must make it): the ranks agree on whether the windows tile [0, N) uniformly, in which case a
+ * full-gradient pass also all-gathers the per-row scalars c_i(z_full) its inner epochs use. */
 int ciao_set_pass_window(ciao_ctx *ctx, int64_t row_lo, int64_t n);
 
 /* Row-sharded problems beyond one GPU's HBM: every rank exports its shard (ciao_rows_ipc_handle, 64 bytes, CUDA IPC),

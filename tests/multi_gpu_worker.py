@@ -49,6 +49,13 @@ def main():
     def rel(a, b):
         return np.linalg.norm(a - b) / np.linalg.norm(b)
 
+    def uid2(r):                                        # a second communicator for the replicated-rows context
+        u = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if r == 0:
+            u = torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(u, 0)
+        return u.cpu().numpy().tobytes()
+
     x = np.random.default_rng(0).standard_normal(d) * 1e-3
     assert rel(sh.full_gradient(x, 1.0 / N), full.full_gradient(x, 1.0 / N)) < 1e-13
     assert abs(sh.objective(x)[0] - full.objective(x)[0]) < 1e-13 * full.objective(x)[0]
@@ -86,6 +93,31 @@ def main():
         full.lfinito_outer(o, 1)
         dist.barrier()
     assert rel(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) < 1e-11
+
+    # replicated rows, windowed passes (bench.py --gpus G): every rank streams N/G rows, the d-vector is all-reduced and the
+    # per-row step scalars c_i(z_full) of the windows are all-gathered for the replicated inner epoch
+    Nw = 4096 * world
+    rep, one = Engine(local), Engine(local)
+    for eng in (rep, one):
+        eng.gen_synthetic(L.SYNTH_LASSO, Nw, d, seed + 1, scale=float(Nw))
+        eng.set_reg(L.REG_NORML1, Nw / 100.0)
+    rep.comm_init(bytes(uid2(rank)), rank, world)
+    rep.set_pass_window(rank * (Nw // world), Nw // world)        # collective
+    g2 = 1.0 / (7.0 * Nw * one.max_row_sqnorm())
+    ra, rb = HostRNG(9), HostRNG(9)
+    rep.svrg_init(np.zeros(d), g2, False)
+    one.svrg_init(np.zeros(d), g2, False)
+    for _ in range(2):
+        rep.svrg_epoch(ra.rand_vec(Nw, Nw // 4))
+        one.svrg_epoch(rb.rand_vec(Nw, Nw // 4))
+    assert rel(rep.get_vec(L.VEC_Z_FULL), one.get_vec(L.VEC_Z_FULL)) < 1e-11
+    assert rel(rep.get_vec(L.VEC_AV), one.get_vec(L.VEC_AV)) < 1e-11
+    t = torch.from_numpy(rep.get_vec(L.VEC_Z_FULL).copy()).cuda()
+    ref = t.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(t, ref)
+    rep.close()
+    one.close()
 
     # tables are not sharded: SAGA on a shard context is refused, not silently wrong
     try:
