@@ -279,6 +279,7 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
     c->device = device;
     c->cache_cz = !(getenv("CIAO_CACHE_CZ") != nullptr && getenv("CIAO_CACHE_CZ")[0] == '0');
     c->seq_table_ldg = getenv("CIAO_SEQ_TABLE_LDG") != nullptr && getenv("CIAO_SEQ_TABLE_LDG")[0] == '1';
+    c->batch_persistent = !(getenv("CIAO_BATCH_PER_LAUNCH") != nullptr && getenv("CIAO_BATCH_PER_LAUNCH")[0] == '1');
     c->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     cudaEvent_t *evs[] = {&c->ev_pa, &c->ev_pb, &c->ev_sa, &c->ev_sb, &c->tm_a, &c->tm_b};
@@ -295,7 +296,7 @@ extern "C" int ciao_destroy(ciao_ctx *c) {
     cudaStreamSynchronize(c->stream);
     ciao_comm_destroy(c);
     free_problem(c);
-    cudaFree(c->ws); cudaFree(c->idx_raw); cudaFree(c->idx_prep); cudaFree(c->ptr_dev); cudaFree(c->err_dev);
+    cudaFree(c->ws); cudaFree(c->idx_raw); cudaFree(c->idx_prep); cudaFree(c->ptr_dev); cudaFree(c->err_dev); cudaFree(c->grid_bar);
     cudaEvent_t evs[] = {c->ev_pa, c->ev_pb, c->ev_sa, c->ev_sb, c->tm_a, c->tm_b};
     for (auto ev : evs) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -778,11 +779,22 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
             for (int64_t t = lo + 1; t < hi && contiguous; ++t) contiguous = idx[t] == idx[t - 1] + 1;
         }
         if (contiguous && batch_ptr[0] == 0 && longest >= BATCH_MIN_ROWS) {
+            std::vector<int64_t> win;   // [first rows…, lengths…] of the non-empty batches
+            for (int64_t j = 0; j < n_batches; ++j)
+                if (batch_ptr[j + 1] > batch_ptr[j]) win.push_back(idx[batch_ptr[j]] - 1);
+            const int64_t nbw = (int64_t)win.size();
+            for (int64_t j = 0; j < n_batches; ++j)
+                if (batch_ptr[j + 1] > batch_ptr[j]) win.push_back(batch_ptr[j + 1] - batch_ptr[j]);
             CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
-            for (int64_t j = 0; j < n_batches; ++j) {
-                const int64_t lo = batch_ptr[j], hi = batch_ptr[j + 1];
-                if (hi > lo) CIAO_TRY(run_batch_step(c, BATCH_FINITO, idx[lo] - 1, hi - lo));
+            int rc = CIAO_ERR_UNSUPPORTED;
+            if (c->batch_persistent && nbw > 1 && nbw < ((int64_t)1 << 22)) {   // all batches in one cooperative launch
+                const int64_t *win_dev;
+                CIAO_TRY(upload_ptr(c, win.data(), 2 * nbw, &win_dev));
+                rc = run_batch_sequence(c, BATCH_FINITO, win_dev, win_dev + nbw, nbw);
+                if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
             }
+            if (rc == CIAO_ERR_UNSUPPORTED)
+                for (int64_t j = 0; j < nbw; ++j) CIAO_TRY(run_batch_step(c, BATCH_FINITO, win[j], win[nbw + j]));
             CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));
             c->timing.last_seq_steps = batch_ptr[n_batches];
             c->seq_timed = true;
@@ -833,11 +845,25 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
     if (total == 0) return CIAO_OK;
     if (r >= BATCH_MIN_ROWS && c->n_rows == c->N_total) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
         CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
-        for (int64_t jj = 0; jj < n_batches; ++jj) {
-            const int64_t j = order[jj];
-            CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));          // :92
-            CIAO_TRY(run_batch_step(c, BATCH_LFINITO, r * (j - 1), (j == nb) ? last_len : r));
+        int rc = CIAO_ERR_UNSUPPORTED;
+        if (c->batch_persistent && n_batches > 1 && n_batches < ((int64_t)1 << 22)) {  // the whole sweep in one cooperative launch
+            std::vector<int64_t> win((size_t)2 * n_batches);
+            for (int64_t jj = 0; jj < n_batches; ++jj) {
+                win[jj] = r * (order[jj] - 1);
+                win[n_batches + jj] = (order[jj] == nb) ? last_len : r;
+            }
+            const int64_t *win_dev;
+            CIAO_TRY(upload_ptr(c, win.data(), 2 * n_batches, &win_dev));
+            CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));          // :92 of the first batch; later ones in the kernel
+            rc = run_batch_sequence(c, BATCH_LFINITO, win_dev, win_dev + n_batches, n_batches);
+            if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
         }
+        if (rc == CIAO_ERR_UNSUPPORTED)
+            for (int64_t jj = 0; jj < n_batches; ++jj) {
+                const int64_t j = order[jj];
+                CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));      // :92
+                CIAO_TRY(run_batch_step(c, BATCH_LFINITO, r * (j - 1), (j == nb) ? last_len : r));
+            }
         CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));
         c->timing.last_seq_steps = total;
         c->seq_timed = true;

@@ -226,6 +226,265 @@ static int launch_batch_loss(ciao_ctx *c, const BatchArgs &a, int grid, int T, s
     return CIAO_OK;
 }
 
+// ---------------------------------------------------------------------------
+// All batches of a call in ONE persistent kernel (cooperative launch, 2 CTAs per SM).  The per-batch version above costs two
+// to three dependent launches per batch (≈ 10 µs each of start-up and ramp) around ≈ 15 µs of HBM time; here a CTA walks the
+// sequence of its row groups across all batches, its TMA ring keeps prefetching the rows of the NEXT batch while the grid
+// closes the current one (rows do not depend on z), and a batch boundary is
+//     partial d-vectors → workspace | grid barrier | distributed fixed-order reduction + av/z update | grid barrier | reload z.
+// The grid barrier is a monotone global counter (release: __threadfence + atomicAdd by one thread per CTA; acquire: a
+// ld.acquire.gpu spin) — co-residency is guaranteed by cudaLaunchCooperativeKernel.  Same arithmetic, same fixed summation
+// order per batch as the per-batch path (CTA partials in CTA order), so results are bitwise reproducible run to run.
+struct BatchPArgs {
+    const double *rec;    // all row records
+    int64_t ld, d_pad;
+    double *table;        // all table rows (Finito) or nullptr
+    const int64_t *b_lo;  // [n_batches] first row of batch j (0-based)
+    const int64_t *b_n;   // [n_batches] rows of batch j
+    int64_t n_batches;
+    double *z, *av;       // state vectors (global): read at every batch start, written by the finish
+    const double *zf;
+    double *ws, *fws;     // [grid][d_pad], [grid]
+    unsigned int *bar;    // grid barrier counter, zero at launch
+    double cN, hat_gamma;
+    RegParams reg;
+    int stages;
+    int red_cols;         // columns per CTA in the distributed reduction (4, 8, 16 or 32)
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int CPT, int MODE, int LOSS>
+__global__ void __launch_bounds__(256, 2) batch_persistent_kernel(const BatchPArgs p) {
+    constexpr int RPG = 16 / CPT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const int S = p.stages;
+    const int64_t G = gridDim.x, bid = blockIdx.x;
+    const size_t stage_doubles = (size_t)RPG * p.ld;
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    double *red = ring + (size_t)S * stage_doubles;          // [2][RPG][32][2]
+    double *rsm = red + 2 * RPG * 32 * 2;                     // [9][33]: the distributed reduction
+    uint64_t *full = reinterpret_cast<uint64_t *>(rsm + 9 * 33 + 1);
+
+    uint64_t policy = 0;
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+        policy = l2_policy_evict_first();
+    }
+    __syncthreads();
+
+    // the sequence of (batch, group) items of this CTA: groups bid, bid + G, … of batch 0, then of batch 1, …
+    auto first_item = [&](int64_t &b, int64_t &g) {
+        b = 0; g = bid;
+        while (b < p.n_batches && g >= (p.b_n[b] + RPG - 1) / RPG) { ++b; g = bid; }
+    };
+    auto next_item = [&](int64_t &b, int64_t &g) {
+        g += G;
+        while (b < p.n_batches && g >= (p.b_n[b] + RPG - 1) / RPG) { ++b; g = bid; }
+    };
+    int64_t pb, pg, issued = 0;  // producer cursor (thread 0)
+    auto issue = [&]() {
+        const int64_t r0 = p.b_lo[pb] + pg * RPG;
+        const int rows = (int)min((int64_t)RPG, p.b_n[pb] - pg * RPG);
+        const uint32_t bytes = (uint32_t)(rows * p.ld * sizeof(double));
+        const int slot = (int)(issued % S);
+        mbar_arrive_expect_tx(&full[slot], bytes);
+        tma_load_1d_stream(ring + (size_t)slot * stage_doubles, p.rec + r0 * p.ld, bytes, &full[slot], policy);
+        ++issued;
+        next_item(pb, pg);
+    };
+    if (tid == 0) {
+        first_item(pb, pg);
+        for (int s = 0; s < S && pb < p.n_batches; ++s) issue();
+    }
+
+    int col[CPT / 2];
+#pragma unroll
+    for (int k = 0; k < CPT / 2; ++k) {
+        col[k] = 2 * (tid + T * k);
+        if (col[k] >= p.d_pad) col[k] = -1;
+    }
+    int64_t cb, cg, it = 0;  // consumer cursor (all threads), items consumed so far
+    first_item(cb, cg);
+    unsigned int bar_target = 0;
+
+    for (int64_t b = 0; b < p.n_batches; ++b) {
+        double zr[CPT], zfr[CPT], acc[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT / 2; ++k)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const bool v = col[k] >= 0;
+                zr[2 * k + e] = v ? __ldcg(p.z + col[k] + e) : 0.0;          // written by other CTAs in the last finish
+                zfr[2 * k + e] = (v && MODE == BATCH_LFINITO) ? p.zf[col[k] + e] : 0.0;
+                acc[2 * k + e] = 0.0;
+            }
+        double fsum = 0.0;
+        const int64_t lo_b = p.b_lo[b], n_b = p.b_n[b];
+        while (cb == b) {
+            const int slot = (int)(it % S);
+            const uint32_t parity = (uint32_t)((it / S) & 1);
+            const int par = (int)(it & 1);
+            const int64_t r0 = lo_b + cg * RPG;
+            const int rows = (int)min((int64_t)RPG, n_b - cg * RPG);
+            double2 so[RPG][CPT / 2];
+            if (MODE == BATCH_FINITO) {
+#pragma unroll
+                for (int r = 0; r < RPG; ++r)
+#pragma unroll
+                    for (int k = 0; k < CPT / 2; ++k)
+                        so[r][k] = (r < rows && col[k] >= 0)
+                                       ? __ldcg(reinterpret_cast<const double2 *>(p.table + (r0 + r) * p.d_pad + col[k]))
+                                       : make_double2(0.0, 0.0);
+            }
+            mbar_wait(&full[slot], parity);
+            const double *sp = ring + (size_t)slot * stage_doubles;
+            double a[RPG][CPT], p0[RPG], p1[RPG], tb[RPG], tl[RPG], tgn[RPG], thg[RPG];
+#pragma unroll
+            for (int r = 0; r < RPG; ++r) {
+                p0[r] = p1[r] = 0.0;
+                const bool rv = r < rows;
+                const double *rp = sp + (size_t)r * p.ld;
+#pragma unroll
+                for (int k = 0; k < CPT / 2; ++k) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (rv && col[k] >= 0) v = *reinterpret_cast<const double2 *>(rp + col[k]);
+                    a[r][2 * k] = v.x;
+                    a[r][2 * k + 1] = v.y;
+                    p0[r] = fma(v.x, zr[2 * k], p0[r]);
+                    p0[r] = fma(v.y, zr[2 * k + 1], p0[r]);
+                    if (MODE == BATCH_LFINITO) {
+                        p1[r] = fma(v.x, zfr[2 * k], p1[r]);
+                        p1[r] = fma(v.y, zfr[2 * k + 1], p1[r]);
+                    }
+                }
+                tb[r] = rv ? rp[p.d_pad + TAIL_B] : 0.0;
+                tl[r] = rv ? rp[p.d_pad + TAIL_LAM] : 0.0;
+                tgn[r] = rv ? rp[p.d_pad + TAIL_GAM_N] : 0.0;
+                thg[r] = rv ? rp[p.d_pad + TAIL_HAT_GAM] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < RPG; ++r) {
+                p0[r] = warp_sum(p0[r]);
+                if (MODE == BATCH_LFINITO) p1[r] = warp_sum(p1[r]);
+                if (lane == 0) {
+                    red[((par * RPG + r) * 32 + warp) * 2] = p0[r];
+                    red[((par * RPG + r) * 32 + warp) * 2 + 1] = p1[r];
+                }
+            }
+            __syncthreads();
+            if (tid == 0 && pb < p.n_batches) issue();  // the slot just read is free: prefetch runs ahead across batch boundaries
+#pragma unroll
+            for (int r = 0; r < RPG; ++r) {
+                double u0 = 0.0, u1 = 0.0;
+                const double *rr = red + (par * RPG + r) * 32 * 2;
+                for (int w = 0; w < W; ++w) {
+                    u0 += rr[2 * w];
+                    u1 += rr[2 * w + 1];
+                }
+                if (r >= rows) continue;
+                const double cz = loss_coef<LOSS>(u0, tb[r], tl[r]);
+                if (MODE == BATCH_FINITO) {  // Finito_basic.jl:112-116
+                    const double cneg = -tgn[r], rr2 = thg[r];
+                    double *trow = p.table + (r0 + r) * p.d_pad;
+#pragma unroll
+                    for (int k = 0; k < CPT / 2; ++k) {
+                        double t0 = __dadd_rn(__dmul_rn(grad_elem<LOSS>(a[r][2 * k], cz, tl[r]), cneg), zr[2 * k]);
+                        double t1 = __dadd_rn(__dmul_rn(grad_elem<LOSS>(a[r][2 * k + 1], cz, tl[r]), cneg), zr[2 * k + 1]);
+                        acc[2 * k] += __dmul_rn(__dsub_rn(t0, so[r][k].x), rr2);
+                        acc[2 * k + 1] += __dmul_rn(__dsub_rn(t1, so[r][k].y), rr2);
+                        if (col[k] >= 0) __stcg(reinterpret_cast<double2 *>(trow + col[k]), make_double2(t0, t1));
+                    }
+                } else {  // Finito_LFinito.jl:94-98
+                    const double czf = loss_coef<LOSS>(u1, tb[r], tl[r]);
+#pragma unroll
+                    for (int e = 0; e < CPT; ++e) {
+                        acc[e] += __dmul_rn(p.cN, grad_elem<LOSS>(a[r][e], czf, tl[r]));
+                        acc[e] -= __dmul_rn(p.cN, grad_elem<LOSS>(a[r][e], cz, tl[r]));
+                    }
+                    if (tid == 0) fsum += thg[r];
+                }
+            }
+            next_item(cb, cg);
+            ++it;
+        }
+        // ---- close the batch ----
+        double *wrow = p.ws + (size_t)bid * p.d_pad;
+#pragma unroll
+        for (int k = 0; k < CPT / 2; ++k)
+            if (col[k] >= 0) __stcg(reinterpret_cast<double2 *>(wrow + col[k]), make_double2(acc[2 * k], acc[2 * k + 1]));
+        if (tid == 0) __stcg(p.fws + bid, fsum);
+        bar_target += (unsigned int)G;
+        grid_barrier(p.bar, bar_target);
+        // distributed fixed-order reduction over ALL CTAs: CTA c owns the RC columns RC·c … (RC = 4…32, a whole number of
+        // sectors); thread (col, slice) sums the CTA partials slice, slice + NS, … with four independent chains, the slices
+        // are combined by shuffles inside a warp and through shared memory across the 8 warps — always in the same order
+        {
+            const int RC = p.red_cols, NS = 256 / RC;
+            const int cl = tid % RC, sl = tid / RC;
+            const int64_t j = bid * RC + cl;
+            const bool jv = j < p.d_pad;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            if (jv) {
+                int64_t q = sl;
+                for (; q + 3 * NS < G; q += 4 * NS) {
+                    s0 += __ldcg(p.ws + (size_t)q * p.d_pad + j);
+                    s1 += __ldcg(p.ws + (size_t)(q + NS) * p.d_pad + j);
+                    s2 += __ldcg(p.ws + (size_t)(q + 2 * NS) * p.d_pad + j);
+                    s3 += __ldcg(p.ws + (size_t)(q + 3 * NS) * p.d_pad + j);
+                }
+                for (; q < G; q += NS) s0 += __ldcg(p.ws + (size_t)q * p.d_pad + j);
+            }
+            double sacc = (s0 + s1) + (s2 + s3);
+            for (int o = RC; o < 32; o <<= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (lane < RC) rsm[warp * 33 + lane] = sacc;
+            double f = 0.0;
+            if (MODE == BATCH_LFINITO) {  // Σ γ̂/γ_i of the batch: every CTA needs it; thread t takes fws[t], fws[t+256], …
+                for (int64_t q = tid; q < G; q += 256) f += __ldcg(p.fws + q);
+                f = warp_sum(f);
+                if (lane == 0) rsm[8 * 33 + warp] = f;
+            }
+            __syncthreads();
+            if (tid < RC && jv) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += rsm[w * 33 + tid];
+                double anew = __dadd_rn(__ldcg(p.av + j), t);
+                const double lo = p.reg.lo_v ? p.reg.lo_v[j] : p.reg.lo_s, hi = p.reg.hi_v ? p.reg.hi_v[j] : p.reg.hi_s;
+                const double gl = p.hat_gamma * p.reg.lambda;
+                if (MODE == BATCH_LFINITO) {
+                    double fs = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) fs += rsm[8 * 33 + w];
+                    anew = __dadd_rn(anew, __dmul_rn(fs, __dsub_rn(__ldcg(p.z + j), p.zf[j])));              // :98
+                    __stcg(p.av + j, anew);
+                    if (b + 1 < p.n_batches) __stcg(p.z + j, prox_rt(p.reg.kind, anew, gl, lo, hi));          // :92 of the next batch
+                } else {
+                    __stcg(p.av + j, anew);
+                    __stcg(p.z + j, prox_rt(p.reg.kind, anew, gl, lo, hi));                                   // Finito_basic.jl:118
+                }
+            }
+            __syncthreads();  // rsm is reused by the next batch
+        }
+        bar_target += (unsigned int)G;
+        grid_barrier(p.bar, bar_target);
+    }
+}
+
 // One minibatch over the contiguous rows [row_lo, row_lo + n): pass + reduction + finish, on the context stream.
 int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
     const int64_t d_pad = c->d_pad;
@@ -276,5 +535,85 @@ int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
         a.ws, a.fws, grid, ctx_vec(c, CIAO_VEC_AV), ctx_vec(c, CIAO_VEC_Z), ctx_vec(c, CIAO_VEC_Z_FULL), d_pad, mode, c->hat_gamma, c->reg);
     CUDA_TRY(cudaGetLastError());
     c->timing.launches += 2;
+    return CIAO_OK;
+}
+
+// All batches in one cooperative launch.  rows/lens: device arrays of n_batches batch windows.  Returns CIAO_ERR_UNSUPPORTED
+// when a cooperative grid of 2 CTAs/SM is not available (the caller then falls back to one pass per batch).
+template <int CPT, int MODE, int LOSS>
+static int launch_batch_persistent(ciao_ctx *c, BatchPArgs &a, int T, size_t smem) {
+    auto kern = batch_persistent_kernel<CPT, MODE, LOSS>;
+    static size_t configured[CIAO_MAX_DEVICES] = {};
+    if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device % CIAO_MAX_DEVICES] = smem;
+    }
+    int occ = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
+    if (occ < 1) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "persistent minibatch kernel does not fit on an SM");
+    const int grid = std::min(occ, 2) * c->num_sms;
+    const size_t need = ((size_t)grid * a.d_pad + grid + 16) * sizeof(double);
+    if (need > c->ws_bytes) {
+        if (c->ws) cudaFree(c->ws);
+        c->ws = nullptr;
+        c->ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&c->ws, need));
+        c->ws_bytes = need;
+    }
+    a.ws = c->ws; a.fws = c->ws + (size_t)grid * a.d_pad;
+    int rc_cols = 4;
+    while (rc_cols < 32 && (int64_t)rc_cols * grid < a.d_pad) rc_cols *= 2;
+    if ((int64_t)rc_cols * grid < a.d_pad) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "persistent minibatch kernel: d too large for the distributed reduction");
+    a.red_cols = rc_cols;
+    void *args[] = {(void *)&a};
+    CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(T), args, smem, c->stream));
+    return CIAO_OK;
+}
+
+template <int CPT, int MODE>
+static int launch_batch_persistent_loss(ciao_ctx *c, BatchPArgs &a, int T, size_t smem) {
+    return c->loss_kind == CIAO_LOSS_LS ? launch_batch_persistent<CPT, MODE, CIAO_LOSS_LS>(c, a, T, smem)
+                                        : launch_batch_persistent<CPT, MODE, CIAO_LOSS_LOGISTIC>(c, a, T, smem);
+}
+
+// b_lo_dev / b_n_dev: device arrays (n_batches) of batch windows; z (and z_full for LFinito) as the first batch needs them
+int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int64_t *b_n_dev, int64_t n_batches) {
+    if (n_batches <= 0) return CIAO_OK;
+    const int64_t d_pad = c->d_pad;
+    int cpt = 2;
+    while (cpt < 16 && (d_pad + cpt - 1) / cpt > 256) cpt *= 2;
+    const int64_t Tn = ((d_pad + cpt - 1) / cpt + 31) / 32 * 32;
+    if (Tn > 256) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "minibatch pass: d = %lld exceeds 4096", (long long)c->d);
+    const int T = 256, rpg = 16 / cpt;   // the distributed reduction wants 256 threads; extra threads own no columns
+    const size_t stage_bytes = (size_t)rpg * c->ld * sizeof(double);
+    const size_t fixed = (2 * rpg * 32 * 2 + 9 * 33 + 1) * sizeof(double) + 16 * sizeof(uint64_t) + 256;
+    int S = 3;
+    while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)110 * 1024) --S;
+    const size_t smem = (size_t)S * stage_bytes + fixed;
+    if (!c->grid_bar) CUDA_TRY(cudaMalloc(&c->grid_bar, 64));
+    CUDA_TRY(cudaMemsetAsync(c->grid_bar, 0, 64, c->stream));
+    BatchPArgs a;
+    a.rec = c->rec; a.ld = c->ld; a.d_pad = d_pad; a.table = c->table; a.b_lo = b_lo_dev; a.b_n = b_n_dev; a.n_batches = n_batches;
+    a.z = ctx_vec(c, CIAO_VEC_Z); a.av = ctx_vec(c, CIAO_VEC_AV); a.zf = ctx_vec(c, CIAO_VEC_Z_FULL);
+    a.bar = c->grid_bar; a.cN = c->hat_gamma / (double)c->N_total; a.hat_gamma = c->hat_gamma; a.reg = c->reg; a.stages = S;
+    a.ws = nullptr; a.fws = nullptr;
+    int rc;
+    if (mode == BATCH_FINITO) {
+        switch (cpt) {
+            case 2: rc = launch_batch_persistent_loss<2, BATCH_FINITO>(c, a, T, smem); break;
+            case 4: rc = launch_batch_persistent_loss<4, BATCH_FINITO>(c, a, T, smem); break;
+            case 8: rc = launch_batch_persistent_loss<8, BATCH_FINITO>(c, a, T, smem); break;
+            default: rc = launch_batch_persistent_loss<16, BATCH_FINITO>(c, a, T, smem); break;
+        }
+    } else {
+        switch (cpt) {
+            case 2: rc = launch_batch_persistent_loss<2, BATCH_LFINITO>(c, a, T, smem); break;
+            case 4: rc = launch_batch_persistent_loss<4, BATCH_LFINITO>(c, a, T, smem); break;
+            case 8: rc = launch_batch_persistent_loss<8, BATCH_LFINITO>(c, a, T, smem); break;
+            default: rc = launch_batch_persistent_loss<16, BATCH_LFINITO>(c, a, T, smem); break;
+        }
+    }
+    CIAO_TRY(rc);
+    c->timing.launches += 1;
     return CIAO_OK;
 }

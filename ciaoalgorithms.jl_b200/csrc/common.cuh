@@ -100,6 +100,8 @@ struct ciao_ctx {
     // Debug/test knob (env CIAO_SEQ_TABLE_LDG=1): SAGA/Finito table rows by register prefetch instead of the TMA-staged
     // ring (the path taken anyway when the ring does not fit in shared memory).
     bool seq_table_ldg = false;
+    // minibatch sequences run in one persistent cooperative kernel (batch.cu); env CIAO_BATCH_PER_LAUNCH=1 keeps one pass per batch
+    bool batch_persistent = true;
     // workspace
     double *ws = nullptr;  size_t ws_bytes = 0;
     double *partial = nullptr;         // [d_pad + 8] partial d-vector + scalars (allreduce buffer)
@@ -107,6 +109,7 @@ struct ciao_ctx {
     size_t idx_cap = 0, ptr_cap = 0;
     int64_t staged = 0;
     int *err_dev = nullptr;
+    unsigned int *grid_bar = nullptr;  // grid barrier counter of the persistent minibatch kernel (batch.cu)
     double *host_pin = nullptr; size_t host_pin_bytes = 0;
     // comm
     void *nccl_comm = nullptr; int rank = 0, world = 1;

@@ -15,7 +15,9 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("kind,N,d,batch", [(orc.LOSS_LS, 1500, 64, 256), (orc.LOSS_LOGISTIC, 2100, 1024, 512),
                                              (orc.LOSS_LS, 1024, 4096, 256), (orc.LOSS_LOGISTIC, 900, 130, 300)])
 @pytest.mark.parametrize("sweeping", [2, 3])
-def test_finito_static_minibatch_pass(kind, N, d, batch, sweeping):
+@pytest.mark.parametrize("launch", ["persistent", "per_batch"])
+def test_finito_static_minibatch_pass(kind, N, d, batch, sweeping, launch, monkeypatch):
+    monkeypatch.setenv("CIAO_BATCH_PER_LAUNCH", "1" if launch == "per_batch" else "0")   # read by ciao_create
     p, e = make_rows(kind, N, d, 0xBA7 + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
     Li = np.sum(p.A * p.A, axis=1) * (N if kind == orc.LOSS_LS else 0.25)
     gam = 0.999 * N / Li
@@ -38,7 +40,9 @@ def test_finito_static_minibatch_pass(kind, N, d, batch, sweeping):
 
 @pytest.mark.parametrize("kind,N,d,batch", [(orc.LOSS_LS, 1500, 64, 256), (orc.LOSS_LOGISTIC, 2100, 1024, 700)])
 @pytest.mark.parametrize("sweeping", [2, 3])
-def test_lfinito_minibatch_sweep_pass(kind, N, d, batch, sweeping):
+@pytest.mark.parametrize("launch", ["persistent", "per_batch"])
+def test_lfinito_minibatch_sweep_pass(kind, N, d, batch, sweeping, launch, monkeypatch):
+    monkeypatch.setenv("CIAO_BATCH_PER_LAUNCH", "1" if launch == "per_batch" else "0")
     p, e = make_rows(kind, N, d, 0xBA8 + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
     Li = np.sum(p.A * p.A, axis=1) * (N if kind == orc.LOSS_LS else 0.25)
     gam = 0.999 * N / Li
