@@ -48,6 +48,7 @@ struct SeqArgs {
     int plus, sag;
     int npart_pad;          // C·W rounded up to a multiple of 32
     int table_tma;          // table rows are staged in the ring by TMA (else: register prefetch with ld.global)
+    int zero;               // always 0, opaque to the compiler (pins work in front of the exchange wait, see below)
     RegParams reg;
 };
 
@@ -288,12 +289,16 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             if (lane < C) st_async_v2f64(send_dst[par], v0, v1, send_bar[par]);
             // ---- in the shadow of the exchange: ∇f_i(z_full) = c_i(z_full)·a_i from the cached scalar (the step is fp64-issue
             //      bound after the exchange, so every product formed here comes off the critical path)
+            // ptxas sinks register-only arithmetic below the wait loop; making the wait's parity operand depend on the products
+            // (through a mask that is zero at run time) keeps them here
             double gz[CPT];
+            int pin = 0;
             if (CZ) {
 #pragma unroll
                 for (int q = 0; q < CPT; ++q) {
                     gz[q] = grad_elem<LOSS>(cur.a[q], cur.cz, cur.lam);
                     if (ALG == ALG_LFINITO) gz[q] = __dmul_rn(cN, gz[q]);
+                    pin ^= __double2hiint(gz[q]);
                 }
             }
             // ---- while the exchange is in flight: the next row and its table row go to registers
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 if (TABLE && !TT) load_table(nxt);
             }
             PROF_T(t_c);
-            mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1));
+            mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1) ^ (uint32_t)(pin & p.zero));
             PROF_T(t_d);
             // every warp reduces the same C·W partials with the same butterfly → identical bits everywhere
             double u0 = 0.0, u1 = 0.0;
@@ -548,7 +553,7 @@ static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, doub
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_zfull = ctx_vec(c, CIAO_VEC_Z_FULL); a.v_w = ctx_vec(c, CIAO_VEC_W);
     a.v_av = ctx_vec(c, CIAO_VEC_AV); a.v_zsum = ctx_vec(c, CIAO_VEC_Z);  // SVRG: state.z is the running sum of inner iterates
     a.gamma = c->gamma; a.hat_gamma = c->hat_gamma; a.Nd = (double)c->N_total; a.m_d = m_d;
-    a.plus = c->plus; a.sag = c->sag; a.reg = c->reg; a.npart_pad = sh.npart_pad;
+    a.plus = c->plus; a.sag = c->sag; a.reg = c->reg; a.npart_pad = sh.npart_pad; a.zero = 0;
     a.table_tma = (ALG == ALG_SAGA || ALG == ALG_FINITO) && seq_smem_bytes(sh, true) <= 200 * 1024 && !c->seq_table_ldg;
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
     int rc;
