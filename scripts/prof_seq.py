@@ -36,17 +36,23 @@ for loss in losses:
             if alg == "svrg":
                 e.svrg_init(x0, 1.0 / (7.0 * Lmax), True)
                 e.svrg_epoch(idx); e.svrg_epoch(idx)
-            elif alg == "saga":
-                e.saga_init(x0, 1.0 / (3.0 * Lmax), False)
+            elif alg in ("saga", "sag"):
+                e.saga_init(x0, 1.0 / ((16.0 if alg == "sag" else 3.0) * Lmax), alg == "sag")
                 e.saga_steps(idx); e.saga_steps(idx)
+            elif alg == "lfinito":
+                gam = np.full(N, 0.999 * N / Lmax)
+                e.lfinito_init(x0, gam, 1 / np.sum(1 / gam))
+                e.lfinito_outer(np.arange(1, N + 1, dtype=np.int64), 1)
+                e.lfinito_outer(np.arange(1, N + 1, dtype=np.int64), 1)
             else:
                 gam = np.full(N, 0.999 * N / Lmax)
                 e.finito_init(x0, gam, 1 / np.sum(1 / gam))
                 bp = np.arange(m + 1, dtype=np.int64)
                 e.finito_steps(idx, bp); e.finito_steps(idx, bp)
             t = e.last_timing()
-            fn = getattr(e.lib, f"ciao_debug_seq_prof_{alg}", None)
-            line = f"{alg:7s} {loss:8s} d={d} C={C_} T={T}: {1e3 * t.last_seq_ms / m:.4f} us/step"
+            steps = N if alg == "lfinito" else m
+            fn = getattr(e.lib, f"ciao_debug_seq_prof_{'saga' if alg == 'sag' else alg}", None)
+            line = f"{alg:7s} {loss:8s} d={d} C={C_} T={T}: {1e3 * t.last_seq_ms / steps:.4f} us/step"
             if fn is not None:
                 fn.argtypes = [C.c_void_p, C.c_void_p]
                 fn(e.h, prof)
