@@ -623,3 +623,52 @@ def test_full_scale_properties():
             outs.append(z1)
             assert f1 < f0
         assert np.array_equal(outs[0], outs[1])
+
+
+def test_full_scale_table_invariants_c2_c5():
+    """BASELINE configs 2 and 5 at full size (N = 2^20 × 1024 logistic; 2^18 blocks × 1024): the running averages the
+    sequential kernels keep in registers must equal what the N×d tables hold in HBM — size-independent invariants of
+    the reference's updates (SAGA_basic.jl:47,62: av = Σ s_i / N;  Finito_basic.jl:83,115: av = γ̂ Σ s_i/γ_i with equal
+    γ_i;  ProShI_basic.jl:83,113-119: av = Σ s_i), checked after random steps with the table hazard path active."""
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 40e9:
+        pytest.skip("needs 40 GB of HBM")
+    N, d = 1 << 20, 1024
+    with Engine(0) as e:
+        e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0)
+        e.set_reg(L.REG_NORML1, 1.0 / N)
+        Lmax = 0.25 * e.max_row_sqnorm()
+        idx = HostRNG(0x1D0002).rand_vec(N, N // 2)
+        idx[1000:1040] = idx[999]                       # repeats inside the prefetch window
+        e.saga_init(np.ones(d), 1 / (3 * Lmax), False)
+        e.saga_steps(idx)
+        av = e.get_vec(L.VEC_AV)
+        assert rel(av * N, e.table_colsum()) < 1e-9
+        z1 = e.get_vec(L.VEC_Z)
+        e.saga_init(np.ones(d), 1 / (3 * Lmax), False)
+        e.saga_steps(idx)
+        assert np.array_equal(z1, e.get_vec(L.VEC_Z))   # bitwise reproducible at full size
+        gam = np.full(N, 0.999 * N / Lmax)
+        hat = 1 / np.sum(1 / gam)
+        e.finito_init(np.ones(d), gam, hat)
+        e.finito_steps(idx, np.arange(len(idx) + 1, dtype=np.int64))
+        assert rel(e.get_vec(L.VEC_AV), e.table_colsum() * (hat / gam[0])) < 1e-9
+        f0, f1 = sum(e.objective(np.ones(d))), sum(e.objective(e.get_vec(L.VEC_Z)))
+        assert f1 < f0
+    N, n = 1 << 18, 1024
+    with Engine(0) as e:
+        e.gen_synthetic(L.SYNTH_SHARING, N, n, 0x5EED0005)
+        e.set_reg(L.REG_INDBOX, -np.inf, np.ones(n))
+        gam = 0.999 * N / np.full(N, 10.0 + 10.0 * N)
+        e.proshi_init(np.zeros(n), gam, float(np.sum(gam)))
+        idx = HostRNG(0x1D0005).rand_vec(N, N)
+        idx[500:520] = idx[499]
+        e.proshi_steps(idx, np.arange(N + 1, dtype=np.int64))                     # batch 1: producer-lane kernel
+        assert rel(e.get_vec(L.VEC_AV), e.table_colsum()) < 1e-9
+        sw = BatchSweeper(N, 4096, 2, HostRNG(1))
+        bidx, bp = csr(sw.take(sw.d))
+        e.proshi_steps(bidx, bp)                                                   # batch 4096: four-lanes-per-block kernel
+        assert rel(e.get_vec(L.VEC_AV), e.table_colsum()) < 1e-9
+        z = e.get_vec(L.VEC_Z)
+        assert np.all(np.isfinite(z))
