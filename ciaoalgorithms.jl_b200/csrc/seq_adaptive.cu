@@ -29,6 +29,7 @@ struct AdArgs {
     double *v_z, *v_av;
     double Nd, alpha, tol_b;
     int npart_pad;
+    int zero;            // always 0, opaque to the compiler (see seq_impl.cuh)
     RegParams reg;
 };
 
@@ -139,24 +140,45 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
         uint32_t ex = 0;  // exchanges so far (identical in every thread of the cluster)
         bool stopped = false;
 
-        for (int64_t k = 0; k < K; ++k) {
-            const int slot = (int)(k & (D - 1));
-            mbar_wait(&row_bar[slot], (uint32_t)((k >> 3) & 1));
-            const double *rp = ring + slot * slot_doubles;
+        struct Row {
             double a[CPT], s[CPT];
+            double tb, tl, gam, fix, cold;
+            int64_t ik;
+        };
+        // pulls the staged data of `step` into registers and hands the slot back to the producer
+        auto load = [&](int64_t step, Row &r) {
+            const int slot = (int)(step & (D - 1));
+            mbar_wait(&row_bar[slot], (uint32_t)((step >> 3) & 1));
+            const double *rp = ring + slot * slot_doubles;
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 const double2 va = *reinterpret_cast<const double2 *>(rp + lcol[h]);
                 const double2 vs = *reinterpret_cast<const double2 *>(rp + cover + AD_EXTRA + lcol[h]);
-                a[2 * h] = va.x; a[2 * h + 1] = va.y;
-                s[2 * h] = vs.x; s[2 * h + 1] = vs.y;
+                r.a[2 * h] = va.x; r.a[2 * h + 1] = va.y;
+                r.s[2 * h] = vs.x; r.s[2 * h + 1] = vs.y;
             }
-            const double tb = rp[cover + TAIL_B], tl = rp[cover + TAIL_LAM];
-            double gam = rp[cover + CIAO_TAIL_USED], fix = rp[cover + CIAO_TAIL_USED + 1], cold = rp[cover + CIAO_TAIL_USED + 2];
-            const int64_t ik = *reinterpret_cast<const int64_t *>(rp + cover + 10);
+            r.tb = rp[cover + TAIL_B]; r.tl = rp[cover + TAIL_LAM];
+            r.gam = rp[cover + CIAO_TAIL_USED]; r.fix = rp[cover + CIAO_TAIL_USED + 1]; r.cold = rp[cover + CIAO_TAIL_USED + 2];
+            r.ik = *reinterpret_cast<const int64_t *>(rp + cover + 10);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[slot]);  // the slot may be refilled (drained like this after a stop, too)
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);
+        };
+        Row nxt;
+        bool have_next = false;
+        if (K > 0) {
+            load(0, nxt);
+            have_next = true;
+        }
+        for (int64_t k = 0; k < K; ++k) {
+            if (!have_next) load(k, nxt);   // only after a stop (slots are still drained) or when the prefetch below was skipped
+            have_next = false;
             if (stopped) continue;
+            double a[CPT], s[CPT];
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) { a[q] = nxt.a[q]; s[q] = nxt.s[q]; }
+            const double tb = nxt.tb, tl = nxt.tl;
+            double gam = nxt.gam, fix = nxt.fix, cold = nxt.cold;
+            const int64_t ik = nxt.ik;
 
             double *trow = p.table + (ik & CIAO_IDX_MASK) * p.d_pad;
             if (ik & CIAO_FLAG_HAZARD) {
@@ -176,7 +198,7 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                 gold[q] = grad_elem<LOSS>(a[q], cold, tl);  // ∇f_i(x_i)[k], the values the reference's table holds
                 res[q] = __dsub_rn(z[q], s[q]);             // :121
             }
-            double u = 0.0, fi_z = 0.0;
+            double u = 0.0, fi_z = 0.0, r_main = 0.0, cN_main = 0.0;
             for (;;) {                                      // :123-147
                 if (gam < thr) {                            // :124-127  `return nothing`
                     stopped = true;
@@ -197,7 +219,17 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                     st_async_v2f64(send_dst[par], p1, p2, send_bar[par]);
                     st_async_v2f64(send_dst[par] + 16, p3, 0.0, send_bar[par]);
                 }
-                mbar_wait(&part_bar[par], (ex >> 1) & 1);
+                // in the shadow of the exchange: the three divisions that depend only on γ_i and γ̂ (pinned in front of the wait
+                // through the parity operand, as in seq_impl.cuh), and the registers of the next step
+                const double coef = __ddiv_rn(half_N_alpha, gam);      // :131  0.5·N·α / γ_i
+                const double r_hg = __ddiv_rn(hg, gam);                // :149  γ̂ / γ_i
+                const double cN = __ddiv_rn(hg, p.Nd);                 // :151  γ̂ / N
+                const int pin = __double2hiint(coef) ^ __double2hiint(r_hg) ^ __double2hiint(cN);
+                if (!have_next && k + 1 < K) {
+                    load(k + 1, nxt);
+                    have_next = true;
+                }
+                mbar_wait(&part_bar[par], ((ex >> 1) & 1) ^ (uint32_t)(pin & p.zero));
                 if (tid == 0) mbar_arrive_expect_tx(&part_bar[par], part_bytes);  // arm exchange ex + 2
                 double U = 0.0, Dg = 0.0, R2 = 0.0;
                 {
@@ -214,10 +246,12 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                 ++ex;
                 fi_z = loss_value<LOSS>(U, tb, tl);                                              // :128
                 const double nr = __dsqrt_rn(R2);
-                const double fi_model = __dadd_rn(__dadd_rn(fix, Dg), __dmul_rn(__ddiv_rn(half_N_alpha, gam), __dmul_rn(nr, nr)));  // :129-132
+                const double fi_model = __dadd_rn(__dadd_rn(fix, Dg), __dmul_rn(coef, __dmul_rn(nr, nr)));  // :129-132
                 const double tol = __dmul_rn(10 * 2.220446049250313e-16, __dadd_rn(1.0, fabs(fi_z)));  // :133
                 if (fi_z <= __dadd_rn(fi_model, tol)) {                                          // :134
                     u = U;
+                    r_main = r_hg;
+                    cN_main = cN;
                     break;
                 }
                 const double gam_b = gam;                                                        // :136
@@ -239,7 +273,7 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
             }
             if (stopped) continue;
             // ---- main step :149-154 ----
-            const double r = __ddiv_rn(hg, gam), cN = __ddiv_rn(hg, p.Nd);
+            const double r = r_main, cN = cN_main;   // γ̂/γ_i and γ̂/N of the accepted trial
             const double cnew = loss_coef<LOSS>(u, tb, tl);
 #pragma unroll
             for (int q = 0; q < CPT; ++q) {
@@ -411,7 +445,7 @@ int run_seq_adaptive(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double
     a.rec = c->rec; a.ld = c->ld; a.d_pad = c->d_pad; a.dc = sh.dc; a.idx = idx_prepared; a.K = K;
     a.table = c->table; a.ad = c->adapt; a.scal = c->adapt_scal; a.counters = c->adapt_counters;
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_av = ctx_vec(c, CIAO_VEC_AV);
-    a.Nd = (double)c->N_total; a.alpha = alpha; a.tol_b = tol_b; a.npart_pad = sh.npart_pad; a.reg = c->reg;
+    a.Nd = (double)c->N_total; a.alpha = alpha; a.tol_b = tol_b; a.npart_pad = sh.npart_pad; a.zero = 0; a.reg = c->reg;
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
     int rc;
     switch (sh.cpt) {

@@ -139,5 +139,26 @@ c5["cpu_proshi_us_per_block"] = 1e6 * (time.perf_counter() - t0) / len(batches)
 out["C5_sharing_proshi"] = c5
 print(json.dumps(c5), flush=True)
 
+# ------------------------------------------------------------------ adaptive Finito (Finito_adaptive.jl) on a Lasso, N = 2^18, d = 1024
+from ciaoalgorithms_jl_b200.sampling import AdaptiveSweeper  # noqa: E402
+N, d = (1 << 14, 1024) if small else (1 << 18, 1024)
+e = Engine(0)
+e.gen_synthetic(L.SYNTH_LASSO, N, d, 0x5EED0003, scale=float(N))
+e.set_reg(L.REG_NORML1, N / 100.0)
+x0 = np.full(d, 0.01)
+t0 = time.perf_counter()
+e.finito_adaptive_init(x0, 0.999, 1e-9)
+init_s = time.perf_counter() - t0
+f0 = sum(e.objective(x0))
+idx = AdaptiveSweeper(N, 1, HostRNG(0x1D0006)).take(2 * N)
+done = e.finito_adaptive_steps(idx)
+ms = e.last_timing().last_seq_ms
+_, _, _, hat, nbt = e.finito_adaptive_get(gamma=False)
+ad = {"N": N, "d": d, "init_s": init_s, "steps": done, "us_per_step": 1e3 * ms / max(done, 1), "linesearch_reductions": nbt,
+      "objective0": f0, "objective": sum(e.objective(e.get_vec(L.VEC_Z))), "hat_gamma": hat}
+e.close()
+out["adaptive_finito_lasso"] = ad
+print(json.dumps(ad), flush=True)
+
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w"), indent=1)
