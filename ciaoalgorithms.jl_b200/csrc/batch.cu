@@ -31,7 +31,7 @@ template <int CPT, int MODE, int LOSS>
 __global__ void __launch_bounds__(256, 2) batch_pass_kernel(const BatchArgs p) {
     constexpr int RPG = 16 / CPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.stages;
     const size_t stage_doubles = (size_t)RPG * p.ld;
     double *ring = reinterpret_cast<double *>(smem_raw);
@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256, 2) batch_pass_kernel(const BatchArgs p) {
     const int64_t n_groups = (p.n_rows + RPG - 1) / RPG;
     const int64_t my_count = (blockIdx.x < n_groups) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     uint64_t policy = 0;
+    for (int i = tid; i < 2 * RPG * 32 * 2; i += T) red[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
@@ -119,8 +120,8 @@ __global__ void __launch_bounds__(256, 2) batch_pass_kernel(const BatchArgs p) {
         }
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
-            p0[r] = warp_sum(p0[r]);
-            if (MODE == BATCH_LFINITO) p1[r] = warp_sum(p1[r]);
+            p0[r] = warp_sum_mma(p0[r], lane);
+            if (MODE == BATCH_LFINITO) p1[r] = warp_sum_mma(p1[r], lane);
             if (lane == 0) {
                 red[((par * RPG + r) * 32 + warp) * 2] = p0[r];
                 red[((par * RPG + r) * 32 + warp) * 2 + 1] = p1[r];
@@ -130,12 +131,10 @@ __global__ void __launch_bounds__(256, 2) batch_pass_kernel(const BatchArgs p) {
         if (tid == 0 && it + S < my_count) issue(it + S);
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
-            double u0 = 0.0, u1 = 0.0;
-            const double *rr = red + (par * RPG + r) * 32 * 2;
-            for (int w = 0; w < W; ++w) {
-                u0 += rr[2 * w];
-                u1 += rr[2 * w + 1];
-            }
+            // warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp
+            const double2 pr = *reinterpret_cast<const double2 *>(red + ((par * RPG + r) * 32 + lane) * 2);
+            const double u0 = warp_sum_mma(pr.x, lane);
+            const double u1 = (MODE == BATCH_LFINITO) ? warp_sum_mma(pr.y, lane) : 0.0;
             if (r >= rows) continue;
             const double cz = loss_coef<LOSS>(u0, tb[r], tl[r]);
             if (MODE == BATCH_FINITO) {  // Finito_basic.jl:112-116
@@ -270,7 +269,7 @@ template <int CPT, int MODE, int LOSS>
 __global__ void __launch_bounds__(256, 2) batch_persistent_kernel(const BatchPArgs p) {
     constexpr int RPG = 16 / CPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.stages;
     const int64_t G = gridDim.x, bid = blockIdx.x;
     const size_t stage_doubles = (size_t)RPG * p.ld;
@@ -280,6 +279,7 @@ __global__ void __launch_bounds__(256, 2) batch_persistent_kernel(const BatchPAr
     uint64_t *full = reinterpret_cast<uint64_t *>(rsm + 9 * 33 + 1);
 
     uint64_t policy = 0;
+    for (int i = tid; i < 2 * RPG * 32 * 2; i += T) red[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(256, 2) batch_persistent_kernel(const BatchPAr
             }
 #pragma unroll
             for (int r = 0; r < RPG; ++r) {
-                p0[r] = warp_sum(p0[r]);
-                if (MODE == BATCH_LFINITO) p1[r] = warp_sum(p1[r]);
+                p0[r] = warp_sum_mma(p0[r], lane);
+                if (MODE == BATCH_LFINITO) p1[r] = warp_sum_mma(p1[r], lane);
                 if (lane == 0) {
                     red[((par * RPG + r) * 32 + warp) * 2] = p0[r];
                     red[((par * RPG + r) * 32 + warp) * 2 + 1] = p1[r];
@@ -390,12 +390,10 @@ __global__ void __launch_bounds__(256, 2) batch_persistent_kernel(const BatchPAr
             if (tid == 0 && pb < p.n_batches) issue();  // the slot just read is free: prefetch runs ahead across batch boundaries
 #pragma unroll
             for (int r = 0; r < RPG; ++r) {
-                double u0 = 0.0, u1 = 0.0;
-                const double *rr = red + (par * RPG + r) * 32 * 2;
-                for (int w = 0; w < W; ++w) {
-                    u0 += rr[2 * w];
-                    u1 += rr[2 * w + 1];
-                }
+                // warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp
+                const double2 pr = *reinterpret_cast<const double2 *>(red + ((par * RPG + r) * 32 + lane) * 2);
+                const double u0 = warp_sum_mma(pr.x, lane);
+                const double u1 = (MODE == BATCH_LFINITO) ? warp_sum_mma(pr.y, lane) : 0.0;
                 if (r >= rows) continue;
                 const double cz = loss_coef<LOSS>(u0, tb[r], tl[r]);
                 if (MODE == BATCH_FINITO) {  // Finito_basic.jl:112-116

@@ -37,7 +37,7 @@ template <int CPT, int MODE, int LOSS>
 __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
     constexpr int RPG = 16 / CPT;  // rows per group: RPG·CPT = 16 doubles of row data per thread
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+    const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.stages;
     const size_t stage_doubles = (size_t)RPG * p.ld;
     double *ring = reinterpret_cast<double *>(smem_raw);
@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
     const int64_t my_count = (blockIdx.x < n_groups) ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     uint64_t policy = 0;
+    for (int i = tid; i < 2 * RPG * 32; i += T) red[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
         }
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
-            pd[r] = warp_sum(pd[r]);
+            pd[r] = warp_sum_mma(pd[r], lane);   // tensor-core sum: 3 instructions instead of 5 shuffle+add rounds
             if (lane == 0) red[(par * RPG + r) * 32 + warp] = pd[r];
         }
         __syncthreads();
@@ -127,9 +128,8 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
 
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
-            double u = 0.0;
-            const double *rr = red + (par * RPG + r) * 32;
-            for (int w = 0; w < W; ++w) u += rr[w];
+            // the W warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp → identical bits
+            const double u = warp_sum_mma(red[(par * RPG + r) * 32 + lane], lane);
             if (r >= rows) continue;
             if (MODE == PASS_NORMS) {
                 if (tid == 0) fsum = fmax(fsum, u);

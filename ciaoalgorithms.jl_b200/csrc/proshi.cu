@@ -364,7 +364,6 @@ static void grid2d(ciao_ctx *c, int64_t N, int64_t n_pad, dim3 *grid, int *G) {
 
 // leaves Σ (column sums) in c->partial[0..n_pad)
 static int reduce_partials(ciao_ctx *c, int G) {
-    const int nb = (int)((c->d_pad + 255) / 256);
     launch_reduce_ws(c, c->ws, c->ws, G, c->partial, c->partial + c->d_pad, 0, 1);
     CUDA_TRY(cudaGetLastError());
     c->timing.launches += 1;
