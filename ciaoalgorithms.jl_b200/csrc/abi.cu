@@ -315,7 +315,7 @@ extern "C" int ciao_set_tuning(ciao_ctx *c, int pass_threads, int pass_stages, i
     if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_tuning: null context");
     if (seq_cluster != 0 && seq_cluster != 1 && seq_cluster != 2 && seq_cluster != 4 && seq_cluster != 8 && seq_cluster != 16)
         CIAO_FAIL(CIAO_ERR_INVALID, "seq_cluster must be 0, 1, 2, 4, 8 or 16");
-    if (pass_threads < 0 || pass_threads > 512 || seq_threads < 0 || seq_threads > 512 || pass_stages < 0 || pass_ctas_per_sm < 0 || pass_ctas_per_sm > 4)
+    if (pass_threads < 0 || pass_threads > 512 || seq_threads < 0 || seq_threads > 512 || pass_stages < 0 || pass_ctas_per_sm < 0 || pass_ctas_per_sm > 8)
         CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_tuning: value out of range");
     c->pass_threads = pass_threads; c->pass_stages = pass_stages; c->pass_ctas = pass_ctas_per_sm;
     c->seq_cluster = seq_cluster; c->seq_threads = seq_threads;

@@ -255,7 +255,13 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     if (c->loss_kind != CIAO_LOSS_LS && c->loss_kind != CIAO_LOSS_LOGISTIC)
         CIAO_FAIL(CIAO_ERR_STATE, "row pass: no row problem set (ciao_set_rows / ciao_gen_synthetic first)");
     const int64_t d_pad = c->d_pad;
-    int T_target = c->pass_threads > 0 ? c->pass_threads : 256;
+    // Launch shape (scripts/k2_tune.py, gpurun_out/k2_tune.log: sweeps at d = 512 … 4096, 8.6 GB per pass).  A row should be one
+    // group (16 columns per thread, one block reduction per 16 elements of work) and an SM should hold ≈ 512 threads in as many
+    // small CTAs as that takes, each with a 2-stage ring: d = 1024 runs at 6.3 TB/s with 64 threads × 8 CTAs/SM against 3.1 TB/s
+    // with 256 × 2; d = 4096 is 256 × 2 either way (7.0 vs 6.7 TB/s with 2 instead of 3 stages).  The table-init modes also
+    // write N×d and prefer twice the threads per SM in CTAs of d/8 threads.
+    const bool init_mode = mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT;
+    int T_target = c->pass_threads > 0 ? c->pass_threads : (init_mode ? (int)std::min<int64_t>(256, std::max<int64_t>(64, d_pad / 8)) : 64);
     int cpt = 2;
     while (cpt < 16 && (d_pad + cpt - 1) / cpt > T_target) cpt *= 2;
     int64_t Tn = ((d_pad + cpt - 1) / cpt + 31) / 32 * 32;
@@ -263,10 +269,10 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     const int T = (int)Tn;
     const int rpg = 16 / cpt;
     const size_t stage_bytes = (size_t)rpg * c->ld * sizeof(double);
-    const int ctas_per_sm = c->pass_ctas > 0 ? c->pass_ctas : 2;  // 2 × 3 stages beat 1 × 6 (profiles/tune_r1.md)
+    const int ctas_per_sm = c->pass_ctas > 0 ? c->pass_ctas : std::max(1, std::min(8, (init_mode ? 1024 : 512) / T));
     const size_t fixed = 2 * rpg * 32 * sizeof(double) + 16 * sizeof(uint64_t) + 256;
     const size_t budget = (size_t)(227 * 1024) / ctas_per_sm - (ctas_per_sm > 1 ? 1024 : 0);
-    int S = c->pass_stages > 0 ? c->pass_stages : 8;
+    int S = c->pass_stages > 0 ? c->pass_stages : (ctas_per_sm > 1 ? 2 : 3);
     while (S > 1 && (size_t)S * stage_bytes + fixed > budget) --S;
     if ((size_t)S * stage_bytes + fixed > budget) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "row pass: stage does not fit shared memory");
     if (S > 16) S = 16;
