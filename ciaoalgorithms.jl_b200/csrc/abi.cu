@@ -790,7 +790,7 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
             if (c->batch_persistent && nbw > 1 && nbw < ((int64_t)1 << 22)) {   // all batches in one cooperative launch
                 const int64_t *win_dev;
                 CIAO_TRY(upload_ptr(c, win.data(), 2 * nbw, &win_dev));
-                rc = run_batch_sequence(c, BATCH_FINITO, win_dev, win_dev + nbw, nbw);
+                rc = run_batch_sequence(c, BATCH_FINITO, win_dev, win_dev + nbw, nbw, longest);
                 if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
             }
             if (rc == CIAO_ERR_UNSUPPORTED)
@@ -855,7 +855,7 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
             const int64_t *win_dev;
             CIAO_TRY(upload_ptr(c, win.data(), 2 * n_batches, &win_dev));
             CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));          // :92 of the first batch; later ones in the kernel
-            rc = run_batch_sequence(c, BATCH_LFINITO, win_dev, win_dev + n_batches, n_batches);
+            rc = run_batch_sequence(c, BATCH_LFINITO, win_dev, win_dev + n_batches, n_batches, r);
             if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
         }
         if (rc == CIAO_ERR_UNSUPPORTED)

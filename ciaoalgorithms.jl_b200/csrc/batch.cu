@@ -266,7 +266,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int tar
 }
 
 template <int CPT, int MODE, int LOSS>
-__global__ void __launch_bounds__(256, 2) batch_persistent_kernel(const BatchPArgs p) {
+__global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs p) {
     constexpr int RPG = 16 / CPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(256, 2) batch_persistent_kernel(const BatchPAr
         // sectors); thread (col, slice) sums the CTA partials slice, slice + NS, … with four independent chains, the slices
         // are combined by shuffles inside a warp and through shared memory across the 8 warps — always in the same order
         {
-            const int RC = p.red_cols, NS = 256 / RC;
+            const int RC = p.red_cols, NS = T / RC, Wn = T >> 5;
             const int cl = tid % RC, sl = tid / RC;
             const int64_t j = bid * RC + cl;
             const bool jv = j < p.d_pad;
@@ -452,22 +452,20 @@ __global__ void __launch_bounds__(256, 2) batch_persistent_kernel(const BatchPAr
             if (lane < RC) rsm[warp * 33 + lane] = sacc;
             double f = 0.0;
             if (MODE == BATCH_LFINITO) {  // Σ γ̂/γ_i of the batch: every CTA needs it; thread t takes fws[t], fws[t+256], …
-                for (int64_t q = tid; q < G; q += 256) f += __ldcg(p.fws + q);
+                for (int64_t q = tid; q < G; q += T) f += __ldcg(p.fws + q);
                 f = warp_sum(f);
                 if (lane == 0) rsm[8 * 33 + warp] = f;
             }
             __syncthreads();
             if (tid < RC && jv) {
                 double t = 0.0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) t += rsm[w * 33 + tid];
+                for (int w = 0; w < Wn; ++w) t += rsm[w * 33 + tid];
                 double anew = __dadd_rn(__ldcg(p.av + j), t);
                 const double lo = p.reg.lo_v ? p.reg.lo_v[j] : p.reg.lo_s, hi = p.reg.hi_v ? p.reg.hi_v[j] : p.reg.hi_s;
                 const double gl = p.hat_gamma * p.reg.lambda;
                 if (MODE == BATCH_LFINITO) {
                     double fs = 0.0;
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) fs += rsm[8 * 33 + w];
+                    for (int w = 0; w < Wn; ++w) fs += rsm[8 * 33 + w];
                     anew = __dadd_rn(anew, __dmul_rn(fs, __dsub_rn(__ldcg(p.z + j), p.zf[j])));              // :98
                     __stcg(p.av + j, anew);
                     if (b + 1 < p.n_batches) __stcg(p.z + j, prox_rt(p.reg.kind, anew, gl, lo, hi));          // :92 of the next batch
@@ -536,10 +534,13 @@ int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
     return CIAO_OK;
 }
 
+static int g_batch_max_ctas = 2;  // resident CTAs per SM of the persistent kernel (set by run_batch_sequence)
+
 // All batches in one cooperative launch.  rows/lens: device arrays of n_batches batch windows.  Returns CIAO_ERR_UNSUPPORTED
 // when a cooperative grid of 2 CTAs/SM is not available (the caller then falls back to one pass per batch).
 template <int CPT, int MODE, int LOSS>
 static int launch_batch_persistent(ciao_ctx *c, BatchPArgs &a, int T, size_t smem) {
+    const int a_max_ctas = g_batch_max_ctas;
     auto kern = batch_persistent_kernel<CPT, MODE, LOSS>;
     static size_t configured[CIAO_MAX_DEVICES] = {};
     if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
@@ -549,7 +550,7 @@ static int launch_batch_persistent(ciao_ctx *c, BatchPArgs &a, int T, size_t sme
     int occ = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, T, smem));
     if (occ < 1) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "persistent minibatch kernel does not fit on an SM");
-    const int grid = std::min(occ, 2) * c->num_sms;
+    const int grid = std::min(occ, a_max_ctas) * c->num_sms;
     const size_t need = ((size_t)grid * a.d_pad + grid + 16) * sizeof(double);
     if (need > c->ws_bytes) {
         if (c->ws) cudaFree(c->ws);
@@ -561,6 +562,7 @@ static int launch_batch_persistent(ciao_ctx *c, BatchPArgs &a, int T, size_t sme
     a.ws = c->ws; a.fws = c->ws + (size_t)grid * a.d_pad;
     int rc_cols = 4;
     while (rc_cols < 32 && (int64_t)rc_cols * grid < a.d_pad) rc_cols *= 2;
+    if (rc_cols > T) rc_cols = T;
     if ((int64_t)rc_cols * grid < a.d_pad) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "persistent minibatch kernel: d too large for the distributed reduction");
     a.red_cols = rc_cols;
     void *args[] = {(void *)&a};
@@ -575,19 +577,27 @@ static int launch_batch_persistent_loss(ciao_ctx *c, BatchPArgs &a, int T, size_
 }
 
 // b_lo_dev / b_n_dev: device arrays (n_batches) of batch windows; z (and z_full for LFinito) as the first batch needs them
-int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int64_t *b_n_dev, int64_t n_batches) {
+int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int64_t *b_n_dev, int64_t n_batches, int64_t batch_rows) {
     if (n_batches <= 0) return CIAO_OK;
     const int64_t d_pad = c->d_pad;
+    // scripts/batch_probe.py at C2: 128 threads (8 columns each) beat 256 for batches of 4096 rows (170 vs 159 Finito epochs/s,
+    // 219 vs 191 LFinito sweeps/s) and lose for batches of 512 (52 vs 58)
+    int T_target = (batch_rows >= 2048 && d_pad <= 2048) ? 128 : 256;
+    if (const char *tv = getenv("CIAO_BATCH_T")) T_target = std::max(32, std::min(256, atoi(tv)));
     int cpt = 2;
-    while (cpt < 16 && (d_pad + cpt - 1) / cpt > 256) cpt *= 2;
+    while (cpt < 16 && (d_pad + cpt - 1) / cpt > T_target) cpt *= 2;
     const int64_t Tn = ((d_pad + cpt - 1) / cpt + 31) / 32 * 32;
     if (Tn > 256) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "minibatch pass: d = %lld exceeds 4096", (long long)c->d);
-    const int T = 256, rpg = 16 / cpt;   // the distributed reduction wants 256 threads; extra threads own no columns
+    const int T = (int)std::max<int64_t>(Tn, 32), rpg = 16 / cpt;
     const size_t stage_bytes = (size_t)rpg * c->ld * sizeof(double);
     const size_t fixed = (2 * rpg * 32 * 2 + 9 * 33 + 1) * sizeof(double) + 16 * sizeof(uint64_t) + 256;
+    int max_ctas = 2;
+    if (const char *cv = getenv("CIAO_BATCH_CTAS")) max_ctas = std::max(1, std::min(8, atoi(cv)));
     int S = 3;
-    while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)110 * 1024) --S;
+    if (const char *sv = getenv("CIAO_BATCH_STAGES")) S = std::max(1, std::min(8, atoi(sv)));
+    while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)(220 * 1024) / max_ctas) --S;
     const size_t smem = (size_t)S * stage_bytes + fixed;
+    g_batch_max_ctas = max_ctas;
     if (!c->grid_bar) CUDA_TRY(cudaMalloc(&c->grid_bar, 64));
     CUDA_TRY(cudaMemsetAsync(c->grid_bar, 0, 64, c->stream));
     BatchPArgs a;

@@ -1,0 +1,17 @@
+"""C2 minibatch sweeps (Finito / LFinito, batch 4096 and 512) through the persistent kernel; shape knobs via env."""
+import os, sys, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); import ciao_pkg; ciao_pkg.load()
+from ciaoalgorithms_jl_b200 import _lib as L
+from ciaoalgorithms_jl_b200.engine import Engine
+from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, csr
+N, d = 1 << 20, 1024
+e = Engine(0); e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0); e.set_reg(L.REG_NORML1, 1.0 / N)
+Lmax = 0.25 * e.max_row_sqnorm(); gam = np.full(N, 0.999 * N / Lmax); hat = 1 / np.sum(1 / gam)
+tag = " ".join(f"{k[11:]}={os.environ[k]}" for k in ("CIAO_BATCH_T", "CIAO_BATCH_CTAS", "CIAO_BATCH_STAGES", "CIAO_BATCH_PER_LAUNCH") if k in os.environ) or "default"
+for r in (4096, 512):
+    e.finito_init(np.ones(d), gam, hat)
+    sw = BatchSweeper(N, r, 2, HostRNG(1)); idx, bp = csr(sw.take(sw.d))
+    e.finito_steps(idx, bp); e.finito_steps(idx, bp); tf = e.last_timing().last_seq_ms
+    e.lfinito_init(np.ones(d), gam, hat)
+    e.lfinito_outer(np.arange(1, sw.d + 1), r); e.lfinito_outer(np.arange(1, sw.d + 1), r); tl = e.last_timing().last_seq_ms
+    print(f"[{tag}] batch {r}: finito {1e3 / tf:.1f} epochs/s ({1e3 * tf / sw.d:.1f} us/batch), lfinito {1e3 / tl:.1f} sweeps/s ({1e3 * tl / sw.d:.1f} us/batch)", flush=True)
