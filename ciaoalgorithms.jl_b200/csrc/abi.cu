@@ -94,6 +94,7 @@ static void free_problem(ciao_ctx *c) {
     cudaFree(c->rec); cudaFree(c->qd); cudaFree(c->ql); cudaFree(c->vecs); cudaFree(c->table);
     cudaFree(c->gamma_dev); cudaFree(c->partial); cudaFree(c->reg_bounds); cudaFree(c->ss); cudaFree(c->adapt); cudaFree(c->adapt_scal); cudaFree(c->adapt_counters); cudaFree(c->gpair);
     c->rec = c->qd = c->ql = c->vecs = c->table = c->gamma_dev = c->partial = c->reg_bounds = c->ss = c->adapt = c->adapt_scal = c->gpair = nullptr;
+    c->ss_cap = 0;
     c->adapt_counters = nullptr;
     c->reg = RegParams{CIAO_REG_ZERO, 0, 0, 0, nullptr, nullptr};
     c->loss_kind = -1;

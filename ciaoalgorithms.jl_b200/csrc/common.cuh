@@ -97,6 +97,7 @@ struct ciao_ctx {
     // → partial-sector RMW, +1.4 ms per pass.)  Single-process, un-windowed passes only; env CIAO_CACHE_CZ=0 disables it.
     bool cache_cz = true;
     double *ss = nullptr;
+    int64_t ss_cap = 0;                // rows the ss allocation holds
     // Debug/test knob (env CIAO_SEQ_TABLE_LDG=1): SAGA/Finito table rows by register prefetch instead of the TMA-staged
     // ring (the path taken anyway when the ring does not fit in shared memory).
     bool seq_table_ldg = false;

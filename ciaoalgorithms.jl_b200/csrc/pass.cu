@@ -295,10 +295,26 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     a.ss_out = nullptr;
     // the per-row step scalars for the inner kernels: all rows in one process, or — replicated rows, uniformly windowed
     // passes — each rank its window, all-gathered after the kernel
-    const bool gather_ss = cache_cz && mode == PASS_GRAD && windowed && c->world > 1 && c->win_uniform;
+    const bool gather_win = cache_cz && mode == PASS_GRAD && windowed && c->world > 1 && c->win_uniform;
+    // … or row-sharded data with the peers' shards attached (ciao_attach_peer_rows): every rank knows all shard bounds, so
+    // all ranks take the same decision; the array is indexed by the global row
+    bool gather_shard = cache_cz && mode == PASS_GRAD && !windowed && c->world > 1 && c->peers.n == c->world &&
+                        c->N_total % c->world == 0 && c->n_rows == c->N_total / c->world;
+    for (int sidx = 0; gather_shard && sidx < c->peers.n; ++sidx)
+        gather_shard = c->peers.start[sidx] == (int64_t)sidx * c->n_rows;
+    gather_shard = gather_shard && c->row0 == (int64_t)c->rank * c->n_rows;
+    const bool gather_ss = gather_win || gather_shard;
     if (cache_cz && mode == PASS_GRAD && ((!windowed && c->world == 1) || gather_ss)) {
-        if (!c->ss) CUDA_TRY(cudaMalloc(&c->ss, (size_t)(c->n_rows + 1) * 4 * sizeof(double)));
-        a.ss_out = c->ss + 4 * w0;
+        const int64_t ss_rows = gather_shard ? c->N_total : c->n_rows;
+        if (c->ss && c->ss_cap < ss_rows) {
+            cudaFree(c->ss);
+            c->ss = nullptr;
+        }
+        if (!c->ss) {
+            CUDA_TRY(cudaMalloc(&c->ss, (size_t)(ss_rows + 1) * 4 * sizeof(double)));
+            c->ss_cap = ss_rows;
+        }
+        a.ss_out = c->ss + 4 * (gather_shard ? c->row0 : w0);
     }
     if (mode == PASS_GRAD && cache_cz) c->cz_valid = a.ss_out != nullptr;
     a.d_pad = d_pad; a.x = x_dev;

@@ -94,6 +94,30 @@ def main():
         dist.barrier()
     assert rel(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) < 1e-11
 
+    # uniform shards (N divisible by the world size): the per-row step scalars c_i(z_full) of the shards are all-gathered, so
+    # the replicated inner epoch runs the one-dot step with remote rows AND remote-shard scalars
+    Nu = 3072 * world
+    shu, fullu = Engine(local), Engine(local)
+    shu.gen_synthetic(L.SYNTH_LASSO, Nu, d, seed + 2, scale=float(Nu), row0=rank * 3072, n_rows=3072)
+    fullu.gen_synthetic(L.SYNTH_LASSO, Nu, d, seed + 2, scale=float(Nu))
+    for eng in (shu, fullu):
+        eng.set_reg(L.REG_NORML1, Nu / 100.0)
+    shu.comm_init(bytes(uid2(rank)), rank, world)
+    hu = [None] * world
+    dist.all_gather_object(hu, shu.rows_ipc_handle())
+    shu.attach_peer_rows(hu, [r * 3072 for r in range(world)], [3072] * world, rank)
+    gu = 1.0 / (7.0 * Nu * fullu.max_row_sqnorm())
+    rc, rd = HostRNG(11), HostRNG(11)
+    shu.svrg_init(np.zeros(d), gu, False)
+    fullu.svrg_init(np.zeros(d), gu, False)
+    for _ in range(2):
+        shu.svrg_epoch(rc.rand_vec(Nu, Nu // 2))
+        fullu.svrg_epoch(rd.rand_vec(Nu, Nu // 2))
+    assert rel(shu.get_vec(L.VEC_Z_FULL), fullu.get_vec(L.VEC_Z_FULL)) < 1e-11
+    dist.barrier()
+    shu.close()
+    fullu.close()
+
     # replicated rows, windowed passes (bench.py --gpus G): every rank streams N/G rows, the d-vector is all-reduced and the
     # per-row step scalars c_i(z_full) of the windows are all-gathered for the replicated inner epoch
     Nw = 4096 * world
