@@ -44,7 +44,24 @@ class DeviceProblem:
         self.engine = engine
 
 
-def _setup_engine(F, g, N, device=0):
+def _element_type(x0):
+    """The reference is generic in the element type (test_lasso.jl:3 runs Float32/Float64/ComplexF32/ComplexF64).  The engine
+    computes in fp64; real single-precision problems are accepted and their solutions handed back in the caller's type
+    (`eltype(x) == T`, test_lasso.jl:74), complex ones are outside its scope."""
+    dt = np.asarray(x0).dtype
+    if np.issubdtype(dt, np.complexfloating):
+        raise ops.UnsupportedOperator("complex element types are outside the engine's scope (SURVEY.md §8f)")
+    return np.dtype(np.float32) if dt == np.float32 else np.dtype(np.float64)
+
+
+def _setup_engine(F, g, N, device=0, x0=None):
+    out_dtype = _element_type(x0) if x0 is not None else np.dtype(np.float64)
+    e = _setup_engine_fp64(F, g, N, device)
+    e.out_dtype = out_dtype
+    return e
+
+
+def _setup_engine_fp64(F, g, N, device=0):
     if N is None:
         raise TypeError("keyword argument N is required (SVRG.jl:52 `N = N`)")
     if isinstance(F, DeviceProblem):
@@ -71,12 +88,17 @@ class _State:
 
     def __init__(self, engine):
         self.engine = engine
-        self._host = {name: np.empty(engine.d) for name in self._vecs}
+        self._dtype = getattr(engine, "out_dtype", np.dtype(np.float64))
+        self._host = {name: np.empty(engine.d, dtype=self._dtype) for name in self._vecs}
+        self._f64 = None if self._dtype == np.float64 else np.empty(engine.d)
 
     def __getattr__(self, name):
         vecs = type(self)._vecs
         if name in vecs:
-            return self.engine.get_vec(vecs[name], self._host[name])
+            if self._f64 is None:
+                return self.engine.get_vec(vecs[name], self._host[name])
+            self._host[name][:] = self.engine.get_vec(vecs[name], self._f64)   # fp64 on the device, the caller's type outside
+            return self._host[name]
         raise AttributeError(name)
 
 
@@ -113,7 +135,7 @@ class SVRG_basic_iterable:
                 warnings.warn("convergence condition violated...provide a stepsize!")
         else:
             gamma = self.γ
-        e = _setup_engine(self.F, self.g, N, self.device)
+        e = _setup_engine(self.F, self.g, N, self.device, self.x0)
         e.svrg_init(self.x0, gamma, self.plus)                                 # :58-66
         return SVRG_basic_state(e, gamma, m)
 
@@ -176,7 +198,7 @@ class SAGA_basic_iterable:
             gamma = 1 / (16 * L_M) if self.SAG else 1 / (3 * L_M)              # :35
         else:
             gamma = self.γ
-        e = _setup_engine(self.F, self.g, self.N, self.device)
+        e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
         e.saga_init(self.x0, gamma, self.SAG)                                  # :41-48
         return SAGA_basic_state(e, gamma)
 
@@ -255,7 +277,7 @@ class FINITO_basic_iterable:
         if gam is None:
             return None
         hat = 1 / np.sum(1 / gam)                                              # Finito_basic.jl:82
-        e = _setup_engine(self.F, self.g, self.N, self.device)
+        e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
         e.finito_init(self.x0, gam, hat)                                       # :76-84
         return FINITO_basic_state(e, gam, hat, BatchSweeper(self.N, self.batch, self.sweeping, self.rng or GLOBAL_RNG))
 
@@ -290,7 +312,7 @@ class FINITO_LFinito_iterable(FINITO_basic_iterable):
         if gam is None:
             return None
         hat = 1 / np.sum(1 / gam)                                              # Finito_LFinito.jl:66
-        e = _setup_engine(self.F, self.g, self.N, self.device)
+        e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
         e.lfinito_init(self.x0, gam, hat)                                      # :67-72
         return FINITO_LFinito_state(e, gam, hat, LFinitoSweeper(self.N, self.batch, self.sweeping, self.rng or GLOBAL_RNG))
 
@@ -341,7 +363,7 @@ class FINITO_adaptive_iterable:
         self.sweeping, self.α, self.rng, self.device = sweeping, alpha, rng, device
 
     def _init(self):
-        e = _setup_engine(self.F, self.g, self.N, self.device)
+        e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
         e.finito_adaptive_init(self.x0, self.α, self.tol_b)                    # :59-99
         return FINITO_adaptive_state(e, AdaptiveSweeper(self.N, self.sweeping, self.rng or GLOBAL_RNG))
 
@@ -406,7 +428,7 @@ class Proshi_basic_iterable(FINITO_basic_iterable):
         if gam is None:
             return None
         hat = float(np.sum(gam))                                               # ProShI_basic.jl:82
-        e = _setup_engine(self.F, self.g, self.N, self.device)
+        e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
         e.proshi_init(self.x0, gam, hat)                                       # :76-86
         return Proshi_basic_state(e, gam, hat, BatchSweeper(self.N, self.batch, self.sweeping, self.rng or GLOBAL_RNG))
 

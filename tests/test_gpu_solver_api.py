@@ -74,6 +74,18 @@ def test_lasso_adaptive_iterator_and_early_end():                               
     assert n == 1
 
 
+def test_lasso_float32_problem_keeps_its_element_type():                        # test_lasso.jl:3 (T = Float32), :74 eltype(x) == T
+    fx, F, g = lasso_problem()
+    N = fx["N"]
+    F32 = [ops.LeastSquares(fx["A"][i:i + 1, :].astype(np.float32), fx["b"][i:i + 1].astype(np.float32), np.float32(N)) for i in range(N)]
+    x0 = np.zeros(fx["n"], dtype=np.float32)
+    for solver in (S.Finito(maxit=1000, sweeping=2), S.SAGA(maxit=1000, gamma=1 / (3 * fx["L"].max())), S.Finito(maxit=1000, adaptive=True)):
+        x, _ = solver(x0, F=F32, g=g, L=fx["L"].astype(np.float32), N=N, rng=HostRNG(1))
+        assert x.dtype == np.float32 and fx["cost"](x.astype(np.float64)) - fx["f_star"] < 1e-3   # data rounded to single precision
+    with pytest.raises(ops.UnsupportedOperator):
+        S.SAGA(gamma=0.1)(x0.astype(np.complex64), F=F32, g=g, N=N)
+
+
 def test_lasso_scalar_gamma_and_scalar_L():                                     # :128-140
     fx, F, g = lasso_problem()
     N = fx["N"]
