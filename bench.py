@@ -171,7 +171,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "epochs/s (Lasso 4M x 4096 fp64, SVRG++)", "value": cb["value"], "unit": "epochs/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * s_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"C3 Lasso N=2^{args.rows_log2} d={d} SVRG++ m0=N/16 (CPU sample of 2^{args.cpu_rows_log2} rows)"},
+            "config": {"workload": (f"C3 Lasso N=2^{args.rows_log2} d={d} fp64 SVRG++ gamma=1/(7 L_max) m=N/16*2^(k mod 5): persistent inner epoch + "
+                                    f"full-gradient pass"),
+                       "sample": f"the reference's loop (CPU restatement) on 2^{args.cpu_rows_log2} rows of the same generator, same schedule, "
+                                 f"extrapolated per component gradient to N=2^{args.rows_log2}",
+                       "epoch": "N component-gradient evaluations; step = (m + N)/N epochs", "seeds": [SEED_DATA, SEED_IDX]},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
