@@ -672,3 +672,22 @@ def test_full_scale_table_invariants_c2_c5():
         assert rel(e.get_vec(L.VEC_AV), e.table_colsum()) < 1e-9
         z = e.get_vec(L.VEC_Z)
         assert np.all(np.isfinite(z))
+
+
+def test_soft_threshold_bits_match_the_reference_formula():
+    """prox_NormL1 on the device is assembled from |x| − γλ and integer selects; it must give the bits of the reference's
+    x + (x ≤ −γλ ? γλ : (x ≥ γλ ? −γλ : −x)) (ProximalOperators NormL1, restated in the oracle) — including +0 at and
+    inside the threshold.  Exercised through SAGA's z = prox_g((1 − γ)·x0, γ) (SAGA_basic.jl:48) with γ = 1/2, λ = 2."""
+    d = 16
+    x0 = np.array([2.0, -2.0, 0.0, -0.0, 1.0, -1.0, 7.0, -7.0, 2.0 + 2 ** -50, -2.0 - 2 ** -50, 2.0 - 2 ** -51, -2.0 + 2 ** -51,
+                   1e-310, -1e-310, 1e300, -1e300])
+    rs = np.random.RandomState(0)
+    A, b = rs.randn(4, d), rs.randn(4)
+    p = orc.Problem(orc.LOSS_LS, A, b, np.ones(4)).set_reg(orc.REG_NORML1, lam=2.0)
+    want = p.prox(0.5 * x0, 0.5)
+    with Engine(0) as e:
+        e.set_rows(L.LOSS_LS, A, b, 1.0)
+        e.set_reg(L.REG_NORML1, 2.0)
+        e.saga_init(x0, 0.5, False)
+        got = e.get_vec(L.VEC_Z)
+    assert np.array_equal(got.view(np.int64), want.view(np.int64)), (got, want)
