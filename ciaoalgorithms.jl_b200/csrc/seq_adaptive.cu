@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
         double gl = __dmul_rn(hg, p.reg.lambda);
         const double thr = __ddiv_rn(p.tol_b, p.Nd);                           // :124 tol_b / N
         const double half_N_alpha = __dmul_rn(__dmul_rn(0.5, p.Nd), p.alpha);  // :131 0.5 * N * α
+        const double rNd = __drcp_rn(p.Nd);
         const int E = p.npart_pad >> 5;
         double *hist_w = hist + (size_t)warp * AD_HIST * 4;
         uint32_t send_dst[2], send_bar[2];
@@ -169,7 +170,14 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
             load(0, nxt);
             have_next = true;
         }
+#ifdef CIAO_SEQ_PROFILE
+        long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
         for (int64_t k = 0; k < K; ++k) {
+            PROF_T(t_0);
+#ifdef CIAO_SEQ_PROFILE
+            long long t_last = t_0;
+#endif
             if (!have_next) load(k, nxt);   // only after a stop (slots are still drained) or when the prefetch below was skipped
             have_next = false;
             if (stopped) continue;
@@ -204,6 +212,8 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                     stopped = true;
                     break;
                 }
+                PROF_T(t_a);
+                PROF_ADD(0, t_last, t_a);   // everything before the partial sums (first trial: step setup; later: backtracking)
                 double p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
                 for (int q = 0; q < CPT; ++q) {
@@ -215,21 +225,29 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                 p2 = warp_sum_mma(p2, lane);
                 p3 = warp_sum_mma(p3, lane);
                 const int par = (int)(ex & 1);
-                if (lane < C) {
-                    st_async_v2f64(send_dst[par], p1, p2, send_bar[par]);
-                    st_async_v2f64(send_dst[par] + 16, p3, 0.0, send_bar[par]);
+                {   // selects, not array indexing by a run-time parity (that puts the addresses in local memory)
+                    const uint32_t sd = par ? send_dst[1] : send_dst[0], sb = par ? send_bar[1] : send_bar[0];
+                    if (lane < C) {
+                        st_async_v2f64(sd, p1, p2, sb);
+                        st_async_v2f64(sd + 16, p3, 0.0, sb);
+                    }
                 }
+                PROF_T(t_b);
                 // in the shadow of the exchange: the three divisions that depend only on γ_i and γ̂ (pinned in front of the wait
                 // through the parity operand, as in seq_impl.cuh), and the registers of the next step
-                const double coef = __ddiv_rn(half_N_alpha, gam);      // :131  0.5·N·α / γ_i
-                const double r_hg = __ddiv_rn(hg, gam);                // :149  γ̂ / γ_i
-                const double cN = __ddiv_rn(hg, p.Nd);                 // :151  γ̂ / N
+                // one reciprocal + exact-remainder corrections (div_by: the correctly rounded quotients) instead of three divisions
+                const double rgam = __drcp_rn(gam);
+                const double coef = div_by(half_N_alpha, gam, rgam);   // :131  0.5·N·α / γ_i
+                const double r_hg = div_by(hg, gam, rgam);             // :149  γ̂ / γ_i
+                const double cN = div_by(hg, p.Nd, rNd);               // :151  γ̂ / N
                 const int pin = __double2hiint(coef) ^ __double2hiint(r_hg) ^ __double2hiint(cN);
                 if (!have_next && k + 1 < K) {
                     load(k + 1, nxt);
                     have_next = true;
                 }
+                PROF_T(t_c);
                 mbar_wait(&part_bar[par], ((ex >> 1) & 1) ^ (uint32_t)(pin & p.zero));
+                PROF_T(t_d);
                 if (tid == 0) mbar_arrive_expect_tx(&part_bar[par], part_bytes);  // arm exchange ex + 2
                 double U = 0.0, Dg = 0.0, R2 = 0.0;
                 {
@@ -244,6 +262,12 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                     R2 = warp_sum_mma(R2, lane);
                 }
                 ++ex;
+                PROF_ADD(1, t_a, t_b);  // partial sums + warp sums + send
+                PROF_ADD(2, t_b, t_c);  // shadow work: divisions, next-step registers
+                PROF_ADD(3, t_c, t_d);  // remaining exchange wait
+#ifdef CIAO_SEQ_PROFILE
+                t_last = t_d;
+#endif
                 fi_z = loss_value<LOSS>(U, tb, tl);                                              // :128
                 const double nr = __dsqrt_rn(R2);
                 const double fi_model = __dadd_rn(__dadd_rn(fix, Dg), __dmul_rn(coef, __dmul_rn(nr, nr)));  // :129-132
@@ -272,6 +296,8 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                 ++nbt;
             }
             if (stopped) continue;
+            PROF_T(t_e);
+            PROF_ADD(4, t_last, t_e);  // totals + warp sums + model test of the accepted trial
             // ---- main step :149-154 ----
             const double r = r_main, cN = cN_main;   // γ̂/γ_i and γ̂/N of the accepted trial
             const double cnew = loss_coef<LOSS>(u, tb, tl);
@@ -298,6 +324,9 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                 __stcg(o + 1, make_double2(cnew, 0.0));
             }
             ++done;
+            PROF_T(t_f);
+            PROF_ADD(5, t_e, t_f);  // main update, stores, history
+            PROF_ADD(6, t_0, t_f);  // whole step
         }
 #pragma unroll
         for (int h = 0; h < H; ++h) {
@@ -308,6 +337,10 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                 p.v_av[gcol[h] + e] = av[2 * h + e];
             }
         }
+#ifdef CIAO_SEQ_PROFILE
+        if (tid == 0)
+            for (int i = 0; i < 8; ++i) g_seq_prof[rank * 8 + i] = prof_acc[i];
+#endif
         if (rank == 0 && tid == 0) {
             p.scal[0] = hg;
             p.counters[0] = done;
@@ -495,3 +528,11 @@ int run_adaptive_av(ciao_ctx *c, const double *S_dev, const double *G_dev, doubl
     c->timing.launches += 1;
     return CIAO_OK;
 }
+
+#ifdef CIAO_SEQ_PROFILE
+extern "C" int ciao_debug_seq_prof_adaptive(ciao_ctx *c, long long *out128) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(out128, g_seq_prof, 16 * 8 * sizeof(long long)));
+    return CIAO_OK;
+}
+#endif
