@@ -534,13 +534,10 @@ int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
     return CIAO_OK;
 }
 
-static int g_batch_max_ctas = 2;  // resident CTAs per SM of the persistent kernel (set by run_batch_sequence)
-
 // All batches in one cooperative launch.  rows/lens: device arrays of n_batches batch windows.  Returns CIAO_ERR_UNSUPPORTED
 // when a cooperative grid of 2 CTAs/SM is not available (the caller then falls back to one pass per batch).
 template <int CPT, int MODE, int LOSS>
-static int launch_batch_persistent(ciao_ctx *c, BatchPArgs &a, int T, size_t smem) {
-    const int a_max_ctas = g_batch_max_ctas;
+static int launch_batch_persistent(ciao_ctx *c, BatchPArgs &a, int T, size_t smem, int a_max_ctas) {
     auto kern = batch_persistent_kernel<CPT, MODE, LOSS>;
     static size_t configured[CIAO_MAX_DEVICES] = {};
     if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
@@ -571,9 +568,9 @@ static int launch_batch_persistent(ciao_ctx *c, BatchPArgs &a, int T, size_t sme
 }
 
 template <int CPT, int MODE>
-static int launch_batch_persistent_loss(ciao_ctx *c, BatchPArgs &a, int T, size_t smem) {
-    return c->loss_kind == CIAO_LOSS_LS ? launch_batch_persistent<CPT, MODE, CIAO_LOSS_LS>(c, a, T, smem)
-                                        : launch_batch_persistent<CPT, MODE, CIAO_LOSS_LOGISTIC>(c, a, T, smem);
+static int launch_batch_persistent_loss(ciao_ctx *c, BatchPArgs &a, int T, size_t smem, int max_ctas) {
+    return c->loss_kind == CIAO_LOSS_LS ? launch_batch_persistent<CPT, MODE, CIAO_LOSS_LS>(c, a, T, smem, max_ctas)
+                                        : launch_batch_persistent<CPT, MODE, CIAO_LOSS_LOGISTIC>(c, a, T, smem, max_ctas);
 }
 
 // b_lo_dev / b_n_dev: device arrays (n_batches) of batch windows; z (and z_full for LFinito) as the first batch needs them
@@ -597,7 +594,6 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     if (const char *sv = getenv("CIAO_BATCH_STAGES")) S = std::max(1, std::min(8, atoi(sv)));
     while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)(220 * 1024) / max_ctas) --S;
     const size_t smem = (size_t)S * stage_bytes + fixed;
-    g_batch_max_ctas = max_ctas;
     if (!c->grid_bar) CUDA_TRY(cudaMalloc(&c->grid_bar, 64));
     CUDA_TRY(cudaMemsetAsync(c->grid_bar, 0, 64, c->stream));
     BatchPArgs a;
@@ -608,17 +604,17 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     int rc;
     if (mode == BATCH_FINITO) {
         switch (cpt) {
-            case 2: rc = launch_batch_persistent_loss<2, BATCH_FINITO>(c, a, T, smem); break;
-            case 4: rc = launch_batch_persistent_loss<4, BATCH_FINITO>(c, a, T, smem); break;
-            case 8: rc = launch_batch_persistent_loss<8, BATCH_FINITO>(c, a, T, smem); break;
-            default: rc = launch_batch_persistent_loss<16, BATCH_FINITO>(c, a, T, smem); break;
+            case 2: rc = launch_batch_persistent_loss<2, BATCH_FINITO>(c, a, T, smem, max_ctas); break;
+            case 4: rc = launch_batch_persistent_loss<4, BATCH_FINITO>(c, a, T, smem, max_ctas); break;
+            case 8: rc = launch_batch_persistent_loss<8, BATCH_FINITO>(c, a, T, smem, max_ctas); break;
+            default: rc = launch_batch_persistent_loss<16, BATCH_FINITO>(c, a, T, smem, max_ctas); break;
         }
     } else {
         switch (cpt) {
-            case 2: rc = launch_batch_persistent_loss<2, BATCH_LFINITO>(c, a, T, smem); break;
-            case 4: rc = launch_batch_persistent_loss<4, BATCH_LFINITO>(c, a, T, smem); break;
-            case 8: rc = launch_batch_persistent_loss<8, BATCH_LFINITO>(c, a, T, smem); break;
-            default: rc = launch_batch_persistent_loss<16, BATCH_LFINITO>(c, a, T, smem); break;
+            case 2: rc = launch_batch_persistent_loss<2, BATCH_LFINITO>(c, a, T, smem, max_ctas); break;
+            case 4: rc = launch_batch_persistent_loss<4, BATCH_LFINITO>(c, a, T, smem, max_ctas); break;
+            case 8: rc = launch_batch_persistent_loss<8, BATCH_LFINITO>(c, a, T, smem, max_ctas); break;
+            default: rc = launch_batch_persistent_loss<16, BATCH_LFINITO>(c, a, T, smem, max_ctas); break;
         }
     }
     CIAO_TRY(rc);
