@@ -365,9 +365,9 @@ def main():
     clocks = sampler.summary() if rank == 0 else None
     achieved = algo_bytes / pass_ms / 1e6     # GB/s
     # dram__bytes_read.sum + dram__bytes_write.sum of row_pass_kernel from the committed `ncu --set full` capture
-    # (profiles/ncu_row_pass_r1.csv: 137.88 GB read + 0.11 GB written per launch at N=2^22, d=4096, one GPU — the writes are
+    # (profiles/ncu_row_pass_r1.csv: 137.90 GB read + 0.11 GB written per launch at N=2^22, d=4096, one GPU — the writes are
     # the 32 B/row step scalars a single-process pass leaves for the inner kernel; multi-rank passes write 12 MB); null otherwise
-    traffic = ((137.993e9 if world == 1 else 137.808e9)
+    traffic = ((138.011e9 if world == 1 else 137.899e9)
                if (rows_per_gpu == 1 << 22 and d == 4096 and (world == 1 or weak_pass)) else None)
     line = {
         "metric": ("epochs/s (full-gradient passes, 2^22-row epochs)" if weak_pass else
