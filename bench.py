@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="svrgpp", choices=["svrgpp", "fullgrad", "svrgpp-sharded"])
+    ap.add_argument("--workload", default="svrgpp", choices=["svrgpp", "fullgrad", "svrgpp-sharded", "saga-init"])
     ap.add_argument("--rows-log2", type=int, default=22)
     ap.add_argument("--d", type=int, default=4096)
     ap.add_argument("--cpu-rows-log2", type=int, default=17)
@@ -218,9 +218,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    table_init = args.workload == "saga-init"   # sharded K2: SAGA table init pass (read A, write the N×d table) + allreduce
+    if table_init and args.rows_log2 == 22:
+        args.rows_log2 = 21                      # rows + table of a shard must fit: 2^21 × 4096 × 8 B × 2 = 137 GB per GPU (C4 on 8 GPUs)
     rows_per_gpu = 1 << args.rows_log2
     d = args.d
-    weak_pass = args.workload == "fullgrad"
+    weak_pass = args.workload == "fullgrad" or table_init
     sharded = args.workload == "svrgpp-sharded"      # rows sharded over the GPUs, inner epoch reads remote rows over NVLink
     N = rows_per_gpu * world if (weak_pass or sharded) else rows_per_gpu
     e = Engine(local)
@@ -260,35 +263,46 @@ def main():
     if weak_pass:
         # ---- sharded full-gradient pass alone (C4-style, weak scaling) -------------------------
         e.set_vec(L.VEC_X, np.full(d, 1e-3))
+        x_init = np.full(d, 1e-3)
+
+        def one_pass(x_host=None, out=False):
+            if table_init:                         # SAGA_basic.jl:41-48: s_i = ∇f_i(x0) for my rows, av = Σ s_i / N (allreduce), z
+                e.saga_init(x_init if x_host is None else x_host, gamma, False)
+                return e.get_vec(L.VEC_AV) if out else None
+            return e.full_gradient(x_host, 1.0 / N, out=out)
+
         for _ in range(W):
-            e.full_gradient(None, 1.0 / N, out=False)
+            one_pass()
         barrier()
         l0 = e.last_timing().launches
         pass_ms_list = []
         e.timer_begin()
         for _ in range(K):
-            e.full_gradient(None, 1.0 / N, out=False)
+            one_pass()
             pass_ms_list.append(e.last_timing().last_pass_ms)
         ms = max_over_ranks(e.timer_end())
         barrier()
         tm = e.last_timing()
         launches = tm.launches - l0
         pass_ms = max_over_ranks(float(np.mean(pass_ms_list)))
-        value = K * world / (ms / 1e3)          # epochs of 2^22 rows per second, whole job
-        out = e.full_gradient(None, 1.0 / N, out=True)
+        value = K * world * (rows_per_gpu / float(1 << 22)) / (ms / 1e3)          # epochs of 2^22 rows per second, whole job
+        out = one_pass(out=True)
         xh = torch.full((d,), 1e-3, dtype=torch.float64).pin_memory().numpy()
         barrier()
         e2e_t0 = time.perf_counter()
         e.timer_begin()
         for _ in range(K):
-            out = e.full_gradient(xh, 1.0 / N, out=True)
+            out = one_pass(xh, out=True)
         e2e_ms = max_over_ranks(e.timer_end())
-        e2e = {"value": K * world / (e2e_ms / 1e3), "unit": "epochs/s", "h2d_bytes_per_step": 8 * d, "d2h_bytes_per_step": 8 * d,
+        e2e = {"value": K * world * (rows_per_gpu / float(1 << 22)) / (e2e_ms / 1e3), "unit": "epochs/s", "h2d_bytes_per_step": 8 * d, "d2h_bytes_per_step": 8 * d,
                "wall_ms": 1e3 * (time.perf_counter() - e2e_t0)}
-        algo_bytes = rows_per_gpu * ld * 8
-        extra = {"full_gradient": {"rows_per_gpu": rows_per_gpu, "kernel_ms": pass_ms, "gbs_per_gpu": algo_bytes / pass_ms / 1e6,
-                                   "aggregate_gbs": world * rows_per_gpu * ld * 8 / (ms / K) / 1e6, "checksum": float(np.sum(out))}}
-        scaling, workload = "weak", f"C4-style sharded full-gradient pass, Lasso 2^{args.rows_log2} rows/GPU x d={d}, NCCL allreduce of the d-vector"
+        algo_bytes = rows_per_gpu * (ld + (d if table_init else 0)) * 8
+        extra = {"table_init" if table_init else "full_gradient": {"rows_per_gpu": rows_per_gpu, "kernel_ms": pass_ms, "gbs_per_gpu": algo_bytes / pass_ms / 1e6,
+                                   "aggregate_gbs": world * algo_bytes / (ms / K) / 1e6, "checksum": float(np.sum(out))}}
+        scaling = "weak"
+        workload = (f"C4-style sharded SAGA table init (read rows, write the N x d table), Lasso 2^{args.rows_log2} rows/GPU x d={d}, NCCL allreduce of the d-vector"
+                    if table_init else
+                    f"C4-style sharded full-gradient pass, Lasso 2^{args.rows_log2} rows/GPU x d={d}, NCCL allreduce of the d-vector")
         epochs_total = K * world
     else:
         # ---- SVRG++ outer iterations (C3) ---------------------------------------------------------
@@ -370,14 +384,15 @@ def main():
     traffic = ((138.011e9 if world == 1 else 137.899e9)
                if (rows_per_gpu == 1 << 22 and d == 4096 and (world == 1 or weak_pass)) else None)
     line = {
-        "metric": ("epochs/s (full-gradient passes, 2^22-row epochs)" if weak_pass else
+        "metric": ("epochs/s (SAGA table-init passes, 2^22-row epochs)" if table_init else
+                   "epochs/s (full-gradient passes, 2^22-row epochs)" if weak_pass else
                    "epochs/s (SVRG++ on row-sharded data, 2^22-row epochs)" if sharded else "epochs/s (Lasso 4M x 4096 fp64, SVRG++)"),
         "value": value, "unit": "epochs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "l2": "inputs larger than L2 (137 GB of row records per pass; rows sampled at random)",
                    "epoch": "N component-gradient evaluations; step = (m + N)/N epochs", "seeds": [SEED_DATA, SEED_IDX]},
         "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "row_pass_kernel (full gradient)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "row_pass_kernel (SAGA table init: read rows + write table)" if table_init else "row_pass_kernel (full gradient)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes},
         "clocks": clocks, "setup": {"what": "ciao_gen_synthetic (rows generated in HBM)", "seconds": setup_s},

@@ -223,10 +223,17 @@ static int need_rows(ciao_ctx *c, const char *who, bool whole) {
 static int reserve_idx(ciao_ctx *c, size_t n);
 static int reserve_for_solver(ciao_ctx *c) { return reserve_idx(c, (size_t)std::max<int64_t>(c->N_total, 1 << 16)); }
 
+// The N×d table lives next to the rows it belongs to: a row shard holds the table rows of its shard (the table-init passes
+// shard like the full gradient); the sequential steps need the whole table on one GPU (need_whole_table).
 static int alloc_table(ciao_ctx *c) {
-    if (c->n_rows != c->N_total)
-        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "the N×d tables of SAGA/Finito are not sharded: the context must hold all N rows");
     if (!c->table) CUDA_TRY(cudaMalloc(&c->table, (size_t)c->n_rows * c->d_pad * sizeof(double)));
+    return CIAO_OK;
+}
+static int need_whole_table(ciao_ctx *c, const char *who) {
+    if (c->n_rows != c->N_total)
+        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "%s: the N×d tables of SAGA/Finito are not sharded for the sequential steps — this context holds "
+                  "rows %lld..%lld of %lld (table init passes do shard)", who, (long long)c->row0, (long long)(c->row0 + c->n_rows),
+                  (long long)c->N_total);
     return CIAO_OK;
 }
 
@@ -239,8 +246,8 @@ static int set_gammas(ciao_ctx *c, const double *gamma_N, bool tails) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
     if (tails) {
-        set_gamma_tail_kernel<<<blocks_for(c->n_rows), 256, 0, c->stream>>>(c->rec, c->n_rows, c->d_pad, c->ld, c->gamma_dev,
-                                                                             (double)c->N_total, c->hat_gamma);
+        set_gamma_tail_kernel<<<blocks_for(c->n_rows), 256, 0, c->stream>>>(c->rec, c->n_rows, c->d_pad, c->ld, c->gamma_dev + c->row0,
+                                                                             (double)c->N_total, c->hat_gamma);  // γ of MY rows
         CUDA_TRY(cudaGetLastError());
         c->timing.launches += 1;
     }
@@ -700,7 +707,7 @@ extern "C" int ciao_finito_adaptive_get(ciao_ctx *c, double *gamma_N, double *fi
 // SAGA / SAG
 // ---------------------------------------------------------------------------
 extern "C" int ciao_saga_init(ciao_ctx *c, const double *x0, double gamma, int sag) {
-    CIAO_TRY(need_rows(c, "ciao_saga_init", true));
+    CIAO_TRY(need_rows(c, "ciao_saga_init", false));   // shards: table init pass + allreduce of Σ s_i
     if (!x0 || !(gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_saga_init: x0 is null or γ ≤ 0 (SAGA.jl:37)");
     c->algo = ALG_SAGA; c->gamma = gamma; c->sag = sag ? 1 : 0;
     CIAO_TRY(reserve_for_solver(c));
@@ -717,6 +724,7 @@ extern "C" int ciao_saga_init(ciao_ctx *c, const double *x0, double gamma, int s
 extern "C" int ciao_saga_steps(ciao_ctx *c, const int64_t *idx, int64_t K) {
     CIAO_TRY(need_rows(c, "ciao_saga_steps", true));
     if (c->algo != ALG_SAGA) CIAO_FAIL(CIAO_ERR_STATE, "ciao_saga_steps before ciao_saga_init");
+    CIAO_TRY(need_whole_table(c, "ciao_saga_steps"));
     if (K == 0) return CIAO_OK;
     const int64_t *raw;
     CIAO_TRY(fetch_raw_indices(c, idx, K, &raw));
@@ -735,7 +743,7 @@ static int prox_vec(ciao_ctx *c, int src, int dst, double gamma) {
 }
 
 extern "C" int ciao_finito_init(ciao_ctx *c, const double *x0, const double *gamma_N, double hat_gamma) {
-    CIAO_TRY(need_rows(c, "ciao_finito_init", true));
+    CIAO_TRY(need_rows(c, "ciao_finito_init", false));  // shards: table init pass + allreduce of Σ s_i/γ_i
     if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_finito_init: null argument or γ̂ ≤ 0");
     c->algo = ALG_FINITO; c->hat_gamma = hat_gamma;
     CIAO_TRY(reserve_for_solver(c));
@@ -768,6 +776,7 @@ static int batched_indices(ciao_ctx *c, const int64_t *idx, const int64_t *batch
 extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches) {
     CIAO_TRY(need_rows(c, "ciao_finito_steps", true));
     if (c->algo != ALG_FINITO) CIAO_FAIL(CIAO_ERR_STATE, "ciao_finito_steps before ciao_finito_init");
+    CIAO_TRY(need_whole_table(c, "ciao_finito_steps"));
     // static minibatches (contiguous rows, Finito_basic.jl:52-57) of ≥ BATCH_MIN_ROWS rows: one streaming pass per batch
     if (idx && batch_ptr && n_batches > 0 && !is_device_ptr(idx) && !is_device_ptr(batch_ptr)) {
         bool contiguous = true;

@@ -143,10 +143,22 @@ def main():
     rep.close()
     one.close()
 
-    # tables are not sharded: SAGA on a shard context is refused, not silently wrong
+    # the table-init passes shard with the rows (K2): every rank builds the table rows of its shard, Σ s_i is
+    # all-reduced; the sequential steps need the whole table on one GPU and are refused, not silently wrong
+    sh.saga_init(np.full(d, 0.01), gamma, False)
+    full.saga_init(np.full(d, 0.01), gamma, False)
+    assert rel(sh.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-12
+    assert np.array_equal(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) or rel(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) < 1e-12
+    assert np.array_equal(sh.get_table_rows(), full.get_table_rows(lo, hi - lo))
+    gsh = np.linspace(0.5, 2.0, N) * (0.999 * N / (N * full.max_row_sqnorm()))      # non-uniform γ_i: each shard must take its own
+    hsh = 1 / np.sum(1 / gsh)
+    sh.finito_init(np.full(d, 0.01), gsh, hsh)
+    full.finito_init(np.full(d, 0.01), gsh, hsh)
+    assert rel(sh.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-12
+    assert np.array_equal(sh.get_table_rows(), full.get_table_rows(lo, hi - lo))
     try:
-        sh.saga_init(np.zeros(d), gamma, False)
-        raise AssertionError("saga_init on a shard should fail")
+        sh.finito_steps(np.array([1, 2], dtype=np.int64), np.array([0, 1, 2], dtype=np.int64))
+        raise AssertionError("finito_steps on a shard should fail")
     except Exception as ex:
         assert "not sharded" in str(ex)
     dist.barrier()
