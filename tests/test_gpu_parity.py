@@ -691,3 +691,48 @@ def test_soft_threshold_bits_match_the_reference_formula():
         e.saga_init(x0, 0.5, False)
         got = e.get_vec(L.VEC_Z)
     assert np.array_equal(got.view(np.int64), want.view(np.int64)), (got, want)
+
+
+def test_medium_scale_end_to_end_parity():
+    """SURVEY.md §8d parity protocol at reduced scale: same inputs and the same index arrays into oracle and engine,
+    N = 65 536 × 1024 logistic (the C2 generator) and N = 32 768 × 4096 Lasso (the C3 generator, 1 GiB); tolerances of the
+    north star after K epochs: rel. objective ≤ 1e-8, ‖x − x_ref‖/‖x_ref‖ ≤ 1e-6."""
+    # C2 shape: SAGA and Finito, one epoch of random single-sample steps each
+    N, d = 1 << 16, 1024
+    p, e = make_rows(orc.LOSS_LOGISTIC, N, d, 0x5EED0002, lam_reg=1.0 / N)
+    Lmax = 0.25 * p.max_row_sqnorm()
+    x0 = np.ones(d)
+    idx = HostRNG(0x1D0002).rand_vec(N, N)
+    ref = orc.SAGAState(p, x0, 1 / (3 * Lmax))
+    ref.steps(idx)
+    e.saga_init(x0, 1 / (3 * Lmax), False)
+    e.saga_steps(idx)
+    z = e.get_vec(L.VEC_Z)
+    assert rel(z, ref.z) < REL_ITERATE
+    assert abs(sum(e.objective(z)) - sum(p.objective(ref.z))) <= REL_OBJECTIVE * abs(sum(p.objective(ref.z)))
+    gam = np.full(N, 0.999 * N / Lmax)
+    reff = orc.FinitoState(p, x0, gam)
+    reff.steps([idx[k:k + 1] for k in range(N // 2)])
+    e.finito_init(x0, gam, reff.hat_gamma)
+    e.finito_steps(idx[:N // 2], np.arange(N // 2 + 1, dtype=np.int64))
+    z = e.get_vec(L.VEC_Z)
+    assert rel(z, reff.z) < REL_ITERATE
+    assert abs(sum(e.objective(z)) - sum(p.objective(reff.z))) <= REL_OBJECTIVE * abs(sum(p.objective(reff.z)))
+    e.close()
+    # C3 shape: SVRG++ with the bench's schedule m = N/16·2^k, three outer iterations
+    N, d = 1 << 15, 4096
+    p, e = make_rows(orc.LOSS_LS, N, d, 0x5EED0003, lam_reg=N / 100.0)
+    gamma = 1 / (7 * N * p.max_row_sqnorm())
+    ref = orc.SVRGState(p, np.zeros(d), gamma, m=N // 16, plus=True)
+    e.svrg_init(np.zeros(d), gamma, True)
+    rng, m = HostRNG(0x1D0003), N // 16
+    for _ in range(3):
+        idx = rng.rand_vec(N, m)
+        ref.epoch(idx)
+        e.svrg_epoch(idx)
+        m *= 2
+    x = e.get_vec(L.VEC_Z_FULL)
+    assert rel(x, ref.z_full) < REL_ITERATE
+    f, f_ref = sum(e.objective(x)), sum(p.objective(ref.z_full))
+    assert abs(f - f_ref) <= REL_OBJECTIVE * abs(f_ref) and f_ref < sum(p.objective(np.zeros(d)))
+    e.close()
