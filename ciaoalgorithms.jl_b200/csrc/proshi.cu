@@ -7,11 +7,11 @@
 //
 // Design.  With a diagonal Q_i the block update has no coupling
 // between coordinates: every column j of (s, av, z) evolves independently given the
-// index sequence.  proshi_steps_kernel therefore gives each thread two columns, keeps
-// z_j and av_j in registers for the whole call and walks the host-generated index
-// sequence with a P-deep register prefetch of (γ_i, q_i, c_i, s_i) — no barrier, no
-// reduction, no kernel launch per step; the n columns are spread over many SMs so
-// the gathers of different columns overlap.
+// index sequence.  proshi_steps_kernel (batch 1) keeps z_j and av_j of a thread's columns in
+// registers for the whole call while producer lanes TMA-stage the slices of (q_i, c_i, s_i)
+// and (γ_i, γ_i/N) sixteen steps ahead — no barrier, no reduction, no kernel launch per
+// step; proshi_batch_kernel (batches ≥ 64 blocks) works through the blocks of a batch in
+// parallel, four lanes per block, and closes each batch with a fixed-order CTA reduction.
 #include <algorithm>
 
 #include "common.cuh"

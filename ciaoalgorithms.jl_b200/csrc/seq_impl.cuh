@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
         const double gl = gstep * p.reg.lambda;
         const double cN = __ddiv_rn(p.hat_gamma, p.Nd);  // LFinito: γ̂/N
         const double rN = __ddiv_rn(1.0, p.Nd);
-        const int E = p.npart_pad >> 5;                  // partials per lane in the final butterfly
+        const int E = p.npart_pad >> 5;                  // partials per lane in the final sum
 
         struct RowRegs {
             double a[CPT];
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             PROF_T(t_c);
             mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1) ^ (uint32_t)(pin & p.zero));
             PROF_T(t_d);
-            // every warp reduces the same C·W partials with the same butterfly → identical bits everywhere
+            // every warp reduces the same C·W partials with the same tensor-core sum → identical bits everywhere
             double u0 = 0.0, u1 = 0.0;
             {
                 const double2 *pp = reinterpret_cast<const double2 *>(part + (size_t)par * p.npart_pad * 2) + lane;
@@ -413,9 +413,9 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             }
             PROF_T(t_e);
             PROF_ADD(0, t_a, t_b);  // dots + warp shuffles
-            PROF_ADD(1, t_b, t_c);  // send + next-row / table-row register prefetch
+            PROF_ADD(1, t_b, t_c);  // send + products pinned in the shadow + registers of the next step
             PROF_ADD(2, t_c, t_d);  // remaining wait for the cluster exchange
-            PROF_ADD(3, t_d, t_e);  // butterfly of partials + fused update
+            PROF_ADD(3, t_d, t_e);  // sum of the partials + fused update
         };
         int64_t k = 0;
         for (; k + 1 < K; k += 2) {  // ping-pong the row registers: no copies between steps
