@@ -130,3 +130,30 @@ def test_sharded_pass_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err_g < 1e-13 and err_f < 1e-13
+
+
+def test_adaptive_sweeper_follows_the_reference():                # Finito_adaptive.jl:53-55, 107-119
+    from ciaoalgorithms_jl_b200.sampling import AdaptiveSweeper, HostRNG
+    cyc = AdaptiveSweeper(5, 2, HostRNG(0)).take(7)
+    assert cyc.tolist() == [1, 2, 3, 4, 5, 1, 2]                  # idxr starts at 0: the first index is 1 (the basic variant starts at 2)
+    shf = AdaptiveSweeper(5, 3, HostRNG(0)).take(10)
+    assert shf[:5].tolist() == [1, 2, 3, 4, 5] and sorted(shf[5:].tolist()) == [1, 2, 3, 4, 5]   # natural first pass, then randperm
+    rnd = AdaptiveSweeper(5, 1, HostRNG(0)).take(50)
+    assert rnd.min() >= 1 and rnd.max() <= 5
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU restatement on the host cores) prints one JSON line with the contract's keys."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-rows-log2", "11"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "epochs/s" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"] and "model" not in line["config"]
