@@ -124,6 +124,19 @@ static bool is_device_ptr(const void *p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// Pinned (page-locked / registered) host memory: cudaMemcpyAsync from it is truly asynchronous, so a borrowed buffer must be
+// synchronised before the call returns.  Pageable memory is staged by the driver before cudaMemcpyAsync returns (CUDA runtime
+// "API synchronization behavior"), so no extra stream synchronisation is needed — which keeps small calls (the one-step-per-
+// call iterator protocol) from serialising on the previous step's kernel.
+static bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;   // unknown: be conservative
+    }
+    return at.type != cudaMemoryTypeUnregistered;
+}
+
 // host vector (length d) → state vector `which` (padding stays zero); blocks until the copy is done
 static int upload_vec(ciao_ctx *c, int which, const double *x) {
     double *dst = ctx_vec(c, which);
@@ -184,8 +197,9 @@ static int fetch_raw_indices(ciao_ctx *c, const int64_t *idx, int64_t n, const i
         return CIAO_OK;
     }
     c->staged = 0;
+    const bool pinned = host_ptr_is_pinned(idx);
     CUDA_TRY(cudaMemcpyAsync(c->idx_raw, idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));  // host buffer is borrowed for the call only
+    if (pinned) CUDA_TRY(cudaStreamSynchronize(c->stream));  // host buffer is borrowed for the call only
     *raw_dev = c->idx_raw;
     return CIAO_OK;
 }
