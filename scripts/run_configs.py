@@ -115,8 +115,10 @@ for r in (1, 4096):
         idx, bp = csr(batches)
         e.proshi_steps(idx, bp)
         tot_ms += e.last_timing().last_seq_ms
+    # GBs: SURVEY §8d's algorithmic figure (24n per block: table read + write, diag(Q_i)); dram_GBs: what the general block layout
+    # moves (q_i, c_i, s_i read + s_i written = 32n; ncu: 6.47 GB read + 2.10 GB written per sweep)
     c5[f"proshi_cyclic_batch{r}"] = {"sweeps": K, "us_per_block": 1e3 * tot_ms / (K * N), "GBs": 24.0 * n * N * K / tot_ms / 1e6,
-                                     "sweeps_per_s": K / (tot_ms / 1e3)}
+                                     "dram_GBs": 32.0 * n * N * K / tot_ms / 1e6, "sweeps_per_s": K / (tot_ms / 1e3)}
 sw = BatchSweeper(N, 1, 1, rng)
 idx = rng.rand_vec(N, N)
 e.proshi_steps(idx, np.arange(N + 1, dtype=np.int64))
