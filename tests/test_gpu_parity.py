@@ -736,3 +736,31 @@ def test_medium_scale_end_to_end_parity():
     f, f_ref = sum(e.objective(x)), sum(p.objective(ref.z_full))
     assert abs(f - f_ref) <= REL_OBJECTIVE * abs(f_ref) and f_ref < sum(p.objective(np.zeros(d)))
     e.close()
+
+
+def test_large_d_sequential_kernels():
+    """d = 8192: 1024 columns per CTA, 8 columns per thread; the SAGA/Finito ring with table slices no longer fits in shared
+    memory, so the table rows take the register-prefetch path on their own (no environment knob)."""
+    N, d = 96, 8192
+    p, e = make_rows(orc.LOSS_LS, N, d, 0xB16D, lam_reg=0.05)
+    Lmax = N * p.max_row_sqnorm()
+    x0 = np.full(d, 0.01)
+    idx = HostRNG(3).rand_vec(N, 3 * N)
+    ref = orc.SVRGState(p, x0, 1 / (7 * Lmax), m=N, plus=False)
+    e.svrg_init(x0, 1 / (7 * Lmax), False)
+    for k in range(3):
+        ref.epoch(idx[k * N:(k + 1) * N])
+        e.svrg_epoch(idx[k * N:(k + 1) * N])
+    assert rel(e.get_vec(L.VEC_Z_FULL), ref.z_full) < 1e-9
+    refs = orc.SAGAState(p, x0, 1 / (3 * Lmax))
+    refs.steps(idx)
+    e.saga_init(x0, 1 / (3 * Lmax), False)
+    e.saga_steps(idx)
+    assert rel(e.get_vec(L.VEC_Z), refs.z) < 1e-9 and rel(e.get_table_rows(), refs.s) < 1e-9
+    gam = 0.999 * N / (N * np.sum(p.A * p.A, axis=1))
+    reff = orc.FinitoState(p, x0, gam)
+    reff.steps([idx[k:k + 1] for k in range(2 * N)])
+    e.finito_init(x0, gam, reff.hat_gamma)
+    e.finito_steps(idx[:2 * N], np.arange(2 * N + 1, dtype=np.int64))
+    assert rel(e.get_vec(L.VEC_Z), reff.z) < 1e-9 and rel(e.get_table_rows(), reff.s) < 1e-9
+    e.close()
