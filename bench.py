@@ -16,10 +16,17 @@ evaluations in one-data-pass accounting: a step with inner length m is (m + N)/N
               `solver(x0; F=...)`), reported under "setup".
   roofline  : the full-gradient pass kernel (row_pass_kernel), HBM-bound; algorithmic bytes
               = N·(d_pad+8)·8 per launch (the row records incl. the 8-scalar tail b_i, λ_i, …).
-  N > 1     : one process per GPU.  Every rank holds the full problem; the full-gradient pass is
-              row-sharded (each rank streams N/G rows) and all-reduced over NCCL, the sequential
-              inner epoch is replicated (it is sequential in i) → "strong" scaling.
-              `--workload fullgrad` times the sharded pass alone with 2^22 rows per GPU (weak).
+  N > 1     : one process per GPU.  96 % of a step is the sequential inner epoch, which does not shard
+              (step k+1 depends on step k: "replicas only"), so the default workload at
+              N > 1 is N independent SVRG++ solves of the C3 problem — one per GPU, each with its own
+              index stream, no collective on the data path → "weak" scaling; `value` = the epochs all
+              ranks processed ÷ the max-over-ranks time.  The part of the path that does shard — the
+              full-gradient pass, row-windowed over the ranks + NCCL allreduce of the d-vector — is
+              timed in the same run after the solves and reported under "full_gradient_sharded".
+              `--workload svrgpp-strong` runs ONE solve on N GPUs (pass sharded, inner epoch replicated;
+              Amdahl-bound), `--workload fullgrad` the sharded pass alone with 2^22 rows per GPU (weak),
+              `--workload saga-init` the sharded table-init pass, `--workload svrgpp-sharded` a solve
+              over row shards with remote rows fetched over NVLink.
   --impl reference : the CPU restatement of the reference (oracle/, kind "port"; Julia is not
               installed) on a bounded sample of the same workload, single thread like the reference.
 """
@@ -48,7 +55,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="svrgpp", choices=["svrgpp", "fullgrad", "svrgpp-sharded", "saga-init"])
+    ap.add_argument("--workload", default="svrgpp", choices=["svrgpp", "svrgpp-strong", "fullgrad", "svrgpp-sharded", "saga-init"])
     ap.add_argument("--rows-log2", type=int, default=22)
     ap.add_argument("--d", type=int, default=4096)
     ap.add_argument("--cpu-rows-log2", type=int, default=17)
@@ -126,7 +133,7 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference(args, N_full, d, steps, warmup):
+def cpu_reference(args, N_full, d, steps, warmup, seed_idx=SEED_IDX):
     """Times the oracle's SVRG++ outer iteration on a bounded sample (2^cpu_rows_log2 rows of the
     same generator, m = N_s/16·2^k) on one host core; extrapolates per-evaluation cost to N_full."""
     from oracle import oracle as orc
@@ -135,7 +142,7 @@ def cpu_reference(args, N_full, d, steps, warmup):
     p = orc.Problem(orc.LOSS_LS, A, b, np.full(Ns, float(Ns))).set_reg(orc.REG_NORML1, lam=Ns / 100.0)
     gamma = 1 / (7 * Ns * p.max_row_sqnorm())
     st = orc.SVRGState(p, np.zeros(d), gamma, m=Ns // 16, plus=True)
-    rng = np.random.default_rng(SEED_IDX)
+    rng = np.random.default_rng(seed_idx)
     evals, t_inner, t_pass, t_total = 0, 0.0, 0.0, 0.0
     for k in range(-warmup, steps):
         m = (Ns // 16) << (max(k, 0) % SCHEDULE) if k >= 0 else Ns // 16
@@ -161,18 +168,37 @@ def cpu_reference(args, N_full, d, steps, warmup):
             "us_per_pass_row": 1e6 * t_pass / (steps * Ns), "seconds": t_total}, t_total / steps
 
 
+def _reference_replica(job):
+    args, N, d, steps, warmup, r = job
+    return cpu_reference(args, N, d, steps, warmup, seed_idx=SEED_IDX + r)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     N, d = 1 << args.rows_log2, args.d
     steps = max(1, min(args.steps, 5))
-    cb, s_per_step = cpu_reference(args, N, d, steps, min(args.warmup, 1))
+    G = args.gpus if args.workload == "svrgpp" else 1
+    if G > 1:
+        # the GPU arm at N > 1 runs G independent solves, one per GPU: the CPU arm runs the same G solves concurrently,
+        # one single-threaded reference loop per host core (the reference itself has no threading), 2 GiB of rows each
+        import multiprocessing as mp
+        args.cpu_rows_log2 = min(args.cpu_rows_log2, 16)
+        with mp.get_context("spawn").Pool(G) as pool:
+            res = pool.map(_reference_replica, [(args, N, d, steps, min(args.warmup, 1), r) for r in range(G)])
+        s_per_step = max(r[1] for r in res)                    # the job ends with its slowest replica
+        cb = dict(res[0][0])
+        cb["value"] = G * min(r[0]["value"] for r in res)      # whole job: G solves at the pace of the slowest
+        cb["cores"] = G
+        cb["sample"] = f"{G} concurrent replicas, one per host core, each: " + cb["sample"]
+    else:
+        cb, s_per_step = cpu_reference(args, N, d, steps, min(args.warmup, 1))
     line = {"impl": "reference", "metric": "epochs/s (Lasso 4M x 4096 fp64, SVRG++)", "value": cb["value"], "unit": "epochs/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * s_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.workload == "svrgpp-strong" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": (f"C3 Lasso N=2^{args.rows_log2} d={d} fp64 SVRG++ gamma=1/(7 L_max) m=N/16*2^(k mod 5): persistent inner epoch + "
-                                    f"full-gradient pass"),
+                                    f"full-gradient pass" + (f"; {G} independent solves" if G > 1 else "")),
                        "sample": f"the reference's loop (CPU restatement) on 2^{args.cpu_rows_log2} rows of the same generator, same schedule, "
                                  f"extrapolated per component gradient to N=2^{args.rows_log2}",
                        "epoch": "N component-gradient evaluations; step = (m + N)/N epochs", "seeds": [SEED_DATA, SEED_IDX]},
@@ -225,6 +251,8 @@ def main():
     d = args.d
     weak_pass = args.workload == "fullgrad" or table_init
     sharded = args.workload == "svrgpp-sharded"      # rows sharded over the GPUs, inner epoch reads remote rows over NVLink
+    strong = args.workload == "svrgpp-strong" and world > 1    # ONE solve on all GPUs: pass row-windowed, inner epoch replicated
+    replicas = args.workload == "svrgpp" and world > 1         # one independent solve per GPU (the inner epoch does not shard)
     N = rows_per_gpu * world if (weak_pass or sharded) else rows_per_gpu
     e = Engine(local)
     if args.tune:
@@ -237,17 +265,20 @@ def main():
     e.set_reg(L.REG_NORML1, N / 100.0)
     e.sync()
     setup_s = time.perf_counter() - t0
-    if world > 1:
+    def init_comm():
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid = torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         e.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+    if world > 1 and not replicas:       # replicas: the solves run without a communicator (a pass with one all-reduces)
+        init_comm()
         if sharded:
             handles = [None] * world
             dist.all_gather_object(handles, e.rows_ipc_handle())
             e.attach_peer_rows(handles, [r * rows_per_gpu for r in range(world)], [rows_per_gpu] * world, rank)
-        elif not weak_pass:
+        elif strong:
             lo, hi = (rank * N) // world, ((rank + 1) * N) // world
             e.set_pass_window(lo, hi - lo)
     gamma = 1.0 / (7.0 * N * e.max_row_sqnorm())
@@ -306,7 +337,8 @@ def main():
         epochs_total = K * world
     else:
         # ---- SVRG++ outer iterations (C3) ---------------------------------------------------------
-        rng = np.random.default_rng(SEED_IDX)
+        seed_idx = SEED_IDX + (rank if replicas else 0)      # replicas: every GPU walks its own index stream
+        rng = np.random.default_rng(seed_idx)
         idx_host = [rng.integers(1, N + 1, size=m_of(k, N), dtype=np.int64) for k in range(K)]
         idx_warm = rng.integers(1, N + 1, size=N // 16, dtype=np.int64)
         idx_dev = [torch.from_numpy(a).cuda() for a in idx_host]
@@ -329,7 +361,7 @@ def main():
         barrier()
         launches = e.last_timing().launches - l0
         epoch_rows = rows_per_gpu if sharded else N      # sharded: an "epoch" stays 2^22 component gradients
-        epochs_total = sum((m_of(k, N) + N) / epoch_rows for k in range(K))
+        epochs_total = sum((m_of(k, N) + N) / epoch_rows for k in range(K)) * (world if replicas else 1)
         value = epochs_total / (ms / 1e3)
         pass_ms = max_over_ranks(float(np.mean(pass_ms_list)))
         inner_steps = sum(m_of(k, N) for k in range(K))
@@ -346,7 +378,7 @@ def main():
                 return pin[:m_]
 
         solver = solvers.SVRG(gamma=gamma, m=N // 16, plus=True)
-        it = iter(solvers.iterator(solver, x0, F=solvers.DeviceProblem(e), g=ops.NormL1(N / 100.0), N=N, rng=PinnedRNG(SEED_IDX)))
+        it = iter(solvers.iterator(solver, x0, F=solvers.DeviceProblem(e), g=ops.NormL1(N / 100.0), N=N, rng=PinnedRNG(seed_idx)))
         state = next(it)
         barrier()
         w0 = time.perf_counter()
@@ -361,7 +393,8 @@ def main():
         e2e = {"value": epochs_total / (e2e_ms / 1e3), "unit": "epochs/s",
                "h2d_bytes_per_step": int(8 * inner_steps / K), "d2h_bytes_per_step": 8 * d, "wall_ms": wall_ms,
                "api": "solvers.iterator(SVRG(plus=True)) -> next(state) -> solution(state)"}
-        algo_bytes = (rows_per_gpu if sharded else N // world) * ld * 8
+        pass_rows = rows_per_gpu if sharded else (N // world if strong else N)      # rows one rank streams per pass
+        algo_bytes = pass_rows * ld * 8
         extra = {"svrg": {"inner_steps": inner_steps, "us_per_inner_step": 1e3 * float(np.sum(seq_ms_list)) / inner_steps,
                           "inner_ms": [round(v, 3) for v in seq_ms_list], "pass_ms": [round(v, 3) for v in pass_ms_list],
                           "objective_start": f_start, "objective_end": f_end, "checksum_x": float(np.sum(np.abs(xs)))},
@@ -372,24 +405,50 @@ def main():
                                   "share_of_step_time": float(np.sum(seq_ms_list)) / ms,
                                   "exchange_floor_us": 240 / 1965.0, "algorithmic_bytes_per_step": 8 * d + 32,
                                   "achieved_gbs": (8 * d + 32) * inner_steps / float(np.sum(seq_ms_list)) / 1e6},
-                 "full_gradient": {"rows_per_gpu": rows_per_gpu if sharded else N // world, "kernel_ms": pass_ms,
-                                   "aggregate_gbs": N * ld * 8 / pass_ms / 1e6, "gbs_per_gpu": algo_bytes / pass_ms / 1e6,
-                                   "frac_of_8TBs": algo_bytes / pass_ms / 1e6 / 8000.0}}
-        scaling = "weak" if sharded else "strong"
+                 "full_gradient": {"rows_per_gpu": pass_rows, "kernel_ms": pass_ms,
+                                   "aggregate_gbs": (world if replicas else 1) * N * ld * 8 / pass_ms / 1e6,
+                                   "gbs_per_gpu": algo_bytes / pass_ms / 1e6, "frac_of_8TBs": algo_bytes / pass_ms / 1e6 / 8000.0}}
+        if replicas:
+            # The part of the path that shards: the same full-gradient pass row-windowed over the ranks (N/G rows each) +
+            # one NCCL allreduce of the d-vector, timed after the solves (SVRG_basic.jl:58-63 over a sharded F).
+            init_comm()
+            lo, hi = (rank * N) // world, ((rank + 1) * N) // world
+            e.set_pass_window(lo, hi - lo)
+            e.set_vec(L.VEC_X, xs)
+            for _ in range(W):
+                e.full_gradient(None, 1.0 / N, out=False)
+            barrier()
+            sh_ms_list = []
+            e.timer_begin()
+            for _ in range(K):
+                e.full_gradient(None, 1.0 / N, out=False)
+                sh_ms_list.append(e.last_timing().last_pass_ms)
+            sh_ms = max_over_ranks(e.timer_end()) / K
+            barrier()
+            sh_kernel_ms = max_over_ranks(float(np.mean(sh_ms_list)))
+            extra["full_gradient_sharded"] = {
+                "what": f"one full-gradient pass over the C3 rows, row-windowed over {world} GPUs + NCCL allreduce of the d-vector",
+                "rows_per_gpu": hi - lo, "ms_per_pass": sh_ms, "kernel_ms": sh_kernel_ms, "passes": K,
+                "aggregate_gbs": N * ld * 8 / sh_ms / 1e6, "kernel_gbs_per_gpu": (hi - lo) * ld * 8 / sh_kernel_ms / 1e6,
+                "speedup_vs_local_pass": pass_ms / sh_ms}
+        scaling = "strong" if args.workload == "svrgpp-strong" else "weak"   # default: per-GPU work fixed (one solve per GPU)
         if sharded:
             workload = (f"C4-style Lasso N={world}x2^{args.rows_log2} rows sharded over {world} GPUs, d={d} fp64 SVRG++ m=N/16*2^(k mod 5): "
                         f"sharded full-gradient pass + NCCL allreduce; inner epoch replicated, remote rows TMA-prefetched over NVLink (CUDA IPC)")
         else:
             workload = (f"C3 Lasso N=2^{args.rows_log2} d={d} fp64 SVRG++ gamma=1/(7 L_max) m=N/16*2^(k mod 5): persistent inner epoch + "
-                        f"full-gradient pass" + (f"; pass row-sharded over {world} GPUs + NCCL allreduce, inner epoch replicated" if world > 1 else ""))
+                        f"full-gradient pass"
+                        + (f"; ONE solve on {world} GPUs: pass row-sharded + NCCL allreduce, inner epoch replicated" if strong else "")
+                        + (f"; {world} independent solves, one per GPU (own index stream each; the sequential inner epoch does not shard), "
+                           f"no data-path collective" if replicas else ""))
 
     clocks = sampler.summary() if rank == 0 else None
     achieved = algo_bytes / pass_ms / 1e6     # GB/s
     # dram__bytes_read.sum + dram__bytes_write.sum of row_pass_kernel from the committed `ncu --set full` capture
     # (profiles/ncu_row_pass_r1.csv: 137.90 GB read + 0.11 GB written per launch at N=2^22, d=4096, one GPU — the writes are
     # the 32 B/row step scalars a single-process pass leaves for the inner kernel; multi-rank passes write 12 MB); null otherwise
-    traffic = ((138.011e9 if world == 1 else 137.899e9)
-               if (rows_per_gpu == 1 << 22 and d == 4096 and (world == 1 or weak_pass)) else None)
+    traffic = ((138.011e9 if (world == 1 or replicas) else 137.899e9)
+               if (rows_per_gpu == 1 << 22 and d == 4096 and (world == 1 or weak_pass or replicas)) else None)
     line = {
         "metric": ("epochs/s (SAGA table-init passes, 2^22-row epochs)" if table_init else
                    "epochs/s (full-gradient passes, 2^22-row epochs)" if weak_pass else
@@ -407,7 +466,7 @@ def main():
     line.update(extra)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            cb, _ = cpu_reference(args, N, d, 3, 1)
+            cb, _ = cpu_reference(args, N, d, 5, 1)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     e.close()
