@@ -172,7 +172,11 @@ static int reserve_idx(ciao_ctx *c, size_t n) {
         int64_t *nr = nullptr, *np = nullptr;
         const size_t cap = std::max(n, c->idx_cap * 2);
         CUDA_TRY(cudaMalloc(&nr, cap * sizeof(int64_t)));
-        CUDA_TRY(cudaMalloc(&np, cap * sizeof(int64_t)));
+        if (cudaMalloc(&np, cap * sizeof(int64_t)) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(nr);
+            CIAO_FAIL(CIAO_ERR_OOM, "index staging buffers: out of device memory (%zu indices)", cap);
+        }
         if (c->idx_raw && c->staged > 0)
             CUDA_TRY(cudaMemcpyAsync(nr, c->idx_raw, (size_t)c->staged * sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -303,11 +307,19 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
     c->seq_table_ldg = getenv("CIAO_SEQ_TABLE_LDG") != nullptr && getenv("CIAO_SEQ_TABLE_LDG")[0] == '1';
     c->batch_persistent = !(getenv("CIAO_BATCH_PER_LAUNCH") != nullptr && getenv("CIAO_BATCH_PER_LAUNCH")[0] == '1');
     c->num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    cudaEvent_t *evs[] = {&c->ev_pa, &c->ev_pb, &c->ev_sa, &c->ev_sb, &c->tm_a, &c->tm_b};
-    for (auto ev : evs) CUDA_TRY(cudaEventCreate(ev));
-    CUDA_TRY(cudaMalloc(&c->err_dev, sizeof(int)));
-    CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
+    auto init_device_objects = [&]() -> int {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        cudaEvent_t *evs[] = {&c->ev_pa, &c->ev_pb, &c->ev_sa, &c->ev_sb, &c->tm_a, &c->tm_b};
+        for (auto ev : evs) CUDA_TRY(cudaEventCreate(ev));
+        CUDA_TRY(cudaMalloc(&c->err_dev, sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
+        return CIAO_OK;
+    };
+    const int rc = init_device_objects();
+    if (rc != CIAO_OK) {  // a half-built context is torn down here (the error text is already set), never handed out
+        ciao_destroy(c);
+        return rc;
+    }
     *out = c;
     return CIAO_OK;
 }
