@@ -157,3 +157,19 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_bench_reference_arm_runs_one_solve_per_gpu_on_as_many_cores():
+    """At N > 1 the GPU arm runs N independent solves; the reference arm runs the same N solves concurrently, one per core."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                          "--cpu-rows-log2", "11"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["scaling"] == "weak"
+    assert line["cpu_baseline"]["cores"] == 2 and "2 independent solves" in line["config"]["workload"]
+    # a rank other than 0 prints nothing and exits 0 (torchrun launches the arm on every rank)
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1"))
+    assert res.returncode == 0 and res.stdout.strip() == ""
