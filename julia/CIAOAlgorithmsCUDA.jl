@@ -103,8 +103,18 @@ function set_problem!(c::Ctx, F::AbstractVector, g, N::Int)
     return c
 end
 
-getvec!(c::Ctx, which::Cint, out::Vector{Float64}) =
-    (GC.@preserve out check(ccall((:ciao_get_vec, libciao), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), c.h, which, out, length(out))); out)
+# D2H into the fp64 staging buffer, then into the persistent array typed like x0 (the reference's states are typed by x0:
+# `eltype(x) == T`, test_lasso.jl:75); for Float64 problems the two are the same array and nothing is copied.
+function getvec!(c::Ctx, which::Cint, out::AbstractVector, buf::Vector{Float64})
+    GC.@preserve buf check(ccall((:ciao_get_vec, libciao), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), c.h, which, buf, length(buf)))
+    out === buf || copyto!(out, buf)
+    return out
+end
+# the persistent solution array (eltype of x0) and its fp64 staging buffer
+function outvec(x0::AbstractArray)
+    out = zeros(real(eltype(x0)), length(x0))
+    return out, (out isa Vector{Float64} ? out : zeros(Float64, length(x0)))
+end
 
 # ================================ SVRG / SVRG++ (SVRG.jl, SVRG_basic.jl) ================================
 struct SVRG{R<:Real}
@@ -124,7 +134,7 @@ struct SVRG_basic_iterable{R,Tx,Tf,Tg}
     F::Tf; g::Tg; x0::Tx; N::Int; L; μ; γ::Maybe{R}; m::Maybe{Int}; plus::Bool
 end
 mutable struct SVRG_basic_state{R}
-    ctx::Ctx; γ::R; m::Int; z_full::Vector{Float64}; ind::Vector{Int}
+    ctx::Ctx; γ::R; m::Int; z_full::Vector; buf::Vector{Float64}; ind::Vector{Int}
 end
 
 function Base.iterate(iter::SVRG_basic_iterable{R}) where {R}
@@ -145,7 +155,7 @@ function Base.iterate(iter::SVRG_basic_iterable{R}) where {R}
     c = set_problem!(Ctx(), iter.F, iter.g, N)
     x0 = Vector{Float64}(iter.x0)
     GC.@preserve x0 check(ccall((:ciao_svrg_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint), c.h, x0, γ, iter.plus))
-    state = SVRG_basic_state{R}(c, γ, m, zeros(length(x0)), collect(1:N))
+    state = SVRG_basic_state{R}(c, γ, m, outvec(iter.x0)..., collect(1:N))
     return state, state
 end
 
@@ -155,7 +165,7 @@ function Base.iterate(iter::SVRG_basic_iterable{R}, state::SVRG_basic_state{R}) 
     iter.plus && (state.m *= 2)                        # :93
     return state, state
 end
-solution(state::SVRG_basic_state) = getvec!(state.ctx, CIAO_VEC_Z_FULL, state.z_full)   # same array every call (===)
+solution(state::SVRG_basic_state) = getvec!(state.ctx, CIAO_VEC_Z_FULL, state.z_full, state.buf)   # same array every call (===)
 
 function (solver::SVRG{R})(x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, μ = nothing, N = N) where {R}
     m = solver.m === nothing ? N : solver.m
@@ -189,7 +199,7 @@ struct SAGA_basic_iterable{R,Tx,Tf,Tg}
     F::Tf; g::Tg; x0::Tx; N::Int; L; γ::Maybe{R}; SAG::Bool
 end
 mutable struct SAGA_basic_state{R}
-    ctx::Ctx; γ::R; z::Vector{Float64}; ind::Int
+    ctx::Ctx; γ::R; z::Vector; buf::Vector{Float64}; ind::Int
 end
 function Base.iterate(iter::SAGA_basic_iterable{R}) where {R}
     if iter.γ === nothing
@@ -202,7 +212,7 @@ function Base.iterate(iter::SAGA_basic_iterable{R}) where {R}
     c = set_problem!(Ctx(), iter.F, iter.g, iter.N)
     x0 = Vector{Float64}(iter.x0)
     GC.@preserve x0 check(ccall((:ciao_saga_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint), c.h, x0, γ, iter.SAG))
-    state = SAGA_basic_state{R}(c, γ, zeros(length(x0)), 1)
+    state = SAGA_basic_state{R}(c, γ, outvec(iter.x0)..., 1)
     return state, state
 end
 # k reference iterations fused into one persistent kernel; the k draws are k calls of rand(1:N) (SAGA_basic.jl:55)
@@ -213,7 +223,7 @@ function steps!(iter::SAGA_basic_iterable, state::SAGA_basic_state, k::Int)
     return state
 end
 Base.iterate(iter::SAGA_basic_iterable{R}, state::SAGA_basic_state{R}) where {R} = (steps!(iter, state, 1); (state, state))
-solution(state::SAGA_basic_state) = getvec!(state.ctx, CIAO_VEC_Z, state.z)
+solution(state::SAGA_basic_state) = getvec!(state.ctx, CIAO_VEC_Z, state.z, state.buf)
 
 (solver::SAGA{R})(x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
     drive(solver, SAGA_basic_iterable{R,typeof(x0),typeof(F),typeof(g)}(F, g, x0, N, L, solver.γ, solver.SAG_flag), solver.maxit, s -> s.γ)
@@ -252,7 +262,8 @@ struct Table_iterable{R,Tx,Tf,Tg}
     kind::Symbol; F::Tf; g::Tg; x0::Tx; N::Int; L; γ; sweeping::Int8; batch::Int; α::R
 end
 mutable struct Table_state{R}
-    kind::Symbol; ctx::Ctx; γ::Vector{R}; hat_γ::R; z::Vector{Float64}; s::Matrix{Float64}
+    kind::Symbol; ctx::Ctx; γ::Vector{R}; hat_γ::R; z::Vector; buf::Vector{Float64}
+    s::Vector{<:Vector}; sbuf::Matrix{Float64}    # ProShI: the table x_i as the reference holds it (a vector of vectors) + fp64 staging
     d::Int; idxr::Int; idx::Int; inds::Vector{Int}
 end
 
@@ -272,19 +283,21 @@ function Base.iterate(iter::Table_iterable{R}) where {R}
     hat_γ = iter.kind == :proshi ? sum(γ) : 1 / sum(1 ./ γ)           # ProShI_basic.jl:82 / Finito_basic.jl:82
     c = set_problem!(Ctx(), iter.F, iter.g, N)
     x0 = Vector{Float64}(iter.x0)
-    sym = iter.kind == :finito ? :ciao_finito_init : iter.kind == :lfinito ? :ciao_lfinito_init : :ciao_proshi_init
-    GC.@preserve x0 γ begin
+    γ64 = Vector{Float64}(γ)                                             # the engine computes in fp64 (R may be Float32)
+    GC.@preserve x0 γ64 begin
         if iter.kind == :finito
-            check(ccall((:ciao_finito_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ, hat_γ))
+            check(ccall((:ciao_finito_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ64, hat_γ))
         elseif iter.kind == :lfinito
-            check(ccall((:ciao_lfinito_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ, hat_γ))
+            check(ccall((:ciao_lfinito_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ64, hat_γ))
         else
-            check(ccall((:ciao_proshi_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ, hat_γ))
+            check(ccall((:ciao_proshi_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64), c.h, x0, γ64, hat_γ))
         end
     end
     d = cld(N, iter.batch)
-    s = iter.kind == :proshi ? Matrix{Float64}(undef, length(x0), N) : Matrix{Float64}(undef, 0, 0)
-    state = Table_state{R}(iter.kind, c, γ, hat_γ, zeros(length(x0)), s, d, 1, 0, collect(1:d))
+    Te = real(eltype(iter.x0))
+    s = iter.kind == :proshi ? [zeros(Te, length(x0)) for _ = 1:N] : Vector{Te}[]
+    sbuf = iter.kind == :proshi ? Matrix{Float64}(undef, length(x0), N) : Matrix{Float64}(undef, 0, 0)
+    state = Table_state{R}(iter.kind, c, γ, hat_γ, outvec(iter.x0)..., s, sbuf, d, 1, 0, collect(1:d))
     return state, state
 end
 
@@ -332,11 +345,14 @@ Base.iterate(iter::Table_iterable{R}, state::Table_state{R}) where {R} = (steps!
 
 function solution(state::Table_state)
     if state.kind == :proshi                                             # ProShI_basic.jl:127-132 — mutates the table on every call
-        s = state.s
-        GC.@preserve s check(ccall((:ciao_proshi_solution, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}), state.ctx.h, s))
-        return s                                                         # n×N column-major: column i is x_i
+        sbuf = state.sbuf                                                # n×N column-major: column i is x_i
+        GC.@preserve sbuf check(ccall((:ciao_proshi_solution, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}), state.ctx.h, sbuf))
+        for i = 1:length(state.s)
+            copyto!(state.s[i], view(sbuf, :, i))
+        end
+        return state.s                                                   # Vector of x_i, as upstream (test_sharing.jl:42-43)
     end
-    return getvec!(state.ctx, CIAO_VEC_Z, state.z)                        # Finito_basic.jl:123, Finito_LFinito.jl:105
+    return getvec!(state.ctx, CIAO_VEC_Z, state.z, state.buf)             # Finito_basic.jl:123, Finito_LFinito.jl:105
 end
 
 # ---- adaptive Finito (Finito_adaptive.jl): linesearch on γ_i inside the persistent kernel ------------------------------
@@ -344,7 +360,7 @@ struct FINITO_adaptive_iterable{R,Tx,Tf,Tg}
     F::Tf; g::Tg; x0::Tx; N::Int; L; tol::R; tol_b::R; sweeping::Int8; α::R
 end
 mutable struct FINITO_adaptive_state{R}
-    ctx::Ctx; z::Vector{Float64}; γ::Vector{Float64}; hat_γ::R
+    ctx::Ctx; z::Vector; buf::Vector{Float64}; γ::Vector{Float64}; hat_γ::R
     ind::Vector{Int}; idx::Int; idxr::Int            # Finito_adaptive.jl:53-55
 end
 
@@ -361,7 +377,7 @@ function Base.iterate(iter::FINITO_adaptive_iterable{R}) where {R}
     x0 = Vector{Float64}(iter.x0)
     GC.@preserve x0 check(ccall((:ciao_finito_adaptive_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64),
                                 c.h, x0, Float64(iter.α), Float64(iter.tol_b)))                  # :59-99
-    state = FINITO_adaptive_state{R}(c, zeros(length(x0)), zeros(iter.N), R(0), collect(1:iter.N), 0, 0)
+    state = FINITO_adaptive_state{R}(c, outvec(iter.x0)..., zeros(iter.N), R(0), collect(1:iter.N), 0, 0)
     return refresh!(state), state
 end
 
@@ -395,7 +411,7 @@ function Base.iterate(iter::FINITO_adaptive_iterable{R}, state::FINITO_adaptive_
     steps!(iter, state, 1) < 1 && return nothing
     return state, state
 end
-solution(state::FINITO_adaptive_state) = getvec!(state.ctx, CIAO_VEC_Z, state.z)                  # :162
+solution(state::FINITO_adaptive_state) = getvec!(state.ctx, CIAO_VEC_Z, state.z, state.buf)       # :162
 
 function table_iterable(solver::Finito{R}, x0, F, g, L, N) where {R}
     if solver.adaptive && !solver.LFinito                                                        # Finito.jl:92-103
@@ -407,9 +423,14 @@ end
 table_iterable(solver::Proshi{R}, x0, F, g, L, N) where {R} =
     Table_iterable{R,typeof(x0),typeof(F),typeof(g)}(:proshi, F, g, x0, N, L, solver.γ, solver.sweeping, solver.minibatch[2], solver.α)
 
-(solver::Union{Finito{R},Proshi{R}})(x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
+# Finito.jl:66-117, ProShI.jl:42-90 (one method per solver type, as upstream)
+(solver::Finito{R})(x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
     drive(solver, table_iterable(solver, x0, F, g, L, N), solver.maxit, s -> s.hat_γ)
-iterator(solver::Union{Finito{R},Proshi{R}}, x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
+(solver::Proshi{R})(x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
+    drive(solver, table_iterable(solver, x0, F, g, L, N), solver.maxit, s -> s.hat_γ)
+iterator(solver::Finito{R}, x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
+    table_iterable(solver, x0, F, g, L, N)
+iterator(solver::Proshi{R}, x0::AbstractArray; F = nothing, g = ProximalOperators.Zero(), L = nothing, N = N) where {R} =
     table_iterable(solver, x0, F, g, L, N)
 
 # ---- the driver loop of SVRG.jl:70-83 with the steps between two prints fused into one call ----------
