@@ -55,6 +55,8 @@ int nccl_load() {
     } while (0)
 }  // namespace
 
+void ciao_comm_destroy(ciao_ctx *c);
+
 extern "C" int ciao_comm_unique_id(void *out128) {
     if (!out128) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_comm_unique_id: null output");
     CIAO_TRY(nccl_load());
@@ -66,6 +68,7 @@ extern "C" int ciao_comm_unique_id(void *out128) {
 
 extern "C" int ciao_comm_init(ciao_ctx *c, const void *id128, int rank, int world) {
     if (!c || !id128 || world < 1 || rank < 0 || rank >= world) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_comm_init: bad arguments");
+    ciao_comm_destroy(c);   // a second ciao_comm_init replaces the communicator instead of leaking it
     if (world == 1) {
         c->rank = 0;
         c->world = 1;
