@@ -100,3 +100,54 @@ def test_the_shim_binds_every_solver_entry_point():
                 "ciao_lfinito_init", "ciao_lfinito_outer", "ciao_proshi_init", "ciao_proshi_steps", "ciao_proshi_solution",
                 "ciao_finito_adaptive_init", "ciao_finito_adaptive_steps", "ciao_finito_adaptive_get"):
         assert sym in bound, sym
+
+
+def _strip_strings_and_comments(src):
+    out, i, n = [], 0, len(src)
+    while i < n:
+        ch = src[i]
+        if ch == "#":                                   # line comment (the shim has no #= =# blocks)
+            while i < n and src[i] != "\n":
+                i += 1
+        elif ch == '"':                                 # string literal, escapes skipped; $(...) interpolation treated as text
+            i += 1
+            while i < n and src[i] != '"':
+                i += 2 if src[i] == "\\" else 1
+            i += 1
+            out.append('""')
+        elif ch == "'" and i + 2 < n and src[i + 2] == "'":   # character literal
+            i += 3
+            out.append("' '")
+        else:
+            out.append(ch)
+            i += 1
+    return "".join(out)
+
+
+def test_blocks_and_brackets_balance():
+    """No Julia here to parse the shim, so at least: brackets nest properly and every block opener outside brackets
+    (function, if, for, while, struct, begin, module, let, try, do, quote, macro) has its `end`."""
+    src = _strip_strings_and_comments(open(os.path.join(ROOT, "julia", "CIAOAlgorithmsCUDA.jl")).read())
+    pairs = {")": "(", "]": "[", "}": "{"}
+    stack, blocks = [], []
+    openers = {"function", "if", "for", "while", "struct", "begin", "module", "let", "try", "do", "quote", "macro"}
+    word = re.compile("[A-Za-z_\\u0080-\\uffff][A-Za-z_0-9!\\u0080-\\uffff]*|[()\\[\\]{}]")
+    for lineno, line in enumerate(src.splitlines(), 1):
+        for m in word.finditer(line):
+            tok = m.group(0)
+            if tok in "([{":
+                stack.append((tok, lineno))
+            elif tok in ")]}":
+                assert stack and stack[-1][0] == pairs[tok], f"line {lineno}: unmatched {tok}"
+                stack.pop()
+            elif not stack:                              # keywords inside brackets are comprehensions / generators / a[end]
+                prev = line[:m.start()].rstrip()
+                if prev.endswith(".") or prev.endswith(":"):     # field access x.begin / symbol :for — not a keyword
+                    continue
+                if tok in openers:
+                    blocks.append((tok, lineno))
+                elif tok == "end":
+                    assert blocks, f"line {lineno}: `end` without an open block"
+                    blocks.pop()
+    assert not stack, f"unclosed bracket opened at line {stack[-1][1]}"
+    assert not blocks, f"unclosed `{blocks[-1][0]}` opened at line {blocks[-1][1]}"
