@@ -61,3 +61,24 @@ def test_sass_shows_tma_and_cluster_instructions():
     sass = subprocess.run(["cuobjdump", "-sass", B.build()], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass and "SYNCS" in sass and "UCGABAR" in sass
     assert "sm_100a" in sass or "SM100a" in sass.upper() or "EF_CUDA_SM100" in sass
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity, scalar widths and pointer-ness of every entry of the ctypes table against include/ciao_cuda.h — the same
+    check test_julia_shim_static.py makes for the Julia shim's ccalls."""
+    from test_julia_shim_static import header_prototypes
+    C = ctypes
+    scalars = {"int": C.c_int, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "double": C.c_double, "float": C.c_float}
+    rets = {"int": C.c_int, "const char *": C.c_char_p}
+    protos = header_prototypes()
+    assert sorted(protos) == sorted(L.SIGNATURES)
+    for name, (res, args) in L.SIGNATURES.items():
+        c_ret, c_args = protos[name]
+        assert rets[c_ret] is res, f"{name}: return type {c_ret}"
+        assert len(args) == len(c_args), f"{name}: {len(c_args)} parameters in the header, {len(args)} in the ctypes table"
+        for k, (ct, at) in enumerate(zip(c_args, args)):
+            if ct.endswith("*"):
+                is_ptr = at in (C.c_void_p, C.c_char_p) or hasattr(at, "contents") or issubclass(at, C._Pointer)
+                assert is_ptr, f"{name}: argument {k + 1} is `{ct}` in the header but {at} in the ctypes table"
+            else:
+                assert scalars[ct] is at, f"{name}: argument {k + 1} is `{ct}` in the header but {at} in the ctypes table"
