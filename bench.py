@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--d", type=int, default=4096)
     ap.add_argument("--cpu-rows-log2", type=int, default=17)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the c2/c5/c4 blocks measured after the headline")
     ap.add_argument("--tune", default="", help="pass_threads,pass_stages,pass_ctas,seq_cluster,seq_threads")
     return ap.parse_args()
 
@@ -133,19 +134,17 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference(args, N_full, d, steps, warmup, seed_idx=SEED_IDX):
-    """Times the oracle's SVRG++ outer iteration on a bounded sample (2^cpu_rows_log2 rows of the
-    same generator, m = N_s/16·2^k) on one host core; extrapolates per-evaluation cost to N_full."""
+def _cpu_run(Ns, d, steps, warmup, seed_idx, schedule=True):
+    """`steps` SVRG++ outer iterations of the oracle on the first Ns rows of the C3 generator; per-phase seconds."""
     from oracle import oracle as orc
-    Ns = 1 << args.cpu_rows_log2
     A, b = orc.gen_rows(orc.SYN_LASSO, d, SEED_DATA, 0, Ns)
     p = orc.Problem(orc.LOSS_LS, A, b, np.full(Ns, float(Ns))).set_reg(orc.REG_NORML1, lam=Ns / 100.0)
     gamma = 1 / (7 * Ns * p.max_row_sqnorm())
     st = orc.SVRGState(p, np.zeros(d), gamma, m=Ns // 16, plus=True)
     rng = np.random.default_rng(seed_idx)
-    evals, t_inner, t_pass, t_total = 0, 0.0, 0.0, 0.0
+    evals, inner_steps, t_inner, t_pass = 0, 0, 0.0, 0.0
     for k in range(-warmup, steps):
-        m = (Ns // 16) << (max(k, 0) % SCHEDULE) if k >= 0 else Ns // 16
+        m = (Ns // 16) << ((k % SCHEDULE) if (k >= 0 and schedule) else 0)
         idx = rng.integers(1, Ns + 1, size=m, dtype=np.int64)
         st.m = m
         t0 = time.perf_counter()
@@ -155,22 +154,67 @@ def cpu_reference(args, N_full, d, steps, warmup, seed_idx=SEED_IDX):
         t2 = time.perf_counter()
         if k >= 0:
             evals += m + Ns
+            inner_steps += m
             t_inner += t1 - t0
             t_pass += t2 - t1
-            t_total += t2 - t0
-    per_eval = t_total / evals
-    return {"value": 1.0 / (per_eval * N_full), "unit": "epochs/s", "cores": 1, "kind": "port",
-            "sample": f"oracle (C restatement of the single-threaded reference; Julia is not installed) SVRG++ outer "
-                      f"iterations on {Ns} rows x {d} (same generator), {steps} steps, {evals} component gradients in "
-                      f"{t_total:.2f} s on 1 core (the reference has no threading; its BLAS calls are 1 x d gemv); "
-                      f"extrapolated per component gradient to N = {N_full}",
-            "us_per_inner_step": 1e6 * t_inner / max(1, evals - steps * Ns),
-            "us_per_pass_row": 1e6 * t_pass / (steps * Ns), "seconds": t_total}, t_total / steps
+    return {"rows": Ns, "steps": steps, "evals": evals, "seconds": t_inner + t_pass, "us_per_inner_step": 1e6 * t_inner / inner_steps,
+            "us_per_pass_row": 1e6 * t_pass / (steps * Ns), "us_per_component_gradient": 1e6 * (t_inner + t_pass) / evals}, p, st
+
+
+def cpu_reference(args, N_full, d, steps, warmup, seed_idx=SEED_IDX, extras=True):
+    """The reference's loop (oracle port, one thread like the reference) on a bounded sample: `steps` SVRG++ outer iterations
+    with the bench's own m schedule on 2^cpu_rows_log2 rows of the same generator, extrapolated per component gradient to
+    N_full.  With `extras`: the same per-gradient costs at a quarter and at four times the sample (is the extrapolation
+    linear?) and the separately labelled all-cores full-gradient pass SURVEY.md §8d allows."""
+    Ns = 1 << args.cpu_rows_log2
+    main, p, st = _cpu_run(Ns, d, steps, warmup, seed_idx)
+    per_eval = main["seconds"] / main["evals"]
+    cb = {"value": 1.0 / (per_eval * N_full), "unit": "epochs/s", "cores": 1, "kind": "port",
+          "sample": f"oracle (C restatement of the single-threaded reference; Julia is not installed) SVRG++ outer "
+                    f"iterations on {Ns} rows x {d} (same generator), {steps} steps of the bench's m schedule, {main['evals']} "
+                    f"component gradients in {main['seconds']:.2f} s on 1 core (the reference has no threading; its BLAS calls "
+                    f"are 1 x d gemv); extrapolated per component gradient to N = {N_full}",
+          "us_per_inner_step": main["us_per_inner_step"], "us_per_pass_row": main["us_per_pass_row"], "seconds": main["seconds"]}
+    if extras:
+        from oracle import oracle as orc
+        cores = orc.num_threads()
+        x = st.z_full.copy()
+        p.full_gradient_omp(x, 1.0 / Ns, cores)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            p.full_gradient_omp(x, 1.0 / Ns, cores)
+        t_omp = (time.perf_counter() - t0) / reps
+        cb["all_cores_full_gradient"] = {
+            "what": "NOT the reference's algorithm (it is single-threaded): the same per-row operation sequence with the rows split "
+                    "over all host cores, labelled separately as SURVEY.md 8d allows", "cores": cores, "rows": Ns,
+            "us_per_row": 1e6 * t_omp / Ns, "extrapolated_pass_s_at_N": t_omp / Ns * N_full, "gbs": Ns * d * 8 / t_omp / 1e9}
+        del p, st
+        lin = [main]
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 0
+        for lg, st_n, sched in ((args.cpu_rows_log2 - 2, 5, True), (args.cpu_rows_log2 + 2, 1, False)):
+            need = (1 << lg) * d * 8
+            if need * 2.5 > avail:
+                lin.append({"rows": 1 << lg, "skipped": f"needs {need / 2**30:.0f} GiB of host memory"})
+                continue
+            r, p2, st2 = _cpu_run(1 << lg, d, st_n, 0, seed_idx, schedule=sched)
+            del p2, st2
+            lin.append(r)
+        ok = [r for r in lin if "skipped" not in r]
+        cb["linearity"] = {"what": "per-gradient cost of the port at three sample sizes (the extrapolation to N assumes it is flat)",
+                           "runs": sorted(lin, key=lambda r: r["rows"]),
+                           "max_dev_us_per_pass_row": max(abs(r["us_per_pass_row"] / main["us_per_pass_row"] - 1) for r in ok),
+                           "max_dev_us_per_inner_step": max(abs(r["us_per_inner_step"] / main["us_per_inner_step"] - 1) for r in ok)}
+    return cb, main["seconds"] / steps
 
 
 def _reference_replica(job):
     args, N, d, steps, warmup, r = job
-    return cpu_reference(args, N, d, steps, warmup, seed_idx=SEED_IDX + r)
+    return cpu_reference(args, N, d, steps, warmup, seed_idx=SEED_IDX + r, extras=False)
 
 
 def run_reference(args):
@@ -178,7 +222,7 @@ def run_reference(args):
     if rank != 0:
         return
     N, d = 1 << args.rows_log2, args.d
-    steps = max(1, min(args.steps, 5))
+    steps = max(1, args.steps)          # the same number of outer iterations, on the same m schedule, as the GPU arm times
     G = args.gpus if args.workload == "svrgpp" else 1
     if G > 1:
         # the GPU arm at N > 1 runs G independent solves, one per GPU: the CPU arm runs the same G solves concurrently,
@@ -186,16 +230,16 @@ def run_reference(args):
         import multiprocessing as mp
         args.cpu_rows_log2 = min(args.cpu_rows_log2, 16)
         with mp.get_context("spawn").Pool(G) as pool:
-            res = pool.map(_reference_replica, [(args, N, d, steps, min(args.warmup, 1), r) for r in range(G)])
+            res = pool.map(_reference_replica, [(args, N, d, steps, min(args.warmup, 2), r) for r in range(G)])
         s_per_step = max(r[1] for r in res)                    # the job ends with its slowest replica
         cb = dict(res[0][0])
         cb["value"] = G * min(r[0]["value"] for r in res)      # whole job: G solves at the pace of the slowest
         cb["cores"] = G
         cb["sample"] = f"{G} concurrent replicas, one per host core, each: " + cb["sample"]
     else:
-        cb, s_per_step = cpu_reference(args, N, d, steps, min(args.warmup, 1))
+        cb, s_per_step = cpu_reference(args, N, d, steps, min(args.warmup, 2))
     line = {"impl": "reference", "metric": "epochs/s (Lasso 4M x 4096 fp64, SVRG++)", "value": cb["value"], "unit": "epochs/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * s_per_step,
+            "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * s_per_step,
             "higher_is_better": True, "scaling": "strong" if args.workload == "svrgpp-strong" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": (f"C3 Lasso N=2^{args.rows_log2} d={d} fp64 SVRG++ gamma=1/(7 L_max) m=N/16*2^(k mod 5): persistent inner epoch + "
                                     f"full-gradient pass" + (f"; {G} independent solves" if G > 1 else "")),
@@ -205,6 +249,196 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations, measured in the same run and printed under their own keys:
+# none of them is the headline `value`; each carries its own roofline figure against the measured copy peak.
+def bench_c2(local, peak, K=2):
+    """configs[1] "C2": L1-logistic N = 2^20, d = 1024 — SAGA + Finito steps (batch 1, latency-bound), their table-init passes
+    and the static-minibatch passes (HBM-bound).  SAGA_basic.jl:41-68, Finito_basic.jl:76-121, Finito_LFinito.jl:78-103."""
+    from ciaoalgorithms_jl_b200 import _lib as L
+    from ciaoalgorithms_jl_b200.engine import Engine
+    from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, csr
+    N, d = 1 << 20, 1024
+    ld = d + 8
+    out = {"workload": "C2 L1-logistic N=2^20 d=1024 fp64, NormL1(1/N), x0 = ones", "N": N, "d": d}
+    with Engine(local) as e:
+        e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0)
+        e.set_reg(L.REG_NORML1, 1.0 / N)
+        Lmax = 0.25 * e.max_row_sqnorm()
+        x0 = np.ones(d)
+        rng = HostRNG(0x1D0002)
+        f0 = sum(e.objective(x0))
+
+        def pass_stats():
+            t = e.last_timing()
+            g = t.last_pass_bytes / t.last_pass_ms / 1e6
+            return {"ms": t.last_pass_ms, "GBs": g, "frac_of_peak": g / peak, "algorithmic_bytes": int(t.last_pass_bytes)}
+
+        e.saga_init(x0, 1 / (3 * Lmax), False)
+        e.saga_init(x0, 1 / (3 * Lmax), False)
+        out["saga_table_init"] = pass_stats()
+        e.saga_steps(rng.rand_vec(N, N // 8))                       # warm-up
+        ms = 0.0
+        for _ in range(K):
+            e.saga_steps(rng.rand_vec(N, N))
+            ms += e.last_timing().last_seq_ms
+        out["saga"] = {"epochs": K, "us_per_step": 1e3 * ms / (K * N), "epochs_per_s": K / (ms / 1e3), "bytes_per_step": 24 * d + 64,
+                       "objective_start": f0, "objective": sum(e.objective(e.get_vec(L.VEC_Z))), "smids": e.last_seq_placement()}
+        gam = np.full(N, 0.999 * N / Lmax)
+        hat = 1 / np.sum(1 / gam)
+        e.finito_init(x0, gam, hat)
+        out["finito_table_init"] = pass_stats()
+        bp1 = np.arange(N + 1, dtype=np.int64)
+        e.finito_steps(rng.rand_vec(N, N // 8), bp1[: N // 8 + 1])
+        ms = 0.0
+        for _ in range(K):
+            e.finito_steps(rng.rand_vec(N, N), bp1)
+            ms += e.last_timing().last_seq_ms
+        out["finito"] = {"epochs": K, "us_per_step": 1e3 * ms / (K * N), "epochs_per_s": K / (ms / 1e3), "sweeping": 1,
+                         "objective": sum(e.objective(e.get_vec(L.VEC_Z)))}
+        for r in (4096, 65536):                                     # static minibatches: streaming passes (batch.cu)
+            e.finito_init(x0, gam, hat)
+            sw = BatchSweeper(N, r, 2, rng)
+            idx, bp = csr(sw.take(sw.d))
+            e.finito_steps(idx, bp)
+            ms = 0.0
+            for _ in range(K):
+                idx, bp = csr(sw.take(sw.d))
+                e.finito_steps(idx, bp)
+                ms += e.last_timing().last_seq_ms
+            g = K * N * (ld + 2 * d) * 8 / ms / 1e6
+            out[f"finito_batch{r}"] = {"epochs": K, "epochs_per_s": K / (ms / 1e3), "GBs": g, "frac_of_peak": g / peak,
+                                       "us_per_batch": 1e3 * ms / (K * sw.d), "objective": sum(e.objective(e.get_vec(L.VEC_Z)))}
+            e.lfinito_init(x0, gam, hat)
+            order = np.arange(1, sw.d + 1, dtype=np.int64)
+            e.lfinito_outer(order, r)
+            ms = 0.0
+            for _ in range(K):
+                e.lfinito_outer(order, r)
+                ms += e.last_timing().last_seq_ms
+            g = K * N * ld * 8 / ms / 1e6
+            out[f"lfinito_sweep_batch{r}"] = {"sweeps": K, "sweeps_per_s": K / (ms / 1e3), "GBs": g, "frac_of_peak": g / peak,
+                                              "us_per_batch": 1e3 * ms / (K * sw.d), "objective": sum(e.objective(e.get_vec(L.VEC_Z)))}
+    return out
+
+
+def bench_c5(local, peak, K=3):
+    """configs[4] "C5": sharing problem, N = 2^18 blocks of n = 1024 — ProShI block steps (batch 1: latency-bound chain per
+    column; batch 4096: HBM-bound), table init and the in-place solution.  ProShI_basic.jl:76-132."""
+    from ciaoalgorithms_jl_b200 import _lib as L
+    from ciaoalgorithms_jl_b200.engine import Engine
+    from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, csr
+    N, n = 1 << 18, 1024
+    out = {"workload": "C5 sharing N=2^18 blocks x n=1024 fp64: diag Quadratic + SqrDistL2(box) blocks, g = IndBox(-inf, 1)", "N": N, "n": n}
+    with Engine(local) as e:
+        e.gen_synthetic(L.SYNTH_SHARING, N, n, 0x5EED0005)
+        e.set_reg(L.REG_INDBOX, -np.inf, np.ones(n))
+        gam = 0.999 * N / np.full(N, 10.0 + 10.0 * N)
+        e.proshi_init(np.zeros(n), gam, float(np.sum(gam)))
+        e.proshi_init(np.zeros(n), gam, float(np.sum(gam)))
+        t = e.last_timing()
+        g = t.last_pass_bytes / t.last_pass_ms / 1e6
+        out["table_init"] = {"ms": t.last_pass_ms, "GBs": g, "frac_of_peak": g / peak}
+        rng = HostRNG(0x1D0005)
+        for r in (1, 4096):
+            sw = BatchSweeper(N, r, 2, rng)
+            idx, bp = csr(sw.take(sw.d))
+            e.proshi_steps(idx, bp)
+            ms = 0.0
+            for _ in range(K):
+                idx, bp = csr(sw.take(sw.d))
+                e.proshi_steps(idx, bp)
+                ms += e.last_timing().last_seq_ms
+            ga, gd = 24.0 * n * N * K / ms / 1e6, 32.0 * n * N * K / ms / 1e6
+            out[f"proshi_batch{r}"] = {"sweeps": K, "us_per_block": 1e3 * ms / (K * N), "sweeps_per_s": K / (ms / 1e3),
+                                       "GBs_algorithmic_24n": ga, "GBs_dram_32n": gd, "frac_of_peak_dram": gd / peak}
+        e.proshi_solution(None)
+        e.proshi_solution(None)
+        t = e.last_timing()
+        g = t.last_pass_bytes / t.last_pass_ms / 1e6
+        out["solution_inplace"] = {"ms": t.last_pass_ms, "GBs": g, "frac_of_peak": g / peak}
+        out["sum_x_first3"] = e.table_colsum()[:3].tolist()
+    return out
+
+
+def bench_c4(local, rank, world, peak, d, K, W, init_comm, barrier, max_over_ranks, same_on_all_ranks):
+    """configs[3] "C4": Lasso rows sharded over the GPUs — the full-gradient pass (SVRG_basic.jl:58-63 over a sharded F) with
+    min(2^22, 2^24/G) rows per GPU (N = 2^24 in total at 4 and 8 GPUs) and the SAGA table-init pass (SAGA_basic.jl:41-47) with
+    min(2^21, 2^24/G) rows + their table rows per GPU, each closed by the exchange of the d-vector.  Weak scaling."""
+    from ciaoalgorithms_jl_b200 import _lib as L
+    from ciaoalgorithms_jl_b200.engine import Engine
+    out = {}
+    ld = (d + 3) // 4 * 4 + 8
+    for what, rows in (("full_gradient", min(1 << 22, (1 << 24) // world)), ("saga_table_init", min(1 << 21, (1 << 24) // world))):
+        N = rows * world
+        with Engine(local) as e:
+            e.gen_synthetic(L.SYNTH_LASSO, N, d, SEED_DATA, scale=float(N), row0=rank * rows, n_rows=rows)
+            e.set_reg(L.REG_NORML1, N / 100.0)
+            init_comm(e)
+            x = np.full(d, 1e-3)
+            e.set_vec(L.VEC_X, x)
+            gamma = 1e-9
+
+            def one(read=False):
+                if what == "full_gradient":
+                    return e.full_gradient(None, 1.0 / N, out=read)
+                e.saga_init(x, gamma, False)
+                return e.get_vec(L.VEC_AV) if read else None
+
+            for _ in range(W):
+                one()
+            barrier()
+            kms = []
+            e.timer_begin()
+            for _ in range(K):
+                one()
+                kms.append(e.last_timing().last_pass_ms)
+            ms = max_over_ranks(e.timer_end()) / K
+            barrier()
+            kernel_ms = max_over_ranks(float(np.mean(kms)))
+            res = one(read=True)
+            bytes_per_gpu = rows * (ld + (d if what == "saga_table_init" else 0)) * 8
+            out[what] = {"N_total": N, "rows_per_gpu": rows, "ms_per_pass": ms, "kernel_ms": kernel_ms, "tail_us": 1e3 * (ms - kernel_ms),
+                         "aggregate_gbs": world * bytes_per_gpu / ms / 1e6, "kernel_gbs_per_gpu": bytes_per_gpu / kernel_ms / 1e6,
+                         "frac_of_peak_per_gpu": bytes_per_gpu / ms / 1e6 / peak, "epochs_per_s_2p22_rows": world * (rows / float(1 << 22)) / (ms / 1e3),
+                         "bitwise_equal_across_ranks": bool(same_on_all_ranks(res)), "checksum": float(np.sum(res)), "passes": K}
+            barrier()
+    return out
+
+
+def bench_host_rows(local):
+    """F handed over from HOST memory (ciao_set_rows, what `solver(x0; F=...)` does with a Julia F): seconds and GB/s of the one big
+    copy that the e2e figure amortises over the solve.  2^20 x 4096 (34 GB) when the host has the memory, else smaller."""
+    from ciaoalgorithms_jl_b200 import _lib as L
+    from ciaoalgorithms_jl_b200.engine import Engine
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 8 << 30
+    d = 4096
+    lg = 20
+    while lg > 14 and (1 << lg) * d * 8 * 1.3 > avail:
+        lg -= 1
+    n = 1 << lg
+    blk, rhs = Engine.gen_host(L.SYNTH_LASSO, d, SEED_DATA, 0, 1 << 12)
+    A = np.empty((n, d))
+    for r0 in range(0, n, 1 << 12):
+        A[r0:r0 + (1 << 12)] = blk
+    b = np.tile(rhs, n >> 12)
+    out = {"rows": n, "d": d, "bytes": int(A.nbytes)}
+    with Engine(local) as e:
+        t0 = time.perf_counter()
+        e.set_rows(L.LOSS_LS, A, b, float(n))
+        e.sync()
+        dt = time.perf_counter() - t0
+        out.update({"seconds": dt, "GBs": A.nbytes / dt / 1e9, "source": "pageable host memory (numpy)"})
+        x = np.full(d, 1e-3)
+        g1 = e.full_gradient(x, 1.0 / n)
+        out["checksum"] = float(np.sum(g1))
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -265,12 +499,22 @@ def main():
     e.set_reg(L.REG_NORML1, N / 100.0)
     e.sync()
     setup_s = time.perf_counter() - t0
-    def init_comm():
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(uid, 0)
-        e.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    def init_comm(eng=None):
+        """NCCL communicator (its all-gather carries the per-row step scalars of a sharded solve) + the one-shot peer-memory
+        exchange that the passes' all-reduce uses (ciao_comm_p2p_*: deterministic rank-ordered sum in the pass's tail kernel)."""
+        eng = e if eng is None else eng
+        obj = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, 0)
+        eng.comm_init(obj[0], rank, world)
+        if os.environ.get("CIAO_BENCH_EXCHANGE", "p2p") == "p2p":
+            hs = [None] * world
+            dist.all_gather_object(hs, eng.comm_p2p_handle())
+            eng.comm_p2p_attach(rank, world, hs)
+
+    def same_on_all_ranks(a):
+        blobs = [None] * world
+        dist.all_gather_object(blobs, np.ascontiguousarray(a).tobytes())
+        return all(b == blobs[0] for b in blobs)
 
     if world > 1 and not replicas:       # replicas: the solves run without a communicator (a pass with one all-reduces)
         init_comm()
@@ -366,6 +610,19 @@ def main():
         pass_ms = max_over_ranks(float(np.mean(pass_ms_list)))
         inner_steps = sum(m_of(k, N) for k in range(K))
         x_dev_path = e.get_vec(L.VEC_Z_FULL)
+        smids = e.last_seq_placement()
+        # latency floor of the cluster exchange, measured on this GPU with the kernel's own st.async → mbarrier path (seq_floor.cu):
+        # every 8-CTA cluster position reports its round time; the position the inner kernel ran on is looked up by its SM ids
+        fl = e.measure_exchange(8, 4, 100000, 1)
+        fl0 = e.measure_exchange(8, 4, 100000, 0)
+        here = [k for k, r in enumerate(fl) if sorted(r[2]) == sorted(smids)]
+        floor = {"what": "ns per round of exchange + partial sum + dependent next message (mode 1) / exchange only (mode 0), all "
+                         "cluster positions of the GPU measured at once; `here` = the position the inner kernel ran on",
+                 "mode1_ns_min": min(r[0] for r in fl), "mode1_ns_median": float(np.median([r[0] for r in fl])),
+                 "mode1_ns_max": max(r[0] for r in fl), "mode0_ns_min": min(r[0] for r in fl0),
+                 "mode0_ns_median": float(np.median([r[0] for r in fl0])), "mode0_ns_max": max(r[0] for r in fl0),
+                 "here_mode1_ns": fl[here[0]][0] if here else None, "here_mode0_ns": fl0[here[0]][0] if here else None,
+                 "cycles_mode1_median": float(np.median([r[1] for r in fl]))}
         f_end = sum(e.objective(x_dev_path))
         f_start = sum(e.objective(x0))
         del idx_dev
@@ -403,7 +660,10 @@ def main():
                  "inner_kernel": {"bound": "latency", "kernel": "seq_kernel (persistent 8-CTA cluster, one launch per epoch)",
                                   "us_per_step": 1e3 * float(np.sum(seq_ms_list)) / inner_steps,
                                   "share_of_step_time": float(np.sum(seq_ms_list)) / ms,
-                                  "exchange_floor_us": 240 / 1965.0, "algorithmic_bytes_per_step": 8 * d + 32,
+                                  "exchange_floor_us": (floor["here_mode1_ns"] or floor["mode1_ns_median"]) / 1e3,
+                                  "exchange_floor": floor, "smids": smids,
+                                  "us_per_step_by_epoch": [round(1e3 * v / m_of(k, N), 4) for k, v in enumerate(seq_ms_list)],
+                                  "algorithmic_bytes_per_step": 8 * d + 32,
                                   "achieved_gbs": (8 * d + 32) * inner_steps / float(np.sum(seq_ms_list)) / 1e6},
                  "full_gradient": {"rows_per_gpu": pass_rows, "kernel_ms": pass_ms,
                                    "aggregate_gbs": (world if replicas else 1) * N * ld * 8 / pass_ms / 1e6,
@@ -411,9 +671,13 @@ def main():
         if replicas:
             # The part of the path that shards: the same full-gradient pass row-windowed over the ranks (N/G rows each) +
             # one NCCL allreduce of the d-vector, timed after the solves (SVRG_basic.jl:58-63 over a sharded F).
+            g_local = e.full_gradient(xs, 1.0 / N)                  # this rank alone, all N rows, no exchange
             init_comm()
             lo, hi = (rank * N) // world, ((rank + 1) * N) // world
             e.set_pass_window(lo, hi - lo)
+            g_sharded = e.full_gradient(xs, 1.0 / N)                # N/G rows per rank + exchange
+            rel_err = float(np.linalg.norm(g_sharded - g_local) / np.linalg.norm(g_local))
+            bitwise = same_on_all_ranks(g_sharded)
             e.set_vec(L.VEC_X, xs)
             for _ in range(W):
                 e.full_gradient(None, 1.0 / N, out=False)
@@ -427,8 +691,11 @@ def main():
             barrier()
             sh_kernel_ms = max_over_ranks(float(np.mean(sh_ms_list)))
             extra["full_gradient_sharded"] = {
-                "what": f"one full-gradient pass over the C3 rows, row-windowed over {world} GPUs + NCCL allreduce of the d-vector",
+                "what": f"one full-gradient pass over the C3 rows, row-windowed over {world} GPUs + exchange of the d-vector "
+                        f"({'one-shot peer-memory exchange fused into the tail kernel of the pass' if os.environ.get('CIAO_BENCH_EXCHANGE', 'p2p') == 'p2p' else 'ncclAllReduce'})",
                 "rows_per_gpu": hi - lo, "ms_per_pass": sh_ms, "kernel_ms": sh_kernel_ms, "passes": K,
+                "tail_us": 1e3 * (sh_ms - sh_kernel_ms),
+                "rel_err_vs_local": max_over_ranks(rel_err), "rel_err_bound": 1e-13, "bitwise_equal_across_ranks": bool(bitwise),
                 "aggregate_gbs": N * ld * 8 / sh_ms / 1e6, "kernel_gbs_per_gpu": (hi - lo) * ld * 8 / sh_kernel_ms / 1e6,
                 "speedup_vs_local_pass": pass_ms / sh_ms}
         scaling = "strong" if args.workload == "svrgpp-strong" else "weak"   # default: per-GPU work fixed (one solve per GPU)
@@ -447,8 +714,12 @@ def main():
     # dram__bytes_read.sum + dram__bytes_write.sum of row_pass_kernel from the committed `ncu --set full` capture
     # (profiles/ncu_row_pass_r1.csv: 137.90 GB read + 0.11 GB written per launch at N=2^22, d=4096, one GPU — the writes are
     # the 32 B/row step scalars a single-process pass leaves for the inner kernel; multi-rank passes write 12 MB); null otherwise
-    traffic = ((138.011e9 if (world == 1 or replicas) else 137.899e9)
-               if (rows_per_gpu == 1 << 22 and d == 4096 and (world == 1 or weak_pass or replicas)) else None)
+    traffic, traffic_src = None, None
+    cap = os.path.join(ROOT, "profiles", "ncu_row_pass_traffic.json")
+    if os.path.exists(cap) and rows_per_gpu == 1 << 22 and d == 4096 and (world == 1 or weak_pass or replicas):
+        cj = json.load(open(cap))
+        traffic = float(cj["dram_bytes_read"] + cj["dram_bytes_write"])
+        traffic_src = cj["source"]
     line = {
         "metric": ("epochs/s (SAGA table-init passes, 2^22-row epochs)" if table_init else
                    "epochs/s (full-gradient passes, 2^22-row epochs)" if weak_pass else
@@ -459,17 +730,24 @@ def main():
                    "epoch": "N component-gradient evaluations; step = (m + N)/N epochs", "seeds": [SEED_DATA, SEED_IDX]},
         "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "row_pass_kernel (SAGA table init: read rows + write table)" if table_init else "row_pass_kernel (full gradient)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes},
         "clocks": clocks, "setup": {"what": "ciao_gen_synthetic (rows generated in HBM)", "seconds": setup_s},
     }
     line.update(extra)
+    e.close()
+    if args.workload == "svrgpp" and not args.headline_only:
+        if world == 1:
+            line["c2"] = bench_c2(local, peak)
+            line["c5"] = bench_c5(local, peak)
+            line["setup_host_rows"] = bench_host_rows(local)
+        else:
+            line["c4"] = bench_c4(local, rank, world, peak, d, K, W, init_comm, barrier, max_over_ranks, same_on_all_ranks)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference(args, N, d, 5, 1)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
-    e.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -49,6 +49,8 @@ SIGNATURES = {
     "ciao_gen_host": (i32, [i32, i64, C.c_uint64, i64, i64, C.c_void_p, C.c_void_p]),
     "ciao_comm_unique_id": (i32, [C.c_void_p]),
     "ciao_comm_init": (i32, [_ctx, C.c_void_p, i32, i32]),
+    "ciao_comm_p2p_handle": (i32, [_ctx, C.c_void_p]),
+    "ciao_comm_p2p_attach": (i32, [_ctx, i32, i32, C.c_void_p]),
     "ciao_set_pass_window": (i32, [_ctx, i64, i64]),
     "ciao_rows_ipc_handle": (i32, [_ctx, C.c_void_p]),
     "ciao_attach_peer_rows": (i32, [_ctx, i32, C.c_void_p, C.c_void_p, C.c_void_p, i32]),
@@ -77,6 +79,9 @@ SIGNATURES = {
     "ciao_timer_begin": (i32, [_ctx]),
     "ciao_timer_end": (i32, [_ctx, C.POINTER(C.c_float)]),
     "ciao_last_timing": (i32, [_ctx, C.POINTER(Timing)]),
+    "ciao_last_seq_placement": (i32, [_ctx, C.POINTER(i32), C.POINTER(i32)]),
+    "ciao_measure_exchange": (i32, [_ctx, i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                    C.POINTER(i32)]),
     "ciao_set_tuning": (i32, [_ctx, i32, i32, i32, i32, i32]),
 }
 

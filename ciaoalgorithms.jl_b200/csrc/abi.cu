@@ -161,7 +161,9 @@ static int check_err_flag(ciao_ctx *c) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (h) {
         CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
-        CIAO_FAIL(CIAO_ERR_INVALID, "index out of range 1..N (or malformed batch_ptr / batch_order) in a previous call");
+        if (h == 3) CIAO_FAIL(CIAO_ERR_COMM, "peer exchange timed out: a rank of the collective did not arrive (ciao_comm_p2p_attach)");
+        CIAO_FAIL(CIAO_ERR_INVALID, "index out of range 1..N (or malformed batch_ptr / batch_order) in a previous call; the steps of that "
+                  "call were not executed");
     }
     return CIAO_OK;
 }
@@ -313,6 +315,8 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
         for (auto ev : evs) CUDA_TRY(cudaEventCreate(ev));
         CUDA_TRY(cudaMalloc(&c->err_dev, sizeof(int)));
         CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
+        CUDA_TRY(cudaMalloc(&c->seq_smid, 16 * sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(c->seq_smid, 0xff, 16 * sizeof(int), c->stream));
         return CIAO_OK;
     };
     const int rc = init_device_objects();
@@ -330,7 +334,7 @@ extern "C" int ciao_destroy(ciao_ctx *c) {
     cudaStreamSynchronize(c->stream);
     ciao_comm_destroy(c);
     free_problem(c);
-    cudaFree(c->ws); cudaFree(c->idx_raw); cudaFree(c->idx_prep); cudaFree(c->ptr_dev); cudaFree(c->err_dev); cudaFree(c->grid_bar);
+    cudaFree(c->ws); cudaFree(c->idx_raw); cudaFree(c->idx_prep); cudaFree(c->ptr_dev); cudaFree(c->err_dev); cudaFree(c->grid_bar); cudaFree(c->seq_smid);
     cudaEvent_t evs[] = {c->ev_pa, c->ev_pb, c->ev_sa, c->ev_sb, c->tm_a, c->tm_b};
     for (auto ev : evs) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -551,27 +555,17 @@ extern "C" int ciao_gen_synthetic(ciao_ctx *c, int kind, int64_t N_total, int64_
 // ---------------------------------------------------------------------------
 // passes
 // ---------------------------------------------------------------------------
-__global__ void finish_kernel(const double *partial, const double *base, double scale, double den, int64_t d_pad, double *out) {
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j >= d_pad) return;
-    double v = partial[j];
-    if (den != 1.0) v = __ddiv_rn(v, den);
-    if (scale != 1.0) v = __dmul_rn(scale, v);
-    out[j] = base ? __dadd_rn(base[j], v) : v;
-}
-// out = base + scale·(Σ/den)
-static int run_finish(ciao_ctx *c, const double *base, double scale, double den, double *out) {
-    finish_kernel<<<blocks_for(c->d_pad), 256, 0, c->stream>>>(c->partial, base, scale, den, c->d_pad, out);
-    CUDA_TRY(cudaGetLastError());
-    c->timing.launches += 1;
-    return CIAO_OK;
+// one streaming pass with its closing update out = base + scale·(Σ/den) fused into the pass's tail kernel (pass.cu)
+static int run_pass_finish(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz, const double *base, double scale, double den,
+                           double *out) {
+    const FinishSpec f{base, scale, den, out};
+    return run_row_pass(c, mode, x_dev, cache_cz, &f);
 }
 
 extern "C" int ciao_full_gradient(ciao_ctx *c, const double *x, double scale, double *out) {
     CIAO_TRY(need_rows(c, "ciao_full_gradient", false));
     if (x) CIAO_TRY(upload_vec(c, CIAO_VEC_X, x));
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X)));
-    CIAO_TRY(run_finish(c, nullptr, scale, 1.0, ctx_vec(c, CIAO_VEC_TMP)));
+    CIAO_TRY(run_pass_finish(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X), false, nullptr, scale, 1.0, ctx_vec(c, CIAO_VEC_TMP)));
     if (out) {
         CUDA_TRY(cudaMemcpyAsync(out, ctx_vec(c, CIAO_VEC_TMP), (size_t)c->d * sizeof(double), cudaMemcpyDefault, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -621,8 +615,8 @@ extern "C" int ciao_svrg_init(ciao_ctx *c, const double *x0, double gamma, int p
     CIAO_TRY(upload_vec(c, CIAO_VEC_Z_FULL, x0));                                  // z_full = copy(x0)  :64
     CIAO_TRY(copy_vec(c, CIAO_VEC_W, CIAO_VEC_Z_FULL));                            // w = copy(x0)       :66
     CUDA_TRY(cudaMemsetAsync(ctx_vec(c, CIAO_VEC_Z), 0, (size_t)c->d_pad * 8, c->stream));  // z = 0        :65
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz));  // :58-63
-    return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
+    return run_pass_finish(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz, nullptr, 1.0, (double)c->N_total,
+                           ctx_vec(c, CIAO_VEC_AV));                                  // :58-63
 }
 
 extern "C" int ciao_svrg_epoch(ciao_ctx *c, const int64_t *idx, int64_t m) {
@@ -633,8 +627,8 @@ extern "C" int ciao_svrg_epoch(ciao_ctx *c, const int64_t *idx, int64_t m) {
     CIAO_TRY(fetch_raw_indices(c, idx, m, &raw));
     CIAO_TRY(launch_prep_indices(c, raw, m, c->N_total, c->idx_prep));
     CIAO_TRY(run_seq(c, ALG_SVRG, c->idx_prep, m, (double)m));                     // :73-86
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz));  // :87-92
-    return run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV));
+    return run_pass_finish(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz, nullptr, 1.0, (double)c->N_total,
+                           ctx_vec(c, CIAO_VEC_AV));                                  // :87-92
 }
 
 // ---------------------------------------------------------------------------
@@ -666,8 +660,7 @@ extern "C" int ciao_finito_adaptive_init(ciao_ctx *c, const double *x0, double a
     if (!c->adapt_scal) CUDA_TRY(cudaMalloc(&c->adapt_scal, 8 * sizeof(double)));
     if (!c->adapt_counters) CUDA_TRY(cudaMalloc(&c->adapt_counters, 4 * sizeof(int64_t)));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X0)));                  // sum(∇f)  :90
-    CIAO_TRY(run_finish(c, nullptr, 1.0, 1.0, ctx_vec(c, CIAO_VEC_TMP)));
+    CIAO_TRY(run_pass_finish(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X0), false, nullptr, 1.0, 1.0, ctx_vec(c, CIAO_VEC_TMP)));  // sum(∇f)  :90
     int chunks = 0;
     CIAO_TRY(run_adaptive_init(c, ctx_vec(c, CIAO_VEC_X0), alpha, &chunks));        // :65-87, partial sums of x0 ./ γ_i
     launch_reduce_ws(c, c->ws, c->ws + (size_t)chunks * c->d_pad, chunks, c->partial, c->partial + c->d_pad, 0, 1);
@@ -739,8 +732,8 @@ extern "C" int ciao_saga_init(ciao_ctx *c, const double *x0, double gamma, int s
     CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(alloc_table(c));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
-    CIAO_TRY(run_row_pass(c, PASS_SAGA_INIT, ctx_vec(c, CIAO_VEC_X0)));            // :41-45
-    CIAO_TRY(run_finish(c, nullptr, 1.0, (double)c->N_total, ctx_vec(c, CIAO_VEC_AV)));  // :47
+    CIAO_TRY(run_pass_finish(c, PASS_SAGA_INIT, ctx_vec(c, CIAO_VEC_X0), false, nullptr, 1.0, (double)c->N_total,
+                             ctx_vec(c, CIAO_VEC_AV)));                              // :41-47
     saga_z0_kernel<<<blocks_for(c->d_pad), 256, 0, c->stream>>>(ctx_vec(c, CIAO_VEC_X0), ctx_vec(c, CIAO_VEC_Z), c->d_pad, gamma, c->reg);  // :48
     CUDA_TRY(cudaGetLastError());
     c->timing.launches += 1;
@@ -776,8 +769,8 @@ extern "C" int ciao_finito_init(ciao_ctx *c, const double *x0, const double *gam
     CIAO_TRY(alloc_table(c));
     CIAO_TRY(set_gammas(c, gamma_N, true));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
-    CIAO_TRY(run_row_pass(c, PASS_FINITO_INIT, ctx_vec(c, CIAO_VEC_X0)));          // :76-80
-    CIAO_TRY(run_finish(c, nullptr, hat_gamma, 1.0, ctx_vec(c, CIAO_VEC_AV)));     // :83
+    CIAO_TRY(run_pass_finish(c, PASS_FINITO_INIT, ctx_vec(c, CIAO_VEC_X0), false, nullptr, hat_gamma, 1.0,
+                             ctx_vec(c, CIAO_VEC_AV)));                              // :76-83
     return prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, hat_gamma);                        // :84
 }
 
@@ -850,8 +843,8 @@ extern "C" int ciao_lfinito_init(ciao_ctx *c, const double *x0, const double *ga
     CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(set_gammas(c, gamma_N, true));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X0)));                 // :68-72
-    CIAO_TRY(run_finish(c, ctx_vec(c, CIAO_VEC_X0), -(hat_gamma / (double)c->N_total), 1.0, ctx_vec(c, CIAO_VEC_AV)));
+    CIAO_TRY(run_pass_finish(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X0), false, ctx_vec(c, CIAO_VEC_X0), -(hat_gamma / (double)c->N_total), 1.0,
+                             ctx_vec(c, CIAO_VEC_AV)));                              // :68-72
     CIAO_TRY(copy_vec(c, CIAO_VEC_Z, CIAO_VEC_AV));                                // placeholders, ctor :33-35
     return copy_vec(c, CIAO_VEC_Z_FULL, CIAO_VEC_AV);
 }
@@ -876,8 +869,8 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
         total += (j == nb) ? last_len : r;
     }
     CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z_FULL, c->hat_gamma));             // :83
-    CIAO_TRY(run_row_pass(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz));  // :85-88
-    CIAO_TRY(run_finish(c, ctx_vec(c, CIAO_VEC_Z_FULL), -(c->hat_gamma / (double)N), 1.0, ctx_vec(c, CIAO_VEC_AV)));
+    CIAO_TRY(run_pass_finish(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz, ctx_vec(c, CIAO_VEC_Z_FULL),
+                             -(c->hat_gamma / (double)N), 1.0, ctx_vec(c, CIAO_VEC_AV)));  // :85-88
     if (total == 0) return CIAO_OK;
     if (r >= BATCH_MIN_ROWS && c->n_rows == c->N_total) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
         CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
@@ -1027,6 +1020,15 @@ extern "C" int ciao_timer_end(ciao_ctx *c, float *ms) {
     CUDA_TRY(cudaEventRecord(c->tm_b, c->stream));
     CUDA_TRY(cudaEventSynchronize(c->tm_b));
     CUDA_TRY(cudaEventElapsedTime(ms, c->tm_a, c->tm_b));
+    return CIAO_OK;
+}
+
+extern "C" int ciao_last_seq_placement(ciao_ctx *c, int *smid16, int *n_ctas) {
+    if (!c || !smid16 || !n_ctas) CIAO_FAIL(CIAO_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(smid16, c->seq_smid, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *n_ctas = c->seq_smid_n;
     return CIAO_OK;
 }
 

@@ -52,6 +52,14 @@ struct PeerTable {
     int n;
 };
 
+// Exchange arena: mail[2][CIAO_MAX_PEERS][P2P_CAP] doubles (double-buffered by collective parity: a slot of collective n is
+// rewritten by collective n + 2, which a peer can only start after it has seen this rank's flag of n + 1, i.e. after this
+// rank has finished reading n), then flags[CIAO_MAX_PEERS][P2P_CHUNKS] sequence numbers (one per source rank and 32-column chunk).
+#define P2P_CAP 8224                           // d_pad ≤ 8192 columns + the scalar, padded to a multiple of 32
+#define P2P_CHUNKS (P2P_CAP / 32)
+#define P2P_MAIL_DOUBLES ((size_t)2 * CIAO_MAX_PEERS * P2P_CAP)
+#define P2P_ARENA_BYTES (P2P_MAIL_DOUBLES * 8 + (size_t)CIAO_MAX_PEERS * P2P_CHUNKS * 4 + 256)
+
 struct RegParams {
     int kind;
     double lambda;       // NormL1
@@ -110,12 +118,22 @@ struct ciao_ctx {
     size_t idx_cap = 0, ptr_cap = 0;
     int64_t staged = 0;
     int *err_dev = nullptr;
+    int *seq_smid = nullptr;           // [16] SM ids of the CTAs of the last sequential cluster kernel (ciao_last_seq_placement)
+    int seq_smid_n = 0;
     unsigned int *grid_bar = nullptr;  // grid barrier counter of the persistent minibatch kernel (batch.cu)
     double *host_pin = nullptr; size_t host_pin_bytes = 0;
     // comm
     void *nccl_comm = nullptr; int rank = 0, world = 1;
     PeerTable peers{};                 // filled by ciao_attach_peer_rows (n = 0: not attached)
     void *peer_mapped[CIAO_MAX_PEERS] = {};  // cudaIpcOpenMemHandle results to close
+    // one-shot peer-memory exchange (comm.cu, pass.cu pass_tail_kernel): every rank owns an arena of mail slots + flags that the
+    // peers map (CUDA IPC, or directly inside one process) and store into; deterministic rank-ordered sums, no NCCL on the pass path
+    double *p2p_arena = nullptr;               // mine
+    double *p2p_peer[CIAO_MAX_PEERS] = {};     // every rank's arena as addressed from this GPU (own entry = p2p_arena)
+    void *p2p_mapped[CIAO_MAX_PEERS] = {};     // cudaIpcOpenMemHandle results to close
+    bool p2p_ready = false;
+    uint32_t p2p_seq = 0;                      // collectives issued so far (all ranks in lock step)
+    uint64_t p2p_timeout_ns = 20000000000ull;  // a peer that never shows up ends the wait with CIAO_ERR_COMM, not a hang
     // tuning
     int pass_threads = 0, pass_stages = 0, pass_ctas = 0, seq_cluster = 0, seq_threads = 0;
     ciao_timing timing{0, 0, 0, 0, 0};

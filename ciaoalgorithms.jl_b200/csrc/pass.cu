@@ -15,6 +15,8 @@
 // registers.  CTA partial d-vectors go to a workspace and are summed by
 // reduce_ws_kernel in a fixed order: no floating-point atomics anywhere, so the
 // result is bitwise reproducible run to run (test_lasso.jl:192 `==` tests).
+#include <string.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -216,6 +218,168 @@ static inline void launch_reduce_ws(ciao_ctx *c, const double *ws, const double 
 }
 
 // ---------------------------------------------------------------------------
+// The tail of a pass, ONE kernel: fixed-order sum of the CTA partials → (G ranks: one-shot exchange over peer memory, sum in
+// rank order) → out = base + scale·(Σ/den).  Replaces reduce_ws_kernel → ncclAllReduce → finish_kernel (round 1: 0.265 ms
+// per pass at 8 GPUs, ten times what a 32 KiB exchange should cost).
+//   block = 32 columns × REDUCE_SLICES slices; column j < d_pad comes from ws[b][j], column j == d_pad is the scalar
+//   (Σ_b fws[b], or max_b for the row-norm pass).  Exchange, per 32-column chunk and independent of all other chunks:
+//   warp r < world stores the chunk into rank r's mail slot [seq & 1][my rank] (NVLink / local), one thread per peer
+//   fences (system scope) and raises flag[my rank][chunk] = seq there, then waits for flag[r][chunk] ≥ seq in its own
+//   arena (bounded wait: a missing peer surfaces as CIAO_ERR_COMM), and the chunk is summed over the slots 0 … world − 1 in
+//   rank order — bit-identical on every rank, no floating-point atomics, no dependence on arrival order.
+struct TailArgs {
+    const double *ws, *fws;      // [G][d_pad], [G] (fws may be null: no scalar column)
+    int G, len, fmax_mode, with_vec, chunk0;
+    int64_t d_pad;
+    int world, rank;
+    uint32_t seq;
+    uint64_t timeout_ns;
+    double *arena[CIAO_MAX_PEERS];
+    double *sum_out;             // [len]: the raw all-rank sum (vector, then the scalar)
+    const double *base;          // finish (out == nullptr: none)
+    double scale, den;
+    double *out;
+    int *err;
+};
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(32 * REDUCE_SLICES) pass_tail_kernel(const TailArgs a) {
+    __shared__ double sm[REDUCE_SLICES][33];
+    const int x = threadIdx.x, y = threadIdx.y;
+    const int chunk = blockIdx.x + a.chunk0;
+    const int64_t j = chunk * 32ll + x;
+    const bool scalar_col = a.fws != nullptr && j == a.d_pad;
+    const bool is_max = scalar_col && a.fmax_mode;
+    double s = 0.0;
+    if (j < a.d_pad) {
+        if (a.with_vec)
+            for (int b = y; b < a.G; b += REDUCE_SLICES) s += a.ws[(size_t)b * a.d_pad + j];
+    } else if (scalar_col) {
+        for (int b = y; b < a.G; b += REDUCE_SLICES) s = a.fmax_mode ? fmax(s, a.fws[b]) : s + a.fws[b];
+    }
+    sm[y][x] = s;
+    __syncthreads();
+    double t = 0.0;
+    if (y == 0) {
+#pragma unroll
+        for (int q = 0; q < REDUCE_SLICES; ++q) t = is_max ? fmax(t, sm[q][x]) : t + sm[q][x];
+    }
+    if (a.world > 1) {
+        const int buf = (int)(a.seq & 1u);
+        __syncthreads();
+        if (y == 0) sm[0][x] = t;
+        __syncthreads();
+        if (y < a.world && j < a.len)    // warp y → rank y's arena, slot [buf][my rank], 256 contiguous bytes
+            st_relaxed_sys_f64(a.arena[y] + ((size_t)buf * CIAO_MAX_PEERS + a.rank) * P2P_CAP + j, sm[0][x]);
+        __syncwarp();
+        if (x == 0 && y < a.world) {
+            uint32_t *flags_there = reinterpret_cast<uint32_t *>(a.arena[y] + P2P_MAIL_DOUBLES);
+            __threadfence_system();       // the warp's stores (ordered before this thread by the warp barrier) before the flag
+            st_release_sys_u32(flags_there + a.rank * P2P_CHUNKS + chunk, a.seq);
+            const uint32_t *flag_here = reinterpret_cast<const uint32_t *>(a.arena[a.rank] + P2P_MAIL_DOUBLES) + y * P2P_CHUNKS + chunk;
+            const uint64_t t0 = global_timer_ns();
+            while ((int32_t)(ld_acquire_sys_u32(flag_here) - a.seq) < 0) {
+                if (global_timer_ns() - t0 > a.timeout_ns) {
+                    atomicExch(a.err, 3);
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        if (y == 0 && j < a.len) {
+            const double *mine = a.arena[a.rank] + (size_t)buf * CIAO_MAX_PEERS * P2P_CAP + j;
+            t = 0.0;
+            for (int r = 0; r < a.world; ++r) {
+                const double v = ld_relaxed_sys_f64(mine + (size_t)r * P2P_CAP);
+                t = is_max ? fmax(t, v) : t + v;
+            }
+        }
+    }
+    if (y == 0 && j < a.len) {
+        a.sum_out[j] = t;
+        if (a.out && j < a.d_pad) {
+            double v = t;
+            if (a.den != 1.0) v = __ddiv_rn(v, a.den);
+            if (a.scale != 1.0) v = __dmul_rn(a.scale, v);
+            a.out[j] = a.base ? __dadd_rn(a.base[j], v) : v;
+        }
+    }
+}
+
+// out = base + scale·(partial/den)   (the NCCL route and the non-row passes; the row passes fuse it into pass_tail_kernel)
+__global__ void finish_kernel(const double *partial, const double *base, double scale, double den, int64_t d_pad, double *out) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= d_pad) return;
+    double v = partial[j];
+    if (den != 1.0) v = __ddiv_rn(v, den);
+    if (scale != 1.0) v = __dmul_rn(scale, v);
+    out[j] = base ? __dadd_rn(base[j], v) : v;
+}
+struct FinishSpec {
+    const double *base;
+    double scale, den;
+    double *out;
+};
+static int run_finish(ciao_ctx *c, const double *base, double scale, double den, double *out) {
+    finish_kernel<<<(int)((c->d_pad + 255) / 256), 256, 0, c->stream>>>(c->partial, base, scale, den, c->d_pad, out);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+static void fill_exchange(ciao_ctx *c, TailArgs &t, bool exchange) {
+    t.world = exchange ? c->world : 1;
+    t.rank = c->rank;
+    t.seq = 0;
+    t.timeout_ns = c->p2p_timeout_ns;
+    for (int r = 0; r < CIAO_MAX_PEERS; ++r) t.arena[r] = c->p2p_peer[r];
+    t.err = c->err_dev;
+    if (exchange) t.seq = ++c->p2p_seq;
+}
+
+// in-place all-reduce of a plain device buffer through the peer exchange (collective; count ≤ P2P_CAP)
+int run_p2p_allreduce(ciao_ctx *c, double *buf, int64_t count, int op_max) {
+    if (count < 1 || count > P2P_CAP || (op_max && count != 1))
+        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "peer exchange: 1..%d doubles per collective (max: one scalar)", P2P_CAP);
+    TailArgs t;
+    memset(&t, 0, sizeof(t));
+    if (op_max) {   // the scalar column carries the maximum
+        t.ws = nullptr; t.fws = buf; t.d_pad = 0; t.with_vec = 0; t.fmax_mode = 1;
+    } else {
+        t.ws = buf; t.fws = nullptr; t.d_pad = count; t.with_vec = 1; t.fmax_mode = 0;
+    }
+    t.G = 1; t.len = (int)count; t.chunk0 = 0;
+    t.sum_out = buf; t.out = nullptr;
+    fill_exchange(c, t, true);
+    pass_tail_kernel<<<(int)((count + 31) / 32), dim3(32, REDUCE_SLICES), 0, c->stream>>>(t);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+// ---------------------------------------------------------------------------
 template <int CPT, int MODE, int LOSS>
 static int launch_one(ciao_ctx *c, const PassArgs &a, int grid, int T, size_t smem) {
     auto kern = row_pass_kernel<CPT, MODE, LOSS>;
@@ -251,7 +415,8 @@ int ciao_comm_allreduce(ciao_ctx *c, double *buf, int64_t count, int op_max);  /
 int ciao_comm_allgather_inplace(ciao_ctx *c, double *buf, int64_t count_per_rank);
 
 // Runs one streaming pass.  Result: c->partial[0..d_pad) = Σ (unscaled, all ranks), c->partial[d_pad] = Σ f_i (or max).
-int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = false) {
+// With `fin` the closing update out = base + scale·(Σ/den) rides in the same tail kernel.
+int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = false, const FinishSpec *fin = nullptr) {
     if (c->loss_kind != CIAO_LOSS_LS && c->loss_kind != CIAO_LOSS_LOGISTIC)
         CIAO_FAIL(CIAO_ERR_STATE, "row pass: no row problem set (ciao_set_rows / ciao_gen_synthetic first)");
     const int64_t d_pad = c->d_pad;
@@ -295,10 +460,11 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     a.ss_out = nullptr;
     // the per-row step scalars for the inner kernels: all rows in one process, or — replicated rows, uniformly windowed
     // passes — each rank its window, all-gathered after the kernel
-    const bool gather_win = cache_cz && mode == PASS_GRAD && windowed && c->world > 1 && c->win_uniform;
+    const bool can_gather = c->world > 1 && c->nccl_comm != nullptr;   // the all-gather of the step scalars is NCCL's
+    const bool gather_win = cache_cz && mode == PASS_GRAD && windowed && can_gather && c->win_uniform;
     // … or row-sharded data with the peers' shards attached (ciao_attach_peer_rows): every rank knows all shard bounds, so
     // all ranks take the same decision; the array is indexed by the global row
-    bool gather_shard = cache_cz && mode == PASS_GRAD && !windowed && c->world > 1 && c->peers.n == c->world &&
+    bool gather_shard = cache_cz && mode == PASS_GRAD && !windowed && can_gather && c->peers.n == c->world &&
                         c->N_total % c->world == 0 && c->n_rows == c->N_total / c->world;
     for (int sidx = 0; gather_shard && sidx < c->peers.n; ++sidx)
         gather_shard = c->peers.start[sidx] == (int64_t)sidx * c->n_rows;
@@ -333,19 +499,35 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     }
     CIAO_TRY(rc);
     CUDA_TRY(cudaEventRecord(c->ev_pb, c->stream));
-    launch_reduce_ws(c, a.ws, a.fws, grid, c->partial, c->partial + d_pad, mode == PASS_NORMS, mode != PASS_NORMS);
+    // tail: CTA partials → (peer exchange) → closing update, one kernel; with NCCL only (no peer arenas attached) the exchange
+    // and the closing update are separate launches
+    const bool p2p = c->world > 1 && c->p2p_ready;
+    const bool nccl_route = c->world > 1 && !p2p;
+    TailArgs t;
+    memset(&t, 0, sizeof(t));
+    t.ws = a.ws; t.fws = a.fws; t.G = grid; t.d_pad = d_pad; t.len = (int)d_pad + 1;
+    t.fmax_mode = mode == PASS_NORMS; t.with_vec = mode != PASS_NORMS;
+    t.chunk0 = mode == PASS_NORMS ? (int)(d_pad / 32) : 0;
+    t.sum_out = c->partial;
+    if (fin && !nccl_route) {
+        t.base = fin->base; t.scale = fin->scale; t.den = fin->den; t.out = fin->out;
+    }
+    fill_exchange(c, t, p2p);
+    const int tail_grid = mode == PASS_NORMS ? 1 : (int)((d_pad + 1 + 31) / 32);
+    pass_tail_kernel<<<tail_grid, dim3(32, REDUCE_SLICES), 0, c->stream>>>(t);
     CUDA_TRY(cudaGetLastError());
     c->timing.launches += 2;
     c->pass_timed = true;
     c->timing.last_pass_bytes = (int64_t)wn * c->ld * 8 +
                                 ((mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT) ? (int64_t)c->n_rows * d_pad * 8 : 0);
-    if (c->world > 1) {
+    if (nccl_route) {
         if (mode == PASS_NORMS) {
             CIAO_TRY(ciao_comm_allreduce(c, c->partial + d_pad, 1, 1));
         } else {
             CIAO_TRY(ciao_comm_allreduce(c, c->partial, d_pad + 1, 0));
         }
-        if (gather_ss) CIAO_TRY(ciao_comm_allgather_inplace(c, c->ss, 4 * wn));
+        if (fin) CIAO_TRY(run_finish(c, fin->base, fin->scale, fin->den, fin->out));
     }
+    if (gather_ss) CIAO_TRY(ciao_comm_allgather_inplace(c, c->ss, 4 * wn));
     return CIAO_OK;
 }

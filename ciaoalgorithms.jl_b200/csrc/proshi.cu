@@ -26,6 +26,7 @@ struct ProshiArgs {
     double *v_z, *v_av;
     double box_lo, box_hi, eta, Nd, hat_gamma;
     RegParams reg;
+    const int *err;         // context error flag (out-of-range index seen by prep_indices_kernel): no block step runs
 };
 
 __device__ __forceinline__ double proshi_grad(double q, double c, double s, double lo, double hi, double eta) {
@@ -47,7 +48,7 @@ __device__ __forceinline__ double proshi_grad(double q, double c, double s, doub
 // cp.async groups at 0.30 µs/block (≈ 190 instructions per step on the one warp that also walks the chain); with the staging
 // moved to producer lanes the compute warp issues ≈ 70.
 constexpr int PROSHI_D = 16;  // ring depth; a staged table slice is stale if the block recurs within D + 1 steps → HAZARD flag
-static_assert((PROSHI_D & (PROSHI_D - 1)) == 0 && PROSHI_D + 1 <= CIAO_HAZARD_WINDOW - 1,
+static_assert((PROSHI_D & (PROSHI_D - 1)) == 0 && PROSHI_D + 2 <= CIAO_HAZARD_WINDOW,
               "prep_indices_kernel must flag repeats within the prefetch window");
 
 #ifndef PROSHI_NP
@@ -57,6 +58,7 @@ constexpr int PROSHI_PRODUCERS = PROSHI_NP;  // producer lanes (one warp each), 
 
 template <int CPT, int REG>
 __global__ void __launch_bounds__(32 * (1 + PROSHI_PRODUCERS)) proshi_steps_kernel(const ProshiArgs p) {
+    if (*reinterpret_cast<const volatile int *>(p.err) != 0) return;   // ProShI_basic.jl:113 would throw BoundsError first
     constexpr int D = PROSHI_D;
     constexpr int COLS = 32 * CPT;                 // columns per CTA
     constexpr int SLOT = 3 * COLS + 4;             // doubles: q | c | s | γ, γ/N | index word | pad
@@ -170,6 +172,10 @@ __global__ void __launch_bounds__(32 * (1 + PROSHI_PRODUCERS)) proshi_steps_kern
             if (CPT == 2) __stcg(reinterpret_cast<double2 *>(srow), make_double2(t[0], t[CPT - 1]));
             else __stcg(srow, t[0]);
         }
+        // generic-proxy table write → visible to the producers' later TMA reads: this fence, then the warp barrier + release
+        // arrive on empty_bar in take() below, then the producer's acquire wait on that barrier before it refills the slot —
+        // every repeat at distance ≥ PROSHI_D + 1 is ordered that way, closer ones carry the HAZARD flag (window 19)
+        fence_proxy_async();
         if (ik & CIAO_FLAG_PROX) {  // :121-123
 #pragma unroll
             for (int e = 0; e < CPT; ++e)
@@ -205,6 +211,7 @@ constexpr int PROSHI_BATCH_MIN = 64;
 template <int PROSHI_BT, int PROSHI_BU>
 __global__ void __launch_bounds__(PROSHI_BT) proshi_batch_kernel(const ProshiArgs p, const int64_t *ptr, int64_t n_batches) {
     __shared__ double red[2][PROSHI_BT / 32][4][2];
+    if (*reinterpret_cast<const volatile int *>(p.err) != 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h = tid & 3, rs = tid >> 2;            // piece of the 64-byte chunk, block slot
     const int64_t col = 8 * (int64_t)blockIdx.x + 2 * h;
@@ -319,18 +326,39 @@ __global__ void __launch_bounds__(256) table_colsum_kernel(const double *table, 
     ws[(size_t)blockIdx.x * n_pad + col + 1] = a1;
 }
 
+// s_i += γ_i z for every block, in place (ProShI_basic.jl:127-132): a pure streaming read-modify-write of the table.  Four rows
+// per thread are in flight (independent 128-bit loads issued before the first use; round 1's one-load-at-a-time loop ran at
+// 2.9 TB/s of 16·N·n bytes), streaming cache hints on both sides.
 __global__ void __launch_bounds__(256) proshi_solution_kernel(double *table, const double *gam, const double *z, int64_t N,
                                                               int64_t n_pad) {
+    constexpr int U = 4;
     const int64_t col = 2 * (blockIdx.y * (int64_t)blockDim.x + threadIdx.x);
     if (col >= n_pad) return;
     const double z0 = z[col], z1 = z[col + 1];
-    for (int64_t i = blockIdx.x; i < N; i += gridDim.x) {
+    const int64_t stride = gridDim.x;
+    int64_t i = blockIdx.x;
+    for (; i + (U - 1) * stride < N; i += U * stride) {
+        double2 s[U];
+        double gi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            s[u] = __ldcs(reinterpret_cast<const double2 *>(table + (i + u * stride) * n_pad + col));
+            gi[u] = __ldg(gam + i + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            s[u].x = __dadd_rn(s[u].x, __dmul_rn(gi[u], z0));
+            s[u].y = __dadd_rn(s[u].y, __dmul_rn(gi[u], z1));
+            __stcs(reinterpret_cast<double2 *>(table + (i + u * stride) * n_pad + col), s[u]);
+        }
+    }
+    for (; i < N; i += stride) {
         double2 *sp = reinterpret_cast<double2 *>(table + i * n_pad + col);
-        double2 s = *sp;
+        double2 s = __ldcs(sp);
         const double gi = __ldg(gam + i);
         s.x = __dadd_rn(s.x, __dmul_rn(gi, z0));
         s.y = __dadd_rn(s.y, __dmul_rn(gi, z1));
-        *sp = s;
+        __stcs(sp, s);
     }
 }
 
@@ -403,6 +431,7 @@ int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, const 
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_av = ctx_vec(c, CIAO_VEC_AV);
     a.box_lo = c->box_lo; a.box_hi = c->box_hi; a.eta = c->eta; a.Nd = (double)c->N_total; a.hat_gamma = c->hat_gamma;
     a.reg = c->reg;
+    a.err = c->err_dev;
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
     if (n_batches > 0 && K / n_batches >= PROSHI_BATCH_MIN) {
         // minibatches: blocks of a batch in parallel, one CTA per 8 columns

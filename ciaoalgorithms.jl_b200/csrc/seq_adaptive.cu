@@ -36,7 +36,8 @@ struct AdArgs {
 constexpr int AD_D = 8;       // ring depth
 constexpr int AD_HIST = 32;   // steps of per-component scalar history (≥ CIAO_HAZARD_WINDOW)
 constexpr int AD_EXTRA = 12;  // scalar area of a slot: record tail [0,6) | {γ_i, f_i, c_i, 0} [6,10) | index word [10] | pad
-static_assert(AD_D + 1 <= CIAO_HAZARD_WINDOW - 1 && CIAO_HAZARD_WINDOW <= AD_HIST, "hazard window vs ring depth / history");
+static_assert((AD_D & (AD_D - 1)) == 0 && AD_D + 2 <= CIAO_HAZARD_WINDOW - 1 && CIAO_HAZARD_WINDOW <= AD_HIST,
+              "hazard window vs ring depth / history");
 
 template <int CPT, int LOSS, int REG>
 __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
         // pulls the staged data of `step` into registers and hands the slot back to the producer
         auto load = [&](int64_t step, Row &r) {
             const int slot = (int)(step & (D - 1));
-            mbar_wait(&row_bar[slot], (uint32_t)((step >> 3) & 1));
+            mbar_wait(&row_bar[slot], (uint32_t)((step / D) & 1));
             const double *rp = ring + slot * slot_doubles;
 #pragma unroll
             for (int h = 0; h < H; ++h) {
@@ -318,11 +319,16 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                 hp[0] = gam; hp[1] = fi_z; hp[2] = cnew;
             }
             __syncwarp();
-            if (rank == 0 && tid == 0) {
-                double2 *o = reinterpret_cast<double2 *>(p.ad + 4 * (ik & CIAO_IDX_MASK));
-                __stcg(o, make_double2(gam, fi_z));
-                __stcg(o + 1, make_double2(cnew, 0.0));
+            // Every CTA stores the (bit-identical) scalars itself, so that each CTA's TMA reads of p.ad are ordered behind a
+            // write of its own: table row and scalars → fence.proxy.async → warp barrier + release arrive on empty_bar in the
+            // next load() → the producer's acquire wait before it refills that slot (distance ≥ AD_D + 2; closer repeats carry
+            // the HAZARD flag and use the history / re-read behind the own store).
+            if (tid == 0) {
+                double *o = p.ad + 4 * (ik & CIAO_IDX_MASK);
+                asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(o), "d"(gam), "d"(fi_z) : "memory");
+                asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(o + 2), "d"(cnew), "d"(0.0) : "memory");
             }
+            fence_proxy_async();
             ++done;
             PROF_T(t_f);
             PROF_ADD(5, t_e, t_f);  // main update, stores, history

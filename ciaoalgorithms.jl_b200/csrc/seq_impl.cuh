@@ -49,6 +49,8 @@ struct SeqArgs {
     int npart_pad;          // C·W rounded up to a multiple of 32
     int table_tma;          // table rows are staged in the ring by TMA (else: register prefetch with ld.global)
     int zero;               // always 0, opaque to the compiler (pins work in front of the exchange wait, see below)
+    int *smid_out;          // [C]: the SM each CTA of the cluster runs on (cross-SM DSMEM latency is a per-pair constant)
+    const int *err;         // error flag of the context: set by prep_indices_kernel when an index is out of range → no step runs
     RegParams reg;
 };
 
@@ -62,7 +64,19 @@ static __device__ long long g_seq_prof[16 * 8];  // [CTA rank][phase]: accumulat
 #endif
 
 constexpr int SEQ_D = 8;           // row ring depth (steps of prefetch), power of two
+static_assert((SEQ_D & (SEQ_D - 1)) == 0, "ring slots and mbarrier parities are derived from step & (D - 1), step / D");
 static_assert(SEQ_D + 1 <= CIAO_HAZARD_WINDOW - 1, "prep_indices_kernel must flag repeats within the prefetch window");
+// Table rows (SAGA/Finito) are written by the compute threads through the generic proxy (st.global.cg) and re-read, D steps
+// ahead of their use, by the producer lane's TMA copies through the async proxy.  A repeat at distance < CIAO_HAZARD_WINDOW is
+// flagged and re-read by the writing thread itself; for the others the write is ordered before the copy by a chain the PTX
+// memory model recognises: st.global → fence.proxy.async → warp barrier → mbarrier.arrive (release) on a "written" barrier
+// of step k → the producer's try_wait (acquire) on that barrier before it issues the copies for step k + 1 + D.  Repeats at
+// distance ≥ D + 1 are therefore ordered, repeats at distance ≤ CIAO_HAZARD_WINDOW − 1 are flagged: no gap, no timing assumption.
+//   CIAO_TABLE_FENCE = 0: round-1 behaviour (no fence; measurement only), 1: proxy fence only, 2 (default): fence + barrier.
+#ifndef CIAO_TABLE_FENCE
+#define CIAO_TABLE_FENCE 2
+#endif
+static_assert(SEQ_D + 1 <= CIAO_HAZARD_WINDOW - 1, "every repeat closer than the ordered distance D + 1 must carry the HAZARD flag");
 constexpr int SEQ_MAX_PART = 128;  // C·W ≤ 128
 constexpr int SEQ_SLOT_EXTRA = 12;  // staged scalars [0,10) + index word [10] + pad (slots stay 16-byte aligned)
 constexpr int SEQ_IDX_POS = 10;
@@ -84,6 +98,9 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
     constexpr int D = SEQ_D;
     constexpr int H = CPT / 2;
 
+    // an out-of-range index (flagged by prep_indices_kernel, same stream) must not touch z, av or the table: the reference throws
+    // BoundsError before any state changes (SAGA_basic.jl:56).  Uniform over the cluster, so nobody is left at a barrier.
+    if (*reinterpret_cast<const volatile int *>(p.err) != 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int Tc = blockDim.x - 32;  // compute threads; the last warp is the producer
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = Tc >> 5;
@@ -96,6 +113,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
     double *part = ring + D * slot_doubles;           // [2][npart_pad][2]
     uint64_t *row_bar = reinterpret_cast<uint64_t *>(part + 2 * (size_t)p.npart_pad * 2);
     uint64_t *part_bar = row_bar + D;
+    uint64_t *wr_bar = part_bar + 2;                  // [D]: "table row of step k written" (W arrivals, TABLE kernels)
     const int64_t K = p.K;
     const int64_t cbase = (int64_t)rank * dc;
     const uint32_t part_bytes = C * W * 16;
@@ -103,9 +121,14 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
     // zero the ring padding and the unused partial slots once
     for (size_t i = tid; i < D * slot_doubles + 2 * (size_t)p.npart_pad * 2; i += blockDim.x) ring[i] = 0.0;
     if (tid == 0) {
+        uint32_t sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        p.smid_out[rank] = (int)sm;
         for (int s = 0; s < D; ++s) mbar_init(&row_bar[s], 1);
         mbar_init(&part_bar[0], 1);  // one local arrive (expect_tx) per phase; the data arrives as tx bytes
         mbar_init(&part_bar[1], 1);
+        if (TABLE)
+            for (int s = 0; s < D; ++s) mbar_init(&wr_bar[s], W);
         fence_mbar_init();
     }
     fence_proxy_async();  // the zero fill (generic proxy) is ordered before the TMA writes into the ring
@@ -159,8 +182,16 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             if (Ki > 0) mbar_arrive_expect_tx_s(part_bar_s, part_bytes);
             if (Ki > 1) mbar_arrive_expect_tx_s(part_bar_s + 8, part_bytes);
             for (int st = 0; st < D && st < Ki; ++st) issue_row(st, __ldg(p.idx + st));
+#ifdef CIAO_SEQ_PROD4
+            // experiment: the index words four iterations ahead (an L2 miss of the 8-byte load is longer than a step)
+            int64_t nq[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nq[q] = (D + q < Ki) ? __ldg(p.idx + D + q) : 0;
+            const int64_t *idx_ahead = p.idx + D + 4;
+#else
             int64_t n1 = (D < Ki) ? __ldg(p.idx + D) : 0, n2 = (D + 1 < Ki) ? __ldg(p.idx + D + 1) : 0;
             const int64_t *idx_ahead = p.idx + D + 2;
+#endif
 #ifdef CIAO_SEQ_PROFILE
             long long prod_busy = 0;
 #endif
@@ -172,9 +203,19 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const long long pw = clock64();
 #endif
                 if (k + 2 < Ki) mbar_arrive_expect_tx_s(pb, part_bytes);  // arm the exchange of step k+2
+                // the table writes of steps ≤ k − 1 (all warps have sent partial k, hence finished step k − 1: this wait never
+                // spins) are acquired before the copies of step k + D read the table
+                if (TT && CIAO_TABLE_FENCE >= 2 && k >= 1)
+                    mbar_wait_s(smem_u32(wr_bar) + (((uint32_t)k - 1u) & (D - 1)) * 8, (((uint32_t)k - 1u) / D) & 1u);
+#ifdef CIAO_SEQ_PROD4
+                if (k + D < Ki) issue_row(k + D, nq[0]);
+                nq[0] = nq[1]; nq[1] = nq[2]; nq[2] = nq[3];
+                nq[3] = (k + D + 4 < Ki) ? __ldg(idx_ahead + k) : 0;
+#else
                 if (k + D < Ki) issue_row(k + D, n1);
                 n1 = n2;
                 n2 = (k + D + 2 < Ki) ? __ldg(idx_ahead + k) : 0;
+#endif
 #ifdef CIAO_SEQ_PROFILE
                 prod_busy += clock64() - pw;
 #endif
@@ -222,7 +263,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
         // waits for the staged row of `step` and pulls this thread's slice + the scalars into registers
         auto load_row = [&](int64_t step, RowRegs &r) {
             const int slot = (int)(step & (D - 1));
-            mbar_wait(&row_bar[slot], (uint32_t)((step >> 3) & 1));
+            mbar_wait(&row_bar[slot], (uint32_t)((step / D) & 1));
             const double *rp = ring + slot * slot_doubles;
 #pragma unroll
             for (int h = 0; h < H; ++h) {
@@ -306,7 +347,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
 #ifdef CIAO_SEQ_PROFILE
                 {
                     const long long w0 = clock64();
-                    mbar_wait(&row_bar[(k + 1) & (D - 1)], (uint32_t)(((k + 1) >> 3) & 1));
+                    mbar_wait(&row_bar[(k + 1) & (D - 1)], (uint32_t)(((k + 1) / D) & 1));
                     prof_acc[4] += clock64() - w0;  // wait for the staged row of the next step (included in phase 1)
                 }
 #endif
@@ -314,7 +355,14 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 if (TABLE && !TT) load_table(nxt);
             }
             PROF_T(t_c);
+#ifdef CIAO_SEQ_SPIN
+            {   // experiment: poll the phase with the non-blocking test instead of the suspending try_wait
+                const uint32_t ph = (uint32_t)((k >> 1) & 1) ^ (uint32_t)(pin & p.zero);
+                while (!mbar_test(&part_bar[par], ph)) {}
+            }
+#else
             mbar_wait(&part_bar[par], (uint32_t)((k >> 1) & 1) ^ (uint32_t)(pin & p.zero));
+#endif
             PROF_T(t_d);
             // every warp reduces the same C·W partials with the same tensor-core sum → identical bits everywhere
             double u0 = 0.0, u1 = 0.0;
@@ -323,11 +371,13 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const double2 v = pp[0];  // E == 1 (C·W ≤ 32) is the common shape: no loop, no branches
                 u0 = v.x;
                 if (TWO_DOTS) u1 = v.y;
+#ifndef CIAO_SEQ_E1   // experiment CIAO_SEQ_E1: C·W ≤ 32 assumed at compile time
                 for (int e = 1; e < E; ++e) {
                     const double2 w = pp[e * 32];
                     u0 += w.x;
                     if (TWO_DOTS) u1 += w.y;
                 }
+#endif
                 u0 = warp_sum_mma(u0, lane);
                 if (TWO_DOTS) u1 = warp_sum_mma(u1, lane);
             }
@@ -410,6 +460,13 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 for (int h = 0; h < H; ++h)
                     if (valid[h])
                         __stcg(reinterpret_cast<double2 *>(trow + gcol[h]), make_double2(snew[2 * h], snew[2 * h + 1]));
+                if (TT && CIAO_TABLE_FENCE >= 1) {
+                    fence_proxy_async();   // generic-proxy table writes → visible to later async-proxy (TMA) reads
+                    if (CIAO_TABLE_FENCE >= 2) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&wr_bar[k & (D - 1)]);
+                    }
+                }
             }
             PROF_T(t_e);
             PROF_ADD(0, t_a, t_b);  // dots + warp shuffles
@@ -459,7 +516,7 @@ struct SeqShape {
 
 static size_t seq_smem_bytes(const SeqShape &sh, bool table_in_ring) {
     const size_t cover = (size_t)sh.Tc * sh.cpt;
-    return (size_t)SEQ_D * (cover + SEQ_SLOT_EXTRA + (table_in_ring ? cover : 0)) * 8 + 2 * (size_t)sh.npart_pad * 2 * 8 + (SEQ_D + 2) * 8 + 128;
+    return (size_t)SEQ_D * (cover + SEQ_SLOT_EXTRA + (table_in_ring ? cover : 0)) * 8 + 2 * (size_t)sh.npart_pad * 2 * 8 + (2 * SEQ_D + 2) * 8 + 128;
 }
 
 template <int CPT, int ALG, int LOSS, int REG, bool CZ>
@@ -553,7 +610,8 @@ static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, doub
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_zfull = ctx_vec(c, CIAO_VEC_Z_FULL); a.v_w = ctx_vec(c, CIAO_VEC_W);
     a.v_av = ctx_vec(c, CIAO_VEC_AV); a.v_zsum = ctx_vec(c, CIAO_VEC_Z);  // SVRG: state.z is the running sum of inner iterates
     a.gamma = c->gamma; a.hat_gamma = c->hat_gamma; a.Nd = (double)c->N_total; a.m_d = m_d;
-    a.plus = c->plus; a.sag = c->sag; a.reg = c->reg; a.npart_pad = sh.npart_pad; a.zero = 0;
+    a.plus = c->plus; a.sag = c->sag; a.reg = c->reg; a.npart_pad = sh.npart_pad; a.zero = 0; a.err = c->err_dev;
+    a.smid_out = c->seq_smid; c->seq_smid_n = sh.C;
     a.table_tma = (ALG == ALG_SAGA || ALG == ALG_FINITO) && seq_smem_bytes(sh, true) <= 200 * 1024 && !c->seq_table_ldg;
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
     int rc;

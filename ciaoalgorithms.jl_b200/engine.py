@@ -89,6 +89,16 @@ class Engine:
         buf = C.create_string_buffer(uid, 128)
         check(self.lib.ciao_comm_init(self.h, buf, rank, world))
 
+    def comm_p2p_handle(self) -> bytes:
+        """128-byte blob of this context's exchange arena; all-gather the blobs in rank order, then comm_p2p_attach."""
+        buf = C.create_string_buffer(128)
+        check(self.lib.ciao_comm_p2p_handle(self.h, buf))
+        return buf.raw
+
+    def comm_p2p_attach(self, rank: int, world: int, handles):
+        blob = C.create_string_buffer(b"".join(handles), 128 * len(handles))
+        check(self.lib.ciao_comm_p2p_attach(self.h, int(rank), int(world), blob))
+
     def rows_ipc_handle(self) -> bytes:
         buf = C.create_string_buffer(64)
         check(self.lib.ciao_rows_ipc_handle(self.h, buf))
@@ -222,6 +232,19 @@ class Engine:
         t = L.Timing()
         check(self.lib.ciao_last_timing(self.h, C.byref(t)))
         return t
+
+    def last_seq_placement(self):
+        """SM ids of the CTAs of the last sequential cluster kernel."""
+        sm, n = (C.c_int * 16)(), C.c_int()
+        check(self.lib.ciao_last_seq_placement(self.h, sm, C.byref(n)))
+        return list(sm[: n.value])
+
+    def measure_exchange(self, cluster=8, warps=4, iters=100000, mode=1, max_clusters=74):
+        """Per-cluster (ns per round, SM cycles per round, SM ids) of the cluster-exchange floor (seq_floor.cu)."""
+        ns, cyc = (C.c_float * max_clusters)(), (C.c_float * max_clusters)()
+        sm, n = (C.c_int * (max_clusters * cluster))(), C.c_int()
+        check(self.lib.ciao_measure_exchange(self.h, cluster, warps, iters, mode, max_clusters, C.byref(n), ns, cyc, sm))
+        return [(ns[k], cyc[k], list(sm[k * cluster:(k + 1) * cluster])) for k in range(n.value)]
 
     def set_tuning(self, pass_threads=0, pass_stages=0, pass_ctas_per_sm=0, seq_cluster=0, seq_threads=0):
         check(self.lib.ciao_set_tuning(self.h, pass_threads, pass_stages, pass_ctas_per_sm, seq_cluster, seq_threads))

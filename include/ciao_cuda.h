@@ -104,6 +104,17 @@ int ciao_gen_host(int synth_kind, int64_t d, uint64_t seed, int64_t row0, int64_
 /* out must hold 128 bytes (ncclUniqueId); rank 0 creates it, the host broadcasts it */
 int ciao_comm_unique_id(void *out128);
 int ciao_comm_init(ciao_ctx *ctx, const void *id128, int rank, int world);
+/* One-shot exchange over peer memory — the deterministic all-reduce of the row-sharded passes (SVRG_basic.jl:58-63 over a
+ * sharded F).  Every rank exports an arena (ciao_comm_p2p_handle: 128 opaque bytes), the host all-gathers
+ * the blobs in rank order and every rank attaches them (CUDA IPC between processes — also between processes sharing one GPU —
+ * or plain peer access inside one process).  From then on the tail kernel of a pass stores its partial d-vector into every
+ * peer's arena, raises a flag, waits for the peers' flags (bounded: a missing peer gives CIAO_ERR_COMM at the next synchronising
+ * call) and sums the slots in rank order: bit-identical results on every rank and run to run, one kernel launch after the pass.
+ * Without attached arenas the passes fall back to ncclAllReduce (ciao_comm_init).  Collective calls must be made by all
+ * ranks in the same order. */
+int ciao_comm_p2p_handle(ciao_ctx *ctx, void *out128);
+int ciao_comm_p2p_attach(ciao_ctx *ctx, int rank, int world, const void *handles128);
+
 /* Replicated data, sharded pass: restrict the full-gradient / objective passes of this context to
  * the local rows [row_lo, row_lo + n) (0-based); with a communicator the partial d-vectors are
  * all-reduced, so G ranks holding the same rows each stream 1/G of them.  n = 0 resets.  With a communicator the call is
@@ -173,6 +184,14 @@ int ciao_stage_indices(ciao_ctx *ctx, const int64_t *idx_host, int64_t n);    /*
 int ciao_timer_begin(ciao_ctx *ctx);                                          /* CUDA event on the ctx stream */
 int ciao_timer_end(ciao_ctx *ctx, float *ms);                                 /* records, synchronises, returns elapsed */
 int ciao_last_timing(ciao_ctx *ctx, ciao_timing *out);
+/* SM ids of the CTAs of the last sequential cluster kernel (n_ctas ≤ 16 entries of smid16 are valid) */
+int ciao_last_seq_placement(ciao_ctx *ctx, int *smid16, int *n_ctas);
+/* Latency floor of the sequential kernels' cluster exchange on this device (seq_floor.cu): every cluster of `cluster` CTAs ×
+ * `warps` warps that fits on the GPU runs `iters` rounds of the st.async → mbarrier exchange (mode 0) or of exchange + partial
+ * sum + dependent next message (mode 1) and reports its own ns and SM cycles per round and the SMs it sits on
+ * (smid[k·cluster + r]).  Arrays hold max_clusters (·cluster) entries; *n_clusters of them are written. */
+int ciao_measure_exchange(ciao_ctx *ctx, int cluster, int warps, int iters, int mode, int max_clusters, int *n_clusters,
+                          float *ns_per_round, float *cyc_per_round, int *smid);
 /* tuning knobs (0 = default): threads per CTA and ring stages of the streaming pass, cluster size of the sequential kernels */
 int ciao_set_tuning(ciao_ctx *ctx, int pass_threads, int pass_stages, int pass_ctas_per_sm, int seq_cluster, int seq_threads);
 

@@ -171,6 +171,136 @@ void orc_full_gradient(const orc_problem *p, const double *x, double scale, doub
     free(g);
 }
 
+/* ------------------------------------------------------------------------ */
+/* Multi-threaded full-gradient passes.  NOT a restatement of the reference  */
+/* (which is single-threaded, SVRG_basic.jl:58-63): (a) the generous,        */
+/* separately labelled all-cores CPU baseline SURVEY.md §8d allows, and (b)  */
+/* the full-scale parity check of the CUDA pass (N = 2^22 × 4096 does not    */
+/* fit host memory: rows are regenerated on the fly from the generator).     */
+/* Plain pthreads (the image's default CC has no libgomp spec).              */
+/* Rows are split into nthreads contiguous chunks; every thread runs the     */
+/* reference's per-row operation sequence into its own accumulator; the      */
+/* accumulators are added in thread order (deterministic for a given count). */
+/* ------------------------------------------------------------------------ */
+#include <pthread.h>
+#include <unistd.h>
+
+int orc_num_threads(void) {
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    return n < 1 ? 1 : (n > 256 ? 256 : (int)n);
+}
+
+typedef struct {
+    void (*fn)(int t, int T, void *ctx);
+    int t, T;
+    void *ctx;
+} orc_task;
+static void *orc_task_main(void *arg) {
+    orc_task *k = (orc_task *)arg;
+    k->fn(k->t, k->T, k->ctx);
+    return NULL;
+}
+/* runs fn(t, T, ctx) for t = 0 … T−1 on T threads (plain pthreads: the image's default compiler has no libgomp spec) */
+static void orc_parallel(int T, void (*fn)(int, int, void *), void *ctx) {
+    if (T < 1) T = 1;
+    pthread_t *th = (pthread_t *)malloc((size_t)T * sizeof(pthread_t));
+    orc_task *tk = (orc_task *)malloc((size_t)T * sizeof(orc_task));
+    for (int t = 0; t < T; ++t) {
+        tk[t].fn = fn; tk[t].t = t; tk[t].T = T; tk[t].ctx = ctx;
+        if (t > 0 && pthread_create(&th[t], NULL, orc_task_main, &tk[t]) != 0) th[t] = 0, fn(t, T, ctx);
+    }
+    fn(0, T, ctx);
+    for (int t = 1; t < T; ++t)
+        if (th[t]) pthread_join(th[t], NULL);
+    free(th);
+    free(tk);
+}
+
+typedef struct {
+    const orc_problem *p;
+    const double *x;
+    double scale;
+    double *acc;
+} orc_fg_ctx;
+static void orc_fg_chunk(int t, int T, void *vc) {
+    orc_fg_ctx *c = (orc_fg_ctx *)vc;
+    const int64_t d = c->p->d, N = c->p->N;
+    double *g = (double *)malloc((size_t)d * sizeof(double));
+    double *a = c->acc + (size_t)t * d;
+    const int64_t lo = N * t / T, hi = N * (t + 1) / T;
+    for (int64_t i = lo; i < hi; ++i) {
+        orc_gradient(c->p, i, c->x, g);
+        for (int64_t k = 0; k < d; ++k) g[k] *= c->scale;
+        for (int64_t k = 0; k < d; ++k) a[k] += g[k];
+    }
+    free(g);
+}
+void orc_full_gradient_omp(const orc_problem *p, const double *x, double scale, double *out, int nthreads) {
+    const int64_t d = p->d;
+    if (nthreads < 1) nthreads = 1;
+    double *acc = (double *)calloc((size_t)nthreads * (size_t)d, sizeof(double));
+    orc_fg_ctx c = {p, x, scale, acc};
+    orc_parallel(nthreads, orc_fg_chunk, &c);
+    memset(out, 0, (size_t)d * sizeof(double));
+    for (int t = 0; t < nthreads; ++t)
+        for (int64_t k = 0; k < d; ++k) out[k] += acc[(size_t)t * d + k];
+    free(acc);
+}
+
+/* out = scale · Σ_{i in [i0, i0+n)} ∇f_i(x) and *f_sum = Σ f_i(x) for the synthetic row problem (kind, d, seed) with
+ * λ_i = μ_i = lam for all i, rows regenerated on the fly (never stored).  Long-double accumulation of the row dot and
+ * of the per-thread sums, so that the result is a reference for the GPU pass rather than a peer. */
+typedef struct {
+    int kind;
+    int64_t d, i0, n;
+    uint64_t seed;
+    double lam;
+    const double *x;
+    long double *acc;
+} orc_syn_ctx;
+static void orc_syn_chunk(int t, int T, void *vc) {
+    orc_syn_ctx *c = (orc_syn_ctx *)vc;
+    const int64_t d = c->d;
+    const int kind = c->kind;
+    double *row = (double *)malloc((size_t)d * sizeof(double));
+    long double *a = c->acc + (size_t)t * (d + 1);
+    const int64_t lo = c->i0 + c->n * t / T, hi = c->i0 + c->n * (t + 1) / T;
+    for (int64_t i = lo; i < hi; ++i) {
+        long double u = 0.0L;
+        for (int64_t j = 0; j < d; ++j) {
+            row[j] = ciao_syn_entry(kind, d, c->seed, i, j);
+            u += (long double)row[j] * (long double)c->x[j];
+        }
+        const double rhs = ciao_syn_rhs(kind, d, c->seed, i);
+        double cf;
+        if (kind == CIAO_SYN_LASSO) {
+            const double res = (double)u - rhs;
+            cf = res * c->lam;
+            a[d] += (long double)(c->lam / 2) * ((long double)res * res);
+        } else {
+            const double e = exp(rhs * (double)u);
+            cf = -c->lam * rhs / (1 + e);
+            a[d] += (long double)c->lam * logl(1 + 1 / (long double)e);
+        }
+        for (int64_t j = 0; j < d; ++j) a[j] += (long double)row[j] * cf;
+    }
+    free(row);
+}
+void orc_full_gradient_synth_omp(int kind, int64_t d, uint64_t seed, double lam, int64_t i0, int64_t n, const double *x,
+                                 double scale, double *out, double *f_sum, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    long double *acc = (long double *)calloc((size_t)nthreads * (size_t)(d + 1), sizeof(long double));
+    orc_syn_ctx c = {kind, d, i0, n, seed, lam, x, acc};
+    orc_parallel(nthreads, orc_syn_chunk, &c);
+    for (int64_t k = 0; k <= d; ++k) {
+        long double s = 0.0L;
+        for (int t = 0; t < nthreads; ++t) s += acc[(size_t)t * (d + 1) + k];
+        if (k < d) out[k] = (double)(s * scale);
+        else if (f_sum) *f_sum = (double)s;
+    }
+    free(acc);
+}
+
 /* Julia's sum over a Vector of d-vectors with stride ld (Base.mapreduce_impl:
  * pairwise, sequential below 1024 terms).  out = Σ_{i in [lo,hi)} v_i */
 static void orc_pairwise_sum(const double *v, int64_t ld, int64_t d, int64_t lo, int64_t hi,
@@ -566,12 +696,24 @@ void orc_proshi_solution(const orc_problem *p, const double *gamma, const double
 /* synthetic inputs (bit-identical to the device generator, include/ciao_gen.h) */
 /* ------------------------------------------------------------------------ */
 
-void orc_gen_rows(int kind, int64_t d, uint64_t seed, int64_t i0, int64_t n, double *A, double *rhs) {
-    for (int64_t r = 0; r < n; ++r) {
-        int64_t i = i0 + r;
-        for (int64_t j = 0; j < d; ++j) A[r * d + j] = ciao_syn_entry(kind, d, seed, i, j);
-        if (rhs && kind != CIAO_SYN_SHARING) rhs[r] = ciao_syn_rhs(kind, d, seed, i);
+typedef struct {
+    int kind;
+    int64_t d, i0, n;
+    uint64_t seed;
+    double *A, *rhs;
+} orc_gen_ctx;
+static void orc_gen_chunk(int t, int T, void *vc) {
+    orc_gen_ctx *c = (orc_gen_ctx *)vc;
+    for (int64_t r = c->n * t / T; r < c->n * (t + 1) / T; ++r) {
+        int64_t i = c->i0 + r;
+        for (int64_t j = 0; j < c->d; ++j) c->A[r * c->d + j] = ciao_syn_entry(c->kind, c->d, c->seed, i, j);
+        if (c->rhs && c->kind != CIAO_SYN_SHARING) c->rhs[r] = ciao_syn_rhs(c->kind, c->d, c->seed, i);
     }
+}
+/* every entry is a pure function of (seed, i, j): the same bits with any thread count */
+void orc_gen_rows(int kind, int64_t d, uint64_t seed, int64_t i0, int64_t n, double *A, double *rhs) {
+    orc_gen_ctx c = {kind, d, i0, n, seed, A, rhs};
+    orc_parallel(n * d >= (1 << 22) ? orc_num_threads() : 1, orc_gen_chunk, &c);
 }
 
 void orc_gen_xtrue(int kind, int64_t d, uint64_t seed, double *x) {

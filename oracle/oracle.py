@@ -137,6 +137,13 @@ class Problem:
         lib().orc_full_gradient(self.ref, _d(_f64(x)), C.c_double(scale), _d(out))
         return out
 
+    def full_gradient_omp(self, x, scale=1.0, nthreads=None):
+        """All-cores variant (NOT the reference's algorithm, which is single-threaded): the labelled generous CPU baseline."""
+        out = np.empty(self.d)
+        nt = num_threads() if nthreads is None else int(nthreads)
+        lib().orc_full_gradient_omp(self.ref, _d(_f64(x)), C.c_double(scale), _d(out), C.c_int(nt))
+        return out
+
     def max_row_sqnorm(self):
         return lib().orc_max_row_sqnorm(self.ref)
 
@@ -206,8 +213,10 @@ class FinitoState:
         lib().orc_finito_init(prob.ref, _d(_f64(x0)), _d(self.gamma), C.c_double(self.hat_gamma),
                               _d(self.s), _d(self.av), _d(self.z))
 
-    def steps(self, batches):
-        idx, ptr = _csr(batches)
+    def steps(self, batches, ptr=None):
+        """batches: list of 1-based index arrays, or (with ptr) an already flattened CSR pair."""
+        idx, ptr = _csr(batches) if ptr is None else (_i64(batches), _i64(ptr))
+        batches = range(len(ptr) - 1)
         lib().orc_finito_steps(self.prob.ref, _d(self.gamma), C.c_double(self.hat_gamma), _i(idx), _i(ptr),
                                C.c_int64(len(batches)), _d(self.s), _d(self.av), _d(self.z))
 
@@ -282,8 +291,10 @@ class ProshiState:
         lib().orc_proshi_init(prob.ref, _d(_f64(x0)), _d(self.gamma), C.c_double(self.hat_gamma),
                               _d(self.s), _d(self.av), _d(self.z))
 
-    def steps(self, batches):
-        idx, ptr = _csr(batches)
+    def steps(self, batches, ptr=None):
+        """batches: list of 1-based index arrays, or (with ptr) an already flattened CSR pair."""
+        idx, ptr = _csr(batches) if ptr is None else (_i64(batches), _i64(ptr))
+        batches = range(len(ptr) - 1)
         lib().orc_proshi_steps(self.prob.ref, _d(self.gamma), C.c_double(self.hat_gamma), _i(idx), _i(ptr),
                                C.c_int64(len(batches)), _d(self.s), _d(self.av), _d(self.z))
 
@@ -291,6 +302,22 @@ class ProshiState:
         """Mutates the table on every call, like ProShI_basic.jl:127-132."""
         lib().orc_proshi_solution(self.prob.ref, _d(self.gamma), _d(self.z), _d(self.s))
         return self.s
+
+
+def num_threads():
+    lib().orc_num_threads.restype = C.c_int
+    return int(lib().orc_num_threads())
+
+
+def full_gradient_synth(kind, N, d, seed, lam, x, scale=1.0, i0=0, n=None, nthreads=None):
+    """scale·Σ ∇f_i(x) and Σ f_i(x) over rows [i0, i0+n) of the synthetic problem, rows regenerated on the fly on all host
+    cores with long-double accumulation: the full-scale check of the CUDA pass (SURVEY.md §8d parity protocol)."""
+    n = N - i0 if n is None else n
+    out, fs = np.empty(d), C.c_double()
+    nt = num_threads() if nthreads is None else int(nthreads)
+    lib().orc_full_gradient_synth_omp(C.c_int(kind), C.c_int64(d), C.c_uint64(seed), C.c_double(lam), C.c_int64(i0), C.c_int64(n),
+                                      _d(_f64(x)), C.c_double(scale), _d(out), C.byref(fs), C.c_int(nt))
+    return out, fs.value
 
 
 # -- synthetic inputs (bit-identical to the device generator) -----------------

@@ -1,9 +1,16 @@
-"""Worker of tests/test_gpu_multi.py — launched with torch.distributed.run on G GPUs of one box.
+"""Worker of tests/test_gpu_multi.py — launched with torch.distributed.run, one process per rank.
 
-Row-sharded problem (each rank generates and holds only its shard), NCCL allreduce in the passes, peers' shards
-attached over CUDA IPC so that the replicated SVRG++ / LFinito inner loops TMA-prefetch remote rows over NVLink.
-Every rank checks its results against a single-context run of the whole problem on its own GPU (bitwise for the
-sequential kernels, ≤ 1e-13 for the all-reduced passes) and rank 0 prints MULTI_GPU_OK."""
+Row-sharded problem (each rank generates and holds only its shard); the passes exchange their partial d-vectors through the
+one-shot peer-memory exchange (ciao_comm_p2p_*: deterministic, rank-ordered) — or, with CIAO_TEST_EXCHANGE=nccl, through
+ncclAllReduce — and the peers' shards are attached over CUDA IPC so that the replicated SVRG++ / LFinito inner loops
+TMA-prefetch remote rows.  Every rank checks its results against a single-context run of the whole problem on its own
+GPU (bitwise across ranks, ≤ 1e-13 against the unsharded pass) and rank 0 prints MULTI_GPU_OK.
+
+Two layouts:
+  * one GPU per rank (gpurun --gpus 2 …): torch backend nccl; NCCL communicator + peer exchange; remote rows over NVLink;
+  * CIAO_TEST_SHARE_GPU=1: all ranks on cuda:0 (the driver's 1-GPU test box) — torch backend gloo for the host-side
+    handle exchange, no NCCL (it refuses two ranks on one device), the peer exchange and the row shards go through CUDA IPC
+    between processes on the same device; the GPU time-slices between the processes while one waits for the other's flag."""
 import os
 import sys
 
@@ -24,8 +31,33 @@ from ciaoalgorithms_jl_b200.sampling import HostRNG, LFinitoSweeper, shard_rows 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    share = os.environ.get("CIAO_TEST_SHARE_GPU") == "1"
+    use_nccl = not share
+    use_p2p = share or os.environ.get("CIAO_TEST_EXCHANGE", "p2p") == "p2p"
+    if share:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if share:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def comm_setup(eng):
+        """NCCL communicator (its all-gather serves the step scalars) and/or the peer exchange (the passes' all-reduce)."""
+        if use_nccl:
+            obj = [Engine.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(obj, 0)
+            eng.comm_init(obj[0], rank, world)
+        if use_p2p:
+            hs = [None] * world
+            dist.all_gather_object(hs, eng.comm_p2p_handle())
+            eng.comm_p2p_attach(rank, world, hs)
+
+    def same_on_all_ranks(a):
+        blobs = [None] * world
+        dist.all_gather_object(blobs, np.ascontiguousarray(a).tobytes())
+        return all(b == blobs[0] for b in blobs)
+
     N, d, seed = 6000 + 37, 1024, 0x5EED0003
     lo, hi = shard_rows(N, world, rank)
     lam = N / 100.0
@@ -33,11 +65,7 @@ def main():
     sh = Engine(local)                                  # my shard only
     sh.gen_synthetic(L.SYNTH_LASSO, N, d, seed, scale=float(N), row0=lo, n_rows=hi - lo)
     sh.set_reg(L.REG_NORML1, lam)
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid = torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8).cuda()
-    dist.broadcast(uid, 0)
-    sh.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    comm_setup(sh)
     handles = [None] * world
     dist.all_gather_object(handles, (sh.rows_ipc_handle(), lo, hi - lo))
     sh.attach_peer_rows([h[0] for h in handles], [h[1] for h in handles], [h[2] for h in handles], rank)
@@ -49,15 +77,11 @@ def main():
     def rel(a, b):
         return np.linalg.norm(a - b) / np.linalg.norm(b)
 
-    def uid2(r):                                        # a second communicator for the replicated-rows context
-        u = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if r == 0:
-            u = torch.frombuffer(bytearray(Engine.comm_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(u, 0)
-        return u.cpu().numpy().tobytes()
-
     x = np.random.default_rng(0).standard_normal(d) * 1e-3
-    assert rel(sh.full_gradient(x, 1.0 / N), full.full_gradient(x, 1.0 / N)) < 1e-13
+    g_sh = sh.full_gradient(x, 1.0 / N)
+    assert rel(g_sh, full.full_gradient(x, 1.0 / N)) < 1e-13
+    assert same_on_all_ranks(g_sh)                      # rank-ordered sum: the same bits everywhere
+    assert np.array_equal(g_sh, sh.full_gradient(x, 1.0 / N))   # and run to run
     assert abs(sh.objective(x)[0] - full.objective(x)[0]) < 1e-13 * full.objective(x)[0]
     assert abs(sh.max_row_sqnorm() - full.max_row_sqnorm()) == 0.0
     gamma = 1.0 / (7.0 * N * full.max_row_sqnorm())
@@ -74,10 +98,7 @@ def main():
     zs, zf = sh.get_vec(L.VEC_Z_FULL), full.get_vec(L.VEC_Z_FULL)
     assert rel(zs, zf) < 1e-11, rel(zs, zf)
     # all ranks hold the same iterate bit for bit (the inner epoch is replicated, the allreduce is identical everywhere)
-    t = torch.from_numpy(zs.copy()).cuda()
-    ref = t.clone()
-    dist.broadcast(ref, 0)
-    assert torch.equal(t, ref)
+    assert same_on_all_ranks(zs)
 
     # LFinito sweeps (sequential kernel with remote rows)
     Li = np.full(N, N * full.max_row_sqnorm())
@@ -102,7 +123,7 @@ def main():
     fullu.gen_synthetic(L.SYNTH_LASSO, Nu, d, seed + 2, scale=float(Nu))
     for eng in (shu, fullu):
         eng.set_reg(L.REG_NORML1, Nu / 100.0)
-    shu.comm_init(bytes(uid2(rank)), rank, world)
+    comm_setup(shu)
     hu = [None] * world
     dist.all_gather_object(hu, shu.rows_ipc_handle())
     shu.attach_peer_rows(hu, [r * 3072 for r in range(world)], [3072] * world, rank)
@@ -125,7 +146,7 @@ def main():
     for eng in (rep, one):
         eng.gen_synthetic(L.SYNTH_LASSO, Nw, d, seed + 1, scale=float(Nw))
         eng.set_reg(L.REG_NORML1, Nw / 100.0)
-    rep.comm_init(bytes(uid2(rank)), rank, world)
+    comm_setup(rep)
     rep.set_pass_window(rank * (Nw // world), Nw // world)        # collective
     g2 = 1.0 / (7.0 * Nw * one.max_row_sqnorm())
     ra, rb = HostRNG(9), HostRNG(9)
@@ -136,10 +157,8 @@ def main():
         one.svrg_epoch(rb.rand_vec(Nw, Nw // 4))
     assert rel(rep.get_vec(L.VEC_Z_FULL), one.get_vec(L.VEC_Z_FULL)) < 1e-11
     assert rel(rep.get_vec(L.VEC_AV), one.get_vec(L.VEC_AV)) < 1e-11
-    t = torch.from_numpy(rep.get_vec(L.VEC_Z_FULL).copy()).cuda()
-    ref = t.clone()
-    dist.broadcast(ref, 0)
-    assert torch.equal(t, ref)
+    assert same_on_all_ranks(rep.get_vec(L.VEC_Z_FULL))
+    dist.barrier()
     rep.close()
     one.close()
 
@@ -163,7 +182,7 @@ def main():
         assert "not sharded" in str(ex)
     dist.barrier()
     if rank == 0:
-        print("MULTI_GPU_OK world", world)
+        print("MULTI_GPU_OK world", world, "share_gpu" if share else "one_gpu_per_rank", "p2p" if use_p2p else "nccl")
     sh.close()
     full.close()
     dist.destroy_process_group()
