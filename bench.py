@@ -615,9 +615,14 @@ def main():
         # every 8-CTA cluster position reports its round time; the position the inner kernel ran on is looked up by its SM ids
         fl = e.measure_exchange(8, 4, 100000, 1)
         fl0 = e.measure_exchange(8, 4, 100000, 0)
+        lone1 = e.measure_exchange(8, 4, 100000, 1, max_clusters=1)[0]     # one cluster alone on the GPU, like the inner kernel
+        lone0 = e.measure_exchange(8, 4, 100000, 0, max_clusters=1)[0]
         here = [k for k, r in enumerate(fl) if sorted(r[2]) == sorted(smids)]
-        floor = {"what": "ns per round of exchange + partial sum + dependent next message (mode 1) / exchange only (mode 0), all "
-                         "cluster positions of the GPU measured at once; `here` = the position the inner kernel ran on",
+        floor = {"what": "ns per round of exchange + partial sum + dependent next message (mode 1) / exchange only (mode 0): `lone` = "
+                         "one cluster alone on the GPU (the inner kernel's situation; same SMs when lone_same_sms), the others = all "
+                         "cluster positions of the GPU running at once (clusters that share an SM slow each other down)",
+                 "lone_mode1_ns": lone1[0], "lone_mode0_ns": lone0[0], "lone_mode1_cycles": lone1[1],
+                 "lone_same_sms": sorted(lone1[2]) == sorted(smids),
                  "mode1_ns_min": min(r[0] for r in fl), "mode1_ns_median": float(np.median([r[0] for r in fl])),
                  "mode1_ns_max": max(r[0] for r in fl), "mode0_ns_min": min(r[0] for r in fl0),
                  "mode0_ns_median": float(np.median([r[0] for r in fl0])), "mode0_ns_max": max(r[0] for r in fl0),
@@ -660,7 +665,7 @@ def main():
                  "inner_kernel": {"bound": "latency", "kernel": "seq_kernel (persistent 8-CTA cluster, one launch per epoch)",
                                   "us_per_step": 1e3 * float(np.sum(seq_ms_list)) / inner_steps,
                                   "share_of_step_time": float(np.sum(seq_ms_list)) / ms,
-                                  "exchange_floor_us": (floor["here_mode1_ns"] or floor["mode1_ns_median"]) / 1e3,
+                                  "exchange_floor_us": floor["lone_mode1_ns"] / 1e3,
                                   "exchange_floor": floor, "smids": smids,
                                   "us_per_step_by_epoch": [round(1e3 * v / m_of(k, N), 4) for k, v in enumerate(seq_ms_list)],
                                   "algorithmic_bytes_per_step": 8 * d + 32,

@@ -74,6 +74,8 @@ SIGNATURES = {
     "ciao_get_vec": (i32, [_ctx, i32, C.c_void_p, i64]),
     "ciao_set_vec": (i32, [_ctx, i32, C.c_void_p, i64]),
     "ciao_get_table_rows": (i32, [_ctx, i64, i64, C.c_void_p]),
+    "ciao_set_table_rows": (i32, [_ctx, i64, i64, C.c_void_p]),
+    "ciao_solver_restore": (i32, [_ctx, i32, f64, i32, C.c_void_p, f64]),
     "ciao_table_colsum": (i32, [_ctx, C.c_void_p]),
     "ciao_stage_indices": (i32, [_ctx, C.c_void_p, i64]),
     "ciao_timer_begin": (i32, [_ctx]),

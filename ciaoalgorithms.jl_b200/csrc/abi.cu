@@ -589,6 +589,19 @@ extern "C" int ciao_objective(ciao_ctx *c, const double *x, double *f_mean, doub
         if (c->reg.kind == CIAO_REG_NORML1) {
             for (int64_t j = 0; j < c->d; ++j) g += fabs(hx[j]);
             g *= c->reg.lambda;
+        } else if (c->reg.kind == CIAO_REG_INDBOX) {   // IndBox: 0 inside [lo, hi], +Inf outside (ProximalOperators indBox.jl call operator)
+            std::vector<double> bounds;
+            if (c->reg.lo_v) {
+                bounds.resize((size_t)2 * c->d_pad);
+                CUDA_TRY(cudaMemcpy(bounds.data(), c->reg_bounds, bounds.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            }
+            for (int64_t j = 0; j < c->d; ++j) {
+                const double lo = c->reg.lo_v ? bounds[j] : c->reg.lo_s, hi = c->reg.lo_v ? bounds[c->d_pad + j] : c->reg.hi_s;
+                if (hx[j] < lo || hx[j] > hi) {
+                    g = INFINITY;
+                    break;
+                }
+            }
         }
         *g_val = g;
     }
@@ -656,7 +669,7 @@ extern "C" int ciao_finito_adaptive_init(ciao_ctx *c, const double *x0, double a
     CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(alloc_table(c));
     const int64_t N = c->N_total;
-    if (!c->adapt) CUDA_TRY(cudaMalloc(&c->adapt, (size_t)N * 4 * sizeof(double)));
+    if (!c->adapt) CUDA_TRY(cudaMalloc(&c->adapt, (size_t)8 * N * 4 * sizeof(double)));   // one copy per CTA of the cluster
     if (!c->adapt_scal) CUDA_TRY(cudaMalloc(&c->adapt_scal, 8 * sizeof(double)));
     if (!c->adapt_counters) CUDA_TRY(cudaMalloc(&c->adapt_counters, 4 * sizeof(int64_t)));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
@@ -678,6 +691,8 @@ extern "C" int ciao_finito_adaptive_init(ciao_ctx *c, const double *x0, double a
         CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito: ∇f_i(x0 + 1) == ∇f_i(x0) for some i; the reference then perturbs x0 at random "
                   "(Finito_adaptive.jl:75-81), which the engine does not do — choose another x0");
     }
+    for (int r = 1; r < 8; ++r)   // the per-CTA copies of {γ_i, f_i, c_i} start identical
+        CUDA_TRY(cudaMemcpyAsync(c->adapt + (size_t)r * 4 * N, c->adapt, (size_t)N * 4 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     c->hat_gamma = 1 / pairwise_recip_sum(gam.data(), 0, N);                        // :89
     CUDA_TRY(cudaMemcpyAsync(c->adapt_scal, &c->hat_gamma, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CIAO_TRY(run_adaptive_av(c, c->partial, ctx_vec(c, CIAO_VEC_TMP), c->hat_gamma));  // :90
@@ -979,6 +994,57 @@ extern "C" int ciao_get_table_rows(ciao_ctx *c, int64_t i0, int64_t n, double *o
     if (n == 0) return CIAO_OK;
     CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)c->d * 8, c->table + i0 * c->d_pad, (size_t)c->d_pad * 8, (size_t)c->d * 8, (size_t)n,
                                cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CIAO_OK;
+}
+
+// rows [i0, i0+n) of the table ← host/device array (n×d row-major): the restore half of "the iterator state is the checkpoint"
+extern "C" int ciao_set_table_rows(ciao_ctx *c, int64_t i0, int64_t n, const double *in) {
+    if (!c || !in) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_table_rows: null argument");
+    if (!c->table) CIAO_FAIL(CIAO_ERR_STATE, "ciao_set_table_rows: no table (a table solver's init or ciao_solver_restore first)");
+    if (i0 < 0 || n < 0 || i0 + n > c->n_rows) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_table_rows: rows out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (n == 0) return CIAO_OK;
+    CUDA_TRY(cudaMemcpy2DAsync(c->table + i0 * c->d_pad, (size_t)c->d_pad * 8, in, (size_t)c->d * 8, (size_t)c->d * 8, (size_t)n,
+                               cudaMemcpyDefault, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return CIAO_OK;
+}
+
+// Re-creates a solver's device state WITHOUT running its init pass, for a restore from a checkpoint: sets the algorithm, its
+// stepsizes (γ or γ_i, γ̂) and flags, allocates the table; the caller then restores the vectors with ciao_set_vec (z, z_full,
+// w, av) and the table with ciao_set_table_rows and continues with the *_steps / *_epoch calls.
+//   algo: 1 SVRG (gamma, flag = plus) | 2 SAGA (gamma, flag = sag) | 3 Finito | 4 LFinito | 5 ProShI (gamma_N, hat_gamma)
+extern "C" int ciao_solver_restore(ciao_ctx *c, int algo, double gamma, int flag, const double *gamma_N, double hat_gamma) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_solver_restore: null context");
+    if (algo == ALG_PROSHI) CIAO_TRY(need_blocks(c, "ciao_solver_restore"));
+    else CIAO_TRY(need_rows(c, "ciao_solver_restore", false));
+    switch (algo) {
+        case ALG_SVRG:
+        case ALG_SAGA:
+            if (!(gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_solver_restore: γ ≤ 0");
+            c->gamma = gamma;
+            if (algo == ALG_SVRG) c->plus = flag ? 1 : 0;
+            else c->sag = flag ? 1 : 0;
+            break;
+        case ALG_FINITO:
+        case ALG_LFINITO:
+        case ALG_PROSHI:
+            if (!gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_solver_restore: γ_i missing or γ̂ ≤ 0");
+            c->hat_gamma = hat_gamma;
+            break;
+        default:
+            CIAO_FAIL(CIAO_ERR_INVALID, "ciao_solver_restore: algo must be 1 (SVRG) … 5 (ProShI)");
+    }
+    c->algo = algo;
+    c->cz_valid = false;
+    CIAO_TRY(reserve_for_solver(c));
+    if (algo == ALG_SAGA || algo == ALG_FINITO || algo == ALG_PROSHI) CIAO_TRY(alloc_table(c));
+    if (algo == ALG_FINITO || algo == ALG_LFINITO) CIAO_TRY(set_gammas(c, gamma_N, true));
+    if (algo == ALG_PROSHI) {
+        CIAO_TRY(set_gammas(c, gamma_N, false));
+        CIAO_TRY(run_proshi_gpair(c));
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return CIAO_OK;
 }

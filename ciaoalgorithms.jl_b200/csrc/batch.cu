@@ -481,8 +481,12 @@ __global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs 
     }
 }
 
-// One minibatch over the contiguous rows [row_lo, row_lo + n): pass + reduction + finish, on the context stream.
-int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
+// One minibatch over the contiguous rows [row_lo, row_lo + n) (0-based, GLOBAL row numbers): pass over the rows this context
+// holds + tail kernel (fixed-order reduction of the CTA partials, exchange over the ranks when the rows are sharded, closing
+// update), on the context stream.  Row-sharded problems (SURVEY.md §8e last item, §8f rank 3): every rank streams the part of
+// the batch it owns — rows and table rows live together — and the batch's Σ is all-reduced in the tail kernel
+// (Finito_basic.jl:110-118 / Finito_LFinito.jl:91-100 with the batch split by row owner); `last` = last batch of the call.
+int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n, bool last = false) {
     const int64_t d_pad = c->d_pad;
     int cpt = 2;
     while (cpt < 16 && (d_pad + cpt - 1) / cpt > 256) cpt *= 2;
@@ -494,9 +498,12 @@ int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
     int S = 3;  // 2 CTAs per SM: a batch is short, so parallelism across CTAs matters more than ring depth
     while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)112 * 1024) --S;
     const size_t smem = (size_t)S * stage_bytes + fixed;
-    const int64_t n_groups = (n + rpg - 1) / rpg;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_groups, 2 * c->num_sms));
-    const size_t need = ((size_t)grid * d_pad + grid + 16) * sizeof(double);
+    // the part of the batch this context holds
+    const int64_t lo = std::max(row_lo, c->row0), hi = std::min(row_lo + n, c->row0 + c->n_rows);
+    const int64_t n_loc = std::max<int64_t>(0, hi - lo), lo_loc = lo - c->row0;
+    const int64_t n_groups = (n_loc + rpg - 1) / rpg;
+    const int grid = (int)std::min<int64_t>(n_groups, 2 * c->num_sms);
+    const size_t need = ((size_t)std::max(grid, 1) * d_pad + std::max(grid, 1) + 16) * sizeof(double);
     if (need > c->ws_bytes) {
         if (c->ws) cudaFree(c->ws);
         c->ws = nullptr;
@@ -505,32 +512,47 @@ int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n) {
         c->ws_bytes = need;
     }
     BatchArgs a;
-    a.rec = c->rec + row_lo * c->ld; a.n_rows = n; a.ld = c->ld; a.d_pad = d_pad;
+    a.rec = c->rec + lo_loc * c->ld; a.n_rows = n_loc; a.ld = c->ld; a.d_pad = d_pad;
     a.z = ctx_vec(c, CIAO_VEC_Z); a.zf = ctx_vec(c, CIAO_VEC_Z_FULL);
-    a.table = c->table ? c->table + row_lo * d_pad : nullptr;
-    a.ws = c->ws; a.fws = c->ws + (size_t)grid * d_pad;
+    a.table = c->table ? c->table + lo_loc * d_pad : nullptr;
+    a.ws = c->ws; a.fws = c->ws + (size_t)std::max(grid, 1) * d_pad;
     a.cN = c->hat_gamma / (double)c->N_total; a.stages = S;
-    int rc;
-    if (mode == BATCH_FINITO) {
-        switch (cpt) {
-            case 2: rc = launch_batch_loss<2, BATCH_FINITO>(c, a, grid, T, smem); break;
-            case 4: rc = launch_batch_loss<4, BATCH_FINITO>(c, a, grid, T, smem); break;
-            case 8: rc = launch_batch_loss<8, BATCH_FINITO>(c, a, grid, T, smem); break;
-            default: rc = launch_batch_loss<16, BATCH_FINITO>(c, a, grid, T, smem); break;
+    int rc = CIAO_OK;
+    if (grid > 0) {
+        if (mode == BATCH_FINITO) {
+            switch (cpt) {
+                case 2: rc = launch_batch_loss<2, BATCH_FINITO>(c, a, grid, T, smem); break;
+                case 4: rc = launch_batch_loss<4, BATCH_FINITO>(c, a, grid, T, smem); break;
+                case 8: rc = launch_batch_loss<8, BATCH_FINITO>(c, a, grid, T, smem); break;
+                default: rc = launch_batch_loss<16, BATCH_FINITO>(c, a, grid, T, smem); break;
+            }
+        } else {
+            switch (cpt) {
+                case 2: rc = launch_batch_loss<2, BATCH_LFINITO>(c, a, grid, T, smem); break;
+                case 4: rc = launch_batch_loss<4, BATCH_LFINITO>(c, a, grid, T, smem); break;
+                case 8: rc = launch_batch_loss<8, BATCH_LFINITO>(c, a, grid, T, smem); break;
+                default: rc = launch_batch_loss<16, BATCH_LFINITO>(c, a, grid, T, smem); break;
+            }
         }
-    } else {
-        switch (cpt) {
-            case 2: rc = launch_batch_loss<2, BATCH_LFINITO>(c, a, grid, T, smem); break;
-            case 4: rc = launch_batch_loss<4, BATCH_LFINITO>(c, a, grid, T, smem); break;
-            case 8: rc = launch_batch_loss<8, BATCH_LFINITO>(c, a, grid, T, smem); break;
-            default: rc = launch_batch_loss<16, BATCH_LFINITO>(c, a, grid, T, smem); break;
-        }
+        CIAO_TRY(rc);
+        c->timing.launches += 1;
     }
-    CIAO_TRY(rc);
-    batch_reduce_finish_kernel<<<(int)((d_pad + 31) / 32), dim3(32, REDUCE_SLICES), 0, c->stream>>>(
-        a.ws, a.fws, grid, ctx_vec(c, CIAO_VEC_AV), ctx_vec(c, CIAO_VEC_Z), ctx_vec(c, CIAO_VEC_Z_FULL), d_pad, mode, c->hat_gamma, c->reg);
+    const bool sharded = c->world > 1 && c->n_rows != c->N_total;
+    if (sharded && !c->p2p_ready)
+        CIAO_FAIL(CIAO_ERR_STATE, "minibatch steps on row shards need the peer exchange (ciao_comm_p2p_handle / ciao_comm_p2p_attach)");
+    TailArgs t;
+    memset(&t, 0, sizeof(t));
+    t.ws = a.ws; t.fws = a.fws; t.G = grid; t.d_pad = d_pad; t.len = (int)d_pad + 1;
+    t.fmax_mode = 0; t.with_vec = 1; t.chunk0 = 0;
+    t.sum_out = c->partial;
+    t.fin_mode = mode == BATCH_FINITO ? FIN_FINITO : FIN_LFINITO;
+    t.last_batch = last ? 1 : 0;
+    t.av = ctx_vec(c, CIAO_VEC_AV); t.z = ctx_vec(c, CIAO_VEC_Z); t.zf = ctx_vec(c, CIAO_VEC_Z_FULL);
+    t.hat_gamma = c->hat_gamma; t.reg = c->reg;
+    fill_exchange(c, t, sharded);
+    pass_tail_kernel<<<(int)((d_pad + 1 + 31) / 32), dim3(32, REDUCE_SLICES), 0, c->stream>>>(t);
     CUDA_TRY(cudaGetLastError());
-    c->timing.launches += 2;
+    c->timing.launches += 1;
     return CIAO_OK;
 }
 

@@ -196,6 +196,15 @@ __device__ __forceinline__ void tma_load_1d_s(uint32_t smem_dst, const void *gsr
                  "l"(gsrc), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// 16-byte asynchronous copy global → shared through the GENERIC proxy (LDGSTS, L2 only); used for data that is also written
+// inside the same kernel, where a TMA bulk copy (async proxy) would need a proxy fence in the writing thread
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+// the executing thread's earlier cp.async copies arrive on the mbarrier when they complete (the count was armed for it: .noinc)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void sts_b64(uint32_t addr, int64_t v) {
     asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
 }

@@ -236,11 +236,20 @@ struct TailArgs {
     uint64_t timeout_ns;
     double *arena[CIAO_MAX_PEERS];
     double *sum_out;             // [len]: the raw all-rank sum (vector, then the scalar)
-    const double *base;          // finish (out == nullptr: none)
+    const double *base;          // FIN_PASS: out = base + scale·(Σ/den)   (out == nullptr: none)
     double scale, den;
     double *out;
+    // closing update of a minibatch whose rows are sharded over the ranks (batch.cu run_batch_step_sharded):
+    //   FIN_FINITO   av += Σ;  z = prox_g(av, γ̂)                                   Finito_basic.jl:115-118
+    //   FIN_LFINITO  av += Σ + (Σ_i γ̂/γ_i)·(z − z_full);  z = prox_g(av, γ̂) unless last    Finito_LFinito.jl:92-98
+    int fin_mode, last_batch;
+    double *av, *z;
+    const double *zf;
+    double hat_gamma;
+    RegParams reg;
     int *err;
 };
+enum { FIN_PASS = 0, FIN_FINITO = 1, FIN_LFINITO = 2 };
 
 __device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -316,6 +325,50 @@ __global__ void __launch_bounds__(32 * REDUCE_SLICES) pass_tail_kernel(const Tai
                 t = is_max ? fmax(t, v) : t + v;
             }
         }
+    }
+    if (a.fin_mode != FIN_PASS) {   // minibatch closing update on this chunk's columns
+        // LFinito needs the batch's scalar Σ_i γ̂/γ_i in every chunk: each block sums the CTA partials itself (G ≤ a few hundred
+        // L2-resident doubles) and, with several ranks, waits for the scalar chunk's flags and adds the ranks' slots in rank order
+        __shared__ double fs_sh;
+        if (a.fin_mode == FIN_LFINITO) {
+            double f = 0.0;
+            if (y == 0 && x == 0) {
+                if (a.world > 1) {
+                    const int sc = (int)(a.d_pad / 32);
+                    const uint32_t *flags = reinterpret_cast<const uint32_t *>(a.arena[a.rank] + P2P_MAIL_DOUBLES);
+                    const uint64_t t0 = global_timer_ns();
+                    for (int r = 0; r < a.world; ++r)
+                        while ((int32_t)(ld_acquire_sys_u32(flags + r * P2P_CHUNKS + sc) - a.seq) < 0) {
+                            if (global_timer_ns() - t0 > a.timeout_ns) {
+                                atomicExch(a.err, 3);
+                                break;
+                            }
+                            __nanosleep(100);
+                        }
+                    const double *slot = a.arena[a.rank] + (size_t)(a.seq & 1u) * CIAO_MAX_PEERS * P2P_CAP + a.d_pad;
+                    for (int r = 0; r < a.world; ++r) f += ld_relaxed_sys_f64(slot + (size_t)r * P2P_CAP);
+                } else {
+                    // same slice order as the scalar column above, so every block and the scalar chunk agree bit for bit
+                    for (int q = 0; q < REDUCE_SLICES; ++q) {
+                        double sq = 0.0;
+                        for (int b = q; b < a.G; b += REDUCE_SLICES) sq += a.fws[b];
+                        f += sq;
+                    }
+                }
+                fs_sh = f;
+            }
+            __syncthreads();
+        }
+        if (y == 0 && j < a.d_pad) {
+            double anew = __dadd_rn(a.av[j], t);
+            if (a.fin_mode == FIN_LFINITO) anew = __dadd_rn(anew, __dmul_rn(fs_sh, __dsub_rn(a.z[j], a.zf[j])));
+            a.av[j] = anew;
+            if (a.fin_mode == FIN_FINITO || !a.last_batch) {
+                const double lo = a.reg.lo_v ? a.reg.lo_v[j] : a.reg.lo_s, hi = a.reg.hi_v ? a.reg.hi_v[j] : a.reg.hi_s;
+                a.z[j] = prox_rt(a.reg.kind, anew, a.hat_gamma * a.reg.lambda, lo, hi);
+            }
+        }
+        return;
     }
     if (y == 0 && j < a.len) {
         a.sum_out[j] = t;

@@ -40,9 +40,9 @@ __device__ __forceinline__ double proshi_grad(double q, double c, double s, doub
 
 // Batch-1 steps: a true dependency chain per column (z_j → s_ij → av_j → z_j), so the kernel is latency/issue bound and
 // everything that is not on that chain has to stay off the compute warp.  A CTA owns 32·CPT columns: ONE compute warp keeps
-// z_j, av_j of its columns in registers for the whole call; TWO producer lanes (warps 1 and 2, even and odd steps) TMA-stage
-// the column slices of (q_i, c_i, s_i), the pair (γ_i, γ_i/N) and the index word of the block needed PROSHI_D steps later
-// into a full/empty mbarrier ring.  No reduction, no CTA barrier, no kernel launch per step.
+// z_j, av_j of its columns in registers for the whole call; TWO producer warps (even and odd steps) stage the column slices
+// of (q_i, c_i) and the pair (γ_i, γ_i/N) by TMA, the table slice s_i by cp.async and the index word of the block needed
+// PROSHI_D steps later into a full/empty mbarrier ring.  No reduction, no CTA barrier, no kernel launch per step.
 // History: register prefetch with ld.global ran at 0.74 µs/block (ptxas tracks all those loads with one scoreboard, so the
 // first use of step k's registers also waited for the load just issued for step k+D: one DRAM latency per step); per-thread
 // cp.async groups at 0.30 µs/block (≈ 190 instructions per step on the one warp that also walks the chain); with the staging
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(32 * (1 + PROSHI_PRODUCERS)) proshi_steps_kern
     for (int i = tid; i < D * SLOT; i += blockDim.x) ring[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < D; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], 33);   // lane 0's arrive.expect_tx + one cp.async arrive per lane of the producer warp
             mbar_init(&empty_bar[s], 1);
         }
         fence_mbar_init();
@@ -80,26 +80,34 @@ __global__ void __launch_bounds__(32 * (1 + PROSHI_PRODUCERS)) proshi_steps_kern
     __syncthreads();
 
     if (warp >= 1) {
-        // ===================== producer lanes: warp 1 stages the even steps, warp 2 the odd ones =====================
-        if (lane == 0) {
-            const int Ki = (int)K;
-            const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
-            const uint32_t bytes = (uint32_t)ncol * 8;
-            const uint32_t tx = 3 * bytes + 16;
-            for (int st = warp - 1; st < Ki; st += PROSHI_PRODUCERS) {
-                const uint32_t slot = (uint32_t)st & (D - 1);
+        // ===================== producer warps: warp 1 stages the even steps, warp 2 the odd ones =====================
+        // Lane 0 waits for the slot, arms the barrier and issues the bulk copies of the read-only slices (q_i, c_i, γ pair);
+        // the TABLE slice — written inside this kernel by the compute warp — is copied by the lanes of the producer warp with
+        // cp.async (generic proxy, like the stores; see seq_impl.cuh): the compute warp's st.global of step k is ordered before
+        // it by the warp barrier + release arrive on empty_bar in take(), this warp's acquire wait on that barrier and its own
+        // warp barrier.  Every repeat at distance ≥ PROSHI_D + 1 is ordered that way, closer ones carry the HAZARD flag.
+        const int Ki = (int)K;
+        const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
+        const uint32_t bytes = (uint32_t)ncol * 8;
+        const uint32_t tx = 2 * bytes + 16;
+        const uint32_t n_chunks = (uint32_t)ncol / 2;   // 16-byte chunks of the table slice (≤ 32)
+        for (int st = warp - 1; st < Ki; st += PROSHI_PRODUCERS) {
+            const uint32_t slot = (uint32_t)st & (D - 1);
+            const int64_t pidx = __ldg(p.idx + st);
+            const int64_t i = pidx & CIAO_IDX_MASK;
+            const int64_t off = i * p.n_pad + col0;
+            const uint32_t dst = ring_s + slot * (SLOT * 8), bar = full_s + slot * 8;
+            if (lane == 0) {
                 if (st >= D) mbar_wait_s(empty_s + slot * 8, (((uint32_t)st / D) - 1u) & 1u);  // step st − D has left the slot
-                const int64_t pidx = __ldg(p.idx + st);
-                const int64_t i = pidx & CIAO_IDX_MASK;
-                const int64_t off = i * p.n_pad + col0;
-                const uint32_t dst = ring_s + slot * (SLOT * 8), bar = full_s + slot * 8;
                 sts_b64(dst + (3 * COLS + 2) * 8, pidx);  // released by the arrive below
                 mbar_arrive_expect_tx_s(bar, tx);
                 tma_load_1d_s(dst, p.qd + off, bytes, bar);
                 tma_load_1d_s(dst + COLS * 8, p.ql + off, bytes, bar);
-                tma_load_1d_s(dst + 2 * COLS * 8, p.table + off, bytes, bar);
                 tma_load_1d_s(dst + 3 * COLS * 8, p.gpair + 2 * i, 16, bar);
             }
+            __syncwarp();
+            if ((uint32_t)lane < n_chunks) cp_async_16(dst + 2 * COLS * 8 + lane * 16, p.table + off + 2 * lane);
+            cp_async_arrive_noinc(bar);
         }
         return;
     }
@@ -172,10 +180,6 @@ __global__ void __launch_bounds__(32 * (1 + PROSHI_PRODUCERS)) proshi_steps_kern
             if (CPT == 2) __stcg(reinterpret_cast<double2 *>(srow), make_double2(t[0], t[CPT - 1]));
             else __stcg(srow, t[0]);
         }
-        // generic-proxy table write → visible to the producers' later TMA reads: this fence, then the warp barrier + release
-        // arrive on empty_bar in take() below, then the producer's acquire wait on that barrier before it refills the slot —
-        // every repeat at distance ≥ PROSHI_D + 1 is ordered that way, closer ones carry the HAZARD flag (window 19)
-        fence_proxy_async();
         if (ik & CIAO_FLAG_PROX) {  // :121-123
 #pragma unroll
             for (int e = 0; e < CPT; ++e)
@@ -412,6 +416,19 @@ int run_proshi_init(ciao_ctx *c, const double *x0_dev) {
     c->timing.last_pass_bytes = c->N_total * c->d_pad * 24;
     c->pass_timed = true;
     return reduce_partials(c, G);
+}
+
+// gpair[i] = (γ_i, γ_i/N) without touching the table (ciao_solver_restore)
+__global__ void proshi_gpair_kernel(const double *gam, double *gpair, int64_t N, double Nd) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < N) reinterpret_cast<double2 *>(gpair)[i] = make_double2(gam[i], __ddiv_rn(gam[i], Nd));
+}
+int run_proshi_gpair(ciao_ctx *c) {
+    if (!c->gpair) CUDA_TRY(cudaMalloc(&c->gpair, (size_t)c->N_total * 2 * sizeof(double)));
+    proshi_gpair_kernel<<<(int)((c->N_total + 255) / 256), 256, 0, c->stream>>>(c->gamma_dev, c->gpair, c->N_total, (double)c->N_total);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
 }
 
 int run_proshi_dual(ciao_ctx *c) {

@@ -23,7 +23,9 @@ struct AdArgs {
     const int64_t *idx;  // prepared: 0-based row | HAZARD | distance
     int64_t K;
     double *table;       // [N][d_pad]  x_i            (state.s)
-    double *ad;          // [N][4]      {γ_i, f_i(x_i), c_i(x_i), 0}   (state.γ, state.fi_x, state.∇f as a scalar)
+    double *ad;          // [8][N][4]   {γ_i, f_i(x_i), c_i(x_i), 0}   (state.γ, state.fi_x, state.∇f as a scalar), one private
+                         //             copy per CTA of the cluster: a CTA stages (cp.async) only what it wrote itself
+    int64_t N;
     double *scal;        // [0] γ̂ (in/out)
     int64_t *counters;   // [0] steps completed by this call, [1] linesearch reductions of γ
     double *v_z, *v_av;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
     for (size_t i = tid; i < D * slot_doubles + 2 * (size_t)p.npart_pad * 4 + (size_t)W * AD_HIST * 4; i += blockDim.x) ring[i] = 0.0;
     if (tid == 0) {
         for (int s = 0; s < D; ++s) {
-            mbar_init(&row_bar[s], 1);
+            mbar_init(&row_bar[s], 33);   // lane 0's arrive.expect_tx + one cp.async arrive per producer lane
             mbar_init(&empty_bar[s], W);
         }
         mbar_init(&part_bar[0], 1);
@@ -75,32 +77,38 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
     cluster_sync_all();
 
     if (warp == W) {
-        // ===================== producer lane: keeps the ring D steps ahead =====================
-        if (lane == 0) {
-            const int Ki = (int)K;
-            const uint32_t ring_s = smem_u32(ring), row_bar_s = smem_u32(row_bar), empty_bar_s = smem_u32(empty_bar);
-            const uint32_t slot_bytes = (uint32_t)(slot_doubles * 8), row_bytes = (uint32_t)(dc * 8);
-            const uint32_t tail_off = (uint32_t)cover * 8, table_off = (uint32_t)(cover + AD_EXTRA) * 8;
-            const uint32_t tx_bytes = 2 * row_bytes + CIAO_TAIL_USED * 8 + 32;
-            auto issue = [&](int step) {
-                const int64_t pidx = __ldg(p.idx + step);
-                const int64_t i = pidx & CIAO_IDX_MASK;
-                const uint32_t slot = (uint32_t)step & (D - 1);
-                const uint32_t dst = ring_s + slot * slot_bytes, bar = row_bar_s + slot * 8;
+        // ===================== producer warp: keeps the ring D steps ahead =====================
+        // Lane 0 waits for the slot and issues the bulk copies of the row and its tail (never written in the kernel); the table
+        // row x_i and the scalars {γ_i, f_i, c_i} — both rewritten by the compute warps of THIS CTA — are copied by all lanes
+        // with cp.async (generic proxy, see seq_impl.cuh).  Ordering: st.global of step k → warp barrier + release arrive on
+        // empty_bar in the next load() → lane 0's acquire wait below → this warp's barrier → the copies.  Repeats at distance
+        // ≥ AD_D + 2 are ordered that way, closer ones carry the HAZARD flag (history / re-read behind the own store).
+        const int Ki = (int)K;
+        const uint32_t ring_s = smem_u32(ring), row_bar_s = smem_u32(row_bar), empty_bar_s = smem_u32(empty_bar);
+        const uint32_t slot_bytes = (uint32_t)(slot_doubles * 8), row_bytes = (uint32_t)(dc * 8);
+        const uint32_t tail_off = (uint32_t)cover * 8, table_off = (uint32_t)(cover + AD_EXTRA) * 8;
+        const uint32_t tx_bytes = row_bytes + CIAO_TAIL_USED * 8;
+        const uint32_t n_chunks = (uint32_t)(dc / 2);
+        const double *ad_mine = p.ad + (size_t)rank * 4 * (size_t)p.N;
+        for (int st = 0; st < Ki; ++st) {
+            const int64_t pidx = __ldg(p.idx + st);
+            const int64_t i = pidx & CIAO_IDX_MASK;
+            const uint32_t slot = (uint32_t)st & (D - 1);
+            const uint32_t dst = ring_s + slot * slot_bytes, bar = row_bar_s + slot * 8;
+            if (lane == 0) {
+                // every compute warp has pulled step st − D out of this slot
+                if (st >= D) mbar_wait_s(empty_bar_s + slot * 8, (((uint32_t)st / D) - 1u) & 1u);
                 const double *src = p.rec + i * p.ld;
                 sts_b64(dst + tail_off + 80, pidx);
                 mbar_arrive_expect_tx_s(bar, tx_bytes);
                 tma_load_1d_s(dst, src + cbase, row_bytes, bar);
                 tma_load_1d_s(dst + tail_off, src + p.d_pad, CIAO_TAIL_USED * 8, bar);
-                tma_load_1d_s(dst + tail_off + CIAO_TAIL_USED * 8, p.ad + 4 * i, 32, bar);
-                tma_load_1d_s(dst + table_off, p.table + i * p.d_pad + cbase, row_bytes, bar);
-            };
-            for (int st = 0; st < D && st < Ki; ++st) issue(st);
-            for (int st = D; st < Ki; ++st) {
-                // every compute warp has pulled step st − D out of this slot
-                mbar_wait_s(empty_bar_s + ((uint32_t)st & (D - 1)) * 8, (((uint32_t)st / D) - 1u) & 1u);
-                issue(st);
             }
+            __syncwarp();
+            const double *trow = p.table + i * p.d_pad + cbase;
+            for (uint32_t ch = lane; ch < n_chunks; ch += 32) cp_async_16(dst + table_off + ch * 16, trow + 2 * ch);
+            if (lane < 2) cp_async_16(dst + tail_off + CIAO_TAIL_USED * 8 + lane * 16, ad_mine + 4 * i + 2 * lane);
+            cp_async_arrive_noinc(bar);
         }
     } else {
         // ===================== compute warps =====================
@@ -319,16 +327,13 @@ __global__ void __launch_bounds__(288, 1) adaptive_kernel(const AdArgs p) {
                 hp[0] = gam; hp[1] = fi_z; hp[2] = cnew;
             }
             __syncwarp();
-            // Every CTA stores the (bit-identical) scalars itself, so that each CTA's TMA reads of p.ad are ordered behind a
-            // write of its own: table row and scalars → fence.proxy.async → warp barrier + release arrive on empty_bar in the
-            // next load() → the producer's acquire wait before it refills that slot (distance ≥ AD_D + 2; closer repeats carry
-            // the HAZARD flag and use the history / re-read behind the own store).
+            // every CTA keeps its own copy of the (bit-identical) scalars, so that what its producer warp stages later was written
+            // by this CTA and is ordered by the CTA-scope release/acquire chain through empty_bar
             if (tid == 0) {
-                double *o = p.ad + 4 * (ik & CIAO_IDX_MASK);
-                asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(o), "d"(gam), "d"(fi_z) : "memory");
-                asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1, %2};" ::"l"(o + 2), "d"(cnew), "d"(0.0) : "memory");
+                double2 *o = reinterpret_cast<double2 *>(p.ad + (size_t)rank * 4 * (size_t)p.N + 4 * (ik & CIAO_IDX_MASK));
+                __stcg(o, make_double2(gam, fi_z));
+                __stcg(o + 1, make_double2(cnew, 0.0));
             }
-            fence_proxy_async();
             ++done;
             PROF_T(t_f);
             PROF_ADD(5, t_e, t_f);  // main update, stores, history
@@ -482,7 +487,7 @@ int run_seq_adaptive(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double
     sh.npart_pad = (sh.C * (sh.Tc / 32) + 31) / 32 * 32;
     AdArgs a;
     a.rec = c->rec; a.ld = c->ld; a.d_pad = c->d_pad; a.dc = sh.dc; a.idx = idx_prepared; a.K = K;
-    a.table = c->table; a.ad = c->adapt; a.scal = c->adapt_scal; a.counters = c->adapt_counters;
+    a.table = c->table; a.ad = c->adapt; a.N = c->N_total; a.scal = c->adapt_scal; a.counters = c->adapt_counters;
     a.v_z = ctx_vec(c, CIAO_VEC_Z); a.v_av = ctx_vec(c, CIAO_VEC_AV);
     a.Nd = (double)c->N_total; a.alpha = alpha; a.tol_b = tol_b; a.npart_pad = sh.npart_pad; a.zero = 0; a.reg = c->reg;
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));

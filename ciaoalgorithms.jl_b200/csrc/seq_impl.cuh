@@ -47,7 +47,7 @@ struct SeqArgs {
     double gamma, hat_gamma, Nd, m_d;
     int plus, sag;
     int npart_pad;          // C·W rounded up to a multiple of 32
-    int table_tma;          // table rows are staged in the ring by TMA (else: register prefetch with ld.global)
+    int table_tma;          // table rows are staged in the ring (cp.async by the producer warp; else: register prefetch with ld.global)
     int zero;               // always 0, opaque to the compiler (pins work in front of the exchange wait, see below)
     int *smid_out;          // [C]: the SM each CTA of the cluster runs on (cross-SM DSMEM latency is a per-pair constant)
     const int *err;         // error flag of the context: set by prep_indices_kernel when an index is out of range → no step runs
@@ -66,15 +66,18 @@ static __device__ long long g_seq_prof[16 * 8];  // [CTA rank][phase]: accumulat
 constexpr int SEQ_D = 8;           // row ring depth (steps of prefetch), power of two
 static_assert((SEQ_D & (SEQ_D - 1)) == 0, "ring slots and mbarrier parities are derived from step & (D - 1), step / D");
 static_assert(SEQ_D + 1 <= CIAO_HAZARD_WINDOW - 1, "prep_indices_kernel must flag repeats within the prefetch window");
-// Table rows (SAGA/Finito) are written by the compute threads through the generic proxy (st.global.cg) and re-read, D steps
-// ahead of their use, by the producer lane's TMA copies through the async proxy.  A repeat at distance < CIAO_HAZARD_WINDOW is
-// flagged and re-read by the writing thread itself; for the others the write is ordered before the copy by a chain the PTX
-// memory model recognises: st.global → fence.proxy.async → warp barrier → mbarrier.arrive (release) on a "written" barrier
-// of step k → the producer's try_wait (acquire) on that barrier before it issues the copies for step k + 1 + D.  Repeats at
-// distance ≥ D + 1 are therefore ordered, repeats at distance ≤ CIAO_HAZARD_WINDOW − 1 are flagged: no gap, no timing assumption.
-//   CIAO_TABLE_FENCE = 0: round-1 behaviour (no fence; measurement only), 1: proxy fence only, 2 (default): fence + barrier.
-#ifndef CIAO_TABLE_FENCE
-#define CIAO_TABLE_FENCE 2
+// Table rows (SAGA/Finito) are written by the compute threads with st.global.cg and re-read, D steps ahead of their use, into
+// the ring.  Both sides stay in the GENERIC proxy: the staging copies are cp.async (LDGSTS, 16 bytes per lane of the producer
+// warp, completion on the slot's mbarrier with cp.async.mbarrier.arrive), not TMA bulk copies — a bulk copy reads through the
+// async proxy, and ordering a generic-proxy write before it needs fence.proxy.async in the WRITING thread, which waits for the
+// thread's stores to reach L2: measured +0.34 µs per step, twice the step (profiles/seq_variants_r2.log).  With one proxy the
+// ordering is ordinary release/acquire at CTA scope: st.global → warp barrier → mbarrier.arrive (release) on the "written"
+// barrier of step k → the producer warp's try_wait (acquire) on it before it issues the copies of step k + 1 + D.  Repeats at
+// distance ≥ D + 1 are ordered that way, repeats at distance ≤ CIAO_HAZARD_WINDOW − 1 carry the HAZARD flag and are re-read by
+// the thread that wrote them: no gap and no timing assumption.  (The rows a_i, their tails and the pass-written scalars are
+// never written inside the kernel and stay on TMA.)   CIAO_TABLE_ORDERED=0 drops the barrier (measurement only).
+#ifndef CIAO_TABLE_ORDERED
+#define CIAO_TABLE_ORDERED 1
 #endif
 static_assert(SEQ_D + 1 <= CIAO_HAZARD_WINDOW - 1, "every repeat closer than the ordered distance D + 1 must carry the HAZARD flag");
 constexpr int SEQ_MAX_PART = 128;  // C·W ≤ 128
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
     const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
     const int64_t dc = p.dc;
     const int cover = Tc * CPT;                       // columns covered by the thread grid (≥ dc)
-    const bool TT = TABLE && p.table_tma;             // table row slices ride in the ring slots, behind the record tail
+    const bool TT = TABLE && p.table_tma;             // table row slices are staged in the ring slots, behind the record tail
     const size_t slot_doubles = (size_t)cover + SEQ_SLOT_EXTRA + (TT ? cover : 0);
     double *ring = reinterpret_cast<double *>(smem_raw);
     double *part = ring + D * slot_doubles;           // [2][npart_pad][2]
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
         uint32_t sm;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
         p.smid_out[rank] = (int)sm;
-        for (int s = 0; s < D; ++s) mbar_init(&row_bar[s], 1);
+        for (int s = 0; s < D; ++s) mbar_init(&row_bar[s], TT ? 33 : 1);  // + one cp.async arrive per producer lane
         mbar_init(&part_bar[0], 1);  // one local arrive (expect_tx) per phase; the data arrives as tx bytes
         mbar_init(&part_bar[1], 1);
         if (TABLE)
@@ -142,7 +145,9 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
         // and byte counts computed once, no shard search when all rows are local, two bulk copies per step for the
         // table-free algorithms.  (Profile: a 64-bit/three-copy version took ≈ 650 cycles per iteration and was the
         // bottleneck of every variant whose compute path is shorter than that.)
-        if (lane == 0) {
+        // With a staged table (TT) all 32 lanes walk the loop: lane 0 does the waits, the arming and the bulk copies, then
+        // every lane copies 16-byte chunks of the table row slice with cp.async.
+        if (lane == 0 || TT) {
             const int Ki = (int)K;  // run_seq_alg guarantees K < 2^31
             const uint32_t ring_s = smem_u32(ring), row_bar_s = smem_u32(row_bar), part_bar_s = smem_u32(part_bar);
             const uint32_t slot_bytes = (uint32_t)(slot_doubles * 8);
@@ -152,7 +157,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             const uint32_t tail_off = (uint32_t)cover * 8, idx_off = (uint32_t)(cover + SEQ_IDX_POS) * 8;
             const uint32_t table_off = (uint32_t)(cover + SEQ_SLOT_EXTRA) * 8;
             const uint32_t tail_bytes = (uint32_t)(CIAO_TAIL_USED * 8);
-            const uint32_t tx_bytes = row_bytes * (TT ? 2u : 1u) + (SS_ONLY ? 32u : tail_bytes + (SS_EXTRA ? 32u : 0u));
+            const uint32_t tx_bytes = row_bytes + (SS_ONLY ? 32u : tail_bytes + (SS_EXTRA ? 32u : 0u));
+            const uint32_t n_chunks = (uint32_t)(dc / 2);        // 16-byte chunks of a table row slice
             const bool one_shard = p.rows.n <= 1;
             const double *base0 = p.rows.base[0] + cbase;
             const double *table0 = TABLE ? p.table + cbase : nullptr;
@@ -161,67 +167,67 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const int64_t i = pidx & CIAO_IDX_MASK;
                 const uint32_t slot = (uint32_t)step & (D - 1);
                 const uint32_t dst = ring_s + slot * slot_bytes, bar = row_bar_s + slot * 8;
-                const double *src;
-                if (one_shard) {
-                    src = base0 + i * ld;
-                } else {  // shard holding row i (≤ 8 shards: linear search)
-                    int sh = 0;
-                    while (sh + 1 < p.rows.n && i >= p.rows.start[sh + 1]) ++sh;
-                    src = p.rows.base[sh] + (i - p.rows.start[sh]) * ld + cbase;
+                if (lane == 0) {
+                    const double *src;
+                    if (one_shard) {
+                        src = base0 + i * ld;
+                    } else {  // shard holding row i (≤ 8 shards: linear search)
+                        int sh = 0;
+                        while (sh + 1 < p.rows.n && i >= p.rows.start[sh + 1]) ++sh;
+                        src = p.rows.base[sh] + (i - p.rows.start[sh]) * ld + cbase;
+                    }
+                    sts_b64(dst + idx_off, pidx);  // released by the arrive below
+                    mbar_arrive_expect_tx_s(bar, tx_bytes);
+                    tma_load_1d_s(dst, src, row_bytes, bar);
+                    // the step's scalars: the record tail and/or {b_i, λ_i, 0, c_i(z_full)} from the dense array of the last pass
+                    if (!SS_ONLY) tma_load_1d_s(dst + tail_off, src + (d_pad - cbase), tail_bytes, bar);
+                    if (SS_ONLY) tma_load_1d_s(dst + tail_off, p.ss + 4 * i, 32, bar);
+                    if (SS_EXTRA) tma_load_1d_s(dst + tail_off + CIAO_TAIL_USED * 8, p.ss + 4 * i, 32, bar);
+                    if (TABLE && !TT) tma_prefetch_l2(table0 + i * d_pad, row_bytes);
                 }
-                sts_b64(dst + idx_off, pidx);  // released by the arrive below
-                mbar_arrive_expect_tx_s(bar, tx_bytes);
-                tma_load_1d_s(dst, src, row_bytes, bar);
-                // the step's scalars: the record tail and/or {b_i, λ_i, 0, c_i(z_full)} from the dense array of the last pass
-                if (!SS_ONLY) tma_load_1d_s(dst + tail_off, src + (d_pad - cbase), tail_bytes, bar);
-                if (SS_ONLY) tma_load_1d_s(dst + tail_off, p.ss + 4 * i, 32, bar);
-                if (SS_EXTRA) tma_load_1d_s(dst + tail_off + CIAO_TAIL_USED * 8, p.ss + 4 * i, 32, bar);
-                if (TT) tma_load_1d_s(dst + table_off, table0 + i * d_pad, row_bytes, bar);
-                else if (TABLE) tma_prefetch_l2(table0 + i * d_pad, row_bytes);
+                if (TT) {
+                    __syncwarp();  // lane 0's acquire of the "written" barrier is ordered before every lane's copies
+                    const double *trow = table0 + i * d_pad;
+                    for (uint32_t ch = lane; ch < n_chunks; ch += 32) cp_async_16(dst + table_off + ch * 16, trow + 2 * ch);
+                    cp_async_arrive_noinc(bar);
+                }
             };
-            if (Ki > 0) mbar_arrive_expect_tx_s(part_bar_s, part_bytes);
-            if (Ki > 1) mbar_arrive_expect_tx_s(part_bar_s + 8, part_bytes);
+            if (lane == 0) {
+                if (Ki > 0) mbar_arrive_expect_tx_s(part_bar_s, part_bytes);
+                if (Ki > 1) mbar_arrive_expect_tx_s(part_bar_s + 8, part_bytes);
+            }
             for (int st = 0; st < D && st < Ki; ++st) issue_row(st, __ldg(p.idx + st));
-#ifdef CIAO_SEQ_PROD4
-            // experiment: the index words four iterations ahead (an L2 miss of the 8-byte load is longer than a step)
-            int64_t nq[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) nq[q] = (D + q < Ki) ? __ldg(p.idx + D + q) : 0;
-            const int64_t *idx_ahead = p.idx + D + 4;
-#else
             int64_t n1 = (D < Ki) ? __ldg(p.idx + D) : 0, n2 = (D + 1 < Ki) ? __ldg(p.idx + D + 1) : 0;
             const int64_t *idx_ahead = p.idx + D + 2;
-#endif
 #ifdef CIAO_SEQ_PROFILE
             long long prod_busy = 0;
 #endif
             for (int k = 0; k < Ki; ++k) {
-                const uint32_t pb = part_bar_s + ((uint32_t)k & 1u) * 8;
-                // phase k complete ⇒ every warp of the cluster has consumed row k and sent its partial
-                mbar_wait_s(pb, ((uint32_t)k >> 1) & 1u);
 #ifdef CIAO_SEQ_PROFILE
-                const long long pw = clock64();
+                long long pw = 0;
 #endif
-                if (k + 2 < Ki) mbar_arrive_expect_tx_s(pb, part_bytes);  // arm the exchange of step k+2
-                // the table writes of steps ≤ k − 1 (all warps have sent partial k, hence finished step k − 1: this wait never
-                // spins) are acquired before the copies of step k + D read the table
-                if (TT && CIAO_TABLE_FENCE >= 2 && k >= 1)
-                    mbar_wait_s(smem_u32(wr_bar) + (((uint32_t)k - 1u) & (D - 1)) * 8, (((uint32_t)k - 1u) / D) & 1u);
-#ifdef CIAO_SEQ_PROD4
-                if (k + D < Ki) issue_row(k + D, nq[0]);
-                nq[0] = nq[1]; nq[1] = nq[2]; nq[2] = nq[3];
-                nq[3] = (k + D + 4 < Ki) ? __ldg(idx_ahead + k) : 0;
-#else
+                if (lane == 0) {
+                    const uint32_t pb = part_bar_s + ((uint32_t)k & 1u) * 8;
+                    // phase k complete ⇒ every warp of the cluster has consumed row k and sent its partial
+                    mbar_wait_s(pb, ((uint32_t)k >> 1) & 1u);
+#ifdef CIAO_SEQ_PROFILE
+                    pw = clock64();
+#endif
+                    if (k + 2 < Ki) mbar_arrive_expect_tx_s(pb, part_bytes);  // arm the exchange of step k+2
+                    // the table writes of steps ≤ k − 1 (every warp has sent partial k, hence finished step k − 1: this wait
+                    // never spins) are acquired before the copies of step k + D read the table
+                    if (TT && CIAO_TABLE_ORDERED && k >= 1)
+                        mbar_wait_s(smem_u32(wr_bar) + (((uint32_t)k - 1u) & (D - 1)) * 8, (((uint32_t)k - 1u) / D) & 1u);
+                }
                 if (k + D < Ki) issue_row(k + D, n1);
                 n1 = n2;
                 n2 = (k + D + 2 < Ki) ? __ldg(idx_ahead + k) : 0;
-#endif
 #ifdef CIAO_SEQ_PROFILE
-                prod_busy += clock64() - pw;
+                if (lane == 0) prod_busy += clock64() - pw;
 #endif
             }
 #ifdef CIAO_SEQ_PROFILE
-            g_seq_prof[rank * 8 + 5] = prod_busy;  // producer: cycles from wake-up to the end of its iteration
+            if (lane == 0) g_seq_prof[rank * 8 + 5] = prod_busy;  // producer: cycles from wake-up to the end of its iteration
 #endif
         }
     } else {
@@ -460,12 +466,9 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 for (int h = 0; h < H; ++h)
                     if (valid[h])
                         __stcg(reinterpret_cast<double2 *>(trow + gcol[h]), make_double2(snew[2 * h], snew[2 * h + 1]));
-                if (TT && CIAO_TABLE_FENCE >= 1) {
-                    fence_proxy_async();   // generic-proxy table writes → visible to later async-proxy (TMA) reads
-                    if (CIAO_TABLE_FENCE >= 2) {
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&wr_bar[k & (D - 1)]);
-                    }
+                if (TT && CIAO_TABLE_ORDERED) {   // release: this warp's table writes of step k are visible to whoever acquires wr_bar
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&wr_bar[k & (D - 1)]);
                 }
             }
             PROF_T(t_e);

@@ -210,6 +210,16 @@ class Engine:
         check(self.lib.ciao_get_table_rows(self.h, i0, n, ptr(out)))
         return out
 
+    def set_table_rows(self, rows, i0=0):
+        rows = f64arr(rows)
+        assert rows.ndim == 2 and rows.shape[1] == self.d
+        check(self.lib.ciao_set_table_rows(self.h, int(i0), rows.shape[0], ptr(rows)))
+
+    def solver_restore(self, algo, gamma=0.0, flag=False, gamma_N=None, hat_gamma=0.0):
+        """algo: 1 SVRG, 2 SAGA, 3 Finito, 4 LFinito, 5 ProShI — state without the init pass; then set_vec / set_table_rows."""
+        g = None if gamma_N is None else f64arr(gamma_N)
+        check(self.lib.ciao_solver_restore(self.h, int(algo), float(gamma), int(flag), ptr(g), float(hat_gamma)))
+
     def table_colsum(self):
         o = np.empty(self.d)
         check(self.lib.ciao_table_colsum(self.h, ptr(o)))

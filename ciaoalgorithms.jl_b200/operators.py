@@ -77,11 +77,17 @@ class UnsupportedOperator(TypeError):
     pass
 
 
-def pack_F(F, N):
+def pack_F(F, N, d=None):
     """→ ("rows", loss_kind, A[N,d], b[N], scale[N])  or  ("blocks", Qdiag[N,n], qlin[N,n], (lo,hi), eta)."""
     if len(F) != N:
         raise ValueError(f"F has {len(F)} components, N = {N}")
     f0 = F[0]
+    if all(isinstance(f, Zero) for f in F):
+        # F === nothing → fill(Zero(), N) (SVRG.jl:58, SAGA.jl:55, Finito.jl:78): ∇f_i ≡ 0, f_i ≡ 0.  Least-squares rows with
+        # a_i = 0, b_i = 0, λ_i = 0 give exactly that (every product is +0), so no extra loss kind is needed.
+        if d is None:
+            raise UnsupportedOperator("all-Zero F needs the dimension of x0")
+        return ("rows", L.LOSS_LS, np.zeros((N, d)), np.zeros(N), np.zeros(N))
     if isinstance(f0, LeastSquares):
         d = np.asarray(f0.A).reshape(1, -1).shape[1]
         A, b, s = np.empty((N, d)), np.empty(N), np.empty(N)

@@ -56,12 +56,12 @@ def _element_type(x0):
 
 def _setup_engine(F, g, N, device=0, x0=None):
     out_dtype = _element_type(x0) if x0 is not None else np.dtype(np.float64)
-    e = _setup_engine_fp64(F, g, N, device)
+    e = _setup_engine_fp64(F, g, N, device, None if x0 is None else int(np.size(x0)))
     e.out_dtype = out_dtype
     return e
 
 
-def _setup_engine_fp64(F, g, N, device=0):
+def _setup_engine_fp64(F, g, N, device=0, d=None):
     if N is None:
         raise TypeError("keyword argument N is required (SVRG.jl:52 `N = N`)")
     if isinstance(F, DeviceProblem):
@@ -70,8 +70,8 @@ def _setup_engine_fp64(F, g, N, device=0):
             raise ValueError(f"DeviceProblem holds N = {e.N}, got N = {N}")
     else:
         if F is None:
-            raise ops.UnsupportedOperator("F = nothing (all-Zero f_i) is outside the engine's scope")
-        packed = ops.pack_F(list(F), N)
+            F = [ops.Zero()] * N          # F === nothing && (F = fill(ProximalOperators.Zero(), (N,)))   SVRG.jl:58
+        packed = ops.pack_F(list(F), N, d)
         e = Engine(device)
         if packed[0] == "rows":
             e.set_rows(packed[1], packed[2], packed[3], packed[4])

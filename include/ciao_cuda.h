@@ -177,6 +177,11 @@ int ciao_proshi_solution(ciao_ctx *ctx, double *S_out_or_null);
 int ciao_get_vec(ciao_ctx *ctx, int which, double *out, int64_t len);
 int ciao_set_vec(ciao_ctx *ctx, int which, const double *in, int64_t len);
 int ciao_get_table_rows(ciao_ctx *ctx, int64_t i0, int64_t n, double *out);   /* rows [i0, i0+n) of s, 0-based */
+int ciao_set_table_rows(ciao_ctx *ctx, int64_t i0, int64_t n, const double *in); /* restore rows [i0, i0+n) of s        */
+/* Restore from a checkpoint: re-creates a solver's device state without its init pass (SAGA_basic.jl:11-20 — the state
+ * struct IS the checkpoint): algo 1 SVRG (gamma, flag = plus) | 2 SAGA (gamma, flag = SAG) | 3 Finito | 4 LFinito | 5 ProShI
+ * (gamma_N, hat_gamma); then ciao_set_vec (z, z_full, w, av) and ciao_set_table_rows put the state back. */
+int ciao_solver_restore(ciao_ctx *ctx, int algo, double gamma, int flag, const double *gamma_N, double hat_gamma);
 int ciao_table_colsum(ciao_ctx *ctx, double *out);                             /* Σ_i s_i (sum(x_proshi), test_sharing.jl:42) */
 
 /* ---- measurement ----------------------------------------------------------- */

@@ -1,8 +1,9 @@
 """Stress of the table read-after-write paths (SAGA_basic.jl:65, Finito_basic.jl:116, ProShI_basic.jl:119).
 
-Table rows are written by the compute threads (generic proxy) and prefetched D steps ahead by TMA copies (async proxy).
-A repeat closer than CIAO_HAZARD_WINDOW = 20 steps carries a HAZARD flag and is re-read by the thread that wrote it; a repeat
-further away is ordered by fence.proxy.async + an mbarrier release/acquire chain (seq_impl.cuh, proshi.cu).  These tests put
+Table rows are written by the compute threads (st.global) and prefetched D steps ahead into a shared-memory ring by cp.async
+copies of the producer warp (both generic proxy).  A repeat closer than CIAO_HAZARD_WINDOW = 20 steps carries a HAZARD flag and
+is re-read by the thread that wrote it; a repeat further away is ordered by an mbarrier release/acquire chain at CTA scope
+(seq_impl.cuh, proshi.cu).  These tests put
 ≥ 10^6 steps on tiny problems (N = 24, 40, 64), with every repeat distance around the window edges — 19, 20, 21 (window − 1,
 window, window + 1), 9, 10 (SAGA/Finito ring + 1, + 2), 17, 18 (ProShI ring) — and require
   * SAGA / Finito: the TMA-ring path BITWISE equal to the register-prefetch path (CIAO_SEQ_TABLE_LDG=1), which never touches
@@ -97,11 +98,16 @@ def test_proshi_long_run_bitwise_equals_oracle(N, n):
     p = orc.Problem(orc.LOSS_DIAGQUAD, Q, np.ones((N, n)), box=(-2.0, 2.0), eta=eta).set_reg(orc.REG_INDBOX, lo=-np.inf, hi=np.ones(n))
     gam = 0.999 * N / (np.abs(Q).max(axis=1) + eta)
     ref = orc.ProshiState(p, np.zeros(n), gam)
-    ref.steps(idx, ptr)
     with Engine(0) as e:
         e.gen_synthetic(L.SYNTH_SHARING, N, n, 0x5EED0005)
         e.set_reg(L.REG_INDBOX, -np.inf, np.ones(n))
         e.proshi_init(np.zeros(n), gam, ref.hat_gamma)
+        # the init sums Σ s_i in different orders (Julia: left to right; device: per CTA, then slices) — a 1-ulp difference in
+        # av would never wash out, so the run starts from the oracle's av; everything after is elementwise and must be exact
+        av0 = e.get_vec(L.VEC_AV)
+        assert np.abs(av0 - ref.av).max() <= 4e-16 * np.abs(ref.av).max() and np.array_equal(e.get_vec(L.VEC_Z), ref.z)
+        e.set_vec(L.VEC_AV, ref.av)
+        ref.steps(idx, ptr)
         e.proshi_steps(idx, ptr)
         assert np.array_equal(e.get_table_rows(), ref.s)
         assert np.array_equal(e.get_vec(L.VEC_Z), ref.z)

@@ -625,6 +625,26 @@ def test_full_scale_properties():
         assert np.array_equal(outs[0], outs[1])
 
 
+def test_full_scale_gradient_against_threaded_cpu_pass():
+    """SURVEY.md §8d parity protocol at BASELINE.json's full size: the N = 2^22 × 4096 full-gradient pass (137.6 GB of row
+    records) against a CPU pass over the same rows, regenerated on the fly on all host cores with long-double accumulation
+    (oracle.full_gradient_synth; the matrix does not fit host memory).  SVRG_basic.jl:58-63, 88-92."""
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 150e9:
+        pytest.skip("needs a 180 GB B200")
+    N, d, seed = 1 << 22, 4096, 0x5EED0003
+    x = np.random.default_rng(7).standard_normal(d) * 1e-3
+    with Engine(0) as e:
+        e.gen_synthetic(L.SYNTH_LASSO, N, d, seed, scale=float(N))
+        g_dev = e.full_gradient(x, 1.0 / N)
+        f_dev = e.objective(x)[0]
+    g_cpu, f_sum = orc.full_gradient_synth(orc.SYN_LASSO, N, d, seed, float(N), x, 1.0 / N)
+    assert rel(g_dev, g_cpu) <= 1e-12
+    assert np.abs(g_dev - g_cpu).max() <= 1e-11 * np.abs(g_cpu).max()
+    assert abs(f_dev - f_sum / N) <= 1e-12 * abs(f_sum / N)
+
+
 def test_full_scale_table_invariants_c2_c5():
     """BASELINE configs 2 and 5 at full size (N = 2^20 × 1024 logistic; 2^18 blocks × 1024): the running averages the
     sequential kernels keep in registers must equal what the N×d tables hold in HBM — size-independent invariants of
@@ -764,3 +784,132 @@ def test_large_d_sequential_kernels():
     e.finito_steps(idx[:2 * N], np.arange(2 * N + 1, dtype=np.int64))
     assert rel(e.get_vec(L.VEC_Z), reff.z) < 1e-9 and rel(e.get_table_rows(), reff.s) < 1e-9
     e.close()
+
+
+# ----------------------------------------------------------------------------
+# "the iterator state is the checkpoint" (SAGA_basic.jl:11-20): read the state out, put it back into a fresh context,
+# continue — bit for bit the uninterrupted run for the table solvers
+@pytest.mark.parametrize("alg", ["saga", "finito", "proshi"])
+def test_checkpoint_restore_continues_bitwise(alg):
+    N, d = 300, 256
+    rng = HostRNG(21)
+    if alg == "proshi":
+        def fresh():
+            e = Engine(0)
+            e.gen_synthetic(L.SYNTH_SHARING, N, d, 0x5EED0005)
+            e.set_reg(L.REG_INDBOX, -np.inf, np.ones(d))
+            return e
+        gam = 0.999 * N / np.full(N, 10.0 + 10.0 * N)
+        hat = float(np.sum(gam))
+        x0 = np.zeros(d)
+    else:
+        def fresh():
+            e = Engine(0)
+            e.gen_synthetic(L.SYNTH_LASSO, N, d, 0xC0FFEE, scale=float(N))
+            e.set_reg(L.REG_NORML1, 0.05)
+            return e
+        x0 = np.full(d, 0.1)
+    a = fresh()
+    Lmax = N * a.max_row_sqnorm() if alg != "proshi" else None
+    if alg == "finito":
+        gam = np.linspace(0.6, 1.0, N) * (0.999 * N / Lmax)
+        hat = 1 / np.sum(1 / gam)
+    idx1, idx2 = rng.rand_vec(N, 2 * N), rng.rand_vec(N, 2 * N)
+    bp = np.arange(2 * N + 1, dtype=np.int64)
+
+    def steps(e, idx):
+        if alg == "saga":
+            e.saga_steps(idx)
+        elif alg == "finito":
+            e.finito_steps(idx, bp)
+        else:
+            e.proshi_steps(idx, bp)
+
+    if alg == "saga":
+        a.saga_init(x0, 1 / (3 * Lmax), False)
+    elif alg == "finito":
+        a.finito_init(x0, gam, hat)
+    else:
+        a.proshi_init(x0, gam, hat)
+    steps(a, idx1)
+    ck = {"z": a.get_vec(L.VEC_Z), "av": a.get_vec(L.VEC_AV), "s": a.get_table_rows()}      # the checkpoint
+    steps(a, idx2)
+    b = fresh()
+    if alg == "saga":
+        b.solver_restore(2, gamma=1 / (3 * Lmax))
+    else:
+        b.solver_restore(3 if alg == "finito" else 5, gamma_N=gam, hat_gamma=hat)
+    b.set_vec(L.VEC_Z, ck["z"])
+    b.set_vec(L.VEC_AV, ck["av"])
+    b.set_table_rows(ck["s"][:100])
+    b.set_table_rows(ck["s"][100:], 100)
+    steps(b, idx2)
+    assert np.array_equal(a.get_vec(L.VEC_Z), b.get_vec(L.VEC_Z))
+    assert np.array_equal(a.get_vec(L.VEC_AV), b.get_vec(L.VEC_AV))
+    assert np.array_equal(a.get_table_rows(), b.get_table_rows())
+    a.close()
+    b.close()
+
+
+def test_checkpoint_restore_svrg():
+    N, d = 512, 256
+    def fresh():
+        e = Engine(0)
+        e.gen_synthetic(L.SYNTH_LASSO, N, d, 0xC0FFEE, scale=float(N))
+        e.set_reg(L.REG_NORML1, 0.05)
+        return e
+    a = fresh()
+    gamma = 1 / (7 * N * a.max_row_sqnorm())
+    rng = HostRNG(5)
+    i1, i2 = rng.rand_vec(N, N // 2), rng.rand_vec(N, N)
+    a.svrg_init(np.zeros(d), gamma, True)
+    a.svrg_epoch(i1)
+    ck = {k: a.get_vec(v) for k, v in (("z", L.VEC_Z), ("zf", L.VEC_Z_FULL), ("w", L.VEC_W), ("av", L.VEC_AV))}
+    a.svrg_epoch(i2)
+    b = fresh()
+    b.solver_restore(1, gamma=gamma, flag=True)
+    for k, v in (("z", L.VEC_Z), ("zf", L.VEC_Z_FULL), ("w", L.VEC_W), ("av", L.VEC_AV)):
+        b.set_vec(v, ck[k])
+    b.svrg_epoch(i2)
+    # the restored context recomputes c_i(z_full) inside the inner kernel instead of taking it from the last pass: rounding-level
+    assert rel(b.get_vec(L.VEC_Z_FULL), a.get_vec(L.VEC_Z_FULL)) < 1e-12
+    assert rel(b.get_vec(L.VEC_AV), a.get_vec(L.VEC_AV)) < 1e-10
+    a.close()
+    b.close()
+
+
+def test_objective_indbox_is_infinite_outside_the_box():
+    N, d = 64, 32
+    with Engine(0) as e:
+        e.gen_synthetic(L.SYNTH_LASSO, N, d, 3, scale=float(N))
+        e.set_reg(L.REG_INDBOX, -1.0, 1.0)
+        assert e.objective(np.full(d, 0.5))[1] == 0.0
+        x = np.full(d, 0.5)
+        x[7] = 1.0 + 1e-12
+        assert e.objective(x)[1] == np.inf
+        e.set_reg(L.REG_INDBOX, -np.inf, np.linspace(0.0, 1.0, d))
+        assert e.objective(np.zeros(d))[1] == 0.0 and e.objective(np.full(d, 0.5))[1] == np.inf
+
+
+def test_out_of_range_index_leaves_the_state_untouched():
+    """The reference throws BoundsError at F[i] before any state changes (SAGA_basic.jl:56): an invalid index anywhere in a call
+    means none of the call's steps run; the error surfaces at the next synchronising call and the context stays usable."""
+    N, d = 200, 128
+    with Engine(0) as e:
+        e.gen_synthetic(L.SYNTH_LASSO, N, d, 11, scale=float(N))
+        e.set_reg(L.REG_NORML1, 0.05)
+        Lmax = N * e.max_row_sqnorm()
+        e.saga_init(np.full(d, 0.2), 1 / (3 * Lmax), False)
+        good = HostRNG(1).rand_vec(N, 50)
+        e.saga_steps(good)
+        z, av, s = e.get_vec(L.VEC_Z), e.get_vec(L.VEC_AV), e.get_table_rows()
+        bad = good.copy()
+        bad[30] = N + 1
+        e.saga_steps(bad)
+        with pytest.raises(CiaoError) as ei:
+            e.get_vec(L.VEC_Z)
+        assert ei.value.code == -1
+        assert np.array_equal(e.get_vec(L.VEC_Z), z) and np.array_equal(e.get_vec(L.VEC_AV), av)
+        assert np.array_equal(e.get_table_rows(), s)
+        e.saga_steps(good)                                   # still usable
+        assert not np.array_equal(e.get_vec(L.VEC_Z), z)

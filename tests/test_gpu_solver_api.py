@@ -207,3 +207,18 @@ def test_unsupported_operator_is_rejected_before_any_device_call():
         S.SAGA(gamma=0.1)(fx["x0"], F=[object()] * fx["N"], g=g, N=fx["N"])
     with pytest.raises(ops.UnsupportedOperator):
         S.Finito(adaptive=True)(fx["x0"], F=F, g=object(), L=fx["L"], N=fx["N"])
+
+
+def test_default_F_is_all_zero_components():                                    # SVRG.jl:58, SAGA.jl:55: F === nothing → fill(Zero(), N)
+    x0 = np.array([3.0, -0.2, 0.7, -5.0])
+    soft = lambda v, t: np.sign(v) * np.maximum(np.abs(v) - t, 0.0)              # noqa: E731
+    # SAGA with ∇f_i ≡ 0: z = prox((1−γ)x0, γ) (SAGA_basic.jl:48), then every step is z ← prox_g(z, γ)
+    gam, lam = 0.25, 0.8
+    x, it = S.SAGA(gamma=gam, maxit=4)(x0, F=None, g=ops.NormL1(lam), N=5, rng=HostRNG(1))
+    want = soft((1 - gam) * x0, gam * lam)
+    for _ in range(3):
+        want = soft(want, gam * lam)
+    assert it == 4 and np.allclose(x, want, rtol=0, atol=1e-15)
+    # SVRG with g = Zero as well: nothing moves
+    x, _ = S.SVRG(gamma=0.1, maxit=3, m=7)(x0, F=None, N=5, rng=HostRNG(1))
+    assert np.allclose(x, x0, rtol=1e-15, atol=0)      # z_full = (Σ_m w)/m with w ≡ x0: equal up to the rounding of the mean
