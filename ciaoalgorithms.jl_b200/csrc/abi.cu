@@ -808,9 +808,12 @@ static int batched_indices(ciao_ctx *c, const int64_t *idx, const int64_t *batch
 }
 
 extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t *batch_ptr, int64_t n_batches) {
-    CIAO_TRY(need_rows(c, "ciao_finito_steps", true));
+    CIAO_TRY(need_rows(c, "ciao_finito_steps", false));
     if (c->algo != ALG_FINITO) CIAO_FAIL(CIAO_ERR_STATE, "ciao_finito_steps before ciao_finito_init");
-    CIAO_TRY(need_whole_table(c, "ciao_finito_steps"));
+    // Row shards (one process per GPU): static minibatches shard by row owner — every rank streams its part of a batch, the
+    // batch's Σ is all-reduced in the tail kernel (collective: all ranks make the same call).  Single samples / scattered
+    // batches need the whole table on one GPU.
+    const bool sharded = c->n_rows != c->N_total;
     // static minibatches (contiguous rows, Finito_basic.jl:52-57) of ≥ BATCH_MIN_ROWS rows: one streaming pass per batch
     if (idx && batch_ptr && n_batches > 0 && !is_device_ptr(idx) && !is_device_ptr(batch_ptr)) {
         bool contiguous = true;
@@ -831,7 +834,7 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
                 if (batch_ptr[j + 1] > batch_ptr[j]) win.push_back(batch_ptr[j + 1] - batch_ptr[j]);
             CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
             int rc = CIAO_ERR_UNSUPPORTED;
-            if (c->batch_persistent && nbw > 1 && nbw < ((int64_t)1 << 22)) {   // all batches in one cooperative launch
+            if (!sharded && c->batch_persistent && nbw > 1 && nbw < ((int64_t)1 << 22)) {   // all batches in one cooperative launch
                 const int64_t *win_dev;
                 CIAO_TRY(upload_ptr(c, win.data(), 2 * nbw, &win_dev));
                 rc = run_batch_sequence(c, BATCH_FINITO, win_dev, win_dev + nbw, nbw, longest);
@@ -845,13 +848,14 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
             return CIAO_OK;
         }
     }
+    CIAO_TRY(need_whole_table(c, "ciao_finito_steps (single samples or scattered batches)"));
     int64_t n_idx = 0;
     CIAO_TRY(batched_indices(c, idx, batch_ptr, n_batches, &n_idx));
     return run_seq(c, ALG_FINITO, c->idx_prep, n_idx, 1.0);
 }
 
 extern "C" int ciao_lfinito_init(ciao_ctx *c, const double *x0, const double *gamma_N, double hat_gamma) {
-    CIAO_TRY(need_rows(c, "ciao_lfinito_init", true));
+    CIAO_TRY(need_rows(c, "ciao_lfinito_init", false));   // the init is a pass: it shards like the full gradient
     if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_lfinito_init: null argument or γ̂ ≤ 0");
     c->algo = ALG_LFINITO; c->hat_gamma = hat_gamma;
     c->cz_valid = false;
@@ -865,7 +869,8 @@ extern "C" int ciao_lfinito_init(ciao_ctx *c, const double *x0, const double *ga
 }
 
 extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64_t n_batches, int64_t r) {
-    CIAO_TRY(need_rows(c, "ciao_lfinito_outer", true));
+    // row shards without attached peers: only the minibatch sweep (r ≥ BATCH_MIN_ROWS) shards — by row owner, one exchange per batch
+    CIAO_TRY(need_rows(c, "ciao_lfinito_outer", !(r >= BATCH_MIN_ROWS && c && c->n_rows != c->N_total && c->world > 1)));
     if (c->algo != ALG_LFINITO) CIAO_FAIL(CIAO_ERR_STATE, "ciao_lfinito_outer before ciao_lfinito_init");
     if (!batch_order || r <= 0 || n_batches < 0) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_lfinito_outer: bad arguments");
     const int64_t N = c->N_total, nb = (N + r - 1) / r;
@@ -887,10 +892,11 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
     CIAO_TRY(run_pass_finish(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_Z_FULL), c->cache_cz, ctx_vec(c, CIAO_VEC_Z_FULL),
                              -(c->hat_gamma / (double)N), 1.0, ctx_vec(c, CIAO_VEC_AV)));  // :85-88
     if (total == 0) return CIAO_OK;
-    if (r >= BATCH_MIN_ROWS && c->n_rows == c->N_total) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
+    const bool sharded = c->n_rows != c->N_total;
+    if (r >= BATCH_MIN_ROWS && (!sharded || c->world > 1)) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
         CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
         int rc = CIAO_ERR_UNSUPPORTED;
-        if (c->batch_persistent && n_batches > 1 && n_batches < ((int64_t)1 << 22)) {  // the whole sweep in one cooperative launch
+        if (!sharded && c->batch_persistent && n_batches > 1 && n_batches < ((int64_t)1 << 22)) {  // the whole sweep in one cooperative launch
             std::vector<int64_t> win((size_t)2 * n_batches);
             for (int64_t jj = 0; jj < n_batches; ++jj) {
                 win[jj] = r * (order[jj] - 1);
@@ -903,10 +909,10 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
             if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
         }
         if (rc == CIAO_ERR_UNSUPPORTED)
-            for (int64_t jj = 0; jj < n_batches; ++jj) {
+            for (int64_t jj = 0; jj < n_batches; ++jj) {   // z = prox_g(av) (:92) of batch jj + 1 is formed by the tail kernel of batch jj
                 const int64_t j = order[jj];
-                CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));      // :92
-                CIAO_TRY(run_batch_step(c, BATCH_LFINITO, r * (j - 1), (j == nb) ? last_len : r));
+                if (jj == 0) CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));
+                CIAO_TRY(run_batch_step(c, BATCH_LFINITO, r * (j - 1), (j == nb) ? last_len : r, jj + 1 == n_batches));
             }
         CUDA_TRY(cudaEventRecord(c->ev_sb, c->stream));
         c->timing.last_seq_steps = total;

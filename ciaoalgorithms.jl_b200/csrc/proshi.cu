@@ -40,9 +40,9 @@ __device__ __forceinline__ double proshi_grad(double q, double c, double s, doub
 
 // Batch-1 steps: a true dependency chain per column (z_j → s_ij → av_j → z_j), so the kernel is latency/issue bound and
 // everything that is not on that chain has to stay off the compute warp.  A CTA owns 32·CPT columns: ONE compute warp keeps
-// z_j, av_j of its columns in registers for the whole call; TWO producer warps (even and odd steps) stage the column slices
-// of (q_i, c_i) and the pair (γ_i, γ_i/N) by TMA, the table slice s_i by cp.async and the index word of the block needed
-// PROSHI_D steps later into a full/empty mbarrier ring.  No reduction, no CTA barrier, no kernel launch per step.
+// z_j, av_j of its columns in registers for the whole call; TWO producer lanes (warps 1 and 2, even and odd steps) stage the
+// column slices of (q_i, c_i), the pair (γ_i, γ_i/N) and the index word by TMA, a table producer warp the slice of s_i by
+// cp.async, all for the block needed PROSHI_D steps later, into a full/empty mbarrier ring.  No reduction, no CTA barrier, no kernel launch per step.
 // History: register prefetch with ld.global ran at 0.74 µs/block (ptxas tracks all those loads with one scoreboard, so the
 // first use of step k's registers also waited for the load just issued for step k+D: one DRAM latency per step); per-thread
 // cp.async groups at 0.30 µs/block (≈ 190 instructions per step on the one warp that also walks the chain); with the staging
@@ -57,7 +57,7 @@ static_assert((PROSHI_D & (PROSHI_D - 1)) == 0 && PROSHI_D + 2 <= CIAO_HAZARD_WI
 constexpr int PROSHI_PRODUCERS = PROSHI_NP;  // producer lanes (one warp each), step st is staged by producer st mod NP
 
 template <int CPT, int REG>
-__global__ void __launch_bounds__(32 * (1 + PROSHI_PRODUCERS)) proshi_steps_kernel(const ProshiArgs p) {
+__global__ void __launch_bounds__(32 * (2 + PROSHI_PRODUCERS)) proshi_steps_kernel(const ProshiArgs p) {
     if (*reinterpret_cast<const volatile int *>(p.err) != 0) return;   // ProShI_basic.jl:113 would throw BoundsError first
     constexpr int D = PROSHI_D;
     constexpr int COLS = 32 * CPT;                 // columns per CTA
@@ -79,35 +79,46 @@ __global__ void __launch_bounds__(32 * (1 + PROSHI_PRODUCERS)) proshi_steps_kern
     fence_proxy_async();
     __syncthreads();
 
-    if (warp >= 1) {
-        // ===================== producer warps: warp 1 stages the even steps, warp 2 the odd ones =====================
-        // Lane 0 waits for the slot, arms the barrier and issues the bulk copies of the read-only slices (q_i, c_i, γ pair);
-        // the TABLE slice — written inside this kernel by the compute warp — is copied by the lanes of the producer warp with
-        // cp.async (generic proxy, like the stores; see seq_impl.cuh): the compute warp's st.global of step k is ordered before
-        // it by the warp barrier + release arrive on empty_bar in take(), this warp's acquire wait on that barrier and its own
-        // warp barrier.  Every repeat at distance ≥ PROSHI_D + 1 is ordered that way, closer ones carry the HAZARD flag.
-        const int Ki = (int)K;
-        const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
-        const uint32_t bytes = (uint32_t)ncol * 8;
-        const uint32_t tx = 2 * bytes + 16;
-        const uint32_t n_chunks = (uint32_t)ncol / 2;   // 16-byte chunks of the table slice (≤ 32)
-        for (int st = warp - 1; st < Ki; st += PROSHI_PRODUCERS) {
-            const uint32_t slot = (uint32_t)st & (D - 1);
-            const int64_t pidx = __ldg(p.idx + st);
-            const int64_t i = pidx & CIAO_IDX_MASK;
-            const int64_t off = i * p.n_pad + col0;
-            const uint32_t dst = ring_s + slot * (SLOT * 8), bar = full_s + slot * 8;
-            if (lane == 0) {
+    if (warp >= 1 && warp <= PROSHI_PRODUCERS) {
+        // ===================== producer lanes: warp 1 stages the even steps, warp 2 the odd ones =====================
+        // bulk copies (TMA) of the read-only slices q_i, c_i and of the pair (γ_i, γ_i/N), and the index word
+        if (lane == 0) {
+            const int Ki = (int)K;
+            const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
+            const uint32_t bytes = (uint32_t)ncol * 8;
+            const uint32_t tx = 2 * bytes + 16;
+            for (int st = warp - 1; st < Ki; st += PROSHI_PRODUCERS) {
+                const uint32_t slot = (uint32_t)st & (D - 1);
                 if (st >= D) mbar_wait_s(empty_s + slot * 8, (((uint32_t)st / D) - 1u) & 1u);  // step st − D has left the slot
+                const int64_t pidx = __ldg(p.idx + st);
+                const int64_t i = pidx & CIAO_IDX_MASK;
+                const int64_t off = i * p.n_pad + col0;
+                const uint32_t dst = ring_s + slot * (SLOT * 8), bar = full_s + slot * 8;
                 sts_b64(dst + (3 * COLS + 2) * 8, pidx);  // released by the arrive below
                 mbar_arrive_expect_tx_s(bar, tx);
                 tma_load_1d_s(dst, p.qd + off, bytes, bar);
                 tma_load_1d_s(dst + COLS * 8, p.ql + off, bytes, bar);
                 tma_load_1d_s(dst + 3 * COLS * 8, p.gpair + 2 * i, 16, bar);
             }
-            __syncwarp();
-            if ((uint32_t)lane < n_chunks) cp_async_16(dst + 2 * COLS * 8 + lane * 16, p.table + off + 2 * lane);
-            cp_async_arrive_noinc(bar);
+        }
+        return;
+    }
+    if (warp == PROSHI_PRODUCERS + 1) {
+        // ===================== table producer warp =====================
+        // The TABLE slice is written inside this kernel by the compute warp, so it is staged through the same (generic) proxy:
+        // 16-byte cp.async copies by the lanes of this warp (see seq_impl.cuh for why not TMA).  The compute warp's st.global of
+        // step k is ordered before them by its warp barrier + release arrive on empty_bar in take() and by the acquire wait of
+        // every lane here.  Every repeat at distance ≥ PROSHI_D + 1 is ordered that way, closer ones carry the HAZARD flag.
+        const int Ki = (int)K;
+        const uint32_t ring_s = smem_u32(ring), full_s = smem_u32(full_bar), empty_s = smem_u32(empty_bar);
+        const uint32_t n_chunks = (uint32_t)ncol / 2;   // 16-byte chunks of the table slice (≤ 32)
+        for (int st = 0; st < Ki; ++st) {
+            const uint32_t slot = (uint32_t)st & (D - 1);
+            if (st >= D) mbar_wait_s(empty_s + slot * 8, (((uint32_t)st / D) - 1u) & 1u);
+            const int64_t i = __ldg(p.idx + st) & CIAO_IDX_MASK;
+            if ((uint32_t)lane < n_chunks)
+                cp_async_16(ring_s + slot * (SLOT * 8) + 2 * COLS * 8 + lane * 16, p.table + i * p.n_pad + col0 + 2 * lane);
+            cp_async_arrive_noinc(full_s + slot * 8);
         }
         return;
     }
@@ -461,16 +472,16 @@ int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, const 
         const int grid = (int)(one ? nc1 : (c->d_pad + 63) / 64);
         switch (c->reg.kind) {
             case CIAO_REG_NORML1:
-                if (one) proshi_steps_kernel<1, CIAO_REG_NORML1><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
-                else proshi_steps_kernel<2, CIAO_REG_NORML1><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                if (one) proshi_steps_kernel<1, CIAO_REG_NORML1><<<grid, 32 * (2 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                else proshi_steps_kernel<2, CIAO_REG_NORML1><<<grid, 32 * (2 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
                 break;
             case CIAO_REG_INDBOX:
-                if (one) proshi_steps_kernel<1, CIAO_REG_INDBOX><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
-                else proshi_steps_kernel<2, CIAO_REG_INDBOX><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                if (one) proshi_steps_kernel<1, CIAO_REG_INDBOX><<<grid, 32 * (2 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                else proshi_steps_kernel<2, CIAO_REG_INDBOX><<<grid, 32 * (2 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
                 break;
             default:
-                if (one) proshi_steps_kernel<1, CIAO_REG_ZERO><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
-                else proshi_steps_kernel<2, CIAO_REG_ZERO><<<grid, 32 * (1 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                if (one) proshi_steps_kernel<1, CIAO_REG_ZERO><<<grid, 32 * (2 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
+                else proshi_steps_kernel<2, CIAO_REG_ZERO><<<grid, 32 * (2 + PROSHI_PRODUCERS), 0, c->stream>>>(a);
         }
     }
     CUDA_TRY(cudaGetLastError());

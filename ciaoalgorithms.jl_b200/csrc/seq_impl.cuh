@@ -72,13 +72,12 @@ static_assert(SEQ_D + 1 <= CIAO_HAZARD_WINDOW - 1, "prep_indices_kernel must fla
 // async proxy, and ordering a generic-proxy write before it needs fence.proxy.async in the WRITING thread, which waits for the
 // thread's stores to reach L2: measured +0.34 µs per step, twice the step (profiles/seq_variants_r2.log).  With one proxy the
 // ordering is ordinary release/acquire at CTA scope: st.global → warp barrier → mbarrier.arrive (release) on the "written"
-// barrier of step k → the producer warp's try_wait (acquire) on it before it issues the copies of step k + 1 + D.  Repeats at
-// distance ≥ D + 1 are ordered that way, repeats at distance ≤ CIAO_HAZARD_WINDOW − 1 carry the HAZARD flag and are re-read by
-// the thread that wrote them: no gap and no timing assumption.  (The rows a_i, their tails and the pass-written scalars are
-// never written inside the kernel and stay on TMA.)   CIAO_TABLE_ORDERED=0 drops the barrier (measurement only).
-#ifndef CIAO_TABLE_ORDERED
-#define CIAO_TABLE_ORDERED 1
-#endif
+// barrier of step k → the try_wait (acquire) of every lane of the TABLE PRODUCER warp on it before the lane issues its copies
+// for step k + D.  Repeats at distance ≥ D are ordered that way, repeats at distance ≤ CIAO_HAZARD_WINDOW − 1 carry the HAZARD
+// flag and are re-read by the thread that wrote them: no gap and no timing assumption.  The table producer is a second
+// producer warp: folded into the lane that drives the TMA ring and re-arms the exchange barrier, the copies made that lane's
+// iteration (831 cycles) longer than a step and it became the bottleneck (profiles/prof_seq_table_r2.log).  The rows a_i,
+// their tails and the pass-written scalars are never written inside the kernel and stay on TMA.
 static_assert(SEQ_D + 1 <= CIAO_HAZARD_WINDOW - 1, "every repeat closer than the ordered distance D + 1 must carry the HAZARD flag");
 constexpr int SEQ_MAX_PART = 128;  // C·W ≤ 128
 constexpr int SEQ_SLOT_EXTRA = 12;  // staged scalars [0,10) + index word [10] + pad (slots stay 16-byte aligned)
@@ -94,7 +93,7 @@ __device__ __forceinline__ void tma_prefetch_l2(const void *gsrc, uint32_t bytes
 // CZ: c_i(z_full) is read from the record tail (written by the last full-gradient pass at z_full)
 // instead of being recomputed from a second dot product a_i·z_full.
 template <int CPT, int ALG, int LOSS, int REG, bool CZ>
-__global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
+__global__ void __launch_bounds__(320, 1) seq_kernel(const SeqArgs p) {
     constexpr bool TABLE = (ALG == ALG_SAGA || ALG == ALG_FINITO);
     constexpr bool USES_ZFULL = (ALG == ALG_SVRG || ALG == ALG_LFINITO);
     constexpr bool TWO_DOTS = USES_ZFULL && !CZ;
@@ -105,12 +104,12 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
     // BoundsError before any state changes (SAGA_basic.jl:56).  Uniform over the cluster, so nobody is left at a barrier.
     if (*reinterpret_cast<const volatile int *>(p.err) != 0) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int Tc = blockDim.x - 32;  // compute threads; the last warp is the producer
+    const bool TT = TABLE && p.table_tma;             // table row slices are staged in the ring slots, behind the record tail
+    const int Tc = blockDim.x - (TT ? 64 : 32);       // compute threads; then the producer warp and (TT) the table producer warp
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = Tc >> 5;
     const uint32_t rank = cluster_ctarank(), C = cluster_nctarank();
     const int64_t dc = p.dc;
     const int cover = Tc * CPT;                       // columns covered by the thread grid (≥ dc)
-    const bool TT = TABLE && p.table_tma;             // table row slices are staged in the ring slots, behind the record tail
     const size_t slot_doubles = (size_t)cover + SEQ_SLOT_EXTRA + (TT ? cover : 0);
     double *ring = reinterpret_cast<double *>(smem_raw);
     double *part = ring + D * slot_doubles;           // [2][npart_pad][2]
@@ -145,9 +144,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
         // and byte counts computed once, no shard search when all rows are local, two bulk copies per step for the
         // table-free algorithms.  (Profile: a 64-bit/three-copy version took ≈ 650 cycles per iteration and was the
         // bottleneck of every variant whose compute path is shorter than that.)
-        // With a staged table (TT) all 32 lanes walk the loop: lane 0 does the waits, the arming and the bulk copies, then
-        // every lane copies 16-byte chunks of the table row slice with cp.async.
-        if (lane == 0 || TT) {
+        if (lane == 0) {
             const int Ki = (int)K;  // run_seq_alg guarantees K < 2^31
             const uint32_t ring_s = smem_u32(ring), row_bar_s = smem_u32(row_bar), part_bar_s = smem_u32(part_bar);
             const uint32_t slot_bytes = (uint32_t)(slot_doubles * 8);
@@ -155,10 +152,8 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             constexpr bool SS_ONLY = CZ && ALG == ALG_SVRG;     // the pass-written scalars replace the record tail
             constexpr bool SS_EXTRA = CZ && ALG == ALG_LFINITO;  // … or come next to it
             const uint32_t tail_off = (uint32_t)cover * 8, idx_off = (uint32_t)(cover + SEQ_IDX_POS) * 8;
-            const uint32_t table_off = (uint32_t)(cover + SEQ_SLOT_EXTRA) * 8;
             const uint32_t tail_bytes = (uint32_t)(CIAO_TAIL_USED * 8);
             const uint32_t tx_bytes = row_bytes + (SS_ONLY ? 32u : tail_bytes + (SS_EXTRA ? 32u : 0u));
-            const uint32_t n_chunks = (uint32_t)(dc / 2);        // 16-byte chunks of a table row slice
             const bool one_shard = p.rows.n <= 1;
             const double *base0 = p.rows.base[0] + cbase;
             const double *table0 = TABLE ? p.table + cbase : nullptr;
@@ -167,35 +162,25 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 const int64_t i = pidx & CIAO_IDX_MASK;
                 const uint32_t slot = (uint32_t)step & (D - 1);
                 const uint32_t dst = ring_s + slot * slot_bytes, bar = row_bar_s + slot * 8;
-                if (lane == 0) {
-                    const double *src;
-                    if (one_shard) {
-                        src = base0 + i * ld;
-                    } else {  // shard holding row i (≤ 8 shards: linear search)
-                        int sh = 0;
-                        while (sh + 1 < p.rows.n && i >= p.rows.start[sh + 1]) ++sh;
-                        src = p.rows.base[sh] + (i - p.rows.start[sh]) * ld + cbase;
-                    }
-                    sts_b64(dst + idx_off, pidx);  // released by the arrive below
-                    mbar_arrive_expect_tx_s(bar, tx_bytes);
-                    tma_load_1d_s(dst, src, row_bytes, bar);
-                    // the step's scalars: the record tail and/or {b_i, λ_i, 0, c_i(z_full)} from the dense array of the last pass
-                    if (!SS_ONLY) tma_load_1d_s(dst + tail_off, src + (d_pad - cbase), tail_bytes, bar);
-                    if (SS_ONLY) tma_load_1d_s(dst + tail_off, p.ss + 4 * i, 32, bar);
-                    if (SS_EXTRA) tma_load_1d_s(dst + tail_off + CIAO_TAIL_USED * 8, p.ss + 4 * i, 32, bar);
-                    if (TABLE && !TT) tma_prefetch_l2(table0 + i * d_pad, row_bytes);
+                const double *src;
+                if (one_shard) {
+                    src = base0 + i * ld;
+                } else {  // shard holding row i (≤ 8 shards: linear search)
+                    int sh = 0;
+                    while (sh + 1 < p.rows.n && i >= p.rows.start[sh + 1]) ++sh;
+                    src = p.rows.base[sh] + (i - p.rows.start[sh]) * ld + cbase;
                 }
-                if (TT) {
-                    __syncwarp();  // lane 0's acquire of the "written" barrier is ordered before every lane's copies
-                    const double *trow = table0 + i * d_pad;
-                    for (uint32_t ch = lane; ch < n_chunks; ch += 32) cp_async_16(dst + table_off + ch * 16, trow + 2 * ch);
-                    cp_async_arrive_noinc(bar);
-                }
+                sts_b64(dst + idx_off, pidx);  // released by the arrive below
+                mbar_arrive_expect_tx_s(bar, tx_bytes);
+                tma_load_1d_s(dst, src, row_bytes, bar);
+                // the step's scalars: the record tail and/or {b_i, λ_i, 0, c_i(z_full)} from the dense array of the last pass
+                if (!SS_ONLY) tma_load_1d_s(dst + tail_off, src + (d_pad - cbase), tail_bytes, bar);
+                if (SS_ONLY) tma_load_1d_s(dst + tail_off, p.ss + 4 * i, 32, bar);
+                if (SS_EXTRA) tma_load_1d_s(dst + tail_off + CIAO_TAIL_USED * 8, p.ss + 4 * i, 32, bar);
+                if (TABLE && !TT) tma_prefetch_l2(table0 + i * d_pad, row_bytes);
             };
-            if (lane == 0) {
-                if (Ki > 0) mbar_arrive_expect_tx_s(part_bar_s, part_bytes);
-                if (Ki > 1) mbar_arrive_expect_tx_s(part_bar_s + 8, part_bytes);
-            }
+            if (Ki > 0) mbar_arrive_expect_tx_s(part_bar_s, part_bytes);
+            if (Ki > 1) mbar_arrive_expect_tx_s(part_bar_s + 8, part_bytes);
             for (int st = 0; st < D && st < Ki; ++st) issue_row(st, __ldg(p.idx + st));
             int64_t n1 = (D < Ki) ? __ldg(p.idx + D) : 0, n2 = (D + 1 < Ki) ? __ldg(p.idx + D + 1) : 0;
             const int64_t *idx_ahead = p.idx + D + 2;
@@ -203,32 +188,51 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
             long long prod_busy = 0;
 #endif
             for (int k = 0; k < Ki; ++k) {
+                const uint32_t pb = part_bar_s + ((uint32_t)k & 1u) * 8;
+                // phase k complete ⇒ every warp of the cluster has consumed row k and sent its partial
+                mbar_wait_s(pb, ((uint32_t)k >> 1) & 1u);
 #ifdef CIAO_SEQ_PROFILE
-                long long pw = 0;
+                const long long pw = clock64();
 #endif
-                if (lane == 0) {
-                    const uint32_t pb = part_bar_s + ((uint32_t)k & 1u) * 8;
-                    // phase k complete ⇒ every warp of the cluster has consumed row k and sent its partial
-                    mbar_wait_s(pb, ((uint32_t)k >> 1) & 1u);
-#ifdef CIAO_SEQ_PROFILE
-                    pw = clock64();
-#endif
-                    if (k + 2 < Ki) mbar_arrive_expect_tx_s(pb, part_bytes);  // arm the exchange of step k+2
-                    // the table writes of steps ≤ k − 1 (every warp has sent partial k, hence finished step k − 1: this wait
-                    // never spins) are acquired before the copies of step k + D read the table
-                    if (TT && CIAO_TABLE_ORDERED && k >= 1)
-                        mbar_wait_s(smem_u32(wr_bar) + (((uint32_t)k - 1u) & (D - 1)) * 8, (((uint32_t)k - 1u) / D) & 1u);
-                }
+                if (k + 2 < Ki) mbar_arrive_expect_tx_s(pb, part_bytes);  // arm the exchange of step k+2
                 if (k + D < Ki) issue_row(k + D, n1);
                 n1 = n2;
                 n2 = (k + D + 2 < Ki) ? __ldg(idx_ahead + k) : 0;
 #ifdef CIAO_SEQ_PROFILE
-                if (lane == 0) prod_busy += clock64() - pw;
+                prod_busy += clock64() - pw;
 #endif
             }
 #ifdef CIAO_SEQ_PROFILE
-            if (lane == 0) g_seq_prof[rank * 8 + 5] = prod_busy;  // producer: cycles from wake-up to the end of its iteration
+            g_seq_prof[rank * 8 + 5] = prod_busy;  // producer: cycles from wake-up to the end of its iteration
 #endif
+        }
+    } else if (warp == W + 1) {
+        // ===================== table producer warp (TT kernels only) =====================
+        // Every lane copies 16-byte chunks of the table row slice of step k + D with cp.async (generic proxy) once the
+        // "written" barrier of step k is complete: every compute warp has then finished step k, i.e. consumed the slot's
+        // previous contents (row k) and released its table writes of steps ≤ k.
+        const int Ki = (int)K;
+        const uint32_t ring_s = smem_u32(ring), row_bar_s = smem_u32(row_bar), wr_bar_s = smem_u32(wr_bar);
+        const uint32_t slot_bytes = (uint32_t)(slot_doubles * 8);
+        const uint32_t table_off = (uint32_t)(cover + SEQ_SLOT_EXTRA) * 8;
+        const uint32_t n_chunks = (uint32_t)(dc / 2);
+        const double *table0 = p.table + cbase;
+        const int64_t d_pad = p.d_pad;
+        auto issue_table = [&](int step, int64_t pidx) {
+            const uint32_t slot = (uint32_t)step & (D - 1);
+            const uint32_t dst = ring_s + slot * slot_bytes + table_off, bar = row_bar_s + slot * 8;
+            const double *trow = table0 + (pidx & CIAO_IDX_MASK) * d_pad;
+            for (uint32_t ch = lane; ch < n_chunks; ch += 32) cp_async_16(dst + ch * 16, trow + 2 * ch);
+            cp_async_arrive_noinc(bar);
+        };
+        for (int st = 0; st < D && st < Ki; ++st) issue_table(st, __ldg(p.idx + st));
+        int64_t n1 = (D < Ki) ? __ldg(p.idx + D) : 0, n2 = (D + 1 < Ki) ? __ldg(p.idx + D + 1) : 0;
+        const int64_t *idx_ahead = p.idx + D + 2;
+        for (int k = 0; k + D < Ki; ++k) {
+            mbar_wait_s(wr_bar_s + ((uint32_t)k & (D - 1)) * 8, ((uint32_t)k / D) & 1u);   // acquire, every lane
+            issue_table(k + D, n1);
+            n1 = n2;
+            n2 = (k + D + 2 < Ki) ? __ldg(idx_ahead + k) : 0;
         }
     } else {
         // ===================== compute warps =====================
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(288, 1) seq_kernel(const SeqArgs p) {
                 for (int h = 0; h < H; ++h)
                     if (valid[h])
                         __stcg(reinterpret_cast<double2 *>(trow + gcol[h]), make_double2(snew[2 * h], snew[2 * h + 1]));
-                if (TT && CIAO_TABLE_ORDERED) {   // release: this warp's table writes of step k are visible to whoever acquires wr_bar
+                if (TT) {   // release: this warp's table writes of step k are visible to whoever acquires wr_bar
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&wr_bar[k & (D - 1)]);
                 }
@@ -538,7 +542,7 @@ static int launch_seq(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(sh.C);
-    cfg.blockDim = dim3(sh.Tc + 32);
+    cfg.blockDim = dim3(sh.Tc + (a.table_tma ? 64 : 32));   // + producer warp (+ table producer warp)
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
     cudaLaunchAttribute at[1];

@@ -47,9 +47,19 @@ mutable struct Ctx
 end
 
 # ---- F / g recognition (replaces dynamic dispatch on F::Array{Tf}, SVRG_basic.jl:2) --------------
-function set_problem!(c::Ctx, F::AbstractVector, g, N::Int)
+function set_problem!(c::Ctx, F, g, N::Int, x0 = nothing)
+    F === nothing && (F = fill(ProximalOperators.Zero(), (N,)))   # SVRG.jl:58, SAGA.jl:55, Finito.jl:78, ProShI.jl:54
+    eltype(x0 === nothing ? Float64[] : x0) <: Complex && error("complex element types are outside the engine's scope")
     f1 = F[1]
-    if f1 isa ProximalOperators.LeastSquares            # test_lasso.jl:53-54: LeastSquares(A[i:i,:], b[i:i], N)
+    if all(f -> f isa ProximalOperators.Zero, F)         # ∇f_i ≡ 0: least-squares rows with a_i = 0, b_i = 0, λ_i = 0
+        x0 === nothing && error("an all-Zero F needs x0 for the dimension")
+        d = length(x0)
+        A = zeros(Float64, d, N); b = zeros(Float64, N); s = zeros(Float64, N)
+        GC.@preserve A b s check(ccall((:ciao_set_rows, libciao), Cint,
+            (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Float64),
+            c.h, 0, N, 0, N, d, A, d, b, s, 0.0))
+        c.N, c.d = N, d
+    elseif f1 isa ProximalOperators.LeastSquares            # test_lasso.jl:53-54: LeastSquares(A[i:i,:], b[i:i], N)
         d = size(f1.A, 2)
         A = Matrix{Float64}(undef, d, N)                 # column-major d×N == row-major N×d
         b = Vector{Float64}(undef, N); s = Vector{Float64}(undef, N)
@@ -152,7 +162,7 @@ function Base.iterate(iter::SVRG_basic_iterable{R}) where {R}
     else
         γ = iter.γ
     end
-    c = set_problem!(Ctx(), iter.F, iter.g, N)
+    c = set_problem!(Ctx(), iter.F, iter.g, N, iter.x0)
     x0 = Vector{Float64}(iter.x0)
     GC.@preserve x0 check(ccall((:ciao_svrg_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint), c.h, x0, γ, iter.plus))
     state = SVRG_basic_state{R}(c, γ, m, outvec(iter.x0)..., collect(1:N))
@@ -209,7 +219,7 @@ function Base.iterate(iter::SAGA_basic_iterable{R}) where {R}
     else
         γ = iter.γ
     end
-    c = set_problem!(Ctx(), iter.F, iter.g, iter.N)
+    c = set_problem!(Ctx(), iter.F, iter.g, iter.N, iter.x0)
     x0 = Vector{Float64}(iter.x0)
     GC.@preserve x0 check(ccall((:ciao_saga_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint), c.h, x0, γ, iter.SAG))
     state = SAGA_basic_state{R}(c, γ, outvec(iter.x0)..., 1)
@@ -281,7 +291,7 @@ function Base.iterate(iter::Table_iterable{R}) where {R}
     γ === nothing && return nothing
     N = iter.N
     hat_γ = iter.kind == :proshi ? sum(γ) : 1 / sum(1 ./ γ)           # ProShI_basic.jl:82 / Finito_basic.jl:82
-    c = set_problem!(Ctx(), iter.F, iter.g, N)
+    c = set_problem!(Ctx(), iter.F, iter.g, N, iter.x0)
     x0 = Vector{Float64}(iter.x0)
     γ64 = Vector{Float64}(γ)                                             # the engine computes in fp64 (R may be Float32)
     GC.@preserve x0 γ64 begin
@@ -373,7 +383,7 @@ function refresh!(state::FINITO_adaptive_state)       # γ and hat_γ change on 
 end
 
 function Base.iterate(iter::FINITO_adaptive_iterable{R}) where {R}
-    c = set_problem!(Ctx(), iter.F, iter.g, iter.N)
+    c = set_problem!(Ctx(), iter.F, iter.g, iter.N, iter.x0)
     x0 = Vector{Float64}(iter.x0)
     GC.@preserve x0 check(ccall((:ciao_finito_adaptive_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64),
                                 c.h, x0, Float64(iter.α), Float64(iter.tol_b)))                  # :59-99

@@ -26,7 +26,7 @@ import torch.distributed as dist  # noqa: E402
 
 from ciaoalgorithms_jl_b200 import _lib as L  # noqa: E402
 from ciaoalgorithms_jl_b200.engine import Engine  # noqa: E402
-from ciaoalgorithms_jl_b200.sampling import HostRNG, LFinitoSweeper, shard_rows  # noqa: E402
+from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, LFinitoSweeper, csr, shard_rows  # noqa: E402
 
 
 def main():
@@ -175,6 +175,30 @@ def main():
     full.finito_init(np.full(d, 0.01), gsh, hsh)
     assert rel(sh.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-12
     assert np.array_equal(sh.get_table_rows(), full.get_table_rows(lo, hi - lo))
+    # static minibatches shard by row owner (Finito_basic.jl:110-118 with the batch split over the ranks, one exchange of the
+    # batch's Σ in the tail kernel): batches of 512 rows, one of them straddles the shard boundary, the last one is short
+    if use_p2p:
+        sw_a, sw_b = BatchSweeper(N, 512, 2, HostRNG(3)), BatchSweeper(N, 512, 2, HostRNG(3))
+        for _ in range(2):
+            ia, pa = csr(sw_a.take(sw_a.d))
+            ib, pb = csr(sw_b.take(sw_b.d))
+            sh.finito_steps(ia, pa)
+            full.finito_steps(ib, pb)
+        assert rel(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) < 1e-11, rel(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z))
+        assert rel(sh.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-11
+        assert rel(sh.get_table_rows(), full.get_table_rows(lo, hi - lo)) < 1e-12
+        assert same_on_all_ranks(sh.get_vec(L.VEC_Z))
+        # LFinito minibatch sweeps on the shards (Finito_LFinito.jl:78-103)
+        sh.lfinito_init(np.full(d, 0.01), gsh, hsh)
+        full.lfinito_init(np.full(d, 0.01), gsh, hsh)
+        order = np.arange(1, -(-N // 512) + 1, dtype=np.int64)
+        for _ in range(2):
+            sh.lfinito_outer(order, 512)
+            full.lfinito_outer(order, 512)
+        assert rel(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) < 1e-11, rel(sh.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z))
+        assert rel(sh.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-11
+        assert same_on_all_ranks(sh.get_vec(L.VEC_Z))
+        sh.finito_init(np.full(d, 0.01), gsh, hsh)
     try:
         sh.finito_steps(np.array([1, 2], dtype=np.int64), np.array([0, 1, 2], dtype=np.int64))
         raise AssertionError("finito_steps on a shard should fail")
