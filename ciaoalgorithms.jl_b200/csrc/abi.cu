@@ -309,6 +309,7 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
     c->seq_table_ldg = getenv("CIAO_SEQ_TABLE_LDG") != nullptr && getenv("CIAO_SEQ_TABLE_LDG")[0] == '1';
     c->batch_persistent = !(getenv("CIAO_BATCH_PER_LAUNCH") != nullptr && getenv("CIAO_BATCH_PER_LAUNCH")[0] == '1');
     c->num_sms = prop.multiProcessorCount;
+    if (const char *pos = getenv("CIAO_SEQ_CLUSTER_POS")) c->seq_cluster_pos = atoi(pos);
     auto init_device_objects = [&]() -> int {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         cudaEvent_t *evs[] = {&c->ev_pa, &c->ev_pb, &c->ev_sa, &c->ev_sb, &c->tm_a, &c->tm_b};

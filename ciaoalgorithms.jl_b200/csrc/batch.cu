@@ -486,6 +486,7 @@ __global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs 
 // the batch it owns — rows and table rows live together — and the batch's Σ is all-reduced in the tail kernel
 // (Finito_basic.jl:110-118 / Finito_LFinito.jl:91-100 with the batch split by row owner); `last` = last batch of the call.
 int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n, bool last = false) {
+    NvtxRange nvtx("ciao:minibatch:step");
     const int64_t d_pad = c->d_pad;
     int cpt = 2;
     while (cpt < 16 && (d_pad + cpt - 1) / cpt > 256) cpt *= 2;
@@ -596,6 +597,7 @@ static int launch_batch_persistent_loss(ciao_ctx *c, BatchPArgs &a, int T, size_
 
 // b_lo_dev / b_n_dev: device arrays (n_batches) of batch windows; z (and z_full for LFinito) as the first batch needs them
 int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int64_t *b_n_dev, int64_t n_batches, int64_t batch_rows) {
+    NvtxRange nvtx("ciao:minibatch:persistent");
     if (n_batches <= 0) return CIAO_OK;
     const int64_t d_pad = c->d_pad;
     // scripts/batch_probe.py at C2: 128 threads (8 columns each) beat 256 for batches of 4096 rows (170 vs 159 Finito epochs/s,

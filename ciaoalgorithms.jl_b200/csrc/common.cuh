@@ -7,6 +7,14 @@
 #include <stdio.h>
 
 #include "../../include/ciao_cuda.h"
+// NVTX ranges around every pass / persistent-kernel call (header-only nvtx3: a no-op unless a profiler is attached)
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 #ifdef __CUDACC__
 #include "fastmath.cuh"
 #endif
@@ -120,6 +128,7 @@ struct ciao_ctx {
     int *err_dev = nullptr;
     int *seq_smid = nullptr;           // [16] SM ids of the CTAs of the last sequential cluster kernel (ciao_last_seq_placement)
     int seq_smid_n = 0;
+    int seq_cluster_pos = 0;           // which cluster of a full grid runs the sequential kernels (env CIAO_SEQ_CLUSTER_POS, calibration)
     unsigned int *grid_bar = nullptr;  // grid barrier counter of the persistent minibatch kernel (batch.cu)
     double *host_pin = nullptr; size_t host_pin_bytes = 0;
     // comm

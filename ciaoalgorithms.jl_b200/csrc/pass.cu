@@ -470,6 +470,7 @@ int ciao_comm_allgather_inplace(ciao_ctx *c, double *buf, int64_t count_per_rank
 // Runs one streaming pass.  Result: c->partial[0..d_pad) = Σ (unscaled, all ranks), c->partial[d_pad] = Σ f_i (or max).
 // With `fin` the closing update out = base + scale·(Σ/den) rides in the same tail kernel.
 int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = false, const FinishSpec *fin = nullptr) {
+    NvtxRange nvtx(mode == PASS_GRAD ? "ciao:pass:full_gradient" : mode == PASS_NORMS ? "ciao:pass:row_norms" : "ciao:pass:table_init");
     if (c->loss_kind != CIAO_LOSS_LS && c->loss_kind != CIAO_LOSS_LOGISTIC)
         CIAO_FAIL(CIAO_ERR_STATE, "row pass: no row problem set (ciao_set_rows / ciao_gen_synthetic first)");
     const int64_t d_pad = c->d_pad;

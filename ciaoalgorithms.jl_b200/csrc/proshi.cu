@@ -451,6 +451,7 @@ int run_proshi_dual(ciao_ctx *c) {
 }
 
 int run_proshi_steps(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, const int64_t *ptr_dev, int64_t n_batches) {
+    NvtxRange nvtx("ciao:proshi:steps");
     if (K <= 0) return CIAO_OK;
     if (K >= (int64_t)1 << 31) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "ProShI: more than 2^31 - 1 block steps in one call");
     ProshiArgs a;

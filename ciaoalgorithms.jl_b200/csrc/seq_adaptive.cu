@@ -474,6 +474,7 @@ static int launch_adaptive_loss(ciao_ctx *c, const AdArgs &a, const SeqShape &sh
 
 // K steps on prepared indices; c->adapt_counters[0..1] = {steps completed, reductions of γ} afterwards
 int run_seq_adaptive(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double alpha, double tol_b) {
+    NvtxRange nvtx("ciao:seq:finito_adaptive");
     if (K <= 0) return CIAO_OK;
     if (K >= (int64_t)1 << 31) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito: more than 2^31 - 1 steps in one call");
     SeqShape sh;

@@ -49,6 +49,7 @@ struct SeqArgs {
     int npart_pad;          // C·W rounded up to a multiple of 32
     int table_tma;          // table rows are staged in the ring (cp.async by the producer warp; else: register prefetch with ld.global)
     int zero;               // always 0, opaque to the compiler (pins work in front of the exchange wait, see below)
+    int active_cluster;     // the cluster of the grid that does the work (the others exit at once): cluster position = SM set
     int *smid_out;          // [C]: the SM each CTA of the cluster runs on (cross-SM DSMEM latency is a per-pair constant)
     const int *err;         // error flag of the context: set by prep_indices_kernel when an index is out of range → no step runs
     RegParams reg;
@@ -103,6 +104,10 @@ __global__ void __launch_bounds__(320, 1) seq_kernel(const SeqArgs p) {
     // an out-of-range index (flagged by prep_indices_kernel, same stream) must not touch z, av or the table: the reference throws
     // BoundsError before any state changes (SAGA_basic.jl:56).  Uniform over the cluster, so nobody is left at a barrier.
     if (*reinterpret_cast<const volatile int *>(p.err) != 0) return;
+    // Cross-SM DSMEM latency is a per-SM-pair constant that differs between SM sets and between GPUs (seq_floor.cu), and a step
+    // ends with the slowest pair of the cluster.  The kernel is therefore launched as a full grid of clusters — CTA → SM
+    // placement of an idle GPU is deterministic — of which only the one at the calibrated position works.
+    if ((int)(blockIdx.x / cluster_nctarank()) != p.active_cluster) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const bool TT = TABLE && p.table_tma;             // table row slices are staged in the ring slots, behind the record tail
     const int Tc = blockDim.x - (TT ? 64 : 32);       // compute threads; then the producer warp and (TT) the table producer warp
@@ -206,8 +211,11 @@ __global__ void __launch_bounds__(320, 1) seq_kernel(const SeqArgs p) {
             g_seq_prof[rank * 8 + 5] = prod_busy;  // producer: cycles from wake-up to the end of its iteration
 #endif
         }
-    } else if (warp == W + 1) {
+    } else if (TABLE && warp == W + 1) {
         // ===================== table producer warp (TT kernels only) =====================
+        // (`TABLE &&`: compiled out of the table-free kernels.  Present but never taken, this branch changed ptxas' register
+        // allocation of the SVRG step loop — 113 instead of 116 registers — and cost 10 %: 0.311 → 0.343 µs/step at d = 4096,
+        // profiles/seq_kernel_history_r2.md.)
         // Every lane copies 16-byte chunks of the table row slice of step k + D with cp.async (generic proxy) once the
         // "written" barrier of step k is complete: every compute warp has then finished step k, i.e. consumed the slot's
         // previous contents (row k) and released its table writes of steps ≤ k.
@@ -541,7 +549,7 @@ static int launch_seq(ciao_ctx *c, const SeqArgs &a, const SeqShape &sh) {
         big_cluster[c->device % CIAO_MAX_DEVICES] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(sh.C);
+    cfg.gridDim = dim3(sh.C * (a.active_cluster + 1));   // clusters 0 … active − 1 exit at once
     cfg.blockDim = dim3(sh.Tc + (a.table_tma ? 64 : 32));   // + producer warp (+ table producer warp)
     cfg.dynamicSmemBytes = smem;
     cfg.stream = c->stream;
@@ -599,6 +607,7 @@ static int seq_shape(ciao_ctx *c, SeqShape *sh) {
 // one translation unit per algorithm (seq_svrg.cu, …) instantiates this
 template <int ALG>
 static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d) {
+    NvtxRange nvtx(ALG == ALG_SVRG ? "ciao:seq:svrg" : ALG == ALG_SAGA ? "ciao:seq:saga" : ALG == ALG_FINITO ? "ciao:seq:finito" : "ciao:seq:lfinito");
     if (K <= 0) return CIAO_OK;
     if (K >= (int64_t)1 << 31) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "sequential kernel: more than 2^31 - 1 steps in one call");
     SeqShape sh;
@@ -619,6 +628,7 @@ static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, doub
     a.gamma = c->gamma; a.hat_gamma = c->hat_gamma; a.Nd = (double)c->N_total; a.m_d = m_d;
     a.plus = c->plus; a.sag = c->sag; a.reg = c->reg; a.npart_pad = sh.npart_pad; a.zero = 0; a.err = c->err_dev;
     a.smid_out = c->seq_smid; c->seq_smid_n = sh.C;
+    a.active_cluster = std::max(0, std::min(c->seq_cluster_pos, c->num_sms / sh.C - 1));
     a.table_tma = (ALG == ALG_SAGA || ALG == ALG_FINITO) && seq_smem_bytes(sh, true) <= 200 * 1024 && !c->seq_table_ldg;
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
     int rc;

@@ -5,7 +5,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ciao_pkg; ciao_pkg.load()
 from ciaoalgorithms_jl_b200 import build as b
-VARIANTS = {"e1": ("CIAO_SEQ_E1",), "spin": ("CIAO_SEQ_SPIN",), "prod4": ("CIAO_SEQ_PROD4",), "fence0": ("CIAO_TABLE_FENCE=0",),
-            "fence1": ("CIAO_TABLE_FENCE=1",), "all": ("CIAO_SEQ_E1", "CIAO_SEQ_PROD4")}
+VARIANTS = {"e1": ("CIAO_SEQ_E1",), "spin": ("CIAO_SEQ_SPIN",)}
 for tag in (sys.argv[1:] or VARIANTS):
     print(b.build(force=True, defines=VARIANTS[tag], so=os.path.join(b.HERE, f"libciao_cuda_{tag}.so")), flush=True)
