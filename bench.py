@@ -390,17 +390,23 @@ def bench_c4(local, rank, world, peak, d, K, W, init_comm, barrier, max_over_ran
             for _ in range(W):
                 one()
             barrier()
-            kms = []
             e.timer_begin()
-            for _ in range(K):
+            for _ in range(K):                  # timed: back-to-back passes
                 one()
-                kms.append(e.last_timing().last_pass_ms)
             ms = max_over_ranks(e.timer_end()) / K
+            barrier()
+            kms, tms = [], []
+            for _ in range(K):                  # per-kernel device times (reading them synchronises: separate loop)
+                one()
+                tm = e.last_timing()
+                kms.append(tm.last_pass_ms)
+                tms.append(tm.last_tail_ms)
             barrier()
             kernel_ms = max_over_ranks(float(np.mean(kms)))
             res = one(read=True)
             bytes_per_gpu = rows * (ld + (d if what == "saga_table_init" else 0)) * 8
             out[what] = {"N_total": N, "rows_per_gpu": rows, "ms_per_pass": ms, "kernel_ms": kernel_ms, "tail_us": 1e3 * (ms - kernel_ms),
+                         "tail_kernel_us": 1e3 * max_over_ranks(float(np.mean(tms))),
                          "aggregate_gbs": world * bytes_per_gpu / ms / 1e6, "kernel_gbs_per_gpu": bytes_per_gpu / kernel_ms / 1e6,
                          "frac_of_peak_per_gpu": bytes_per_gpu / ms / 1e6 / peak, "epochs_per_s_2p22_rows": world * (rows / float(1 << 22)) / (ms / 1e3),
                          "bitwise_equal_across_ranks": bool(same_on_all_ranks(res)), "checksum": float(np.sum(res)), "passes": K}
@@ -676,6 +682,9 @@ def main():
         if replicas:
             # The part of the path that shards: the same full-gradient pass row-windowed over the ranks (N/G rows each) +
             # one NCCL allreduce of the d-vector, timed after the solves (SVRG_basic.jl:58-63 over a sharded F).
+            obj = [np.asarray(xs, dtype=np.float64).tobytes() if rank == 0 else None]   # every replica ended somewhere else:
+            dist.broadcast_object_list(obj, 0)                                          # the pass is evaluated at rank 0's x
+            xs = np.frombuffer(obj[0], dtype=np.float64).copy()
             g_local = e.full_gradient(xs, 1.0 / N)                  # this rank alone, all N rows, no exchange
             init_comm()
             lo, hi = (rank * N) // world, ((rank + 1) * N) // world
@@ -687,12 +696,17 @@ def main():
             for _ in range(W):
                 e.full_gradient(None, 1.0 / N, out=False)
             barrier()
-            sh_ms_list = []
             e.timer_begin()
-            for _ in range(K):
+            for _ in range(K):                                      # timed: back-to-back passes, no host synchronisation between them
                 e.full_gradient(None, 1.0 / N, out=False)
-                sh_ms_list.append(e.last_timing().last_pass_ms)
             sh_ms = max_over_ranks(e.timer_end()) / K
+            barrier()
+            sh_ms_list, tail_ms_list = [], []
+            for _ in range(K):                                      # per-kernel device times (reading them synchronises: separate loop)
+                e.full_gradient(None, 1.0 / N, out=False)
+                tm = e.last_timing()
+                sh_ms_list.append(tm.last_pass_ms)
+                tail_ms_list.append(tm.last_tail_ms)
             barrier()
             sh_kernel_ms = max_over_ranks(float(np.mean(sh_ms_list)))
             extra["full_gradient_sharded"] = {
@@ -700,6 +714,9 @@ def main():
                         f"({'one-shot peer-memory exchange fused into the tail kernel of the pass' if os.environ.get('CIAO_BENCH_EXCHANGE', 'p2p') == 'p2p' else 'ncclAllReduce'})",
                 "rows_per_gpu": hi - lo, "ms_per_pass": sh_ms, "kernel_ms": sh_kernel_ms, "passes": K,
                 "tail_us": 1e3 * (sh_ms - sh_kernel_ms),
+                "tail_kernel_us": 1e3 * max_over_ranks(float(np.mean(tail_ms_list))),
+                "tail_what": "ms_per_pass - kernel_ms: launch gap + tail kernel (reduction of the CTA partials, exchange incl. the wait "
+                             "for the slowest rank's pass, closing update); tail_kernel_us = that kernel alone, max over ranks",
                 "rel_err_vs_local": max_over_ranks(rel_err), "rel_err_bound": 1e-13, "bitwise_equal_across_ranks": bool(bitwise),
                 "aggregate_gbs": N * ld * 8 / sh_ms / 1e6, "kernel_gbs_per_gpu": (hi - lo) * ld * 8 / sh_kernel_ms / 1e6,
                 "speedup_vs_local_pass": pass_ms / sh_ms}

@@ -31,7 +31,8 @@ i64, f64, i32 = C.c_int64, C.c_double, C.c_int
 
 class Timing(C.Structure):
     _fields_ = [("last_pass_ms", C.c_float), ("last_seq_ms", C.c_float),
-                ("last_pass_bytes", C.c_int64), ("last_seq_steps", C.c_int64), ("launches", C.c_int64)]
+                ("last_pass_bytes", C.c_int64), ("last_seq_steps", C.c_int64), ("launches", C.c_int64),
+                ("last_tail_ms", C.c_float)]
 
 
 # name → (restype, argtypes); must list every symbol of include/ciao_cuda.h

@@ -129,14 +129,21 @@ __global__ void __launch_bounds__(256, 2) batch_pass_kernel(const BatchArgs p) {
         }
         __syncthreads();
         if (tid == 0 && it + S < my_count) issue(it + S);
+        // warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp; then the (row, dot)
+        // coefficients, one evaluation per warp (loss_coef_lanes)
+        constexpr int NP = (MODE == BATCH_LFINITO ? 2 : 1) * RPG;
+        double uq[NP], bq[NP], lq[NP], cq[NP];
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
-            // warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp
             const double2 pr = *reinterpret_cast<const double2 *>(red + ((par * RPG + r) * 32 + lane) * 2);
-            const double u0 = warp_sum_mma(pr.x, lane);
-            const double u1 = (MODE == BATCH_LFINITO) ? warp_sum_mma(pr.y, lane) : 0.0;
+            uq[r] = warp_sum_mma(pr.x, lane); bq[r] = tb[r]; lq[r] = tl[r];
+            if (MODE == BATCH_LFINITO) { uq[RPG + r] = warp_sum_mma(pr.y, lane); bq[RPG + r] = tb[r]; lq[RPG + r] = tl[r]; }
+        }
+        loss_coef_lanes<LOSS, NP>(uq, bq, lq, lane, cq);
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) {
             if (r >= rows) continue;
-            const double cz = loss_coef<LOSS>(u0, tb[r], tl[r]);
+            const double cz = cq[r];
             if (MODE == BATCH_FINITO) {  // Finito_basic.jl:112-116
                 const double cneg = -tgn[r], rr2 = thg[r];
                 double *trow = p.table + (r0 + r) * p.d_pad;
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(256, 2) batch_pass_kernel(const BatchArgs p) {
                 // (γ̂/N)(∇f_i(z_full) − ∇f_i(z)) = a_i · [(γ̂/N)·λ_i·(c_i(z_full) − c_i(z))]: one scalar per row and ONE fma per
                 // element instead of ten fp64 operations (the pass was fp64-issue bound at 3.3 TB/s); the batch sum has its own
                 // summation order anyway, and forming the coefficient difference first loses less to cancellation near z = z_full
-                const double czf = loss_coef<LOSS>(u1, tb[r], tl[r]);
+                const double czf = cq[(MODE == BATCH_LFINITO ? RPG : 0) + r];
                 const double wrow = p.cN * ((LOSS == CIAO_LOSS_LS ? tl[r] : 1.0) * (czf - cz));
 #pragma unroll
                 for (int e = 0; e < CPT; ++e) acc[e] = fma(a[r][e], wrow, acc[e]);
@@ -250,8 +257,17 @@ struct BatchPArgs {
     RegParams reg;
     int stages;
     int red_cols;         // columns per CTA in the distributed reduction (4, 8, 16 or 32)
+    int l2_prefetch;      // pull the CTA's rows (and table rows) of the NEXT batch into L2 while the grid closes the current one
 };
 
+#ifdef CIAO_SEQ_PROFILE
+static __device__ long long g_batch_prof[8];   // CTA 0, thread 0: cycles in [rows, partial write, barrier 1, reduction, barrier 2, z reload]
+#define BPROF_T(v) const long long v = clock64()
+#define BPROF_ADD(i, a, b) if (bid == 0 && tid == 0) bprof[i] += (b) - (a)
+#else
+#define BPROF_T(v)
+#define BPROF_ADD(i, a, b)
+#endif
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -323,7 +339,11 @@ __global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs 
     first_item(cb, cg);
     unsigned int bar_target = 0;
 
+#ifdef CIAO_SEQ_PROFILE
+    long long bprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int64_t b = 0; b < p.n_batches; ++b) {
+        BPROF_T(t_0);
         double zr[CPT], zfr[CPT], acc[CPT];
 #pragma unroll
         for (int k = 0; k < CPT / 2; ++k)
@@ -336,6 +356,8 @@ __global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs 
             }
         double fsum = 0.0;
         const int64_t lo_b = p.b_lo[b], n_b = p.b_n[b];
+        BPROF_T(t_1);
+        BPROF_ADD(5, t_0, t_1);
         while (cb == b) {
             const int slot = (int)(it % S);
             const uint32_t parity = (uint32_t)((it / S) & 1);
@@ -389,14 +411,21 @@ __global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs 
             }
             __syncthreads();
             if (tid == 0 && pb < p.n_batches) issue();  // the slot just read is free: prefetch runs ahead across batch boundaries
+            // warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp; then the (row, dot)
+            // coefficients, one evaluation per warp (loss_coef_lanes)
+            constexpr int NP = (MODE == BATCH_LFINITO ? 2 : 1) * RPG;
+            double uq[NP], bq[NP], lq[NP], cq[NP];
 #pragma unroll
             for (int r = 0; r < RPG; ++r) {
-                // warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp
                 const double2 pr = *reinterpret_cast<const double2 *>(red + ((par * RPG + r) * 32 + lane) * 2);
-                const double u0 = warp_sum_mma(pr.x, lane);
-                const double u1 = (MODE == BATCH_LFINITO) ? warp_sum_mma(pr.y, lane) : 0.0;
+                uq[r] = warp_sum_mma(pr.x, lane); bq[r] = tb[r]; lq[r] = tl[r];
+                if (MODE == BATCH_LFINITO) { uq[RPG + r] = warp_sum_mma(pr.y, lane); bq[RPG + r] = tb[r]; lq[RPG + r] = tl[r]; }
+            }
+            loss_coef_lanes<LOSS, NP>(uq, bq, lq, lane, cq);
+#pragma unroll
+            for (int r = 0; r < RPG; ++r) {
                 if (r >= rows) continue;
-                const double cz = loss_coef<LOSS>(u0, tb[r], tl[r]);
+                const double cz = cq[r];
                 if (MODE == BATCH_FINITO) {  // Finito_basic.jl:112-116
                     const double cneg = -tgn[r], rr2 = thg[r];
                     double *trow = p.table + (r0 + r) * p.d_pad;
@@ -409,7 +438,7 @@ __global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs 
                         if (col[k] >= 0) __stcg(reinterpret_cast<double2 *>(trow + col[k]), make_double2(t0, t1));
                     }
                 } else {  // Finito_LFinito.jl:94-98
-                    const double czf = loss_coef<LOSS>(u1, tb[r], tl[r]);   // see batch_pass_kernel: one fma per element
+                    const double czf = cq[(MODE == BATCH_LFINITO ? RPG : 0) + r];   // see batch_pass_kernel: one fma per element
                     const double wrow = p.cN * ((LOSS == CIAO_LOSS_LS ? tl[r] : 1.0) * (czf - cz));
 #pragma unroll
                     for (int e = 0; e < CPT; ++e) acc[e] = fma(a[r][e], wrow, acc[e]);
@@ -420,13 +449,32 @@ __global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs 
             ++it;
         }
         // ---- close the batch ----
+        BPROF_T(t_2);
+        BPROF_ADD(0, t_1, t_2);
         double *wrow = p.ws + (size_t)bid * p.d_pad;
 #pragma unroll
         for (int k = 0; k < CPT / 2; ++k)
             if (col[k] >= 0) __stcg(reinterpret_cast<double2 *>(wrow + col[k]), make_double2(acc[2 * k], acc[2 * k + 1]));
         if (tid == 0) __stcg(p.fws + bid, fsum);
+        // The batch boundary (two grid barriers + the reduction, ≈ 8 µs) is dead time for HBM: the ring holds only S row groups.
+        // L2 (126 MB) holds a whole batch, so the rows this CTA will stream next are requested now and the boundary overlaps
+        // with their HBM traffic; the next rows phase then runs out of L2.
+        if (p.l2_prefetch && warp == 0 && b + 1 < p.n_batches) {
+            const int64_t lo_n = p.b_lo[b + 1], n_n = p.b_n[b + 1];
+            const int64_t ng = (n_n + RPG - 1) / RPG;
+            for (int64_t g = bid + (int64_t)lane * G; g < ng; g += 32 * G) {
+                const int64_t r0 = lo_n + g * RPG;
+                const uint32_t nr = (uint32_t)min((int64_t)RPG, n_n - g * RPG);
+                tma_prefetch_l2(p.rec + r0 * p.ld, nr * (uint32_t)(p.ld * sizeof(double)));
+                if (MODE == BATCH_FINITO) tma_prefetch_l2(p.table + r0 * p.d_pad, nr * (uint32_t)(p.d_pad * sizeof(double)));
+            }
+        }
         bar_target += (unsigned int)G;
+        BPROF_T(t_3);
+        BPROF_ADD(1, t_2, t_3);
         grid_barrier(p.bar, bar_target);
+        BPROF_T(t_4);
+        BPROF_ADD(2, t_3, t_4);
         // distributed fixed-order reduction over ALL CTAs: CTA c owns the RC columns RC·c … (RC = 4…32, a whole number of
         // sectors); thread (col, slice) sums the CTA partials slice, slice + NS, … with four independent chains, the slices
         // are combined by shuffles inside a warp and through shared memory across the 8 warps — always in the same order
@@ -476,9 +524,24 @@ __global__ void __launch_bounds__(256) batch_persistent_kernel(const BatchPArgs 
             __syncthreads();  // rsm is reused by the next batch
         }
         bar_target += (unsigned int)G;
+        BPROF_T(t_5);
+        BPROF_ADD(3, t_4, t_5);
         grid_barrier(p.bar, bar_target);
+        BPROF_T(t_6);
+        BPROF_ADD(4, t_5, t_6);
     }
+#ifdef CIAO_SEQ_PROFILE
+    if (bid == 0 && tid == 0)
+        for (int i = 0; i < 8; ++i) g_batch_prof[i] = bprof[i];
+#endif
 }
+#ifdef CIAO_SEQ_PROFILE
+extern "C" int ciao_debug_batch_prof(ciao_ctx *c, long long *out8) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(out8, g_batch_prof, 8 * sizeof(long long)));
+    return CIAO_OK;
+}
+#endif
 
 // One minibatch over the contiguous rows [row_lo, row_lo + n) (0-based, GLOBAL row numbers): pass over the rows this context
 // holds + tail kernel (fixed-order reduction of the CTA partials, exchange over the ranks when the rows are sharded, closing
@@ -611,7 +674,9 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     const int T = (int)std::max<int64_t>(Tn, 32), rpg = 16 / cpt;
     const size_t stage_bytes = (size_t)rpg * c->ld * sizeof(double);
     const size_t fixed = (2 * rpg * 32 * 2 + 9 * 33 + 1) * sizeof(double) + 16 * sizeof(uint64_t) + 256;
-    int max_ctas = 2;
+    // a batch with no more row groups than SMs cannot use a second CTA per SM; it only makes the grid barriers and the
+    // reduction over the CTA partials longer (measured at C2, batch 512: 58 sweeps/s with 148 CTAs, 48 with 296)
+    int max_ctas = (batch_rows + rpg - 1) / rpg <= (int64_t)c->num_sms ? 1 : 2;
     if (const char *cv = getenv("CIAO_BATCH_CTAS")) max_ctas = std::max(1, std::min(8, atoi(cv)));
     int S = 3;
     if (const char *sv = getenv("CIAO_BATCH_STAGES")) S = std::max(1, std::min(8, atoi(sv)));
@@ -624,6 +689,10 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     a.z = ctx_vec(c, CIAO_VEC_Z); a.av = ctx_vec(c, CIAO_VEC_AV); a.zf = ctx_vec(c, CIAO_VEC_Z_FULL);
     a.bar = c->grid_bar; a.cN = c->hat_gamma / (double)c->N_total; a.hat_gamma = c->hat_gamma; a.reg = c->reg; a.stages = S;
     a.ws = nullptr; a.fws = nullptr;
+    // measured at C2, batch 4096: 25.6 µs per batch with the prefetch against 22.7 without — the rows phase is bound by the
+    // per-CTA latency of a row group, not by HBM, and the extra requests delay the barrier; off unless CIAO_BATCH_L2PF=1
+    a.l2_prefetch = 0;
+    if (const char *pf = getenv("CIAO_BATCH_L2PF")) a.l2_prefetch = atoi(pf) != 0;
     int rc;
     if (mode == BATCH_FINITO) {
         switch (cpt) {

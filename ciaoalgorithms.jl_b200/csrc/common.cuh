@@ -80,8 +80,8 @@ struct ciao_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_pa = nullptr, ev_pb = nullptr, ev_sa = nullptr, ev_sb = nullptr, tm_a = nullptr, tm_b = nullptr;
-    bool pass_timed = false, seq_timed = false;
+    cudaEvent_t ev_pa = nullptr, ev_pb = nullptr, ev_sa = nullptr, ev_sb = nullptr, tm_a = nullptr, tm_b = nullptr, ev_pc = nullptr;
+    bool pass_timed = false, seq_timed = false, tail_timed = false;
     // problem
     int loss_kind = -1;
     int64_t N_total = 0, row0 = 0, n_rows = 0, d = 0, d_pad = 0, ld = 0;
@@ -145,7 +145,7 @@ struct ciao_ctx {
     uint64_t p2p_timeout_ns = 20000000000ull;  // a peer that never shows up ends the wait with CIAO_ERR_COMM, not a hang
     // tuning
     int pass_threads = 0, pass_stages = 0, pass_ctas = 0, seq_cluster = 0, seq_threads = 0;
-    ciao_timing timing{0, 0, 0, 0, 0};
+    ciao_timing timing{0, 0, 0, 0, 0, 0};
 };
 
 void ciao_set_error(const char *fmt, ...);
@@ -261,6 +261,9 @@ __device__ __forceinline__ void tma_load_1d_stream(void *smem_dst, const void *g
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2(const void *gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -370,6 +373,31 @@ __device__ __forceinline__ double loss_coef(double u, double b, double lam) {
 #else
     return logistic_coef_fast(u, b, lam);  // fastmath.cuh: same formula, latency-optimised exp and division
 #endif
+}
+// c_p = loss_coef(u_p, b_p, λ_p) for p = 0 … P−1 with ONE evaluation per warp: lane p takes pair p, the results come back by
+// shuffle.  The logistic coefficient is ≈ 60 instructions; with every warp evaluating all P (row, dot) pairs of a row group the
+// streaming passes at d = 1024 were instruction-bound in exactly that code (LFinito minibatch pass: 3.3 TB/s).  Same function on
+// the same inputs: bit-identical to P separate evaluations.  Must be called by all 32 lanes.
+template <int LOSS, int P>
+__device__ __forceinline__ void loss_coef_lanes(const double (&u)[P], const double (&b)[P], const double (&lam)[P], int lane,
+                                                double (&c)[P]) {
+    static_assert(P <= 32, "one lane per pair");
+    if (LOSS == CIAO_LOSS_LS || P == 1) {
+#pragma unroll
+        for (int q = 0; q < P; ++q) c[q] = loss_coef<LOSS>(u[q], b[q], lam[q]);
+        return;
+    }
+    double ul = u[0], bl = b[0], ll = lam[0];
+#pragma unroll
+    for (int q = 1; q < P; ++q) {
+        const bool m = lane == q;
+        ul = m ? u[q] : ul;
+        bl = m ? b[q] : bl;
+        ll = m ? lam[q] : ll;
+    }
+    const double cl = loss_coef<LOSS>(ul, bl, ll);
+#pragma unroll
+    for (int q = 0; q < P; ++q) c[q] = __shfl_sync(0xffffffffu, cl, q);
 }
 template <int LOSS>
 __device__ __forceinline__ double loss_value(double u, double b, double lam) {

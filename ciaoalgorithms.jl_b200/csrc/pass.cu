@@ -128,16 +128,20 @@ __global__ void __launch_bounds__(512, 1) row_pass_kernel(const PassArgs p) {
         // every thread has its slice of the stage in registers: the slot can be refilled
         if (tid == 0 && it + S < my_count) issue(it + S);
 
+        // the W warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp → identical bits
+        double uu[RPG], cc[RPG];
+#pragma unroll
+        for (int r = 0; r < RPG; ++r) uu[r] = warp_sum_mma(red[(par * RPG + r) * 32 + lane], lane);
+        if (MODE != PASS_NORMS) loss_coef_lanes<LOSS, RPG>(uu, tb, tl, lane, cc);   // rows beyond `rows` carry zeros: harmless
 #pragma unroll
         for (int r = 0; r < RPG; ++r) {
-            // the W warp partials (entries ≥ W stay zero) summed by the same tensor-core reduction in every warp → identical bits
-            const double u = warp_sum_mma(red[(par * RPG + r) * 32 + lane], lane);
+            const double u = uu[r];
             if (r >= rows) continue;
             if (MODE == PASS_NORMS) {
                 if (tid == 0) fsum = fmax(fsum, u);
                 continue;
             }
-            const double c = loss_coef<LOSS>(u, tb[r], tl[r]);
+            const double c = cc[r];
             if (tid == 0) {
                 fsum += loss_value<LOSS>(u, tb[r], tl[r]);
                 if (MODE == PASS_GRAD && p.ss_out) {
@@ -282,8 +286,18 @@ __global__ void __launch_bounds__(32 * REDUCE_SLICES) pass_tail_kernel(const Tai
     const bool is_max = scalar_col && a.fmax_mode;
     double s = 0.0;
     if (j < a.d_pad) {
-        if (a.with_vec)
-            for (int b = y; b < a.G; b += REDUCE_SLICES) s += a.ws[(size_t)b * a.d_pad + j];
+        if (a.with_vec) {   // four independent chains: the loads of a slice are in flight together (fixed order → deterministic)
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int b = y;
+            for (; b + 3 * REDUCE_SLICES < a.G; b += 4 * REDUCE_SLICES) {
+                s0 += a.ws[(size_t)b * a.d_pad + j];
+                s1 += a.ws[(size_t)(b + REDUCE_SLICES) * a.d_pad + j];
+                s2 += a.ws[(size_t)(b + 2 * REDUCE_SLICES) * a.d_pad + j];
+                s3 += a.ws[(size_t)(b + 3 * REDUCE_SLICES) * a.d_pad + j];
+            }
+            for (; b < a.G; b += REDUCE_SLICES) s0 += a.ws[(size_t)b * a.d_pad + j];
+            s = (s0 + s1) + (s2 + s3);
+        }
     } else if (scalar_col) {
         for (int b = y; b < a.G; b += REDUCE_SLICES) s = a.fmax_mode ? fmax(s, a.fws[b]) : s + a.fws[b];
     }
@@ -570,8 +584,10 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     const int tail_grid = mode == PASS_NORMS ? 1 : (int)((d_pad + 1 + 31) / 32);
     pass_tail_kernel<<<tail_grid, dim3(32, REDUCE_SLICES), 0, c->stream>>>(t);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev_pc, c->stream));
     c->timing.launches += 2;
     c->pass_timed = true;
+    c->tail_timed = true;
     c->timing.last_pass_bytes = (int64_t)wn * c->ld * 8 +
                                 ((mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT) ? (int64_t)c->n_rows * d_pad * 8 : 0);
     if (nccl_route) {

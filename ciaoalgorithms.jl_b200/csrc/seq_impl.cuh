@@ -87,9 +87,6 @@ constexpr int SEQ_IDX_POS = 10;
 //   SVRG with cached c_i:    ss at [0,4)             → b, λ at 0, 1 as in the tail, c at 3        (2 bulk copies per step)
 //   LFinito with cached c_i: tail at [0,6), ss at [6,10) → γ̂/γ at 4, c at 9                        (3 bulk copies per step)
 
-__device__ __forceinline__ void tma_prefetch_l2(const void *gsrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
 
 // CZ: c_i(z_full) is read from the record tail (written by the last full-gradient pass at z_full)
 // instead of being recomputed from a second dot product a_i·z_full.

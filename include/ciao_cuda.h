@@ -71,6 +71,8 @@ typedef struct {
     int64_t last_pass_bytes; /* algorithmic HBM bytes of that pass                                           */
     int64_t last_seq_steps;
     int64_t launches;       /* kernels launched by this context so far                                      */
+    float last_tail_ms;     /* device time of the last pass's tail kernel: CTA-partial reduction, exchange over the
+                               ranks (including the wait for the slowest rank) and the closing update              */
 } ciao_timing;
 
 /* ---- lifetime ----------------------------------------------------------- */

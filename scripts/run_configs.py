@@ -1,6 +1,6 @@
 """Measures BASELINE.json configs[1] (C2: L1-logistic N=2^20 d=1024, SAGA + Finito) and configs[4]
 (C5: sharing N=2^18 blocks n=1024, ProShI) on one B200, event-timed, with an oracle-side CPU sample.
-Writes gpurun_out/configs_r1.json (copied to profiles/ by hand)."""
+Writes gpurun_out/configs_r2.json (copied to profiles/ by hand)."""
 import json
 import os
 import sys
@@ -163,4 +163,4 @@ out["adaptive_finito_lasso"] = ad
 print(json.dumps(ad), flush=True)
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_r1.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs_r2.json"), "w"), indent=1)
