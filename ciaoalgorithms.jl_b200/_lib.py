@@ -78,6 +78,10 @@ SIGNATURES = {
     "ciao_set_table_rows": (i32, [_ctx, i64, i64, C.c_void_p]),
     "ciao_solver_restore": (i32, [_ctx, i32, f64, i32, C.c_void_p, f64]),
     "ciao_table_colsum": (i32, [_ctx, C.c_void_p]),
+    "ciao_jlrng_next_u64": (i32, [C.c_void_p, C.c_void_p, i64]),
+    "ciao_jlrng_rand_range": (i32, [C.c_void_p, i64, C.c_void_p, i64]),
+    "ciao_jlrng_randperm": (i32, [C.c_void_p, i64, C.c_void_p]),
+    "ciao_jlrng_sample_norep": (i32, [C.c_void_p, i64, i64, C.c_void_p]),
     "ciao_stage_indices": (i32, [_ctx, C.c_void_p, i64]),
     "ciao_timer_begin": (i32, [_ctx]),
     "ciao_timer_end": (i32, [_ctx, C.POINTER(C.c_float)]),

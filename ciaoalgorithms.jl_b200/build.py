@@ -24,7 +24,7 @@ FLAGS = [
     "-Xptxas", "-v",
 ]
 # translation units (abi.cu is a unity file that includes pass/gen/indices/proshi/comm)
-UNITS = ["abi.cu", "seq_svrg.cu", "seq_saga.cu", "seq_finito.cu", "seq_lfinito.cu", "seq_adaptive.cu", "seq_floor.cu"]
+UNITS = ["abi.cu", "seq_svrg.cu", "seq_saga.cu", "seq_finito.cu", "seq_lfinito.cu", "seq_adaptive.cu", "seq_floor.cu", "jlrng.cu"]
 
 
 def sources():

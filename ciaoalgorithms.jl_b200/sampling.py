@@ -39,6 +39,59 @@ class HostRNG:
         return (self.g.permutation(n) + 1).astype(np.int64)
 
 
+class JuliaRNG(HostRNG):
+    """The same four draws from a restatement of Julia ≥ 1.7's default RNG (Xoshiro256++ seeded like ``Random.seed!(seed)``)
+    and of Random's / StatsBase 0.33's samplers (csrc/jlrng.cu): with it the Python twin walks the index stream the Julia
+    shim would draw for the same seed.  Pinned: the raw stream (known answer in Julia's docs, tests/test_host_logic.py);
+    unverified against a running Julia: the integer samplers built on it.  Julia ≤ 1.6 (MersenneTwister) draws differently."""
+
+    def __init__(self, seed=0):
+        import hashlib
+        import struct
+        from . import _lib as L
+        self.lib = L.load()
+        words, n = [], int(seed)
+        if n < 0:
+            raise ValueError("Random.seed! takes a non-negative integer")
+        while True:                                    # Random.make_seed(n): the seed's UInt32 words, little end first
+            words.append(n & 0xFFFFFFFF)
+            n >>= 32
+            if n == 0:
+                break
+        digest = hashlib.sha256(b"".join(struct.pack("<I", w) for w in words)).digest()   # seed!(::Xoshiro, ::Vector{UInt32})
+        self.state = np.array(struct.unpack("<4Q", digest), dtype=np.uint64)
+
+    def _call(self, fn, *args):
+        from ._lib import check
+        check(fn(self.state.ctypes.data, *args))
+
+    def next_u64(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint64)
+        self._call(self.lib.ciao_jlrng_next_u64, out.ctypes.data, n)
+        return out
+
+    def rand_float(self, n: int) -> np.ndarray:               # rand(n) of Float64 one at a time: (u >>> 11)·2^-53
+        return (self.next_u64(n) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+    def rand_range(self, N: int) -> int:
+        return int(self.rand_vec(N, 1)[0])
+
+    def rand_vec(self, N: int, m: int) -> np.ndarray:
+        out = np.empty(m, dtype=np.int64)
+        self._call(self.lib.ciao_jlrng_rand_range, int(N), out.ctypes.data, int(m))
+        return out
+
+    def sample_norep(self, N: int, k: int) -> np.ndarray:
+        out = np.empty(k, dtype=np.int64)
+        self._call(self.lib.ciao_jlrng_sample_norep, int(N), int(k), out.ctypes.data)
+        return out
+
+    def randperm(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.int64)
+        self._call(self.lib.ciao_jlrng_randperm, int(n), out.ctypes.data)
+        return out
+
+
 def static_batches(N: int, r: int):
     """Finito_basic.jl:52-57 / Finito_LFinito.jl:44-49 / ProShI_basic.jl:52-57:
     batch j (1-based) = r(j−1)+1 .. jr, plus one remainder batch."""

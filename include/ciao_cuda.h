@@ -186,6 +186,18 @@ int ciao_set_table_rows(ciao_ctx *ctx, int64_t i0, int64_t n, const double *in);
 int ciao_solver_restore(ciao_ctx *ctx, int algo, double gamma, int flag, const double *gamma_N, double hat_gamma);
 int ciao_table_colsum(ciao_ctx *ctx, double *out);                             /* Σ_i s_i (sum(x_proshi), test_sharing.jl:42) */
 
+/* ---- host-side index draws (no device involved) ----------------------------- */
+/* Restatement of Julia >= 1.7's default RNG (task-local Xoshiro256++) and of the samplers the reference's RNG call sites go
+ * through (SVRG_basic.jl:73 rand(ind, m); SAGA_basic.jl:55 rand(1:N); Finito_basic.jl:97 sample(1:N, k, replace=false);
+ * Finito_basic.jl:102 randperm(d)), for hosts without Julia (the Python twin of the shim).  state4 = the four UInt64 state
+ * words (in/out); seeding (Random.seed!(n): SHA-256 of the seed's UInt32 words) is the caller's.  The raw stream is pinned by
+ * the known answer in Julia's documentation; the integer samplers are restated from Random / StatsBase 0.33 sources and are
+ * unverified against a running Julia (jlrng.cu).  All outputs are 1-based, as Julia returns them. */
+int ciao_jlrng_next_u64(uint64_t *state4, uint64_t *out, int64_t n);
+int ciao_jlrng_rand_range(uint64_t *state4, int64_t N, int64_t *out, int64_t m);
+int ciao_jlrng_randperm(uint64_t *state4, int64_t n, int64_t *out);
+int ciao_jlrng_sample_norep(uint64_t *state4, int64_t N, int64_t k, int64_t *out);
+
 /* ---- measurement ----------------------------------------------------------- */
 int ciao_stage_indices(ciao_ctx *ctx, const int64_t *idx_host, int64_t n);    /* pre-upload indices (device-resident timing) */
 int ciao_timer_begin(ciao_ctx *ctx);                                          /* CUDA event on the ctx stream */

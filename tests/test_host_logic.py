@@ -173,3 +173,44 @@ def test_bench_reference_arm_runs_one_solve_per_gpu_on_as_many_cores():
     res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=60, env=dict(os.environ, RANK="1"))
     assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+# ---- Julia's default RNG, restated (csrc/jlrng.cu, sampling.JuliaRNG) -----------------------------------------------
+def test_julia_rng_known_answer_from_the_julia_docs():
+    """`Random.seed!(1234); rand(2)` in Julia's documentation of Random.seed! / Xoshiro (Julia ≥ 1.7):
+    0.32597672886359486, 0.5490511363155669 — pins seeding (SHA-256 of the seed words), xoshiro256++ and the Float64 conversion."""
+    from ciaoalgorithms_jl_b200.sampling import JuliaRNG
+    x = JuliaRNG(1234).rand_float(2)
+    assert x[0] == 0.32597672886359486 and x[1] == 0.5490511363155669
+
+
+def test_julia_rng_samplers_are_well_formed_and_follow_the_stream():
+    from ciaoalgorithms_jl_b200.sampling import JuliaRNG
+    M64 = (1 << 64) - 1
+    # rand(1:N): Lemire's nearly-divisionless method on the UInt64 stream, re-derived here in Python integers
+    a, b = JuliaRNG(7), JuliaRNG(7)
+    N = 1000003
+    got = a.rand_vec(N, 2000)
+    raw = iter(int(v) for v in b.next_u64(4000))
+    want = []
+    for _ in range(2000):
+        m = next(raw) * N
+        if (m & M64) < N:
+            t = ((1 << 64) - N) % N
+            while (m & M64) < t:
+                m = next(raw) * N
+        want.append((m >> 64) + 1)
+    assert got.tolist() == want and got.min() >= 1 and got.max() <= N
+    # randperm / sample without replacement: permutations, distinct, in range, reproducible, state carried over between calls
+    r = JuliaRNG(3)
+    p = r.randperm(1000)
+    assert sorted(p.tolist()) == list(range(1, 1001))
+    assert not np.array_equal(p, r.randperm(1000))
+    assert np.array_equal(JuliaRNG(3).randperm(1000), p)
+    for N, k in ((50, 1), (50, 2), (50, 7), (100000, 5), (10, 10)):      # k = 1 | samplepair | Fisher–Yates | self-avoiding | all
+        s = r.sample_norep(N, k)
+        assert len(set(s.tolist())) == k and s.min() >= 1 and s.max() <= N
+    # the samplers plug into the reference's index-selection logic
+    sw = BatchSweeper(10, 3, 3, JuliaRNG(0))
+    seen = [b for _ in range(2 * sw.d) for b in sw.next().tolist()]
+    assert sorted(seen[:10]) == list(range(1, 11)) and sorted(seen[10:]) == list(range(1, 11))
