@@ -600,13 +600,14 @@ def main():
         e.svrg_init(x0, gamma, True)
         barrier()
         l0 = e.last_timing().launches
-        pass_ms_list, seq_ms_list = [], []
+        pass_ms_list, seq_ms_list, seq_mhz_list = [], [], []
         e.timer_begin()
         for k in range(K):
             e.svrg_epoch(idx_dev[k].data_ptr(), m_of(k, N))
             tm = e.last_timing()
             pass_ms_list.append(tm.last_pass_ms)
             seq_ms_list.append(tm.last_seq_ms)
+            seq_mhz_list.append(e.last_seq_clock_mhz())
         ms = max_over_ranks(e.timer_end())
         barrier()
         launches = e.last_timing().launches - l0
@@ -674,6 +675,8 @@ def main():
                                   "exchange_floor_us": floor["lone_mode1_ns"] / 1e3,
                                   "exchange_floor": floor, "smids": smids,
                                   "us_per_step_by_epoch": [round(1e3 * v / m_of(k, N), 4) for k, v in enumerate(seq_ms_list)],
+                                  "sm_mhz_by_epoch": [round(v, 1) for v in seq_mhz_list],
+                                  "cycles_per_step_by_epoch": [round(1e3 * v / m_of(k, N) * f, 1) for k, (v, f) in enumerate(zip(seq_ms_list, seq_mhz_list))],
                                   "algorithmic_bytes_per_step": 8 * d + 32,
                                   "achieved_gbs": (8 * d + 32) * inner_steps / float(np.sum(seq_ms_list)) / 1e6},
                  "full_gradient": {"rows_per_gpu": pass_rows, "kernel_ms": pass_ms,

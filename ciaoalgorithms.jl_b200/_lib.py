@@ -87,6 +87,7 @@ SIGNATURES = {
     "ciao_timer_end": (i32, [_ctx, C.POINTER(C.c_float)]),
     "ciao_last_timing": (i32, [_ctx, C.POINTER(Timing)]),
     "ciao_last_seq_placement": (i32, [_ctx, C.POINTER(i32), C.POINTER(i32)]),
+    "ciao_last_seq_clock": (i32, [_ctx, _ip, _ip]),
     "ciao_measure_exchange": (i32, [_ctx, i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                     C.POINTER(i32)]),
     "ciao_set_tuning": (i32, [_ctx, i32, i32, i32, i32, i32]),

@@ -317,8 +317,9 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
         for (auto ev : evs) CUDA_TRY(cudaEventCreate(ev));
         CUDA_TRY(cudaMalloc(&c->err_dev, sizeof(int)));
         CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
-        CUDA_TRY(cudaMalloc(&c->seq_smid, 16 * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&c->seq_smid, 16 * sizeof(int) + 2 * sizeof(long long)));   // SM ids, then {cycles, ns} of the last kernel
         CUDA_TRY(cudaMemsetAsync(c->seq_smid, 0xff, 16 * sizeof(int), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->seq_smid + 16, 0, 2 * sizeof(long long), c->stream));
         return CIAO_OK;
     };
     const int rc = init_device_objects();
@@ -1159,6 +1160,19 @@ extern "C" int ciao_last_seq_placement(ciao_ctx *c, int *smid16, int *n_ctas) {
     CUDA_TRY(cudaMemcpyAsync(smid16, c->seq_smid, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *n_ctas = c->seq_smid_n;
+    return CIAO_OK;
+}
+
+// SM cycles and wall nanoseconds CTA 0 of the last sequential cluster kernel spent in it: cycles/ns = the SM clock (GHz) the kernel
+// actually ran at — a latency-bound kernel's µs/step scales with it, and NVML's 100 ms samples do not resolve short dips
+extern "C" int ciao_last_seq_clock(ciao_ctx *c, int64_t *cycles, int64_t *ns) {
+    if (!c || !cycles || !ns) CIAO_FAIL(CIAO_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    long long h[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h, c->seq_smid + 16, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *cycles = h[0];
+    *ns = h[1];
     return CIAO_OK;
 }
 

@@ -50,6 +50,7 @@ struct SeqArgs {
     int table_tma;          // table rows are staged in the ring (cp.async by the producer warp; else: register prefetch with ld.global)
     int zero;               // always 0, opaque to the compiler (pins work in front of the exchange wait, see below)
     int active_cluster;     // the cluster of the grid that does the work (the others exit at once): cluster position = SM set
+    long long *clk_out;     // [2]: SM cycles and nanoseconds (globaltimer) CTA 0 spent in the kernel → the SM clock it actually ran at
     int *smid_out;          // [C]: the SM each CTA of the cluster runs on (cross-SM DSMEM latency is a per-pair constant)
     const int *err;         // error flag of the context: set by prep_indices_kernel when an index is out of range → no step runs
     RegParams reg;
@@ -124,10 +125,15 @@ __global__ void __launch_bounds__(320, 1) seq_kernel(const SeqArgs p) {
 
     // zero the ring padding and the unused partial slots once
     for (size_t i = tid; i < D * slot_doubles + 2 * (size_t)p.npart_pad * 2; i += blockDim.x) ring[i] = 0.0;
+    __shared__ long long clk_start[2];   // in shared memory, not registers: the step loop's register allocation must not change (§6 of the history)
     if (tid == 0) {
         uint32_t sm;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
         p.smid_out[rank] = (int)sm;
+        uint64_t ns0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+        clk_start[0] = clock64();
+        clk_start[1] = (long long)ns0;
         for (int s = 0; s < D; ++s) mbar_init(&row_bar[s], TT ? 33 : 1);  // + one cp.async arrive per producer lane
         mbar_init(&part_bar[0], 1);  // one local arrive (expect_tx) per phase; the data arrives as tx bytes
         mbar_init(&part_bar[1], 1);
@@ -518,6 +524,12 @@ __global__ void __launch_bounds__(320, 1) seq_kernel(const SeqArgs p) {
 #endif
     }
     cluster_sync_all();  // nobody exits while a peer may still touch its shared memory
+    if (tid == 0 && rank == 0) {
+        uint64_t ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        p.clk_out[0] = clock64() - clk_start[0];
+        p.clk_out[1] = (long long)ns1 - clk_start[1];
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -625,6 +637,7 @@ static int run_seq_alg(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, doub
     a.gamma = c->gamma; a.hat_gamma = c->hat_gamma; a.Nd = (double)c->N_total; a.m_d = m_d;
     a.plus = c->plus; a.sag = c->sag; a.reg = c->reg; a.npart_pad = sh.npart_pad; a.zero = 0; a.err = c->err_dev;
     a.smid_out = c->seq_smid; c->seq_smid_n = sh.C;
+    a.clk_out = reinterpret_cast<long long *>(c->seq_smid + 16);
     a.active_cluster = std::max(0, std::min(c->seq_cluster_pos, c->num_sms / sh.C - 1));
     a.table_tma = (ALG == ALG_SAGA || ALG == ALG_FINITO) && seq_smem_bytes(sh, true) <= 200 * 1024 && !c->seq_table_ldg;
     CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));

@@ -249,6 +249,12 @@ class Engine:
         check(self.lib.ciao_last_seq_placement(self.h, sm, C.byref(n)))
         return list(sm[: n.value])
 
+    def last_seq_clock_mhz(self) -> float:
+        """SM clock (MHz) the last sequential cluster kernel actually ran at: its own cycle counter over the global timer."""
+        cyc, ns = C.c_int64(), C.c_int64()
+        check(self.lib.ciao_last_seq_clock(self.h, C.byref(cyc), C.byref(ns)))
+        return 1e3 * cyc.value / ns.value if ns.value > 0 else 0.0
+
     def measure_exchange(self, cluster=8, warps=4, iters=100000, mode=1, max_clusters=74):
         """Per-cluster (ns per round, SM cycles per round, SM ids) of the cluster-exchange floor (seq_floor.cu)."""
         ns, cyc = (C.c_float * max_clusters)(), (C.c_float * max_clusters)()

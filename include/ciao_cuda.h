@@ -205,6 +205,8 @@ int ciao_timer_end(ciao_ctx *ctx, float *ms);                                 /*
 int ciao_last_timing(ciao_ctx *ctx, ciao_timing *out);
 /* SM ids of the CTAs of the last sequential cluster kernel (n_ctas ≤ 16 entries of smid16 are valid) */
 int ciao_last_seq_placement(ciao_ctx *ctx, int *smid16, int *n_ctas);
+/* SM cycles and nanoseconds the last sequential cluster kernel ran: cycles / ns = the SM clock (GHz) it actually saw */
+int ciao_last_seq_clock(ciao_ctx *ctx, int64_t *cycles, int64_t *ns);
 /* Latency floor of the sequential kernels' cluster exchange on this device (seq_floor.cu): every cluster of `cluster` CTAs ×
  * `warps` warps that fits on the GPU runs `iters` rounds of the st.async → mbarrier exchange (mode 0) or of exchange + partial
  * sum + dependent next message (mode 1) and reports its own ns and SM cycles per round and the SMs it sits on
