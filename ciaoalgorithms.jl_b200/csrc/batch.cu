@@ -676,7 +676,9 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     const size_t fixed = (2 * rpg * 32 * 2 + 9 * 33 + 1) * sizeof(double) + 16 * sizeof(uint64_t) + 256;
     // a batch with no more row groups than SMs cannot use a second CTA per SM; it only makes the grid barriers and the
     // reduction over the CTA partials longer (measured at C2, batch 512: 58 sweeps/s with 148 CTAs, 48 with 296)
-    int max_ctas = (batch_rows + rpg - 1) / rpg <= (int64_t)c->num_sms ? 1 : 2;
+    // LFinito's rows phase is latency-bound per CTA (two dots, two coefficients per row; 127 registers): four CTAs per SM lift a
+    // 65 536-row batch from 408 to 542 sweeps/s at C2 (profiles/batch_shape_sweep_r2.log); Finito's is HBM-bound already at two
+    int max_ctas = (batch_rows + rpg - 1) / rpg <= (int64_t)c->num_sms ? 1 : (mode == BATCH_LFINITO ? 4 : 2);
     if (const char *cv = getenv("CIAO_BATCH_CTAS")) max_ctas = std::max(1, std::min(8, atoi(cv)));
     int S = 3;
     if (const char *sv = getenv("CIAO_BATCH_STAGES")) S = std::max(1, std::min(8, atoi(sv)));
