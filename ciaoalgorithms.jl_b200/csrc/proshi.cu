@@ -8,8 +8,8 @@
 // Design.  With a diagonal Q_i the block update has no coupling
 // between coordinates: every column j of (s, av, z) evolves independently given the
 // index sequence.  proshi_steps_kernel (batch 1) keeps z_j and av_j of a thread's columns in
-// registers for the whole call while producer lanes TMA-stage the slices of (q_i, c_i, s_i)
-// and (γ_i, γ_i/N) sixteen steps ahead — no barrier, no reduction, no kernel launch per
+// registers for the whole call while producer lanes TMA-stage the slices of (q_i, c_i) and (γ_i, γ_i/N)
+// and a table producer warp cp.async-stages the slice of s_i sixteen steps ahead — no barrier, no reduction, no kernel launch per
 // step; proshi_batch_kernel (batches ≥ 64 blocks) works through the blocks of a batch in
 // parallel, four lanes per block, and closes each batch with a fixed-order CTA reduction.
 #include <algorithm>

@@ -8,12 +8,14 @@
 //
 // Design.  A cluster of C CTAs splits the d columns; a compute thread
 // owns CPT fixed columns of every state vector (w/z, av, z_full, Σw) in REGISTERS for
-// the whole call.  Each CTA has W compute warps and one PRODUCER warp.  Per step:
-//   1. producer: the sampled row slice a_i[cols of this CTA] + its record tail (b_i, λ_i,
-//      γ_i/N, γ̂/γ_i, cached c_i(z_full)) + the prepared index word + (SAGA/Finito) the same
-//      slice of the table row s_i are staged D steps ahead into an mbarrier ring by TMA
-//      (cp.async.bulk), driven by the host-generated index sequence.  A slot is free once the
-//      exchange phase of the step that used it is over.
+// the whole call.  Each CTA has W compute warps, one PRODUCER warp and, for the table algorithms, one TABLE PRODUCER
+// warp.  Per step:
+//   1. producer lane: the sampled row slice a_i[cols of this CTA] + its record tail (b_i, λ_i,
+//      γ_i/N, γ̂/γ_i, cached c_i(z_full)) + the prepared index word are staged D steps ahead into an
+//      mbarrier ring by TMA (cp.async.bulk), driven by the host-generated index sequence.  A slot is free
+//      once the exchange phase of the step that used it is over.  (SAGA/Finito) the same slice of the
+//      table row s_i joins it in the slot — copied by the table producer warp with cp.async, the generic
+//      proxy the rows are also written through (see the comment above CIAO table ordering below).
 //   2. compute: partial dots → warp shuffles → each warp pushes its partial into EVERY CTA
 //      of the cluster through DSMEM with st.async (a remote store that completes on the
 //      destination CTA's mbarrier by tx-count, so neither side needs a cluster-scope
@@ -27,7 +29,8 @@
 // Table rows are written by their owner threads only (st.global.cg → L2).  A staged copy is
 // stale when the same row index occurs again within the D-step prefetch window; such steps are
 // flagged by prep_indices_kernel (HAZARD) and re-read the row with ld.global.cg after the previous
-// write (same thread wrote those addresses → coherent).
+// write (same thread wrote those addresses → coherent); every other repeat is ordered behind the write
+// by a release/acquire chain through the "written" mbarrier.
 // The step is latency/issue bound (one warp per SM sub-partition), so the loop body is
 // kept free of predicates and global index loads: ring slots are zero padded to the thread
 // grid and carry everything a step needs.

@@ -1,14 +1,14 @@
 """Counts the SASS mnemonics that show how each hot kernel is built (B200_PROFILING.md, "what proves a Blackwell-native
-kernel"): UBLKCP = TMA bulk copy, UBLKPF = TMA L2 prefetch, SYNCS = mbarrier operations, STAS = st.async to a peer CTA's shared
+kernel"): UBLKCP = TMA bulk copy, UBLKPF = TMA L2 prefetch, LDGSTS = cp.async (generic-proxy staging of table rows, round 2), SYNCS = mbarrier operations, STAS = st.async to a peer CTA's shared
 memory, DMMA = fp64 tensor-core MMA, plus the fp64 pipe, memory and barrier instructions.  No GPU needed.
 
-    python scripts/sass_summary.py > profiles/sass_summary_r1.md
+    python scripts/sass_summary.py > profiles/sass_summary_r2.md
 """
 import os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "ciaoalgorithms.jl_b200", "libciao_cuda.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-keys = ["UBLKCP", "UBLKPF", "SYNCS", "STAS", "DMMA", "DFMA", "DMUL", "DADD", "MUFU", "LDG", "STG", "LDS", "STS", "SHFL", "BAR.SYNC", "MEMBAR", "ATOM"]
+keys = ["UBLKCP", "UBLKPF", "LDGSTS", "SYNCS", "STAS", "DMMA", "DFMA", "DMUL", "DADD", "MUFU", "LDG", "STG", "LDS", "STS", "SHFL", "BAR.SYNC", "MEMBAR", "ATOM"]
 want = {
     "row_pass_kernel<16, 0, 0>": "K1 full gradient, d = 4096, least squares (the roofline kernel)",
     "row_pass_kernel<4, 1, 1>": "K2 SAGA table init, d = 1024, logistic",
@@ -19,6 +19,8 @@ want = {
     "batch_persistent_kernel<4, 0, 1>": "Finito minibatches in one persistent cooperative kernel, logistic",
     "proshi_steps_kernel<1, 2>": "K7 ProShI, batch 1, IndBox",
     "proshi_batch_kernel<512, 4>": "K7 ProShI, batches >= 64 blocks",
+    "pass_tail_kernel": "tail of a pass: CTA-partial reduction + peer-memory exchange + closing update (round 2)",
+    "exchange_floor_kernel<1>": "exchange-latency measurement (round 2)",
 }
 rows = {}
 for f in re.split(r"\n\s*Function : ", txt)[1:]:
@@ -28,7 +30,7 @@ for f in re.split(r"\n\s*Function : ", txt)[1:]:
         rows[short] = (len(re.findall(r"/\*[0-9a-f]{4}\*/", f)), {k: len(re.findall(r"\b" + re.escape(k) + r"[\.\s;]", f)) for k in keys})
 print("# SASS inventory of the hot kernels (`scripts/sass_summary.py`, `cuobjdump -sass` of the in-tree libciao_cuda.so, sm_100a)\n")
 print("Static instruction counts of one representative instantiation per kernel family.  UBLKCP = TMA bulk copy (`cp.async.bulk`), UBLKPF = TMA L2")
-print("prefetch, SYNCS = mbarrier operations, STAS = `st.async` into a peer CTA's shared memory (the DSMEM exchange), DMMA = fp64")
+print("prefetch, LDGSTS = `cp.async` (the generic-proxy staging of table rows written inside the kernel, round 2), SYNCS = mbarrier operations, STAS = `st.async` into a peer CTA's shared memory (the DSMEM exchange), DMMA = fp64")
 print("tensor-core MMA (the shuffle-free warp sums); SHFL = 0 in the sequential kernels — no shuffle is left on the step's path;")
 print("ATOM = 0 everywhere — no floating-point atomics (fixed-order reductions, bitwise reproducible).\n")
 print("| kernel | role | instr | " + " | ".join(keys) + " |")
