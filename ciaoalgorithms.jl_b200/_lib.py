@@ -67,6 +67,7 @@ SIGNATURES = {
     "ciao_lfinito_init": (i32, [_ctx, C.c_void_p, C.c_void_p, f64]),
     "ciao_lfinito_outer": (i32, [_ctx, C.c_void_p, i64, i64]),
     "ciao_finito_adaptive_init": (i32, [_ctx, C.c_void_p, f64, f64]),
+    "ciao_finito_adaptive_init_cb": (i32, [_ctx, C.c_void_p, f64, f64, C.c_void_p, C.c_void_p]),
     "ciao_finito_adaptive_steps": (i32, [_ctx, C.c_void_p, i64, _ip]),
     "ciao_finito_adaptive_get": (i32, [_ctx, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _ip]),
     "ciao_proshi_init": (i32, [_ctx, C.c_void_p, C.c_void_p, f64]),
@@ -92,6 +93,9 @@ SIGNATURES = {
                                     C.POINTER(i32)]),
     "ciao_set_tuning": (i32, [_ctx, i32, i32, i32, i32, i32]),
 }
+
+
+PERTURB_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_double))   # ciao_perturb_fn
 
 
 class CiaoError(RuntimeError):

@@ -2,6 +2,7 @@
 // problem upload, the solver entry points that replace Base.iterate of the
 // reference's iterables, state read-back and measurement.  Unity build: the
 // kernel files are included here so that every kernel lives in one module.
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -31,7 +32,9 @@ int run_seq_saga(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d
 int run_seq_finito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
 int run_seq_lfinito(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double m_d);
 int run_seq_adaptive(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double alpha, double tol_b);  // seq_adaptive.cu
-int run_adaptive_init(ciao_ctx *c, const double *x0_dev, double alpha, int *n_chunks_out);
+int run_adaptive_init(ciao_ctx *c, const double *x0_dev, double alpha);
+int run_adaptive_retry(ciao_ctx *c, int64_t i, const double *x0_dev, const double *xeps_dev, double *out_dev);
+int run_adaptive_sdivg(ciao_ctx *c, const double *x0_dev, int *n_chunks_out);
 int run_adaptive_av(ciao_ctx *c, const double *S_dev, const double *G_dev, double hat_gamma);
 static int run_seq(ciao_ctx *c, int alg, const int64_t *idx_prepared, int64_t K, double m_d) {
     switch (alg) {
@@ -719,7 +722,11 @@ static double pairwise_recip_sum(const double *v, int64_t lo, int64_t hi) {
     return pairwise_recip_sum(v, lo, mid) + pairwise_recip_sum(v, mid, hi);
 }
 
-extern "C" int ciao_finito_adaptive_init(ciao_ctx *c, const double *x0, double alpha, double tol_b) {
+// :59-99.  `perturb` (may be NULL) serves the random restart of the stepsize estimate (:77-83): for a component with
+// ∇f_i(x0 + 1) == ∇f_i(x0) it is called as perturb(user, i (1-based), t, xeps) and must fill xeps = x0 .+ rand(t·[−1, 1], size(x0))
+// from the host's RNG — components in ascending order, t = 1, 2, 4, … per component, exactly the reference's draw order.
+extern "C" int ciao_finito_adaptive_init_cb(ciao_ctx *c, const double *x0, double alpha, double tol_b, ciao_perturb_fn perturb,
+                                            void *user) {
     CIAO_TRY(need_rows(c, "ciao_finito_adaptive_init", true));
     if (!x0 || !(alpha > 0) || !(tol_b > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_finito_adaptive_init: x0 is null, α ≤ 0 or tol_b ≤ 0 (Finito.jl:57-60)");
     if (c->peers.n > 1) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito keeps N×d tables: not available on row-sharded problems");
@@ -733,23 +740,51 @@ extern "C" int ciao_finito_adaptive_init(ciao_ctx *c, const double *x0, double a
     if (!c->adapt_counters) CUDA_TRY(cudaMalloc(&c->adapt_counters, 4 * sizeof(int64_t)));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
     CIAO_TRY(run_pass_finish(c, PASS_GRAD, ctx_vec(c, CIAO_VEC_X0), false, nullptr, 1.0, 1.0, ctx_vec(c, CIAO_VEC_TMP)));  // sum(∇f)  :90
-    int chunks = 0;
-    CIAO_TRY(run_adaptive_init(c, ctx_vec(c, CIAO_VEC_X0), alpha, &chunks));        // :65-87, partial sums of x0 ./ γ_i
-    launch_reduce_ws(c, c->ws, c->ws + (size_t)chunks * c->d_pad, chunks, c->partial, c->partial + c->d_pad, 0, 1);
-    CUDA_TRY(cudaGetLastError());
-    c->timing.launches += 1;
+    CIAO_TRY(run_adaptive_init(c, ctx_vec(c, CIAO_VEC_X0), alpha));                 // :65-87 with t = 1
     std::vector<double> gam((size_t)N);
     CUDA_TRY(cudaMemcpy2DAsync(gam.data(), sizeof(double), c->adapt, 4 * sizeof(double), sizeof(double), (size_t)N, cudaMemcpyDeviceToHost,
                                c->stream));
     int h = 0;
     CUDA_TRY(cudaMemcpyAsync(&h, c->err_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (h) {
+    if (h) {   // some ∇f_i(x0 + 1) == ∇f_i(x0): the random restart, :77-83
         CUDA_TRY(cudaMemsetAsync(c->err_dev, 0, sizeof(int), c->stream));
-        c->algo = 0;
-        CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito: ∇f_i(x0 + 1) == ∇f_i(x0) for some i; the reference then perturbs x0 at random "
-                  "(Finito_adaptive.jl:75-81), which the engine does not do — choose another x0");
+        if (!perturb) {
+            c->algo = 0;
+            CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito: ∇f_i(x0 + 1) == ∇f_i(x0) for some i; the reference then perturbs x0 at random "
+                      "(Finito_adaptive.jl:77-83) — pass a perturbation callback (ciao_finito_adaptive_init_cb) or choose another x0");
+        }
+        std::vector<double> nmg((size_t)N), xeps((size_t)c->d);
+        CUDA_TRY(cudaMemcpy2D(nmg.data(), sizeof(double), c->adapt + 3, 4 * sizeof(double), sizeof(double), (size_t)N, cudaMemcpyDeviceToHost));
+        const double sqrt_d = sqrt((double)c->d);
+        for (int64_t i = 0; i < N; ++i) {
+            if (!(nmg[(size_t)i] < 2.220446049250313e-16)) continue;
+            double nm = nmg[(size_t)i];
+            int64_t t = 1;                                                          // :76
+            while (nm < 2.220446049250313e-16) {                                    // :77
+                if (t > ((int64_t)1 << 52) || perturb(user, i + 1, t, xeps.data()) != 0) {   // :79 (the host's RNG)
+                    c->algo = 0;
+                    CIAO_FAIL(CIAO_ERR_INVALID, "adaptive Finito: the perturbation callback failed for component %lld (t = %lld)",
+                              (long long)(i + 1), (long long)t);
+                }
+                CIAO_TRY(upload_vec(c, CIAO_VEC_X, xeps.data()));
+                CIAO_TRY(run_adaptive_retry(c, i, ctx_vec(c, CIAO_VEC_X0), ctx_vec(c, CIAO_VEC_X), c->partial + c->d_pad + 2));   // :80-81
+                CUDA_TRY(cudaMemcpyAsync(&nm, c->partial + c->d_pad + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                t *= 2;                                                             // :82
+            }
+            double L_int = nm / ((double)t * sqrt_d);                               // :84
+            L_int /= (double)N;                                                     // :85
+            gam[(size_t)i] = alpha / L_int;                                         // :86
+            CUDA_TRY(cudaMemcpyAsync(c->adapt + 4 * i, &gam[(size_t)i], sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
     }
+    int chunks = 0;
+    CIAO_TRY(run_adaptive_sdivg(c, ctx_vec(c, CIAO_VEC_X0), &chunks));              // partial sums of x0 ./ γ_i
+    launch_reduce_ws(c, c->ws, c->ws + (size_t)chunks * c->d_pad, chunks, c->partial, c->partial + c->d_pad, 0, 1);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
     for (int r = 1; r < 8; ++r)   // the per-CTA copies of {γ_i, f_i, c_i} start identical
         CUDA_TRY(cudaMemcpyAsync(c->adapt + (size_t)r * 4 * N, c->adapt, (size_t)N * 4 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     c->hat_gamma = 1 / pairwise_recip_sum(gam.data(), 0, N);                        // :89
@@ -758,6 +793,10 @@ extern "C" int ciao_finito_adaptive_init(ciao_ctx *c, const double *x0, double a
     CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));                   // :91
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return CIAO_OK;
+}
+
+extern "C" int ciao_finito_adaptive_init(ciao_ctx *c, const double *x0, double alpha, double tol_b) {
+    return ciao_finito_adaptive_init_cb(c, x0, alpha, tol_b, nullptr, nullptr);
 }
 
 extern "C" int ciao_finito_adaptive_steps(ciao_ctx *c, const int64_t *idx, int64_t K, int64_t *steps_done) {

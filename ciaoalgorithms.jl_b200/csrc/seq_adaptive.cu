@@ -402,13 +402,47 @@ __global__ void __launch_bounds__(256) adaptive_init_kernel(const double *rec, i
         __syncthreads();
         if (tid == 0) {
             const double nmg = __dsqrt_rn(nm2);                                               // :75
-            if (nmg < 2.220446049250313e-16) atomicExch(err, 2);                              // :77
+            if (nmg < 2.220446049250313e-16) atomicExch(err, 2);                              // :77: the host runs the random restart
             double L_int = __ddiv_rn(nmg, __dsqrt_rn((double)d));                             // :84 (t = 1)
             L_int = __ddiv_rn(L_int, Nd);                                                     // :85
             double2 *o = reinterpret_cast<double2 *>(ad + 4 * i);
             o[0] = make_double2(__ddiv_rn(alpha, L_int), loss_value<LOSS>(u0, b, lam));       // :86, :66
-            o[1] = make_double2(c0, 0.0);
+            o[1] = make_double2(c0, nmg);   // slot 3: ‖∇f_i(x0+1) − ∇f_i(x0)‖ for the host (the step kernel resets it to 0)
         }
+    }
+}
+
+// one degenerate component: out[0] = ‖∇f_i(xeps) − ∇f_i(x0)‖ for a host-drawn xeps (the random restart, :79-81).  One CTA.
+template <int LOSS>
+__global__ void __launch_bounds__(256) adaptive_retry_kernel(const double *row, int64_t d_pad, const double *x0, const double *xeps,
+                                                             double *out) {
+    __shared__ double red[2][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t k = tid; k < d_pad; k += blockDim.x) {
+        s0 = fma(row[k], x0[k], s0);
+        s1 = fma(row[k], xeps[k], s1);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if (lane == 0) { red[0][warp] = s0; red[1][warp] = s1; }
+    __syncthreads();
+    double u0 = 0.0, u1 = 0.0;
+    for (int w = 0; w < 8; ++w) { u0 += red[0][w]; u1 += red[1][w]; }
+    __syncthreads();
+    const double b = row[d_pad + TAIL_B], lam = row[d_pad + TAIL_LAM];
+    const double c0 = loss_coef<LOSS>(u0, b, lam), c1 = loss_coef<LOSS>(u1, b, lam);
+    double q = 0.0;
+    for (int64_t k = tid; k < d_pad; k += blockDim.x) {
+        const double df = __dsub_rn(grad_elem<LOSS>(row[k], c1, lam), grad_elem<LOSS>(row[k], c0, lam));
+        q = fma(df, df, q);
+    }
+    q = warp_sum(q);
+    if (lane == 0) red[0][warp] = q;
+    __syncthreads();
+    if (tid == 0) {
+        double nm2 = 0.0;
+        for (int w = 0; w < 8; ++w) nm2 += red[0][w];
+        out[0] = __dsqrt_rn(nm2);
     }
 }
 
@@ -505,8 +539,8 @@ int run_seq_adaptive(ciao_ctx *c, const int64_t *idx_prepared, int64_t K, double
     return CIAO_OK;
 }
 
-// table, per-component scalars and Σ_i x0/γ_i (left in c->ws row 0 … reduced into c->partial by the caller's reduce)
-int run_adaptive_init(ciao_ctx *c, const double *x0_dev, double alpha, int *n_chunks_out) {
+// table and per-component scalars {γ_i (t = 1), f_i(x0), c_i(x0), ‖∇f_i(x0+1) − ∇f_i(x0)‖}; the error flag is 2 if some norm is < eps
+int run_adaptive_init(ciao_ctx *c, const double *x0_dev, double alpha) {
     const int grid = (int)std::min<int64_t>(c->N_total, (int64_t)c->num_sms * 8);
     if (c->loss_kind == CIAO_LOSS_LS)
         adaptive_init_kernel<CIAO_LOSS_LS><<<grid, 256, 0, c->stream>>>(c->rec, c->N_total, c->d, c->d_pad, c->ld, x0_dev, c->table, c->adapt,
@@ -515,6 +549,22 @@ int run_adaptive_init(ciao_ctx *c, const double *x0_dev, double alpha, int *n_ch
         adaptive_init_kernel<CIAO_LOSS_LOGISTIC><<<grid, 256, 0, c->stream>>>(c->rec, c->N_total, c->d, c->d_pad, c->ld, x0_dev, c->table,
                                                                              c->adapt, alpha, (double)c->N_total, c->err_dev);
     CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+// ‖∇f_i(xeps) − ∇f_i(x0)‖ for component i (0-based) → out_dev[0]
+int run_adaptive_retry(ciao_ctx *c, int64_t i, const double *x0_dev, const double *xeps_dev, double *out_dev) {
+    const double *row = c->rec + i * c->ld;
+    if (c->loss_kind == CIAO_LOSS_LS) adaptive_retry_kernel<CIAO_LOSS_LS><<<1, 256, 0, c->stream>>>(row, c->d_pad, x0_dev, xeps_dev, out_dev);
+    else adaptive_retry_kernel<CIAO_LOSS_LOGISTIC><<<1, 256, 0, c->stream>>>(row, c->d_pad, x0_dev, xeps_dev, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    return CIAO_OK;
+}
+
+// Σ_i x0/γ_i as chunk partials in c->ws (reduced into c->partial by the caller's reduce)
+int run_adaptive_sdivg(ciao_ctx *c, const double *x0_dev, int *n_chunks_out) {
     const int chunks_y = (int)((c->d_pad + 255) / 256);
     int rows = std::max(1, c->num_sms * 8 / chunks_y);
     if (rows > c->N_total) rows = (int)c->N_total;
@@ -528,7 +578,7 @@ int run_adaptive_init(ciao_ctx *c, const double *x0_dev, double alpha, int *n_ch
     }
     adaptive_sdivg_kernel<<<dim3(rows, chunks_y), 256, 0, c->stream>>>(x0_dev, c->adapt, c->N_total, c->d_pad, c->ws);
     CUDA_TRY(cudaGetLastError());
-    c->timing.launches += 2;
+    c->timing.launches += 1;
     *n_chunks_out = rows;
     return CIAO_OK;
 }

@@ -165,8 +165,24 @@ class Engine:
         o = i64arr(batch_order)
         check(self.lib.ciao_lfinito_outer(self.h, ptr(o), len(o), int(r)))
 
-    def finito_adaptive_init(self, x0, alpha=0.999, tol_b=1e-9):
-        check(self.lib.ciao_finito_adaptive_init(self.h, ptr(f64arr(x0)), float(alpha), float(tol_b)))
+    def finito_adaptive_init(self, x0, alpha=0.999, tol_b=1e-9, perturb=None):
+        """perturb(i, t) -> d-vector `rand(t * [-1, 1], size(x0))` from the host's RNG: the random restart of the stepsize
+        estimate for components with ∇f_i(x0 + 1) == ∇f_i(x0) (Finito_adaptive.jl:77-83); None → such a problem is refused."""
+        x0 = f64arr(x0)
+        if perturb is None:
+            check(self.lib.ciao_finito_adaptive_init(self.h, ptr(x0), float(alpha), float(tol_b)))
+            return
+        d = self.d
+
+        def _cb(_user, i1, t, out):
+            try:
+                np.ctypeslib.as_array(out, shape=(d,))[:] = x0 + np.asarray(perturb(int(i1), int(t)), dtype=np.float64)
+                return 0
+            except Exception:
+                return 1
+
+        cb = L.PERTURB_FN(_cb)
+        check(self.lib.ciao_finito_adaptive_init_cb(self.h, ptr(x0), float(alpha), float(tol_b), C.cast(cb, C.c_void_p), None))
 
     def finito_adaptive_steps(self, idx, K=None) -> int:
         """Returns the number of steps completed (< K ⇔ `return nothing`, Finito_adaptive.jl:124-127)."""

@@ -38,6 +38,10 @@ class HostRNG:
     def randperm(self, n: int) -> np.ndarray:                  # randperm(n)
         return (self.g.permutation(n) + 1).astype(np.int64)
 
+    def rand_pm(self, t: int, d: int) -> np.ndarray:           # rand(t * [-1, 1], d)   Finito_adaptive.jl:79
+        """d draws from the two-element array [-t, t]: element k is v[rand(1:2)], one draw after the other."""
+        return np.where(self.rand_vec(2, d) == 1, -float(t), float(t))
+
 
 class JuliaRNG(HostRNG):
     """The same four draws from a restatement of Julia ≥ 1.7's default RNG (Xoshiro256++ seeded like ``Random.seed!(seed)``)

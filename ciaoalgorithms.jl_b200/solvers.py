@@ -364,7 +364,10 @@ class FINITO_adaptive_iterable:
 
     def _init(self):
         e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
-        e.finito_adaptive_init(self.x0, self.α, self.tol_b)                    # :59-99
+        rng = self.rng or GLOBAL_RNG
+        d = int(np.size(self.x0))
+        # :59-99; the random restart of the stepsize estimate (:77-83) draws from the host's RNG, in the reference's order
+        e.finito_adaptive_init(self.x0, self.α, self.tol_b, perturb=lambda i, t: rng.rand_pm(t, d))
         return FINITO_adaptive_state(e, AdaptiveSweeper(self.N, self.sweeping, self.rng or GLOBAL_RNG))
 
     def steps(self, state, k):

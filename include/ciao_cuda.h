@@ -160,8 +160,13 @@ int ciao_lfinito_outer(ciao_ctx *ctx, const int64_t *batch_order, int64_t n_batc
 /* ---- Finito adaptive  (Finito_adaptive.jl) ----------------------------------- */
 /* :59-99 — tables x_i = x0, ∇f_i(x0) (kept as the scalar c_i: ∇f_i = c_i·a_i for row models), f_i(x0);
  * γ_i = α / (‖∇f_i(x0+1) − ∇f_i(x0)‖ / (√d·N)); γ̂, av, z.  CIAO_ERR_UNSUPPORTED if some ∇f_i(x0+1) == ∇f_i(x0)
- * (the reference then draws random perturbations from the global RNG, :75-81). */
+ * (the reference then draws random perturbations from the global RNG, :75-81: use ciao_finito_adaptive_init_cb). */
 int ciao_finito_adaptive_init(ciao_ctx *ctx, const double *x0, double alpha, double tol_b);
+/* Same, with the random restart of :77-83: for a component i with ∇f_i(x0+1) == ∇f_i(x0) the library calls
+ * perturb(user, i (1-based), t, xeps), which must fill xeps[0..d) = x0 .+ rand(t·[−1, 1], size(x0)) from the HOST's RNG (Julia:
+ * a @cfunction) and return 0 — components in ascending order, t = 1, 2, 4, … per component: the reference's draw order. */
+typedef int (*ciao_perturb_fn)(void *user, int64_t i, int64_t t, double *xeps);
+int ciao_finito_adaptive_init_cb(ciao_ctx *ctx, const double *x0, double alpha, double tol_b, ciao_perturb_fn perturb, void *user);
 /* :101-160, K single-index steps with the backtracking linesearch on γ_i; *steps_done < K ⇔ the reference's
  * `return nothing` (γ_i < tol_b/N, :124-127) at step *steps_done + 1 */
 int ciao_finito_adaptive_steps(ciao_ctx *ctx, const int64_t *idx, int64_t K, int64_t *steps_done);

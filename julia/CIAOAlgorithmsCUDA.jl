@@ -385,8 +385,17 @@ end
 function Base.iterate(iter::FINITO_adaptive_iterable{R}) where {R}
     c = set_problem!(Ctx(), iter.F, iter.g, iter.N, iter.x0)
     x0 = Vector{Float64}(iter.x0)
-    GC.@preserve x0 check(ccall((:ciao_finito_adaptive_init, libciao), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64),
-                                c.h, x0, Float64(iter.α), Float64(iter.tol_b)))                  # :59-99
+    # :59-99.  The random restart of the stepsize estimate (:77-83) draws from Julia's global RNG exactly like the reference:
+    # the library calls back for every component with ∇f_i(x0+1) == ∇f_i(x0), in ascending order, with t = 1, 2, 4, …
+    function perturb(::Ptr{Cvoid}, i::Int64, t::Int64, xeps::Ptr{Float64})::Cint
+        println("initial upper bound for L too small")                                               # :78
+        unsafe_copyto!(xeps, pointer(x0 .+ rand(t * [-1, 1], size(x0))), length(x0))                 # :79
+        return Cint(0)
+    end
+    cb = @cfunction($perturb, Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}))
+    GC.@preserve x0 cb check(ccall((:ciao_finito_adaptive_init_cb, libciao), Cint,
+                                   (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Ptr{Cvoid}, Ptr{Cvoid}),
+                                   c.h, x0, Float64(iter.α), Float64(iter.tol_b), cb, C_NULL))
     state = FINITO_adaptive_state{R}(c, outvec(iter.x0)..., zeros(iter.N), R(0), collect(1:iter.N), 0, 0)
     return refresh!(state), state
 end

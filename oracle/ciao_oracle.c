@@ -502,8 +502,14 @@ static double orc_norm2(const double *v, int64_t d) {
 /* Finito_adaptive.jl:59-99.  Tables: s (N×d, x_i), gf (N×d, ∇f_i(x_i)), fi_x (N), gamma (N, out).
  * Returns 0, or −1 when ∇f_i(x0 + 1) == ∇f_i(x0) for some i: the reference then draws random perturbations
  * (:75-81, global RNG) — unsupported here as in the engine. */
-int orc_finito_adaptive_init(const orc_problem *p, const double *x0, double alpha, double *s, double *gf,
-                             double *fi_x, double *gamma, double *hat_gamma, double *av, double *z) {
+/* The random restart of the stepsize estimate (:77-83) draws from Julia's global RNG; the draw stays with the caller:
+ * perturb(user, i (1-based), t, xeps) must fill xeps = x0 .+ rand(t * [-1, 1], size(x0)) and return 0.  NULL: a degenerate
+ * component (∇f_i(x0 + 1) == ∇f_i(x0)) makes the init return -1. */
+typedef int (*orc_perturb_fn)(void *user, int64_t i1, int64_t t, double *xeps);
+
+int orc_finito_adaptive_init_cb(const orc_problem *p, const double *x0, double alpha, double *s, double *gf,
+                                double *fi_x, double *gamma, double *hat_gamma, double *av, double *z,
+                                orc_perturb_fn perturb, void *user) {
     const int64_t d = p->d, N = p->N;
     double *xeps = (double *)malloc((size_t)d * sizeof(double));
     double *ge = (double *)malloc((size_t)d * sizeof(double));
@@ -511,13 +517,20 @@ int orc_finito_adaptive_init(const orc_problem *p, const double *x0, double alph
         fi_x[i] = orc_gradient(p, i, x0, gf + i * d);
         memcpy(s + i * d, x0, (size_t)d * sizeof(double));
     }
-    for (int64_t k = 0; k < d; ++k) xeps[k] = x0[k] + 1.0;                       /* :73 */
     for (int64_t i = 0; i < N; ++i) {                                            /* :71-87 */
+        for (int64_t k = 0; k < d; ++k) xeps[k] = x0[k] + 1.0;                   /* :73 */
         orc_gradient(p, i, xeps, ge);
         for (int64_t k = 0; k < d; ++k) ge[k] -= gf[i * d + k];
         double nmg = orc_norm2(ge, d);                                           /* :75 */
-        if (nmg < 2.220446049250313e-16) { free(xeps); free(ge); return -1; }    /* :77 eps(R) */
-        double L_int = nmg / (1 * sqrt((double)d));                              /* :84, t = 1 */
+        int64_t t = 1;                                                           /* :76 */
+        while (nmg < 2.220446049250313e-16) {                                    /* :77 eps(R) */
+            if (!perturb || perturb(user, i + 1, t, xeps) != 0) { free(xeps); free(ge); return -1; }   /* :79 */
+            orc_gradient(p, i, xeps, ge);                                        /* :80 */
+            for (int64_t k = 0; k < d; ++k) ge[k] -= gf[i * d + k];
+            nmg = orc_norm2(ge, d);                                              /* :81 */
+            t *= 2;                                                              /* :82 */
+        }
+        double L_int = nmg / ((double)t * sqrt((double)d));                      /* :84 */
         L_int /= (double)N;                                                      /* :85 */
         gamma[i] = alpha / L_int;                                                /* :86 */
     }
@@ -529,6 +542,11 @@ int orc_finito_adaptive_init(const orc_problem *p, const double *x0, double alph
     orc_prox(p, z, av, *hat_gamma);                                              /* :91 */
     free(xeps); free(ge); free(sg);
     return 0;
+}
+
+int orc_finito_adaptive_init(const orc_problem *p, const double *x0, double alpha, double *s, double *gf,
+                             double *fi_x, double *gamma, double *hat_gamma, double *av, double *z) {
+    return orc_finito_adaptive_init_cb(p, x0, alpha, s, gf, fi_x, gamma, hat_gamma, av, z, NULL, NULL);
 }
 
 /* Finito_adaptive.jl:101-160, K steps on the given (1-based) indices (selection :107-119 is the caller's).

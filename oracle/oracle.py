@@ -227,18 +227,29 @@ class FinitoState:
 class FinitoAdaptiveState:
     """Finito_adaptive.jl:13-57 + :59-160 (index selection is the caller's).  Tables s (x_i) and gf (∇f_i(x_i))."""
 
-    def __init__(self, prob: Problem, x0, alpha=0.999, tol_b=1e-9):
+    def __init__(self, prob: Problem, x0, alpha=0.999, tol_b=1e-9, perturb=None):
+        """perturb(i, t) -> d-vector `rand(t * [-1, 1], size(x0))` (the caller's RNG), for the random restart of :77-83."""
         self.prob, self.alpha, self.tol_b = prob, float(alpha), float(tol_b)
         N, d = prob.N, prob.d
         self.s, self.gf = np.empty((N, d)), np.empty((N, d))
         self.fi_x, self.gamma = np.empty(N), np.empty(N)
         self.av, self.z = np.empty(d), np.empty(d)
         hg = C.c_double()
-        lib().orc_finito_adaptive_init.restype = C.c_int
-        rc = lib().orc_finito_adaptive_init(prob.ref, _d(_f64(x0)), C.c_double(self.alpha), _d(self.s), _d(self.gf),
-                                            _d(self.fi_x), _d(self.gamma), C.byref(hg), _d(self.av), _d(self.z))
+        x0 = _f64(x0)
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, _dp)
+
+        def _cb(_user, i1, t, out):
+            if perturb is None:
+                return 1
+            np.ctypeslib.as_array(out, shape=(d,))[:] = x0 + np.asarray(perturb(int(i1), int(t)), dtype=np.float64)
+            return 0
+
+        cb = CB(_cb)
+        lib().orc_finito_adaptive_init_cb.restype = C.c_int
+        rc = lib().orc_finito_adaptive_init_cb(prob.ref, _d(x0), C.c_double(self.alpha), _d(self.s), _d(self.gf),
+                                               _d(self.fi_x), _d(self.gamma), C.byref(hg), _d(self.av), _d(self.z), cb, None)
         if rc != 0:
-            raise ValueError("∇f_i(x0 + 1) == ∇f_i(x0): the reference's random fallback (Finito_adaptive.jl:75-81) is not restated")
+            raise ValueError("∇f_i(x0 + 1) == ∇f_i(x0) and no perturbation source for the random restart (Finito_adaptive.jl:77-83)")
         self.hat_gamma = hg.value
         self.backtracks = 0
 

@@ -237,7 +237,7 @@ class ProShI:
 
 # ---- Finito_adaptive.jl ----------------------------------------------------------------------------------
 class FinitoAdaptive:
-    def __init__(self, F, g, x0, alpha=0.999, tol_b=1e-9):       # :59-99
+    def __init__(self, F, g, x0, alpha=0.999, tol_b=1e-9, perturb=None):       # :59-99; perturb(i, t) = rand(t*[-1,1], size(x0))
         self.F, self.g, self.N, self.alpha, self.tol_b = F, g, len(F), alpha, tol_b
         N = self.N
         x0 = np.asarray(x0, float)
@@ -252,8 +252,14 @@ class FinitoAdaptive:
             xeps = x0 + 1.0
             grad_eps, _ = F[i].gradient(xeps)
             nmg = np.linalg.norm(grad_eps - self.gf[i])
-            assert nmg >= np.finfo(float).eps, "the reference's random restart (:75-81) is outside the restatement"
-            L_int = nmg / (1 * np.sqrt(len(x0)))
+            t = 1
+            while nmg < np.finfo(float).eps:                      # :77-83, the draw is the caller's
+                assert perturb is not None, "∇f_i(x0 + 1) == ∇f_i(x0) and no perturbation source"
+                xeps = x0 + perturb(i + 1, t)
+                grad_eps, _ = F[i].gradient(xeps)
+                nmg = np.linalg.norm(grad_eps - self.gf[i])
+                t *= 2
+            L_int = nmg / (t * np.sqrt(len(x0)))
             L_int /= N
             self.gam[i] = alpha / L_int
         self.hat = 1 / np.sum(1 / self.gam)

@@ -913,3 +913,40 @@ def test_out_of_range_index_leaves_the_state_untouched():
         assert np.array_equal(e.get_table_rows(), s)
         e.saga_steps(good)                                   # still usable
         assert not np.array_equal(e.get_vec(L.VEC_Z), z)
+
+
+def test_finito_adaptive_random_restart():
+    """Finito_adaptive.jl:77-83 through the C ABI: the library calls back into the host for the perturbation draws of the
+    degenerate components, in the reference's order; same draws → same γ_i, γ̂, av, z as the oracle, and the steps continue from there."""
+    from ciaoalgorithms_jl_b200.sampling import JuliaRNG
+    N, d = 40, 96
+    rs = np.random.default_rng(5)
+    A = rs.standard_normal((N, d))
+    for i in (3, 17, 18):                       # small integers with Σ_k a_ik = 0: ∇f_i(x0 + 1) == ∇f_i(x0) exactly, in any order
+        A[i, :d // 2] = rs.integers(-3, 4, size=d // 2)
+        A[i, d // 2:] = -A[i, :d // 2]
+    b = rs.standard_normal(N)
+    p = orc.Problem(orc.LOSS_LS, A, b, np.full(N, float(N))).set_reg(orc.REG_NORML1, lam=0.05)
+    x0 = np.zeros(d)
+    with Engine(0) as e:
+        e.set_rows(L.LOSS_LS, A, b, float(N))
+        e.set_reg(L.REG_NORML1, 0.05)
+        with pytest.raises(CiaoError) as ei:
+            e.finito_adaptive_init(x0)
+        assert ei.value.code == -4
+        ra, rb, calls = JuliaRNG(11), JuliaRNG(11), []
+
+        def pert(i, t):
+            calls.append((i, t))
+            return rb.rand_pm(t, d)
+
+        ref = orc.FinitoAdaptiveState(p, x0, perturb=lambda i, t: ra.rand_pm(t, d))
+        e.finito_adaptive_init(x0, perturb=pert)
+        assert [c[0] for c in calls if c[1] == 1] == [4, 18, 19]
+        gam, fi_x, _, hat, _ = e.finito_adaptive_get(fi_x=True)
+        assert rel(gam, ref.gamma) < 1e-12 and abs(hat - ref.hat_gamma) <= 1e-12 * ref.hat_gamma
+        assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-10 and rel(e.get_vec(L.VEC_Z), ref.z) < 1e-10
+        idx = AdaptiveSweeper(N, 1, HostRNG(2)).take(6 * N)
+        assert ref.steps(idx) == e.finito_adaptive_steps(idx)
+        assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+        assert rel(e.finito_adaptive_get()[0], ref.gamma) < 1e-12

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # Julia ccall type  →  the C parameter types it may be bound to
 JL2C = {
-    "Ptr{Cvoid}": {"ciao_ctx *", "void *", "const void *"},
+    "Ptr{Cvoid}": {"ciao_ctx *", "void *", "const void *", "ciao_perturb_fn"},   # the last one: a @cfunction pointer
     "Ref{Ptr{Cvoid}}": {"ciao_ctx **"},
     "Cint": {"int"},
     "Int64": {"int64_t"},
@@ -98,7 +98,7 @@ def test_the_shim_binds_every_solver_entry_point():
     for sym in ("ciao_create", "ciao_destroy", "ciao_last_error", "ciao_set_rows", "ciao_set_blocks", "ciao_set_reg", "ciao_get_vec",
                 "ciao_svrg_init", "ciao_svrg_epoch", "ciao_saga_init", "ciao_saga_steps", "ciao_finito_init", "ciao_finito_steps",
                 "ciao_lfinito_init", "ciao_lfinito_outer", "ciao_proshi_init", "ciao_proshi_steps", "ciao_proshi_solution",
-                "ciao_finito_adaptive_init", "ciao_finito_adaptive_steps", "ciao_finito_adaptive_get"):
+                "ciao_finito_adaptive_init_cb", "ciao_finito_adaptive_steps", "ciao_finito_adaptive_get"):
         assert sym in bound, sym
 
 

@@ -208,3 +208,38 @@ def test_finito_adaptive_every_step_same_linesearch_decisions(name, sweeping):
         close(a.gf, np.array(b.gf), f"step {k} gradient table", scale=uscale)
         close(a.fi_x, b.fi_x, f"step {k} f_i(x_i)", scale=uscale)
     assert b.backtracks > 0        # the linesearch was exercised
+
+
+def test_finito_adaptive_random_restart_of_the_stepsize_estimate():
+    """Finito_adaptive.jl:77-83: a component with ∇f_i(x0 + 1) == ∇f_i(x0) (here: rows whose entries sum to zero) gets a random
+    ±t perturbation of x0, t doubling per retry, and γ_i from the t after the loop.  Both restatements are fed the same draws
+    (sampling.JuliaRNG: `rand(t * [-1, 1], size(x0))` as the reference would draw them) in the same order."""
+    from ciaoalgorithms_jl_b200.sampling import JuliaRNG
+    N, d = 7, 6
+    rs = np.random.default_rng(5)
+    A = rs.standard_normal((N, d))
+    A[1] = [1, -1, 2, -2, 3, -3]            # Σ_k a_k = 0: the +1 shift does not change a·x
+    A[4] = [2, 2, -1, -1, -2, 0]
+    b = rs.standard_normal(N)
+    p = orc.Problem(orc.LOSS_LS, A, b, np.full(N, float(N))).set_reg(orc.REG_NORML1, lam=0.1)
+    F = [R2.LeastSquaresRow(A[i], b[i], float(N)) for i in range(N)]
+    x0 = np.zeros(d)                        # integer data: a_i·(x0 + 1) − a_i·x0 is exactly 0 in any summation order
+    with pytest.raises(ValueError):
+        orc.FinitoAdaptiveState(p, x0)
+    ra, rb, calls = JuliaRNG(11), JuliaRNG(11), []
+
+    def pert_a(i, t):
+        calls.append((i, t))
+        return ra.rand_pm(t, d)
+
+    a = orc.FinitoAdaptiveState(p, x0, perturb=pert_a)
+    b2 = R2.FinitoAdaptive(F, R2.NormL1(0.1), x0, perturb=lambda i, t: rb.rand_pm(t, d))
+    assert [c[0] for c in calls if c[1] == 1] == [2, 5]          # the degenerate components, ascending, each starting at t = 1
+    close(a.gamma, b2.gam, "gamma after the restart")
+    close(a.hat_gamma, b2.hat, "hat_gamma")
+    close(a.av, b2.av, "av")
+    close(a.z, b2.z, "z")
+    for k, i in enumerate([2, 5, 1, 2, 7, 5, 3]):
+        assert a.steps([i]) == 1 and b2.step(i)
+        close(a.z, b2.z, f"step {k} z")
+        close(a.gamma, b2.gam, f"step {k} gamma")
