@@ -92,10 +92,10 @@ def pack_F(F, N, d=None):
         d = np.asarray(f0.A).reshape(1, -1).shape[1]
         A, b, s = np.empty((N, d)), np.empty(N), np.empty(N)
         for i, f in enumerate(F):
-            Ai = np.asarray(f.A, dtype=np.float64)
+            Ai = L.f64arr(f.A)          # complex-typed real data is accepted (zero imaginary parts), see _lib.f64arr
             if not isinstance(f, LeastSquares) or Ai.size != d or np.size(f.b) != 1:
                 raise UnsupportedOperator("engine covers LeastSquares with a 1×d matrix per f_i (test_lasso.jl:53)")
-            A[i], b[i], s[i] = Ai.reshape(-1), float(np.asarray(f.b).reshape(-1)[0]), float(f.lam)
+            A[i], b[i], s[i] = Ai.reshape(-1), float(L.f64arr(f.b).reshape(-1)[0]), float(np.real(f.lam))
         return ("rows", L.LOSS_LS, A, b, s)
     if isinstance(f0, Precompose) and isinstance(f0.f, LogisticLoss):
         d = np.asarray(f0.L).reshape(1, -1).shape[1]

@@ -47,10 +47,11 @@ class DeviceProblem:
 def _element_type(x0):
     """The reference is generic in the element type (test_lasso.jl:3 runs Float32/Float64/ComplexF32/ComplexF64).  The engine
     computes in fp64; real single-precision problems are accepted and their solutions handed back in the caller's type
-    (`eltype(x) == T`, test_lasso.jl:74), complex ones are outside its scope."""
+    (`eltype(x) == T`, test_lasso.jl:74).  Complex-typed problems are accepted when their data is real (zero imaginary parts:
+    exactly what test_lasso.jl builds for ComplexF32/ComplexF64, see _lib.f64arr) and get complex-typed solutions back."""
     dt = np.asarray(x0).dtype
     if np.issubdtype(dt, np.complexfloating):
-        raise ops.UnsupportedOperator("complex element types are outside the engine's scope (SURVEY.md §8f)")
+        return np.dtype(np.complex64) if dt == np.complex64 else np.dtype(np.complex128)
     return np.dtype(np.float32) if dt == np.float32 else np.dtype(np.float64)
 
 

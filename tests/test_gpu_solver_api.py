@@ -82,8 +82,8 @@ def test_lasso_float32_problem_keeps_its_element_type():                        
     for solver in (S.Finito(maxit=1000, sweeping=2), S.SAGA(maxit=1000, gamma=1 / (3 * fx["L"].max())), S.Finito(maxit=1000, adaptive=True)):
         x, _ = solver(x0, F=F32, g=g, L=fx["L"].astype(np.float32), N=N, rng=HostRNG(1))
         assert x.dtype == np.float32 and fx["cost"](x.astype(np.float64)) - fx["f_star"] < 1e-3   # data rounded to single precision
-    with pytest.raises(ops.UnsupportedOperator):
-        S.SAGA(gamma=0.1)(x0.astype(np.complex64), F=F32, g=g, N=N)
+    with pytest.raises(TypeError):            # genuinely complex data is refused (complex-typed REAL data is accepted, see below)
+        S.SAGA(gamma=0.1)(x0.astype(np.complex64) + 1j, F=F32, g=g, N=N)
 
 
 def test_lasso_scalar_gamma_and_scalar_L():                                     # :128-140
@@ -222,3 +222,23 @@ def test_default_F_is_all_zero_components():                                    
     # SVRG with g = Zero as well: nothing moves
     x, _ = S.SVRG(gamma=0.1, maxit=3, m=7)(x0, F=None, N=5, rng=HostRNG(1))
     assert np.allclose(x, x0, rtol=1e-15, atol=0)      # z_full = (Σ_m w)/m with w ≡ x0: equal up to the rounding of the mean
+
+
+@pytest.mark.parametrize("T", [np.complex64, np.complex128])
+def test_lasso_complex_typed_problem(T):                                           # test_lasso.jl:3 (T = ComplexF32, ComplexF64)
+    """The reference's complex Lasso problems are complex only in their element type: C = rand(R, N, n) (:19), alpha, x_star and b
+    carry zero imaginary parts, so its complex arithmetic never leaves the real axis.  The engine computes on the real parts and
+    hands the solution back in the caller's type (:74 `eltype(x) == T`); data with non-zero imaginary parts is refused."""
+    fx, _, g = lasso_problem()
+    N = fx["N"]
+    R = np.float32 if T == np.complex64 else np.float64
+    F = [ops.LeastSquares(fx["A"][i:i + 1, :].astype(T), fx["b"][i:i + 1].astype(T), R(N)) for i in range(N)]
+    x0 = np.zeros(fx["n"], dtype=T)
+    tol = 1e-3 if T == np.complex64 else TOL
+    for solver in (S.Finito(maxit=1000, sweeping=2), S.SVRG(gamma=R(1 / (7 * fx["L"].max())), maxit=1000), S.SAGA(maxit=1000)):
+        x, _ = solver(x0, F=F, g=g, L=fx["L"].astype(R), N=N, rng=HostRNG(1))
+        assert x.dtype == T and np.all(x.imag == 0)
+        assert fx["cost"](x.real.astype(np.float64)) - fx["f_star"] < tol
+    F[2] = ops.LeastSquares(fx["A"][2:3, :].astype(T) * (1 + 1j), fx["b"][2:3].astype(T), R(N))
+    with pytest.raises(TypeError):
+        S.SAGA(maxit=10)(x0, F=F, g=g, L=fx["L"].astype(R), N=N, rng=HostRNG(1))
