@@ -19,7 +19,7 @@ ERR_NAMES = {-1: "CIAO_ERR_INVALID", -2: "CIAO_ERR_CUDA", -3: "CIAO_ERR_STATE",
              -4: "CIAO_ERR_UNSUPPORTED", -5: "CIAO_ERR_COMM", -6: "CIAO_ERR_OOM"}
 
 LOSS_LS, LOSS_LOGISTIC, LOSS_DIAGQUAD = 0, 1, 2
-REG_ZERO, REG_NORML1, REG_INDBOX = 0, 1, 2
+REG_ZERO, REG_NORML1, REG_INDBOX, REG_NORML1_PAIRS = 0, 1, 2, 3
 VEC_Z, VEC_Z_FULL, VEC_W, VEC_AV, VEC_X = 0, 1, 2, 3, 4
 SYNTH_LASSO, SYNTH_LOGISTIC, SYNTH_SHARING = 0, 1, 2
 
@@ -44,6 +44,7 @@ SIGNATURES = {
     "ciao_destroy": (i32, [_ctx]),
     "ciao_sync": (i32, [_ctx]),
     "ciao_set_rows": (i32, [_ctx, i32, i64, i64, i64, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, f64]),
+    "ciao_set_row_blocks": (i32, [_ctx, i32, i64, i64, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, f64]),
     "ciao_set_blocks": (i32, [_ctx, i64, i64, C.c_void_p, i64, C.c_void_p, i64, f64, f64, f64]),
     "ciao_set_reg": (i32, [_ctx, i32, C.c_void_p, i64]),
     "ciao_gen_synthetic": (i32, [_ctx, i32, i64, i64, i64, i64, C.c_uint64, f64]),
@@ -132,14 +133,35 @@ def f64arr(a):
     """fp64 view/copy of a host array.  Complex-typed input is accepted when every imaginary part is zero — what the reference's
     complex test problems are (test_lasso.jl:3, :19: `C = rand(R, N, n)` is real, only the element type is complex), and for such
     data the reference's complex arithmetic keeps every imaginary part at exactly 0, so computing on the real parts gives the same
-    bits; genuinely complex data needs two real rows per component and a group soft-threshold and is outside the engine's scope."""
+    bits.  Genuinely complex data never comes through here: operators.pack_F realifies it first (realify_rows / realify_vec)."""
     a = np.asarray(a)
     if np.iscomplexobj(a):
         if np.any(a.imag != 0):
-            raise TypeError("complex data with non-zero imaginary parts is outside the engine's scope (SURVEY.md §8f): "
-                            "only complex-typed problems whose data is real are accepted")
+            raise TypeError("complex data with non-zero imaginary parts must be realified first (realify_rows / realify_vec)")
         a = a.real
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def realify_vec(z):
+    """complex d-vector → real 2d-vector (re_0, im_0, re_1, im_1, …): the memory layout of a Julia Vector{ComplexF64}."""
+    z = np.asarray(z, dtype=np.complex128).reshape(-1)
+    return np.ascontiguousarray(np.column_stack([z.real, z.imag]).reshape(-1))
+
+
+def complexify_vec(x):
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    return x[0::2] + 1j * x[1::2]
+
+
+def realify_rows(A):
+    """complex m×d matrix → real 2m×2d block [Re; Im] acting on realify_vec(x): rows 2r, 2r+1 give Re and Im of (A x)_r, and
+    its transpose applied to (Re res, Im res) gives realify_vec(Aᴴ res) — the LeastSquares gradient of the complex problem."""
+    A = np.atleast_2d(np.asarray(A, dtype=np.complex128))
+    m, d = A.shape
+    out = np.empty((2 * m, 2 * d))
+    out[0::2, 0::2], out[0::2, 1::2] = A.real, -A.imag
+    out[1::2, 0::2], out[1::2, 1::2] = A.imag, A.real
+    return out
 
 
 def i64arr(a):

@@ -23,6 +23,7 @@ void ciao_set_error(const char *fmt, ...) {
 
 #include "pass.cu"
 #include "batch.cu"
+#include "blockseq.cu"
 #include "gen.cu"
 #include "indices.cu"
 
@@ -36,7 +37,11 @@ int run_adaptive_init(ciao_ctx *c, const double *x0_dev, double alpha);
 int run_adaptive_retry(ciao_ctx *c, int64_t i, const double *x0_dev, const double *xeps_dev, double *out_dev);
 int run_adaptive_sdivg(ciao_ctx *c, const double *x0_dev, int *n_chunks_out);
 int run_adaptive_av(ciao_ctx *c, const double *S_dev, const double *G_dev, double hat_gamma);
+int run_block_seq(ciao_ctx *c, int alg, const int64_t *idx_prepared, int64_t K, double m_d);   // blockseq.cu
+// block components (M > 1) and the complex soft-threshold take the general kernel; everything else the tuned cluster kernels
+static inline bool use_block_kernel(const ciao_ctx *c) { return c->M > 1 || c->reg.kind == CIAO_REG_NORML1_PAIRS || c->force_block; }
 static int run_seq(ciao_ctx *c, int alg, const int64_t *idx_prepared, int64_t K, double m_d) {
+    if (use_block_kernel(c)) return run_block_seq(c, alg, idx_prepared, K, m_d);
     switch (alg) {
         case ALG_SVRG: return run_seq_svrg(c, idx_prepared, K, m_d);
         case ALG_SAGA: return run_seq_saga(c, idx_prepared, K, m_d);
@@ -56,6 +61,11 @@ void ciao_comm_destroy(ciao_ctx *c);
 __global__ void prox_vec_kernel(const double *in, double *out, int64_t d_pad, double gamma, RegParams reg) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j >= d_pad) return;
+    if (reg.kind == CIAO_REG_NORML1_PAIRS) {   // the thread of each element recomputes its pair (d_pad is even)
+        const double2 y = prox_pair(reg, make_double2(in[j & ~1ll], in[j | 1ll]), gamma * reg.lambda, j & ~1ll);
+        out[j] = (j & 1) ? y.y : y.x;
+        return;
+    }
     const double lo = reg.lo_v ? reg.lo_v[j] : reg.lo_s, hi = reg.hi_v ? reg.hi_v[j] : reg.hi_s;
     out[j] = prox_rt(reg.kind, in[j], gamma * reg.lambda, lo, hi);
 }
@@ -63,6 +73,12 @@ __global__ void prox_vec_kernel(const double *in, double *out, int64_t d_pad, do
 __global__ void saga_z0_kernel(const double *x0, double *z, int64_t d_pad, double gamma, RegParams reg) {
     const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (j >= d_pad) return;
+    if (reg.kind == CIAO_REG_NORML1_PAIRS) {
+        const double2 y = prox_pair(reg, make_double2(__dmul_rn(1 - gamma, x0[j & ~1ll]), __dmul_rn(1 - gamma, x0[j | 1ll])),
+                                    gamma * reg.lambda, j & ~1ll);
+        z[j] = (j & 1) ? y.y : y.x;
+        return;
+    }
     const double lo = reg.lo_v ? reg.lo_v[j] : reg.lo_s, hi = reg.hi_v ? reg.hi_v[j] : reg.hi_s;
     z[j] = prox_rt(reg.kind, __dmul_rn(1 - gamma, x0[j]), gamma * reg.lambda, lo, hi);
 }
@@ -108,6 +124,7 @@ static void free_problem(ciao_ctx *c) {
 static int alloc_common(ciao_ctx *c, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d) {
     free_problem(c);
     c->N_total = N_total; c->row0 = row0; c->n_rows = n_rows; c->d = d;
+    c->M = 1;
     c->win0 = c->win_n = 0;
     c->cz_valid = false;
     c->d_pad = (d + 3) / 4 * 4;
@@ -269,7 +286,7 @@ static int set_gammas(ciao_ctx *c, const double *gamma_N, bool tails) {
         CUDA_TRY(cudaMemcpyAsync(c->gamma_dev, gamma_N, (size_t)c->N_total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
-    if (tails) {
+    if (tails && c->M == 1) {   // block components read γ_i from gamma_dev (blockseq.cu)
         set_gamma_tail_kernel<<<blocks_for(c->n_rows), 256, 0, c->stream>>>(c->rec, c->n_rows, c->d_pad, c->ld, c->gamma_dev + c->row0,
                                                                              (double)c->N_total, c->hat_gamma);  // γ of MY rows
         CUDA_TRY(cudaGetLastError());
@@ -311,6 +328,7 @@ extern "C" int ciao_create(ciao_ctx **out, int device) {
     c->device = device;
     c->cache_cz = !(getenv("CIAO_CACHE_CZ") != nullptr && getenv("CIAO_CACHE_CZ")[0] == '0');
     c->seq_table_ldg = getenv("CIAO_SEQ_TABLE_LDG") != nullptr && getenv("CIAO_SEQ_TABLE_LDG")[0] == '1';
+    c->force_block = getenv("CIAO_FORCE_BLOCK_KERNEL") != nullptr && getenv("CIAO_FORCE_BLOCK_KERNEL")[0] == '1';
     c->batch_persistent = !(getenv("CIAO_BATCH_PER_LAUNCH") != nullptr && getenv("CIAO_BATCH_PER_LAUNCH")[0] == '1');
     c->num_sms = prop.multiProcessorCount;
     if (const char *pos = getenv("CIAO_SEQ_CLUSTER_POS")) c->seq_cluster_pos = atoi(pos);
@@ -536,6 +554,45 @@ extern "C" int ciao_set_rows(ciao_ctx *c, int loss_kind, int64_t N_total, int64_
     return CIAO_OK;
 }
 
+// per-row tails of a block problem: row r of component i = r / M carries b_r and the component's λ_i
+__global__ void pack_block_tails_kernel(double *rec, int64_t n_rows_total, int64_t M, int64_t d_pad, int64_t ld, const double *b,
+                                        const double *scale, double scale_scalar) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rows_total) return;
+    double *t = rec + r * ld + d_pad;
+    t[0] = b[r];
+    t[1] = scale ? scale[r / M] : scale_scalar;
+    for (int k = 2; k < CIAO_TAIL; ++k) t[k] = 0.0;
+}
+
+extern "C" int ciao_set_row_blocks(ciao_ctx *c, int loss_kind, int64_t N, int64_t M, int64_t d, const double *A, int64_t lda,
+                                   const double *b_or_y, const double *scale, double scale_scalar) {
+    if (!c || !A || !b_or_y) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_row_blocks: null argument");
+    if (loss_kind != CIAO_LOSS_LS && loss_kind != CIAO_LOSS_LOGISTIC) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "ciao_set_row_blocks: unknown loss kind %d", loss_kind);
+    if (N <= 0 || M <= 0 || M > 4096 || d <= 0 || lda < d) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_row_blocks: bad shape N=%lld M=%lld d=%lld lda=%lld",
+                                                                     (long long)N, (long long)M, (long long)d, (long long)lda);
+    if (d > 8192) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "ciao_set_row_blocks: d = %lld exceeds 8192", (long long)d);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CIAO_TRY(alloc_common(c, N, 0, N, d));
+    c->M = (int)M;
+    const int64_t rows = N * M;
+    CUDA_TRY(cudaMalloc(&c->rec, (size_t)rows * c->ld * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(c->rec, 0, (size_t)rows * c->ld * sizeof(double), c->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(c->rec, (size_t)c->ld * sizeof(double), A, (size_t)lda * sizeof(double), (size_t)d * sizeof(double),
+                               (size_t)rows, cudaMemcpyDefault, c->stream));
+    double *tmp = nullptr;
+    CUDA_TRY(cudaMalloc(&tmp, (size_t)(rows + N) * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(tmp, b_or_y, (size_t)rows * sizeof(double), cudaMemcpyDefault, c->stream));
+    if (scale) CUDA_TRY(cudaMemcpyAsync(tmp + rows, scale, (size_t)N * sizeof(double), cudaMemcpyDefault, c->stream));
+    pack_block_tails_kernel<<<blocks_for(rows), 256, 0, c->stream>>>(c->rec, rows, M, c->d_pad, c->ld, tmp, scale ? tmp + rows : nullptr, scale_scalar);
+    CUDA_TRY(cudaGetLastError());
+    c->timing.launches += 1;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaFree(tmp);
+    c->loss_kind = loss_kind;
+    return CIAO_OK;
+}
+
 extern "C" int ciao_set_blocks(ciao_ctx *c, int64_t N, int64_t n, const double *Qdiag, int64_t ldq, const double *qlin,
                                int64_t ldl, double box_lo, double box_hi, double eta) {
     if (!c || !Qdiag || !qlin) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_blocks: null argument");
@@ -561,8 +618,9 @@ extern "C" int ciao_set_reg(ciao_ctx *c, int reg_kind, const double *params, int
     CUDA_TRY(cudaSetDevice(c->device));
     RegParams r{reg_kind, 0, 0, 0, nullptr, nullptr};
     if (reg_kind == CIAO_REG_ZERO) {
-    } else if (reg_kind == CIAO_REG_NORML1) {
+    } else if (reg_kind == CIAO_REG_NORML1 || reg_kind == CIAO_REG_NORML1_PAIRS) {
         if (!params || nparams != 1 || !(params[0] >= 0)) CIAO_FAIL(CIAO_ERR_INVALID, "NormL1 takes one parameter λ ≥ 0");
+        if (reg_kind == CIAO_REG_NORML1_PAIRS && (c->d % 2) != 0) CIAO_FAIL(CIAO_ERR_INVALID, "NormL1 on (re, im) pairs needs an even d");
         r.lambda = params[0];
     } else if (reg_kind == CIAO_REG_INDBOX) {
         if (params && nparams == 2) {
@@ -651,6 +709,9 @@ extern "C" int ciao_objective(ciao_ctx *c, const double *x, double *f_mean, doub
         if (c->reg.kind == CIAO_REG_NORML1) {
             for (int64_t j = 0; j < c->d; ++j) g += fabs(hx[j]);
             g *= c->reg.lambda;
+        } else if (c->reg.kind == CIAO_REG_NORML1_PAIRS) {   // λ Σ_k |x_k| over the complex entries
+            for (int64_t j = 0; j + 1 < c->d; j += 2) g += hypot(hx[j], hx[j + 1]);
+            g *= c->reg.lambda;
         } else if (c->reg.kind == CIAO_REG_INDBOX) {   // IndBox: 0 inside [lo, hi], +Inf outside (ProximalOperators indBox.jl call operator)
             std::vector<double> bounds;
             if (c->reg.lo_v) {
@@ -730,6 +791,7 @@ extern "C" int ciao_finito_adaptive_init_cb(ciao_ctx *c, const double *x0, doubl
     CIAO_TRY(need_rows(c, "ciao_finito_adaptive_init", true));
     if (!x0 || !(alpha > 0) || !(tol_b > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_finito_adaptive_init: x0 is null, α ≤ 0 or tol_b ≤ 0 (Finito.jl:57-60)");
     if (c->peers.n > 1) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito keeps N×d tables: not available on row-sharded problems");
+    if (use_block_kernel(c) && !c->force_block) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito is not available for M×d block components / complex data");
     c->algo = ALG_FINITO_ADAPTIVE; c->adapt_alpha = alpha; c->adapt_tol_b = tol_b; c->adapt_backtracks = 0;
     c->cz_valid = false;
     CIAO_TRY(reserve_for_solver(c));
@@ -913,7 +975,7 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
     // batches need the whole table on one GPU.
     const bool sharded = c->n_rows != c->N_total;
     // static minibatches (contiguous rows, Finito_basic.jl:52-57) of ≥ BATCH_MIN_ROWS rows: one streaming pass per batch
-    if (idx && batch_ptr && n_batches > 0 && !is_device_ptr(idx) && !is_device_ptr(batch_ptr)) {
+    if (idx && batch_ptr && n_batches > 0 && !is_device_ptr(idx) && !is_device_ptr(batch_ptr) && !use_block_kernel(c)) {
         bool contiguous = true;
         int64_t longest = 0;
         for (int64_t j = 0; j < n_batches && contiguous; ++j) {
@@ -991,7 +1053,7 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
                              -(c->hat_gamma / (double)N), 1.0, ctx_vec(c, CIAO_VEC_AV)));  // :85-88
     if (total == 0) return CIAO_OK;
     const bool sharded = c->n_rows != c->N_total;
-    if (r >= BATCH_MIN_ROWS && (!sharded || c->world > 1)) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
+    if (r >= BATCH_MIN_ROWS && (!sharded || c->world > 1) && !use_block_kernel(c)) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
         CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
         int rc = CIAO_ERR_UNSUPPORTED;
         if (!sharded && c->batch_persistent && n_batches > 1 && n_batches < ((int64_t)1 << 22)) {  // the whole sweep in one cooperative launch

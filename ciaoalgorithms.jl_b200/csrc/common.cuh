@@ -84,7 +84,9 @@ struct ciao_ctx {
     bool pass_timed = false, seq_timed = false, tail_timed = false;
     // problem
     int loss_kind = -1;
-    int64_t N_total = 0, row0 = 0, n_rows = 0, d = 0, d_pad = 0, ld = 0;
+    int64_t N_total = 0, row0 = 0, n_rows = 0, d = 0, d_pad = 0, ld = 0;   // n_rows, N_total count COMPONENTS
+    int M = 1;                         // rows per component (ciao_set_row_blocks); the record array holds n_rows·M rows
+    bool force_block = false;          // env CIAO_FORCE_BLOCK_KERNEL=1: M = 1 problems through the general block kernel too (tests)
     int64_t win0 = 0, win_n = 0;       // pass window over the local rows (0 = all)
     bool win_uniform = false;          // every rank's window is rows [rank·N/world, (rank+1)·N/world): the step scalars can be all-gathered
     double *rec = nullptr;             // row records

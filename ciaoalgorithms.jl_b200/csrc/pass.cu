@@ -479,6 +479,7 @@ static int launch_cpt(ciao_ctx *c, int mode, const PassArgs &a, int grid, int T,
 }
 
 int ciao_comm_allreduce(ciao_ctx *c, double *buf, int64_t count, int op_max);  // comm.cu
+int run_block_table_init(ciao_ctx *c, int mode, const double *x0_dev, int *grid_out);   // blockseq.cu
 int ciao_comm_allgather_inplace(ciao_ctx *c, double *buf, int64_t count_per_rank);
 
 // Runs one streaming pass.  Result: c->partial[0..d_pad) = Σ (unscaled, all ranks), c->partial[d_pad] = Σ f_i (or max).
@@ -488,6 +489,22 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     if (c->loss_kind != CIAO_LOSS_LS && c->loss_kind != CIAO_LOSS_LOGISTIC)
         CIAO_FAIL(CIAO_ERR_STATE, "row pass: no row problem set (ciao_set_rows / ciao_gen_synthetic first)");
     const int64_t d_pad = c->d_pad;
+    const bool init_mode_blk = mode == PASS_SAGA_INIT || mode == PASS_FINITO_INIT;
+    if (c->M > 1 && (c->world > 1 || c->win_n > 0)) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "block components are not sharded or windowed");
+    if (init_mode_blk && c->M > 1) {   // per-component table rows: the general block kernel (blockseq.cu), closed by the same tail kernel
+        int grid_b = 0;
+        CIAO_TRY(run_block_table_init(c, mode, x_dev, &grid_b));
+        TailArgs tb;
+        memset(&tb, 0, sizeof(tb));
+        tb.ws = c->ws; tb.fws = c->ws + (size_t)grid_b * d_pad; tb.G = grid_b; tb.d_pad = d_pad; tb.len = (int)d_pad + 1;
+        tb.with_vec = 1; tb.sum_out = c->partial;
+        if (fin) { tb.base = fin->base; tb.scale = fin->scale; tb.den = fin->den; tb.out = fin->out; }
+        fill_exchange(c, tb, false);
+        pass_tail_kernel<<<(int)((d_pad + 1 + 31) / 32), dim3(32, REDUCE_SLICES), 0, c->stream>>>(tb);
+        CUDA_TRY(cudaGetLastError());
+        c->timing.launches += 1;
+        return CIAO_OK;
+    }
     // Launch shape (scripts/k2_tune.py, gpurun_out/k2_tune.log: sweeps at d = 512 … 4096, 8.6 GB per pass).  A row should be one
     // group (16 columns per thread, one block reduction per 16 elements of work) and an SM should hold ≈ 512 threads in as many
     // small CTAs as that takes, each with a 2-stage ring: d = 1024 runs at 6.3 TB/s with 64 threads × 8 CTAs/SM against 3.1 TB/s
@@ -511,7 +528,7 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
     if (S > 16) S = 16;
     const size_t smem = (size_t)S * stage_bytes + fixed;
     const bool windowed = c->win_n > 0 && (mode == PASS_GRAD || mode == PASS_NORMS);
-    const int64_t w0 = windowed ? c->win0 : 0, wn = windowed ? c->win_n : c->n_rows;
+    const int64_t w0 = windowed ? c->win0 : 0, wn = windowed ? c->win_n : c->n_rows * c->M;   // rows streamed (M per component)
     const int64_t n_groups = (wn + rpg - 1) / rpg;
     int grid = (int)std::min<int64_t>(n_groups, (int64_t)c->num_sms * ctas_per_sm);
     if (grid < 1) grid = 1;
@@ -538,7 +555,7 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
         gather_shard = c->peers.start[sidx] == (int64_t)sidx * c->n_rows;
     gather_shard = gather_shard && c->row0 == (int64_t)c->rank * c->n_rows;
     const bool gather_ss = gather_win || gather_shard;
-    if (cache_cz && mode == PASS_GRAD && ((!windowed && c->world == 1) || gather_ss)) {
+    if (cache_cz && c->M == 1 && mode == PASS_GRAD && ((!windowed && c->world == 1) || gather_ss)) {
         const int64_t ss_rows = gather_shard ? c->N_total : c->n_rows;
         if (c->ss && c->ss_cap < ss_rows) {
             cudaFree(c->ss);

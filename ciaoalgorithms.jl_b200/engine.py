@@ -50,6 +50,18 @@ class Engine:
                                      ptr(sv), float(scale) if sv is None else 0.0))
         self.N, self.d, self.n_rows = N_total, d, n_rows
 
+    def set_row_blocks(self, loss_kind, A, b, M, scale=1.0):
+        """Components that are M×d blocks: A is (N·M)×d, b has N·M entries, scale N entries or a scalar."""
+        A, b = f64arr(A), f64arr(b)
+        rows, d = A.shape
+        M = int(M)
+        assert rows % M == 0 and b.shape == (rows,)
+        N = rows // M
+        sv = None if np.isscalar(scale) else f64arr(scale)
+        check(self.lib.ciao_set_row_blocks(self.h, loss_kind, N, M, d, ptr(A), A.strides[0] // 8, ptr(b), ptr(sv),
+                                           float(scale) if sv is None else 0.0))
+        self.N, self.d, self.n_rows = N, d, N
+
     def set_blocks(self, Qdiag, qlin, box, eta):
         Q, q = f64arr(Qdiag), f64arr(qlin)
         N, n = Q.shape

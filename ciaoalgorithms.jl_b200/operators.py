@@ -77,8 +77,9 @@ class UnsupportedOperator(TypeError):
     pass
 
 
-def pack_F(F, N, d=None):
-    """→ ("rows", loss_kind, A[N,d], b[N], scale[N])  or  ("blocks", Qdiag[N,n], qlin[N,n], (lo,hi), eta)."""
+def pack_F(F, N, d=None, force_complex=False):
+    """→ ("rows", loss_kind, A[N,d], b[N], scale[N])  |  ("rowblocks", loss_kind, A[N·M,d], b[N·M], scale[N], M, complex)
+    |  ("blocks", Qdiag[N,n], qlin[N,n], (lo,hi), eta)."""
     if len(F) != N:
         raise ValueError(f"F has {len(F)} components, N = {N}")
     f0 = F[0]
@@ -89,14 +90,30 @@ def pack_F(F, N, d=None):
             raise UnsupportedOperator("all-Zero F needs the dimension of x0")
         return ("rows", L.LOSS_LS, np.zeros((N, d)), np.zeros(N), np.zeros(N))
     if isinstance(f0, LeastSquares):
-        d = np.asarray(f0.A).reshape(1, -1).shape[1]
-        A, b, s = np.empty((N, d)), np.empty(N), np.empty(N)
-        for i, f in enumerate(F):
-            Ai = L.f64arr(f.A)          # complex-typed real data is accepted (zero imaginary parts), see _lib.f64arr
-            if not isinstance(f, LeastSquares) or Ai.size != d or np.size(f.b) != 1:
-                raise UnsupportedOperator("engine covers LeastSquares with a 1×d matrix per f_i (test_lasso.jl:53)")
-            A[i], b[i], s[i] = Ai.reshape(-1), float(L.f64arr(f.b).reshape(-1)[0]), float(np.real(f.lam))
-        return ("rows", L.LOSS_LS, A, b, s)
+        # LeastSquares(A_i (m×d), b_i (m), λ_i).  m = 1 with real data is the reference's own case (test_lasso.jl:53) and takes the
+        # tuned kernels; m > 1 (uniform) runs as M×d block components; genuinely complex data (non-zero imaginary parts in A, b or
+        # x0) is realified — x as (re, im) pairs, every complex row as the real block [Re; Im] — into blocks of M = 2m rows.
+        mats = []
+        for f in F:
+            if not isinstance(f, LeastSquares):
+                raise UnsupportedOperator("F mixes operator kinds")
+            Ai = np.asarray(f.A)
+            mats.append(Ai.reshape(1, -1) if Ai.ndim < 2 else Ai)
+        m, dc = mats[0].shape
+        if any(Ai.shape != (m, dc) for Ai in mats) or any(np.size(f.b) != m for f in F):
+            raise UnsupportedOperator("engine covers LeastSquares terms of one common shape m×d with m entries of b each")
+        is_cplx = force_complex or any(np.iscomplexobj(Ai) and np.any(Ai.imag != 0) for Ai in mats) or \
+            any(np.iscomplexobj(f.b) and np.any(np.asarray(f.b).imag != 0) for f in F)
+        s = np.array([float(np.real(f.lam)) for f in F])
+        if is_cplx:
+            A = np.vstack([L.realify_rows(Ai) for Ai in mats])
+            b = np.concatenate([L.realify_vec(np.asarray(f.b).reshape(-1)) for f in F])
+            return ("rowblocks", L.LOSS_LS, A, b, s, 2 * m, True)
+        A = np.vstack([L.f64arr(Ai) for Ai in mats])          # complex-typed real data is accepted (zero imaginary parts)
+        b = np.concatenate([L.f64arr(np.asarray(f.b).reshape(-1)) for f in F])
+        if m == 1:
+            return ("rows", L.LOSS_LS, A, b, s)
+        return ("rowblocks", L.LOSS_LS, A, b, s, m, False)
     if isinstance(f0, Precompose) and isinstance(f0.f, LogisticLoss):
         d = np.asarray(f0.L).reshape(1, -1).shape[1]
         A, y, mu = np.empty((N, d)), np.empty(N), np.empty(N)
@@ -130,11 +147,14 @@ def pack_F(F, N, d=None):
     raise UnsupportedOperator(f"f_i of type {type(f0).__name__} is outside the engine's scope (no CPU fallback)")
 
 
-def reg_params(g):
+def reg_params(g, complex_data=False):
     if g is None or isinstance(g, Zero):
         return (L.REG_ZERO,)
     if isinstance(g, NormL1):
-        return (L.REG_NORML1, float(g.lam))
+        # complex data: sign(x)·max(0, |x| − γλ) on every complex entry = a group soft-threshold on the (re, im) pairs
+        return (L.REG_NORML1_PAIRS if complex_data else L.REG_NORML1, float(g.lam))
+    if complex_data:
+        raise UnsupportedOperator(f"g of type {type(g).__name__} on complex data is outside the engine's scope (Zero, NormL1)")
     if isinstance(g, IndBox):
         return (L.REG_INDBOX, g.lo, g.hi)
     raise UnsupportedOperator(f"g of type {type(g).__name__} is outside the engine's scope (Zero, NormL1, IndBox)")

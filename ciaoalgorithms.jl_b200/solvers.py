@@ -57,12 +57,20 @@ def _element_type(x0):
 
 def _setup_engine(F, g, N, device=0, x0=None):
     out_dtype = _element_type(x0) if x0 is not None else np.dtype(np.float64)
-    e = _setup_engine_fp64(F, g, N, device, None if x0 is None else int(np.size(x0)))
+    x0_cplx = x0 is not None and np.iscomplexobj(x0) and bool(np.any(np.asarray(x0).imag != 0))
+    e = _setup_engine_fp64(F, g, N, device, None if x0 is None else int(np.size(x0)), x0_cplx)
     e.out_dtype = out_dtype
+    if getattr(e, "complex_data", False) and not np.issubdtype(out_dtype, np.complexfloating):
+        raise ops.UnsupportedOperator("complex F needs a complex x0 (the reference's state vectors take x0's element type)")
     return e
 
 
-def _setup_engine_fp64(F, g, N, device=0, d=None):
+def _x0(e, x0):
+    """x0 as the engine takes it: real fp64, or — genuinely complex problems — realified as (re, im) pairs."""
+    return L.realify_vec(x0) if getattr(e, "complex_data", False) else x0
+
+
+def _setup_engine_fp64(F, g, N, device=0, d=None, force_complex=False):
     if N is None:
         raise TypeError("keyword argument N is required (SVRG.jl:52 `N = N`)")
     if isinstance(F, DeviceProblem):
@@ -72,13 +80,16 @@ def _setup_engine_fp64(F, g, N, device=0, d=None):
     else:
         if F is None:
             F = [ops.Zero()] * N          # F === nothing && (F = fill(ProximalOperators.Zero(), (N,)))   SVRG.jl:58
-        packed = ops.pack_F(list(F), N, d)
+        packed = ops.pack_F(list(F), N, d, force_complex)
         e = Engine(device)
         if packed[0] == "rows":
             e.set_rows(packed[1], packed[2], packed[3], packed[4])
+        elif packed[0] == "rowblocks":
+            e.set_row_blocks(packed[1], packed[2], packed[3], packed[5], packed[4])
+            e.complex_data = packed[6]
         else:
             e.set_blocks(packed[1], packed[2], packed[3], packed[4])
-    e.set_reg(*ops.reg_params(g))
+    e.set_reg(*ops.reg_params(g, getattr(e, "complex_data", False)))
     return e
 
 
@@ -90,12 +101,17 @@ class _State:
     def __init__(self, engine):
         self.engine = engine
         self._dtype = getattr(engine, "out_dtype", np.dtype(np.float64))
-        self._host = {name: np.empty(engine.d, dtype=self._dtype) for name in self._vecs}
+        self._cplx = bool(getattr(engine, "complex_data", False))       # device vectors hold (re, im) pairs
+        n_host = engine.d // 2 if self._cplx else engine.d
+        self._host = {name: np.empty(n_host, dtype=self._dtype) for name in self._vecs}
         self._f64 = None if self._dtype == np.float64 else np.empty(engine.d)
 
     def __getattr__(self, name):
         vecs = type(self)._vecs
         if name in vecs:
+            if self._cplx:
+                self._host[name][:] = L.complexify_vec(self.engine.get_vec(vecs[name], self._f64))
+                return self._host[name]
             if self._f64 is None:
                 return self.engine.get_vec(vecs[name], self._host[name])
             self._host[name][:] = self.engine.get_vec(vecs[name], self._f64)   # fp64 on the device, the caller's type outside
@@ -137,7 +153,7 @@ class SVRG_basic_iterable:
         else:
             gamma = self.γ
         e = _setup_engine(self.F, self.g, N, self.device, self.x0)
-        e.svrg_init(self.x0, gamma, self.plus)                                 # :58-66
+        e.svrg_init(_x0(e, self.x0), gamma, self.plus)                                 # :58-66
         return SVRG_basic_state(e, gamma, m)
 
     def __iter__(self):
@@ -200,7 +216,7 @@ class SAGA_basic_iterable:
         else:
             gamma = self.γ
         e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
-        e.saga_init(self.x0, gamma, self.SAG)                                  # :41-48
+        e.saga_init(_x0(e, self.x0), gamma, self.SAG)                                  # :41-48
         return SAGA_basic_state(e, gamma)
 
     def steps(self, state, k):
@@ -279,7 +295,7 @@ class FINITO_basic_iterable:
             return None
         hat = 1 / np.sum(1 / gam)                                              # Finito_basic.jl:82
         e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
-        e.finito_init(self.x0, gam, hat)                                       # :76-84
+        e.finito_init(_x0(e, self.x0), gam, hat)                                       # :76-84
         return FINITO_basic_state(e, gam, hat, BatchSweeper(self.N, self.batch, self.sweeping, self.rng or GLOBAL_RNG))
 
     def steps(self, state, k):
@@ -314,7 +330,7 @@ class FINITO_LFinito_iterable(FINITO_basic_iterable):
             return None
         hat = 1 / np.sum(1 / gam)                                              # Finito_LFinito.jl:66
         e = _setup_engine(self.F, self.g, self.N, self.device, self.x0)
-        e.lfinito_init(self.x0, gam, hat)                                      # :67-72
+        e.lfinito_init(_x0(e, self.x0), gam, hat)                                      # :67-72
         return FINITO_LFinito_state(e, gam, hat, LFinitoSweeper(self.N, self.batch, self.sweeping, self.rng or GLOBAL_RNG))
 
     def steps(self, state, k):

@@ -50,6 +50,8 @@ extern "C" {
 #define CIAO_REG_ZERO 0   /* Zero()            prox = identity            SVRG.jl:49   */
 #define CIAO_REG_NORML1 1 /* NormL1(λ)         soft threshold             test_lasso.jl:59 */
 #define CIAO_REG_INDBOX 2 /* IndBox(lo, hi)    clamp (scalar or vector)   test_sharing.jl:25 */
+#define CIAO_REG_NORML1_PAIRS 3 /* NormL1(λ) on complex data stored as interleaved (re, im) pairs: sign(x)·max(0, |x| − γλ)
+                                   (ProximalOperators normL1.jl, complex method; test_lasso.jl:3 with T = ComplexF64)          */
 
 /* state vectors readable with ciao_get_vec (names follow the reference's state structs) */
 #define CIAO_VEC_Z 0      /* state.z      (SAGA/Finito/LFinito/ProShI iterate; SVRG inner sum) */
@@ -91,10 +93,17 @@ int ciao_sync(ciao_ctx *ctx);
  * with N_total components (single GPU: row0 = 0, n_rows = N_total). */
 int ciao_set_rows(ciao_ctx *ctx, int loss_kind, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d,
                   const double *A, int64_t lda, const double *b_or_y, const double *scale, double scale_scalar);
+/* Components that are M×d blocks: f_i = LeastSquares(A_i (M×d), b_i (M), λ_i) or Precompose(LogisticLoss(y_i (M), μ_i), L_i (M×d))
+ * (test_lasso.jl:52-54 is the case M = 1).  A is row-major (N·M)×d, component i holds rows i·M … i·M+M−1; b_or_y has N·M
+ * entries, scale N entries (NULL → scale_scalar).  A complex 1×d row is the M = 2 real block [Re; Im] of the realified problem
+ * (x interleaved as re, im), to be used with CIAO_REG_NORML1_PAIRS.  The passes stream the N·M rows like any rows; the sequential
+ * loops run in the general block kernel (csrc/blockseq.cu), not in the tuned cluster kernels; not sharded, no adaptive Finito. */
+int ciao_set_row_blocks(ciao_ctx *ctx, int loss_kind, int64_t N, int64_t M, int64_t d, const double *A, int64_t lda,
+                        const double *b_or_y, const double *scale, double scale_scalar);
 /* Sharing blocks f_i(x_i) = ½x'diag(q_i)x + c_i'x + (η/2)dist²(x, [lo,hi])   (test_sharing.jl:15-22) */
 int ciao_set_blocks(ciao_ctx *ctx, int64_t N, int64_t n, const double *Qdiag, int64_t ldq, const double *qlin,
                     int64_t ldl, double box_lo, double box_hi, double eta);
-/* g: ZERO (nparams 0) | NORML1 (params = {λ}) | INDBOX (params = {lo,hi} or lo[d] followed by hi[d]) */
+/* g: ZERO (nparams 0) | NORML1 (params = {λ}) | INDBOX (params = {lo,hi} or lo[d] followed by hi[d]) | NORML1_PAIRS (params = {λ}) */
 int ciao_set_reg(ciao_ctx *ctx, int reg_kind, const double *params, int64_t nparams);
 /* Counter-based synthetic shard generated directly in HBM (ciao_gen.h); scale = λ_i / μ_i for all rows */
 int ciao_gen_synthetic(ciao_ctx *ctx, int synth_kind, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d,

@@ -48,7 +48,9 @@ end
 
 # Complex-typed problems (test_lasso.jl:3, T = ComplexF32/ComplexF64) are accepted when their data is real — what the reference's
 # tests build (C = rand(R, N, n), :19): complex arithmetic on such data never leaves the real axis, so the engine computes on the
-# real parts and the solution comes back in the caller's element type.  Non-zero imaginary parts are refused.
+# real parts and the solution comes back in the caller's element type.  Non-zero imaginary parts are refused HERE: the library runs
+# genuinely complex data as realified M = 2 blocks with CIAO_REG_NORML1_PAIRS (ciao_set_row_blocks; the Python twin does it,
+# operators.pack_F), but this shim's state vectors are not yet laid out as (re, im) pairs.
 realdata(a) = eltype(a) <: Complex ?
     (all(iszero, imag.(a)) ? real.(a) : error("complex data with non-zero imaginary parts is outside the engine's scope")) : a
 
@@ -64,17 +66,27 @@ function set_problem!(c::Ctx, F, g, N::Int, x0 = nothing)
             (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Float64),
             c.h, 0, N, 0, N, d, A, d, b, s, 0.0))
         c.N, c.d = N, d
-    elseif f1 isa ProximalOperators.LeastSquares            # test_lasso.jl:53-54: LeastSquares(A[i:i,:], b[i:i], N)
-        d = size(f1.A, 2)
-        A = Matrix{Float64}(undef, d, N)                 # column-major d×N == row-major N×d
-        b = Vector{Float64}(undef, N); s = Vector{Float64}(undef, N)
+    elseif f1 isa ProximalOperators.LeastSquares            # test_lasso.jl:53-54: LeastSquares(A[i:i,:], b[i:i], N); also m×d blocks
+        m, d = size(f1.A)
+        all(f -> size(f.A) == (m, d) && length(f.b) == m, F) || error("engine covers LeastSquares terms of one common shape m×d")
+        A = Matrix{Float64}(undef, d, N * m)             # column-major d×(N·m) == row-major (N·m)×d: component i holds rows (i−1)m+1 … im
+        b = Vector{Float64}(undef, N * m); s = Vector{Float64}(undef, N)
         for i = 1:N
-            size(F[i].A, 1) == 1 || error("engine covers 1×d LeastSquares terms")
-            copyto!(view(A, :, i), realdata(vec(F[i].A))); b[i] = realdata(F[i].b)[1]; s[i] = F[i].lambda
+            Ai = realdata(F[i].A); bi = realdata(F[i].b)
+            for r = 1:m
+                copyto!(view(A, :, (i - 1) * m + r), view(Ai, r, :)); b[(i - 1) * m + r] = bi[r]
+            end
+            s[i] = F[i].lambda
         end
-        GC.@preserve A b s check(ccall((:ciao_set_rows, libciao), Cint,
-            (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Float64),
-            c.h, 0, N, 0, N, d, A, d, b, s, 0.0))
+        if m == 1
+            GC.@preserve A b s check(ccall((:ciao_set_rows, libciao), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Float64),
+                c.h, 0, N, 0, N, d, A, d, b, s, 0.0))
+        else                                             # m×d blocks: the general block kernel (csrc/blockseq.cu)
+            GC.@preserve A b s check(ccall((:ciao_set_row_blocks, libciao), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Float64),
+                c.h, 0, N, m, d, A, d, b, s, 0.0))
+        end
         c.N, c.d = N, d
     elseif f1 isa ProximalOperators.Precompose && f1.f isa ProximalOperators.LogisticLoss   # test_logistic_l1.jl:36
         d = size(f1.L, 2)

@@ -49,6 +49,7 @@
 #define ORC_REG_ZERO 0
 #define ORC_REG_NORML1 1
 #define ORC_REG_INDBOX 2
+#define ORC_REG_NORML1_PAIRS 3 /* NormL1(λ) on ComplexF64 data stored as interleaved (re, im) pairs: sign(x)·max(0, |x| − γλ) */
 
 typedef struct {
     int32_t loss_kind;
@@ -64,6 +65,8 @@ typedef struct {
     const double *reg_lo; /* IndBox lower bound: length d, or NULL → scalar */
     const double *reg_hi;
     double reg_lo_s, reg_hi_s;
+    int64_t M;          /* rows per component: f_i = LeastSquares(A_i (M×d), b_i (M), λ_i) or Precompose(LogisticLoss(y_i (M)), L_i (M×d));
+                           component i holds rows i·M … i·M+M−1 of A and b.  0 or 1: one row per component (test_lasso.jl:53).      */
 } orc_problem;
 
 /* ------------------------------------------------------------------------ */
@@ -86,6 +89,34 @@ static double orc_dot(const double *a, const double *x, int64_t d) {
  */
 double orc_gradient(const orc_problem *p, int64_t i, const double *x, double *y) {
     const int64_t d = p->d;
+    if (p->M > 1 && p->loss_kind != ORC_LOSS_DIAGQUAD) {
+        /* M×d blocks (ProximalOperators 0.14 leastSquaresDirect.jl / precompose.jl with a dense M×d matrix):
+         *   LeastSquares:  res = A x − b (gemv);  y = Aᴴ res (gemv, accumulated over the rows r = 1…M);  y .*= λ;  f = (λ/2)‖res‖²
+         *   Precompose(LogisticLoss(y, μ), L): u = L x;  c_r = −μ y_r/(1 + exp(y_r u_r));  y = Lᴴ c;  f = μ Σ_r log(1 + 1/exp(y_r u_r)) */
+        const int64_t M = p->M;
+        const double lam = p->lam[i];
+        double val = 0.0;
+        for (int64_t k = 0; k < d; ++k) y[k] = 0.0;
+        for (int64_t r = 0; r < M; ++r) {
+            const double *a = p->A + (i * M + r) * p->lda;
+            const double br = p->b[i * M + r];
+            double c;
+            if (p->loss_kind == ORC_LOSS_LS) {
+                c = orc_dot(a, x, d) - br;
+                val += c * c;
+            } else {
+                double e = exp(br * orc_dot(a, x, d));
+                c = -lam * br / (1 + e);
+                val += log(1 + 1 / e);
+            }
+            for (int64_t k = 0; k < d; ++k) y[k] += a[k] * c;
+        }
+        if (p->loss_kind == ORC_LOSS_LS) {
+            for (int64_t k = 0; k < d; ++k) y[k] *= lam;
+            return (lam / 2) * val;
+        }
+        return lam * val;
+    }
     const double *a = p->A + i * p->lda;
     if (p->loss_kind == ORC_LOSS_LS) {
         double res = orc_dot(a, x, d) - p->b[i];
@@ -125,6 +156,16 @@ void orc_prox(const orc_problem *p, double *y, const double *x, double gamma) {
             double xk = x[k];
             y[k] = xk + (xk <= -gl ? gl : (xk >= gl ? -gl : -xk));
         }
+    } else if (p->reg_kind == ORC_REG_NORML1_PAIRS) {
+        /* complex NormL1 (normL1.jl, complex method): y_k = sign(x_k)·max(0, |x_k| − γλ), sign(z) = z/|z|, on (re, im) pairs */
+        double gl = gamma * p->reg_lambda;
+        for (int64_t k = 0; k + 1 < d; k += 2) {
+            double re = x[k], im = x[k + 1];
+            double ab = hypot(re, im);
+            double m = ab - gl > 0 ? ab - gl : 0.0;
+            y[k] = ab == 0 ? 0.0 : (re / ab) * m;
+            y[k + 1] = ab == 0 ? 0.0 : (im / ab) * m;
+        }
     } else if (p->reg_kind == ORC_REG_INDBOX) {
         for (int64_t k = 0; k < d; ++k) {
             double lo = p->reg_lo ? p->reg_lo[k] : p->reg_lo_s;
@@ -138,6 +179,11 @@ void orc_prox(const orc_problem *p, double *y, const double *x, double gamma) {
 }
 
 double orc_reg_value(const orc_problem *p, const double *x) {
+    if (p->reg_kind == ORC_REG_NORML1_PAIRS) {
+        double s = 0.0;
+        for (int64_t k = 0; k + 1 < p->d; k += 2) s += hypot(x[k], x[k + 1]);
+        return p->reg_lambda * s;
+    }
     if (p->reg_kind == ORC_REG_NORML1) {
         double s = 0.0;
         for (int64_t k = 0; k < p->d; ++k) s += fabs(x[k]);
@@ -745,7 +791,7 @@ void orc_gen_xtrue(int kind, int64_t d, uint64_t seed, double *x) {
  * 0.25‖a_i‖² (logistic, test_logistic_l1.jl:39) */
 double orc_max_row_sqnorm(const orc_problem *p) {
     double mx = 0.0;
-    for (int64_t i = 0; i < p->N; ++i) {
+    for (int64_t i = 0; i < p->N * (p->M > 1 ? p->M : 1); ++i) {
         const double *a = p->A + i * p->lda;
         double s = orc_dot(a, a, p->d);
         if (s > mx) mx = s;

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libciao_oracle.so")
 
 LOSS_LS, LOSS_LOGISTIC, LOSS_DIAGQUAD = 0, 1, 2
-REG_ZERO, REG_NORML1, REG_INDBOX = 0, 1, 2
+REG_ZERO, REG_NORML1, REG_INDBOX, REG_NORML1_PAIRS = 0, 1, 2, 3
 SYN_LASSO, SYN_LOGISTIC, SYN_SHARING = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -32,6 +32,7 @@ class _Problem(C.Structure):
         ("box_lo", C.c_double), ("box_hi", C.c_double), ("eta", C.c_double),
         ("reg_lambda", C.c_double), ("reg_lo", _dp), ("reg_hi", _dp),
         ("reg_lo_s", C.c_double), ("reg_hi_s", C.c_double),
+        ("M", C.c_int64),
     ]
 
 
@@ -82,9 +83,13 @@ def _i64(a):
 class Problem:
     """(1/N) Σ f_i(x) + g(x)   or   (1/N) Σ f_i(x_i) + g(Σ x_i)."""
 
-    def __init__(self, loss_kind, A, b, lam=None, *, box=(-2.0, 2.0), eta=0.0):
+    def __init__(self, loss_kind, A, b, lam=None, *, box=(-2.0, 2.0), eta=0.0, rows_per_component=1):
+        """rows_per_component = M > 1: component i is the M×d block of rows i·M … i·M+M−1 (LeastSquares / Precompose(LogisticLoss)
+        with an M×d matrix); A then has N·M rows, b N·M entries, lam N entries."""
         self.A = _f64(A)
-        self.N, self.d = self.A.shape
+        self.M = int(rows_per_component)
+        self.N, self.d = self.A.shape[0] // self.M, self.A.shape[1]
+        assert self.A.shape[0] == self.N * self.M
         self.b = _f64(b)
         self.lam = _f64(np.ones(self.N) if lam is None else np.broadcast_to(lam, (self.N,)))
         self.loss_kind = loss_kind
@@ -93,6 +98,7 @@ class Problem:
         self.p.N, self.p.d, self.p.lda = self.N, self.d, self.d
         self.p.A, self.p.b, self.p.lam = _d(self.A), _d(self.b), _d(self.lam)
         self.p.box_lo, self.p.box_hi, self.p.eta = box[0], box[1], eta
+        self.p.M = self.M
         self.set_reg(REG_ZERO)
 
     def set_reg(self, kind, lam=0.0, lo=-np.inf, hi=np.inf):

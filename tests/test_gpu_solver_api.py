@@ -82,8 +82,8 @@ def test_lasso_float32_problem_keeps_its_element_type():                        
     for solver in (S.Finito(maxit=1000, sweeping=2), S.SAGA(maxit=1000, gamma=1 / (3 * fx["L"].max())), S.Finito(maxit=1000, adaptive=True)):
         x, _ = solver(x0, F=F32, g=g, L=fx["L"].astype(np.float32), N=N, rng=HostRNG(1))
         assert x.dtype == np.float32 and fx["cost"](x.astype(np.float64)) - fx["f_star"] < 1e-3   # data rounded to single precision
-    with pytest.raises(TypeError):            # genuinely complex data is refused (complex-typed REAL data is accepted, see below)
-        S.SAGA(gamma=0.1)(x0.astype(np.complex64) + 1j, F=F32, g=g, N=N)
+    x, _ = S.SAGA(gamma=1 / (3 * fx["L"].max()), maxit=50)(x0.astype(np.complex64) + 1j, F=F32, g=g, N=N, rng=HostRNG(1))
+    assert x.dtype == np.complex64             # a complex x0 makes the problem complex: realified block path (test_gpu_blocks.py)
 
 
 def test_lasso_scalar_gamma_and_scalar_L():                                     # :128-140
@@ -228,7 +228,7 @@ def test_default_F_is_all_zero_components():                                    
 def test_lasso_complex_typed_problem(T):                                           # test_lasso.jl:3 (T = ComplexF32, ComplexF64)
     """The reference's complex Lasso problems are complex only in their element type: C = rand(R, N, n) (:19), alpha, x_star and b
     carry zero imaginary parts, so its complex arithmetic never leaves the real axis.  The engine computes on the real parts and
-    hands the solution back in the caller's type (:74 `eltype(x) == T`); data with non-zero imaginary parts is refused."""
+    hands the solution back in the caller's type (:74 `eltype(x) == T`)."""
     fx, _, g = lasso_problem()
     N = fx["N"]
     R = np.float32 if T == np.complex64 else np.float64
@@ -239,6 +239,21 @@ def test_lasso_complex_typed_problem(T):                                        
         x, _ = solver(x0, F=F, g=g, L=fx["L"].astype(R), N=N, rng=HostRNG(1))
         assert x.dtype == T and np.all(x.imag == 0)
         assert fx["cost"](x.real.astype(np.float64)) - fx["f_star"] < tol
+    # data that really leaves the real axis takes the realified block path (tests/test_gpu_blocks.py): complex solution, finite
     F[2] = ops.LeastSquares(fx["A"][2:3, :].astype(T) * (1 + 1j), fx["b"][2:3].astype(T), R(N))
-    with pytest.raises(TypeError):
-        S.SAGA(maxit=10)(x0, F=F, g=g, L=fx["L"].astype(R), N=N, rng=HostRNG(1))
+    x, _ = S.SAGA(maxit=200, gamma=1 / (6 * fx["L"].max()))(x0, F=F, g=g, N=N, rng=HostRNG(1))
+    assert x.dtype == T and np.all(np.isfinite(x)) and np.any(x.imag != 0)
+
+
+def test_lasso_with_two_rows_per_component():                                   # test_lasso.jl:52-54 with A[2i-1:2i, :] instead of A[i:i, :]
+    """LeastSquares terms that are 2×n blocks: (1/3)Σ_i (3/2)‖A_i x − b_i‖² is the same Lasso objective, so the planted optimum holds."""
+    fx, _, g = lasso_problem()
+    N, M = fx["N"] // 2, 2
+    F = [ops.LeastSquares(fx["A"][M * i:M * (i + 1), :], fx["b"][M * i:M * (i + 1)], float(N)) for i in range(N)]
+    Lc = np.array([np.linalg.norm(fx["A"][M * i:M * (i + 1), :], 2) ** 2 * N for i in range(N)])          # opnorm(tempA)^2 * N, :55
+    for solver in (S.Finito(maxit=2000, sweeping=2), S.Finito(maxit=2000, sweeping=1, LFinito=True), S.SAGA(maxit=3000),
+                   S.SVRG(gamma=1 / (7 * Lc.max()), maxit=500)):
+        x, _ = solver(fx["x0"], F=F, g=g, L=Lc, N=N, rng=HostRNG(1))
+        assert fx["cost"](x) - fx["f_star"] < TOL
+    with pytest.raises(Exception):                                              # adaptive Finito: not for block components
+        S.Finito(maxit=10, adaptive=True)(fx["x0"], F=F, g=g, L=Lc, N=N, rng=HostRNG(1))
