@@ -358,7 +358,7 @@ extern "C" int ciao_destroy(ciao_ctx *c) {
     cudaStreamSynchronize(c->stream);
     ciao_comm_destroy(c);
     free_problem(c);
-    cudaFree(c->ws); cudaFree(c->idx_raw); cudaFree(c->idx_prep); cudaFree(c->ptr_dev); cudaFree(c->err_dev); cudaFree(c->grid_bar); cudaFree(c->seq_smid);
+    cudaFree(c->ws); cudaFree(c->idx_raw); cudaFree(c->idx_prep); cudaFree(c->ptr_dev); cudaFree(c->err_dev); cudaFree(c->grid_bar); cudaFree(c->ll_buf); cudaFree(c->seq_smid);
     cudaEvent_t evs[] = {c->ev_pa, c->ev_pb, c->ev_sa, c->ev_sb, c->tm_a, c->tm_b, c->ev_pc};
     for (auto ev : evs) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -997,7 +997,17 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
             if (!sharded && c->batch_persistent && nbw > 1 && nbw < ((int64_t)1 << 22)) {   // all batches in one cooperative launch
                 const int64_t *win_dev;
                 CIAO_TRY(upload_ptr(c, win.data(), 2 * nbw, &win_dev));
-                rc = run_batch_sequence(c, BATCH_FINITO, win_dev, win_dev + nbw, nbw, longest);
+                // do rows repeat inside the call, and if so always in the same window?  (sorted by first row: equal or disjoint neighbours)
+                std::vector<std::pair<int64_t, int64_t>> ws_sorted((size_t)nbw);
+                for (int64_t j = 0; j < nbw; ++j) ws_sorted[(size_t)j] = {win[j], win[nbw + j]};
+                std::sort(ws_sorted.begin(), ws_sorted.end());
+                int windows = BATCH_WINDOWS_DISJOINT;
+                for (int64_t j = 1; j < nbw && windows != BATCH_WINDOWS_ANY; ++j) {
+                    const auto &u = ws_sorted[(size_t)j - 1], &v = ws_sorted[(size_t)j];
+                    if (u == v) windows = BATCH_WINDOWS_ALIGNED;
+                    else if (u.first + u.second > v.first) windows = BATCH_WINDOWS_ANY;
+                }
+                rc = run_batch_sequence(c, BATCH_FINITO, win_dev, win_dev + nbw, nbw, longest, windows);
                 if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
             }
             if (rc == CIAO_ERR_UNSUPPORTED)
@@ -1065,7 +1075,7 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
             const int64_t *win_dev;
             CIAO_TRY(upload_ptr(c, win.data(), 2 * n_batches, &win_dev));
             CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));          // :92 of the first batch; later ones in the kernel
-            rc = run_batch_sequence(c, BATCH_LFINITO, win_dev, win_dev + n_batches, n_batches, r);
+            rc = run_batch_sequence(c, BATCH_LFINITO, win_dev, win_dev + n_batches, n_batches, r, BATCH_WINDOWS_ANY);   // no table: irrelevant
             if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
         }
         if (rc == CIAO_ERR_UNSUPPORTED)

@@ -131,7 +131,11 @@ struct ciao_ctx {
     int *seq_smid = nullptr;           // [16] SM ids of the CTAs of the last sequential cluster kernel (ciao_last_seq_placement)
     int seq_smid_n = 0;
     int seq_cluster_pos = 0;           // which cluster of a full grid runs the sequential kernels (env CIAO_SEQ_CLUSTER_POS, calibration)
-    unsigned int *grid_bar = nullptr;  // grid barrier counter of the persistent minibatch kernel (batch.cu)
+    unsigned int *grid_bar = nullptr;  // grid barrier counter of the persistent minibatch kernel (batch.cu, CIAO_BATCH_EXCHANGE=barrier)
+    // flagged-word exchange buffers of the persistent minibatch kernel (batch.cu batch_ll_kernel): [z | Σγ̂/γ_i ×2 | CTA partials], every
+    // double stored as two 64-bit words {32 data bits, 32-bit epoch}; zeroed at allocation, the epoch keeps counting across launches
+    unsigned long long *ll_buf = nullptr;  size_t ll_bytes = 0;
+    int ll_grid = 0;  int64_t ll_d = 0;  uint32_t ll_epoch = 0;
     double *host_pin = nullptr; size_t host_pin_bytes = 0;
     // comm
     void *nccl_comm = nullptr; int rank = 0, world = 1;
@@ -215,6 +219,16 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void *gsrc)
 // the executing thread's earlier cp.async copies arrive on the mbarrier when they complete (the count was armed for it: .noinc)
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n of the executing thread's committed cp.async groups are pending (n ≤ 3 here; the operand is an immediate)
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
 }
 __device__ __forceinline__ void sts_b64(uint32_t addr, int64_t v) {
     asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");

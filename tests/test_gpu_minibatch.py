@@ -58,3 +58,74 @@ def test_lfinito_minibatch_sweep_pass(kind, N, d, batch, sweeping, launch, monke
     assert rel(e.get_vec(L.VEC_Z_FULL), ref.z_full) < 1e-9
     assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
     e.close()
+
+
+@pytest.mark.parametrize("kind,N,d,batch", [(orc.LOSS_LOGISTIC, 2100, 1024, 512), (orc.LOSS_LS, 1500, 64, 256), (orc.LOSS_LS, 1024, 4096, 256)])
+@pytest.mark.parametrize("exchange", ["words", "barrier"])
+def test_finito_minibatch_one_epoch_per_call(kind, N, d, batch, exchange, monkeypatch):
+    """One epoch per call: the windows of a call are pairwise disjoint, so the persistent kernel stages the table rows in its
+    ring (cp.async across the batch boundary; d ≤ 2048).  Three calls = three epochs against the oracle's sequential loop."""
+    monkeypatch.setenv("CIAO_BATCH_EXCHANGE", exchange)   # read at every call
+    p, e = make_rows(kind, N, d, 0xBA9 + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
+    Li = np.sum(p.A * p.A, axis=1) * (N if kind == orc.LOSS_LS else 0.25)
+    gam = 0.999 * N / Li
+    x0 = np.full(d, 0.1)
+    ref = orc.FinitoState(p, x0, gam)
+    e.finito_init(x0, gam, ref.hat_gamma)
+    sw = BatchSweeper(N, batch, 3, HostRNG(7))
+    for _ in range(3):
+        batches = sw.take(sw.d)
+        ref.steps(batches)
+        e.finito_steps(*csr(batches))
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    assert rel(e.get_table_rows(), ref.s) < 1e-9
+    e.close()
+
+
+@pytest.mark.parametrize("exchange", ["words", "barrier"])
+def test_finito_minibatch_rows_change_window(exchange, monkeypatch):
+    """Contiguous batches whose boundaries differ from pass to pass inside ONE call: a row is then handled by different CTAs,
+    and its table row written in one batch is read by another CTA a few batches later (the fenced variant of the exchange)."""
+    monkeypatch.setenv("CIAO_BATCH_EXCHANGE", exchange)
+    kind, N, d = orc.LOSS_LOGISTIC, 2304, 1024
+    p, e = make_rows(kind, N, d, 0xBAA, lam_reg=1.0 / N)
+    gam = 0.999 * N / (np.sum(p.A * p.A, axis=1) * 0.25)
+    x0 = np.full(d, 0.1)
+    ref = orc.FinitoState(p, x0, gam)
+    e.finito_init(x0, gam, ref.hat_gamma)
+    batches = []
+    for width in (256, 384, 288, 576, 256):
+        batches += [np.arange(lo + 1, min(lo + width, N) + 1, dtype=np.int64) for lo in range(0, N, width)]
+    ref.steps(batches)
+    e.finito_steps(*csr(batches))
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    assert rel(e.get_table_rows(), ref.s) < 1e-9
+    z1 = e.get_vec(L.VEC_Z)
+    e.finito_init(x0, gam, ref.hat_gamma)
+    e.finito_steps(*csr(batches))
+    assert np.array_equal(z1, e.get_vec(L.VEC_Z))
+    e.close()
+
+
+@pytest.mark.parametrize("exchange", ["words", "barrier"])
+def test_lfinito_minibatch_many_small_batches(exchange, monkeypatch):
+    """Many batches per launch (65 per sweep, 5 sweeps) with more CTAs than row groups: CTAs without rows still take part in
+    the exchange of every batch; the epoch counter of the flagged words keeps counting across the launches."""
+    monkeypatch.setenv("CIAO_BATCH_EXCHANGE", exchange)
+    kind, N, d, batch = orc.LOSS_LS, 16600, 130, 256
+    p, e = make_rows(kind, N, d, 0xBAB, lam_reg=0.05)
+    gam = 0.999 * N / (np.sum(p.A * p.A, axis=1) * N)
+    x0 = np.full(d, 0.1)
+    ref = orc.LFinitoState(p, x0, gam, batch)
+    e.lfinito_init(x0, gam, ref.hat_gamma)
+    sw = LFinitoSweeper(N, batch, 3, HostRNG(5))
+    for _ in range(5):
+        order = sw.next()
+        ref.outer(order)
+        e.lfinito_outer(order, batch)
+    assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
+    assert rel(e.get_vec(L.VEC_Z_FULL), ref.z_full) < 1e-9
+    assert rel(e.get_vec(L.VEC_AV), ref.av) < 1e-8
+    e.close()
