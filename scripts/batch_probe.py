@@ -44,20 +44,29 @@ if fn is not None and os.environ.get("CIAO_BATCH_EXCHANGE") != "barrier":   # pe
             e.finito_init(np.ones(d), gam, hat); e.finito_steps(idx, bp)
         else:
             e.lfinito_init(np.ones(d), gam, hat); e.lfinito_outer(np.arange(1, sw.d + 1), 4096)
-        out = (C.c_ulonglong * 6000)(); fn(e.h, out)
-        a = np.array(out[:], dtype=np.int64).reshape(1200, 5)
+        out = (C.c_ulonglong * 9600)(); fn(e.h, out)
+        a = np.array(out[:], dtype=np.int64).reshape(1200, 8)
         a = a[a[:, 1] > 0]
         t0 = a[:, 1].min()
         rel_ns = a[:, 1:] - t0
-        names = ["rows_start", "rows_end", "owner_done", "z_received"]
+        names = ["rows_start", "rows_end(sg0)", "owner_done", "z_received", "all_subgroups", "partial_sent", "owner_polled"]
         print(f"{mode}: {len(a)} CTAs, ns after the first CTA started the batch (min / median / max):")
         for i, n in enumerate(names):
             v = rel_ns[:, i]
-            print(f"   {n:12s} {v.min():7d} {int(np.median(v)):7d} {v.max():7d}")
+            print(f"   {n:14s} {v.min():7d} {int(np.median(v)):7d} {v.max():7d}" + (f"   owners only: {v[:128].min()} {int(np.median(v[:128]))} {v[:128].max()}" if n.startswith("owner") else ""))
         dur = rel_ns[:, 1] - rel_ns[:, 0]
         print(f"   rows duration {dur.min()} / {int(np.median(dur))} / {dur.max()} ns; by SM parity (even/odd SM id) median {int(np.median(dur[a[:,0]%2==0]))} / {int(np.median(dur[a[:,0]%2==1]))}")
         slow = np.argsort(-rel_ns[:, 1])[:12]
         print("   latest rows_end: " + ", ".join(f"cta{int(i)}@sm{int(a[i,0])}:{int(rel_ns[i,1])}" for i in slow))
         res[mode] = {"smid": a[:, 0].tolist(), "ns": rel_ns.tolist()}
+        fd = getattr(e.lib, "ciao_debug_batch_dur", None)
+        if fd is not None:
+            fd.argtypes = [C.c_void_p, C.c_void_p]
+            o2 = (C.c_uint * 4800)(); fd(e.h, o2)
+            du = np.array(o2[:], dtype=np.float64).reshape(1200, 4)[:len(a)]
+            cc = np.corrcoef(du.T)
+            print(f"   rows phase of 4 consecutive batches: per-SM correlation between batches {cc[0,1]:.2f} {cc[1,2]:.2f} {cc[2,3]:.2f} {cc[0,3]:.2f}; "
+                  f"spread (max/median) {[round(float(du[:,i].max()/np.median(du[:,i])),3) for i in range(4)]}")
+            res[mode]["dur"] = du.tolist()
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/batch_trace.json", "w"))

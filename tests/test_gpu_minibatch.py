@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kind,N,d,batch", [(orc.LOSS_LS, 1500, 64, 256), (orc.LOSS_LOGISTIC, 2100, 1024, 512),
-                                             (orc.LOSS_LS, 1024, 4096, 256), (orc.LOSS_LOGISTIC, 900, 130, 300)])
+                                             (orc.LOSS_LS, 1024, 4096, 256), (orc.LOSS_LOGISTIC, 900, 130, 300),
+                                             (orc.LOSS_LS, 6000, 64, 3000)])   # the last: several sub-groups of 32 threads per SM
 @pytest.mark.parametrize("sweeping", [2, 3])
 @pytest.mark.parametrize("launch", ["persistent", "per_batch"])
 def test_finito_static_minibatch_pass(kind, N, d, batch, sweeping, launch, monkeypatch):
@@ -38,7 +39,7 @@ def test_finito_static_minibatch_pass(kind, N, d, batch, sweeping, launch, monke
     e.close()
 
 
-@pytest.mark.parametrize("kind,N,d,batch", [(orc.LOSS_LS, 1500, 64, 256), (orc.LOSS_LOGISTIC, 2100, 1024, 700)])
+@pytest.mark.parametrize("kind,N,d,batch", [(orc.LOSS_LS, 1500, 64, 256), (orc.LOSS_LOGISTIC, 2100, 1024, 700), (orc.LOSS_LS, 6000, 64, 3000)])
 @pytest.mark.parametrize("sweeping", [2, 3])
 @pytest.mark.parametrize("launch", ["persistent", "per_batch"])
 def test_lfinito_minibatch_sweep_pass(kind, N, d, batch, sweeping, launch, monkeypatch):
