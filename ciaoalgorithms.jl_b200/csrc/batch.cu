@@ -655,6 +655,11 @@ __global__ void __launch_bounds__(256) batch_fsum_kernel(const double *rec, int6
     }
 }
 
+// (The warp sums stay on the fp64 tensor core.  A DMMA.8x8x4 occupies the sub-partition's fp64 pipe for 16 cycles against 2 for a
+// DFMA — scripts/micro/fp64_tput.cu — so the 16 DMMAs of an LFinito item are 57 % of its fp64 pipe time; replacing them by a
+// transpose-reduce with 6 double shuffles for the 4 sums of an item, and the second-stage sums by plain adds, halved the pipe
+// load and changed nothing: 12.0 vs 11.9 µs per 4096-row batch, 115 vs 112 µs per 65 536-row batch.  The row loop is bound by
+// the dependent chain of an item, not by the pipe.)
 // threads per CTA: LFinito at 4 or 8 columns per thread keeps ≤ 128 registers (4 sub-groups of 128 or 2 of 256 threads)
 template <int CPT, int MODE>
 struct BatchSmShape {
