@@ -1222,7 +1222,7 @@ static int launch_batch_sm_shape(ciao_ctx *c, BatchLArgs &a, int TS, int max_sub
     while (nsg * 2 * TS <= BatchSmShape<CPT, MODE>::MAXT && nsg * 2 <= std::min(max_sub, 4)) nsg *= 2;   // 1, 2 or 4 (the combine step)
     const size_t stage_rows = (size_t)RPG * a.ld * sizeof(double), stage_tab = (size_t)RPG * a.d_pad * sizeof(double);
     const size_t shared_part = ((size_t)((nsg > 1 ? nsg : 0) + 1 + (MODE == BATCH_LFINITO ? 1 : 0)) * a.d_pad + 17 * 33 + 1 + 5 * 32) * sizeof(double) + (size_t)nsg * 4 * sizeof(uint64_t) + 256;
-    const size_t limit = 227 * 1024 - 1024;
+    const size_t limit = 227 * 1024;   // the opt-in maximum of dynamic shared memory per CTA
     auto smem_for = [&](int S, bool stg) { return (size_t)nsg * ((size_t)S * (stage_rows + (stg ? stage_tab : 0)) + 2 * RPG * 32 * 2 * sizeof(double)) + shared_part; };
     bool stg = MODE == BATCH_FINITO && stg_ok && smem_for(S_want, true) <= limit;
     int S = S_want;
