@@ -573,12 +573,11 @@ extern "C" int ciao_debug_batch_prof(ciao_ctx *c, long long *out8) {
 // global arrival counters as a gate (8 µs), and a two-level version with groups of 8 CTAs (six hops: 6 µs).
 // Summation order: sub-groups (tree), then CTAs in a fixed order per column — bitwise reproducible run to run.
 //
-// Table rows (Finito) are staged in the same ring as the rows, by cp.async of the columns the thread itself consumes and later
-// rewrites (generic proxy, program order: no fence), STG = true, when the windows of the call are pairwise disjoint (one
-// epoch per call): the ring then prefetches rows AND table rows of the next batch across the boundary.  When windows repeat
-// inside a call the table rows are loaded at the start of the item (after the thread's own earlier stores), and when repeated
-// windows are not aligned — a row may then move to another SM — `fence` puts a __threadfence() before every store and after
-// every successful poll of the exchange (the chain partial → owner → z → reader is per column).
+// Table rows (Finito) are read and rewritten by the same thread of the same SM whenever a window repeats inside a call as the same
+// window (program order: no fence); when repeated windows are not aligned — a row may then move to another SM — `fence` puts a
+// __threadfence() before every store and after every successful poll of the exchange (the chain partial → owner → z → reader
+// is per column).  (Staging the table rows in the TMA ring with cp.async, so that the prefetch crosses the boundary, was built
+// and measured: 19.3 µs per 4096-row batch against 18.9 without, 270 against 242 µs at 65 536 rows — dropped.)
 struct BatchLArgs {
     const double *rec;
     int64_t ld, d_pad;
@@ -666,7 +665,7 @@ struct BatchSmShape {
     static constexpr int MAXT = (MODE == BATCH_LFINITO && (CPT == 4 || CPT == 8)) ? 512 : 256;
 };
 
-template <int CPT, int MODE, int LOSS, bool STG>
+template <int CPT, int MODE, int LOSS>
 __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_kernel(const BatchLArgs p) {
     constexpr int RPG = 16 / CPT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -677,7 +676,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
     const int64_t G = gridDim.x, bid = blockIdx.x;
     const int64_t VG = G * NSG, vb = (int64_t)sg * G + bid;         // virtual CTA of the item distribution
     const size_t rec_doubles = (size_t)RPG * p.ld;
-    const size_t stage_doubles = rec_doubles + (STG ? (size_t)RPG * p.d_pad : 0);
+    const size_t stage_doubles = rec_doubles;
     // shared memory: per sub-group {ring[S], red[2][RPG][32][2]}; then comb[NSG][d_pad] (sub-group partials, NSG > 1), zsm[d_pad] (z of
     // the current batch), zfs[d_pad] (z_full, LFinito), rsm[17][33], own[5][32], full[NSG][4].  z and z_full are read from
     // shared memory in every item: 32 registers less, which is what lets LFinito run 512 threads without spilling.
@@ -713,42 +712,41 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
     }
     const bool all_cols = p.d_pad == (int64_t)CPT * TS;   // every thread owns CPT valid columns
     // the sequence of (batch, group) items of this sub-group: groups vb, vb + VG, … of batch 0, then of batch 1, …
-    auto first_item = [&](int64_t &b, int64_t &g) {
-        b = 0; g = vb;
-        while (b < p.n_batches && g >= (p.b_n[b] + RPG - 1) / RPG) { ++b; g = vb; }
-    };
-    auto next_item = [&](int64_t &b, int64_t &g) {
-        g += VG;
-        while (b < p.n_batches && g >= (p.b_n[b] + RPG - 1) / RPG) { ++b; g = vb; }
-    };
-    int64_t pb, pg, issued = 0;  // producer cursor, kept by all threads: thread 0 of the sub-group drives the TMA, every thread stages its own table columns
-    auto issue = [&]() {
-        if ((STG || lt == 0) && pb < p.n_batches) {
-            const int64_t r0 = p.b_lo[pb] + pg * RPG;
-            const int rows = (int)min((int64_t)RPG, p.b_n[pb] - pg * RPG);
-            const int slot = (int)(issued % S);
-            double *dst = ring + (size_t)slot * stage_doubles;
-            if (lt == 0) {
-                const uint32_t bytes = (uint32_t)(rows * p.ld * sizeof(double));
-                mbar_arrive_expect_tx(&full[slot], bytes);
-                tma_load_1d_stream(dst, p.rec + r0 * p.ld, bytes, &full[slot], policy);
-            }
-            if (STG) {
-#pragma unroll
-                for (int r = 0; r < RPG; ++r)
-#pragma unroll
-                    for (int k = 0; k < CPT / 2; ++k)
-                        if (r < rows && col[k] >= 0)
-                            cp_async_16(smem_u32(dst + rec_doubles + (size_t)r * p.d_pad + col[k]), p.table + (r0 + r) * p.d_pad + col[k]);
-            }
-            ++issued;
-            next_item(pb, pg);
+    // Producer cursor (thread 0 of the sub-group drives the TMA): batch pb with its window (p_lo, p_n) and group count p_ng in
+    // registers, group pg, ring slot p_slot — no division and no reload of the window on the per-item path.
+    int64_t pb = -1, pg = 0, p_lo = 0, p_n = 0, p_ng = 0;
+    int p_slot = 0;
+    auto next_batch = [&]() {   // first batch after pb in which this sub-group has an item
+        for (++pb; pb < p.n_batches; ++pb) {
+            p_n = p.b_n[pb];
+            p_ng = (p_n + RPG - 1) / RPG;
+            if (vb < p_ng) { p_lo = p.b_lo[pb]; pg = vb; return; }
         }
-        if (STG) cp_async_commit();   // one group per call, empty when nothing is left: the pending count stays S − 1 at every wait
     };
-    first_item(pb, pg);
+    auto issue = [&]() {
+        if (lt == 0 && pb < p.n_batches) {
+            const int64_t r0 = p_lo + pg * RPG;
+            const int rows = (int)min((int64_t)RPG, p_n - pg * RPG);
+            const uint32_t bytes = (uint32_t)(rows * p.ld * sizeof(double));
+            mbar_arrive_expect_tx(&full[p_slot], bytes);
+            tma_load_1d_stream(ring + (size_t)p_slot * stage_doubles, p.rec + r0 * p.ld, bytes, &full[p_slot], policy);
+            p_slot = p_slot + 1 == S ? 0 : p_slot + 1;
+            pg += VG;
+            if (pg >= p_ng) next_batch();
+        }
+    };
+    if (lt == 0) next_batch();
     for (int s = 0; s < S; ++s) issue();
-    int64_t it = 0;  // items consumed so far
+    // Consumer: ring slot, its mbarrier phase, parity of the red[] buffer.  LFinito keeps them incrementally; Finito derives
+    // slot and phase from the item count with a division by the (run-time) ring depth — measured, three runs each on two GPUs
+    // (profiles/batch_exchange_r2.md §4): Finito 18.9 / 64.8 / 242 µs per batch of 4096 / 16 384 / 65 536 rows with the
+    // division against 22.2 / 80 / 306 µs without; LFinito 11.1 / 30.8 / 111.6 against 10.8 / 29.4 / 106.1.  The SASS of the two
+    // Finito builds has the same loads, barriers and stores in the same order; like the sequential kernels (profiles/
+    // seq_kernel_history_r2.md §6) the item loop is sensitive to ptxas' schedule.  Re-measure after touching this loop.
+    int64_t it = 0;
+    int c_slot = 0;
+    uint32_t c_phase = 0;
+    int par = 0;
 
     // owner role: CTA c owns the RC columns RC·c … of av and z (a whole number of 32-byte sectors), for the whole call
     const int RC = p.red_cols, NS = Tall / RC, Wn = Tall >> 5;
@@ -779,9 +777,8 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
         for (int e = 0; e < CPT; ++e) acc[e] = 0.0;
         const int64_t lo_b = p.b_lo[b], n_b = p.b_n[b], ng_b = (n_b + RPG - 1) / RPG;
         for (int64_t cg = vb; cg < ng_b; cg += VG) {
-            const int slot = (int)(it % S);
-            const uint32_t parity = (uint32_t)((it / S) & 1);
-            const int par = (int)(it & 1);
+            const int slot = MODE == BATCH_FINITO ? (int)(it % S) : c_slot;
+            const uint32_t parity = MODE == BATCH_FINITO ? (uint32_t)((it / S) & 1) : c_phase;
             const int64_t r0 = lo_b + cg * RPG;
             const int rows = (int)min((int64_t)RPG, n_b - cg * RPG);
             const double *sp = ring + (size_t)slot * stage_doubles;
@@ -789,7 +786,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
             auto item = [&](auto full_tag) {
                 constexpr bool FULL = decltype(full_tag)::value;
                 double2 so[RPG][CPT / 2];
-                if (MODE == BATCH_FINITO && !STG) {
+                if (MODE == BATCH_FINITO) {   // old table rows: plain loads, issued before the wait so that they overlap it
 #pragma unroll
                     for (int r = 0; r < RPG; ++r)
 #pragma unroll
@@ -809,7 +806,6 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                         zfr[2 * k] = fv.x; zfr[2 * k + 1] = fv.y;
                     }
                 }
-                if (STG) cp_async_wait_pending(S - 1);
                 mbar_wait(&full[slot], parity);
                 double a[RPG][CPT], p0[RPG], p1[RPG], tb[RPG], tl[RPG], tgn[RPG], thg[RPG];
 #pragma unroll
@@ -829,10 +825,6 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                             p1[r] = fma(v.x, zfr[2 * k], p1[r]);
                             p1[r] = fma(v.y, zfr[2 * k + 1], p1[r]);
                         }
-                        if (MODE == BATCH_FINITO && STG)   // the thread's own cp.async data: visible to it after the wait
-                            so[r][k] = (FULL || (rv && col[k] >= 0))
-                                           ? *reinterpret_cast<const double2 *>(sp + rec_doubles + (size_t)r * p.d_pad + col[k])
-                                           : make_double2(0.0, 0.0);
                     }
                     tb[r] = rv ? rp[p.d_pad + TAIL_B] : 0.0;
                     tl[r] = rv ? rp[p.d_pad + TAIL_LAM] : 0.0;
@@ -886,6 +878,8 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
             };
             if (all_cols && rows == RPG) item(std::true_type{});
             else item(std::false_type{});
+            par ^= 1;
+            if (++c_slot == S) { c_slot = 0; c_phase ^= 1u; }
             ++it;
         }
         // ---- close the batch ----
@@ -1016,7 +1010,6 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
         BPROF_ADD(3, t_4, t_5);
         BTRACE(4);
     }
-    if (STG) cp_async_wait_pending(0);
 #ifdef CIAO_SEQ_PROFILE
     if (tid == 0 && bid < 1200) {
         unsigned int sm;
@@ -1160,9 +1153,9 @@ static int launch_batch_persistent_loss(ciao_ctx *c, BatchPArgs &a, int T, size_
 }
 
 // the one-CTA-per-SM version: sub-groups instead of CTAs per SM; the exchange buffers live in the context (zeroed when (re)allocated)
-template <int CPT, int MODE, int LOSS, bool STG>
+template <int CPT, int MODE, int LOSS>
 static int launch_batch_sm(ciao_ctx *c, BatchLArgs &a, int TS, int nsg, size_t smem) {
-    auto kern = batch_sm_kernel<CPT, MODE, LOSS, STG>;
+    auto kern = batch_sm_kernel<CPT, MODE, LOSS>;
     static size_t configured[CIAO_MAX_DEVICES] = {};
     if (smem > configured[c->device % CIAO_MAX_DEVICES]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1214,31 +1207,27 @@ static int launch_batch_sm(ciao_ctx *c, BatchLArgs &a, int TS, int nsg, size_t s
     CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Tall), args, smem, c->stream));
     return CIAO_OK;
 }
-// shape of the launch: sub-groups, ring depth, whether the table rows are staged; then the instantiation
+// shape of the launch: sub-groups, ring depth; then the instantiation
 template <int CPT, int MODE>
-static int launch_batch_sm_shape(ciao_ctx *c, BatchLArgs &a, int TS, int max_sub, int S_want, bool stg_ok) {
+static int launch_batch_sm_shape(ciao_ctx *c, BatchLArgs &a, int TS, int max_sub, int S_want) {
     constexpr int RPG = 16 / CPT;
     int nsg = 1;
     while (nsg * 2 * TS <= BatchSmShape<CPT, MODE>::MAXT && nsg * 2 <= std::min(max_sub, 4)) nsg *= 2;   // 1, 2 or 4 (the combine step)
-    const size_t stage_rows = (size_t)RPG * a.ld * sizeof(double), stage_tab = (size_t)RPG * a.d_pad * sizeof(double);
+    const size_t stage_rows = (size_t)RPG * a.ld * sizeof(double);
     const size_t shared_part = ((size_t)((nsg > 1 ? nsg : 0) + 1 + (MODE == BATCH_LFINITO ? 1 : 0)) * a.d_pad + 17 * 33 + 1 + 5 * 32) * sizeof(double) + (size_t)nsg * 4 * sizeof(uint64_t) + 256;
     const size_t limit = 227 * 1024;   // the opt-in maximum of dynamic shared memory per CTA
-    auto smem_for = [&](int S, bool stg) { return (size_t)nsg * ((size_t)S * (stage_rows + (stg ? stage_tab : 0)) + 2 * RPG * 32 * 2 * sizeof(double)) + shared_part; };
-    bool stg = MODE == BATCH_FINITO && stg_ok && smem_for(S_want, true) <= limit;
+    auto smem_for = [&](int S) { return (size_t)nsg * ((size_t)S * stage_rows + 2 * RPG * 32 * 2 * sizeof(double)) + shared_part; };
     int S = S_want;
-    while (S > 1 && smem_for(S, stg) > limit) --S;
+    while (S > 1 && smem_for(S) > limit) --S;
     a.stages = S;
-    const size_t smem = smem_for(S, stg);
-    if (MODE == BATCH_FINITO && stg)
-        return c->loss_kind == CIAO_LOSS_LS ? launch_batch_sm<CPT, MODE, CIAO_LOSS_LS, MODE == BATCH_FINITO>(c, a, TS, nsg, smem)
-                                            : launch_batch_sm<CPT, MODE, CIAO_LOSS_LOGISTIC, MODE == BATCH_FINITO>(c, a, TS, nsg, smem);
-    return c->loss_kind == CIAO_LOSS_LS ? launch_batch_sm<CPT, MODE, CIAO_LOSS_LS, false>(c, a, TS, nsg, smem)
-                                        : launch_batch_sm<CPT, MODE, CIAO_LOSS_LOGISTIC, false>(c, a, TS, nsg, smem);
+    const size_t smem = smem_for(S);
+    return c->loss_kind == CIAO_LOSS_LS ? launch_batch_sm<CPT, MODE, CIAO_LOSS_LS>(c, a, TS, nsg, smem)
+                                        : launch_batch_sm<CPT, MODE, CIAO_LOSS_LOGISTIC>(c, a, TS, nsg, smem);
 }
 
 // b_lo_dev / b_n_dev: device arrays (n_batches) of batch windows; z (and z_full for LFinito) as the first batch needs them
 // windows: BATCH_WINDOWS_DISJOINT (no row twice in the call), _ALIGNED (windows repeat, always as the same window: a row stays with
-// its CTA and thread) or _ANY (a row may move between CTAs: the exchange is bracketed by fences)
+// its SM and thread) or _ANY (a row may move between SMs: the exchange is bracketed by fences)
 int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int64_t *b_n_dev, int64_t n_batches, int64_t batch_rows,
                        int windows) {
     NvtxRange nvtx("ciao:minibatch:persistent");
@@ -1269,10 +1258,6 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     bool barrier_version = false;
     if (const char *xv = getenv("CIAO_BATCH_EXCHANGE")) barrier_version = !strcmp(xv, "barrier");
     if (!barrier_version) {
-        // table rows staged in the ring (Finito, one epoch per call) when the deeper stage still gives the full ring depth
-        // (batches of 512 rows: 7.0 µs with the staged table rows against 6.2 without — one item per sub-group, nothing to prefetch)
-        bool stg_ok = mode == BATCH_FINITO && windows == BATCH_WINDOWS_DISJOINT && batch_rows >= 2048;
-        if (const char *gv = getenv("CIAO_BATCH_STAGE_TABLE")) stg_ok = stg_ok && atoi(gv) != 0;
         // LFinito's row loop is bound by fp64 issue, not by the ring: two stages measured faster than three (12.9 vs 13.5 µs per batch)
         const int S_ll = (mode == BATCH_LFINITO && !getenv("CIAO_BATCH_STAGES")) ? 2 : S_want;
         BatchLArgs a;
@@ -1284,17 +1269,17 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
         int rc;
         if (mode == BATCH_FINITO) {
             switch (cpt) {
-                case 2: rc = launch_batch_sm_shape<2, BATCH_FINITO>(c, a, T, max_ctas, S_want, stg_ok); break;
-                case 4: rc = launch_batch_sm_shape<4, BATCH_FINITO>(c, a, T, max_ctas, S_want, stg_ok); break;
-                case 8: rc = launch_batch_sm_shape<8, BATCH_FINITO>(c, a, T, max_ctas, S_want, stg_ok); break;
-                default: rc = launch_batch_sm_shape<16, BATCH_FINITO>(c, a, T, max_ctas, S_want, stg_ok); break;
+                case 2: rc = launch_batch_sm_shape<2, BATCH_FINITO>(c, a, T, max_ctas, S_want); break;
+                case 4: rc = launch_batch_sm_shape<4, BATCH_FINITO>(c, a, T, max_ctas, S_want); break;
+                case 8: rc = launch_batch_sm_shape<8, BATCH_FINITO>(c, a, T, max_ctas, S_want); break;
+                default: rc = launch_batch_sm_shape<16, BATCH_FINITO>(c, a, T, max_ctas, S_want); break;
             }
         } else {
             switch (cpt) {
-                case 2: rc = launch_batch_sm_shape<2, BATCH_LFINITO>(c, a, T, max_ctas, S_ll, false); break;
-                case 4: rc = launch_batch_sm_shape<4, BATCH_LFINITO>(c, a, T, max_ctas, S_ll, false); break;
-                case 8: rc = launch_batch_sm_shape<8, BATCH_LFINITO>(c, a, T, max_ctas, S_ll, false); break;
-                default: rc = launch_batch_sm_shape<16, BATCH_LFINITO>(c, a, T, max_ctas, S_ll, false); break;
+                case 2: rc = launch_batch_sm_shape<2, BATCH_LFINITO>(c, a, T, max_ctas, S_ll); break;
+                case 4: rc = launch_batch_sm_shape<4, BATCH_LFINITO>(c, a, T, max_ctas, S_ll); break;
+                case 8: rc = launch_batch_sm_shape<8, BATCH_LFINITO>(c, a, T, max_ctas, S_ll); break;
+                default: rc = launch_batch_sm_shape<16, BATCH_LFINITO>(c, a, T, max_ctas, S_ll); break;
             }
         }
         CIAO_TRY(rc);

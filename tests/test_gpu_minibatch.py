@@ -62,11 +62,11 @@ def test_lfinito_minibatch_sweep_pass(kind, N, d, batch, sweeping, launch, monke
 
 
 @pytest.mark.parametrize("kind,N,d,batch", [(orc.LOSS_LOGISTIC, 2100, 1024, 512), (orc.LOSS_LS, 1500, 64, 256), (orc.LOSS_LS, 1024, 4096, 256),
-                                             (orc.LOSS_LOGISTIC, 4500, 1024, 2200), (orc.LOSS_LS, 4500, 256, 2100)])   # ≥ 2048 rows: staged table rows
+                                             (orc.LOSS_LOGISTIC, 4500, 1024, 2200), (orc.LOSS_LS, 4500, 256, 2100)])
 @pytest.mark.parametrize("exchange", ["words", "barrier"])
 def test_finito_minibatch_one_epoch_per_call(kind, N, d, batch, exchange, monkeypatch):
-    """One epoch per call: the windows of a call are pairwise disjoint, so for batches of ≥ 2048 rows the persistent kernel stages
-    the table rows in its ring (cp.async across the batch boundary).  Three calls = three epochs against the oracle's loop."""
+    """One epoch per call (the windows of a call are pairwise disjoint; the epoch counter of the exchange keeps counting across the
+    launches).  Three calls = three epochs against the oracle's sequential loop."""
     monkeypatch.setenv("CIAO_BATCH_EXCHANGE", exchange)   # read at every call
     p, e = make_rows(kind, N, d, 0xBA9 + d, lam_reg=0.05 if kind == orc.LOSS_LS else 1.0 / N)
     Li = np.sum(p.A * p.A, axis=1) * (N if kind == orc.LOSS_LS else 0.25)
