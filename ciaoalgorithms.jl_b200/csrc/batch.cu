@@ -577,7 +577,8 @@ extern "C" int ciao_debug_batch_prof(ciao_ctx *c, long long *out8) {
 // window (program order: no fence); when repeated windows are not aligned — a row may then move to another SM — `fence` puts a
 // __threadfence() before every store and after every successful poll of the exchange (the chain partial → owner → z → reader
 // is per column).  (Staging the table rows in the TMA ring with cp.async, so that the prefetch crosses the boundary, was built
-// and measured: 19.3 µs per 4096-row batch against 18.9 without, 270 against 242 µs at 65 536 rows — dropped.)
+// and measured: 19.3 µs per 4096-row batch against 18.9 without, 270 against 242 µs at 65 536 rows — dropped; so was an L2
+// prefetch of the item's table rows issued together with its TMA copy: 18.8 / 262 µs.)
 struct BatchLArgs {
     const double *rec;
     int64_t ld, d_pad;
