@@ -994,9 +994,16 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
                 if (batch_ptr[j + 1] > batch_ptr[j]) win.push_back(batch_ptr[j + 1] - batch_ptr[j]);
             CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
             int rc = CIAO_ERR_UNSUPPORTED;
-            if (!sharded && c->batch_persistent && nbw > 1 && nbw < ((int64_t)1 << 22)) {   // all batches in one cooperative launch
+            if ((!sharded || (c->p2p_ready && c->world > 1)) && c->batch_persistent && nbw > 1 && nbw < ((int64_t)1 << 22)) {   // all batches in one cooperative launch
+                std::vector<int64_t> loc(win);   // row shards: the part of every window this context holds, in local row numbers
+                if (sharded)
+                    for (int64_t j = 0; j < nbw; ++j) {
+                        const int64_t lo = std::max(win[j], c->row0), hi = std::min(win[j] + win[nbw + j], c->row0 + c->n_rows);
+                        loc[j] = std::max<int64_t>(0, lo - c->row0);
+                        loc[nbw + j] = std::max<int64_t>(0, hi - lo);
+                    }
                 const int64_t *win_dev;
-                CIAO_TRY(upload_ptr(c, win.data(), 2 * nbw, &win_dev));
+                CIAO_TRY(upload_ptr(c, loc.data(), 2 * nbw, &win_dev));
                 // do rows repeat inside the call, and if so always in the same window?  (sorted by first row: equal or disjoint neighbours)
                 std::vector<std::pair<int64_t, int64_t>> ws_sorted((size_t)nbw);
                 for (int64_t j = 0; j < nbw; ++j) ws_sorted[(size_t)j] = {win[j], win[nbw + j]};
@@ -1007,7 +1014,7 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
                     if (u == v) windows = BATCH_WINDOWS_ALIGNED;
                     else if (u.first + u.second > v.first) windows = BATCH_WINDOWS_ANY;
                 }
-                rc = run_batch_sequence(c, BATCH_FINITO, win_dev, win_dev + nbw, nbw, longest, windows);
+                rc = run_batch_sequence(c, BATCH_FINITO, win_dev, win_dev + nbw, nbw, longest, windows, sharded);
                 if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
             }
             if (rc == CIAO_ERR_UNSUPPORTED)
@@ -1066,16 +1073,21 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
     if (r >= BATCH_MIN_ROWS && (!sharded || c->world > 1) && !use_block_kernel(c)) {  // minibatch sweep: prox + one streaming pass per batch (:91-100)
         CUDA_TRY(cudaEventRecord(c->ev_sa, c->stream));
         int rc = CIAO_ERR_UNSUPPORTED;
-        if (!sharded && c->batch_persistent && n_batches > 1 && n_batches < ((int64_t)1 << 22)) {  // the whole sweep in one cooperative launch
+        if ((!sharded || c->p2p_ready) && c->batch_persistent && n_batches > 1 && n_batches < ((int64_t)1 << 22)) {  // the whole sweep in one cooperative launch
             std::vector<int64_t> win((size_t)2 * n_batches);
             for (int64_t jj = 0; jj < n_batches; ++jj) {
                 win[jj] = r * (order[jj] - 1);
                 win[n_batches + jj] = (order[jj] == nb) ? last_len : r;
+                if (sharded) {   // the part of the window this context holds, in local row numbers
+                    const int64_t lo = std::max(win[jj], c->row0), hi = std::min(win[jj] + win[n_batches + jj], c->row0 + c->n_rows);
+                    win[jj] = std::max<int64_t>(0, lo - c->row0);
+                    win[n_batches + jj] = std::max<int64_t>(0, hi - lo);
+                }
             }
             const int64_t *win_dev;
             CIAO_TRY(upload_ptr(c, win.data(), 2 * n_batches, &win_dev));
             CIAO_TRY(prox_vec(c, CIAO_VEC_AV, CIAO_VEC_Z, c->hat_gamma));          // :92 of the first batch; later ones in the kernel
-            rc = run_batch_sequence(c, BATCH_LFINITO, win_dev, win_dev + n_batches, n_batches, r, BATCH_WINDOWS_ANY);   // no table: irrelevant
+            rc = run_batch_sequence(c, BATCH_LFINITO, win_dev, win_dev + n_batches, n_batches, r, BATCH_WINDOWS_ANY, sharded);   // no table: the window kind is irrelevant
             if (rc != CIAO_OK && rc != CIAO_ERR_UNSUPPORTED) return rc;
         }
         if (rc == CIAO_ERR_UNSUPPORTED)

@@ -597,6 +597,11 @@ struct BatchLArgs {
     int stages;
     int red_cols;
     int ts, nsg;                // threads per sub-group, sub-groups per CTA
+    // row shards (one process per GPU): the owners of a column on the `world` ranks exchange their rank sums through the peer
+    // arenas (flagged words, system scope) and add them in rank order, so every rank forms the same av and z
+    int world, rank;
+    unsigned long long *xw[CIAO_MAX_PEERS];   // every rank's flagged-word area as addressed from this GPU (own entry: local)
+    uint32_t xepoch0;
 };
 
 __device__ __forceinline__ void ll_store(unsigned long long *p, double v, uint32_t flag) {
@@ -617,6 +622,16 @@ __device__ __forceinline__ bool ll_load(const unsigned long long *p, uint32_t fl
 #else
 #define LL_BACKOFF()
 #endif
+__device__ __forceinline__ void ll_store_sys(unsigned long long *p, double v, uint32_t flag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), f = (unsigned long long)flag << 32;
+    asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | f), "l"((b >> 32) | f) : "memory");
+}
+__device__ __forceinline__ bool ll_load_sys(const unsigned long long *p, uint32_t flag, double &v) {
+    unsigned long long lo, hi;
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    v = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+    return (uint32_t)(lo >> 32) == flag && (uint32_t)(hi >> 32) == flag;
+}
 __device__ __forceinline__ void bar_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // profile build: g_batch_prof = cycles of CTA 0, thread 0 in [rows, combine + partial write, owner: poll + sum + update, z poll];
@@ -963,7 +978,31 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                     t0 += rsm[w * 33 + tid]; t1 += rsm[(w + 1) * 33 + tid];
                     t2 += rsm[(w + 2) * 33 + tid]; t3 += rsm[(w + 3) * 33 + tid];
                 }
-                double anew = __dadd_rn(own[tid], (t0 + t1) + (t2 + t3));
+                double tsum = (t0 + t1) + (t2 + t3);
+                if (p.world > 1) {
+                    // row shards: this rank's sum of the column goes to the same owner thread on every rank (one flagged word per
+                    // peer over NVLink, one buffer per batch parity: a rank is at most one batch ahead of its slowest peer), and
+                    // the sums of all ranks are added in rank order — the same bits on every rank
+                    const uint32_t epx = p.xepoch0 + (uint32_t)b + 1u;
+                    const size_t slot = ((size_t)(b & 1) * CIAO_MAX_PEERS + p.rank) * P2P_CAP + j_own;
+                    for (int q = 0; q < p.world; ++q) ll_store_sys(p.xw[q] + slot * 2, tsum, epx);
+                    const unsigned long long *mine = p.xw[p.rank] + ((size_t)(b & 1) * CIAO_MAX_PEERS * P2P_CAP + j_own) * 2;
+                    double v[CIAO_MAX_PEERS];
+                    for (int spins = 0;; ++spins) {
+                        bool ok = true;
+#pragma unroll
+                        for (int q = 0; q < CIAO_MAX_PEERS; ++q) {
+                            v[q] = 0.0;
+                            if (q < p.world) ok &= ll_load_sys(mine + (size_t)q * P2P_CAP * 2, epx, v[q]);
+                        }
+                        if (ok) break;
+                        if (spins > LL_SPIN_LIMIT) __trap();
+                    }
+                    tsum = 0.0;
+#pragma unroll
+                    for (int q = 0; q < CIAO_MAX_PEERS; ++q) tsum += v[q];   // entries ≥ world are zero
+                }
+                double anew = __dadd_rn(own[tid], tsum);
                 bool new_z = true;
                 if (MODE == BATCH_LFINITO) {
                     anew = __dadd_rn(anew, __dmul_rn(bfs_b, __dsub_rn(own[32 + tid], own[64 + tid])));   // Finito_LFinito.jl:98
@@ -1200,10 +1239,19 @@ static int launch_batch_sm(ciao_ctx *c, BatchLArgs &a, int TS, int nsg, size_t s
         batch_fsum_kernel<<<(unsigned)a.n_batches, 256, 0, c->stream>>>(a.rec, a.ld, a.d_pad, a.b_lo, a.b_n, c->ws);
         CUDA_TRY(cudaGetLastError());
         c->timing.launches += 1;
+        if (a.world > 1)   // the batch's rows are spread over the ranks: rank-ordered sums of the per-rank parts
+            for (int64_t o = 0; o < a.n_batches; o += P2P_CAP)
+                CIAO_TRY(run_p2p_allreduce(c, c->ws + o, std::min<int64_t>(P2P_CAP, a.n_batches - o), 0));
         a.bfs = c->ws;
     }
     a.epoch0 = c->ll_epoch;
     c->ll_epoch += (uint32_t)a.n_batches;
+    if (a.world > 1) {   // collective: all ranks launch the same sequence of batches
+        for (int q = 0; q < a.world; ++q)
+            a.xw[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(c->p2p_peer[q]) + P2P_LL_OFFSET);
+        a.xepoch0 = c->p2p_ll_epoch;
+        c->p2p_ll_epoch += (uint32_t)a.n_batches;
+    }
     void *args[] = {(void *)&a};
     CUDA_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(Tall), args, smem, c->stream));
     return CIAO_OK;
@@ -1229,8 +1277,10 @@ static int launch_batch_sm_shape(ciao_ctx *c, BatchLArgs &a, int TS, int max_sub
 // b_lo_dev / b_n_dev: device arrays (n_batches) of batch windows; z (and z_full for LFinito) as the first batch needs them
 // windows: BATCH_WINDOWS_DISJOINT (no row twice in the call), _ALIGNED (windows repeat, always as the same window: a row stays with
 // its SM and thread) or _ANY (a row may move between SMs: the exchange is bracketed by fences)
+// Row shards: b_lo / b_n are the parts of the windows this context holds (local row numbers, possibly empty), batch_rows the
+// length of the whole batch, and the call is collective (every rank launches the same batches; needs the peer exchange).
 int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int64_t *b_n_dev, int64_t n_batches, int64_t batch_rows,
-                       int windows) {
+                       int windows, bool sharded = false) {
     NvtxRange nvtx("ciao:minibatch:persistent");
     if (n_batches <= 0) return CIAO_OK;
     const int64_t d_pad = c->d_pad;
@@ -1258,6 +1308,10 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     const size_t smem = (size_t)S * stage_bytes + fixed;
     bool barrier_version = false;
     if (const char *xv = getenv("CIAO_BATCH_EXCHANGE")) barrier_version = !strcmp(xv, "barrier");
+    if (sharded) {
+        if (!c->p2p_ready || c->world < 2) return CIAO_ERR_UNSUPPORTED;   // the caller falls back to one pass + tail kernel per batch
+        barrier_version = false;
+    }
     if (!barrier_version) {
         // LFinito's row loop is bound by fp64 issue, not by the ring: two stages measured faster than three (12.9 vs 13.5 µs per batch)
         const int S_ll = (mode == BATCH_LFINITO && !getenv("CIAO_BATCH_STAGES")) ? 2 : S_want;
@@ -1267,6 +1321,8 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
         a.z = ctx_vec(c, CIAO_VEC_Z); a.av = ctx_vec(c, CIAO_VEC_AV); a.zf = ctx_vec(c, CIAO_VEC_Z_FULL);
         a.cN = c->hat_gamma / (double)c->N_total; a.hat_gamma = c->hat_gamma; a.reg = c->reg;
         a.fence = (mode == BATCH_FINITO && windows == BATCH_WINDOWS_ANY) ? 1 : 0;
+        a.world = sharded ? c->world : 1;
+        a.rank = c->rank;
         int rc;
         if (mode == BATCH_FINITO) {
             switch (cpt) {

@@ -205,4 +205,5 @@ void ciao_comm_destroy(ciao_ctx *c) {
     if (c->p2p_arena) cudaFree(c->p2p_arena);
     c->p2p_arena = nullptr;
     c->p2p_seq = 0;
+    c->p2p_ll_epoch = 0;
 }

@@ -66,7 +66,11 @@ struct PeerTable {
 #define P2P_CAP 8224                           // d_pad ≤ 8192 columns + the scalar, padded to a multiple of 32
 #define P2P_CHUNKS (P2P_CAP / 32)
 #define P2P_MAIL_DOUBLES ((size_t)2 * CIAO_MAX_PEERS * P2P_CAP)
-#define P2P_ARENA_BYTES (P2P_MAIL_DOUBLES * 8 + (size_t)CIAO_MAX_PEERS * P2P_CHUNKS * 4 + 256)
+// … then, 256-byte aligned, the flagged-word area of the persistent minibatch kernel on row shards (batch.cu): xw[2][CIAO_MAX_PEERS]
+// [P2P_CAP] doubles as two 64-bit words {32 data bits | 32-bit epoch} each, double-buffered by batch parity
+#define P2P_LL_OFFSET ((P2P_MAIL_DOUBLES * 8 + (size_t)CIAO_MAX_PEERS * P2P_CHUNKS * 4 + 255) / 256 * 256)
+#define P2P_LL_WORDS ((size_t)2 * CIAO_MAX_PEERS * P2P_CAP * 2)
+#define P2P_ARENA_BYTES (P2P_LL_OFFSET + P2P_LL_WORDS * 8 + 256)
 
 struct RegParams {
     int kind;
@@ -148,6 +152,7 @@ struct ciao_ctx {
     void *p2p_mapped[CIAO_MAX_PEERS] = {};     // cudaIpcOpenMemHandle results to close
     bool p2p_ready = false;
     uint32_t p2p_seq = 0;                      // collectives issued so far (all ranks in lock step)
+    uint32_t p2p_ll_epoch = 0;                 // batches exchanged so far by the persistent minibatch kernel (all ranks in lock step)
     uint64_t p2p_timeout_ns = 20000000000ull;  // a peer that never shows up ends the wait with CIAO_ERR_COMM, not a hang
     // tuning
     int pass_threads = 0, pass_stages = 0, pass_ctas = 0, seq_cluster = 0, seq_threads = 0;
