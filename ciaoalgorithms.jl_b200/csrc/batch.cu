@@ -550,14 +550,14 @@ extern "C" int ciao_debug_batch_prof(ciao_ctx *c, long long *out8) {
 // The persistent kernel with ONE CTA PER SM and the batch boundary as a flagged-word exchange (default; the grid-barrier
 // version above stays selectable with CIAO_BATCH_EXCHANGE=barrier).
 //
-// What was wrong with the barrier version (profiles/ncu_lfinito_batch_r2.csv, warp samples, LFinito, batch 4096, 592 CTAs):
+// What was wrong with the barrier version (profiles/ncu_lfinito_batch_barrier_r2.csv, warp samples, LFinito, batch 4096, 592 CTAs):
 // 32 % of the warp time in the row loop, 20 % waiting in grid barrier 1, 14 % in the reduction, 25 % in grid barrier 2, 9 %
 // reloading z.  The boundary is a chain of dependent L2 hops (≈ 0.6 µs each when 300–600 CTAs poll), two fences, and 2·G atomics
 // on one address.  Three changes:
 //
 // * One exchange participant per SM.  The CTA has NSG sub-groups of TS threads (what used to be 2–4 CTAs per SM); a sub-group
 //   walks its own items with its own TMA ring and named barrier, exactly like a CTA of the old kernel with the virtual id
-//   sg·G + bid.  At the end of a batch the sub-groups' partial vectors are added through shared memory (fixed tree), so the
+//   sg·G + bid.  At the end of a batch the sub-groups' partial vectors are added through shared memory (fixed order), so the
 //   grid exchanges G = #SMs partials instead of 2–4 times as many, and z is fetched once per SM.
 // * Data carries its own readiness.  A double travels as two 64-bit words {32 data bits | 32-bit epoch} (the layout of NCCL's LL
 //   protocol), written with one relaxed 16-byte store and read with one relaxed 16-byte load; a 64-bit word cannot tear, so a
@@ -571,7 +571,7 @@ extern "C" int ciao_debug_batch_prof(ciao_ctx *c, long long *out8) {
 // Tried and dropped (profiles/batch_exchange_r2.md): the same exchange between 2–4 CTAs per SM (every owner polls 592 partials,
 // every CTA polls z: the polls serialise in a few L2 slices, the slowest owner finished 8–11 µs after the last partial), 16
 // global arrival counters as a gate (8 µs), and a two-level version with groups of 8 CTAs (six hops: 6 µs).
-// Summation order: sub-groups (tree), then CTAs in a fixed order per column — bitwise reproducible run to run.
+// Summation order: sub-groups, then CTAs (then ranks) in a fixed order per column — bitwise reproducible run to run.
 //
 // Table rows (Finito) are read and rewritten by the same thread of the same SM whenever a window repeats inside a call as the same
 // window (program order: no fence); when repeated windows are not aligned — a row may then move to another SM — `fence` puts a
@@ -915,6 +915,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                 if (col[k] >= 0) *reinterpret_cast<double2 *>(dst + col[k]) = make_double2(acc[2 * k], acc[2 * k + 1]);
             __syncthreads();
             BTRACE(5);
+            if (p.fence) __threadfence();   // the storing thread's own fence, after the barrier that ordered the sub-groups' table stores before it
             for (int64_t c = 2 * (int64_t)tid; c < p.d_pad; c += 2 * (int64_t)Tall) {
                 double2 v0 = *reinterpret_cast<const double2 *>(comb + c);
                 const double2 v1 = *reinterpret_cast<const double2 *>(comb + p.d_pad + c);
