@@ -45,6 +45,7 @@ SIGNATURES = {
     "ciao_sync": (i32, [_ctx]),
     "ciao_set_rows": (i32, [_ctx, i32, i64, i64, i64, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, f64]),
     "ciao_set_row_blocks": (i32, [_ctx, i32, i64, i64, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p, f64]),
+    "ciao_set_row_interleave": (i32, [_ctx, i64, i32, i32]),
     "ciao_set_blocks": (i32, [_ctx, i64, i64, C.c_void_p, i64, C.c_void_p, i64, f64, f64, f64]),
     "ciao_set_reg": (i32, [_ctx, i32, C.c_void_p, i64]),
     "ciao_gen_synthetic": (i32, [_ctx, i32, i64, i64, i64, i64, C.c_uint64, f64]),

@@ -93,11 +93,11 @@ __global__ void pack_tails_kernel(double *rec, int64_t n_rows, int64_t d_pad, in
     for (int k = 2; k < CIAO_TAIL; ++k) t[k] = 0.0;
 }
 __global__ void set_gamma_tail_kernel(double *rec, int64_t n_rows, int64_t d_pad, int64_t ld, const double *gam, double Nd,
-                                      double hat_gamma) {
+                                      double hat_gamma, int64_t il_block, int il_rank, int il_world) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_rows) return;
     double *t = rec + i * ld + d_pad;
-    const double g = gam[i];
+    const double g = gam[il_block ? il_global(i, il_block, il_rank, il_world) : i];   // gam: first row of a contiguous shard, or all N
     t[TAIL_GAM] = g;
     t[TAIL_GAM_N] = __ddiv_rn(g, Nd);
     t[TAIL_HAT_GAM] = __ddiv_rn(hat_gamma, g);
@@ -287,8 +287,9 @@ static int set_gammas(ciao_ctx *c, const double *gamma_N, bool tails) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
     if (tails && c->M == 1) {   // block components read γ_i from gamma_dev (blockseq.cu)
-        set_gamma_tail_kernel<<<blocks_for(c->n_rows), 256, 0, c->stream>>>(c->rec, c->n_rows, c->d_pad, c->ld, c->gamma_dev + c->row0,
-                                                                             (double)c->N_total, c->hat_gamma);  // γ of MY rows
+        set_gamma_tail_kernel<<<blocks_for(c->n_rows), 256, 0, c->stream>>>(c->rec, c->n_rows, c->d_pad, c->ld,
+                                                                             c->gamma_dev + (c->il_block ? 0 : c->row0), (double)c->N_total,
+                                                                             c->hat_gamma, c->il_block, c->il_rank, c->il_world);  // γ of MY rows
         CUDA_TRY(cudaGetLastError());
         c->timing.launches += 1;
     }
@@ -410,6 +411,7 @@ extern "C" int ciao_rows_ipc_handle(ciao_ctx *c, void *out64) {
 extern "C" int ciao_attach_peer_rows(ciao_ctx *c, int n_shards, const void *handles64, const int64_t *row0, const int64_t *n_rows,
                                      int my_shard) {
     if (!c || !handles64 || !row0 || !n_rows) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_attach_peer_rows: null argument");
+    if (c->il_block) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "ciao_attach_peer_rows: remote rows are for contiguous shards (interleaved shards serve minibatches and passes)");
     if (n_shards < 1 || n_shards > CIAO_MAX_PEERS || my_shard < 0 || my_shard >= n_shards)
         CIAO_FAIL(CIAO_ERR_INVALID, "ciao_attach_peer_rows: 1..%d shards, my_shard inside", CIAO_MAX_PEERS);
     if (!c->rec) CIAO_FAIL(CIAO_ERR_STATE, "ciao_attach_peer_rows: no row problem set");
@@ -529,6 +531,7 @@ static int upload_rows(ciao_ctx *c, const double *A, int64_t lda, int64_t n_rows
     return rc;
 }
 
+static int check_interleave(ciao_ctx *c, const char *who, int64_t N_total, int64_t row0, int64_t n_rows);
 extern "C" int ciao_set_rows(ciao_ctx *c, int loss_kind, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d,
                              const double *A, int64_t lda, const double *b_or_y, const double *scale, double scale_scalar) {
     if (!c || !A || !b_or_y) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_rows: null argument");
@@ -537,6 +540,7 @@ extern "C" int ciao_set_rows(ciao_ctx *c, int loss_kind, int64_t N_total, int64_
         CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_rows: bad shape N=%lld row0=%lld n_rows=%lld d=%lld lda=%lld", (long long)N_total,
                   (long long)row0, (long long)n_rows, (long long)d, (long long)lda);
     CUDA_TRY(cudaSetDevice(c->device));
+    CIAO_TRY(check_interleave(c, "ciao_set_rows", N_total, row0, n_rows));
     CIAO_TRY(alloc_common(c, N_total, row0, n_rows, d));
     CUDA_TRY(cudaMalloc(&c->rec, (size_t)n_rows * c->ld * sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(c->rec, 0, (size_t)n_rows * c->ld * sizeof(double), c->stream));
@@ -649,11 +653,31 @@ extern "C" int ciao_set_reg(ciao_ctx *c, int reg_kind, const double *params, int
     return CIAO_OK;
 }
 
+// Interleaved row shards: declared before the rows arrive.  The data calls then take row0 = rank·block_rows (the first row this
+// rank owns) and n_rows = the number of rows it owns.
+extern "C" int ciao_set_row_interleave(ciao_ctx *c, int64_t block_rows, int rank, int world) {
+    if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_row_interleave: null context");
+    if (c->rec || c->qd) CIAO_FAIL(CIAO_ERR_STATE, "ciao_set_row_interleave: call it before the rows are set");
+    if (block_rows == 0) { c->il_block = 0; c->il_rank = 0; c->il_world = 1; return CIAO_OK; }
+    if (block_rows < 1 || world < 1 || world > CIAO_MAX_PEERS || rank < 0 || rank >= world)
+        CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_row_interleave: block_rows ≥ 1, 1..%d ranks, rank inside", CIAO_MAX_PEERS);
+    c->il_block = block_rows; c->il_rank = rank; c->il_world = world;
+    return CIAO_OK;
+}
+static int check_interleave(ciao_ctx *c, const char *who, int64_t N_total, int64_t row0, int64_t n_rows) {
+    if (!c->il_block) return CIAO_OK;
+    const int64_t want = il_count(N_total, c->il_block, c->il_rank, c->il_world);
+    if (row0 != (int64_t)c->il_rank * c->il_block || n_rows != want)
+        CIAO_FAIL(CIAO_ERR_INVALID, "%s: interleaved shard of rank %d/%d with blocks of %lld rows holds %lld rows starting at row %lld",
+                  who, c->il_rank, c->il_world, (long long)c->il_block, (long long)want, (long long)((int64_t)c->il_rank * c->il_block));
+    return CIAO_OK;
+}
 extern "C" int ciao_gen_synthetic(ciao_ctx *c, int kind, int64_t N_total, int64_t row0, int64_t n_rows, int64_t d,
                                   uint64_t seed, double scale) {
     if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_gen_synthetic: null context");
     if (kind < 0 || kind > 2 || N_total <= 0 || n_rows <= 0 || d <= 0 || row0 < 0 || row0 + n_rows > N_total)
         CIAO_FAIL(CIAO_ERR_INVALID, "ciao_gen_synthetic: bad arguments");
+    CIAO_TRY(check_interleave(c, "ciao_gen_synthetic", N_total, row0, n_rows));
     CUDA_TRY(cudaSetDevice(c->device));
     CIAO_TRY(alloc_common(c, N_total, row0, n_rows, d));
     if (kind == CIAO_SYNTH_SHARING) {
@@ -997,11 +1021,7 @@ extern "C" int ciao_finito_steps(ciao_ctx *c, const int64_t *idx, const int64_t 
             if ((!sharded || (c->p2p_ready && c->world > 1)) && c->batch_persistent && nbw > 1 && nbw < ((int64_t)1 << 22)) {   // all batches in one cooperative launch
                 std::vector<int64_t> loc(win);   // row shards: the part of every window this context holds, in local row numbers
                 if (sharded)
-                    for (int64_t j = 0; j < nbw; ++j) {
-                        const int64_t lo = std::max(win[j], c->row0), hi = std::min(win[j] + win[nbw + j], c->row0 + c->n_rows);
-                        loc[j] = std::max<int64_t>(0, lo - c->row0);
-                        loc[nbw + j] = std::max<int64_t>(0, hi - lo);
-                    }
+                    for (int64_t j = 0; j < nbw; ++j) CIAO_TRY(local_window(c, win[j], win[nbw + j], &loc[j], &loc[nbw + j]));
                 const int64_t *win_dev;
                 CIAO_TRY(upload_ptr(c, loc.data(), 2 * nbw, &win_dev));
                 // do rows repeat inside the call, and if so always in the same window?  (sorted by first row: equal or disjoint neighbours)
@@ -1079,9 +1099,8 @@ extern "C" int ciao_lfinito_outer(ciao_ctx *c, const int64_t *batch_order, int64
                 win[jj] = r * (order[jj] - 1);
                 win[n_batches + jj] = (order[jj] == nb) ? last_len : r;
                 if (sharded) {   // the part of the window this context holds, in local row numbers
-                    const int64_t lo = std::max(win[jj], c->row0), hi = std::min(win[jj] + win[n_batches + jj], c->row0 + c->n_rows);
-                    win[jj] = std::max<int64_t>(0, lo - c->row0);
-                    win[n_batches + jj] = std::max<int64_t>(0, hi - lo);
+                    const int64_t glo = win[jj], gn = win[n_batches + jj];
+                    CIAO_TRY(local_window(c, glo, gn, &win[jj], &win[n_batches + jj]));
                 }
             }
             const int64_t *win_dev;

@@ -16,6 +16,23 @@
 
 #include "common.cuh"
 
+// the local rows [*lo_loc, *lo_loc + *n_loc) of the global window [lo, lo + n) (minibatches on row shards)
+int local_window(ciao_ctx *c, int64_t lo, int64_t n, int64_t *lo_loc, int64_t *n_loc) {
+    if (c->il_block) {
+        const int64_t sb = c->il_block * c->il_world;
+        if (lo % sb != 0)
+            CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "interleaved row shards: a minibatch must start at a multiple of block_rows·world = %lld rows (starts at %lld)",
+                      (long long)sb, (long long)lo);
+        *lo_loc = lo / c->il_world;
+        *n_loc = il_count(n, c->il_block, c->il_rank, c->il_world);
+        return CIAO_OK;
+    }
+    const int64_t a = std::max(lo, c->row0), b = std::min(lo + n, c->row0 + c->n_rows);
+    *lo_loc = std::max<int64_t>(0, a - c->row0);
+    *n_loc = std::max<int64_t>(0, b - a);
+    return CIAO_OK;
+}
+
 enum { BATCH_FINITO = 0, BATCH_LFINITO = 1 };
 constexpr int BATCH_MIN_ROWS = 256;
 enum { BATCH_WINDOWS_DISJOINT = 0, BATCH_WINDOWS_ALIGNED = 1, BATCH_WINDOWS_ANY = 2 };
@@ -1097,8 +1114,8 @@ int run_batch_step(ciao_ctx *c, int mode, int64_t row_lo, int64_t n, bool last =
     while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)112 * 1024) --S;
     const size_t smem = (size_t)S * stage_bytes + fixed;
     // the part of the batch this context holds
-    const int64_t lo = std::max(row_lo, c->row0), hi = std::min(row_lo + n, c->row0 + c->n_rows);
-    const int64_t n_loc = std::max<int64_t>(0, hi - lo), lo_loc = lo - c->row0;
+    int64_t lo_loc = 0, n_loc = 0;
+    CIAO_TRY(local_window(c, row_lo, n, &lo_loc, &n_loc));
     const int64_t n_groups = (n_loc + rpg - 1) / rpg;
     const int grid = (int)std::min<int64_t>(n_groups, 2 * c->num_sms);
     const size_t need = ((size_t)std::max(grid, 1) * d_pad + std::max(grid, 1) + 16) * sizeof(double);

@@ -72,6 +72,15 @@ struct PeerTable {
 #define P2P_LL_WORDS ((size_t)2 * CIAO_MAX_PEERS * P2P_CAP * 2)
 #define P2P_ARENA_BYTES (P2P_LL_OFFSET + P2P_LL_WORDS * 8 + 256)
 
+// interleaved shards: global row of local row r, and the local rows [*lo_loc, *lo_loc + *n_loc) of the global window [lo, lo + n)
+__host__ __device__ __forceinline__ int64_t il_global(int64_t r, int64_t B, int rank, int world) {
+    return ((r / B) * world + rank) * B + r % B;
+}
+static inline int64_t il_count(int64_t n, int64_t B, int rank, int world) {   // rows of [0, n) this rank owns
+    const int64_t sb = B * world, rem = n % sb - (int64_t)rank * B;
+    return (n / sb) * B + (rem < 0 ? 0 : (rem > B ? B : rem));
+}
+
 struct RegParams {
     int kind;
     double lambda;       // NormL1
@@ -89,6 +98,12 @@ struct ciao_ctx {
     // problem
     int loss_kind = -1;
     int64_t N_total = 0, row0 = 0, n_rows = 0, d = 0, d_pad = 0, ld = 0;   // n_rows, N_total count COMPONENTS
+    // Interleaved row shards (ciao_set_row_interleave): il_block > 0 ⇒ this context holds the blocks of il_block consecutive rows
+    // number il_rank, il_rank + il_world, … of the global row sequence, in that order (local row r is global row il_global(r)).
+    // Every static minibatch of a multiple of il_block·il_world rows is then spread evenly over the ranks.  Contiguous shards
+    // (row0, n_rows) otherwise.
+    int64_t il_block = 0;
+    int il_rank = 0, il_world = 1;
     int M = 1;                         // rows per component (ciao_set_row_blocks); the record array holds n_rows·M rows
     bool force_block = false;          // env CIAO_FORCE_BLOCK_KERNEL=1: M = 1 problems through the general block kernel too (tests)
     int64_t win0 = 0, win_n = 0;       // pass window over the local rows (0 = all)

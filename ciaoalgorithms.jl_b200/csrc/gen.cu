@@ -5,10 +5,10 @@
 
 // row records [n_rows][ld]: a_i | tail = b_i or y_i | scale | 0 …
 __global__ void gen_records_kernel(double *rec, int64_t n_rows, int64_t row0, int64_t d, int64_t d_pad, int64_t ld,
-                                   int kind, uint64_t seed, double scale) {
+                                   int kind, uint64_t seed, double scale, int64_t il_block, int il_rank, int il_world) {
     const int64_t total = n_rows * ld;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = e / ld, j = e - r * ld, i = row0 + r;
+        const int64_t r = e / ld, j = e - r * ld, i = il_block ? il_global(r, il_block, il_rank, il_world) : row0 + r;
         double v = 0.0;
         if (j < d) v = ciao_syn_entry(kind, d, seed, i, j);
         else if (j == d_pad) v = ciao_syn_rhs(kind, d, seed, i);
@@ -28,7 +28,8 @@ __global__ void gen_blocks_kernel(double *qd, double *ql, int64_t N, int64_t n, 
 }
 
 int launch_gen_records(ciao_ctx *c, int kind, uint64_t seed, double scale) {
-    gen_records_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(c->rec, c->n_rows, c->row0, c->d, c->d_pad, c->ld, kind, seed, scale);
+    gen_records_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(c->rec, c->n_rows, c->row0, c->d, c->d_pad, c->ld, kind, seed, scale,
+                                                              c->il_block, c->il_rank, c->il_world);
     CUDA_TRY(cudaGetLastError());
     c->timing.launches += 1;
     return CIAO_OK;

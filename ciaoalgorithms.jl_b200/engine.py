@@ -78,6 +78,10 @@ class Engine:
             p = f64arr(np.asarray(params, dtype=np.float64).reshape(-1))
         check(self.lib.ciao_set_reg(self.h, kind, ptr(p) if p.size else None, p.size))
 
+    def set_row_interleave(self, block_rows, rank, world):
+        """Interleaved row shards: this context holds the blocks of `block_rows` rows number rank, rank + world, … (before the rows are set)."""
+        check(self.lib.ciao_set_row_interleave(self.h, block_rows, rank, world))
+
     def gen_synthetic(self, kind, N_total, d, seed, scale=1.0, row0=0, n_rows=None):
         n_rows = N_total if n_rows is None else n_rows
         check(self.lib.ciao_gen_synthetic(self.h, kind, N_total, row0, n_rows, d, seed, float(scale)))

@@ -207,6 +207,12 @@ def csr(batches):
     return idx, ptr
 
 
+def interleaved_rows(N: int, block: int, world: int, rank: int) -> np.ndarray:
+    """Global (0-based) row numbers of an interleaved shard, in local order: blocks rank, rank + world, … of `block` rows."""
+    g = np.arange(N, dtype=np.int64)
+    return g[(g // block) % world == rank]
+
+
 def shard_rows(N: int, world: int, rank: int):
     """Contiguous row partition: rank k owns rows [k·N/G, (k+1)·N/G)."""
     return (rank * N) // world, ((rank + 1) * N) // world

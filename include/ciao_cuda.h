@@ -100,6 +100,13 @@ int ciao_set_rows(ciao_ctx *ctx, int loss_kind, int64_t N_total, int64_t row0, i
  * loops run in the general block kernel (csrc/blockseq.cu), not in the tuned cluster kernels; not sharded, no adaptive Finito. */
 int ciao_set_row_blocks(ciao_ctx *ctx, int loss_kind, int64_t N, int64_t M, int64_t d, const double *A, int64_t lda,
                         const double *b_or_y, const double *scale, double scale_scalar);
+/* Interleaved row shards (one process per GPU; the reference has no counterpart — where the rows of F live is the host's
+ * choice): rank k of `world` holds the blocks of block_rows consecutive rows number k, k + world, … in that order.  Call it
+ * before the rows are set; ciao_set_rows / ciao_gen_synthetic then take row0 = rank·block_rows and n_rows = the number of rows
+ * the rank owns.  A static minibatch (Finito_basic.jl:52-57: contiguous rows) that starts at a multiple of block_rows·world
+ * is then spread evenly over the ranks, so minibatch sweeps scale with the GPUs; passes shard as with contiguous shards.
+ * Single-sample steps and remote rows are for contiguous shards.  block_rows = 0 returns to contiguous shards. */
+int ciao_set_row_interleave(ciao_ctx *ctx, int64_t block_rows, int rank, int world);
 /* Sharing blocks f_i(x_i) = ½x'diag(q_i)x + c_i'x + (η/2)dist²(x, [lo,hi])   (test_sharing.jl:15-22) */
 int ciao_set_blocks(ciao_ctx *ctx, int64_t N, int64_t n, const double *Qdiag, int64_t ldq, const double *qlin,
                     int64_t ldl, double box_lo, double box_hi, double eta);

@@ -7,7 +7,7 @@ import os, sys, json, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); import ciao_pkg; ciao_pkg.load()
 from ciaoalgorithms_jl_b200 import _lib as L
 from ciaoalgorithms_jl_b200.engine import Engine
-from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, csr, shard_rows
+from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, csr, interleaved_rows, shard_rows
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -15,10 +15,15 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 N, d = 1 << 20, 1024
 lo, hi = shard_rows(N, world, rank)
 res = {}
-for per_launch in ("0", "1"):
+BLOCK = 256
+for per_launch, layout in (("0", "interleaved"), ("0", "contiguous"), ("1", "contiguous")):
     os.environ["CIAO_BATCH_PER_LAUNCH"] = per_launch        # read by ciao_create
     e = Engine(local)
-    e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0, row0=lo, n_rows=hi - lo)
+    if layout == "interleaved":                             # blocks of 256 rows dealt round-robin: every batch is spread over all ranks
+        e.set_row_interleave(BLOCK, rank, world)
+        e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0, row0=rank * BLOCK, n_rows=len(interleaved_rows(N, BLOCK, world, rank)))
+    else:
+        e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0, row0=lo, n_rows=hi - lo)
     e.set_reg(L.REG_NORML1, 1.0 / N)
     hs = [None] * world
     dist.all_gather_object(hs, e.comm_p2p_handle())
@@ -34,7 +39,7 @@ for per_launch in ("0", "1"):
         z = e.get_vec(L.VEC_Z)
         blobs = [None] * world; dist.all_gather_object(blobs, z.tobytes())
         t = torch.tensor([tf, tl], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); tf, tl = t.tolist()
-        key = f"{'per_batch' if per_launch == '1' else 'fused'}_batch{r}"
+        key = f"{layout}_{'per_batch' if per_launch == '1' else 'fused'}_batch{r}"
         res[key] = {"finito_us_per_batch": 1e3 * tf / sw.d, "lfinito_us_per_batch": 1e3 * tl / sw.d, "finito_epochs_per_s": 1e3 / tf,
                     "lfinito_sweeps_per_s": 1e3 / tl, "z_bitwise_equal_across_ranks": all(b == blobs[0] for b in blobs)}
         if rank == 0:

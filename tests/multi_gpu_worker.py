@@ -26,7 +26,7 @@ import torch.distributed as dist  # noqa: E402
 
 from ciaoalgorithms_jl_b200 import _lib as L  # noqa: E402
 from ciaoalgorithms_jl_b200.engine import Engine  # noqa: E402
-from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, LFinitoSweeper, csr, shard_rows  # noqa: E402
+from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, LFinitoSweeper, csr, interleaved_rows, shard_rows  # noqa: E402
 
 
 def main():
@@ -202,6 +202,49 @@ def main():
         assert rel(sh.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-11
         assert same_on_all_ranks(sh.get_vec(L.VEC_Z))
         sh.finito_init(np.full(d, 0.01), gsh, hsh)
+    if use_p2p:
+        # Interleaved shards: blocks of 64 rows dealt round-robin to the ranks, so EVERY static minibatch (a multiple of
+        # 64·world rows) is spread over all ranks and a sweep scales with the GPUs.  Same checks as above against the whole problem.
+        B = 64
+        gl = interleaved_rows(N, B, world, rank)
+        shi = Engine(local)
+        shi.set_row_interleave(B, rank, world)
+        shi.gen_synthetic(L.SYNTH_LASSO, N, d, seed, scale=float(N), row0=rank * B, n_rows=len(gl))
+        shi.set_reg(L.REG_NORML1, lam)
+        comm_setup(shi)
+        assert rel(shi.full_gradient(x, 1.0 / N), full.full_gradient(x, 1.0 / N)) < 1e-13
+        rb = 4 * B * world
+        shi.finito_init(np.full(d, 0.01), gsh, hsh)
+        full.finito_init(np.full(d, 0.01), gsh, hsh)
+        assert rel(shi.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-12
+        assert np.array_equal(shi.get_table_rows(), full.get_table_rows()[gl])          # each rank took the γ_i of ITS rows
+        sw_a, sw_b = BatchSweeper(N, rb, 3, HostRNG(4)), BatchSweeper(N, rb, 3, HostRNG(4))
+        for _ in range(2):
+            ia, pa = csr(sw_a.take(sw_a.d))
+            ib, pb = csr(sw_b.take(sw_b.d))
+            l0 = shi.last_timing().launches
+            shi.finito_steps(ia, pa)
+            assert shi.last_timing().launches - l0 <= 2
+            full.finito_steps(ib, pb)
+        assert rel(shi.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) < 1e-11, rel(shi.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z))
+        assert rel(shi.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-11
+        assert rel(shi.get_table_rows(), full.get_table_rows()[gl]) < 1e-12
+        assert same_on_all_ranks(shi.get_vec(L.VEC_Z))
+        shi.lfinito_init(np.full(d, 0.01), gsh, hsh)
+        full.lfinito_init(np.full(d, 0.01), gsh, hsh)
+        order = np.arange(1, -(-N // rb) + 1, dtype=np.int64)
+        for _ in range(2):
+            shi.lfinito_outer(order, rb)
+            full.lfinito_outer(order, rb)
+        assert rel(shi.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z)) < 1e-11, rel(shi.get_vec(L.VEC_Z), full.get_vec(L.VEC_Z))
+        assert rel(shi.get_vec(L.VEC_AV), full.get_vec(L.VEC_AV)) < 1e-11
+        assert same_on_all_ranks(shi.get_vec(L.VEC_Z))
+        try:   # a batch that does not start at a multiple of 64·world rows has no contiguous local part
+            shi.lfinito_outer(np.arange(1, -(-N // (rb + B)) + 1, dtype=np.int64), rb + B)
+            raise AssertionError("misaligned minibatch on interleaved shards should fail")
+        except Exception as ex:
+            assert "multiple of block_rows" in str(ex), str(ex)
+        shi.close()
     try:
         sh.finito_steps(np.array([1, 2], dtype=np.int64), np.array([0, 1, 2], dtype=np.int64))
         raise AssertionError("finito_steps on a shard should fail")
