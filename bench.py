@@ -415,41 +415,44 @@ def bench_c4(local, rank, world, peak, d, K, W, init_comm, barrier, max_over_ran
 
 
 def bench_sharded_minibatch(local, rank, world, init_comm, barrier, max_over_ranks, same_on_all_ranks):
-    """configs[1] "C2" rows in `world` contiguous shards (the N x d table lives with its rows): one epoch of static Finito
-    minibatches (Finito_basic.jl:110-118) and one LFinito sweep (Finito_LFinito.jl:91-100) of 4096-row batches, each a single
-    persistent kernel per rank whose column owners exchange the ranks' sums through the peer arenas (batch.cu).  A contiguous
-    batch lives on one rank, so this measures capacity scaling: the figure to compare with is C2's single-GPU µs per batch."""
+    """configs[1] "C2" rows as interleaved shards (blocks of 256 rows dealt round-robin to the GPUs, the N x d table lives with its
+    rows): one epoch of static Finito minibatches (Finito_basic.jl:110-118) and one LFinito sweep (Finito_LFinito.jl:91-100), each
+    a single persistent kernel per rank whose column owners exchange the ranks' sums through the peer arenas (batch.cu).  Batches
+    of 4096 rows per GPU (weak) and of 65 536 rows in total (strong); compare with C2's single-GPU µs per batch."""
     from ciaoalgorithms_jl_b200 import _lib as L
     from ciaoalgorithms_jl_b200.engine import Engine
-    from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, csr, shard_rows
-    N, d, r = 1 << 20, 1024, 4096
-    lo, hi = shard_rows(N, world, rank)
-    out = {"N": N, "d": d, "batch": r, "rows_per_gpu": hi - lo}
+    from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, csr, interleaved_rows
+    N, d, B = 1 << 20, 1024, 256
+    n_loc = len(interleaved_rows(N, B, world, rank))
+    out = {"N": N, "d": d, "layout": f"interleaved, blocks of {B} rows", "rows_per_gpu": n_loc}
     with Engine(local) as e:
-        e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0, row0=lo, n_rows=hi - lo)
+        e.set_row_interleave(B, rank, world)
+        e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0, row0=rank * B, n_rows=n_loc)
         e.set_reg(L.REG_NORML1, 1.0 / N)
         init_comm(e)
         gam = np.full(N, 0.999 * N / (0.25 * e.max_row_sqnorm()))
         hat = 1 / np.sum(1 / gam)
-        sw = BatchSweeper(N, r, 2, HostRNG(1))
-        idx, bp = csr(sw.take(sw.d))
-        e.finito_init(np.ones(d), gam, hat)
-        e.finito_steps(idx, bp)
-        barrier()
-        e.finito_steps(idx, bp)
-        tf = max_over_ranks(e.last_timing().last_seq_ms)
-        out["finito_us_per_batch"] = 1e3 * tf / sw.d
-        out["finito_z_bitwise_equal_across_ranks"] = bool(same_on_all_ranks(e.get_vec(L.VEC_Z)))
-        e.lfinito_init(np.ones(d), gam, hat)
-        order = np.arange(1, sw.d + 1)
-        e.lfinito_outer(order, r)
-        barrier()
-        e.lfinito_outer(order, r)
-        tl = max_over_ranks(e.last_timing().last_seq_ms)
-        out["lfinito_us_per_batch"] = 1e3 * tl / sw.d
-        out["lfinito_z_bitwise_equal_across_ranks"] = bool(same_on_all_ranks(e.get_vec(L.VEC_Z)))
-        out["objective"] = sum(e.objective(e.get_vec(L.VEC_Z)))
-        barrier()
+        for r in (4096 * world, 65536):
+            sw = BatchSweeper(N, r, 2, HostRNG(1))
+            idx, bp = csr(sw.take(sw.d))
+            e.finito_init(np.ones(d), gam, hat)
+            e.finito_steps(idx, bp)
+            barrier()
+            e.finito_steps(idx, bp)
+            tf = max_over_ranks(e.last_timing().last_seq_ms)
+            zf = e.get_vec(L.VEC_Z)
+            e.lfinito_init(np.ones(d), gam, hat)
+            order = np.arange(1, sw.d + 1)
+            e.lfinito_outer(order, r)
+            barrier()
+            e.lfinito_outer(order, r)
+            tl = max_over_ranks(e.last_timing().last_seq_ms)
+            zl = e.get_vec(L.VEC_Z)
+            out[f"batch{r}"] = {"rows_per_gpu_and_batch": r // world, "finito_us_per_batch": 1e3 * tf / sw.d, "finito_epochs_per_s": 1e3 / tf,
+                                "lfinito_us_per_batch": 1e3 * tl / sw.d, "lfinito_sweeps_per_s": 1e3 / tl,
+                                "z_bitwise_equal_across_ranks": bool(same_on_all_ranks(zf)) and bool(same_on_all_ranks(zl)),
+                                "objective": sum(e.objective(zl))}
+            barrier()
     return out
 
 
