@@ -214,3 +214,34 @@ def test_julia_rng_samplers_are_well_formed_and_follow_the_stream():
     sw = BatchSweeper(10, 3, 3, JuliaRNG(0))
     seen = [b for _ in range(2 * sw.d) for b in sw.next().tolist()]
     assert sorted(seen[:10]) == list(range(1, 11)) and sorted(seen[10:]) == list(range(1, 11))
+
+
+def test_interleaved_shards_give_every_aligned_batch_a_contiguous_local_window():
+    """Interleaved row shards (ciao_set_row_interleave): rank k holds the blocks of B rows number k, k + G, …  A static batch that
+    starts at a multiple of B·G rows must map to ONE contiguous range of local rows on every rank — [lo/G, lo/G + count) with the
+    count formula of csrc/common.cuh il_count — and the ranks' parts must tile the batch."""
+    from ciaoalgorithms_jl_b200.sampling import interleaved_rows
+
+    def il_count(n, B, rank, world):
+        sb = B * world
+        rem = n % sb - rank * B
+        return (n // sb) * B + min(max(rem, 0), B)
+
+    for N, B, G in ((6037, 64, 2), (6037, 64, 3), (1 << 14, 256, 8), (1000, 7, 4)):
+        owned = [interleaved_rows(N, B, G, k) for k in range(G)]
+        assert sorted(np.concatenate(owned).tolist()) == list(range(N))
+        for k in range(G):
+            assert len(owned[k]) == il_count(N, B, k, G)
+            assert owned[k][0] == k * B or len(owned[k]) == 0
+        r = 4 * B * G
+        for lo in range(0, N, r):
+            n = min(r, N - lo)
+            total = 0
+            for k in range(G):
+                loc = np.nonzero((owned[k] >= lo) & (owned[k] < lo + n))[0]
+                cnt = il_count(n, B, k, G)
+                assert len(loc) == cnt
+                if cnt:
+                    assert loc[0] == lo // G and loc[-1] == lo // G + cnt - 1      # contiguous local rows
+                total += cnt
+            assert total == n
