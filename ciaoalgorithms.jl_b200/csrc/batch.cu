@@ -619,6 +619,7 @@ struct BatchLArgs {
     int world, rank;
     unsigned long long *xw[CIAO_MAX_PEERS];   // every rank's flagged-word area as addressed from this GPU (own entry: local)
     uint32_t xepoch0;
+    unsigned long long xtimeout_ns;           // a peer that does not show up for this long (ciao_ctx::p2p_timeout_ns) ends the kernel with a trap
 };
 
 __device__ __forceinline__ void ll_store(unsigned long long *p, double v, uint32_t flag) {
@@ -1006,6 +1007,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                     for (int q = 0; q < p.world; ++q) ll_store_sys(p.xw[q] + slot * 2, tsum, epx);
                     const unsigned long long *mine = p.xw[p.rank] + ((size_t)(b & 1) * CIAO_MAX_PEERS * P2P_CAP + j_own) * 2;
                     double v[CIAO_MAX_PEERS];
+                    unsigned long long t_start = 0;   // the ranks' hosts launch at different times: the limit is wall time, not polls
                     for (int spins = 0;; ++spins) {
                         bool ok = true;
 #pragma unroll
@@ -1014,7 +1016,12 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                             if (q < p.world) ok &= ll_load_sys(mine + (size_t)q * P2P_CAP * 2, epx, v[q]);
                         }
                         if (ok) break;
-                        if (spins > LL_SPIN_LIMIT) __trap();
+                        if ((spins & 1023) == 1023) {
+                            unsigned long long now;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                            if (!t_start) t_start = now;
+                            else if (now - t_start > p.xtimeout_ns) __trap();
+                        }
                     }
                     tsum = 0.0;
 #pragma unroll
@@ -1268,6 +1275,7 @@ static int launch_batch_sm(ciao_ctx *c, BatchLArgs &a, int TS, int nsg, size_t s
         for (int q = 0; q < a.world; ++q)
             a.xw[q] = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(c->p2p_peer[q]) + P2P_LL_OFFSET);
         a.xepoch0 = c->p2p_ll_epoch;
+        a.xtimeout_ns = c->p2p_timeout_ns;
         c->p2p_ll_epoch += (uint32_t)a.n_batches;
     }
     void *args[] = {(void *)&a};
