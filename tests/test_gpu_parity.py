@@ -950,3 +950,32 @@ def test_finito_adaptive_random_restart():
         assert ref.steps(idx) == e.finito_adaptive_steps(idx)
         assert rel(e.get_vec(L.VEC_Z), ref.z) < 1e-9
         assert rel(e.finito_adaptive_get()[0], ref.gamma) < 1e-12
+
+
+def test_interleaved_shards_host_rows_generator_and_whole_problem_agree():
+    """ciao_set_row_interleave: rank k of G holds the blocks of B rows number k, k + G, …  Rows handed over from the host in that
+    order and rows generated on the device must give the same shard, and the shards' partial gradients must add up to the whole
+    problem's (no communicator here: every "rank" is a context of its own on this GPU)."""
+    from ciaoalgorithms_jl_b200.sampling import interleaved_rows
+    N, d, B, G, seed = 500, 40, 16, 3, 0x11AB
+    A, rhs = orc.gen_rows(orc.SYN_LASSO, d, seed, 0, N)
+    x = np.random.default_rng(3).standard_normal(d)
+    with Engine(0) as full:
+        full.gen_synthetic(L.SYNTH_LASSO, N, d, seed, scale=float(N))
+        g_full = full.full_gradient(x, 1.0)
+    total = np.zeros(d)
+    for k in range(G):
+        gl = interleaved_rows(N, B, G, k)
+        with Engine(0) as a, Engine(0) as b:
+            a.set_row_interleave(B, k, G)
+            a.set_rows(L.LOSS_LS, A[gl], rhs[gl], float(N), N_total=N, row0=k * B)
+            b.set_row_interleave(B, k, G)
+            b.gen_synthetic(L.SYNTH_LASSO, N, d, seed, scale=float(N), row0=k * B, n_rows=len(gl))
+            ga, gb = a.full_gradient(x, 1.0), b.full_gradient(x, 1.0)
+            assert np.array_equal(ga, gb)
+            total += ga
+    assert rel(total, g_full) < 1e-13
+    with Engine(0) as e:
+        e.set_row_interleave(B, 1, G)
+        with pytest.raises(Exception, match="interleaved shard"):
+            e.gen_synthetic(L.SYNTH_LASSO, N, d, seed, scale=float(N), row0=B, n_rows=N // G)     # rank 1 owns 164 rows, not 166
