@@ -54,6 +54,13 @@ end
 realdata(a) = eltype(a) <: Complex ?
     (all(iszero, imag.(a)) ? real.(a) : error("complex data with non-zero imaginary parts is outside the engine's scope")) : a
 
+# Multi-GPU hosts (one process per GPU): declare before set_problem! that this process holds the blocks of `block` rows number
+# rank, rank + world, … of F (0-based rank), and hand set_problem! only those components, in that order.  Static minibatches of a
+# multiple of block·world rows are then spread over all GPUs (the ranks' sums meet inside the persistent minibatch kernel).
+set_row_interleave!(c::Ctx, block::Integer, rank::Integer, world::Integer) =
+    check(ccall((:ciao_set_row_interleave, libciao), Cint, (Ptr{Cvoid}, Int64, Cint, Cint), c.h, block, rank, world))
+interleaved_rows(N::Integer, block::Integer, rank::Integer, world::Integer) = [i for i in 1:N if ((i - 1) ÷ block) % world == rank]
+
 # ---- F / g recognition (replaces dynamic dispatch on F::Array{Tf}, SVRG_basic.jl:2) --------------
 function set_problem!(c::Ctx, F, g, N::Int, x0 = nothing)
     F === nothing && (F = fill(ProximalOperators.Zero(), (N,)))   # SVRG.jl:58, SAGA.jl:55, Finito.jl:78, ProShI.jl:54
