@@ -54,9 +54,11 @@ end
 realdata(a) = eltype(a) <: Complex ?
     (all(iszero, imag.(a)) ? real.(a) : error("complex data with non-zero imaginary parts is outside the engine's scope")) : a
 
-# Multi-GPU hosts (one process per GPU): declare before set_problem! that this process holds the blocks of `block` rows number
-# rank, rank + world, … of F (0-based rank), and hand set_problem! only those components, in that order.  Static minibatches of a
-# multiple of block·world rows are then spread over all GPUs (the ranks' sums meet inside the persistent minibatch kernel).
+# Multi-GPU hosts (one process per GPU; INTEGRATION.md): declare, before the rows are set, that this process holds the blocks of
+# `block` rows number rank, rank + world, … of F (0-based rank).  Static minibatches of a multiple of block·world rows are then
+# spread over all GPUs (the ranks' sums meet inside the persistent minibatch kernel).  set_problem! below is the single-GPU path
+# (row0 = 0, all of F); a multi-GPU host packs interleaved_rows(…) of F itself and calls ciao_set_rows with N_total = N,
+# row0 = rank·block, n_rows = length(interleaved_rows(…)).
 set_row_interleave!(c::Ctx, block::Integer, rank::Integer, world::Integer) =
     check(ccall((:ciao_set_row_interleave, libciao), Cint, (Ptr{Cvoid}, Int64, Cint, Cint), c.h, block, rank, world))
 interleaved_rows(N::Integer, block::Integer, rank::Integer, world::Integer) = [i for i in 1:N if ((i - 1) ÷ block) % world == rank]
