@@ -126,7 +126,7 @@ static int alloc_common(ciao_ctx *c, int64_t N_total, int64_t row0, int64_t n_ro
     c->N_total = N_total; c->row0 = row0; c->n_rows = n_rows; c->d = d;
     c->M = 1;
     c->win0 = c->win_n = 0;
-    c->cz_valid = false;
+    c->cz_valid = false; c->cz_local_valid = false;
     c->d_pad = (d + 3) / 4 * 4;
     c->ld = c->d_pad + CIAO_TAIL;
     CUDA_TRY(cudaMalloc(&c->vecs, (size_t)CIAO_NUM_VECS * c->d_pad * sizeof(double)));
@@ -445,7 +445,7 @@ extern "C" int ciao_attach_peer_rows(ciao_ctx *c, int n_shards, const void *hand
 extern "C" int ciao_set_pass_window(ciao_ctx *c, int64_t row_lo, int64_t n) {
     if (!c) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_pass_window: null context");
     c->win_uniform = false;
-    c->cz_valid = false;
+    c->cz_valid = false; c->cz_local_valid = false;
     if (n == 0) {
         c->win0 = c->win_n = 0;
         if (c->world <= 1) return CIAO_OK;
@@ -817,7 +817,7 @@ extern "C" int ciao_finito_adaptive_init_cb(ciao_ctx *c, const double *x0, doubl
     if (c->peers.n > 1) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito keeps N×d tables: not available on row-sharded problems");
     if (use_block_kernel(c) && !c->force_block) CIAO_FAIL(CIAO_ERR_UNSUPPORTED, "adaptive Finito is not available for M×d block components / complex data");
     c->algo = ALG_FINITO_ADAPTIVE; c->adapt_alpha = alpha; c->adapt_tol_b = tol_b; c->adapt_backtracks = 0;
-    c->cz_valid = false;
+    c->cz_valid = false; c->cz_local_valid = false;
     CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(alloc_table(c));
     const int64_t N = c->N_total;
@@ -1055,7 +1055,7 @@ extern "C" int ciao_lfinito_init(ciao_ctx *c, const double *x0, const double *ga
     CIAO_TRY(need_rows(c, "ciao_lfinito_init", false));   // the init is a pass: it shards like the full gradient
     if (!x0 || !gamma_N || !(hat_gamma > 0)) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_lfinito_init: null argument or γ̂ ≤ 0");
     c->algo = ALG_LFINITO; c->hat_gamma = hat_gamma;
-    c->cz_valid = false;
+    c->cz_valid = false; c->cz_local_valid = false;
     CIAO_TRY(reserve_for_solver(c));
     CIAO_TRY(set_gammas(c, gamma_N, true));
     CIAO_TRY(upload_vec(c, CIAO_VEC_X0, x0));
@@ -1189,7 +1189,7 @@ extern "C" int ciao_set_vec(ciao_ctx *c, int which, const double *in, int64_t le
     if (!c->vecs) CIAO_FAIL(CIAO_ERR_STATE, "ciao_set_vec: no problem set");
     if (which < 0 || which > CIAO_VEC_X || len != c->d) CIAO_FAIL(CIAO_ERR_INVALID, "ciao_set_vec: bad vector id or length");
     CUDA_TRY(cudaSetDevice(c->device));
-    c->cz_valid = false;  // z_full may have changed: the cached c_i(z_full) no longer apply
+    c->cz_valid = false; c->cz_local_valid = false;  // z_full may have changed: the cached c_i(z_full) no longer apply
     return upload_vec(c, which, in);
 }
 
@@ -1244,7 +1244,7 @@ extern "C" int ciao_solver_restore(ciao_ctx *c, int algo, double gamma, int flag
             CIAO_FAIL(CIAO_ERR_INVALID, "ciao_solver_restore: algo must be 1 (SVRG) … 5 (ProShI)");
     }
     c->algo = algo;
-    c->cz_valid = false;
+    c->cz_valid = false; c->cz_local_valid = false;
     CIAO_TRY(reserve_for_solver(c));
     if (algo == ALG_SAGA || algo == ALG_FINITO || algo == ALG_PROSHI) CIAO_TRY(alloc_table(c));
     if (algo == ALG_FINITO || algo == ALG_LFINITO) CIAO_TRY(set_gammas(c, gamma_N, true));

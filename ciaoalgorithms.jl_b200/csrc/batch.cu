@@ -33,7 +33,8 @@ int local_window(ciao_ctx *c, int64_t lo, int64_t n, int64_t *lo_loc, int64_t *n
     return CIAO_OK;
 }
 
-enum { BATCH_FINITO = 0, BATCH_LFINITO = 1 };
+enum { BATCH_FINITO = 0, BATCH_LFINITO = 1,
+       BATCH_LFINITO_CZ = 2 };   // LFinito with c_i(z_full) of every row cached by the pass at z_full (batch_sm_kernel only)
 constexpr int BATCH_MIN_ROWS = 256;
 enum { BATCH_WINDOWS_DISJOINT = 0, BATCH_WINDOWS_ALIGNED = 1, BATCH_WINDOWS_ANY = 2 };
 
@@ -607,6 +608,7 @@ struct BatchLArgs {
     unsigned long long *llz;    // [d_pad][2]        new z, written by the column owners
     unsigned long long *llws;   // [grid][d_pad][2]  CTA partials
     const double *bfs;          // LFinito: Σ γ̂/γ_i of every batch (batch_fsum_kernel)
+    const double *ss;           // LFinito with cached coefficients: {b_i, λ_i, 0, c_i(z_full)} of this context's rows
     uint32_t epoch0;            // flags of this launch: epoch0 + b + 1
     int fence;
     double cN, hat_gamma;
@@ -696,12 +698,16 @@ __global__ void __launch_bounds__(256) batch_fsum_kernel(const double *rec, int6
 // threads per CTA: LFinito at 4 or 8 columns per thread keeps ≤ 128 registers (4 sub-groups of 128 or 2 of 256 threads)
 template <int CPT, int MODE>
 struct BatchSmShape {
-    static constexpr int MAXT = (MODE == BATCH_LFINITO && (CPT == 4 || CPT == 8)) ? 512 : 256;
+    static constexpr int MAXT = (MODE != BATCH_FINITO && (CPT == 4 || CPT == 8)) ? 512 : 256;
 };
 
 template <int CPT, int MODE, int LOSS>
 __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_kernel(const BatchLArgs p) {
     constexpr int RPG = 16 / CPT;
+    // LF: an LFinito sweep.  CZ: c_i(z_full) of the rows comes from the scalars the pass at z_full left (ciao_ctx::ss, one 32-byte
+    // sector per row, staged with the rows), so an item needs ONE dot product per row, half the warp sums, and no z_full in
+    // shared memory — the item loop is bound by its dependent chain and by the fp64 pipe, not by HBM (§4.3).
+    constexpr bool LF = MODE != BATCH_FINITO, CZ = MODE == BATCH_LFINITO_CZ, TWO_DOTS = LF && !CZ;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, Tall = blockDim.x;
     const int TS = p.ts, NSG = p.nsg;
@@ -710,7 +716,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
     const int64_t G = gridDim.x, bid = blockIdx.x;
     const int64_t VG = G * NSG, vb = (int64_t)sg * G + bid;         // virtual CTA of the item distribution
     const size_t rec_doubles = (size_t)RPG * p.ld;
-    const size_t stage_doubles = rec_doubles;
+    const size_t stage_doubles = rec_doubles + (CZ ? RPG * 4 : 0);
     // shared memory: per sub-group {ring[S], red[2][RPG][32][2]}; then comb[NSG][d_pad] (sub-group partials, NSG > 1), zsm[d_pad] (z of
     // the current batch), zfs[d_pad] (z_full, LFinito), rsm[17][33], own[5][32], full[NSG][4].  z and z_full are read from
     // shared memory in every item: 32 registers less, which is what lets LFinito run 512 threads without spilling.
@@ -720,7 +726,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
     double *comb = reinterpret_cast<double *>(smem_raw) + (size_t)NSG * sg_doubles;
     double *zsm = comb + (size_t)(NSG > 1 ? NSG : 0) * p.d_pad;
     double *zfs = zsm + p.d_pad;
-    double *rsm = zfs + (MODE == BATCH_LFINITO ? p.d_pad : 0);
+    double *rsm = zfs + (TWO_DOTS ? p.d_pad : 0);
     double *own = rsm + 17 * 33 + 1;
     uint64_t *full = reinterpret_cast<uint64_t *>(own + 5 * 32) + sg * 4;
 
@@ -729,7 +735,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
     for (int i = tid; i < 17 * 33 + 1; i += Tall) rsm[i] = 0.0;
     for (int64_t c = tid; c < p.d_pad; c += Tall) {
         zsm[c] = p.z[c];
-        if (MODE == BATCH_LFINITO) zfs[c] = p.zf[c];
+        if (TWO_DOTS) zfs[c] = p.zf[c];
     }
     if (lt == 0) {
         for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -762,8 +768,9 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
             const int64_t r0 = p_lo + pg * RPG;
             const int rows = (int)min((int64_t)RPG, p_n - pg * RPG);
             const uint32_t bytes = (uint32_t)(rows * p.ld * sizeof(double));
-            mbar_arrive_expect_tx(&full[p_slot], bytes);
+            mbar_arrive_expect_tx(&full[p_slot], bytes + (CZ ? (uint32_t)rows * 32u : 0u));
             tma_load_1d_stream(ring + (size_t)p_slot * stage_doubles, p.rec + r0 * p.ld, bytes, &full[p_slot], policy);
+            if (CZ) tma_load_1d_stream(ring + (size_t)p_slot * stage_doubles + rec_doubles, p.ss + r0 * 4, (uint32_t)rows * 32u, &full[p_slot], policy);
             p_slot = p_slot + 1 == S ? 0 : p_slot + 1;
             pg += VG;
             if (pg >= p_ng) next_batch();
@@ -792,7 +799,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
     if (fin) {   // only thread tid touches own[·][tid]: no synchronisation needed
         own[tid] = p.av[j_own];
         own[32 + tid] = p.z[j_own];
-        own[64 + tid] = MODE == BATCH_LFINITO ? p.zf[j_own] : 0.0;
+        own[64 + tid] = LF ? p.zf[j_own] : 0.0;
         own[96 + tid] = p.reg.lo_v ? p.reg.lo_v[j_own] : p.reg.lo_s;
         own[128 + tid] = p.reg.hi_v ? p.reg.hi_v[j_own] : p.reg.hi_s;
     }
@@ -835,13 +842,13 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                     const bool v = FULL || col[k] >= 0;
                     const double2 zv = v ? *reinterpret_cast<const double2 *>(zsm + col[k]) : make_double2(0.0, 0.0);
                     zr[2 * k] = zv.x; zr[2 * k + 1] = zv.y;
-                    if (MODE == BATCH_LFINITO) {
+                    if (TWO_DOTS) {
                         const double2 fv = v ? *reinterpret_cast<const double2 *>(zfs + col[k]) : make_double2(0.0, 0.0);
                         zfr[2 * k] = fv.x; zfr[2 * k + 1] = fv.y;
                     }
                 }
                 mbar_wait(&full[slot], parity);
-                double a[RPG][CPT], p0[RPG], p1[RPG], tb[RPG], tl[RPG], tgn[RPG], thg[RPG];
+                double a[RPG][CPT], p0[RPG], p1[RPG], tb[RPG], tl[RPG], tgn[RPG], thg[RPG], czfv[RPG];
 #pragma unroll
                 for (int r = 0; r < RPG; ++r) {
                     p0[r] = p1[r] = 0.0;
@@ -855,13 +862,14 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                         a[r][2 * k + 1] = v.y;
                         p0[r] = fma(v.x, zr[2 * k], p0[r]);
                         p0[r] = fma(v.y, zr[2 * k + 1], p0[r]);
-                        if (MODE == BATCH_LFINITO) {
+                        if (TWO_DOTS) {
                             p1[r] = fma(v.x, zfr[2 * k], p1[r]);
                             p1[r] = fma(v.y, zfr[2 * k + 1], p1[r]);
                         }
                     }
                     tb[r] = rv ? rp[p.d_pad + TAIL_B] : 0.0;
                     tl[r] = rv ? rp[p.d_pad + TAIL_LAM] : 0.0;
+                    if (CZ) czfv[r] = rv ? sp[rec_doubles + (size_t)r * 4 + 3] : 0.0;   // {b_i, λ_i, 0, c_i(z_full)}: read before the slot is handed back
                     if (MODE == BATCH_FINITO) {
                         tgn[r] = rv ? rp[p.d_pad + TAIL_GAM_N] : 0.0;
                         thg[r] = rv ? rp[p.d_pad + TAIL_HAT_GAM] : 0.0;
@@ -870,7 +878,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
 #pragma unroll
                 for (int r = 0; r < RPG; ++r) {
                     p0[r] = warp_sum_mma(p0[r], lane);
-                    if (MODE == BATCH_LFINITO) p1[r] = warp_sum_mma(p1[r], lane);
+                    if (TWO_DOTS) p1[r] = warp_sum_mma(p1[r], lane);
                     if (lane == 0) {
                         red[((par * RPG + r) * 32 + lwarp) * 2] = p0[r];
                         red[((par * RPG + r) * 32 + lwarp) * 2 + 1] = p1[r];
@@ -878,13 +886,13 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                 }
                 bar_named(1 + sg, TS);
                 issue();  // the slot just read is free: the prefetch runs ahead across batch boundaries
-                constexpr int NP = (MODE == BATCH_LFINITO ? 2 : 1) * RPG;
+                constexpr int NP = (TWO_DOTS ? 2 : 1) * RPG;
                 double uq[NP], bq[NP], lq[NP], cq[NP];
 #pragma unroll
                 for (int r = 0; r < RPG; ++r) {
                     const double2 pr = *reinterpret_cast<const double2 *>(red + ((par * RPG + r) * 32 + lane) * 2);
                     uq[r] = warp_sum_mma(pr.x, lane); bq[r] = tb[r]; lq[r] = tl[r];
-                    if (MODE == BATCH_LFINITO) { uq[RPG + r] = warp_sum_mma(pr.y, lane); bq[RPG + r] = tb[r]; lq[RPG + r] = tl[r]; }
+                    if (TWO_DOTS) { uq[RPG + r] = warp_sum_mma(pr.y, lane); bq[RPG + r] = tb[r]; lq[RPG + r] = tl[r]; }
                 }
                 loss_coef_lanes<LOSS, NP>(uq, bq, lq, lane, cq);
 #pragma unroll
@@ -903,7 +911,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                             if (FULL || col[k] >= 0) __stcg(reinterpret_cast<double2 *>(trow + col[k]), make_double2(t0, t1));
                         }
                     } else {  // Finito_LFinito.jl:94-98, one fma per element (see batch_pass_kernel)
-                        const double czf = cq[(MODE == BATCH_LFINITO ? RPG : 0) + r];
+                        const double czf = CZ ? czfv[r] : cq[(TWO_DOTS ? RPG : 0) + r];
                         const double wrow = p.cN * ((LOSS == CIAO_LOSS_LS ? tl[r] : 1.0) * (czf - cz));
 #pragma unroll
                         for (int e = 0; e < CPT; ++e) acc[e] = fma(a[r][e], wrow, acc[e]);
@@ -921,7 +929,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
         BPROF_ADD(0, t_1, t_2);
         BTRACE(2);
         BDUR_END();
-        const double bfs_b = (MODE == BATCH_LFINITO && fin) ? p.bfs[b] : 0.0;   // needed at the very end of the boundary: loaded now
+        const double bfs_b = (LF && fin) ? p.bfs[b] : 0.0;   // needed at the very end of the boundary: loaded now
         // (1) + (2) the sub-groups' partials meet in shared memory; every thread of the CTA then adds the NSG values of its
         // columns in a fixed order and sends them to the column owners as flagged words (hop 1)
         if (p.fence) __threadfence();
@@ -1029,7 +1037,7 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
                 }
                 double anew = __dadd_rn(own[tid], tsum);
                 bool new_z = true;
-                if (MODE == BATCH_LFINITO) {
+                if (LF) {
                     anew = __dadd_rn(anew, __dmul_rn(bfs_b, __dsub_rn(own[32 + tid], own[64 + tid])));   // Finito_LFinito.jl:98
                     new_z = b + 1 < p.n_batches;                                                  // :92 of the next batch
                 }
@@ -1252,7 +1260,7 @@ static int launch_batch_sm(ciao_ctx *c, BatchLArgs &a, int TS, int nsg, size_t s
     }
     a.llz = c->ll_buf;
     a.llws = a.llz + 2 * (size_t)a.d_pad;
-    if (MODE == BATCH_LFINITO) {   // Σ γ̂/γ_i per batch, in the (otherwise unused) CTA-partial workspace
+    if (MODE != BATCH_FINITO) {   // Σ γ̂/γ_i per batch, in the (otherwise unused) CTA-partial workspace
         const size_t need = (size_t)a.n_batches * sizeof(double);
         if (need > c->ws_bytes) {
             if (c->ws) cudaFree(c->ws);
@@ -1288,7 +1296,7 @@ static int launch_batch_sm_shape(ciao_ctx *c, BatchLArgs &a, int TS, int max_sub
     constexpr int RPG = 16 / CPT;
     int nsg = 1;
     while (nsg * 2 * TS <= BatchSmShape<CPT, MODE>::MAXT && nsg * 2 <= std::min(max_sub, 4)) nsg *= 2;   // 1, 2 or 4 (the combine step)
-    const size_t stage_rows = (size_t)RPG * a.ld * sizeof(double);
+    const size_t stage_rows = (size_t)RPG * a.ld * sizeof(double) + (MODE == BATCH_LFINITO_CZ ? (size_t)RPG * 32 : 0);
     const size_t shared_part = ((size_t)((nsg > 1 ? nsg : 0) + 1 + (MODE == BATCH_LFINITO ? 1 : 0)) * a.d_pad + 17 * 33 + 1 + 5 * 32) * sizeof(double) + (size_t)nsg * 4 * sizeof(uint64_t) + 256;
     const size_t limit = 227 * 1024;   // the opt-in maximum of dynamic shared memory per CTA
     auto smem_for = [&](int S) { return (size_t)nsg * ((size_t)S * stage_rows + 2 * RPG * 32 * 2 * sizeof(double)) + shared_part; };
@@ -1356,6 +1364,15 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
                 case 4: rc = launch_batch_sm_shape<4, BATCH_FINITO>(c, a, T, max_ctas, S_want); break;
                 case 8: rc = launch_batch_sm_shape<8, BATCH_FINITO>(c, a, T, max_ctas, S_want); break;
                 default: rc = launch_batch_sm_shape<16, BATCH_FINITO>(c, a, T, max_ctas, S_want); break;
+            }
+        } else if (c->cache_cz && c->cz_local_valid && c->ss && !getenv("CIAO_BATCH_TWO_DOTS")) {
+            // the pass at z_full that opened this sweep (ciao_lfinito_outer) left c_i(z_full) of the local rows: one dot per row
+            a.ss = c->ss + 4 * c->ss_row0;
+            switch (cpt) {
+                case 2: rc = launch_batch_sm_shape<2, BATCH_LFINITO_CZ>(c, a, T, max_ctas, S_ll); break;
+                case 4: rc = launch_batch_sm_shape<4, BATCH_LFINITO_CZ>(c, a, T, max_ctas, S_ll); break;
+                case 8: rc = launch_batch_sm_shape<8, BATCH_LFINITO_CZ>(c, a, T, max_ctas, S_ll); break;
+                default: rc = launch_batch_sm_shape<16, BATCH_LFINITO_CZ>(c, a, T, max_ctas, S_ll); break;
             }
         } else {
             switch (cpt) {

@@ -127,6 +127,8 @@ struct ciao_ctx {
     double gamma = 0, hat_gamma = 0;
     int plus = 0, sag = 0;
     bool cz_valid = false;             // ss holds c_i(z_full) for the current z_full
+    bool cz_local_valid = false;       // … at least for the rows of this context (what the LFinito minibatch kernel needs); ss_row0:
+    int64_t ss_row0 = 0;               // index in ss of this context's first row (0, or row0 when ss covers all shards' rows)
     // The full-gradient pass at z_full leaves the scalars a sequential step needs, {b_i, λ_i, 0, c_i(z_full)}, in the dense
     // array ss[n_rows][4] (one full 32-byte sector per row, 0.1 % of the pass traffic), so that the SVRG/LFinito step needs
     // one dot product instead of two, forms ∇f_i(z_full) = c_i·a_i while the cluster exchange is in flight, and its producer

@@ -555,7 +555,10 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
         gather_shard = c->peers.start[sidx] == (int64_t)sidx * c->n_rows;
     gather_shard = gather_shard && c->row0 == (int64_t)c->rank * c->n_rows;
     const bool gather_ss = gather_win || gather_shard;
-    if (cache_cz && c->M == 1 && mode == PASS_GRAD && ((!windowed && c->world == 1) || gather_ss)) {
+    // (a rank of a sharded problem without gathered scalars still keeps the scalars of ITS rows: the LFinito minibatch kernel
+    // reads c_i(z_full) of the local rows from there instead of forming a second dot product)
+    const bool local_only = !windowed && c->world > 1 && !gather_ss;
+    if (cache_cz && c->M == 1 && mode == PASS_GRAD && ((!windowed && c->world == 1) || gather_ss || local_only)) {
         const int64_t ss_rows = gather_shard ? c->N_total : c->n_rows;
         if (c->ss && c->ss_cap < ss_rows) {
             cudaFree(c->ss);
@@ -567,7 +570,11 @@ int run_row_pass(ciao_ctx *c, int mode, const double *x_dev, bool cache_cz = fal
         }
         a.ss_out = c->ss + 4 * (gather_shard ? c->row0 : w0);
     }
-    if (mode == PASS_GRAD && cache_cz) c->cz_valid = a.ss_out != nullptr;
+    if (mode == PASS_GRAD && cache_cz) {
+        c->cz_valid = a.ss_out != nullptr && !local_only;          // the sequential kernels need the scalars of ALL rows
+        c->cz_local_valid = a.ss_out != nullptr && !windowed;
+        c->ss_row0 = gather_shard ? c->row0 : 0;
+    }
     a.d_pad = d_pad; a.x = x_dev;
     a.ws = c->ws; a.fws = c->ws + (size_t)grid * d_pad; a.table = c->table;
     a.Nd = (double)c->N_total; a.stages = S;

@@ -6,8 +6,9 @@ tail -5 gpurun_out/pytest_minibatch_ll.log
 export CIAO_PROBE_BATCHES=4096,512,16384,65536
 {
   timeout 300 python scripts/batch_probe.py
+  CIAO_BATCH_TWO_DOTS=1 timeout 300 python scripts/batch_probe.py
   CIAO_BATCH_EXCHANGE=barrier timeout 300 python scripts/batch_probe.py
-  CIAO_BATCH_STAGES=2 timeout 300 python scripts/batch_probe.py
+  CIAO_BATCH_STAGES=3 timeout 300 python scripts/batch_probe.py
   CIAO_PROBE_BATCHES=4096 CIAO_SO=$PWD/ciaoalgorithms.jl_b200/libciao_cuda_prof.so timeout 300 python scripts/batch_probe.py
 } > gpurun_out/batch_ll_r2.log 2>&1
 cat gpurun_out/batch_ll_r2.log

@@ -9,7 +9,7 @@ from ciaoalgorithms_jl_b200.sampling import BatchSweeper, HostRNG, csr
 N, d = 1 << 20, 1024
 e = Engine(0); e.gen_synthetic(L.SYNTH_LOGISTIC, N, d, 0x5EED0002, scale=1.0); e.set_reg(L.REG_NORML1, 1.0 / N)
 Lmax = 0.25 * e.max_row_sqnorm(); gam = np.full(N, 0.999 * N / Lmax); hat = 1 / np.sum(1 / gam)
-tag = " ".join(f"{k[11:]}={os.environ[k]}" for k in ("CIAO_BATCH_T", "CIAO_BATCH_CTAS", "CIAO_BATCH_STAGES", "CIAO_BATCH_PER_LAUNCH", "CIAO_BATCH_EXCHANGE", "CIAO_BATCH_STAGE_TABLE", "CIAO_BATCH_GROUP", "CIAO_BATCH_XPF") if k in os.environ) or "default"
+tag = " ".join(f"{k[11:]}={os.environ[k]}" for k in ("CIAO_BATCH_T", "CIAO_BATCH_CTAS", "CIAO_BATCH_STAGES", "CIAO_BATCH_PER_LAUNCH", "CIAO_BATCH_EXCHANGE", "CIAO_BATCH_STAGE_TABLE", "CIAO_BATCH_GROUP", "CIAO_BATCH_XPF", "CIAO_BATCH_TWO_DOTS") if k in os.environ) or "default"
 for r in [int(v) for v in os.environ.get('CIAO_PROBE_BATCHES', '4096,512').split(',')]:
     e.finito_init(np.ones(d), gam, hat)
     sw = BatchSweeper(N, r, 2, HostRNG(1)); idx, bp = csr(sw.take(sw.d))

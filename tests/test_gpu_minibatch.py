@@ -111,11 +111,14 @@ def test_finito_minibatch_rows_change_window(exchange, monkeypatch):
     e.close()
 
 
-@pytest.mark.parametrize("exchange", ["words", "barrier"])
+@pytest.mark.parametrize("exchange", ["words", "words_two_dots", "barrier"])
 def test_lfinito_minibatch_many_small_batches(exchange, monkeypatch):
     """Many batches per launch (65 per sweep, 5 sweeps) with more CTAs than row groups: CTAs without rows still take part in
-    the exchange of every batch; the epoch counter of the flagged words keeps counting across the launches."""
-    monkeypatch.setenv("CIAO_BATCH_EXCHANGE", exchange)
+    the exchange of every batch; the epoch counter of the flagged words keeps counting across the launches.  By default the sweep
+    takes c_i(z_full) of every row from the pass at z_full that opened it; "two_dots" forms it again from a second dot product."""
+    monkeypatch.setenv("CIAO_BATCH_EXCHANGE", exchange.split("_")[0])
+    if exchange.endswith("two_dots"):
+        monkeypatch.setenv("CIAO_BATCH_TWO_DOTS", "1")
     kind, N, d, batch = orc.LOSS_LS, 16600, 130, 256
     p, e = make_rows(kind, N, d, 0xBAB, lam_reg=0.05)
     gam = 0.999 * N / (np.sum(p.A * p.A, axis=1) * N)
