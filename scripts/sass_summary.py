@@ -16,7 +16,9 @@ want = {
     "seq_kernel<2, 2, 1, 1, false>": "K4 SAGA steps, d = 1024, logistic + NormL1",
     "seq_kernel<2, 3, 1, 1, false>": "K5 Finito steps, d = 1024, logistic + NormL1",
     "adaptive_kernel<2, 1, 1>": "adaptive Finito (on-device linesearch), logistic + NormL1",
-    "batch_persistent_kernel<4, 0, 1>": "Finito minibatches in one persistent cooperative kernel, logistic",
+    "batch_sm_kernel<8, 0, 1>": "Finito minibatches, one CTA per SM, flagged-word exchange (round 2), d = 1024, logistic",
+    "batch_sm_kernel<8, 2, 1>": "LFinito minibatch sweep with cached c_i(z_full), same kernel",
+    "batch_persistent_kernel<4, 0, 1>": "round-1 persistent minibatch kernel (grid barriers), kept as CIAO_BATCH_EXCHANGE=barrier",
     "proshi_steps_kernel<1, 2>": "K7 ProShI, batch 1, IndBox",
     "proshi_batch_kernel<512, 4>": "K7 ProShI, batches >= 64 blocks",
     "pass_tail_kernel": "tail of a pass: CTA-partial reduction + peer-memory exchange + closing update (round 2)",
