@@ -1320,7 +1320,16 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     const int64_t d_pad = c->d_pad;
     // scripts/batch_probe.py at C2: 128 threads (8 columns each) beat 256 for batches of 4096 rows (170 vs 159 Finito epochs/s,
     // 219 vs 191 LFinito sweeps/s) and lose for batches of 512 (52 vs 58)
+    bool barrier_version = false;
+    if (const char *xv = getenv("CIAO_BATCH_EXCHANGE")) barrier_version = !strcmp(xv, "barrier");
+    if (sharded) {
+        if (!c->p2p_ready || c->world < 2) return CIAO_ERR_UNSUPPORTED;   // the caller falls back to one pass + tail kernel per batch
+        barrier_version = false;
+    }
     int T_target = (batch_rows >= 2048 && d_pad <= 2048) ? 128 : 256;
+    // batch_sm_kernel (profiles/batch_sweep_sm_r2.log): Finito is as fast or faster with one sub-group of 256 threads and four rows per
+    // item (18.4 vs 19.0 µs per 4096-row batch, 241.8 vs 242.6 µs at 65 536); LFinito wants four sub-groups of 128 (9.4 vs 10.2, 86.5 vs 100.8)
+    if (!barrier_version && mode == BATCH_FINITO) T_target = 256;
     if (const char *tv = getenv("CIAO_BATCH_T")) T_target = std::max(32, std::min(256, atoi(tv)));
     int cpt = 2;
     while (cpt < 16 && (d_pad + cpt - 1) / cpt > T_target) cpt *= 2;
@@ -1340,12 +1349,6 @@ int run_batch_sequence(ciao_ctx *c, int mode, const int64_t *b_lo_dev, const int
     const int S_want = S;
     while (S > 1 && (size_t)S * stage_bytes + fixed > (size_t)(220 * 1024) / max_ctas) --S;
     const size_t smem = (size_t)S * stage_bytes + fixed;
-    bool barrier_version = false;
-    if (const char *xv = getenv("CIAO_BATCH_EXCHANGE")) barrier_version = !strcmp(xv, "barrier");
-    if (sharded) {
-        if (!c->p2p_ready || c->world < 2) return CIAO_ERR_UNSUPPORTED;   // the caller falls back to one pass + tail kernel per batch
-        barrier_version = false;
-    }
     if (!barrier_version) {
         // LFinito's row loop is bound by fp64 issue, not by the ring: two stages measured faster than three (12.9 vs 13.5 µs per batch)
         const int S_ll = (mode == BATCH_LFINITO && !getenv("CIAO_BATCH_STAGES")) ? 2 : S_want;
