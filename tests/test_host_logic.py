@@ -245,3 +245,62 @@ def test_interleaved_shards_give_every_aligned_batch_a_contiguous_local_window()
                     assert loc[0] == lo // G and loc[-1] == lo // G + cnt - 1      # contiguous local rows
                 total += cnt
             assert total == n
+
+
+def _minibatch_worker(rank, world, port, q):
+    """One rank of a Finito minibatch epoch on interleaved row shards, emulated with the oracle's component gradients and a gloo
+    all-reduce per batch: every rank updates the table rows it owns and contributes its part of the batch's Σ (Finito_basic.jl:110-118)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ciao_pkg
+    ciao_pkg.load()
+    from ciaoalgorithms_jl_b200.sampling import interleaved_rows, static_batches
+    from oracle import oracle as orc
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, d, seed, B = 192, 24, 7, 8
+    A, b = orc.gen_rows(orc.SYN_LASSO, d, seed, 0, N)
+    prob = orc.Problem(orc.LOSS_LS, A, b, np.full(N, float(N))).set_reg(orc.REG_NORML1, lam=0.05)
+    gam = 0.999 * N / (np.sum(A * A, axis=1) * N) * np.linspace(0.7, 1.3, N)
+    x0 = np.full(d, 0.1)
+    ref = orc.FinitoState(prob, x0, gam)                      # the whole problem, sequential loop over every batch
+    batches = static_batches(N, 2 * B * world) * 2            # two epochs; every batch starts at a multiple of B·world rows
+    mine = set(interleaved_rows(N, B, world, rank).tolist())  # 0-based global rows of this rank
+    s = {i: ref.s[i].copy() for i in mine}                    # my table rows after init
+    av, z, hat = ref.av.copy(), ref.z.copy(), ref.hat_gamma
+    for batch in batches:
+        part = np.zeros(d)
+        for i1 in batch:
+            i = int(i1) - 1
+            if i in mine:
+                t = z - (gam[i] / N) * prob.gradient(i, z)[0]
+                part += (t - s[i]) * (hat / gam[i])
+                s[i] = t
+        tt = torch.from_numpy(part)
+        dist.all_reduce(tt)                                   # the ranks' sums, then the closing update on every rank
+        av = av + tt.numpy()
+        z = prob.prox(av, hat)
+    ref.steps(batches)
+    err = max(np.abs(z - ref.z).max() / np.abs(ref.z).max(), np.abs(av - ref.av).max() / np.abs(ref.av).max(),
+              max(np.abs(s[i] - ref.s[i]).max() for i in mine) / np.abs(ref.s).max())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, float(err))
+    if rank == 0:
+        q.put(max(gathered))
+    dist.destroy_process_group()
+
+
+def test_interleaved_minibatch_epoch_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_minibatch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-12
