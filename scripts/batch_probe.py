@@ -22,7 +22,7 @@ fn = getattr(e.lib, "ciao_debug_batch_prof", None)
 if fn is not None:       # profile build (CIAO_SO=…libciao_cuda_prof.so): cycles per batch of CTA 0 in each phase of the last call
     import ctypes as C
     names = ["rows", "partial_write", "barrier1", "reduction", "barrier2", "z_reload"] if os.environ.get("CIAO_BATCH_EXCHANGE") == "barrier" \
-        else ["rows", "partial+group_gate", "group_sum+owner", "z_hops"]
+        else ["rows", "combine+partial_store", "owner_poll_sum_update", "z_poll"]
     for mode in ("finito", "lfinito"):
         sw = BatchSweeper(N, 4096, 2, HostRNG(1)); idx, bp = csr(sw.take(sw.d))
         if mode == "finito":
