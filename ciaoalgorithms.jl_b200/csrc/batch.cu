@@ -781,7 +781,8 @@ __global__ void __launch_bounds__(BatchSmShape<CPT, MODE>::MAXT, 1) batch_sm_ker
     // Consumer: ring slot, its mbarrier phase, parity of the red[] buffer.  LFinito keeps them incrementally; Finito derives
     // slot and phase from the item count with a division by the (run-time) ring depth — measured, three runs each on two GPUs
     // (profiles/batch_exchange_r2.md §4): Finito 18.9 / 64.8 / 242 µs per batch of 4096 / 16 384 / 65 536 rows with the
-    // division against 22.2 / 80 / 306 µs without; LFinito 11.1 / 30.8 / 111.6 against 10.8 / 29.4 / 106.1.  The SASS of the two
+    // division against 22.2 / 80 / 306 µs without; LFinito 11.1 / 30.8 / 111.6 against 10.8 / 29.4 / 106.1 (one-dot sweep: 9.8 / 25.8 /
+    // 91.8 against 9.4 / 24.1 / 86.2).  The SASS of the two
     // Finito builds has the same loads, barriers and stores in the same order; like the sequential kernels (profiles/
     // seq_kernel_history_r2.md §6) the item loop is sensitive to ptxas' schedule.  Re-measure after touching this loop.
     int64_t it = 0;
